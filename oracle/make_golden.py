@@ -1,0 +1,129 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference from /root/reference.
+
+Run once in the authoring container (``python -m oracle.make_golden``); the GPU box has no
+/root/reference, so only the committed vectors travel.  Versions used: see ``meta`` in each
+file.  Inputs are stored as fp16 mantissas times a per-clip fp32 scale so the fixture stays
+small while the fp32 input fed to the reference and to the CUDA path is bit-identical
+(``load_clips`` in tests/golden_io.py re-creates it with the same fp32 multiply).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from cough_detector_b200 import synth  # noqa: E402  (pure-python helper, no CUDA)
+
+REF = "/root/reference"
+GOLD = os.path.join(ROOT, "tests", "golden")
+FLAGS = dict(use_pcen=False, use_pre_emphasis=False, use_delta_delta=False, use_spectral_contrast=False)
+
+
+def quantize_clip(x: torch.Tensor):
+    """x -> (fp16 mantissa array, fp32 scale) with x_q = float32(m) * scale exactly reproducible."""
+    peak = float(x.abs().max()) if x.numel() else 0.0
+    scale = np.float32(peak if peak > 0 else 1.0)
+    m = (x.numpy().astype(np.float32) / scale).astype(np.float16)
+    return m, scale
+
+
+def dequantize_clip(m: np.ndarray, scale) -> torch.Tensor:
+    return torch.from_numpy(m.astype(np.float32) * np.float32(scale))
+
+
+def main():
+    sys.path.insert(0, REF)
+    import torchaudio
+    from src.preprocessing import AudioPreprocessor, RealtimePreprocessor  # the reference
+    from src.model import create_model, count_parameters
+    from src.inference import CoughDetectorInference
+
+    torch.set_num_threads(1)
+    meta = np.array([torch.__version__, torchaudio.__version__])
+    os.makedirs(GOLD, exist_ok=True)
+
+    # ---- features: reference process() (normalize -> pad_or_trim -> extract_features) ----
+    pp = AudioPreprocessor(**FLAGS)
+    assert pp.get_num_features() == 90 and pp.get_expected_time_frames() == 101
+    raw = synth.synth_clips(20, seed=0) + synth.edge_clips()
+    mant, scales, feats = [], [], []
+    for x in raw:
+        m, s = quantize_clip(x)
+        xq = dequantize_clip(m, s)
+        mant.append(m)
+        scales.append(s)
+        feats.append(pp.process(xq.reshape(1, -1), 16000)[0].numpy())
+    feats = np.stack(feats).astype(np.float32)
+    lens = np.array([m.size for m in mant], dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLD, "features.npz"), mant=np.concatenate(mant), lens=lens,
+                        scales=np.array(scales, dtype=np.float32), features=feats, meta=meta,
+                        hann=pp.mel_spectrogram.spectrogram.window.numpy(),
+                        fb=pp.mel_spectrogram.mel_scale.fb.numpy(),
+                        dct=pp.mfcc_transform.dct_mat.numpy())
+
+    # ---- model: default init (seed 0) and BN-randomised weights, logits on golden features ----
+    torch.manual_seed(0)
+    model = create_model("residual", n_mels=90, num_classes=2, in_channels=1).eval()
+    assert count_parameters(model) == 290370
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    sd1 = synth.randomized_state_dict(model, seed=1)
+    x = torch.from_numpy(feats).unsqueeze(1)
+    out = {}
+    with torch.no_grad():
+        for name, sd in (("default", sd0), ("random", sd1)):
+            model.load_state_dict(sd)
+            logits = model(x)
+            preds, probs = model.predict(x)
+            out[f"logits_{name}"] = logits.numpy()
+            out[f"probs_{name}"] = probs.numpy()
+            out[f"preds_{name}"] = preds.numpy()
+    w = {f"sd0/{k}": v.numpy() for k, v in sd0.items()}
+    w.update({f"sd1/{k}": v.numpy() for k, v in sd1.items()
+              if not torch.equal(v, sd0[k])})
+    np.savez_compressed(os.path.join(GOLD, "model.npz"), meta=meta, **w, **out)
+
+    # ---- streaming: RealtimePreprocessor.add_audio, hop 0.25 s (reference default) and 0.1 s ----
+    g = torch.Generator().manual_seed(7)
+    stream = torch.cat([synth._burst(g, 16000), synth._sines(g, 12000), 0.02 * torch.randn(8000, generator=g)])
+    m, s = quantize_clip(stream)
+    stream = dequantize_clip(m, s)
+    st = {"mant": m, "scale": np.float32(s), "meta": meta}
+    for hop in (0.25, 0.1):
+        rp = RealtimePreprocessor(window_duration=1.0, hop_duration=hop, **FLAGS)
+        got = []
+        for c in range(0, stream.numel(), 1600):          # 100 ms chunks like the mic loop
+            got += rp.add_audio(stream[c:c + 1600])
+        st[f"feat_hop{int(hop * 1000)}"] = torch.stack(got).numpy()
+    np.savez_compressed(os.path.join(GOLD, "stream.npz"), **st)
+
+    # ---- inference engine: checkpoint round trip + process_audio_chunk (debounce 0 -> deterministic) ----
+    cfg = dict(model_type="residual", sample_rate=16000, n_mels=64, n_fft=512, hop_length=160, win_length=400,
+               f_min=100.0, f_max=4000.0, segment_duration=1.0, n_mfcc=13, use_mfcc=True, n_contrast_bands=6,
+               pre_emphasis_coef=0.97, **FLAGS)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "best_model.pt")
+        torch.save({"epoch": 0, "model_state_dict": sd1, "optimizer_state_dict": {}, "metrics": {},
+                    "config": cfg}, path)                  # src/train.py:183-199 format
+        eng = CoughDetectorInference(path, device="cpu", confidence_threshold=0.5, smoothing_window=3,
+                                     debounce_seconds=0.0, verbose=False)
+        fired, confs = [], []
+        for c in range(0, stream.numel(), 4000):           # 250 ms chunks: one window per call
+            r = eng.process_audio_chunk(stream[c:c + 4000].numpy())
+            fired.append(r is not None)
+            confs.append(-1.0 if r is None else float(r[1]))
+        probs = []
+        for f in st["feat_hop250"]:
+            probs.append(eng.predict(torch.from_numpy(f))[1])
+    np.savez_compressed(os.path.join(GOLD, "engine.npz"), fired=np.array(fired), confs=np.array(confs, dtype=np.float64),
+                        probs=np.array(probs, dtype=np.float64), meta=meta)
+    for f in sorted(os.listdir(GOLD)):
+        print(f, os.path.getsize(os.path.join(GOLD, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,37 @@
+"""Loaders for the committed golden vectors (made by oracle/make_golden.py from the reference)."""
+import os
+
+import numpy as np
+import torch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _deq(m, scale):
+    return torch.from_numpy(m.astype(np.float32) * np.float32(scale))
+
+
+def load_features():
+    z = np.load(os.path.join(GOLD, "features.npz"))
+    clips, o = [], 0
+    for n, s in zip(z["lens"], z["scales"]):
+        clips.append(_deq(z["mant"][o:o + n], s))
+        o += int(n)
+    return clips, torch.from_numpy(z["features"]), z
+
+
+def load_model():
+    z = np.load(os.path.join(GOLD, "model.npz"))
+    sd0 = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd0/")}
+    sd1 = dict(sd0)
+    sd1.update({k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd1/")})
+    return sd0, sd1, z
+
+
+def load_stream():
+    z = np.load(os.path.join(GOLD, "stream.npz"))
+    return _deq(z["mant"], z["scale"]), z
+
+
+def load_engine():
+    return np.load(os.path.join(GOLD, "engine.npz"))
