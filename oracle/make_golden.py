@@ -73,6 +73,9 @@ def main():
     sd0 = {k: v.clone() for k, v in model.state_dict().items()}
     sd1 = synth.randomized_state_dict(model, seed=1)
     x = torch.from_numpy(feats).unsqueeze(1)
+    with torch.no_grad():
+        model.load_state_dict(sd1)
+        sd1 = synth.spread_fc(sd1, model(x))
     out = {}
     with torch.no_grad():
         for name, sd in (("default", sd0), ("random", sd1)):
