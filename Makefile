@@ -1,0 +1,25 @@
+# Builds libcough_b200.so (sm_100a only) and nothing else.  `python -c "import __graft_entry__ as g; g.build()"`
+# runs this.  nvcc cross-compiles without a GPU.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
+SRC_DIR   := cough_detector_b200/csrc
+OUT_DIR   := cough_detector_b200/lib
+SRCS      := $(SRC_DIR)/api.cu $(SRC_DIR)/feat_kernel.cu $(SRC_DIR)/cnn_fp32.cu $(SRC_DIR)/cnn_tc.cu
+OBJS      := $(patsubst $(SRC_DIR)/%.cu,build/%.o,$(SRCS))
+LIB       := $(OUT_DIR)/libcough_b200.so
+
+all: $(LIB)
+
+build/%.o: $(SRC_DIR)/%.cu $(SRC_DIR)/cd_common.cuh $(SRC_DIR)/cd_tables.h include/cough_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
+
+$(LIB): $(OBJS)
+	@mkdir -p $(OUT_DIR)
+	$(NVCC) -shared $(ARCH) -o $@ $(OBJS)
+
+clean:
+	rm -rf build $(LIB)
+
+.PHONY: all clean

@@ -1,2 +1,13 @@
-"""B200-native feature + CoughDetectorResidual hot path of cough_detector."""
+"""B200-native feature + CoughDetectorResidual hot path of cough_detector.
+
+Importing the package does not need a GPU or the shared library; the first call that computes
+anything loads ``lib/libcough_b200.so`` and fails loudly if it (or a B200) is missing.
+"""
 __version__ = "0.1.0"
+
+from .preprocessing import AudioPreprocessor, RealtimePreprocessor, create_preprocessor  # noqa: F401
+from .model import CoughDetectorResidual, ResidualBlock, create_model, count_parameters  # noqa: F401
+from .inference import CoughDetectorInference, smooth_and_debounce  # noqa: F401
+
+__all__ = ["AudioPreprocessor", "RealtimePreprocessor", "create_preprocessor", "CoughDetectorResidual",
+           "ResidualBlock", "create_model", "count_parameters", "CoughDetectorInference", "smooth_and_debounce"]

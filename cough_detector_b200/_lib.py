@@ -1,0 +1,276 @@
+"""ctypes binding of libcough_b200.so (C ABI in include/cough_b200.h).
+
+The library is the product; this file only marshals pointers.  There is NO fallback: if the
+shared object is missing or no sm_100 device is usable, the first call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Dict, Optional
+
+import torch
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libcough_b200.so")
+
+SEGMENT = 16000
+N_FEATURES = 90
+N_FRAMES = 101
+PRECISION_FP32 = 0
+PRECISION_BF16 = 1
+
+_f32p = C.POINTER(C.c_float)
+
+
+class _ConvBn(C.Structure):
+    _fields_ = [(n, _f32p) for n in ("weight", "bias", "bn_weight", "bn_bias", "bn_running_mean", "bn_running_var")]
+
+
+class _ResidualWeights(C.Structure):
+    _fields_ = [(n, _ConvBn) for n in ("stem", "b0_conv1", "b0_conv2", "b0_skip", "b1_conv1", "b1_conv2", "b1_skip")] \
+        + [("fc_weight", _f32p), ("fc_bias", _f32p)]
+
+
+# every symbol include/cough_b200.h declares: name -> (restype, argtypes)
+_VP, _I64, _I = C.c_void_p, C.c_int64, C.c_int
+SYMBOLS = {
+    "cd_create": (_I, [_I, C.POINTER(_VP)]),
+    "cd_destroy": (_I, [_VP]),
+    "cd_last_error": (C.c_char_p, [_VP]),
+    "cd_version": (C.c_char_p, []),
+    "cd_get_tables": (_I, [_VP, _VP, _VP]),
+    "cd_feat_forward": (_I, [_VP, _VP, _I64, _I64, _VP, _I, _VP]),
+    "cd_feat_forward_var": (_I, [_VP, _VP, _VP, _VP, _I64, _VP, _VP]),
+    "cd_feat_forward_stream": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
+    "cd_stream_windows": (_I64, [_I64, _I64]),
+    "cd_cnn_load": (_I, [_VP, C.POINTER(_ResidualWeights)]),
+    "cd_cnn_forward": (_I, [_VP, _VP, _I64, _VP, _I, _VP]),
+    "cd_predict": (_I, [_VP, _VP, _I64, C.c_float, _VP, _VP, _VP, _VP]),
+    "cd_e2e_forward": (_I, [_VP, _VP, _I64, _I64, _VP, _VP, _I, _VP]),
+    "cd_e2e_forward_stream": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _I, _VP]),
+    "cd_e2e_forward_host": (_I, [_VP, _VP, _I64, _VP, _I]),
+    "cd_launch_count": (_I64, [_VP]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree library and set the prototypes.  No GPU needed for this step."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()). "
+                    "cough_detector_b200 has no CPU or PyTorch fallback.")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SYMBOLS.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+class CoughB200Error(RuntimeError):
+    pass
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Handle:
+    """One cd_handle on one CUDA device."""
+
+    def __init__(self, device: int):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise CoughB200Error("no CUDA device: cough_detector_b200 runs on B200 (sm_100a) only, there is no CPU path")
+        self.device = int(device)
+        h = _VP()
+        rc = self.lib.cd_create(self.device, C.byref(h))
+        if rc != 0:
+            raise CoughB200Error(f"cd_create({device}) failed ({rc}): {self.lib.cd_last_error(None).decode()}")
+        self._h = h
+        self._weights_key = None
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.cd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise CoughB200Error(f"{what} failed ({rc}): {self.lib.cd_last_error(self._h).decode()}")
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _dev_f32(self, t: torch.Tensor, what: str) -> torch.Tensor:
+        if not (t.is_cuda and t.device.index == self.device):
+            raise CoughB200Error(f"{what} must live on cuda:{self.device}")
+        return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.cd_launch_count(self._h))
+
+    # ---- features ---------------------------------------------------------------------------
+    def feat_forward(self, audio: torch.Tensor, normalize: bool = True) -> torch.Tensor:
+        """(B, 16000) cuda fp32 -> (B, 1, 90, 101)."""
+        audio = self._dev_f32(audio, "audio")
+        if audio.dim() != 2 or audio.shape[1] != SEGMENT:
+            raise CoughB200Error(f"audio must be (B, {SEGMENT}), got {tuple(audio.shape)}")
+        B = audio.shape[0]
+        out = torch.empty(B, 1, N_FEATURES, N_FRAMES, device=audio.device, dtype=torch.float32)
+        self._check(self.lib.cd_feat_forward(self._h, _ptr(audio), SEGMENT, B, _ptr(out), 1 if normalize else 0, self._stream()), "cd_feat_forward")
+        return out
+
+    def feat_forward_var(self, flat: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:
+        flat = self._dev_f32(flat, "audio")
+        offsets = offsets.to(device=flat.device, dtype=torch.int64).contiguous()
+        lengths = lengths.to(device=flat.device, dtype=torch.int32).contiguous()
+        B = offsets.numel()
+        out = torch.empty(B, 1, N_FEATURES, N_FRAMES, device=flat.device, dtype=torch.float32)
+        self._check(self.lib.cd_feat_forward_var(self._h, _ptr(flat), _ptr(offsets), _ptr(lengths), B, _ptr(out),
+                                                 self._stream()), "cd_feat_forward_var")
+        return out
+
+    def stream_windows(self, n: int, hop: int) -> int:
+        return int(self.lib.cd_stream_windows(n, hop))
+
+    def feat_forward_stream(self, audio: torch.Tensor, hop: int) -> torch.Tensor:
+        audio = self._dev_f32(audio.reshape(-1), "audio")
+        n = audio.numel()
+        nw = self.stream_windows(n, hop)
+        out = torch.empty(nw, 1, N_FEATURES, N_FRAMES, device=audio.device, dtype=torch.float32)
+        self._check(self.lib.cd_feat_forward_stream(self._h, _ptr(audio), n, hop, nw, _ptr(out), self._stream()),
+                    "cd_feat_forward_stream")
+        return out
+
+    # ---- model ------------------------------------------------------------------------------
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], key=None):
+        """Upload a reference-format CoughDetectorResidual state_dict (BN folded by the library)."""
+        keep = {}
+
+        def f(name):
+            t = sd[name].detach().to("cpu", torch.float32).contiguous()
+            keep[name] = t
+            return C.cast(t.data_ptr(), _f32p)
+
+        def cb(conv, bn):
+            return _ConvBn(f(conv + ".weight"), f(conv + ".bias"), f(bn + ".weight"), f(bn + ".bias"),
+                           f(bn + ".running_mean"), f(bn + ".running_var"))
+
+        w = _ResidualWeights(
+            cb("conv1.0", "conv1.1"),
+            cb("res_blocks.0.conv1", "res_blocks.0.bn1"), cb("res_blocks.0.conv2", "res_blocks.0.bn2"),
+            cb("res_blocks.0.skip.0", "res_blocks.0.skip.1"),
+            cb("res_blocks.1.conv1", "res_blocks.1.bn1"), cb("res_blocks.1.conv2", "res_blocks.1.bn2"),
+            cb("res_blocks.1.skip.0", "res_blocks.1.skip.1"),
+            f("fc.2.weight"), f("fc.2.bias"))
+        expect = {"conv1.0.weight": (32, 1, 7, 7), "res_blocks.0.conv1.weight": (64, 32, 3, 3),
+                  "res_blocks.0.conv2.weight": (64, 64, 3, 3), "res_blocks.0.skip.0.weight": (64, 32, 1, 1),
+                  "res_blocks.1.conv1.weight": (128, 64, 3, 3), "res_blocks.1.conv2.weight": (128, 128, 3, 3),
+                  "res_blocks.1.skip.0.weight": (128, 64, 1, 1), "fc.2.weight": (2, 128)}
+        for k, shp in expect.items():
+            if tuple(keep[k].shape) != shp:
+                raise CoughB200Error(f"{k}: expected shape {shp}, got {tuple(keep[k].shape)}")
+        self._check(self.lib.cd_cnn_load(self._h, C.byref(w)), "cd_cnn_load")
+        self._weights_key = key
+
+    def cnn_forward(self, feat: torch.Tensor, precision: int = PRECISION_BF16) -> torch.Tensor:
+        feat = self._dev_f32(feat, "features")
+        if feat.dim() == 3:
+            feat = feat.unsqueeze(0)
+        if tuple(feat.shape[1:]) != (1, N_FEATURES, N_FRAMES):
+            raise CoughB200Error(f"features must be (B, 1, {N_FEATURES}, {N_FRAMES}), got {tuple(feat.shape)}")
+        B = feat.shape[0]
+        logits = torch.empty(B, 2, device=feat.device, dtype=torch.float32)
+        self._check(self.lib.cd_cnn_forward(self._h, _ptr(feat), B, _ptr(logits), precision, self._stream()), "cd_cnn_forward")
+        return logits
+
+    def predict(self, logits: torch.Tensor, threshold: float = 0.5):
+        logits = self._dev_f32(logits, "logits")
+        B = logits.shape[0]
+        probs = torch.empty(B, 2, device=logits.device, dtype=torch.float32)
+        preds = torch.empty(B, device=logits.device, dtype=torch.int64)
+        dec = torch.empty(B, device=logits.device, dtype=torch.uint8)
+        self._check(self.lib.cd_predict(self._h, _ptr(logits), B, threshold, _ptr(probs), _ptr(preds), _ptr(dec),
+                                        self._stream()), "cd_predict")
+        return preds, probs, dec.bool()
+
+    # ---- end to end -------------------------------------------------------------------------
+    def e2e_forward(self, audio: torch.Tensor, precision: int = PRECISION_BF16, return_features: bool = False):
+        audio = self._dev_f32(audio, "audio")
+        if audio.dim() != 2 or audio.shape[1] != SEGMENT:
+            raise CoughB200Error(f"audio must be (B, {SEGMENT}), got {tuple(audio.shape)}")
+        B = audio.shape[0]
+        logits = torch.empty(B, 2, device=audio.device, dtype=torch.float32)
+        feat = torch.empty(B, 1, N_FEATURES, N_FRAMES, device=audio.device, dtype=torch.float32) if return_features else None
+        self._check(self.lib.cd_e2e_forward(self._h, _ptr(audio), SEGMENT, B, _ptr(logits), _ptr(feat), precision,
+                                            self._stream()), "cd_e2e_forward")
+        return (logits, feat) if return_features else logits
+
+    def e2e_forward_stream(self, audio: torch.Tensor, hop: int, precision: int = PRECISION_BF16) -> torch.Tensor:
+        audio = self._dev_f32(audio.reshape(-1), "audio")
+        n = audio.numel()
+        nw = self.stream_windows(n, hop)
+        logits = torch.empty(nw, 2, device=audio.device, dtype=torch.float32)
+        self._check(self.lib.cd_e2e_forward_stream(self._h, _ptr(audio), n, hop, nw, _ptr(logits), precision,
+                                                   self._stream()), "cd_e2e_forward_stream")
+        return logits
+
+    def e2e_forward_host(self, audio: torch.Tensor, precision: int = PRECISION_BF16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Host (B, 16000) fp32 tensor (ideally pinned) -> host (B, 2) logits; copies are inside the call."""
+        if audio.is_cuda or audio.dtype != torch.float32 or audio.dim() != 2 or audio.shape[1] != SEGMENT:
+            raise CoughB200Error("e2e_forward_host wants a CPU float32 (B, 16000) tensor")
+        audio = audio.contiguous()
+        B = audio.shape[0]
+        if out is None:
+            out = torch.empty(B, 2, dtype=torch.float32).pin_memory()
+        self._check(self.lib.cd_e2e_forward_host(self._h, _ptr(audio), B, _ptr(out), precision), "cd_e2e_forward_host")
+        return out
+
+
+_handles: Dict[int, Handle] = {}
+
+
+def get_handle(device=None) -> Handle:
+    """Process-wide handle for a CUDA device (default: torch's current device)."""
+    if device is None:
+        if not torch.cuda.is_available():
+            load_library()
+            raise CoughB200Error("no CUDA device: cough_detector_b200 runs on B200 (sm_100a) only, there is no CPU path")
+        device = torch.cuda.current_device()
+    if isinstance(device, torch.device):
+        device = device.index if device.index is not None else torch.cuda.current_device()
+    device = int(device)
+    with _lock:
+        h = _handles.get(device)
+    if h is None:
+        h = Handle(device)
+        with _lock:
+            _handles[device] = h
+    return h
+
+
+def get_tables():
+    """(hann[400], fb[257,64], dct[64,13]) as the library holds them; needs no GPU."""
+    lib = load_library()
+    hann = torch.empty(400)
+    fb = torch.empty(257, 64)
+    dct = torch.empty(64, 13)
+    lib.cd_get_tables(hann.data_ptr(), fb.data_ptr(), dct.data_ptr())
+    return hann, fb, dct

@@ -1,0 +1,101 @@
+// Shared declarations of libcough_b200 (internal; the public surface is include/cough_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+
+#include "../../include/cough_b200.h"
+
+namespace cd {
+
+constexpr int kSeg      = CD_SEGMENT;    // 16000 samples per clip
+constexpr int kFrames   = CD_N_FRAMES;   // 101
+constexpr int kPairs    = 51;            // frame pairs packed into one complex FFT
+constexpr int kMels     = 64;
+constexpr int kMfcc     = 13;
+constexpr int kFeat     = CD_N_FEATURES; // 90
+constexpr int kFeatElem = CD_FEAT_ELEMS; // 9090
+constexpr int kNfft     = 512;
+constexpr int kWin      = 400;
+constexpr int kHop      = 160;
+
+// mel contraction as executed by a lane: slots 0..2 = band `lane` (<= 3 taps for bands 0..31),
+// slots 3..10 = band `lane+32` (<= 8 taps).  idx is the bin index minus 4 (0..123).
+constexpr int kMelSlotsLo = 3;
+constexpr int kMelSlotsHi = 8;
+constexpr int kMelSlots   = kMelSlotsLo + kMelSlotsHi;
+
+struct FeatTables {                 // lives in device global memory, copied to smem per CTA
+    float2 tw1[7][64];              // W512^(m*r), r = 1..7, m = 0..63   (stage-1 twiddles)
+    float2 tw2[7][8];               // W64^(c*u),  u = 1..7, c = 0..7    (stage-2 twiddles)
+    float  win[kWin];               // 0.5 * hann (the 0.5 makes |Z +- conj Z'|^2 the power directly)
+    float2 melt[kMelSlots][32];     // {weight, __int_as_float(bin - 4)}
+};
+
+// Folded network, fp32 (CUDA-core path).  Layouts chosen for the direct-conv kernels:
+// weights [k*k*cin][cout] (cout fastest) so a warp reads them as broadcast float4s.
+struct CnnWeightsF32 {
+    float* stem_w;  float* stem_b;      // [49][32], [32]
+    float* b0c1_w;  float* b0c1_b;      // [9*32][64]
+    float* b0sk_w;  float* b0sk_b;      // [32][64]
+    float* b0c2_w;  float* b0c2_b;      // [9*64][64]
+    float* b1c1_w;  float* b1c1_b;      // [9*64][128]
+    float* b1sk_w;  float* b1sk_b;      // [64][128]
+    float* b1c2_w;  float* b1c2_b;      // [9*128][128]
+    float* fc_w;    float* fc_b;        // [2][128], [2]
+};
+
+}  // namespace cd
+
+struct cd_handle {
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    int64_t launches = 0;
+
+    cd::FeatTables* d_tables = nullptr;
+
+    bool weights_loaded = false;
+    float* d_wblob = nullptr;            // one allocation holding every folded fp32 tensor
+    cd::CnnWeightsF32 w32{};
+    __nv_bfloat16* d_wblob_bf16 = nullptr;
+
+    // workspace (grown on demand, never shrunk)
+    float* d_ws = nullptr;
+    size_t ws_bytes = 0;
+
+    // host-pipeline state for cd_e2e_forward_host
+    cudaStream_t pipe_streams[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_events[3] = {nullptr, nullptr, nullptr};
+    float* pinned_in[3] = {nullptr, nullptr, nullptr};
+    float* dev_in[3] = {nullptr, nullptr, nullptr};
+    float* dev_logits = nullptr;
+    float* pinned_logits = nullptr;
+    int64_t pipe_chunk = 0;
+    int64_t pipe_logits_cap = 0;
+};
+
+namespace cd {
+
+int set_err(cd_handle* h, int code, const char* what, cudaError_t e = cudaSuccess);
+int ensure_ws(cd_handle* h, size_t bytes);
+
+#define CD_CUDA(h, call)                                                     \
+    do {                                                                     \
+        cudaError_t e__ = (call);                                            \
+        if (e__ != cudaSuccess) return cd::set_err((h), CD_E_CUDA, #call, e__); \
+    } while (0)
+
+// kernels' host launchers (each returns a CD_* code and bumps h->launches)
+int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets, const int32_t* d_lengths,
+                    int64_t stride_or_hop, int mode, int64_t B, float* d_feat, cudaStream_t s);
+int launch_cnn_fp32(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, cudaStream_t s);
+size_t cnn_fp32_ws_bytes(int64_t B);
+
+enum FeatMode { kModeFixed = 0, kModeVar = 1, kModeStream = 2, kModeMask = 3, kModeNoNormalize = 4 };
+
+}  // namespace cd

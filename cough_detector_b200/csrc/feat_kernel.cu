@@ -1,0 +1,552 @@
+// Fused feature kernel: clip -> (90, 101) features, one persistent CTA per SM.
+//
+// Replaces, per clip, AudioPreprocessor.normalize (src/preprocessing.py:199-212), pad_or_trim
+// (:358-385) and extract_features (:432-489): T.MelSpectrogram (reflect pad, 400-sample periodic
+// Hann centred in a 512-point frame, rFFT, power, 64-band HTK mel), AmplitudeToDB(top_db=80),
+// (dB+80)/80 clamp, T.MFCC's DCT-II of the floored dB, global mean / unbiased-std normalisation,
+// and the replicate-padded central-difference deltas.  The reference computes the mel
+// spectrogram twice (extract_mel_spectrogram and again inside T.MFCC); here it is computed once.
+//
+// Data flow per clip (all on chip between the 64 000 B read and the 36 360 B write):
+//   global --cp.async.bulk (TMA 1-D, double buffered)--> smem clip[16000]
+//   block max|x| -> in-place scale by 1/max
+//   16 warps x frame PAIRS: z = w*(x_2p + i x_2p+1), complex 512-point FFT as 8x8x8 radix-8
+//       (16 points per lane in registers, two smem exchanges), Z[k], Z[512-k] -> the two power
+//       spectra for bins 4..127 only, banded mel (244 taps), 10 log10 -> smem dB tile [64][101]
+//   block max(dB) -> floor; mel01 rows written; DCT-13 from the floored tile; block mean / std;
+//   normalised MFCC + deltas written.
+// The power spectrum is invariant to a circular shift of the frame, so the 400 windowed samples
+// sit at n = 0..399 of the 512-point frame instead of torch.stft's 56..455.
+#include "cd_common.cuh"
+#include "cd_tables.h"
+
+namespace cd {
+
+constexpr int kFeatWarps   = 16;
+constexpr int kFeatThreads = kFeatWarps * 32;
+constexpr int kXbElems     = 288;             // float2 per warp: 4 rows x 72 (64 + 8 pad)
+constexpr int kXbRow       = 72;
+
+__constant__ float c_dct[kMfcc * kMels];      // [13][64], ortho DCT-II rows
+
+struct FeatSmem {
+    float  clip[2][kSeg];                     // 128 000 B, double buffered
+    float2 xb[kFeatWarps][kXbElems];          //  36 864 B, per-warp FFT exchange; MFCC scratch in the tail
+    float  db[kMels * kFrames];               //  25 856 B, dB tile [band][frame]
+    float2 tw1[7][64];
+    float2 tw2[7][8];
+    float  win[kWin];
+    float2 melt[kMelSlots][32];
+    float  red[64];
+    unsigned long long bar[2];
+};
+
+// ----------------------------------------------------------------------------------------------
+// small PTX wrappers
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine), completion signalled on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+
+// 8-point forward DFT, natural order in and out (decimation in frequency, 3 radix-2 levels).
+// PRUNE: only outputs 0, 1, 6, 7 are produced (the last stage feeds bins 4..127 and 385..508 only).
+template <bool PRUNE>
+__device__ __forceinline__ void fft8(float2 (&x)[8]) {
+    const float h = 0.70710678118654752440f;
+    float2 t0 = cadd(x[0], x[4]), t4 = csub(x[0], x[4]);
+    float2 t1 = cadd(x[1], x[5]), t5 = csub(x[1], x[5]);
+    float2 t2 = cadd(x[2], x[6]), t6 = csub(x[2], x[6]);
+    float2 t3 = cadd(x[3], x[7]), t7 = csub(x[3], x[7]);
+    t5 = make_float2((t5.x + t5.y) * h, (t5.y - t5.x) * h);       // * W8^1
+    t6 = mul_mi(t6);                                               // * W8^2
+    t7 = make_float2((t7.y - t7.x) * h, -(t7.x + t7.y) * h);      // * W8^3
+    float2 u0 = cadd(t0, t2), u2 = csub(t0, t2);
+    float2 u1 = cadd(t1, t3), u3 = mul_mi(csub(t1, t3));
+    float2 u4 = cadd(t4, t6), u6 = csub(t4, t6);
+    float2 u5 = cadd(t5, t7), u7 = mul_mi(csub(t5, t7));
+    x[0] = cadd(u0, u1);
+    x[1] = cadd(u4, u5);
+    x[6] = csub(u2, u3);
+    x[7] = csub(u6, u7);
+    if (!PRUNE) {
+        x[4] = csub(u0, u1);
+        x[2] = cadd(u2, u3);
+        x[5] = csub(u4, u5);
+        x[3] = cadd(u6, u7);
+    }
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// Block-wide reduction over kFeatWarps warps; every thread gets the result.  `red` needs >= 16
+// floats and is safe to reuse after the call returns (two barriers inside).
+template <bool IS_MAX>
+__device__ __forceinline__ float block_reduce(float v, float* red) {
+    v = IS_MAX ? warp_max(v) : warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float r = red[lane & (kFeatWarps - 1)];
+#pragma unroll
+    for (int o = kFeatWarps / 2; o; o >>= 1) {
+        float other = __shfl_xor_sync(0xffffffffu, r, o);
+        r = IS_MAX ? fmaxf(r, other) : r + other;
+    }
+    __syncthreads();
+    return r;
+}
+
+// One windowed sample pair for FFT point n of the frame pair starting at sample `base0`.
+template <bool EDGE>
+__device__ __forceinline__ float2 load_point(const float* __restrict__ clip, const float* __restrict__ win,
+                                             int n, int base0, bool second) {
+    const float w = win[n];
+    int i0 = base0 + n;
+    int i1 = i0 + kHop;
+    if (EDGE) {   // reflect padding of torch.stft(center=True, pad_mode="reflect")
+        i0 = i0 < 0 ? -i0 : i0;
+        i0 = i0 >= kSeg ? 2 * (kSeg - 1) - i0 : i0;
+        i1 = i1 < 0 ? -i1 : i1;
+        i1 = i1 >= kSeg ? 2 * (kSeg - 1) - i1 : i1;
+        return make_float2(w * clip[i0], second ? w * clip[i1] : 0.f);
+    }
+    return make_float2(w * clip[i0], w * clip[i1]);
+}
+
+// The per-warp work item: frames 2p and 2p+1 -> 2 x 64 dB values in the tile.  Returns the lane's
+// running max of the dB values it produced.
+template <bool EDGE>
+__device__ __forceinline__ float frame_pair(FeatSmem& S, const float* __restrict__ clip, float2* __restrict__ xb,
+                                            int p, int lane) {
+    const int c = lane & 7, j = lane >> 3;
+    const int base0 = 2 * kHop * p - kWin / 2;      // sample index of window tap 0 of frame 2p
+    const bool second = (2 * p + 1) < kFrames;
+
+    // ---- stage 1: radix-8 over a (n = 64a + m), m = lane and lane + 32 ------------------------
+    float2 A[8], B[8];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        A[a] = load_point<EDGE>(clip, S.win, 64 * a + lane, base0, second);
+        B[a] = load_point<EDGE>(clip, S.win, 64 * a + lane + 32, base0, second);
+    }
+    A[6] = lane < 16 ? load_point<EDGE>(clip, S.win, 384 + lane, base0, second) : make_float2(0.f, 0.f);
+    A[7] = make_float2(0.f, 0.f);                   // n >= 400: zero padding of the 512-point frame
+    B[6] = make_float2(0.f, 0.f);
+    B[7] = make_float2(0.f, 0.f);
+    fft8<false>(A);
+    fft8<false>(B);
+#pragma unroll
+    for (int r = 1; r < 8; ++r) {
+        A[r] = cmul(A[r], S.tw1[r - 1][lane]);
+        B[r] = cmul(B[r], S.tw1[r - 1][lane + 32]);
+    }
+
+    // ---- exchange 1 (two halves of r) + stage 2: radix-8 over b (m = 8b + c) -------------------
+    float2 C[8], D[8];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        xb[r * kXbRow + lane] = A[r];
+        xb[r * kXbRow + lane + 32] = B[r];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int b = 0; b < 8; ++b) C[b] = xb[j * kXbRow + 8 * b + c];      // r = j
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        xb[r * kXbRow + lane] = A[r + 4];
+        xb[r * kXbRow + lane + 32] = B[r + 4];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int b = 0; b < 8; ++b) D[b] = xb[j * kXbRow + 8 * b + c];      // r = j + 4
+    __syncwarp();
+    fft8<false>(C);
+    fft8<false>(D);
+#pragma unroll
+    for (int u = 1; u < 8; ++u) {
+        const float2 t = S.tw2[u - 1][c];
+        C[u] = cmul(C[u], t);
+        D[u] = cmul(D[u], t);
+    }
+
+    // ---- exchange 2 + stage 3: radix-8 over c', pruned to s in {0,1,6,7} -----------------------
+#pragma unroll
+    for (int u = 0; u < 8; ++u) xb[j * kXbRow + 9 * u + c] = C[u];
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) A[q] = xb[j * kXbRow + 9 * c + q];
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) xb[j * kXbRow + 9 * u + c] = D[u];
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) B[q] = xb[j * kXbRow + 9 * c + q];
+    __syncwarp();
+    fft8<true>(A);      // A[s] = Z[64 s + 8 c + j]
+    fft8<true>(B);      // B[s] = Z[64 s + 8 c + j + 4]
+
+    // ---- Z[k], k in [0,128) u [384,512) -> xb[kk + kk/8], kk = k (k < 128) or k - 256 ----------
+    {
+        const int o = 9 * c + j;
+        xb[o] = A[0];            xb[o + 4] = B[0];
+        xb[72 + o] = A[1];       xb[72 + o + 4] = B[1];
+        xb[144 + o] = A[6];      xb[144 + o + 4] = B[6];
+        xb[216 + o] = A[7];      xb[216 + o + 4] = B[7];
+    }
+    __syncwarp();
+
+    // ---- unpack the two real spectra and take |.|^2 for bins 4..127 ----------------------------
+    // z = x1 + i x2  =>  Z[k] + conj Z[512-k] = 2 X1[k],  Z[k] - conj Z[512-k] = 2i X2[k]
+    float2 P[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = 4 + lane + 32 * i;
+        const int kk = 256 - k;
+        const float2 a = xb[(k + (k >> 3)) & 511];
+        const float2 b = xb[kk + (kk >> 3)];
+        const float sr = a.x + b.x, si = a.y - b.y, dr = a.x - b.x, di = a.y + b.y;
+        P[i] = make_float2(sr * sr + si * si, dr * dr + di * di);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = lane + 32 * i;                 // bin - 4
+        if (k < 124) xb[k] = P[i];
+    }
+    __syncwarp();
+
+    // ---- banded mel contraction: lane owns bands `lane` and `lane + 32` for both frames --------
+    float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < kMelSlotsLo; ++s) {
+        const float2 e = S.melt[s][lane];
+        const float2 pw = xb[__float_as_int(e.y)];
+        lo.x = fmaf(e.x, pw.x, lo.x);
+        lo.y = fmaf(e.x, pw.y, lo.y);
+    }
+#pragma unroll
+    for (int s = kMelSlotsLo; s < kMelSlots; ++s) {
+        const float2 e = S.melt[s][lane];
+        const float2 pw = xb[__float_as_int(e.y)];
+        hi.x = fmaf(e.x, pw.x, hi.x);
+        hi.y = fmaf(e.x, pw.y, hi.y);
+    }
+    __syncwarp();                                    // xb is rewritten by the next pair
+
+    // ---- AmplitudeToDB: 10 log10(max(x, 1e-10)) (torchaudio functional.py:390) ------------------
+    const float kDb = 3.01029995663981195f;          // 10 * log10(2)
+    const float d0 = kDb * __log2f(fmaxf(lo.x, 1e-10f));
+    const float d2 = kDb * __log2f(fmaxf(hi.x, 1e-10f));
+    float* row_lo = S.db + lane * kFrames + 2 * p;
+    float* row_hi = S.db + (lane + 32) * kFrames + 2 * p;
+    row_lo[0] = d0;
+    row_hi[0] = d2;
+    float m = fmaxf(d0, d2);
+    if (second) {
+        const float d1 = kDb * __log2f(fmaxf(lo.y, 1e-10f));
+        const float d3 = kDb * __log2f(fmaxf(hi.y, 1e-10f));
+        row_lo[1] = d1;
+        row_hi[1] = d3;
+        m = fmaxf(m, fmaxf(d1, d3));
+    }
+    return m;
+}
+
+// DCT-II of the floored dB tile for frame t, coefficient set CS (c = CS, CS+4, CS+8[, CS+12]).
+template <int CS>
+__device__ __forceinline__ float mfcc_set(const float* __restrict__ db, float* __restrict__ mf, int t) {
+    constexpr int NC = (CS == 0) ? 4 : 3;
+    float acc[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int m = 0; m < kMels; ++m) {
+        const float d = db[m * kFrames + t];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) acc[i] = fmaf(c_dct[(CS + 4 * i) * kMels + m], d, acc[i]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        mf[(CS + 4 * i) * kFrames + t] = acc[i];
+        s += acc[i];
+    }
+    return s;
+}
+
+struct ClipDesc {
+    const float* src;     // first sample of the clip
+    int len;              // samples available
+};
+
+__device__ __forceinline__ ClipDesc clip_desc(const float* audio, const int64_t* offs, const int32_t* lens,
+                                              int64_t stride_or_hop, int mode, int64_t b) {
+    ClipDesc d;
+    if ((mode & kModeMask) == kModeVar) {
+        d.src = audio + offs[b];
+        d.len = lens[b];
+    } else {
+        d.src = audio + b * stride_or_hop;
+        d.len = kSeg;
+    }
+    return d;
+}
+__device__ __forceinline__ bool bulk_ok(const ClipDesc& d) {
+    return d.len == kSeg && ((reinterpret_cast<uintptr_t>(d.src) & 15) == 0);
+}
+
+__global__ void __launch_bounds__(kFeatThreads, 1)
+feat_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offs, const int32_t* __restrict__ lens,
+            int64_t stride_or_hop, int mode, int64_t B, float* __restrict__ feat,
+            const FeatTables* __restrict__ tables) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FeatSmem& S = *reinterpret_cast<FeatSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- one-time per CTA: tables -> smem, barriers ------------------------------------------------
+    {
+        const float* src = reinterpret_cast<const float*>(tables);
+        float* dst = reinterpret_cast<float*>(&S.tw1[0][0]);
+        constexpr int n = sizeof(FeatTables) / 4;
+        static_assert(offsetof(FeatSmem, melt) - offsetof(FeatSmem, tw1) == offsetof(FeatTables, melt), "layout");
+        for (int i = tid; i < n; i += kFeatThreads) dst[i] = src[i];
+    }
+    if (tid == 0) {
+        mbar_init(&S.bar[0], 1);
+        mbar_init(&S.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    int64_t b = blockIdx.x;
+    if (b >= B) return;
+    if (tid == 0) {
+        ClipDesc d0 = clip_desc(audio, offs, lens, stride_or_hop, mode, b);
+        if (bulk_ok(d0)) {
+            mbar_expect_tx(&S.bar[0], kSeg * 4);
+            bulk_g2s(S.clip[0], d0.src, kSeg * 4, &S.bar[0]);
+        }
+    }
+    uint32_t phase[2] = {0u, 0u};
+
+    for (int it = 0; b < B; b += gridDim.x, ++it) {
+        const int cur = it & 1;
+        float* clip = S.clip[cur];
+        const ClipDesc d = clip_desc(audio, offs, lens, stride_or_hop, mode, b);
+
+        // ---- prefetch the next clip into the other buffer (its last reader finished before the
+        //      barrier that ended the previous iteration) ---------------------------------------------
+        const int64_t bn = b + gridDim.x;
+        if (tid == 0 && bn < B) {
+            ClipDesc dn = clip_desc(audio, offs, lens, stride_or_hop, mode, bn);
+            if (bulk_ok(dn)) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy
+                mbar_expect_tx(&S.bar[cur ^ 1], kSeg * 4);
+                bulk_g2s(S.clip[cur ^ 1], dn.src, kSeg * 4, &S.bar[cur ^ 1]);
+            }
+        }
+
+        // ---- stage the clip + peak ------------------------------------------------------------------
+        float peak = 0.f;
+        if (bulk_ok(d)) {
+            mbar_wait(&S.bar[cur], phase[cur]);
+            phase[cur] ^= 1u;
+            const float4* c4 = reinterpret_cast<const float4*>(clip);
+            for (int i = tid; i < kSeg / 4; i += kFeatThreads) {
+                const float4 v = c4[i];
+                peak = fmaxf(peak, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+            }
+        } else {
+            // AudioPreprocessor.process: normalise over the WHOLE clip, then centre-trim / zero-pad
+            const int n = d.len;
+            for (int i = tid; i < n; i += kFeatThreads) peak = fmaxf(peak, fabsf(d.src[i]));
+            const int start = n > kSeg ? (n - kSeg) / 2 : 0;          // trim offset (src/preprocessing.py:378)
+            const int padl = n < kSeg ? (kSeg - n) / 2 : 0;           // left zero pad (:383)
+            for (int i = tid; i < kSeg; i += kFeatThreads) {
+                const int sidx = i - padl;
+                clip[i] = (sidx >= 0 && sidx < n) ? d.src[start + sidx] : 0.f;
+            }
+        }
+        peak = block_reduce<true>(peak, S.red);                        // also orders the generic stores
+        if (peak > 0.f && !(mode & kModeNoNormalize)) {                // normalize(): skipped for silence (:209-212)
+            const float inv = 1.0f / peak;
+            float4* c4 = reinterpret_cast<float4*>(clip);
+            for (int i = tid; i < kSeg / 4; i += kFeatThreads) {
+                float4 v = c4[i];
+                v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+                c4[i] = v;
+            }
+        }
+        __syncthreads();
+
+        // ---- STFT -> mel -> dB, one frame pair per warp per round -----------------------------------
+        float wmax = -INFINITY;
+        for (int p = warp; p < kPairs; p += kFeatWarps) {
+            const bool edge = (p == 0) || (p >= 49);
+            wmax = fmaxf(wmax, edge ? frame_pair<true>(S, clip, S.xb[warp], p, lane)
+                                    : frame_pair<false>(S, clip, S.xb[warp], p, lane));
+        }
+        const float top = block_reduce<true>(wmax, S.red);             // barrier: dB tile complete
+        const float floor_db = top - 80.0f;                            // top_db = 80
+
+        // ---- mel block rows 0..63: max(dB, floor) -> (dB + 80) / 80 -> clamp ------------------------
+        float* out = feat + b * (int64_t)kFeatElem;
+        for (int i = tid; i < kMels * kFrames; i += kFeatThreads) {
+            const float v = fmaxf(S.db[i], floor_db);
+            S.db[i] = v;
+            out[i] = fminf(fmaxf((v + 80.0f) * 0.0125f, 0.f), 1.f);
+        }
+        __syncthreads();
+
+        // ---- MFCC = DCT-II(13 x 64) of the floored dB, then (x - mean) / (std + 1e-8) ---------------
+        float* mf = reinterpret_cast<float*>(&S.xb[0][0]);             // [13][101], FFT scratch is idle now
+        float part = 0.f;
+        {
+            const int t = tid & 127, cs = tid >> 7;
+            if (t < kFrames) {
+                switch (cs) {
+                    case 0: part = mfcc_set<0>(S.db, mf, t); break;
+                    case 1: part = mfcc_set<1>(S.db, mf, t); break;
+                    case 2: part = mfcc_set<2>(S.db, mf, t); break;
+                    default: part = mfcc_set<3>(S.db, mf, t); break;
+                }
+            }
+        }
+        constexpr int kN = kMfcc * kFrames;                            // 1313
+        const float mean = block_reduce<false>(part, S.red) * (1.0f / kN);
+        float ss = 0.f;
+        for (int i = tid; i < kN; i += kFeatThreads) {
+            const float dlt = mf[i] - mean;
+            ss = fmaf(dlt, dlt, ss);
+        }
+        ss = block_reduce<false>(ss, S.red);
+        const float inv_std = 1.0f / (sqrtf(ss * (1.0f / (kN - 1))) + 1e-8f);
+        for (int i = tid; i < kN; i += kFeatThreads) {
+            const int cidx = i / kFrames, t = i - cidx * kFrames;
+            const float* row = mf + cidx * kFrames;
+            const float x0 = (row[t] - mean) * inv_std;
+            const float xp = (row[min(t + 1, kFrames - 1)] - mean) * inv_std;
+            const float xm = (row[max(t - 1, 0)] - mean) * inv_std;
+            out[(kMels + cidx) * kFrames + t] = x0;
+            out[(kMels + kMfcc + cidx) * kFrames + t] = (xp - xm) * 0.5f;   // compute_deltas (:353-355)
+        }
+        __syncthreads();                                               // xb / db / clip[cur] free again
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side: tables + launcher
+// ----------------------------------------------------------------------------------------------
+static float bits2f(uint32_t u) {
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+int build_feat_tables(cd_handle* h) {
+    FeatTables* t = new FeatTables();
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int r = 1; r < 8; ++r)
+        for (int m = 0; m < 64; ++m) {
+            const double a = -two_pi * (double)((m * r) % 512) / 512.0;
+            t->tw1[r - 1][m] = make_float2((float)cos(a), (float)sin(a));
+        }
+    for (int u = 1; u < 8; ++u)
+        for (int c = 0; c < 8; ++c) {
+            const double a = -two_pi * (double)((c * u) % 64) / 64.0;
+            t->tw2[u - 1][c] = make_float2((float)cos(a), (float)sin(a));
+        }
+    for (int n = 0; n < kWin; ++n) t->win[n] = 0.5f * bits2f(CD_HANN_BITS[n]);   // exact (power of two)
+    for (int lane = 0; lane < 32; ++lane) {
+        for (int s = 0; s < kMelSlots; ++s) {
+            const int band = s < kMelSlotsLo ? lane : lane + 32;
+            const int tap = s < kMelSlotsLo ? s : s - kMelSlotsLo;
+            float w = 0.f;
+            int idx = 0;
+            if (tap < CD_MEL_COUNT[band]) {
+                w = bits2f(CD_MEL_W_BITS[band * CD_MEL_MAX_TAPS + tap]);
+                idx = CD_MEL_START[band] + tap - CD_MEL_FIRST_BIN;
+            }
+            float fi;
+            memcpy(&fi, &idx, 4);
+            t->melt[s][lane] = make_float2(w, fi);
+        }
+        if (CD_MEL_COUNT[lane] > kMelSlotsLo || CD_MEL_COUNT[lane + 32] > kMelSlotsHi) {
+            delete t;
+            return set_err(h, CD_E_STATE, "mel table does not fit the slot layout");
+        }
+    }
+    cudaError_t e = cudaMalloc(&h->d_tables, sizeof(FeatTables));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_tables, t, sizeof(FeatTables), cudaMemcpyHostToDevice);
+    float dct[kMfcc * kMels];
+    for (int i = 0; i < kMfcc * kMels; ++i) dct[i] = bits2f(CD_DCT_BITS[i]);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_dct, dct, sizeof(dct));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeatSmem));
+    delete t;
+    if (e != cudaSuccess) return set_err(h, CD_E_CUDA, "feature tables upload", e);
+    return CD_OK;
+}
+
+int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets, const int32_t* d_lengths,
+                    int64_t stride_or_hop, int mode, int64_t B, float* d_feat, cudaStream_t s) {
+    if (B == 0) return CD_OK;
+    const int grid = (int)(B < (int64_t)h->sm_count ? B : (int64_t)h->sm_count);
+    feat_kernel<<<grid, kFeatThreads, sizeof(FeatSmem), s>>>(d_audio, d_offsets, d_lengths, stride_or_hop, mode, B,
+                                                            d_feat, h->d_tables);
+    h->launches += 1;
+    CD_CUDA(h, cudaGetLastError());
+    return CD_OK;
+}
+
+void get_host_tables(float* hann, float* fb, float* dct) {
+    if (hann)
+        for (int n = 0; n < kWin; ++n) hann[n] = bits2f(CD_HANN_BITS[n]);
+    if (fb) {
+        memset(fb, 0, sizeof(float) * 257 * 64);
+        for (int m = 0; m < 64; ++m)
+            for (int tp = 0; tp < CD_MEL_COUNT[m]; ++tp)
+                fb[(CD_MEL_START[m] + tp) * 64 + m] = bits2f(CD_MEL_W_BITS[m * CD_MEL_MAX_TAPS + tp]);
+    }
+    if (dct)
+        for (int m = 0; m < 64; ++m)
+            for (int c = 0; c < 13; ++c) dct[m * 13 + c] = bits2f(CD_DCT_BITS[c * 64 + m]);
+}
+
+}  // namespace cd

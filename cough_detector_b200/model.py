@@ -1,0 +1,114 @@
+"""CoughDetectorResidual whose forward runs in libcough_b200.so.
+
+Host-side mirror of the reference's ``src/model.py`` for the one architecture on the hot path
+(``CoughDetectorResidual``, src/model.py:210-293).  The module tree, parameter names and shapes
+are the reference's, so ``state_dict`` / ``load_state_dict`` / checkpoints (src/train.py:183-199)
+interchange unchanged; ``forward`` hands the parameters to the C ABI (``cd_cnn_load`` folds
+BatchNorm and repacks, once per weight version) and calls ``cd_cnn_forward``.
+
+Inference only: ``forward`` in training mode raises (batch-statistics BatchNorm, Dropout and the
+backward pass are outside the north-star path).  There is no PyTorch fallback.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+#: precision used when a model does not say otherwise: "bf16" (tcgen05 tensor cores) or "fp32" (CUDA cores)
+DEFAULT_PRECISION = "fp32"
+_PREC = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16}
+
+
+class ResidualBlock(nn.Module):
+    """Parameter container with the reference's names (src/model.py:268-283); computed by the fused kernels."""
+
+    def __init__(self, in_channels: int, out_channels: int, stride: int = 2):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_channels, out_channels, 3, stride=stride, padding=1)
+        self.bn1 = nn.BatchNorm2d(out_channels)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, 3, padding=1)
+        self.bn2 = nn.BatchNorm2d(out_channels)
+        self.skip = nn.Sequential(nn.Conv2d(in_channels, out_channels, 1, stride=stride), nn.BatchNorm2d(out_channels))
+
+    def forward(self, x):  # pragma: no cover - blocks are never run on their own
+        raise RuntimeError("ResidualBlock is executed inside CoughDetectorResidual.forward (fused CUDA kernels)")
+
+
+class CoughDetectorResidual(nn.Module):
+    """7x7/s2 stem + BN + ReLU + maxpool2, two residual blocks, GAP, Linear(128->2) (src/model.py:210-265)."""
+
+    def __init__(self, n_mels: int = 64, num_classes: int = 2, in_channels: int = 1,
+                 channels: Tuple[int, ...] = (32, 64, 128), dropout: float = 0.5, precision: str = None):
+        super().__init__()
+        if num_classes != 2 or in_channels != 1 or tuple(channels) != (32, 64, 128):
+            raise NotImplementedError("the B200 kernels are built for in_channels=1, channels=(32,64,128), num_classes=2")
+        self.conv1 = nn.Sequential(nn.Conv2d(in_channels, channels[0], 7, stride=2, padding=3),
+                                   nn.BatchNorm2d(channels[0]), nn.ReLU(), nn.MaxPool2d(2))
+        self.res_blocks = nn.ModuleList()
+        cin = channels[0]
+        for cout in channels[1:]:
+            self.res_blocks.append(ResidualBlock(cin, cout))
+            cin = cout
+        self.global_pool = nn.AdaptiveAvgPool2d((1, 1))
+        self.fc = nn.Sequential(nn.Flatten(), nn.Dropout(dropout), nn.Linear(channels[-1], num_classes))
+        self.precision = precision or DEFAULT_PRECISION
+        self._uploaded = {}
+
+    # ---- weight upload, once per (device, parameter version) -----------------------------------------
+    def _weights_key(self):
+        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+
+    def _handle(self, x: torch.Tensor) -> "_lib.Handle":
+        h = _lib.get_handle(x.device if x.is_cuda else None)
+        key = (id(self), self._weights_key())
+        if h._weights_key != key:
+            h.load_state_dict(self.state_dict(), key=key)
+        return h
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """(B, 1, 90, 101) -> logits (B, 2) (reference :253-259)."""
+        if self.training:
+            raise RuntimeError("cough_detector_b200 is inference-only: call model.eval() before forward()")
+        if self.precision not in _PREC:
+            raise ValueError(f"precision must be one of {list(_PREC)}, got {self.precision!r}")
+        h = self._handle(x)
+        xd = x.detach().to(device=f"cuda:{h.device}", dtype=torch.float32, non_blocking=True)
+        logits = h.cnn_forward(xd, _PREC[self.precision])
+        return logits if x.is_cuda else logits.to(x.device)
+
+    def predict(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """softmax + argmax (reference :261-265): (LongTensor[B], Tensor[B, 2])."""
+        logits = self.forward(x)
+        h = _lib.get_handle(x.device if x.is_cuda else None)
+        preds, probs, _ = h.predict(logits.to(f"cuda:{h.device}"))
+        return (preds, probs) if x.is_cuda else (preds.to(x.device), probs.to(x.device))
+
+    def forward_audio(self, audio: torch.Tensor, return_features: bool = False):
+        """Additive fused entry: (B, 16000) waveforms -> logits, features never leave the GPU."""
+        if self.training:
+            raise RuntimeError("cough_detector_b200 is inference-only: call model.eval() before forward_audio()")
+        h = self._handle(audio)
+        xd = audio.detach().to(device=f"cuda:{h.device}", dtype=torch.float32, non_blocking=True)
+        out = h.e2e_forward(xd, _PREC[self.precision], return_features)
+        if audio.is_cuda:
+            return out
+        return tuple(o.to(audio.device) for o in out) if return_features else out.to(audio.device)
+
+
+def create_model(model_type: str = "standard", **kwargs) -> nn.Module:
+    """Reference factory signature (src/model.py:296-316).  Only 'residual' is on the hot path; the other two
+    known types raise NotImplementedError, an unknown type raises ValueError like the reference."""
+    known = ["standard", "small", "residual"]
+    if model_type not in known:
+        raise ValueError(f"Unknown model type: {model_type}. Choose from {known}")
+    if model_type != "residual":
+        raise NotImplementedError(f"model_type={model_type!r} has no B200 kernels; the hot path is 'residual' (SURVEY.md §0 D4)")
+    return CoughDetectorResidual(**kwargs)
+
+
+def count_parameters(model: nn.Module) -> int:
+    return sum(p.numel() for p in model.parameters() if p.requires_grad)

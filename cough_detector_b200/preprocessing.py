@@ -1,0 +1,213 @@
+"""AudioPreprocessor / RealtimePreprocessor on the B200 feature kernel.
+
+Host-side mirror of the reference's ``src/preprocessing.py`` (class and method names, argument
+meaning, return shapes, error behaviour) for the 90-feature configuration the reference trains
+with (``src/train.py:264-287``): ``use_pcen=False, use_pre_emphasis=False,
+use_delta_delta=False, use_spectral_contrast=False``.  All feature arithmetic runs in
+``libcough_b200.so`` (csrc/feat_kernel.cu); there is no torchaudio/CPU path here.  Flag
+combinations the kernel does not implement raise ``NotImplementedError`` instead of falling
+back (the 110-feature constructor defaults are SURVEY.md §8f rank 1, "next").
+
+Additive, batched entry points (the reference API is strictly per clip):
+``extract_features_batch``, ``process_batch`` and ``RealtimePreprocessor.stream_features``.
+Batch semantics are per clip: every clip gets its own peak, top_db floor and MFCC mean/std.
+Tensors come back on the device of the input (CPU in -> CPU out), like the reference.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+_FIXED = dict(sample_rate=16000, n_mels=64, n_fft=512, hop_length=160, win_length=400,
+              f_min=100.0, f_max=4000.0, n_mfcc=13)
+
+
+class AudioPreprocessor:
+    """Drop-in for reference ``AudioPreprocessor`` (src/preprocessing.py:13-550), 90-feature config."""
+
+    def __init__(self, sample_rate: int = 16000, n_mels: int = 64, n_fft: int = 512, hop_length: int = 160,
+                 win_length: int = 400, f_min: float = 100.0, f_max: float = 4000.0, segment_duration: float = 1.0,
+                 n_mfcc: int = 13, use_mfcc: bool = True, use_pcen: bool = True, use_pre_emphasis: bool = True,
+                 pre_emphasis_coef: float = 0.97, use_delta_delta: bool = True, use_spectral_contrast: bool = True,
+                 n_contrast_bands: int = 6, device: str = "cpu"):
+        got = dict(sample_rate=sample_rate, n_mels=n_mels, n_fft=n_fft, hop_length=hop_length, win_length=win_length,
+                   f_min=float(f_min), f_max=float(f_max), n_mfcc=n_mfcc)
+        bad = {k: v for k, v in got.items() if v != _FIXED[k]}
+        if bad or float(segment_duration) != 1.0 or not use_mfcc:
+            raise NotImplementedError(
+                f"the B200 feature kernel is built for {_FIXED}, segment_duration=1.0, use_mfcc=True; got {bad or ''} "
+                f"segment_duration={segment_duration} use_mfcc={use_mfcc}")
+        on = [n for n, v in (("use_pcen", use_pcen), ("use_pre_emphasis", use_pre_emphasis),
+                             ("use_delta_delta", use_delta_delta), ("use_spectral_contrast", use_spectral_contrast)) if v]
+        if on:
+            raise NotImplementedError(
+                f"{on} not implemented on the GPU path yet; construct with the reference training config "
+                "(use_pcen=False, use_pre_emphasis=False, use_delta_delta=False, use_spectral_contrast=False, "
+                "src/train.py:264-287).  There is deliberately no CPU fallback.")
+        self.sample_rate, self.n_mels, self.n_fft = sample_rate, n_mels, n_fft
+        self.hop_length, self.win_length, self.f_min, self.f_max = hop_length, win_length, f_min, f_max
+        self.segment_duration = segment_duration
+        self.segment_samples = int(sample_rate * segment_duration)
+        self.n_mfcc, self.use_mfcc = n_mfcc, use_mfcc
+        self.use_pcen, self.use_pre_emphasis, self.pre_emphasis_coef = use_pcen, use_pre_emphasis, pre_emphasis_coef
+        self.use_delta_delta, self.use_spectral_contrast = use_delta_delta, use_spectral_contrast
+        self.n_contrast_bands = n_contrast_bands
+        self.device = device
+
+    # ---- plumbing ------------------------------------------------------------------------------
+    def _gpu(self) -> "_lib.Handle":
+        dev = torch.device(self.device)
+        return _lib.get_handle(dev if dev.type == "cuda" else None)
+
+    @staticmethod
+    def _back(out: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+        return out if like.is_cuda else out.to(like.device)
+
+    # ---- waveform conditioning (host-side mirror, same semantics) -----------------------------------
+    def load_audio(self, path: str) -> Tuple[torch.Tensor, int]:
+        """File decode is outside the hot path; defers to torchaudio like the reference (:155-166)."""
+        import torchaudio
+        return torchaudio.load(path)
+
+    def resample(self, waveform: torch.Tensor, orig_sr: int) -> torch.Tensor:
+        """Identity at 16 kHz (the in-scope case, :179-180); other rates are §8f rank 3."""
+        if orig_sr == self.sample_rate:
+            return waveform
+        raise NotImplementedError(f"on-device resampling from {orig_sr} Hz is not built yet; feed 16 kHz audio")
+
+    def to_mono(self, waveform: torch.Tensor) -> torch.Tensor:
+        """(C, n) -> (1, n) channel mean (:185-197)."""
+        return waveform if waveform.shape[0] == 1 else waveform.mean(dim=0, keepdim=True)
+
+    def normalize(self, waveform: torch.Tensor) -> torch.Tensor:
+        """x / max|x|, unchanged when silent (:199-212).  Standalone use only: ``process`` and the batched
+        entry points fuse this into the kernel."""
+        peak = waveform.abs().max() if waveform.numel() else waveform.new_zeros(())
+        return waveform / peak if peak > 0 else waveform
+
+    def pad_or_trim(self, waveform: torch.Tensor, length: Optional[int] = None) -> torch.Tensor:
+        """Centre trim or zero pad (left = floor(pad/2)) to ``length`` (:358-385)."""
+        length = self.segment_samples if length is None else length
+        n = waveform.shape[1]
+        if n == length:
+            return waveform
+        if n > length:
+            s = (n - length) // 2
+            return waveform[:, s:s + length]
+        p = length - n
+        return torch.nn.functional.pad(waveform, (p // 2, p - p // 2))
+
+    def compute_deltas(self, features: torch.Tensor) -> torch.Tensor:
+        """(x[t+1] - x[t-1]) / 2 with replicated edges (:342-356); the kernel fuses this for the MFCC rows."""
+        p = torch.nn.functional.pad(features, (1, 1), mode="replicate")
+        return (p[:, :, 2:] - p[:, :, :-2]) / 2
+
+    # ---- features ------------------------------------------------------------------------------
+    def extract_features(self, waveform: torch.Tensor) -> torch.Tensor:
+        """(1, 16000) conditioned waveform -> (1, 90, 101), NO normalisation (reference :432-489)."""
+        if waveform.dim() != 2 or waveform.shape[0] != 1:
+            raise ValueError(f"expected waveform of shape (1, samples), got {tuple(waveform.shape)}")
+        if waveform.shape[1] != self.segment_samples:
+            raise ValueError(f"the B200 kernel extracts features of {self.segment_samples}-sample segments; got "
+                             f"{waveform.shape[1]} samples (use process() / pad_or_trim first)")
+        return self.extract_features_batch(waveform, normalize=False)[0]
+
+    def extract_mel_spectrogram(self, waveform: torch.Tensor) -> torch.Tensor:
+        """Rows 0..63 of extract_features (:387-412)."""
+        return self.extract_features(waveform)[:, : self.n_mels]
+
+    def extract_mfcc(self, waveform: torch.Tensor) -> torch.Tensor:
+        """Rows 64..76 of extract_features (:414-430)."""
+        return self.extract_features(waveform)[:, self.n_mels: self.n_mels + self.n_mfcc]
+
+    def extract_features_batch(self, waveforms: torch.Tensor, normalize: bool = True) -> torch.Tensor:
+        """(B, 16000) -> (B, 1, 90, 101); ``normalize`` applies per-clip peak normalisation first."""
+        if waveforms.dim() != 2 or waveforms.shape[1] != self.segment_samples:
+            raise ValueError(f"expected (B, {self.segment_samples}), got {tuple(waveforms.shape)}")
+        h = self._gpu()
+        x = waveforms.to(device=f"cuda:{h.device}", dtype=torch.float32, non_blocking=True)
+        return self._back(h.feat_forward(x, normalize=normalize), waveforms)
+
+    def process(self, waveform: torch.Tensor, orig_sr: int) -> torch.Tensor:
+        """resample -> mono -> normalize -> pad/trim -> features, one kernel (:491-517).  (C, n) -> (1, 90, 101)."""
+        return self.process_batch([waveform], orig_sr)[0]
+
+    def process_batch(self, waveforms: Sequence[torch.Tensor], orig_sr: int = 16000) -> torch.Tensor:
+        """Variable-length clips [(C_i, n_i) or (n_i,)] -> (B, 1, 90, 101); per clip identical to ``process``."""
+        if not len(waveforms):
+            return torch.zeros(0, 1, _lib.N_FEATURES, _lib.N_FRAMES)
+        h = self._gpu()
+        dev = f"cuda:{h.device}"
+        mono = []
+        for w in waveforms:
+            w = self.resample(w, orig_sr)
+            w = w.reshape(1, -1) if w.dim() == 1 else self.to_mono(w)
+            mono.append(w.reshape(-1).to(torch.float32))
+        lens = torch.tensor([m.numel() for m in mono], dtype=torch.int64)
+        pad = (-lens) % 4                                    # keep every clip 16-byte aligned for the bulk copy
+        offs = torch.cumsum(torch.cat([torch.zeros(1, dtype=torch.int64), (lens + pad)[:-1]]), 0)
+        flat = torch.zeros(int((lens + pad).sum()) + 4, dtype=torch.float32, device=dev)
+        for m, o in zip(mono, offs.tolist()):
+            flat[o:o + m.numel()] = m.to(dev, non_blocking=True)
+        out = h.feat_forward_var(flat, offs, lens.to(torch.int32))
+        return self._back(out, waveforms[0])
+
+    def process_file(self, path: str) -> torch.Tensor:
+        waveform, sr = self.load_audio(path)
+        return self.process(waveform, sr)
+
+    def get_expected_time_frames(self) -> int:
+        return (self.segment_samples // self.hop_length) + 1
+
+    def get_num_features(self) -> int:
+        """64 mel + 13 MFCC + 13 delta = 90 in the supported configuration (:536-550)."""
+        n = self.n_mels
+        if self.use_mfcc:
+            n += 2 * self.n_mfcc + (self.n_mfcc if self.use_delta_delta else 0)
+        if self.use_spectral_contrast:
+            n += self.n_contrast_bands + 1
+        return n
+
+
+class RealtimePreprocessor(AudioPreprocessor):
+    """Sliding-window streaming front end (reference :553-616): per-window peak normalisation, no pad/trim."""
+
+    def __init__(self, window_duration: float = 1.0, hop_duration: float = 0.5, **kwargs):
+        super().__init__(segment_duration=window_duration, **kwargs)
+        self.window_duration = window_duration
+        self.hop_duration = hop_duration
+        self.window_samples = int(self.sample_rate * window_duration)
+        self.hop_samples = int(self.sample_rate * hop_duration)
+        if self.hop_samples <= 0:
+            raise ValueError("hop_duration must be at least one sample")
+        self.buffer = torch.zeros(1, 0)
+
+    def stream_features(self, audio: torch.Tensor) -> torch.Tensor:
+        """All complete windows of a 1-D stream at once: (n,) -> (windows, 1, 90, 101)."""
+        h = self._gpu()
+        x = audio.reshape(-1).to(device=f"cuda:{h.device}", dtype=torch.float32)
+        return self._back(h.feat_forward_stream(x, self.hop_samples), audio)
+
+    def add_audio(self, audio_chunk: torch.Tensor) -> List[torch.Tensor]:
+        """Append a chunk; return the features of every window that became complete (:582-612)."""
+        if audio_chunk.dim() == 1:
+            audio_chunk = audio_chunk.unsqueeze(0)
+        self.buffer = torch.cat([self.buffer.to(audio_chunk.device), audio_chunk.to(torch.float32)], dim=1)
+        n = self.buffer.shape[1]
+        if n < self.window_samples:
+            return []
+        nw = (n - self.window_samples) // self.hop_samples + 1
+        feats = self.stream_features(self.buffer[0, : (nw - 1) * self.hop_samples + self.window_samples])
+        self.buffer = self.buffer[:, nw * self.hop_samples:]
+        return [feats[i] for i in range(nw)]
+
+    def reset(self):
+        self.buffer = torch.zeros(1, 0)
+
+
+def create_preprocessor(realtime: bool = False, **kwargs) -> AudioPreprocessor:
+    """Factory with the reference's signature (:619-632)."""
+    return RealtimePreprocessor(**kwargs) if realtime else AudioPreprocessor(**kwargs)

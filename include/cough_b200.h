@@ -1,0 +1,164 @@
+/* cough_b200.h -- C ABI of the B200-native cough_detector hot path (libcough_b200.so).
+ *
+ * The reference has no FFI: its hot path sits behind a Python class/function surface
+ * (SURVEY.md §8b).  These entry points are what a thin binding for that surface calls; each
+ * one names the reference interface it replaces (paths are into the reference repository).
+ * Plain pointers and sizes only -- no torch types.  All device work is enqueued on the
+ * caller's stream (a cudaStream_t passed as void*; NULL = legacy default stream) and is
+ * asynchronous unless stated.  Every function returns 0 on success or a negative CD_E_* code;
+ * cd_last_error() gives the message.  There is no CPU fallback: without a usable sm_100 device
+ * cd_create fails.
+ *
+ * Ownership: pointers are borrowed for the duration of the call (device pointers: until the
+ * enqueued work completes).  Inputs are never written.  A handle owns its constant tables,
+ * folded weights and workspace; one handle per GPU (or per thread), calls on one handle are not
+ * thread-safe, calls on different handles are independent.
+ */
+#ifndef COUGH_B200_H
+#define COUGH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CD_SAMPLE_RATE   16000
+#define CD_SEGMENT       16000   /* AudioPreprocessor.segment_samples, src/preprocessing.py:82 */
+#define CD_N_FEATURES    90      /* get_num_features(), src/preprocessing.py:536-550 (train.py:264-287 flags) */
+#define CD_N_FRAMES      101     /* get_expected_time_frames(), src/preprocessing.py:532-534 */
+#define CD_FEAT_ELEMS    (CD_N_FEATURES * CD_N_FRAMES)
+#define CD_N_CLASSES     2
+
+#define CD_OK            0
+#define CD_E_ARG        -1       /* bad argument (NULL pointer, negative size, unsupported value) */
+#define CD_E_CUDA       -2       /* a CUDA runtime call or kernel launch failed */
+#define CD_E_NODEVICE   -3       /* no CUDA device / device is not sm_100 */
+#define CD_E_STATE      -4       /* call order (e.g. CNN forward before weights were loaded) */
+#define CD_E_NOMEM      -5
+
+#define CD_FEAT_NORMALIZE 1      /* peak-normalise each clip before the features */
+
+#define CD_PRECISION_FP32 0      /* direct convolution on CUDA cores, fp32 weights + activations */
+#define CD_PRECISION_BF16 1      /* implicit-GEMM tcgen05 tiles, bf16 operands, fp32 accumulate */
+
+typedef struct cd_handle cd_handle;
+
+/* One convolution + its BatchNorm, exactly as stored in the reference state_dict
+ * (src/model.py:227-229, 274-283).  Host pointers, fp32, PyTorch layouts:
+ * weight [cout][cin][k][k], everything else [cout]. */
+typedef struct cd_conv_bn {
+    const float* weight;
+    const float* bias;
+    const float* bn_weight;        /* gamma */
+    const float* bn_bias;          /* beta */
+    const float* bn_running_mean;
+    const float* bn_running_var;
+} cd_conv_bn;
+
+/* The 51-tensor state_dict of CoughDetectorResidual (src/model.py:210-247) minus the
+ * num_batches_tracked counters. */
+typedef struct cd_residual_weights {
+    cd_conv_bn stem;               /* conv1.0 / conv1.1          7x7 s2 p3, 1 -> 32   */
+    cd_conv_bn b0_conv1;           /* res_blocks.0.conv1 / bn1   3x3 s2 p1, 32 -> 64  */
+    cd_conv_bn b0_conv2;           /* res_blocks.0.conv2 / bn2   3x3 s1 p1, 64 -> 64  */
+    cd_conv_bn b0_skip;            /* res_blocks.0.skip.0 / .1   1x1 s2,    32 -> 64  */
+    cd_conv_bn b1_conv1;           /* res_blocks.1.conv1 / bn1   3x3 s2 p1, 64 -> 128 */
+    cd_conv_bn b1_conv2;           /* res_blocks.1.conv2 / bn2   3x3 s1 p1, 128 -> 128*/
+    cd_conv_bn b1_skip;            /* res_blocks.1.skip.0 / .1   1x1 s2,    64 -> 128 */
+    const float* fc_weight;        /* fc.2.weight [2][128] */
+    const float* fc_bias;          /* fc.2.bias   [2]      */
+} cd_residual_weights;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+
+/* Create a handle on CUDA device `device`.  Replaces AudioPreprocessor.__init__ (transform /
+ * table construction, src/preprocessing.py:94-127): uploads the Hann, mel-filterbank, DCT and
+ * FFT twiddle tables. */
+int cd_create(int device, cd_handle** out);
+int cd_destroy(cd_handle* h);
+/* Message for the last non-zero return on this handle (or for a failed cd_create when h==NULL). */
+const char* cd_last_error(const cd_handle* h);
+/* Library / build identification, e.g. "cough_b200 0.1 sm_100a". */
+const char* cd_version(void);
+
+/* Host-side copy of the constant tables the kernels use (no GPU needed; h may be NULL):
+ * hann[400], fb[257*64] (dense, row = FFT bin), dct[64*13] (row = mel band).  Any pointer may be
+ * NULL.  Lets a binding check them against torchaudio's. */
+int cd_get_tables(float* hann, float* fb, float* dct);
+
+/* ---- features: AudioPreprocessor ------------------------------------------------------- */
+
+/* B fixed-length clips.  d_audio: device, B rows of 16000 fp32 samples, row pitch `stride`
+ * samples (>= 16000).  d_feat: device, B x 90 x 101 fp32, row-major (feature, time).
+ * flags: CD_FEAT_NORMALIZE applies normalize() (src/preprocessing.py:199-212) first, as
+ * dataset.__getitem__ / process() / add_audio() do; 0 is bare extract_features().
+ * Per clip: [normalize] -> extract_features (:432-489):
+ * mel dB [0,1] rows 0..63 (:387-412), normalised MFCC rows 64..76 (:414-430), deltas rows
+ * 77..89 (:342-356). */
+int cd_feat_forward(cd_handle* h, const float* d_audio, int64_t stride, int64_t B,
+                    float* d_feat, int flags, void* stream);
+
+/* B clips of arbitrary length described by (offset, length) into one device buffer:
+ * clip i = d_audio[d_offsets[i] .. d_offsets[i]+d_lengths[i]).  Per clip: normalize over the
+ * WHOLE clip -> pad_or_trim to 16000 (centre trim / symmetric zero pad, :358-385) ->
+ * extract_features, i.e. AudioPreprocessor.process (:491-517) at 16 kHz mono.
+ * d_offsets / d_lengths are device arrays.  length 0 is allowed (all-zero clip). */
+int cd_feat_forward_var(cd_handle* h, const float* d_audio, const int64_t* d_offsets,
+                        const int32_t* d_lengths, int64_t B, float* d_feat, void* stream);
+
+/* Sliding windows over one stream: window j = d_audio[j*hop .. j*hop+16000), per-window peak
+ * normalisation, no pad/trim: RealtimePreprocessor.add_audio (:582-612).  n_windows must be
+ * cd_stream_windows(n_samples, hop).  d_feat: n_windows x 90 x 101. */
+int cd_feat_forward_stream(cd_handle* h, const float* d_audio, int64_t n_samples, int64_t hop,
+                           int64_t n_windows, float* d_feat, void* stream);
+/* Number of windows add_audio emits for n_samples buffered samples (0 if n_samples < 16000). */
+int64_t cd_stream_windows(int64_t n_samples, int64_t hop);
+
+/* ---- model: CoughDetectorResidual ------------------------------------------------------ */
+
+/* Fold BatchNorm (eval mode, eps 1e-5) into the convolutions, repack for the kernels and upload.
+ * Replaces create_model('residual') + load_state_dict + .to(device) + .eval()
+ * (src/model.py:296-316, src/inference.py:147-157).  Synchronous.  May be called again to swap
+ * weights. */
+int cd_cnn_load(cd_handle* h, const cd_residual_weights* w);
+
+/* forward(): d_feat B x 1 x 90 x 101 fp32 -> d_logits B x 2 fp32 (src/model.py:253-259).
+ * precision: CD_PRECISION_FP32 or CD_PRECISION_BF16. */
+int cd_cnn_forward(cd_handle* h, const float* d_feat, int64_t B, float* d_logits,
+                   int precision, void* stream);
+
+/* predict() on logits: softmax probabilities (B x 2), argmax class (B, int64) as in
+ * src/model.py:261-265, and the batched decision P(cough) >= threshold (B, uint8) that stands in
+ * for the per-window test of src/inference.py:229.  Any output may be NULL. */
+int cd_predict(cd_handle* h, const float* d_logits, int64_t B, float threshold,
+               float* d_probs, int64_t* d_preds, uint8_t* d_decisions, void* stream);
+
+/* ---- end to end ------------------------------------------------------------------------ */
+
+/* audio -> logits in one call: cd_feat_forward + cd_cnn_forward without the features leaving
+ * the GPU.  d_feat_opt may be NULL (features go to the handle's workspace) or a B x 90 x 101
+ * buffer that receives them. */
+int cd_e2e_forward(cd_handle* h, const float* d_audio, int64_t stride, int64_t B,
+                   float* d_logits, float* d_feat_opt, int precision, void* stream);
+
+/* Same, over sliding windows of one stream (window j = d_audio[j*hop ..)); d_logits is
+ * n_windows x 2. */
+int cd_e2e_forward_stream(cd_handle* h, const float* d_audio, int64_t n_samples, int64_t hop,
+                          int64_t n_windows, float* d_logits, int precision, void* stream);
+
+/* HOST buffers: h_audio B x 16000 fp32 (pageable or pinned), h_logits B x 2 fp32.  The library
+ * pipelines chunked host->device copies, the kernels and the device->host copy of the logits on
+ * its own streams, and returns when h_logits is complete (synchronous).  This is the call the
+ * bench's end-to-end number times. */
+int cd_e2e_forward_host(cd_handle* h, const float* h_audio, int64_t B, float* h_logits,
+                        int precision);
+
+/* Number of kernels this handle has launched since creation (the bench's gpu_launches). */
+int64_t cd_launch_count(const cd_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COUGH_B200_H */

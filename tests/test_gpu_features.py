@@ -1,0 +1,132 @@
+"""Parity of the CUDA feature kernel (through the C ABI) with the reference goldens and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from cough_detector_b200 import _lib, synth, AudioPreprocessor, RealtimePreprocessor
+from oracle import cough_oracle as co
+from tests import golden_io as gio
+
+pytestmark = pytest.mark.gpu
+FLAGS = dict(use_pcen=False, use_pre_emphasis=False, use_delta_delta=False, use_spectral_contrast=False)
+TOL = 1e-4          # north_star: fp32 features within 1e-4 abs of the reference
+TOL_ILL = 5e-3      # clips whose above-floor cells sit >90 dB under their frame's peak (see oracle)
+
+
+def _ill(x):
+    return co.ill_conditioned_fraction(co.conditioned_window(x.numpy())) > 0
+
+
+def test_golden_features_process_path():
+    clips, feats, _ = gio.load_features()
+    pp = AudioPreprocessor(**FLAGS)
+    got = pp.process_batch(clips)
+    assert got.shape == (len(clips), 1, 90, 101) and got.device.type == "cpu"
+    worst = 0.0
+    for i, x in enumerate(clips):
+        d = (got[i, 0] - feats[i]).abs().max().item()
+        assert torch.isfinite(got[i]).all()
+        if _ill(x):
+            assert d <= TOL_ILL, (i, d)
+        else:
+            worst = max(worst, d)
+            assert d <= TOL, (i, len(x), d)
+    print("golden features: worst well-conditioned |err| = %.3e" % worst)
+    one = pp.process(clips[3].reshape(1, -1), 16000)          # the reference's per-clip call
+    assert one.shape == (1, 90, 101) and torch.equal(one, got[3])
+
+
+def test_extract_features_does_not_normalise():
+    clips, _, _ = gio.load_features()
+    pp = AudioPreprocessor(**FLAGS)
+    ex = co.Explicit32()
+    x = 0.3 * co.pad_or_trim(co.normalize(clips[7].reshape(1, -1)))      # deliberately NOT peak 1
+    got = pp.extract_features(x)
+    assert (got - ex.features(x)).abs().max().item() <= TOL
+    assert (got - ex.features(x / 0.3)).abs().max().item() > 1e-3
+
+
+def test_seeded_batch_vs_oracle_and_fp64():
+    clips = synth.synth_clips(200, seed=11, fixed_length=True)
+    x = torch.stack(clips)
+    h = _lib.get_handle(0)
+    got = h.feat_forward(x.cuda()).cpu()[:, 0]
+    ex = co.Explicit32()
+    w32 = w64 = 0.0
+    for i in range(len(clips)):
+        ill = _ill(clips[i])
+        ref = ex.process(clips[i].reshape(1, -1))[0]
+        d32 = (got[i] - ref).abs().max().item()
+        assert d32 <= (TOL_ILL if ill else TOL), (i, d32)
+        if not ill:
+            w32 = max(w32, d32)
+            if i % 8 == 0:
+                d64 = np.abs(got[i].numpy() - co.features_fp64(clips[i].numpy())).max()
+                w64 = max(w64, d64)
+                assert d64 <= TOL, (i, d64)
+    print("200 seeded clips: vs fp32 oracle %.3e, vs fp64 truth %.3e" % (w32, w64))
+
+
+def test_batch_is_per_clip_and_order_independent():
+    x = torch.stack(synth.synth_clips(333, seed=5, fixed_length=True)).cuda()
+    h = _lib.get_handle(0)
+    a = h.feat_forward(x)
+    perm = torch.randperm(x.shape[0], device="cuda")
+    b = h.feat_forward(x[perm])
+    assert torch.equal(a[perm], b)                      # bit-identical regardless of batch position / CTA
+    assert torch.equal(h.feat_forward(x[:1]), a[:1])
+    assert h.feat_forward(x[:0]).shape == (0, 1, 90, 101)
+
+
+def test_properties_scale_invariance_and_ranges():
+    x = torch.stack(synth.synth_clips(64, seed=9, fixed_length=True)).cuda()
+    h = _lib.get_handle(0)
+    a = h.feat_forward(x)
+    b = h.feat_forward(x * 8.0)                          # power-of-two gain: peak normalisation removes it exactly
+    assert torch.equal(a, b)
+    mel = a[:, 0, :64]
+    assert mel.min() >= 0 and mel.max() <= 1
+    mf = a[:, 0, 64:77]
+    live = mf.flatten(1).std(dim=1) > 0
+    assert (mf.flatten(1).mean(dim=1).abs()[live] < 1e-4).all()
+    assert ((mf.flatten(1).std(dim=1) - 1).abs()[live] < 1e-4).all()
+    d = a[:, 0, 77:90]
+    assert torch.allclose(d[:, :, 1:-1], (mf[:, :, 2:] - mf[:, :, :-2]) / 2, atol=1e-6)
+    assert torch.allclose(d[:, :, 0], (mf[:, :, 1] - mf[:, :, 0]) / 2, atol=1e-6)
+
+
+def test_stream_matches_reference_realtime_preprocessor():
+    stream, z = gio.load_stream()
+    for hop_ms in (250, 100):
+        ref = torch.from_numpy(z[f"feat_hop{hop_ms}"])
+        rp = RealtimePreprocessor(window_duration=1.0, hop_duration=hop_ms / 1000.0, **FLAGS)
+        got = []
+        for c in range(0, stream.numel(), 1600):         # 100 ms chunks, like the reference mic loop
+            got += rp.add_audio(stream[c:c + 1600])
+        got = torch.stack(got)
+        assert got.shape == ref.shape
+        assert (got - ref).abs().max().item() <= TOL
+        allatonce = rp.stream_features(stream)
+        assert torch.equal(allatonce, got)
+    odd = RealtimePreprocessor(window_duration=1.0, hop_duration=0.0123, **FLAGS)   # hop 196: unaligned windows
+    f = odd.stream_features(stream[:20000])
+    want = co.stream_features(stream[:20000], 196)
+    assert f.shape == want.shape and (f - want).abs().max().item() <= TOL
+
+
+def test_full_size_config2_properties():
+    """BASELINE config 2 size (65 536 clips): idempotence across launches + spot parity vs the oracle."""
+    h = _lib.get_handle(0)
+    x = synth.synth_batch(65536, seed=1, device="cuda")
+    a = h.feat_forward(x)
+    assert torch.isfinite(a).all()
+    idx = torch.tensor([0, 1, 2, 3, 147, 148, 149, 4095, 4096, 32767, 65535])
+    ex = co.Explicit32()
+    xc = x[idx.cuda()].cpu()
+    for k, i in enumerate(idx.tolist()):
+        ref = ex.process(xc[k].reshape(1, -1))[0]
+        assert (a[i, 0].cpu() - ref).abs().max().item() <= TOL, i
+    b = h.feat_forward(x[idx.cuda()])
+    assert torch.equal(b, a[idx.cuda()])
+    checksum = a.double().sum().item()
+    assert checksum == h.feat_forward(x).double().sum().item()

@@ -1,0 +1,140 @@
+"""Parity of the CUDA CoughDetectorResidual forward / predict / engine with the reference goldens."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from cough_detector_b200 import _lib, synth, create_model, CoughDetectorInference
+from cough_detector_b200.model import _PREC
+from oracle import cough_oracle as co
+from tests import golden_io as gio
+
+pytestmark = pytest.mark.gpu
+# stated tolerances: fp32 path vs reference fp32 logits; bf16 path relative to the logit scale
+TOL_FP32 = 2e-4
+TOL_BF16_REL = 3e-2
+PRECISIONS = ["fp32", "bf16"]
+
+
+def _model(sd, precision):
+    m = create_model("residual", n_mels=90, num_classes=2, in_channels=1).eval()
+    m.load_state_dict(sd)
+    m.precision = precision
+    return m
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_golden_logits_and_decisions(precision):
+    _, feats, _ = gio.load_features()
+    sd0, sd1, z = gio.load_model()
+    x = feats.unsqueeze(1)
+    for name, sd in (("default", sd0), ("random", sd1)):
+        m = _model(sd, precision)
+        ref = torch.from_numpy(z[f"logits_{name}"])
+        scale = max(1.0, ref.abs().max().item())
+        logits = m(x)
+        assert logits.shape == (x.shape[0], 2) and logits.device.type == "cpu"
+        err = (logits - ref).abs().max().item()
+        tol = TOL_FP32 * scale if precision == "fp32" else TOL_BF16_REL * scale
+        assert err <= tol, (name, precision, err, tol)
+        preds, probs = m.predict(x)
+        assert preds.dtype == torch.int64 and probs.shape == (x.shape[0], 2)
+        pref = z[f"probs_{name}"]
+        # decisions at 0.7 identical outside the tolerance band |p - 0.7| <= band
+        band = 1e-4 if precision == "fp32" else float(np.abs(probs.numpy() - pref).max()) + 1e-6
+        dec, dref = probs[:, 1].numpy() >= 0.7, pref[:, 1] >= 0.7
+        outside = np.abs(pref[:, 1] - 0.7) > band
+        assert np.array_equal(dec[outside], dref[outside])
+        amb = np.abs(pref[:, 1] - 0.5) > band
+        assert np.array_equal(preds.numpy()[amb], z[f"preds_{name}"][amb])
+        print(f"{name}/{precision}: logit err {err:.3e} (scale {scale:.2f}), prob err {np.abs(probs.numpy() - pref).max():.3e}")
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_seeded_batch_vs_oracle(precision):
+    _, sd1, _ = gio.load_model()
+    h = _lib.get_handle(0)
+    x = torch.stack(synth.synth_clips(300, seed=21, fixed_length=True))
+    feat = h.feat_forward(x.cuda())
+    m = _model(sd1, precision)
+    logits = m(feat)
+    ref = co.cnn_forward(sd1, feat.cpu())
+    scale = max(1.0, ref.abs().max().item())
+    err = (logits.cpu() - ref).abs().max().item()
+    assert err <= (TOL_FP32 if precision == "fp32" else TOL_BF16_REL) * scale, err
+    # fused audio -> logits equals the two-step path bit for bit, and batch position does not matter
+    fused = m.forward_audio(x.cuda())
+    assert torch.equal(fused, logits)
+    perm = torch.randperm(300, device="cuda")
+    assert torch.equal(m.forward_audio(x.cuda()[perm]), fused[perm])
+    assert m(feat[:0]).shape == (0, 2)
+
+
+def test_bf16_within_emulated_bf16_band():
+    """The tcgen05 path should agree with a CPU emulation of bf16 operands / fp32 accumulate much more
+    tightly than with the fp32 reference."""
+    _, feats, _ = gio.load_features()
+    _, sd1, _ = gio.load_model()
+    x = feats.unsqueeze(1)
+    emu = co.cnn_forward_bf16(sd1, x)
+    got = _model(sd1, "bf16")(x)
+    scale = max(1.0, emu.abs().max().item())
+    assert (got - emu).abs().max().item() <= 5e-3 * scale
+
+
+def test_weight_swap_and_reload():
+    _, feats, _ = gio.load_features()
+    sd0, sd1, z = gio.load_model()
+    x = feats[:4].unsqueeze(1)
+    m = _model(sd0, "fp32")
+    a = m(x)
+    m.load_state_dict(sd1)                      # in-place parameter update must trigger a re-upload
+    b = m(x)
+    assert (a - torch.from_numpy(z["logits_default"][:4])).abs().max() <= TOL_FP32
+    assert (b - torch.from_numpy(z["logits_random"][:4])).abs().max() <= TOL_FP32 * max(1.0, float(np.abs(z["logits_random"]).max()))
+    m2 = _model(sd0, "fp32")
+    assert torch.equal(m2(x), a)
+
+
+def test_host_buffer_e2e_equals_device_path():
+    _, sd1, _ = gio.load_model()
+    h = _lib.get_handle(0)
+    m = _model(sd1, "fp32")
+    x = torch.stack(synth.synth_clips(5000, seed=2, fixed_length=True))      # > 2 pipeline chunks
+    dev = m.forward_audio(x.cuda()).cpu()
+    for prec in PRECISIONS:
+        m.precision = prec
+        dev = m.forward_audio(x.cuda()).cpu()
+        host = h.e2e_forward_host(x.pin_memory(), _PREC[prec])
+        assert torch.equal(host, dev)
+        assert torch.equal(h.e2e_forward_host(x, _PREC[prec]), dev)           # pageable buffer
+
+
+def test_engine_checkpoint_roundtrip_and_chunk_loop():
+    stream, zs = gio.load_stream()
+    e = gio.load_engine()
+    _, sd1, _ = gio.load_model()
+    cfg = dict(model_type="residual", use_pcen=False, use_pre_emphasis=False, use_delta_delta=False,
+               use_spectral_contrast=False)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "best_model.pt")
+        torch.save({"epoch": 0, "model_state_dict": sd1, "optimizer_state_dict": {}, "metrics": {}, "config": cfg}, path)
+        eng = CoughDetectorInference(path, device="cuda", confidence_threshold=0.5, smoothing_window=3,
+                                     debounce_seconds=0.0, verbose=False)
+        eng.model.precision = "fp32"
+        fired, confs = [], []
+        for c in range(0, stream.numel(), 4000):
+            r = eng.process_audio_chunk(stream[c:c + 4000].numpy())
+            fired.append(r is not None)
+            confs.append(-1.0 if r is None else float(r[1]))
+        assert fired == list(e["fired"])
+        assert np.allclose(confs, e["confs"], atol=2e-4)
+        probs = eng.stream_probabilities(stream, 0.25).cpu().numpy()
+        assert np.abs(probs - e["probs"]).max() <= 2e-4
+        ev = eng.detect_stream(stream, 0.25)
+        assert [round((t - 1.0) / 0.25) for t, _ in ev] == [i - 3 for i in np.nonzero(e["fired"])[0]]
+        with pytest.raises(NotImplementedError):          # checkpoint without feature flags = 110-feature config
+            torch.save({"model_state_dict": sd1, "config": {"model_type": "residual"}}, path)
+            CoughDetectorInference(path, device="cuda", verbose=False)
