@@ -19,7 +19,7 @@ constexpr int kCnnThreads = 256;
 // ---------------------------------------------------------------------------------------------
 // stem: 7x7 stride 2 pad 3, 1 -> 32, ReLU, MaxPool2d(2) (floor mode: conv row 44 / col 50 unused)
 // ---------------------------------------------------------------------------------------------
-constexpr int kStemRows = 93;      // input rows -3 .. 89
+constexpr int kStemRows = 94;      // input rows -3 .. 89 (+1 so the weight table after it stays 16-byte aligned)
 constexpr int kStemPitch = 106;    // input cols -3 .. 101 (+1)
 constexpr int kPoolH = 22, kPoolW = 25;
 
