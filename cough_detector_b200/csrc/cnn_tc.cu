@@ -1,18 +1,695 @@
-// CoughDetectorResidual forward on the tcgen05 tensor cores (CD_PRECISION_BF16) -- placeholder
-// until the implicit-GEMM kernels land; reports CD_E_STATE so nothing silently falls back.
+// CoughDetectorResidual forward on the 5th-generation tensor cores (CD_PRECISION_BF16).
+//
+// Replaces src/model.py:253-293 (forward of the stem + two ResidualBlocks + head) in eval mode
+// with BatchNorm folded into bf16 weights.  The four 3x3 convolutions and the two 1x1 skip
+// projections are implicit GEMMs: M = (clip, output pixel) rows in tiles of 128, N = C_out,
+// K = 9*C_in walked in 64-element (128-byte) chunks.
+//
+//   producer warps 0-3 : gather the im2col A tile with cp.async (16-byte channel groups of the
+//                        NHWC bf16 activation, zero-fill for padding) straight into the
+//                        SWIZZLE_128B K-major layout tcgen05 reads; thread 0 streams the
+//                        pre-swizzled weight chunk with one cp.async.bulk (TMA engine)
+//   MMA warp 4         : one elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32)
+//                        into TMEM; the 1x1/s2 skip conv re-uses the centre-tap A chunk into a
+//                        second accumulator; tcgen05.commit frees smem stages / publishes tiles
+//   epilogue warps 5-8 : tcgen05.ld the accumulators, + folded bias, ReLU / residual add, store
+//                        bf16 NHWC (or fp32 for the last layer); accumulators are double
+//                        buffered in TMEM so the epilogue of tile i overlaps the MMAs of i+1
+// The stem (C_in = 1) and the 42-pixel average pool + Linear(128->2) run on CUDA cores for now.
 #include <vector>
 
 #include "cd_common.cuh"
 
 namespace cd {
 
-int init_cnn_tc(cd_handle*) { return CD_OK; }
-int upload_cnn_tc(cd_handle*, const std::vector<std::vector<float>>&, const std::vector<std::vector<float>>&) {
+// ----------------------------------------------------------------------------------------------
+// PTX helpers (tcgen05 / mbarrier / cp.async)
+// ----------------------------------------------------------------------------------------------
+namespace tc {
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(s32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (-> launch error the host reports) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();     // ~2 s at 1.9 GHz
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(s32(dst)), "l"(src), "r"(bytes), "r"(s32(bar)) : "memory");
+}
+// 16-byte async copy, src_bytes = 0 zero-fills (implicit-GEMM padding)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 operands, fp32 accumulate, issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane = tile row)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major operand tile in the canonical SWIZZLE_128B layout (cute Layout_K_SW128_Atom): rows of
+// 64 bf16 = 128 B, 16-byte chunk j of row r stored at chunk j ^ (r & 7), 8-row groups 1024 B
+// apart.  Descriptor fields per cute/arch/mma_sm100_desc.hpp (SmemDescriptor): start>>4 [0,14),
+// LBO>>4 [16,30) (=1, unused for swizzled K-major), SBO>>4 [32,46) (=64), version=1 [46,48),
+// layout_type=2 (SWIZZLE_128B) [61,64).  Tile base must be 1024-byte aligned.
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)64 << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// InstrDescriptor (same header): c_format F32=1 [4,6), a/b_format BF16=1 [7,10)/[10,13), both
+// K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t swz128(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
+}  // namespace tc
+
+// ----------------------------------------------------------------------------------------------
+// UMMA self-test: D[128 x N] = A[128 x K] * B[N x K]^T through the exact helpers the conv kernels use
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+umma_selftest_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ Bm, float* __restrict__ D,
+                     int N, int K) {
+    extern __shared__ unsigned char raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    const int kc_n = K / 64;
+    unsigned char* sA = base;                             // [kc][128 rows][128 B]
+    unsigned char* sB = base + (size_t)kc_n * 16384;      // [kc][N rows][128 B]
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 128 * (K / 8); i += 128) {
+        const int row = i / (K / 8), ch = i % (K / 8), kc = ch >> 3, j = ch & 7;
+        *reinterpret_cast<uint4*>(sA + kc * 16384 + tc::swz128(row, j)) = *reinterpret_cast<const uint4*>(A + (size_t)row * K + ch * 8);
+    }
+    for (int i = tid; i < N * (K / 8); i += 128) {
+        const int row = i / (K / 8), ch = i % (K / 8), kc = ch >> 3, j = ch & 7;
+        *reinterpret_cast<uint4*>(sB + (size_t)kc * N * 128 + tc::swz128(row, j)) = *reinterpret_cast<const uint4*>(Bm + (size_t)row * K + ch * 8);
+    }
+    tc::fence_proxy_async();
+    if (warp == 0) tc::tmem_alloc(&tmem_base, 256);
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tm = tmem_base;
+    if (tid == 0) {
+        const uint32_t idesc = tc::idesc_bf16(128, N);
+        for (int kc = 0; kc < kc_n; ++kc)
+            for (int k4 = 0; k4 < 4; ++k4)
+                tc::umma_bf16(tm, tc::desc_sw128(tc::s32(sA + kc * 16384) + k4 * 32),
+                              tc::desc_sw128(tc::s32(sB + (size_t)kc * N * 128) + k4 * 32), idesc, (kc | k4) != 0);
+        tc::tc_commit(&bar);
+    }
+    tc::mbar_wait(&bar, 0);
+    tc::tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        float v[32];
+        tc::tmem_ld32(tm + ((uint32_t)(warp * 32) << 16) + c0, v);
+        for (int i = 0; i < 32; ++i) D[(size_t)tid * N + c0 + i] = v[i];
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tm, 256);
+}
+
+// ----------------------------------------------------------------------------------------------
+// implicit-GEMM 3x3 convolution (pad 1) on tcgen05
+// ----------------------------------------------------------------------------------------------
+constexpr int kTcStages = 4;
+constexpr int kTcProducers = 128, kTcEpilogue = 128;
+constexpr int kTcThreads = kTcProducers + 32 + kTcEpilogue;     // 288
+
+template <int CIN, int COUT>
+struct TcShape {
+    static constexpr int KTOT = 9 * CIN;
+    static constexpr int NKC = (KTOT + 63) / 64;                 // 64-element K chunks (5 / 9 / 18)
+    static constexpr int A_BYTES = 128 * 128;                    // 128 rows x 128 B
+    static constexpr int B_BYTES = COUT * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SKIP_K = CIN < 64 ? CIN : 64;           // K of the 1x1 projection (per 64-chunk)
+    static constexpr size_t SMEM = 1024 + (size_t)kTcStages * STAGE_BYTES + B_BYTES /*skip W*/ + 2 * COUT * 4 + 256;
+};
+
+struct TcArgs {
+    const __nv_bfloat16* x;        // NHWC bf16 input  [B][HIN][WIN][CIN]
+    const __nv_bfloat16* w;        // pre-swizzled weight chunks [NKC][COUT x 128 B]
+    const __nv_bfloat16* wskip;    // pre-swizzled skip weights [COUT x 128 B] (SKIP)
+    const float* bias;             // [COUT]
+    const float* bias_skip;        // [COUT] (SKIP)
+    const float* idt_in;           // [M][COUT] fp32 (RESID)
+    __nv_bfloat16* y_bf16;         // [M][COUT]
+    float* y_f32;                  // [M][COUT] (OUT_F32)
+    float* idt_out;                // [M][COUT] fp32 (SKIP)
+    int B;
+};
+
+template <int CIN, int COUT, int HIN, int WIN, int STRIDE, bool SKIP, bool RESID, bool OUT_F32>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3x3_tc_kernel(const TcArgs a) {
+    using S = TcShape<CIN, COUT>;
+    constexpr int HOUT = (HIN - 1) / STRIDE + 1, WOUT = (WIN - 1) / STRIDE + 1, NPOS = HOUT * WOUT;
+    constexpr int ACC_COLS = SKIP ? 2 * COUT : COUT;             // conv accumulator [+ skip accumulator]
+    constexpr int TMEM_COLS = 2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512);
+    static_assert(2 * ACC_COLS <= 512, "TMEM");
+    constexpr uint32_t IDESC = tc::idesc_bf16(128, COUT);
+
+    extern __shared__ unsigned char raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* s_skipw = base + (size_t)kTcStages * S::STAGE_BYTES;
+    float* s_bias = reinterpret_cast<float*>(s_skipw + S::B_BYTES);      // [2][COUT]
+    __shared__ uint64_t full_bar[kTcStages], empty_bar[kTcStages], tfull_bar[2], tempty_bar[2], skipw_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t M = (int64_t)a.B * NPOS;
+    const int n_tiles = (int)((M + 127) / 128);
+
+    if (tid == 0) {
+        for (int s = 0; s < kTcStages; ++s) {
+            tc::mbar_init(&full_bar[s], kTcProducers);
+            tc::mbar_init(&empty_bar[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&tfull_bar[i], 1);
+            tc::mbar_init(&tempty_bar[i], kTcEpilogue);
+        }
+        tc::mbar_init(&skipw_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < COUT; i += kTcThreads) {
+        s_bias[i] = a.bias[i];
+        s_bias[COUT + i] = SKIP ? a.bias_skip[i] : 0.f;
+    }
+    if (warp == 4) tc::tmem_alloc(&tmem_base_s, TMEM_COLS);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp < 4) {
+        // ======================= producers: im2col gather + weight stream ==========================
+        if (SKIP && tid == 0) {
+            tc::mbar_arrive_expect_tx(&skipw_bar, S::B_BYTES);
+            tc::bulk_g2s(s_skipw, a.wskip, S::B_BYTES, &skipw_bar);
+        }
+        const int j = tid & 7;                       // 16-byte chunk within the 128-byte K row
+        const int r0 = tid >> 3;                     // rows r0 + 16 i
+        const uint32_t dst_off = tc::swz128(r0, j);  // (r0 + 16 i) & 7 == r0 & 7
+        int it = 0;                                  // global chunk counter -> stage / parity
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            int pix_off[8];                          // element offset of input pixel (oy*S-1, ox*S-1), channel 0
+            int iyx[8];                              // (iy0 + 1) << 16 | (ix0 + 1), or -1 for rows past M
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int64_t m = (int64_t)tile * 128 + r0 + 16 * i;
+                if (m < M) {
+                    const int b = (int)(m / NPOS), pos = (int)(m - (int64_t)b * NPOS);
+                    const int oy = pos / WOUT, ox = pos - oy * WOUT;
+                    const int iy0 = oy * STRIDE - 1, ix0 = ox * STRIDE - 1;
+                    pix_off[i] = ((b * HIN + iy0) * WIN + ix0) * CIN;
+                    iyx[i] = ((iy0 + 1) << 16) | (ix0 + 1);
+                } else {
+                    pix_off[i] = 0;
+                    iyx[i] = -1;
+                }
+            }
+            for (int kc = 0; kc < S::NKC; ++kc, ++it) {
+                const int s = it % kTcStages;
+                const uint32_t par = (uint32_t)((it / kTcStages) & 1);
+                tc::mbar_wait(&empty_bar[s], par ^ 1u);
+                unsigned char* stage = base + (size_t)s * S::STAGE_BYTES;
+                if (tid == 0) {
+                    tc::mbar_expect_tx(&full_bar[s], S::B_BYTES);
+                    tc::bulk_g2s(stage + S::A_BYTES, reinterpret_cast<const unsigned char*>(a.w) + (size_t)kc * S::B_BYTES,
+                                 S::B_BYTES, &full_bar[s]);
+                }
+                // K index of this thread's chunk -> (tap, first channel)
+                const int k = kc * 64 + j * 8;
+                const int tap = k / CIN, c0 = k - tap * CIN;
+                const int ky = tap / 3, kx = tap - ky * 3;
+                const int tap_off = (ky * WIN + kx) * CIN + c0;
+                const uint32_t sdst = tc::s32(stage) + dst_off;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int iy = (iyx[i] >> 16) - 1 + ky, ix = (iyx[i] & 0xffff) - 1 + kx;
+                    const bool ok = iyx[i] >= 0 && tap < 9 && iy >= 0 && iy < HIN && ix >= 0 && ix < WIN;
+                    const __nv_bfloat16* src = ok ? a.x + pix_off[i] + tap_off : a.x;
+                    tc::cp_async16(sdst + i * 16 * 128, src, ok ? 16u : 0u);
+                }
+                tc::cp_async_commit();
+                if (it >= 2) {                        // publish the stage filled two chunks ago
+                    tc::cp_async_wait<2>();
+                    tc::fence_proxy_async();
+                    tc::mbar_arrive(&full_bar[(it - 2) % kTcStages]);
+                }
+            }
+        }
+        // drain
+        tc::cp_async_wait<0>();
+        tc::fence_proxy_async();
+        if (it >= 2) tc::mbar_arrive(&full_bar[(it - 2) % kTcStages]);
+        if (it >= 1) tc::mbar_arrive(&full_bar[(it - 1) % kTcStages]);
+    } else if (warp == 4) {
+        // ======================= MMA issuer ==========================================================
+        if (lane == 0) {
+            if (SKIP) tc::mbar_wait(&skipw_bar, 0);
+            int it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+                const int acc = tcount & 1;
+                tc::mbar_wait(&tempty_bar[acc], (uint32_t)(((tcount >> 1) & 1) ^ 1));
+                tc::tc_fence_after();
+                const uint32_t d_conv = tmem_base + acc * ACC_COLS;
+                const uint32_t d_skip = d_conv + COUT;
+                for (int kc = 0; kc < S::NKC; ++kc, ++it) {
+                    const int s = it % kTcStages;
+                    tc::mbar_wait(&full_bar[s], (uint32_t)((it / kTcStages) & 1));
+                    tc::tc_fence_after();
+                    const uint32_t sa = tc::s32(base + (size_t)s * S::STAGE_BYTES);
+                    const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4)
+                        tc::umma_bf16(d_conv, tc::desc_sw128(sa + k4 * 32), tc::desc_sw128(sb + k4 * 32), IDESC,
+                                      (kc | k4) != 0);
+                    if (SKIP) {
+                        // centre tap (ky = kx = 1, tap 4) = K range [4*CIN, 5*CIN)
+                        constexpr int KC_C = (4 * CIN) / 64, K4_0 = ((4 * CIN) % 64) / 16, NK4 = S::SKIP_K / 16;
+                        if (CIN <= 64) {
+                            if (kc == KC_C) {
+#pragma unroll
+                                for (int q = 0; q < NK4; ++q)
+                                    tc::umma_bf16(d_skip, tc::desc_sw128(sa + (K4_0 + q) * 32),
+                                                  tc::desc_sw128(tc::s32(s_skipw) + q * 32), IDESC, q != 0);
+                            }
+                        }
+                    }
+                    tc::tc_commit(&empty_bar[s]);       // frees the stage when these MMAs retire
+                }
+                tc::tc_commit(&tfull_bar[acc]);         // accumulators of this tile complete
+            }
+        }
+    } else {
+        // ======================= epilogue ============================================================
+        const int ew = warp - 5;                        // 0..3
+        const int lane_grp = warp & 3;                  // TMEM lanes 32*(warp%4) .. +31 are this warp's
+        const int row = lane_grp * 32 + lane;
+        (void)ew;
+        int tcount = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+            const int acc = tcount & 1;
+            tc::mbar_wait(&tfull_bar[acc], (uint32_t)((tcount >> 1) & 1));
+            tc::tc_fence_after();
+            const int64_t m = (int64_t)tile * 128 + row;
+            const bool live = m < M;
+            const uint32_t t_conv = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * ACC_COLS;
+#pragma unroll 1
+            for (int c0 = 0; c0 < COUT; c0 += 32) {
+                float v[32];
+                tc::tmem_ld32(t_conv + c0, v);
+                if (live) {
+                    if (RESID) {
+                        const float4* ip = reinterpret_cast<const float4*>(a.idt_in + m * COUT + c0);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 t = __ldg(ip + q);
+                            v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + s_bias[c0 + i], 0.f);
+                    if (OUT_F32) {
+                        float4* op = reinterpret_cast<float4*>(a.y_f32 + m * COUT + c0);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    } else {
+                        uint4* op = reinterpret_cast<uint4*>(a.y_bf16 + m * COUT + c0);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * q], v[8 * q + 1]);
+                            __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+                            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
+                            __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+                            uint4 pk;
+                            pk.x = *reinterpret_cast<uint32_t*>(&p0);
+                            pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&p2);
+                            pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                            op[q] = pk;
+                        }
+                    }
+                }
+            }
+            if (SKIP) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < COUT; c0 += 32) {
+                    float v[32];
+                    tc::tmem_ld32(t_conv + COUT + c0, v);
+                    if (live) {
+                        float4* op = reinterpret_cast<float4*>(a.idt_out + m * COUT + c0);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            op[q] = make_float4(v[4 * q] + s_bias[COUT + c0 + 4 * q], v[4 * q + 1] + s_bias[COUT + c0 + 4 * q + 1],
+                                                v[4 * q + 2] + s_bias[COUT + c0 + 4 * q + 2], v[4 * q + 3] + s_bias[COUT + c0 + 4 * q + 3]);
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            tc::mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ----------------------------------------------------------------------------------------------
+// stem on CUDA cores, bf16 NHWC output for the tensor-core layers; head (GAP + Linear)
+// ----------------------------------------------------------------------------------------------
+constexpr int kStemRowsB = 94, kStemPitchB = 106, kPoolHB = 22, kPoolWB = 25;
+
+__global__ void __launch_bounds__(256)
+stem_bf16_kernel(const float* __restrict__ feat, const float* __restrict__ w /*[49][32] folded, bf16-rounded*/,
+                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ x0 /*[B][22][25][32]*/) {
+    extern __shared__ __align__(16) float sm[];
+    float* tile = sm;
+    float* ws = sm + kStemRowsB * kStemPitchB;
+    const int tid = threadIdx.x;
+    const int64_t b = blockIdx.x;
+    const float* f = feat + b * (int64_t)kFeatElem;
+    for (int i = tid; i < kStemRowsB * kStemPitchB; i += 256) {
+        const int r = i / kStemPitchB - 3, c = i % kStemPitchB - 3;
+        // operands are rounded to bf16 like every other layer's (fp32 accumulate)
+        tile[i] = (r >= 0 && r < kFeat && c >= 0 && c < kFrames) ? __bfloat162float(__float2bfloat16_rn(f[r * kFrames + c])) : 0.f;
+    }
+    for (int i = tid; i < 49 * 32; i += 256) ws[i] = w[i];
+    __syncthreads();
+    for (int item = tid; item < kPoolHB * kPoolWB * 4; item += 256) {
+        const int cg = item & 3, pos = item >> 2;
+        const int py = pos / kPoolWB, px = pos - py * kPoolWB;
+        float acc[4][8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[q][k] = 0.f;
+        const float* bp = tile + (4 * py) * kStemPitchB + 4 * px;
+#pragma unroll 1
+        for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll
+            for (int kx = 0; kx < 7; ++kx) {
+                const float* p = bp + ky * kStemPitchB + kx;
+                const float v00 = p[0], v01 = p[2], v10 = p[2 * kStemPitchB], v11 = p[2 * kStemPitchB + 2];
+                const float4 wa = *reinterpret_cast<const float4*>(ws + (ky * 7 + kx) * 32 + cg * 8);
+                const float4 wb = *reinterpret_cast<const float4*>(ws + (ky * 7 + kx) * 32 + cg * 8 + 4);
+                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    acc[0][k] = fmaf(v00, wv[k], acc[0][k]);
+                    acc[1][k] = fmaf(v01, wv[k], acc[1][k]);
+                    acc[2][k] = fmaf(v10, wv[k], acc[2][k]);
+                    acc[3][k] = fmaf(v11, wv[k], acc[3][k]);
+                }
+            }
+        }
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            o[k] = fmaxf(fmaxf(fmaxf(acc[0][k], acc[1][k]), fmaxf(acc[2][k], acc[3][k])) + bias[cg * 8 + k], 0.f);
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&p0);
+        pk.y = *reinterpret_cast<uint32_t*>(&p1);
+        pk.z = *reinterpret_cast<uint32_t*>(&p2);
+        pk.w = *reinterpret_cast<uint32_t*>(&p3);
+        *reinterpret_cast<uint4*>(x0 + ((b * (kPoolHB * kPoolWB) + pos) * 32 + cg * 8)) = pk;
+    }
+}
+
+// AdaptiveAvgPool2d(1) + Flatten + Linear(128 -> 2); x2 is [B][42][128] fp32; fixed summation order
+__global__ void __launch_bounds__(128)
+head_kernel(const float* __restrict__ x2, const float* __restrict__ fcw, const float* __restrict__ fcb,
+            float* __restrict__ logits, int B) {
+    __shared__ float part[2][4];
+    const int b = blockIdx.x, c = threadIdx.x;
+    const float* p = x2 + (int64_t)b * 42 * 128 + c;
+    float s = 0.f;
+#pragma unroll 6
+    for (int i = 0; i < 42; ++i) s += p[i * 128];
+    s *= (1.0f / 42.0f);
+    float a0 = s * fcw[c], a1 = s * fcw[128 + c];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if ((c & 31) == 0) {
+        part[0][c >> 5] = a0;
+        part[1][c >> 5] = a1;
+    }
+    __syncthreads();
+    if (c < 2) logits[(int64_t)b * 2 + c] = ((part[c][0] + part[c][1]) + (part[c][2] + part[c][3])) + fcb[c];
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+struct TcWeights {                 // device pointers into h->d_wblob_bf16 (bf16 parts) and a float blob
+    __nv_bfloat16 *b0c1, *b0sk, *b0c2, *b1c1, *b1sk, *b1c2;
+    float *stem_w, *stem_b, *b0c1_b, *b0sk_b, *b0c2_b, *b1c1_b, *b1sk_b, *b1c2_b, *fc_w, *fc_b;
+};
+static TcWeights g_tcw[64];        // per device index
+
+static float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// folded weights [tap][cin][cout] fp32 -> [kc][cout rows x 128 B] bf16, SWIZZLE_128B K-major, K padded to 64
+static void pack_weights(const std::vector<float>& wf, int taps, int cin, int cout, std::vector<__nv_bfloat16>& out) {
+    const int ktot = taps * cin, nkc = (ktot + 63) / 64;
+    out.assign((size_t)nkc * cout * 64, __float2bfloat16_rn(0.f));
+    for (int n = 0; n < cout; ++n)
+        for (int k = 0; k < ktot; ++k) {
+            const int kc = k / 64, kk = k % 64, ch = kk / 8, e = kk % 8;
+            const size_t off = (size_t)kc * cout * 64 + (size_t)n * 64 + (size_t)((ch ^ (n & 7)) * 8) + e;
+            out[off] = __float2bfloat16_rn(wf[(size_t)k * cout + n]);      // k = tap*cin + ci
+        }
+}
+
+template <int CIN, int COUT, int HIN, int WIN, int STRIDE, bool SKIP, bool RESID, bool OUT_F32>
+static cudaError_t tc_attr() {
+    return cudaFuncSetAttribute(conv3x3_tc_kernel<CIN, COUT, HIN, WIN, STRIDE, SKIP, RESID, OUT_F32>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcShape<CIN, COUT>::SMEM);
+}
+
+static constexpr size_t kStemSmemB = (size_t)(kStemRowsB * kStemPitchB + 49 * 32) * 4;
+
+int init_cnn_tc(cd_handle* h) {
+    CD_CUDA(h, (tc_attr<32, 64, 22, 25, 2, true, false, false>()));
+    CD_CUDA(h, (tc_attr<64, 64, 11, 13, 1, false, true, false>()));
+    CD_CUDA(h, (tc_attr<64, 128, 11, 13, 2, true, false, false>()));
+    CD_CUDA(h, (tc_attr<128, 128, 6, 7, 1, false, true, true>()));
+    CD_CUDA(h, cudaFuncSetAttribute(stem_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStemSmemB));
+    CD_CUDA(h, cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return CD_OK;
 }
-size_t cnn_tc_ws_bytes(int64_t) { return 0; }
-int launch_cnn_tc(cd_handle* h, const float*, int64_t, float*, cudaStream_t) {
-    return set_err(h, CD_E_STATE, "CD_PRECISION_BF16 (tcgen05 path) is not built in this version");
+
+// wf/bf: [stem, b0c1, b0sk, b0c2, b1c1, b1sk, b1c2, fc] folded fp32, conv weights as [tap][cin][cout]
+int upload_cnn_tc(cd_handle* h, const std::vector<std::vector<float>>& wf, const std::vector<std::vector<float>>& bf) {
+    if (h->device >= 64) return set_err(h, CD_E_ARG, "device index >= 64");
+    std::vector<__nv_bfloat16> packs[6];
+    const int spec[6][3] = {{9, 32, 64}, {1, 32, 64}, {9, 64, 64}, {9, 64, 128}, {1, 64, 128}, {9, 128, 128}};
+    size_t total_bf = 0;
+    for (int i = 0; i < 6; ++i) {
+        pack_weights(wf[1 + i], spec[i][0], spec[i][1], spec[i][2], packs[i]);
+        total_bf += (packs[i].size() + 63) & ~size_t(63);
+    }
+    std::vector<float> stem_w(49 * 32);
+    for (int i = 0; i < 49 * 32; ++i) stem_w[i] = bf16_round(wf[0][i]);
+    std::vector<float> fblob;
+    auto push = [&](const std::vector<float>& v) {
+        size_t off = fblob.size();
+        fblob.insert(fblob.end(), v.begin(), v.end());
+        while (fblob.size() % 4) fblob.push_back(0.f);
+        return off;
+    };
+    const size_t o_stem_w = push(stem_w), o_stem_b = push(bf[0]), o_b0c1 = push(bf[1]), o_b0sk = push(bf[2]),
+                 o_b0c2 = push(bf[3]), o_b1c1 = push(bf[4]), o_b1sk = push(bf[5]), o_b1c2 = push(bf[6]),
+                 o_fcw = push(wf[7]), o_fcb = push(bf[7]);
+    const size_t bf_bytes = total_bf * sizeof(__nv_bfloat16), f_bytes = fblob.size() * sizeof(float);
+    if (!h->d_wblob_bf16) CD_CUDA(h, cudaMalloc(&h->d_wblob_bf16, bf_bytes + f_bytes));
+    std::vector<unsigned char> host(bf_bytes + f_bytes, 0);
+    __nv_bfloat16* dptr[6];
+    size_t off = 0;
+    for (int i = 0; i < 6; ++i) {
+        memcpy(host.data() + off * 2, packs[i].data(), packs[i].size() * 2);
+        dptr[i] = h->d_wblob_bf16 + off;
+        off += (packs[i].size() + 63) & ~size_t(63);
+    }
+    memcpy(host.data() + bf_bytes, fblob.data(), f_bytes);
+    CD_CUDA(h, cudaMemcpy(h->d_wblob_bf16, host.data(), host.size(), cudaMemcpyHostToDevice));
+    float* fbase = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(h->d_wblob_bf16) + bf_bytes);
+    TcWeights& W = g_tcw[h->device];
+    W.b0c1 = dptr[0]; W.b0sk = dptr[1]; W.b0c2 = dptr[2]; W.b1c1 = dptr[3]; W.b1sk = dptr[4]; W.b1c2 = dptr[5];
+    W.stem_w = fbase + o_stem_w; W.stem_b = fbase + o_stem_b; W.b0c1_b = fbase + o_b0c1; W.b0sk_b = fbase + o_b0sk;
+    W.b0c2_b = fbase + o_b0c2; W.b1c1_b = fbase + o_b1c1; W.b1sk_b = fbase + o_b1sk; W.b1c2_b = fbase + o_b1c2;
+    W.fc_w = fbase + o_fcw; W.fc_b = fbase + o_fcb;
+    return CD_OK;
+}
+
+// per-clip workspace (bytes): x0 bf16, h1 bf16, idt1 f32, x1 bf16, h2 bf16, idt2 f32, x2 f32
+constexpr int64_t kTcX0 = 22 * 25 * 32 * 2, kTcH1 = 143 * 64 * 2, kTcI1 = 143 * 64 * 4, kTcH2 = 42 * 128 * 2,
+                  kTcI2 = 42 * 128 * 4, kTcX2 = 42 * 128 * 4;
+constexpr int64_t kTcPerClip = kTcX0 + 2 * kTcH1 + kTcI1 + kTcH2 + kTcI2 + kTcX2;
+constexpr int64_t kTcChunk = 2048;
+
+size_t cnn_tc_ws_bytes(int64_t B) {
+    const int64_t n = B < kTcChunk ? B : kTcChunk;
+    return (size_t)(n * kTcPerClip) + 1024;
+}
+
+template <int CIN, int COUT, int HIN, int WIN, int STRIDE, bool SKIP, bool RESID, bool OUT_F32>
+static void launch_tc(cd_handle* h, const TcArgs& a, cudaStream_t s) {
+    constexpr int HOUT = (HIN - 1) / STRIDE + 1, WOUT = (WIN - 1) / STRIDE + 1;
+    const int64_t M = (int64_t)a.B * HOUT * WOUT;
+    const int tiles = (int)((M + 127) / 128);
+    const int grid = tiles < h->sm_count ? tiles : h->sm_count;
+    conv3x3_tc_kernel<CIN, COUT, HIN, WIN, STRIDE, SKIP, RESID, OUT_F32>
+        <<<grid, kTcThreads, TcShape<CIN, COUT>::SMEM, s>>>(a);
+    h->launches += 1;
+}
+
+int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, cudaStream_t s) {
+    if (B == 0) return CD_OK;
+    const TcWeights& W = g_tcw[h->device];
+    for (int64_t c0 = 0; c0 < B; c0 += kTcChunk) {
+        const int n = (int)((B - c0) < kTcChunk ? (B - c0) : kTcChunk);
+        unsigned char* p = reinterpret_cast<unsigned char*>(h->d_ws);
+        auto carve = [&](int64_t bytes) {
+            unsigned char* r = p;
+            p += (bytes * n + 255) & ~int64_t(255);
+            return r;
+        };
+        __nv_bfloat16* x0 = reinterpret_cast<__nv_bfloat16*>(carve(kTcX0));
+        __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(carve(kTcH1));
+        float* i1 = reinterpret_cast<float*>(carve(kTcI1));
+        __nv_bfloat16* x1 = reinterpret_cast<__nv_bfloat16*>(carve(kTcH1));
+        __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(carve(kTcH2));
+        float* i2 = reinterpret_cast<float*>(carve(kTcI2));
+        float* x2 = reinterpret_cast<float*>(carve(kTcX2));
+        stem_bf16_kernel<<<n, 256, kStemSmemB, s>>>(d_feat + c0 * kFeatElem, W.stem_w, W.stem_b, x0);
+        h->launches += 1;
+        TcArgs a{};
+        a.B = n;
+        a.x = x0; a.w = W.b0c1; a.wskip = W.b0sk; a.bias = W.b0c1_b; a.bias_skip = W.b0sk_b; a.y_bf16 = h1; a.idt_out = i1;
+        launch_tc<32, 64, 22, 25, 2, true, false, false>(h, a, s);
+        a = TcArgs{};
+        a.B = n;
+        a.x = h1; a.w = W.b0c2; a.bias = W.b0c2_b; a.idt_in = i1; a.y_bf16 = x1;
+        launch_tc<64, 64, 11, 13, 1, false, true, false>(h, a, s);
+        a = TcArgs{};
+        a.B = n;
+        a.x = x1; a.w = W.b1c1; a.wskip = W.b1sk; a.bias = W.b1c1_b; a.bias_skip = W.b1sk_b; a.y_bf16 = h2; a.idt_out = i2;
+        launch_tc<64, 128, 11, 13, 2, true, false, false>(h, a, s);
+        a = TcArgs{};
+        a.B = n;
+        a.x = h2; a.w = W.b1c2; a.bias = W.b1c2_b; a.idt_in = i2; a.y_f32 = x2;
+        launch_tc<128, 128, 6, 7, 1, false, true, true>(h, a, s);
+        head_kernel<<<n, 128, 0, s>>>(x2, W.fc_w, W.fc_b, d_logits + c0 * CD_N_CLASSES, n);
+        h->launches += 1;
+        CD_CUDA(h, cudaGetLastError());
+    }
+    return CD_OK;
+}
+
+// D = A * B^T for 128 x K by N x K bf16-rounded inputs (host fp32 in/out); exercises descriptor encodings
+int umma_selftest(cd_handle* h, int N, int K, const float* hA, const float* hB, float* hD) {
+    if (N < 16 || N > 256 || N % 16 || K < 64 || K % 64 || (size_t)(128 + N) * K * 2 + 2048 > 200 * 1024)
+        return set_err(h, CD_E_ARG, "umma_selftest: need N in [16,256] step 16, K multiple of 64, tiles within 200 KB");
+    std::vector<__nv_bfloat16> a((size_t)128 * K), b((size_t)N * K);
+    for (size_t i = 0; i < a.size(); ++i) a[i] = __float2bfloat16_rn(hA[i]);
+    for (size_t i = 0; i < b.size(); ++i) b[i] = __float2bfloat16_rn(hB[i]);
+    __nv_bfloat16 *dA = nullptr, *dB = nullptr;
+    float* dD = nullptr;
+    CD_CUDA(h, cudaMalloc(&dA, a.size() * 2));
+    CD_CUDA(h, cudaMalloc(&dB, b.size() * 2));
+    CD_CUDA(h, cudaMalloc(&dD, (size_t)128 * N * 4));
+    CD_CUDA(h, cudaMemcpy(dA, a.data(), a.size() * 2, cudaMemcpyHostToDevice));
+    CD_CUDA(h, cudaMemcpy(dB, b.data(), b.size() * 2, cudaMemcpyHostToDevice));
+    umma_selftest_kernel<<<1, 128, (size_t)(128 + N) * K * 2 + 2048>>>(dA, dB, dD, N, K);
+    h->launches += 1;
+    CD_CUDA(h, cudaGetLastError());
+    CD_CUDA(h, cudaDeviceSynchronize());
+    CD_CUDA(h, cudaMemcpy(hD, dD, (size_t)128 * N * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dA);
+    cudaFree(dB);
+    cudaFree(dD);
+    return CD_OK;
 }
 
 }  // namespace cd

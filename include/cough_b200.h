@@ -155,6 +155,11 @@ int cd_e2e_forward_stream(cd_handle* h, const float* d_audio, int64_t n_samples,
 int cd_e2e_forward_host(cd_handle* h, const float* h_audio, int64_t B, float* h_logits,
                         int precision);
 
+/* Diagnostic: D[128 x N] = A[128 x K] * B[N x K]^T on one tcgen05 tile through the same shared-memory /
+ * instruction descriptors the convolution kernels use (operands rounded to bf16, fp32 accumulate).
+ * Host pointers; N multiple of 16 in [16, 256], K multiple of 64.  Synchronous. */
+int cd_selftest_umma(cd_handle* h, int N, int K, const float* h_A, const float* h_B, float* h_D);
+
 /* Number of kernels this handle has launched since creation (the bench's gpu_launches). */
 int64_t cd_launch_count(const cd_handle* h);
 
