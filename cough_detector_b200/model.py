@@ -19,7 +19,7 @@ import torch.nn as nn
 from . import _lib
 
 #: precision used when a model does not say otherwise: "bf16" (tcgen05 tensor cores) or "fp32" (CUDA cores)
-DEFAULT_PRECISION = "fp32"
+DEFAULT_PRECISION = "bf16"
 _PREC = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16}
 
 

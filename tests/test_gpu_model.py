@@ -140,7 +140,7 @@ def test_engine_checkpoint_roundtrip_and_chunk_loop():
             CoughDetectorInference(path, device="cuda", verbose=False)
 
 
-@pytest.mark.parametrize("n,k", [(64, 64), (64, 320), (128, 576), (256, 128), (16, 64)])
+@pytest.mark.parametrize("n,k", [(64, 64), (64, 320), (128, 512), (256, 128), (32, 64)])
 def test_tcgen05_tile_selftest_bf16(n, k):
     """One UMMA tile through the conv kernels' descriptor / swizzle helpers vs a float matmul of bf16-rounded operands."""
     g = torch.Generator().manual_seed(n * 1000 + k)
@@ -148,4 +148,5 @@ def test_tcgen05_tile_selftest_bf16(n, k):
     b = torch.randn(n, k, generator=g)
     d = _lib.get_handle(0).selftest_umma(a, b)
     ref = a.bfloat16().double() @ b.bfloat16().double().t()
-    assert (d.double() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+    err, scale = (d.double() - ref).abs().max().item(), ref.abs().max().item()
+    assert err <= 2e-3 * scale
