@@ -41,6 +41,7 @@ int init_cnn_tc(cd_handle* h);
 int upload_cnn_tc(cd_handle* h, const std::vector<std::vector<float>>& wf, const std::vector<std::vector<float>>& bf);
 int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, cudaStream_t s);
 size_t cnn_tc_ws_bytes(int64_t B);
+__nv_bfloat16* cnn_tc_map_ptr(cd_handle* h);
 void get_host_tables(float* hann, float* fb, float* dct);
 int umma_selftest(cd_handle* h, int N, int K, const float* hA, const float* hB, float* hD);
 
@@ -163,7 +164,7 @@ int cd_feat_forward(cd_handle* h, const float* d_audio, int64_t stride, int64_t 
         return set_err(h, CD_E_ARG, "cd_feat_forward: bad argument (need stride >= 16000, non-NULL buffers)");
     DeviceGuard g(h->device);
     const int mode = kModeFixed | ((flags & CD_FEAT_NORMALIZE) ? 0 : kModeNoNormalize);
-    return launch_features(h, d_audio, nullptr, nullptr, stride, mode, B, d_feat, (cudaStream_t)stream);
+    return launch_features(h, d_audio, nullptr, nullptr, stride, mode, B, d_feat, nullptr, (cudaStream_t)stream);
 }
 
 int cd_feat_forward_var(cd_handle* h, const float* d_audio, const int64_t* d_offsets, const int32_t* d_lengths,
@@ -172,7 +173,7 @@ int cd_feat_forward_var(cd_handle* h, const float* d_audio, const int64_t* d_off
     if (B < 0 || (B > 0 && (!d_audio || !d_offsets || !d_lengths || !d_feat)))
         return set_err(h, CD_E_ARG, "cd_feat_forward_var: bad argument");
     DeviceGuard g(h->device);
-    return launch_features(h, d_audio, d_offsets, d_lengths, 0, kModeVar, B, d_feat, (cudaStream_t)stream);
+    return launch_features(h, d_audio, d_offsets, d_lengths, 0, kModeVar, B, d_feat, nullptr, (cudaStream_t)stream);
 }
 
 int cd_feat_forward_stream(cd_handle* h, const float* d_audio, int64_t n_samples, int64_t hop, int64_t n_windows,
@@ -181,7 +182,7 @@ int cd_feat_forward_stream(cd_handle* h, const float* d_audio, int64_t n_samples
     if (hop <= 0 || n_windows != cd_stream_windows(n_samples, hop) || (n_windows > 0 && (!d_audio || !d_feat)))
         return set_err(h, CD_E_ARG, "cd_feat_forward_stream: hop must be > 0 and n_windows == cd_stream_windows()");
     DeviceGuard g(h->device);
-    return launch_features(h, d_audio, nullptr, nullptr, hop, kModeStream, n_windows, d_feat, (cudaStream_t)stream);
+    return launch_features(h, d_audio, nullptr, nullptr, hop, kModeStream, n_windows, d_feat, nullptr, (cudaStream_t)stream);
 }
 
 // ---- model -----------------------------------------------------------------------------------
@@ -282,20 +283,24 @@ static int e2e_impl(cd_handle* h, const float* d_audio, int64_t stride_or_hop, i
                     float* d_feat_opt, int precision, cudaStream_t s) {
     if (!h->weights_loaded) return set_err(h, CD_E_STATE, "cd_e2e_forward: call cd_cnn_load first");
     if (B == 0) return CD_OK;
-    // process in slabs so features of a slab stay L2-resident between the two stages
-    const int64_t slab = d_feat_opt ? B : 2048;
-    const size_t cnn_ws = precision == CD_PRECISION_FP32 ? cnn_fp32_ws_bytes(slab) : cnn_tc_ws_bytes(slab);
-    const size_t feat_bytes = d_feat_opt ? 0 : (size_t)slab * kFeatElem * sizeof(float);
+    // process in slabs so a slab's features stay L2-resident between the two stages.  bf16: the
+    // feature kernel writes the stem's bf16 map straight into the CNN workspace (fp32 features only
+    // if the caller asked for them); fp32: features go through an fp32 buffer.
+    const int64_t slab = 2048;
+    const bool tcp = precision == CD_PRECISION_BF16;
+    const size_t cnn_ws = tcp ? cnn_tc_ws_bytes(slab) : cnn_fp32_ws_bytes(slab);
+    const size_t feat_bytes = (tcp || d_feat_opt) ? 0 : (size_t)slab * kFeatElem * sizeof(float);
     int rc = ensure_ws(h, cnn_ws + feat_bytes);
     if (rc != CD_OK) return rc;
     for (int64_t b0 = 0; b0 < B; b0 += slab) {
         const int64_t n = (B - b0) < slab ? (B - b0) : slab;
         float* feat = d_feat_opt ? d_feat_opt + b0 * kFeatElem
-                                 : reinterpret_cast<float*>(reinterpret_cast<char*>(h->d_ws) + cnn_ws);
-        rc = launch_features(h, d_audio + b0 * stride_or_hop, nullptr, nullptr, stride_or_hop, mode, n, feat, s);
+                                 : (tcp ? nullptr : reinterpret_cast<float*>(reinterpret_cast<char*>(h->d_ws) + cnn_ws));
+        rc = launch_features(h, d_audio + b0 * stride_or_hop, nullptr, nullptr, stride_or_hop, mode, n, feat,
+                             tcp ? cnn_tc_map_ptr(h) : nullptr, s);
         if (rc != CD_OK) return rc;
-        rc = precision == CD_PRECISION_FP32 ? launch_cnn_fp32(h, feat, n, d_logits + b0 * CD_N_CLASSES, s)
-                                            : launch_cnn_tc(h, feat, n, d_logits + b0 * CD_N_CLASSES, s);
+        rc = tcp ? launch_cnn_tc(h, nullptr, n, d_logits + b0 * CD_N_CLASSES, s)
+                 : launch_cnn_fp32(h, feat, n, d_logits + b0 * CD_N_CLASSES, s);
         if (rc != CD_OK) return rc;
     }
     return CD_OK;
@@ -351,10 +356,11 @@ int cd_e2e_forward_host(cd_handle* h, const float* h_audio, int64_t B, float* h_
         h->pipe_logits_cap = B;
     }
     // is the caller's buffer pinned?  (pageable memory is staged by the driver; still correct)
-    const size_t cnn_ws = precision == CD_PRECISION_FP32 ? cnn_fp32_ws_bytes(chunk) : cnn_tc_ws_bytes(chunk);
-    int rc = ensure_ws(h, cnn_ws + (size_t)chunk * kFeatElem * sizeof(float));
+    const bool tcp = precision == CD_PRECISION_BF16;
+    const size_t cnn_ws = tcp ? cnn_tc_ws_bytes(chunk) : cnn_fp32_ws_bytes(chunk);
+    int rc = ensure_ws(h, cnn_ws + (tcp ? 0 : (size_t)chunk * kFeatElem * sizeof(float)));
     if (rc != CD_OK) return rc;
-    float* feat = reinterpret_cast<float*>(reinterpret_cast<char*>(h->d_ws) + cnn_ws);
+    float* feat = tcp ? nullptr : reinterpret_cast<float*>(reinterpret_cast<char*>(h->d_ws) + cnn_ws);
     int k = 0;
     cudaEvent_t prev_compute = nullptr;
     for (int64_t b0 = 0; b0 < B; b0 += chunk, k = (k + 1) % 3) {
@@ -363,10 +369,11 @@ int cd_e2e_forward_host(cd_handle* h, const float* h_audio, int64_t B, float* h_
         CD_CUDA(h, cudaMemcpyAsync(h->dev_in[k], h_audio + b0 * kSeg, (size_t)n * kSeg * sizeof(float),
                                    cudaMemcpyHostToDevice, s));
         if (prev_compute) CD_CUDA(h, cudaStreamWaitEvent(s, prev_compute, 0));   // shared workspace
-        rc = launch_features(h, h->dev_in[k], nullptr, nullptr, kSeg, kModeFixed, n, feat, s);
+        rc = launch_features(h, h->dev_in[k], nullptr, nullptr, kSeg, kModeFixed, n, feat,
+                             tcp ? cnn_tc_map_ptr(h) : nullptr, s);
         if (rc != CD_OK) return rc;
-        rc = precision == CD_PRECISION_FP32 ? launch_cnn_fp32(h, feat, n, h->dev_logits + b0 * CD_N_CLASSES, s)
-                                            : launch_cnn_tc(h, feat, n, h->dev_logits + b0 * CD_N_CLASSES, s);
+        rc = tcp ? launch_cnn_tc(h, nullptr, n, h->dev_logits + b0 * CD_N_CLASSES, s)
+                 : launch_cnn_fp32(h, feat, n, h->dev_logits + b0 * CD_N_CLASSES, s);
         if (rc != CD_OK) return rc;
         CD_CUDA(h, cudaEventRecord(h->pipe_events[k], s));
         prev_compute = h->pipe_events[k];

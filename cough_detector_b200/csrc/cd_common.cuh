@@ -22,6 +22,10 @@ constexpr int kFeatElem = CD_FEAT_ELEMS; // 9090
 constexpr int kNfft     = 512;
 constexpr int kWin      = 400;
 constexpr int kHop      = 160;
+// bf16 copy of the features as the stem consumes it: rows -3..89, cols -3..108, zero padded
+constexpr int kMapRows  = 93;
+constexpr int kMapPitch = 112;
+constexpr int kMapElems = kMapRows * kMapPitch;   // 10 416 bf16 = 20 832 B per clip
 
 // mel contraction as executed by a lane: slots 0..2 = band `lane` (<= 3 taps for bands 0..31),
 // slots 3..10 = band `lane+32` (<= 8 taps).  idx is the bin index minus 4 (0..123).
@@ -92,7 +96,7 @@ int ensure_ws(cd_handle* h, size_t bytes);
 
 // kernels' host launchers (each returns a CD_* code and bumps h->launches)
 int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets, const int32_t* d_lengths,
-                    int64_t stride_or_hop, int mode, int64_t B, float* d_feat, cudaStream_t s);
+                    int64_t stride_or_hop, int mode, int64_t B, float* d_feat, __nv_bfloat16* d_map, cudaStream_t s);
 int launch_cnn_fp32(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, cudaStream_t s);
 size_t cnn_fp32_ws_bytes(int64_t B);
 

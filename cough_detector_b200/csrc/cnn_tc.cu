@@ -431,66 +431,178 @@ conv3x3_tc_kernel(const TcArgs a) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// stem on CUDA cores, bf16 NHWC output for the tensor-core layers; head (GAP + Linear)
+// stem on tcgen05: 7x7/s2 conv (1 -> 32) + bias + ReLU + MaxPool2d(2) as ONE GEMM per pooled pixel
 // ----------------------------------------------------------------------------------------------
-constexpr int kStemRowsB = 94, kStemPitchB = 106, kPoolHB = 22, kPoolWB = 25;
+// Row m = (clip, pooled pixel (py, px)), 550 per clip.  The 2x2 pool window's four conv outputs
+// share a 9 x 9 input patch (rows 4py-3.., cols 4px-3..), so N = 4 pool members x 32 channels = 128
+// and K = 9 patch rows x 16 columns (9 used, 7 zero-weight) = 144: the max-pool becomes an
+// in-register max over four 32-column groups of the accumulator row, and the un-pooled
+// (32, 45, 51) activation never exists.  A rows are 9 contiguous 32-byte runs of the clip's
+// zero-padded bf16 feature map (kMapRows x kMapPitch), staged per clip with one bulk copy.
+constexpr int kStemPix = 22 * 25;                 // 550 pooled pixels per clip
+constexpr int kStemTilesPerClip = 5;              // 4 x 128 + 38
+constexpr int kStemABytes = 3 * 16384;            // 3 K-chunks of 128 rows x 128 B (third: 32 B per row used)
+constexpr int kStemBBytes = 3 * 16384;            // 128 weight rows x 3 chunks
+constexpr int kMapBytes = kMapElems * 2;          // 20 832
+constexpr int kMapBytesPad = (kMapBytes + 127) & ~127;
+constexpr size_t kStemSmem = 1024 + 2 * kStemABytes + kStemBBytes + 2 * kMapBytesPad + 128;
 
-__global__ void __launch_bounds__(256)
-stem_bf16_kernel(const float* __restrict__ feat, const float* __restrict__ w /*[49][32] folded, bf16-rounded*/,
-                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ x0 /*[B][22][25][32]*/) {
-    extern __shared__ __align__(16) float sm[];
-    float* tile = sm;
-    float* ws = sm + kStemRowsB * kStemPitchB;
-    const int tid = threadIdx.x;
-    const int64_t b = blockIdx.x;
-    const float* f = feat + b * (int64_t)kFeatElem;
-    for (int i = tid; i < kStemRowsB * kStemPitchB; i += 256) {
-        const int r = i / kStemPitchB - 3, c = i % kStemPitchB - 3;
-        // operands are rounded to bf16 like every other layer's (fp32 accumulate)
-        tile[i] = (r >= 0 && r < kFeat && c >= 0 && c < kFrames) ? __bfloat162float(__float2bfloat16_rn(f[r * kFrames + c])) : 0.f;
+__global__ void __launch_bounds__(kTcThreads, 1)
+stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __restrict__ wq,
+               const float* __restrict__ bias, __nv_bfloat16* __restrict__ x0, int B) {
+    extern __shared__ unsigned char raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* sA = base;                                   // [2][3][16384]
+    unsigned char* sB = base + 2 * kStemABytes;                 // [3][16384]
+    unsigned char* sMap = sB + kStemBBytes;                     // [2][kMapBytesPad]
+    float* s_bias = reinterpret_cast<float*>(sMap + 2 * kMapBytesPad);
+    __shared__ uint64_t full_bar[2], empty_bar[2], tfull_bar[2], tempty_bar[2], map_bar[2], w_bar;
+    __shared__ uint32_t tmem_base_s;
+    constexpr uint32_t IDESC = tc::idesc_bf16(128, 128);
+    constexpr int TMEM_COLS = 256;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&full_bar[i], kTcProducers);
+            tc::mbar_init(&empty_bar[i], 1);
+            tc::mbar_init(&tfull_bar[i], 1);
+            tc::mbar_init(&tempty_bar[i], kTcEpilogue);
+            tc::mbar_init(&map_bar[i], 1);
+        }
+        tc::mbar_init(&w_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < 49 * 32; i += 256) ws[i] = w[i];
+    if (tid < 32) s_bias[tid] = bias[tid];
+    if (warp == 4) tc::tmem_alloc(&tmem_base_s, TMEM_COLS);
+    tc::tc_fence_before();
     __syncthreads();
-    for (int item = tid; item < kPoolHB * kPoolWB * 4; item += 256) {
-        const int cg = item & 3, pos = item >> 2;
-        const int py = pos / kPoolWB, px = pos - py * kPoolWB;
-        float acc[4][8];
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp < 4) {
+        // ======================= producers ===========================================================
+        if (tid == 0) {
+            tc::mbar_arrive_expect_tx(&w_bar, kStemBBytes);
+            tc::bulk_g2s(sB, wq, kStemBBytes, &w_bar);
+            tc::mbar_arrive_expect_tx(&map_bar[0], kMapBytes);
+            tc::bulk_g2s(sMap, maps + (int64_t)blockIdx.x * kMapElems, kMapBytes, &map_bar[0]);
+        }
+        int it = 0, ci = 0;
+        for (int clip = blockIdx.x; clip < B; clip += gridDim.x, ++ci) {
+            const int mb = ci & 1;
+            if (tid == 0 && clip + (int)gridDim.x < B) {       // prefetch the next clip's map
+                tc::mbar_arrive_expect_tx(&map_bar[mb ^ 1], kMapBytes);
+                tc::bulk_g2s(sMap + (mb ^ 1) * kMapBytesPad, maps + (int64_t)(clip + gridDim.x) * kMapElems, kMapBytes,
+                             &map_bar[mb ^ 1]);
+            }
+            tc::mbar_wait(&map_bar[mb], (uint32_t)((ci >> 1) & 1));
+            const unsigned char* map = sMap + mb * kMapBytesPad;
+            for (int t = 0; t < kStemTilesPerClip; ++t, ++it) {
+                const int s = it & 1;
+                tc::mbar_wait(&empty_bar[s], (uint32_t)(((it >> 1) & 1) ^ 1));
+                const int pix = t * 128 + tid;
+                if (pix < kStemPix) {
+                    const int py = pix / 25, px = pix - py * 25;
+                    const unsigned char* src = map + (4 * py) * (kMapPitch * 2) + px * 8;
+                    unsigned char* dstA = sA + s * kStemABytes;
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+                    for (int ry = 0; ry < 9; ++ry) {
+                        const uint2* q = reinterpret_cast<const uint2*>(src + ry * (kMapPitch * 2));
+                        const uint2 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3];
+                        unsigned char* d = dstA + (ry >> 2) * 16384;
+                        const int j0 = (ry & 3) * 2;
+                        *reinterpret_cast<uint4*>(d + tc::swz128(tid, j0)) = make_uint4(v0.x, v0.y, v1.x, v1.y);
+                        *reinterpret_cast<uint4*>(d + tc::swz128(tid, j0 + 1)) = make_uint4(v2.x, v2.y, v3.x, v3.y);
+                    }
+                }
+                tc::fence_proxy_async();
+                tc::mbar_arrive(&full_bar[s]);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // every producer is done with map[mb]
+        }
+    } else if (warp == 4) {
+        // ======================= MMA issuer ==========================================================
+        if (lane == 0) {
+            tc::mbar_wait(&w_bar, 0);
+            int it = 0;
+            for (int clip = blockIdx.x; clip < B; clip += gridDim.x) {
+                for (int t = 0; t < kStemTilesPerClip; ++t, ++it) {
+                    const int s = it & 1;
+                    tc::mbar_wait(&tempty_bar[s], (uint32_t)(((it >> 1) & 1) ^ 1));
+                    tc::mbar_wait(&full_bar[s], (uint32_t)((it >> 1) & 1));
+                    tc::tc_fence_after();
+                    const uint32_t d = tmem_base + s * 128;
+                    const uint32_t sa = tc::s32(sA + s * kStemABytes), sb = tc::s32(sB);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[q][k] = 0.f;
-        const float* bp = tile + (4 * py) * kStemPitchB + 4 * px;
-#pragma unroll 1
-        for (int ky = 0; ky < 7; ++ky) {
-#pragma unroll
-            for (int kx = 0; kx < 7; ++kx) {
-                const float* p = bp + ky * kStemPitchB + kx;
-                const float v00 = p[0], v01 = p[2], v10 = p[2 * kStemPitchB], v11 = p[2 * kStemPitchB + 2];
-                const float4 wa = *reinterpret_cast<const float4*>(ws + (ky * 7 + kx) * 32 + cg * 8);
-                const float4 wb = *reinterpret_cast<const float4*>(ws + (ky * 7 + kx) * 32 + cg * 8 + 4);
-                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    acc[0][k] = fmaf(v00, wv[k], acc[0][k]);
-                    acc[1][k] = fmaf(v01, wv[k], acc[1][k]);
-                    acc[2][k] = fmaf(v10, wv[k], acc[2][k]);
-                    acc[3][k] = fmaf(v11, wv[k], acc[3][k]);
+                    for (int q = 0; q < 9; ++q) {                // K = 144 = 9 x 16
+                        const uint32_t off = (q >> 2) * 16384 + (q & 3) * 32;
+                        tc::umma_bf16(d, tc::desc_sw128(sa + off), tc::desc_sw128(sb + off), IDESC, q != 0);
+                    }
+                    tc::tc_commit(&empty_bar[s]);
+                    tc::tc_commit(&tfull_bar[s]);
                 }
             }
         }
-        float o[8];
+    } else {
+        // ======================= epilogue: pool max over the 4 column groups, bias, ReLU, bf16 ========
+        const int lane_grp = warp & 3;
+        int it = 0;
+        for (int clip = blockIdx.x; clip < B; clip += gridDim.x) {
+            for (int t = 0; t < kStemTilesPerClip; ++t, ++it) {
+                const int s = it & 1;
+                tc::mbar_wait(&tfull_bar[s], (uint32_t)((it >> 1) & 1));
+                tc::tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + s * 128;
+                float m[32], v[32];
+                tc::tmem_ld32(taddr, m);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            o[k] = fmaxf(fmaxf(fmaxf(acc[0][k], acc[1][k]), fmaxf(acc[2][k], acc[3][k])) + bias[cg * 8 + k], 0.f);
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
-        uint4 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&p0);
-        pk.y = *reinterpret_cast<uint32_t*>(&p1);
-        pk.z = *reinterpret_cast<uint32_t*>(&p2);
-        pk.w = *reinterpret_cast<uint32_t*>(&p3);
-        *reinterpret_cast<uint4*>(x0 + ((b * (kPoolHB * kPoolWB) + pos) * 32 + cg * 8)) = pk;
+                for (int g = 1; g < 4; ++g) {
+                    tc::tmem_ld32(taddr + g * 32, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) m[i] = fmaxf(m[i], v[i]);
+                }
+                tc::tc_fence_before();
+                tc::mbar_arrive(&tempty_bar[s]);
+                const int pix = t * 128 + lane_grp * 32 + lane;
+                if (pix < kStemPix) {
+                    uint4* op = reinterpret_cast<uint4*>(x0 + ((int64_t)clip * kStemPix + pix) * 32);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int c = 8 * q + 2 * e;
+                            __nv_bfloat162 pk = __floats2bfloat162_rn(fmaxf(m[c] + s_bias[c], 0.f), fmaxf(m[c + 1] + s_bias[c + 1], 0.f));
+                            w[e] = *reinterpret_cast<uint32_t*>(&pk);
+                        }
+                        op[q] = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+        }
     }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// fp32 features (B, 90, 101) -> the stem's zero-padded bf16 map (for callers that hand features in)
+__global__ void __launch_bounds__(256)
+map_from_feat_kernel(const float* __restrict__ feat, __nv_bfloat16* __restrict__ maps, int64_t B) {
+    const int64_t b = blockIdx.y;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= kMapElems / 2) return;
+    const float* f = feat + b * (int64_t)kFeatElem;
+    const int r = (2 * i) / kMapPitch - 3, c0 = (2 * i) % kMapPitch - 3;
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int c = c0 + e;
+        v[e] = (r >= 0 && c >= 0 && c < kFrames) ? f[r * kFrames + c] : 0.f;
+    }
+    __nv_bfloat162 pk = __floats2bfloat162_rn(v[0], v[1]);
+    reinterpret_cast<uint32_t*>(maps + b * (int64_t)kMapElems)[i] = *reinterpret_cast<uint32_t*>(&pk);
 }
 
 // AdaptiveAvgPool2d(1) + Flatten + Linear(128 -> 2); x2 is [B][42][128] fp32; fixed summation order
@@ -523,7 +635,8 @@ head_kernel(const float* __restrict__ x2, const float* __restrict__ fcw, const f
 // ----------------------------------------------------------------------------------------------
 struct TcWeights {                 // device pointers into h->d_wblob_bf16 (bf16 parts) and a float blob
     __nv_bfloat16 *b0c1, *b0sk, *b0c2, *b1c1, *b1sk, *b1c2;
-    float *stem_w, *stem_b, *b0c1_b, *b0sk_b, *b0c2_b, *b1c1_b, *b1sk_b, *b1c2_b, *fc_w, *fc_b;
+    __nv_bfloat16* stem_w;
+    float *stem_b, *b0c1_b, *b0sk_b, *b0c2_b, *b1c1_b, *b1sk_b, *b1c2_b, *fc_w, *fc_b;
 };
 static TcWeights g_tcw[64];        // per device index
 
@@ -547,14 +660,12 @@ static cudaError_t tc_attr() {
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcShape<CIN, COUT>::SMEM);
 }
 
-static constexpr size_t kStemSmemB = (size_t)(kStemRowsB * kStemPitchB + 49 * 32) * 4;
-
 int init_cnn_tc(cd_handle* h) {
     CD_CUDA(h, (tc_attr<32, 64, 22, 25, 2, true, false, false>()));
     CD_CUDA(h, (tc_attr<64, 64, 11, 13, 1, false, true, false>()));
     CD_CUDA(h, (tc_attr<64, 128, 11, 13, 2, true, false, false>()));
     CD_CUDA(h, (tc_attr<128, 128, 6, 7, 1, false, true, true>()));
-    CD_CUDA(h, cudaFuncSetAttribute(stem_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStemSmemB));
+    CD_CUDA(h, cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStemSmem));
     CD_CUDA(h, cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return CD_OK;
 }
@@ -562,15 +673,25 @@ int init_cnn_tc(cd_handle* h) {
 // wf/bf: [stem, b0c1, b0sk, b0c2, b1c1, b1sk, b1c2, fc] folded fp32, conv weights as [tap][cin][cout]
 int upload_cnn_tc(cd_handle* h, const std::vector<std::vector<float>>& wf, const std::vector<std::vector<float>>& bf) {
     if (h->device >= 64) return set_err(h, CD_E_ARG, "device index >= 64");
-    std::vector<__nv_bfloat16> packs[6];
+    std::vector<__nv_bfloat16> packs[7];
     const int spec[6][3] = {{9, 32, 64}, {1, 32, 64}, {9, 64, 64}, {9, 64, 128}, {1, 64, 128}, {9, 128, 128}};
     size_t total_bf = 0;
     for (int i = 0; i < 6; ++i) {
         pack_weights(wf[1 + i], spec[i][0], spec[i][1], spec[i][2], packs[i]);
         total_bf += (packs[i].size() + 63) & ~size_t(63);
     }
-    std::vector<float> stem_w(49 * 32);
-    for (int i = 0; i < 49 * 32; ++i) stem_w[i] = bf16_round(wf[0][i]);
+    {   // stem as a pooled GEMM: W2[k = ry*16 + cx][n = (dy*2+dx)*32 + co] = w[co][ry - 2dy][cx - 2dx]
+        std::vector<float> w2((size_t)192 * 128, 0.f);
+        for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx)
+                for (int ky = 0; ky < 7; ++ky)
+                    for (int kx = 0; kx < 7; ++kx)
+                        for (int co = 0; co < 32; ++co)
+                            w2[(size_t)((2 * dy + ky) * 16 + 2 * dx + kx) * 128 + (dy * 2 + dx) * 32 + co] =
+                                wf[0][(size_t)(ky * 7 + kx) * 32 + co];
+        pack_weights(w2, 192, 1, 128, packs[6]);
+        total_bf += (packs[6].size() + 63) & ~size_t(63);
+    }
     std::vector<float> fblob;
     auto push = [&](const std::vector<float>& v) {
         size_t off = fblob.size();
@@ -578,15 +699,15 @@ int upload_cnn_tc(cd_handle* h, const std::vector<std::vector<float>>& wf, const
         while (fblob.size() % 4) fblob.push_back(0.f);
         return off;
     };
-    const size_t o_stem_w = push(stem_w), o_stem_b = push(bf[0]), o_b0c1 = push(bf[1]), o_b0sk = push(bf[2]),
+    const size_t o_stem_b = push(bf[0]), o_b0c1 = push(bf[1]), o_b0sk = push(bf[2]),
                  o_b0c2 = push(bf[3]), o_b1c1 = push(bf[4]), o_b1sk = push(bf[5]), o_b1c2 = push(bf[6]),
                  o_fcw = push(wf[7]), o_fcb = push(bf[7]);
     const size_t bf_bytes = total_bf * sizeof(__nv_bfloat16), f_bytes = fblob.size() * sizeof(float);
     if (!h->d_wblob_bf16) CD_CUDA(h, cudaMalloc(&h->d_wblob_bf16, bf_bytes + f_bytes));
     std::vector<unsigned char> host(bf_bytes + f_bytes, 0);
-    __nv_bfloat16* dptr[6];
+    __nv_bfloat16* dptr[7];
     size_t off = 0;
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < 7; ++i) {
         memcpy(host.data() + off * 2, packs[i].data(), packs[i].size() * 2);
         dptr[i] = h->d_wblob_bf16 + off;
         off += (packs[i].size() + 63) & ~size_t(63);
@@ -596,7 +717,7 @@ int upload_cnn_tc(cd_handle* h, const std::vector<std::vector<float>>& wf, const
     float* fbase = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(h->d_wblob_bf16) + bf_bytes);
     TcWeights& W = g_tcw[h->device];
     W.b0c1 = dptr[0]; W.b0sk = dptr[1]; W.b0c2 = dptr[2]; W.b1c1 = dptr[3]; W.b1sk = dptr[4]; W.b1c2 = dptr[5];
-    W.stem_w = fbase + o_stem_w; W.stem_b = fbase + o_stem_b; W.b0c1_b = fbase + o_b0c1; W.b0sk_b = fbase + o_b0sk;
+    W.stem_w = dptr[6]; W.stem_b = fbase + o_stem_b; W.b0c1_b = fbase + o_b0c1; W.b0sk_b = fbase + o_b0sk;
     W.b0c2_b = fbase + o_b0c2; W.b1c1_b = fbase + o_b1c1; W.b1sk_b = fbase + o_b1sk; W.b1c2_b = fbase + o_b1c2;
     W.fc_w = fbase + o_fcw; W.fc_b = fbase + o_fcb;
     return CD_OK;
@@ -605,13 +726,17 @@ int upload_cnn_tc(cd_handle* h, const std::vector<std::vector<float>>& wf, const
 // per-clip workspace (bytes): x0 bf16, h1 bf16, idt1 f32, x1 bf16, h2 bf16, idt2 f32, x2 f32
 constexpr int64_t kTcX0 = 22 * 25 * 32 * 2, kTcH1 = 143 * 64 * 2, kTcI1 = 143 * 64 * 4, kTcH2 = 42 * 128 * 2,
                   kTcI2 = 42 * 128 * 4, kTcX2 = 42 * 128 * 4;
-constexpr int64_t kTcPerClip = kTcX0 + 2 * kTcH1 + kTcI1 + kTcH2 + kTcI2 + kTcX2;
+constexpr int64_t kTcPerClip = kMapElems * 2 + kTcX0 + 2 * kTcH1 + kTcI1 + kTcH2 + kTcI2 + kTcX2;
 constexpr int64_t kTcChunk = 2048;
 
 size_t cnn_tc_ws_bytes(int64_t B) {
     const int64_t n = B < kTcChunk ? B : kTcChunk;
-    return (size_t)(n * kTcPerClip) + 1024;
+    return (size_t)(n * kTcPerClip) + 8 * 256;
 }
+
+// the first region of the workspace holds the bf16 maps of the current chunk: the feature kernel
+// writes them there directly in the end-to-end path
+__nv_bfloat16* cnn_tc_map_ptr(cd_handle* h) { return reinterpret_cast<__nv_bfloat16*>(h->d_ws); }
 
 template <int CIN, int COUT, int HIN, int WIN, int STRIDE, bool SKIP, bool RESID, bool OUT_F32>
 static void launch_tc(cd_handle* h, const TcArgs& a, cudaStream_t s) {
@@ -624,8 +749,11 @@ static void launch_tc(cd_handle* h, const TcArgs& a, cudaStream_t s) {
     h->launches += 1;
 }
 
+// d_feat != nullptr: features come in as fp32 and are converted chunk by chunk; d_feat == nullptr:
+// the maps of the (single, <= kTcChunk clips) chunk are already in the workspace.
 int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, cudaStream_t s) {
     if (B == 0) return CD_OK;
+    if (!d_feat && B > kTcChunk) return set_err(h, CD_E_ARG, "launch_cnn_tc: pre-filled maps hold one chunk only");
     const TcWeights& W = g_tcw[h->device];
     for (int64_t c0 = 0; c0 < B; c0 += kTcChunk) {
         const int n = (int)((B - c0) < kTcChunk ? (B - c0) : kTcChunk);
@@ -635,6 +763,7 @@ int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits,
             p += (bytes * n + 255) & ~int64_t(255);
             return r;
         };
+        __nv_bfloat16* maps = reinterpret_cast<__nv_bfloat16*>(carve(kMapElems * 2));
         __nv_bfloat16* x0 = reinterpret_cast<__nv_bfloat16*>(carve(kTcX0));
         __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(carve(kTcH1));
         float* i1 = reinterpret_cast<float*>(carve(kTcI1));
@@ -642,7 +771,11 @@ int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits,
         __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(carve(kTcH2));
         float* i2 = reinterpret_cast<float*>(carve(kTcI2));
         float* x2 = reinterpret_cast<float*>(carve(kTcX2));
-        stem_bf16_kernel<<<n, 256, kStemSmemB, s>>>(d_feat + c0 * kFeatElem, W.stem_w, W.stem_b, x0);
+        if (d_feat) {
+            map_from_feat_kernel<<<dim3((kMapElems / 2 + 255) / 256, n), 256, 0, s>>>(d_feat + c0 * kFeatElem, maps, n);
+            h->launches += 1;
+        }
+        stem_tc_kernel<<<n < h->sm_count ? n : h->sm_count, kTcThreads, kStemSmem, s>>>(maps, W.stem_w, W.stem_b, x0, n);
         h->launches += 1;
         TcArgs a{};
         a.B = n;

@@ -334,7 +334,7 @@ __device__ __forceinline__ bool bulk_ok(const ClipDesc& d) {
 __global__ void __launch_bounds__(kFeatThreads, 1)
 feat_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offs, const int32_t* __restrict__ lens,
             int64_t stride_or_hop, int mode, int64_t B, float* __restrict__ feat,
-            const FeatTables* __restrict__ tables) {
+            __nv_bfloat16* __restrict__ map_out, const FeatTables* __restrict__ tables) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FeatSmem& S = *reinterpret_cast<FeatSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -426,11 +426,11 @@ feat_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offs, c
         const float floor_db = top - 80.0f;                            // top_db = 80
 
         // ---- mel block rows 0..63: max(dB, floor) -> (dB + 80) / 80 -> clamp ------------------------
-        float* out = feat + b * (int64_t)kFeatElem;
+        float* out = feat ? feat + b * (int64_t)kFeatElem : nullptr;
         for (int i = tid; i < kMels * kFrames; i += kFeatThreads) {
             const float v = fmaxf(S.db[i], floor_db);
             S.db[i] = v;
-            out[i] = fminf(fmaxf((v + 80.0f) * 0.0125f, 0.f), 1.f);
+            if (out) out[i] = fminf(fmaxf((v + 80.0f) * 0.0125f, 0.f), 1.f);
         }
         __syncthreads();
 
@@ -457,14 +457,45 @@ feat_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offs, c
         }
         ss = block_reduce<false>(ss, S.red);
         const float inv_std = 1.0f / (sqrtf(ss * (1.0f / (kN - 1))) + 1e-8f);
-        for (int i = tid; i < kN; i += kFeatThreads) {
-            const int cidx = i / kFrames, t = i - cidx * kFrames;
-            const float* row = mf + cidx * kFrames;
-            const float x0 = (row[t] - mean) * inv_std;
-            const float xp = (row[min(t + 1, kFrames - 1)] - mean) * inv_std;
-            const float xm = (row[max(t - 1, 0)] - mean) * inv_std;
-            out[(kMels + cidx) * kFrames + t] = x0;
-            out[(kMels + kMfcc + cidx) * kFrames + t] = (xp - xm) * 0.5f;   // compute_deltas (:353-355)
+        if (out) {
+            for (int i = tid; i < kN; i += kFeatThreads) {
+                const int cidx = i / kFrames, t = i - cidx * kFrames;
+                const float* row = mf + cidx * kFrames;
+                // __fmul_rn: never contracted into an FMA, so the bf16 map below sees identical values
+                const float x0 = __fmul_rn(row[t] - mean, inv_std);
+                const float xp = __fmul_rn(row[min(t + 1, kFrames - 1)] - mean, inv_std);
+                const float xm = __fmul_rn(row[max(t - 1, 0)] - mean, inv_std);
+                out[(kMels + cidx) * kFrames + t] = x0;
+                out[(kMels + kMfcc + cidx) * kFrames + t] = (xp - xm) * 0.5f;   // compute_deltas (:353-355)
+            }
+        }
+        if (map_out) {
+            // the CNN stem's operand: the same 90 x 101 values rounded to bf16, zero padded to
+            // [93 rows: -3..89][112 cols: -3..108] so the stem stages a clip with one bulk copy
+            uint32_t* mo = reinterpret_cast<uint32_t*>(map_out + b * (int64_t)kMapElems);
+            for (int i = tid; i < kMapElems / 2; i += kFeatThreads) {
+                const int r = (2 * i) / kMapPitch - 3, c0 = (2 * i) % kMapPitch - 3;
+                float v[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = c0 + e;
+                    float x = 0.f;
+                    if (r >= 0 && c >= 0 && c < kFrames) {
+                        if (r < kMels) {
+                            x = fminf(fmaxf((S.db[r * kFrames + c] + 80.0f) * 0.0125f, 0.f), 1.f);
+                        } else if (r < kMels + kMfcc) {
+                            x = __fmul_rn(mf[(r - kMels) * kFrames + c] - mean, inv_std);
+                        } else {
+                            const float* row = mf + (r - kMels - kMfcc) * kFrames;
+                            x = (__fmul_rn(row[min(c + 1, kFrames - 1)] - mean, inv_std) -
+                                 __fmul_rn(row[max(c - 1, 0)] - mean, inv_std)) * 0.5f;
+                        }
+                    }
+                    v[e] = x;
+                }
+                __nv_bfloat162 pk = __floats2bfloat162_rn(v[0], v[1]);
+                mo[i] = *reinterpret_cast<uint32_t*>(&pk);
+            }
         }
         __syncthreads();                                               // xb / db / clip[cur] free again
     }
@@ -525,11 +556,11 @@ int build_feat_tables(cd_handle* h) {
 }
 
 int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets, const int32_t* d_lengths,
-                    int64_t stride_or_hop, int mode, int64_t B, float* d_feat, cudaStream_t s) {
+                    int64_t stride_or_hop, int mode, int64_t B, float* d_feat, __nv_bfloat16* d_map, cudaStream_t s) {
     if (B == 0) return CD_OK;
     const int grid = (int)(B < (int64_t)h->sm_count ? B : (int64_t)h->sm_count);
     feat_kernel<<<grid, kFeatThreads, sizeof(FeatSmem), s>>>(d_audio, d_offsets, d_lengths, stride_or_hop, mode, B,
-                                                            d_feat, h->d_tables);
+                                                            d_feat, d_map, h->d_tables);
     h->launches += 1;
     CD_CUDA(h, cudaGetLastError());
     return CD_OK;
