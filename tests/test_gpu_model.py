@@ -140,7 +140,7 @@ def test_engine_checkpoint_roundtrip_and_chunk_loop():
             CoughDetectorInference(path, device="cuda", verbose=False)
 
 
-@pytest.mark.parametrize("n,k", [(64, 64), (64, 320), (128, 512), (256, 128), (32, 64)])
+@pytest.mark.parametrize("n,k", [(64, 64), (64, 320), (128, 256), (256, 128), (32, 64)])
 def test_tcgen05_tile_selftest_bf16(n, k):
     """One UMMA tile through the conv kernels' descriptor / swizzle helpers vs a float matmul of bf16-rounded operands."""
     g = torch.Generator().manual_seed(n * 1000 + k)
