@@ -170,6 +170,7 @@ def run_gpu_arm(args):
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("CD_BENCH_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     precision = args.precision or DEFAULT_PRECISION
     prec = _PREC[precision]

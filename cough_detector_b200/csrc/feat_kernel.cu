@@ -133,9 +133,7 @@ __device__ __forceinline__ float block_reduce(float v, float* red) {
 
 // One windowed sample pair for FFT point n of the frame pair starting at sample `base0`.
 template <bool EDGE>
-__device__ __forceinline__ float2 load_point(const float* __restrict__ clip, const float* __restrict__ win,
-                                             int n, int base0, bool second) {
-    const float w = win[n];
+__device__ __forceinline__ float2 load_point(const float* __restrict__ clip, float w, int n, int base0, bool second) {
     int i0 = base0 + n;
     int i1 = i0 + kHop;
     if (EDGE) {   // reflect padding of torch.stft(center=True, pad_mode="reflect")
@@ -152,7 +150,7 @@ __device__ __forceinline__ float2 load_point(const float* __restrict__ clip, con
 // running max of the dB values it produced.
 template <bool EDGE>
 __device__ __forceinline__ float frame_pair(FeatSmem& S, const float* __restrict__ clip, float2* __restrict__ xb,
-                                            int p, int lane) {
+                                            const float (&wA)[7], const float (&wB)[6], int p, int lane) {
     const int c = lane & 7, j = lane >> 3;
     const int base0 = 2 * kHop * p - kWin / 2;      // sample index of window tap 0 of frame 2p
     const bool second = (2 * p + 1) < kFrames;
@@ -161,10 +159,10 @@ __device__ __forceinline__ float frame_pair(FeatSmem& S, const float* __restrict
     float2 A[8], B[8];
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
-        A[a] = load_point<EDGE>(clip, S.win, 64 * a + lane, base0, second);
-        B[a] = load_point<EDGE>(clip, S.win, 64 * a + lane + 32, base0, second);
+        A[a] = load_point<EDGE>(clip, wA[a], 64 * a + lane, base0, second);
+        B[a] = load_point<EDGE>(clip, wB[a], 64 * a + lane + 32, base0, second);
     }
-    A[6] = lane < 16 ? load_point<EDGE>(clip, S.win, 384 + lane, base0, second) : make_float2(0.f, 0.f);
+    A[6] = lane < 16 ? load_point<EDGE>(clip, wA[6], 384 + lane, base0, second) : make_float2(0.f, 0.f);
     A[7] = make_float2(0.f, 0.f);                   // n >= 400: zero padding of the 512-point frame
     B[6] = make_float2(0.f, 0.f);
     B[7] = make_float2(0.f, 0.f);
@@ -221,33 +219,40 @@ __device__ __forceinline__ float frame_pair(FeatSmem& S, const float* __restrict
     fft8<true>(A);      // A[s] = Z[64 s + 8 c + j]
     fft8<true>(B);      // B[s] = Z[64 s + 8 c + j + 4]
 
-    // ---- Z[k], k in [0,128) u [384,512) -> xb[kk + kk/8], kk = k (k < 128) or k - 256 ----------
+    // ---- unpack the two real spectra and take |.|^2 for bins < 128 ------------------------------
+    // z = x1 + i x2  =>  Z[k] + conj Z[512-k] = 2 X1[k],  Z[k] - conj Z[512-k] = 2i X2[k].
+    // Z[512-k] of my A[s] (k = 64s + 8c + j) sits in lane (7-c, 4-j) as B[7-s] (j != 0) or in lane
+    // ((8-c)&7, 0) as A[7-s] (j == 0); of my B[s] (k + 4) in lane (7-c, 4-j) as A[7-s] (j != 0) or in
+    // lane (7-c, 0) as B[7-s] (j == 0).  Each lane serves exactly one requester, so the sender selects.
     {
+        const int srcA = j ? ((7 - c) | ((4 - j) << 3)) : ((8 - c) & 7);
+        const int srcB = j ? ((7 - c) | ((4 - j) << 3)) : (7 - c);
+        float2 pA[2], pB[2];
+#pragma unroll
+        for (int sidx = 0; sidx < 2; ++sidx) {
+            const float2 sendA = j ? B[7 - sidx] : A[7 - sidx];
+            const float2 sendB = j ? A[7 - sidx] : B[7 - sidx];
+            pA[sidx].x = __shfl_sync(0xffffffffu, sendA.x, srcA);
+            pA[sidx].y = __shfl_sync(0xffffffffu, sendA.y, srcA);
+            pB[sidx].x = __shfl_sync(0xffffffffu, sendB.x, srcB);
+            pB[sidx].y = __shfl_sync(0xffffffffu, sendB.y, srcB);
+        }
+        if (lane == 0) pA[1] = A[7];                 // k = 64: 512 - 64 = 448 = Z of this very lane (carry case)
+        // float2 {P_frame0, P_frame1} at padded bin index k + k/8
         const int o = 9 * c + j;
-        xb[o] = A[0];            xb[o + 4] = B[0];
-        xb[72 + o] = A[1];       xb[72 + o + 4] = B[1];
-        xb[144 + o] = A[6];      xb[144 + o + 4] = B[6];
-        xb[216 + o] = A[7];      xb[216 + o + 4] = B[7];
-    }
-    __syncwarp();
-
-    // ---- unpack the two real spectra and take |.|^2 for bins 4..127 ----------------------------
-    // z = x1 + i x2  =>  Z[k] + conj Z[512-k] = 2 X1[k],  Z[k] - conj Z[512-k] = 2i X2[k]
-    float2 P[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int k = 4 + lane + 32 * i;
-        const int kk = 256 - k;
-        const float2 a = xb[(k + (k >> 3)) & 511];
-        const float2 b = xb[kk + (kk >> 3)];
-        const float sr = a.x + b.x, si = a.y - b.y, dr = a.x - b.x, di = a.y + b.y;
-        P[i] = make_float2(sr * sr + si * si, dr * dr + di * di);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int k = lane + 32 * i;                 // bin - 4
-        if (k < 124) xb[k] = P[i];
+        for (int sidx = 0; sidx < 2; ++sidx) {
+            {
+                const float2 za = A[sidx], zb = pA[sidx];
+                const float sr = za.x + zb.x, si = za.y - zb.y, dr = za.x - zb.x, di = za.y + zb.y;
+                xb[72 * sidx + o] = make_float2(sr * sr + si * si, dr * dr + di * di);
+            }
+            {
+                const float2 za = B[sidx], zb = pB[sidx];
+                const float sr = za.x + zb.x, si = za.y - zb.y, dr = za.x - zb.x, di = za.y + zb.y;
+                xb[72 * sidx + o + 4] = make_float2(sr * sr + si * si, dr * dr + di * di);
+            }
+        }
     }
     __syncwarp();
 
@@ -289,6 +294,8 @@ __device__ __forceinline__ float frame_pair(FeatSmem& S, const float* __restrict
 }
 
 // DCT-II of the floored dB tile for frame t, coefficient set CS (c = CS, CS+4, CS+8[, CS+12]).
+// cos(pi (m + 1/2) c / 64) is even (c even) or odd (c odd) about m = 31.5, so each coefficient is a
+// 32-term sum over d[m] +- d[63 - m]; all coefficients of one set share the parity of CS.
 template <int CS>
 __device__ __forceinline__ float mfcc_set(const float* __restrict__ db, float* __restrict__ mf, int t) {
     constexpr int NC = (CS == 0) ? 4 : 3;
@@ -296,8 +303,9 @@ __device__ __forceinline__ float mfcc_set(const float* __restrict__ db, float* _
 #pragma unroll
     for (int i = 0; i < NC; ++i) acc[i] = 0.f;
 #pragma unroll
-    for (int m = 0; m < kMels; ++m) {
-        const float d = db[m * kFrames + t];
+    for (int m = 0; m < kMels / 2; ++m) {
+        const float lo = db[m * kFrames + t], hi = db[(kMels - 1 - m) * kFrames + t];
+        const float d = (CS & 1) ? lo - hi : lo + hi;
 #pragma unroll
         for (int i = 0; i < NC; ++i) acc[i] = fmaf(c_dct[(CS + 4 * i) * kMels + m], d, acc[i]);
     }
@@ -403,34 +411,52 @@ feat_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offs, c
                 clip[i] = (sidx >= 0 && sidx < n) ? d.src[start + sidx] : 0.f;
             }
         }
-        peak = block_reduce<true>(peak, S.red);                        // also orders the generic stores
-        if (peak > 0.f && !(mode & kModeNoNormalize)) {                // normalize(): skipped for silence (:209-212)
-            const float inv = 1.0f / peak;
-            float4* c4 = reinterpret_cast<float4*>(clip);
-            for (int i = tid; i < kSeg / 4; i += kFeatThreads) {
-                float4 v = c4[i];
-                v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
-                c4[i] = v;
-            }
+        peak = block_reduce<true>(peak, S.red);                        // its barriers also order the generic stores
+        // normalize() (:199-212): x / max|x|, skipped for silence.  The scale is folded into this lane's
+        // 13 window weights (held in registers for the whole clip) instead of rewriting the clip.
+        const float inv = (peak > 0.f && !(mode & kModeNoNormalize)) ? 1.0f / peak : 1.0f;
+        float wA[7], wB[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            wA[a] = S.win[64 * a + lane] * inv;
+            wB[a] = S.win[64 * a + lane + 32] * inv;
         }
-        __syncthreads();
+        wA[6] = lane < 16 ? S.win[384 + lane] * inv : 0.f;
 
         // ---- STFT -> mel -> dB, one frame pair per warp per round -----------------------------------
         float wmax = -INFINITY;
         for (int p = warp; p < kPairs; p += kFeatWarps) {
             const bool edge = (p == 0) || (p >= 49);
-            wmax = fmaxf(wmax, edge ? frame_pair<true>(S, clip, S.xb[warp], p, lane)
-                                    : frame_pair<false>(S, clip, S.xb[warp], p, lane));
+            wmax = fmaxf(wmax, edge ? frame_pair<true>(S, clip, S.xb[warp], wA, wB, p, lane)
+                                    : frame_pair<false>(S, clip, S.xb[warp], wA, wB, p, lane));
         }
         const float top = block_reduce<true>(wmax, S.red);             // barrier: dB tile complete
         const float floor_db = top - 80.0f;                            // top_db = 80
 
         // ---- mel block rows 0..63: max(dB, floor) -> (dB + 80) / 80 -> clamp ------------------------
+        // The CNN stem's operand rides along: the same values rounded to bf16 in a zero-padded
+        // [93 rows: -3..89][112 cols: -3..108] map, so the stem stages a clip with one bulk copy.
         float* out = feat ? feat + b * (int64_t)kFeatElem : nullptr;
+        __nv_bfloat16* mo = map_out ? map_out + b * (int64_t)kMapElems : nullptr;
         for (int i = tid; i < kMels * kFrames; i += kFeatThreads) {
             const float v = fmaxf(S.db[i], floor_db);
             S.db[i] = v;
-            if (out) out[i] = fminf(fmaxf((v + 80.0f) * 0.0125f, 0.f), 1.f);
+            const float x01 = fminf(fmaxf((v + 80.0f) * 0.0125f, 0.f), 1.f);
+            if (out) out[i] = x01;
+            if (mo) {
+                const int r = i / kFrames;
+                mo[(r + 3) * kMapPitch + (i - r * kFrames) + 3] = __float2bfloat16_rn(x01);
+            }
+        }
+        if (mo) {       // zero padding: rows -3..-1 whole, cols -3..-1 and 101..108 of the 90 data rows
+            for (int i = tid; i < 3 * kMapPitch + kFeat * 11; i += kFeatThreads) {
+                int idx = i;
+                if (i >= 3 * kMapPitch) {
+                    const int q = i - 3 * kMapPitch, row = q / 11, e = q - row * 11;
+                    idx = (row + 3) * kMapPitch + (e < 3 ? e : kFrames + e);
+                }
+                mo[idx] = __float2bfloat16_rn(0.f);
+            }
         }
         __syncthreads();
 
@@ -457,7 +483,7 @@ feat_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offs, c
         }
         ss = block_reduce<false>(ss, S.red);
         const float inv_std = 1.0f / (sqrtf(ss * (1.0f / (kN - 1))) + 1e-8f);
-        if (out) {
+        {
             for (int i = tid; i < kN; i += kFeatThreads) {
                 const int cidx = i / kFrames, t = i - cidx * kFrames;
                 const float* row = mf + cidx * kFrames;
@@ -465,36 +491,15 @@ feat_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offs, c
                 const float x0 = __fmul_rn(row[t] - mean, inv_std);
                 const float xp = __fmul_rn(row[min(t + 1, kFrames - 1)] - mean, inv_std);
                 const float xm = __fmul_rn(row[max(t - 1, 0)] - mean, inv_std);
-                out[(kMels + cidx) * kFrames + t] = x0;
-                out[(kMels + kMfcc + cidx) * kFrames + t] = (xp - xm) * 0.5f;   // compute_deltas (:353-355)
-            }
-        }
-        if (map_out) {
-            // the CNN stem's operand: the same 90 x 101 values rounded to bf16, zero padded to
-            // [93 rows: -3..89][112 cols: -3..108] so the stem stages a clip with one bulk copy
-            uint32_t* mo = reinterpret_cast<uint32_t*>(map_out + b * (int64_t)kMapElems);
-            for (int i = tid; i < kMapElems / 2; i += kFeatThreads) {
-                const int r = (2 * i) / kMapPitch - 3, c0 = (2 * i) % kMapPitch - 3;
-                float v[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int c = c0 + e;
-                    float x = 0.f;
-                    if (r >= 0 && c >= 0 && c < kFrames) {
-                        if (r < kMels) {
-                            x = fminf(fmaxf((S.db[r * kFrames + c] + 80.0f) * 0.0125f, 0.f), 1.f);
-                        } else if (r < kMels + kMfcc) {
-                            x = __fmul_rn(mf[(r - kMels) * kFrames + c] - mean, inv_std);
-                        } else {
-                            const float* row = mf + (r - kMels - kMfcc) * kFrames;
-                            x = (__fmul_rn(row[min(c + 1, kFrames - 1)] - mean, inv_std) -
-                                 __fmul_rn(row[max(c - 1, 0)] - mean, inv_std)) * 0.5f;
-                        }
-                    }
-                    v[e] = x;
+                const float dl = (xp - xm) * 0.5f;                             // compute_deltas (:353-355)
+                if (out) {
+                    out[(kMels + cidx) * kFrames + t] = x0;
+                    out[(kMels + kMfcc + cidx) * kFrames + t] = dl;
                 }
-                __nv_bfloat162 pk = __floats2bfloat162_rn(v[0], v[1]);
-                mo[i] = *reinterpret_cast<uint32_t*>(&pk);
+                if (mo) {
+                    mo[(kMels + cidx + 3) * kMapPitch + t + 3] = __float2bfloat16_rn(x0);
+                    mo[(kMels + kMfcc + cidx + 3) * kMapPitch + t + 3] = __float2bfloat16_rn(dl);
+                }
             }
         }
         __syncthreads();                                               // xb / db / clip[cur] free again
@@ -532,7 +537,10 @@ int build_feat_tables(cd_handle* h) {
             int idx = 0;
             if (tap < CD_MEL_COUNT[band]) {
                 w = bits2f(CD_MEL_W_BITS[band * CD_MEL_MAX_TAPS + tap]);
-                idx = CD_MEL_START[band] + tap - CD_MEL_FIRST_BIN;
+                const int bin = CD_MEL_START[band] + tap;
+                idx = bin + (bin >> 3);                    // padded bin index used by frame_pair
+            } else {
+                idx = 4 + (4 >> 3);                        // zero weight: any initialised entry
             }
             float fi;
             memcpy(&fi, &idx, 4);
