@@ -184,19 +184,23 @@ umma_selftest_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* _
 // ----------------------------------------------------------------------------------------------
 // implicit-GEMM 3x3 convolution (pad 1) on tcgen05
 // ----------------------------------------------------------------------------------------------
-constexpr int kTcStages = 4;
 constexpr int kTcProducers = 128, kTcEpilogue = 128;
 constexpr int kTcThreads = kTcProducers + 32 + kTcEpilogue;     // 288
 
+// Pipeline depth: the im2col gather is L2-latency bound, so the number of chunks in flight per SM is
+// what matters.  C_out = 64: 4 stages of 24 KB and two CTAs per SM; C_out = 128: 6 stages of 32 KB.
 template <int CIN, int COUT>
 struct TcShape {
+    static constexpr int STAGES = COUT <= 64 ? 4 : 6;
+    static constexpr int LAG = COUT <= 64 ? 3 : 4;               // chunks issued ahead of the one being published
+    static constexpr int CTAS_PER_SM = COUT <= 64 ? 2 : 1;
     static constexpr int KTOT = 9 * CIN;
     static constexpr int NKC = (KTOT + 63) / 64;                 // 64-element K chunks (5 / 9 / 18)
     static constexpr int A_BYTES = 128 * 128;                    // 128 rows x 128 B
     static constexpr int B_BYTES = COUT * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int SKIP_K = CIN < 64 ? CIN : 64;           // K of the 1x1 projection (per 64-chunk)
-    static constexpr size_t SMEM = 1024 + (size_t)kTcStages * STAGE_BYTES + B_BYTES /*skip W*/ + 2 * COUT * 4 + 256;
+    static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + B_BYTES /*skip W*/ + 2 * COUT * 4 + 256;
 };
 
 struct TcArgs {
@@ -213,9 +217,10 @@ struct TcArgs {
 };
 
 template <int CIN, int COUT, int HIN, int WIN, int STRIDE, bool SKIP, bool RESID, bool OUT_F32>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, TcShape<CIN, COUT>::CTAS_PER_SM)
 conv3x3_tc_kernel(const TcArgs a) {
     using S = TcShape<CIN, COUT>;
+    constexpr int kTcStages = S::STAGES, kLag = S::LAG;
     constexpr int HOUT = (HIN - 1) / STRIDE + 1, WOUT = (WIN - 1) / STRIDE + 1, NPOS = HOUT * WOUT;
     constexpr int ACC_COLS = SKIP ? 2 * COUT : COUT;             // conv accumulator [+ skip accumulator]
     constexpr int TMEM_COLS = 2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512);
@@ -306,18 +311,19 @@ conv3x3_tc_kernel(const TcArgs a) {
                     tc::cp_async16(sdst + i * 16 * 128, src, ok ? 16u : 0u);
                 }
                 tc::cp_async_commit();
-                if (it >= 2) {                        // publish the stage filled two chunks ago
-                    tc::cp_async_wait<2>();
+                if (it >= kLag) {                     // publish the stage filled kLag chunks ago
+                    tc::cp_async_wait<kLag>();
                     tc::fence_proxy_async();
-                    tc::mbar_arrive(&full_bar[(it - 2) % kTcStages]);
+                    tc::mbar_arrive(&full_bar[(it - kLag) % kTcStages]);
                 }
             }
         }
         // drain
         tc::cp_async_wait<0>();
         tc::fence_proxy_async();
-        if (it >= 2) tc::mbar_arrive(&full_bar[(it - 2) % kTcStages]);
-        if (it >= 1) tc::mbar_arrive(&full_bar[(it - 1) % kTcStages]);
+#pragma unroll
+        for (int q = kLag; q >= 1; --q)
+            if (it >= q) tc::mbar_arrive(&full_bar[(it - q) % kTcStages]);
     } else if (warp == 4) {
         // ======================= MMA issuer ==========================================================
         if (lane == 0) {
@@ -743,7 +749,8 @@ static void launch_tc(cd_handle* h, const TcArgs& a, cudaStream_t s) {
     constexpr int HOUT = (HIN - 1) / STRIDE + 1, WOUT = (WIN - 1) / STRIDE + 1;
     const int64_t M = (int64_t)a.B * HOUT * WOUT;
     const int tiles = (int)((M + 127) / 128);
-    const int grid = tiles < h->sm_count ? tiles : h->sm_count;
+    const int slots = h->sm_count * TcShape<CIN, COUT>::CTAS_PER_SM;
+    const int grid = tiles < slots ? tiles : slots;
     conv3x3_tc_kernel<CIN, COUT, HIN, WIN, STRIDE, SKIP, RESID, OUT_F32>
         <<<grid, kTcThreads, TcShape<CIN, COUT>::SMEM, s>>>(a);
     h->launches += 1;
