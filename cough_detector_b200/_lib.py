@@ -50,7 +50,7 @@ SYMBOLS = {
     "cd_e2e_forward": (_I, [_VP, _VP, _I64, _I64, _VP, _VP, _I, _VP]),
     "cd_e2e_forward_stream": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _I, _VP]),
     "cd_e2e_forward_host": (_I, [_VP, _VP, _I64, _VP, _I]),
-    "cd_selftest_umma": (_I, [_VP, _I, _I, _VP, _VP, _VP]),
+    "cd_selftest_umma": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP]),
     "cd_launch_count": (_I64, [_VP]),
 }
 
@@ -212,12 +212,14 @@ class Handle:
                                         self._stream()), "cd_predict")
         return preds, probs, dec.bool()
 
-    def selftest_umma(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-        """(128, K) x (N, K)^T on one tcgen05 tile; CPU fp32 tensors in, CPU fp32 (128, N) out."""
+    def selftest_umma(self, a: torch.Tensor, b: torch.Tensor, shift: int = 0, mode: int = 0) -> torch.Tensor:
+        """a[shift:shift+128] (K) x b (N, K)^T on one tcgen05 tile; CPU fp32 tensors in, CPU fp32 (128, N) out."""
         a = a.to("cpu", torch.float32).contiguous()
         b = b.to("cpu", torch.float32).contiguous()
+        assert a.shape[0] == 128 + shift
         d = torch.empty(128, b.shape[0], dtype=torch.float32)
-        self._check(self.lib.cd_selftest_umma(self._h, b.shape[0], a.shape[1], _ptr(a), _ptr(b), _ptr(d)), "cd_selftest_umma")
+        self._check(self.lib.cd_selftest_umma(self._h, b.shape[0], a.shape[1], shift, mode, _ptr(a), _ptr(b), _ptr(d)),
+                    "cd_selftest_umma")
         return d
 
     # ---- end to end -------------------------------------------------------------------------

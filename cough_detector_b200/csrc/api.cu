@@ -43,7 +43,7 @@ int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits,
 size_t cnn_tc_ws_bytes(int64_t B);
 __nv_bfloat16* cnn_tc_map_ptr(cd_handle* h);
 void get_host_tables(float* hann, float* fb, float* dct);
-int umma_selftest(cd_handle* h, int N, int K, const float* hA, const float* hB, float* hD);
+int umma_selftest(cd_handle* h, int N, int K, int shift, int mode, const float* hA, const float* hB, float* hD);
 
 struct DeviceGuard {
     int prev = -1;
@@ -86,11 +86,11 @@ const char* cd_last_error(const cd_handle* h) { return h ? h->err.c_str() : g_cr
 
 int64_t cd_launch_count(const cd_handle* h) { return h ? h->launches : 0; }
 
-int cd_selftest_umma(cd_handle* h, int N, int K, const float* h_A, const float* h_B, float* h_D) {
+int cd_selftest_umma(cd_handle* h, int N, int K, int shift, int mode, const float* h_A, const float* h_B, float* h_D) {
     if (!h) return CD_E_ARG;
     if (!h_A || !h_B || !h_D) return set_err(h, CD_E_ARG, "cd_selftest_umma: NULL pointer");
     DeviceGuard g(h->device);
-    return umma_selftest(h, N, K, h_A, h_B, h_D);
+    return umma_selftest(h, N, K, shift, mode, h_A, h_B, h_D);
 }
 
 int cd_get_tables(float* hann, float* fb, float* dct) {

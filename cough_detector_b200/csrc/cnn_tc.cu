@@ -134,18 +134,20 @@ __device__ __forceinline__ uint32_t swz128(int row, int chunk) { return (uint32_
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 umma_selftest_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ Bm, float* __restrict__ D,
-                     int N, int K) {
+                     int N, int K, int shift, int mode) {
     extern __shared__ unsigned char raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
     const int kc_n = K / 64;
-    unsigned char* sA = base;                             // [kc][128 rows][128 B]
-    unsigned char* sB = base + (size_t)kc_n * 16384;      // [kc][N rows][128 B]
+    const int rowsA = (128 + shift + 7) & ~7;             // A has 128 + shift rows; D[i] = A[i + shift] . B^T
+    const int a_chunk = rowsA * 128;
+    unsigned char* sA = base;                             // [kc][rowsA][128 B]
+    unsigned char* sB = base + (size_t)kc_n * a_chunk;    // [kc][N rows][128 B]
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5;
-    for (int i = tid; i < 128 * (K / 8); i += 128) {
+    for (int i = tid; i < (128 + shift) * (K / 8); i += 128) {
         const int row = i / (K / 8), ch = i % (K / 8), kc = ch >> 3, j = ch & 7;
-        *reinterpret_cast<uint4*>(sA + kc * 16384 + tc::swz128(row, j)) = *reinterpret_cast<const uint4*>(A + (size_t)row * K + ch * 8);
+        *reinterpret_cast<uint4*>(sA + kc * a_chunk + tc::swz128(row, j)) = *reinterpret_cast<const uint4*>(A + (size_t)row * K + ch * 8);
     }
     for (int i = tid; i < N * (K / 8); i += 128) {
         const int row = i / (K / 8), ch = i % (K / 8), kc = ch >> 3, j = ch & 7;
@@ -164,9 +166,12 @@ umma_selftest_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* _
     if (tid == 0) {
         const uint32_t idesc = tc::idesc_bf16(128, N);
         for (int kc = 0; kc < kc_n; ++kc)
-            for (int k4 = 0; k4 < 4; ++k4)
-                tc::umma_bf16(tm, tc::desc_sw128(tc::s32(sA + kc * 16384) + k4 * 32),
-                              tc::desc_sw128(tc::s32(sB + (size_t)kc * N * 128) + k4 * 32), idesc, (kc | k4) != 0);
+            for (int k4 = 0; k4 < 4; ++k4) {
+                // shifted view: start the A operand `shift` rows (128 B each) into the tile
+                uint64_t ad = tc::desc_sw128(tc::s32(sA + kc * a_chunk) + shift * 128 + k4 * 32);
+                if (mode == 1) ad |= (uint64_t)(shift & 7) << 49;      // base_offset variant
+                tc::umma_bf16(tm, ad, tc::desc_sw128(tc::s32(sB + (size_t)kc * N * 128) + k4 * 32), idesc, (kc | k4) != 0);
+            }
         tc::tc_commit(&bar);
     }
     tc::mbar_wait(&bar, 0);
@@ -808,10 +813,11 @@ int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits,
 }
 
 // D = A * B^T for 128 x K by N x K bf16-rounded inputs (host fp32 in/out); exercises descriptor encodings
-int umma_selftest(cd_handle* h, int N, int K, const float* hA, const float* hB, float* hD) {
-    if (N < 16 || N > 256 || N % 16 || K < 64 || K % 64 || (size_t)(128 + N) * K * 2 + 2048 > 200 * 1024)
-        return set_err(h, CD_E_ARG, "umma_selftest: need N in [16,256] step 16, K multiple of 64, tiles within 200 KB");
-    std::vector<__nv_bfloat16> a((size_t)128 * K), b((size_t)N * K);
+int umma_selftest(cd_handle* h, int N, int K, int shift, int mode, const float* hA, const float* hB, float* hD) {
+    const size_t smem = (size_t)(136 + shift + N) * K * 2 + 2048;
+    if (N < 32 || N > 256 || N % 32 || K < 64 || K % 64 || shift < 0 || shift > 64 || smem > 200 * 1024)
+        return set_err(h, CD_E_ARG, "umma_selftest: need N in [32,256] step 32, K multiple of 64, shift in [0,64], tiles within 200 KB");
+    std::vector<__nv_bfloat16> a((size_t)(128 + shift) * K), b((size_t)N * K);
     for (size_t i = 0; i < a.size(); ++i) a[i] = __float2bfloat16_rn(hA[i]);
     for (size_t i = 0; i < b.size(); ++i) b[i] = __float2bfloat16_rn(hB[i]);
     __nv_bfloat16 *dA = nullptr, *dB = nullptr;
@@ -821,7 +827,7 @@ int umma_selftest(cd_handle* h, int N, int K, const float* hA, const float* hB, 
     CD_CUDA(h, cudaMalloc(&dD, (size_t)128 * N * 4));
     CD_CUDA(h, cudaMemcpy(dA, a.data(), a.size() * 2, cudaMemcpyHostToDevice));
     CD_CUDA(h, cudaMemcpy(dB, b.data(), b.size() * 2, cudaMemcpyHostToDevice));
-    umma_selftest_kernel<<<1, 128, (size_t)(128 + N) * K * 2 + 2048>>>(dA, dB, dD, N, K);
+    umma_selftest_kernel<<<1, 128, smem>>>(dA, dB, dD, N, K, shift, mode);
     h->launches += 1;
     CD_CUDA(h, cudaGetLastError());
     CD_CUDA(h, cudaDeviceSynchronize());

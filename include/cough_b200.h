@@ -155,10 +155,14 @@ int cd_e2e_forward_stream(cd_handle* h, const float* d_audio, int64_t n_samples,
 int cd_e2e_forward_host(cd_handle* h, const float* h_audio, int64_t B, float* h_logits,
                         int precision);
 
-/* Diagnostic: D[128 x N] = A[128 x K] * B[N x K]^T on one tcgen05 tile through the same shared-memory /
- * instruction descriptors the convolution kernels use (operands rounded to bf16, fp32 accumulate).
- * Host pointers; N multiple of 16 in [16, 256], K multiple of 64.  Synchronous. */
-int cd_selftest_umma(cd_handle* h, int N, int K, const float* h_A, const float* h_B, float* h_D);
+/* Diagnostic: D[i][n] = sum_k A[i + shift][k] * B[n][k] (i < 128) on one tcgen05 tile through the same
+ * shared-memory / instruction descriptors the convolution kernels use (operands rounded to bf16, fp32
+ * accumulate).  `shift` starts the A operand that many 128-byte rows into the swizzled tile -- the
+ * "shifted view" the stride-1 convolutions use for their nine taps (mode 0: plain address offset; mode 1:
+ * additionally sets the descriptor's base_offset field).  Host pointers; A has 128 + shift rows; N multiple
+ * of 32 in [32, 256], K multiple of 64, shift in [0, 64].  Synchronous. */
+int cd_selftest_umma(cd_handle* h, int N, int K, int shift, int mode, const float* h_A, const float* h_B,
+                     float* h_D);
 
 /* Number of kernels this handle has launched since creation (the bench's gpu_launches). */
 int64_t cd_launch_count(const cd_handle* h);
