@@ -22,7 +22,7 @@
 
 namespace cd {
 
-constexpr int kFeatWarps   = 16;
+constexpr int kFeatWarps   = 8;                // two CTAs per SM: one CTA's tail overlaps the other's FFTs
 constexpr int kFeatThreads = kFeatWarps * 32;
 constexpr int kXbElems     = 288;             // float2 per warp: 4 rows x 72 (64 + 8 pad)
 constexpr int kXbRow       = 72;
@@ -30,16 +30,15 @@ constexpr int kXbRow       = 72;
 __constant__ float c_dct[kMfcc * kMels];      // [13][64], ortho DCT-II rows
 
 struct FeatSmem {
-    float  clip[2][kSeg];                     // 128 000 B, double buffered
-    float2 xb[kFeatWarps][kXbElems];          //  36 864 B, per-warp FFT exchange; MFCC scratch in the tail
+    float  clip[kSeg];                        //  64 000 B, filled by one bulk copy per clip
+    float2 xb[kFeatWarps][kXbElems];          //  18 432 B, per-warp FFT exchange; MFCC scratch in the tail
     float  db[kMels * kFrames];               //  25 856 B, dB tile [band][frame]
-    float2 tw1[7][64];
-    float2 tw2[7][8];
-    float  win[kWin];
-    float2 melt[kMelSlots][32];
+    float2 tw1[7][64];                        //   3 584 B
+    float2 tw2[7][8];                         //     448 B
     float  red[64];
-    unsigned long long bar[2];
-};
+    unsigned long long bar;
+};                                            // 112 640 B -> two CTAs per SM
+static_assert(sizeof(FeatSmem) <= 113 * 1024, "two CTAs per SM");
 
 // ----------------------------------------------------------------------------------------------
 // small PTX wrappers
@@ -150,7 +149,8 @@ __device__ __forceinline__ float2 load_point(const float* __restrict__ clip, flo
 // running max of the dB values it produced.
 template <bool EDGE>
 __device__ __forceinline__ float frame_pair(FeatSmem& S, const float* __restrict__ clip, float2* __restrict__ xb,
-                                            const float (&wA)[7], const float (&wB)[6], int p, int lane) {
+                                            const float (&wA)[7], const float (&wB)[6],
+                                            const float (&mw)[kMelSlots], int bin_lo, int bin_hi, int p, int lane) {
     const int c = lane & 7, j = lane >> 3;
     const int base0 = 2 * kHop * p - kWin / 2;      // sample index of window tap 0 of frame 2p
     const bool second = (2 * p + 1) < kFrames;
@@ -260,17 +260,17 @@ __device__ __forceinline__ float frame_pair(FeatSmem& S, const float* __restrict
     float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
 #pragma unroll
     for (int s = 0; s < kMelSlotsLo; ++s) {
-        const float2 e = S.melt[s][lane];
-        const float2 pw = xb[__float_as_int(e.y)];
-        lo.x = fmaf(e.x, pw.x, lo.x);
-        lo.y = fmaf(e.x, pw.y, lo.y);
+        const int bin = min(bin_lo + s, 127);            // taps past the band carry zero weight
+        const float2 pw = xb[bin + (bin >> 3)];
+        lo.x = fmaf(mw[s], pw.x, lo.x);
+        lo.y = fmaf(mw[s], pw.y, lo.y);
     }
 #pragma unroll
-    for (int s = kMelSlotsLo; s < kMelSlots; ++s) {
-        const float2 e = S.melt[s][lane];
-        const float2 pw = xb[__float_as_int(e.y)];
-        hi.x = fmaf(e.x, pw.x, hi.x);
-        hi.y = fmaf(e.x, pw.y, hi.y);
+    for (int s = 0; s < kMelSlotsHi; ++s) {
+        const int bin = min(bin_hi + s, 127);
+        const float2 pw = xb[bin + (bin >> 3)];
+        hi.x = fmaf(mw[kMelSlotsLo + s], pw.x, hi.x);
+        hi.y = fmaf(mw[kMelSlotsLo + s], pw.y, hi.y);
     }
     __syncwarp();                                    // xb is rewritten by the next pair
 
@@ -293,26 +293,26 @@ __device__ __forceinline__ float frame_pair(FeatSmem& S, const float* __restrict
     return m;
 }
 
-// DCT-II of the floored dB tile for frame t, coefficient set CS (c = CS, CS+4, CS+8[, CS+12]).
-// cos(pi (m + 1/2) c / 64) is even (c even) or odd (c odd) about m = 31.5, so each coefficient is a
-// 32-term sum over d[m] +- d[63 - m]; all coefficients of one set share the parity of CS.
-template <int CS>
-__device__ __forceinline__ float mfcc_set(const float* __restrict__ db, float* __restrict__ mf, int t) {
-    constexpr int NC = (CS == 0) ? 4 : 3;
+// DCT-II of the floored dB tile for frame t, coefficients of one parity (PAR = 0: c = 0,2,..,12;
+// PAR = 1: c = 1,3,..,11).  cos(pi (m + 1/2) c / 64) is even (c even) or odd (c odd) about m = 31.5, so
+// each coefficient is a 32-term sum over d[m] +- d[63 - m], shared by all coefficients of that parity.
+template <int PAR>
+__device__ __forceinline__ float mfcc_par(const float* __restrict__ db, float* __restrict__ mf, int t) {
+    constexpr int NC = PAR ? 6 : 7;
     float acc[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) acc[i] = 0.f;
 #pragma unroll
     for (int m = 0; m < kMels / 2; ++m) {
         const float lo = db[m * kFrames + t], hi = db[(kMels - 1 - m) * kFrames + t];
-        const float d = (CS & 1) ? lo - hi : lo + hi;
+        const float d = PAR ? lo - hi : lo + hi;
 #pragma unroll
-        for (int i = 0; i < NC; ++i) acc[i] = fmaf(c_dct[(CS + 4 * i) * kMels + m], d, acc[i]);
+        for (int i = 0; i < NC; ++i) acc[i] = fmaf(c_dct[(PAR + 2 * i) * kMels + m], d, acc[i]);
     }
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-        mf[(CS + 4 * i) * kFrames + t] = acc[i];
+        mf[(PAR + 2 * i) * kFrames + t] = acc[i];
         s += acc[i];
     }
     return s;
@@ -339,7 +339,7 @@ __device__ __forceinline__ bool bulk_ok(const ClipDesc& d) {
     return d.len == kSeg && ((reinterpret_cast<uintptr_t>(d.src) & 15) == 0);
 }
 
-__global__ void __launch_bounds__(kFeatThreads, 1)
+__global__ void __launch_bounds__(kFeatThreads, 2)
 feat_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offs, const int32_t* __restrict__ lens,
             int64_t stride_or_hop, int mode, int64_t B, float* __restrict__ feat,
             __nv_bfloat16* __restrict__ map_out, const FeatTables* __restrict__ tables) {
@@ -347,54 +347,55 @@ feat_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offs, c
     FeatSmem& S = *reinterpret_cast<FeatSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // ---- one-time per CTA: tables -> smem, barriers ------------------------------------------------
+    // ---- one-time per CTA: twiddles -> smem, per-lane mel taps -> registers, barrier ----------------
     {
         const float* src = reinterpret_cast<const float*>(tables);
         float* dst = reinterpret_cast<float*>(&S.tw1[0][0]);
-        constexpr int n = sizeof(FeatTables) / 4;
-        static_assert(offsetof(FeatSmem, melt) - offsetof(FeatSmem, tw1) == offsetof(FeatTables, melt), "layout");
+        constexpr int n = (sizeof(S.tw1) + sizeof(S.tw2)) / 4;
+        static_assert(offsetof(FeatTables, tw2) == sizeof(S.tw1) && offsetof(FeatSmem, tw2) - offsetof(FeatSmem, tw1) == sizeof(S.tw1), "layout");
         for (int i = tid; i < n; i += kFeatThreads) dst[i] = src[i];
     }
+    float mw[kMelSlots];
+    int bin_lo, bin_hi;
+    {
+#pragma unroll
+        for (int s = 0; s < kMelSlots; ++s) mw[s] = tables->melt[s][lane].x;
+        const int p0 = __float_as_int(tables->melt[0][lane].y), p3 = __float_as_int(tables->melt[kMelSlotsLo][lane].y);
+        bin_lo = p0 - p0 / 9;                          // undo the k + k/8 padding
+        bin_hi = p3 - p3 / 9;
+    }
     if (tid == 0) {
-        mbar_init(&S.bar[0], 1);
-        mbar_init(&S.bar[1], 1);
+        mbar_init(&S.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    int64_t b = blockIdx.x;
-    if (b >= B) return;
-    if (tid == 0) {
-        ClipDesc d0 = clip_desc(audio, offs, lens, stride_or_hop, mode, b);
-        if (bulk_ok(d0)) {
-            mbar_expect_tx(&S.bar[0], kSeg * 4);
-            bulk_g2s(S.clip[0], d0.src, kSeg * 4, &S.bar[0]);
-        }
-    }
-    uint32_t phase[2] = {0u, 0u};
-
-    for (int it = 0; b < B; b += gridDim.x, ++it) {
-        const int cur = it & 1;
-        float* clip = S.clip[cur];
+    uint32_t phase = 0u;
+    float* clip = S.clip;
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
         const ClipDesc d = clip_desc(audio, offs, lens, stride_or_hop, mode, b);
 
-        // ---- prefetch the next clip into the other buffer (its last reader finished before the
-        //      barrier that ended the previous iteration) ---------------------------------------------
-        const int64_t bn = b + gridDim.x;
-        if (tid == 0 && bn < B) {
-            ClipDesc dn = clip_desc(audio, offs, lens, stride_or_hop, mode, bn);
-            if (bulk_ok(dn)) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy
-                mbar_expect_tx(&S.bar[cur ^ 1], kSeg * 4);
-                bulk_g2s(S.clip[cur ^ 1], dn.src, kSeg * 4, &S.bar[cur ^ 1]);
+        // ---- one bulk copy (TMA engine) brings the clip in; the co-resident CTA computes meanwhile.
+        //      The next clip is pulled into L2 now so that copy will be an L2 hit. -----------------------
+        if (tid == 0) {
+            if (bulk_ok(d)) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses -> async proxy
+                mbar_expect_tx(&S.bar, kSeg * 4);
+                bulk_g2s(clip, d.src, kSeg * 4, &S.bar);
+            }
+            const int64_t bn = b + gridDim.x;
+            if (bn < B) {
+                const ClipDesc dn = clip_desc(audio, offs, lens, stride_or_hop, mode, bn);
+                if (bulk_ok(dn))
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(dn.src), "r"(kSeg * 4) : "memory");
             }
         }
 
         // ---- stage the clip + peak ------------------------------------------------------------------
         float peak = 0.f;
         if (bulk_ok(d)) {
-            mbar_wait(&S.bar[cur], phase[cur]);
-            phase[cur] ^= 1u;
+            mbar_wait(&S.bar, phase);
+            phase ^= 1u;
             const float4* c4 = reinterpret_cast<const float4*>(clip);
             for (int i = tid; i < kSeg / 4; i += kFeatThreads) {
                 const float4 v = c4[i];
@@ -418,17 +419,17 @@ feat_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offs, c
         float wA[7], wB[6];
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
-            wA[a] = S.win[64 * a + lane] * inv;
-            wB[a] = S.win[64 * a + lane + 32] * inv;
+            wA[a] = __ldg(&tables->win[64 * a + lane]) * inv;
+            wB[a] = __ldg(&tables->win[64 * a + lane + 32]) * inv;
         }
-        wA[6] = lane < 16 ? S.win[384 + lane] * inv : 0.f;
+        wA[6] = lane < 16 ? __ldg(&tables->win[384 + lane]) * inv : 0.f;
 
         // ---- STFT -> mel -> dB, one frame pair per warp per round -----------------------------------
         float wmax = -INFINITY;
         for (int p = warp; p < kPairs; p += kFeatWarps) {
             const bool edge = (p == 0) || (p >= 49);
-            wmax = fmaxf(wmax, edge ? frame_pair<true>(S, clip, S.xb[warp], wA, wB, p, lane)
-                                    : frame_pair<false>(S, clip, S.xb[warp], wA, wB, p, lane));
+            wmax = fmaxf(wmax, edge ? frame_pair<true>(S, clip, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, p, lane)
+                                    : frame_pair<false>(S, clip, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, p, lane));
         }
         const float top = block_reduce<true>(wmax, S.red);             // barrier: dB tile complete
         const float floor_db = top - 80.0f;                            // top_db = 80
@@ -464,15 +465,9 @@ feat_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offs, c
         float* mf = reinterpret_cast<float*>(&S.xb[0][0]);             // [13][101], FFT scratch is idle now
         float part = 0.f;
         {
-            const int t = tid & 127, cs = tid >> 7;
-            if (t < kFrames) {
-                switch (cs) {
-                    case 0: part = mfcc_set<0>(S.db, mf, t); break;
-                    case 1: part = mfcc_set<1>(S.db, mf, t); break;
-                    case 2: part = mfcc_set<2>(S.db, mf, t); break;
-                    default: part = mfcc_set<3>(S.db, mf, t); break;
-                }
-            }
+            static_assert(kFeatThreads == 256, "two parity groups of 128 threads");
+            const int t = tid & 127;
+            if (t < kFrames) part = (tid >> 7) ? mfcc_par<1>(S.db, mf, t) : mfcc_par<0>(S.db, mf, t);
         }
         constexpr int kN = kMfcc * kFrames;                            // 1313
         const float mean = block_reduce<false>(part, S.red) * (1.0f / kN);
@@ -566,7 +561,8 @@ int build_feat_tables(cd_handle* h) {
 int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets, const int32_t* d_lengths,
                     int64_t stride_or_hop, int mode, int64_t B, float* d_feat, __nv_bfloat16* d_map, cudaStream_t s) {
     if (B == 0) return CD_OK;
-    const int grid = (int)(B < (int64_t)h->sm_count ? B : (int64_t)h->sm_count);
+    const int64_t slots = 2 * (int64_t)h->sm_count;     // two resident CTAs per SM
+    const int grid = (int)(B < slots ? B : slots);
     feat_kernel<<<grid, kFeatThreads, sizeof(FeatSmem), s>>>(d_audio, d_offsets, d_lengths, stride_or_hop, mode, B,
                                                             d_feat, d_map, h->d_tables);
     h->launches += 1;
