@@ -42,6 +42,7 @@ int upload_cnn_tc(cd_handle* h, const std::vector<std::vector<float>>& wf, const
 int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, cudaStream_t s);
 size_t cnn_tc_ws_bytes(int64_t B);
 __nv_bfloat16* cnn_tc_map_ptr(cd_handle* h);
+int ensure_tc_ws(cd_handle* h);
 void get_host_tables(float* hann, float* fb, float* dct);
 int umma_selftest(cd_handle* h, int N, int K, int shift, int mode, const float* hA, const float* hB, float* hD);
 
@@ -142,6 +143,7 @@ int cd_destroy(cd_handle* h) {
     cudaFree(h->d_tables);
     cudaFree(h->d_wblob);
     cudaFree(h->d_wblob_bf16);
+    cudaFree(h->d_ws_tc);
     cudaFree(h->d_ws);
     for (int i = 0; i < 3; ++i) {
         if (h->pipe_streams[i]) cudaStreamDestroy(h->pipe_streams[i]);
@@ -291,6 +293,7 @@ static int e2e_impl(cd_handle* h, const float* d_audio, int64_t stride_or_hop, i
     const size_t cnn_ws = tcp ? cnn_tc_ws_bytes(slab) : cnn_fp32_ws_bytes(slab);
     const size_t feat_bytes = (tcp || d_feat_opt) ? 0 : (size_t)slab * kFeatElem * sizeof(float);
     int rc = ensure_ws(h, cnn_ws + feat_bytes);
+    if (rc == CD_OK && tcp) rc = ensure_tc_ws(h);
     if (rc != CD_OK) return rc;
     for (int64_t b0 = 0; b0 < B; b0 += slab) {
         const int64_t n = (B - b0) < slab ? (B - b0) : slab;
@@ -359,6 +362,7 @@ int cd_e2e_forward_host(cd_handle* h, const float* h_audio, int64_t B, float* h_
     const bool tcp = precision == CD_PRECISION_BF16;
     const size_t cnn_ws = tcp ? cnn_tc_ws_bytes(chunk) : cnn_fp32_ws_bytes(chunk);
     int rc = ensure_ws(h, cnn_ws + (tcp ? 0 : (size_t)chunk * kFeatElem * sizeof(float)));
+    if (rc == CD_OK && tcp) rc = ensure_tc_ws(h);
     if (rc != CD_OK) return rc;
     float* feat = tcp ? nullptr : reinterpret_cast<float*>(reinterpret_cast<char*>(h->d_ws) + cnn_ws);
     int k = 0;

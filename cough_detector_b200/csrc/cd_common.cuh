@@ -67,6 +67,7 @@ struct cd_handle {
     float* d_wblob = nullptr;            // one allocation holding every folded fp32 tensor
     cd::CnnWeightsF32 w32{};
     __nv_bfloat16* d_wblob_bf16 = nullptr;
+    unsigned char* d_ws_tc = nullptr;    // tensor-core path activations (fixed layout, zero-initialised pads)
 
     // workspace (grown on demand, never shrunk)
     float* d_ws = nullptr;

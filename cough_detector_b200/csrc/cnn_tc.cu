@@ -218,10 +218,26 @@ struct TcArgs {
     __nv_bfloat16* y_bf16;         // [M][COUT]
     float* y_f32;                  // [M][COUT] (OUT_F32)
     float* idt_out;                // [M][COUT] fp32 (SKIP)
+    int64_t ps_plane_elems;        // OUT_MODE 2: elements between the 64-channel planes
     int B;
 };
 
-template <int CIN, int COUT, int HIN, int WIN, int STRIDE, bool SKIP, bool RESID, bool OUT_F32>
+// Padded + swizzled ("PS") activation layout consumed by the stride-1 kernel: every clip is a zero-padded
+// (H+2) x (W+2) image whose pixels are 128-byte rows of 64 channels (C = 128: two such planes); global row
+// rg = clip * RPC + (y+1) * WP + (x+1); the 16-byte chunk j of a row is stored at chunk j ^ (rg & 7), i.e.
+// already in the SWIZZLE_128B pattern of a tile that starts at a multiple of 8 rows.  With that, the A
+// operand of tap (ky, kx) for 128 consecutive output rows m' = y * WP + x is the SAME staged rows viewed
+// (ky * WP + kx) rows further down -- no im2col copy; pad rows are zero because the buffer is zeroed once
+// and only interior pixels are ever written.
+template <int H, int W>
+struct PsLayout {
+    static constexpr int HP = H + 2, WP = W + 2, RPC = HP * WP;
+    static constexpr int ROWS_IN = (128 + 2 * WP + 2 + 7) & ~7;     // rows one 128-row tile reads
+};
+
+// OUT_MODE: 0 = bf16 NHWC rows [M][COUT]; 1 = fp32 rows; 2 = bf16 in the padded + swizzled layout the
+// stride-1 kernel bulk-copies (see PsLayout)
+template <int CIN, int COUT, int HIN, int WIN, int STRIDE, bool SKIP, bool RESID, int OUT_MODE>
 __global__ void __launch_bounds__(kTcThreads, TcShape<CIN, COUT>::CTAS_PER_SM)
 conv3x3_tc_kernel(const TcArgs a) {
     using S = TcShape<CIN, COUT>;
@@ -396,11 +412,16 @@ conv3x3_tc_kernel(const TcArgs a) {
                     }
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + s_bias[c0 + i], 0.f);
-                    if (OUT_F32) {
+                    if (OUT_MODE == 1) {
                         float4* op = reinterpret_cast<float4*>(a.y_f32 + m * COUT + c0);
 #pragma unroll
                         for (int q = 0; q < 8; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                     } else {
+                        using PS = PsLayout<HOUT, WOUT>;
+                        const int bq = (int)(m / NPOS), pos = (int)(m - (int64_t)bq * NPOS);
+                        const int oy = pos / WOUT, ox = pos - oy * WOUT;
+                        const int64_t rg = (int64_t)bq * PS::RPC + (oy + 1) * PS::WP + (ox + 1);
+                        __nv_bfloat16* prow = a.y_bf16 + (int64_t)(c0 / 64) * a.ps_plane_elems + rg * 64;
                         uint4* op = reinterpret_cast<uint4*>(a.y_bf16 + m * COUT + c0);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -413,7 +434,12 @@ conv3x3_tc_kernel(const TcArgs a) {
                             pk.y = *reinterpret_cast<uint32_t*>(&p1);
                             pk.z = *reinterpret_cast<uint32_t*>(&p2);
                             pk.w = *reinterpret_cast<uint32_t*>(&p3);
-                            op[q] = pk;
+                            if (OUT_MODE == 2) {
+                                const int jch = (c0 & 63) / 8 + q;           // 16-byte chunk within the 64-channel plane
+                                *reinterpret_cast<uint4*>(prow + ((jch ^ (int)(rg & 7)) << 3)) = pk;
+                            } else {
+                                op[q] = pk;
+                            }
                         }
                     }
                 }
@@ -439,6 +465,186 @@ conv3x3_tc_kernel(const TcArgs a) {
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 4) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ----------------------------------------------------------------------------------------------
+// stride-1 3x3 convolution without im2col: shifted descriptor views over PS-layout rows
+// ----------------------------------------------------------------------------------------------
+// conv2 of each residual block (C -> C, pad 1) + bias + identity add + ReLU.  GEMM rows are the padded
+// pixel rows m' of PsLayout (valid outputs: x < W, y < H; the rest are computed and dropped, 27 % / 42 %
+// of the MMA rows -- the tensor pipe has the headroom, L2 does not).  Per 128-row tile ONE bulk copy per
+// 64-channel plane stages ROWS_IN rows (20 KB) instead of nine im2col chunks (144 KB), and the weights
+// (9 taps x C/64 planes x [64 x 128 B]) stay resident in shared memory: a CTA owns one 64-wide half of
+// the output channels (C = 128: two halves -> the A rows are read twice, the 288 KB of weights never).
+constexpr int kS1Threads = 192;                   // warp 0: bulk-copy producer, warp 1: MMA, warps 2-5: epilogue
+
+template <int C, int H, int W>
+struct S1Shape {
+    using PS = PsLayout<H, W>;
+    static constexpr int NPL = C / 64;                            // 64-channel planes of the input
+    static constexpr int HALVES = C / 64;                         // 64-wide halves of the output channels
+    static constexpr int A_BYTES = PS::ROWS_IN * 128;             // per plane
+    static constexpr int STAGE_BYTES = NPL * A_BYTES;
+    static constexpr int STAGES = C == 64 ? 4 : 2;
+    static constexpr int W_BYTES = 9 * NPL * 8192;                // resident weights of one half
+    static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + W_BYTES + 64 * 4 + 64;
+};
+
+struct S1Args {
+    const __nv_bfloat16* x;        // PS layout, planes ps_plane_elems apart
+    const __nv_bfloat16* w;        // packed chunks [9 * NPL][C rows x 128 B]
+    const float* bias;             // [C]
+    const float* idt;              // [n * H * W][C] fp32
+    __nv_bfloat16* y_bf16;         // [n * H * W][C] bf16 (OUT_F32 == false)
+    float* y_f32;                  // [n * H * W][C] fp32
+    int64_t ps_plane_elems;
+    int n;                         // clips
+};
+
+template <int C, int H, int W, bool OUT_F32>
+__global__ void __launch_bounds__(kS1Threads, 1)
+conv3x3_s1_tc_kernel(const S1Args a) {
+    using S = S1Shape<C, H, W>;
+    using PS = PsLayout<H, W>;
+    constexpr int NPOS = H * W;
+    constexpr uint32_t IDESC = tc::idesc_bf16(128, 64);
+    constexpr int TMEM_COLS = 128;                                // 2 x 64 fp32 columns
+
+    extern __shared__ unsigned char raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* s_w = base + (size_t)S::STAGES * S::STAGE_BYTES;
+    float* s_bias = reinterpret_cast<float*>(s_w + S::W_BYTES);
+    __shared__ uint64_t full_bar[S::STAGES], empty_bar[S::STAGES], tfull_bar[2], tempty_bar[2], w_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int half = blockIdx.x % S::HALVES;                      // which 64 output channels this CTA owns
+    const int cta = blockIdx.x / S::HALVES, n_cta = gridDim.x / S::HALVES;
+    const int64_t rows = (int64_t)a.n * PS::RPC;
+    const int n_tiles = (int)((rows + 127) / 128);
+
+    if (tid == 0) {
+        for (int i = 0; i < S::STAGES; ++i) {
+            tc::mbar_init(&full_bar[i], 1);
+            tc::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&tfull_bar[i], 1);
+            tc::mbar_init(&tempty_bar[i], 128);
+        }
+        tc::mbar_init(&w_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 64) s_bias[tid] = a.bias[half * 64 + tid];
+    if (warp == 1) tc::tmem_alloc(&tmem_base_s, TMEM_COLS);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ======================= producer: weights once, then one bulk copy per plane per tile =========
+        if (lane == 0) {
+            tc::mbar_arrive_expect_tx(&w_bar, S::W_BYTES);
+            for (int q = 0; q < 9 * S::NPL; ++q)      // rows [64 half, 64 half + 64) of every packed chunk
+                tc::bulk_g2s(s_w + q * 8192, a.w + (size_t)q * C * 64 + (size_t)half * 64 * 64, 8192, &w_bar);
+            int it = 0;
+            for (int tile = cta; tile < n_tiles; tile += n_cta, ++it) {
+                const int s = it % S::STAGES;
+                tc::mbar_wait(&empty_bar[s], (uint32_t)(((it / S::STAGES) & 1) ^ 1));
+                tc::mbar_arrive_expect_tx(&full_bar[s], S::STAGE_BYTES);
+#pragma unroll
+                for (int q = 0; q < S::NPL; ++q)
+                    tc::bulk_g2s(base + (size_t)s * S::STAGE_BYTES + q * S::A_BYTES,
+                                 a.x + q * a.ps_plane_elems + (int64_t)tile * 128 * 64, S::A_BYTES, &full_bar[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= MMA issuer: 9 taps x planes x 4 K-steps per tile ====================
+        if (lane == 0) {
+            tc::mbar_wait(&w_bar, 0);
+            int it = 0;
+            for (int tile = cta; tile < n_tiles; tile += n_cta, ++it) {
+                const int s = it % S::STAGES, acc = it & 1;
+                tc::mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+                tc::mbar_wait(&full_bar[s], (uint32_t)((it / S::STAGES) & 1));
+                tc::tc_fence_after();
+                const uint32_t d = tmem_base + acc * 64;
+                const uint32_t sa = tc::s32(base + (size_t)s * S::STAGE_BYTES), sw = tc::s32(s_w);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const uint32_t shift = (uint32_t)((tap / 3) * PS::WP + (tap % 3)) * 128;   // rows down the staged image
+#pragma unroll
+                    for (int q = 0; q < S::NPL; ++q)
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            tc::umma_bf16(d, tc::desc_sw128(sa + q * S::A_BYTES + shift + k4 * 32),
+                                          tc::desc_sw128(sw + (tap * S::NPL + q) * 8192 + k4 * 32), IDESC,
+                                          (tap | q | k4) != 0);
+                }
+                tc::tc_commit(&empty_bar[s]);
+                tc::tc_commit(&tfull_bar[acc]);
+            }
+        }
+    } else {
+        // ======================= epilogue: + bias + identity, ReLU, store the valid pixels ============
+        const int lane_grp = warp & 3;
+        int it = 0;
+        for (int tile = cta; tile < n_tiles; tile += n_cta, ++it) {
+            const int acc = it & 1;
+            const int64_t mp = (int64_t)tile * 128 + lane_grp * 32 + lane;      // padded-row index m'
+            const int clip = (int)(mp / PS::RPC), rem = (int)(mp - (int64_t)clip * PS::RPC);
+            const int y = rem / PS::WP, x = rem - y * PS::WP;
+            const bool live = clip < a.n && y < H && x < W;
+            const int64_t m = (int64_t)clip * NPOS + y * W + x;
+            // the identity values do not depend on the accumulator: fetch them before waiting for it
+            float idv[64];
+            if (live) {
+                const float4* ip = reinterpret_cast<const float4*>(a.idt + m * C + half * 64);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float4 t = __ldg(ip + q);
+                    idv[4 * q] = t.x; idv[4 * q + 1] = t.y; idv[4 * q + 2] = t.z; idv[4 * q + 3] = t.w;
+                }
+            }
+            tc::mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * 64;
+            float v0[32], v1[32];
+            tc::tmem_ld32(taddr, v0);
+            tc::tmem_ld32(taddr + 32, v1);
+            tc::tc_fence_before();
+            tc::mbar_arrive(&tempty_bar[acc]);
+            if (live) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    v0[i] = fmaxf(v0[i] + idv[i] + s_bias[i], 0.f);
+                    v1[i] = fmaxf(v1[i] + idv[32 + i] + s_bias[32 + i], 0.f);
+                }
+                if (OUT_F32) {
+                    float4* op = reinterpret_cast<float4*>(a.y_f32 + m * C + half * 64);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        op[q] = make_float4(v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]);
+                        op[8 + q] = make_float4(v1[4 * q], v1[4 * q + 1], v1[4 * q + 2], v1[4 * q + 3]);
+                    }
+                } else {
+                    uint4* op = reinterpret_cast<uint4*>(a.y_bf16 + m * C + half * 64);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float* v = q < 4 ? v0 + 8 * q : v1 + 8 * (q - 4);
+                        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+                        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+                        op[q] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                                           *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+                    }
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -665,17 +871,19 @@ static void pack_weights(const std::vector<float>& wf, int taps, int cin, int co
         }
 }
 
-template <int CIN, int COUT, int HIN, int WIN, int STRIDE, bool SKIP, bool RESID, bool OUT_F32>
+template <int CIN, int COUT, int HIN, int WIN, int STRIDE, bool SKIP, bool RESID, int OUT_MODE>
 static cudaError_t tc_attr() {
-    return cudaFuncSetAttribute(conv3x3_tc_kernel<CIN, COUT, HIN, WIN, STRIDE, SKIP, RESID, OUT_F32>,
+    return cudaFuncSetAttribute(conv3x3_tc_kernel<CIN, COUT, HIN, WIN, STRIDE, SKIP, RESID, OUT_MODE>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcShape<CIN, COUT>::SMEM);
 }
 
 int init_cnn_tc(cd_handle* h) {
-    CD_CUDA(h, (tc_attr<32, 64, 22, 25, 2, true, false, false>()));
-    CD_CUDA(h, (tc_attr<64, 64, 11, 13, 1, false, true, false>()));
-    CD_CUDA(h, (tc_attr<64, 128, 11, 13, 2, true, false, false>()));
-    CD_CUDA(h, (tc_attr<128, 128, 6, 7, 1, false, true, true>()));
+    CD_CUDA(h, (tc_attr<32, 64, 22, 25, 2, true, false, 2>()));
+    CD_CUDA(h, (tc_attr<64, 128, 11, 13, 2, true, false, 2>()));
+    CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s1_tc_kernel<64, 11, 13, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)S1Shape<64, 11, 13>::SMEM));
+    CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s1_tc_kernel<128, 6, 7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)S1Shape<128, 6, 7>::SMEM));
     CD_CUDA(h, cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStemSmem));
     CD_CUDA(h, cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return CD_OK;
@@ -734,29 +942,47 @@ int upload_cnn_tc(cd_handle* h, const std::vector<std::vector<float>>& wf, const
     return CD_OK;
 }
 
-// per-clip workspace (bytes): x0 bf16, h1 bf16, idt1 f32, x1 bf16, h2 bf16, idt2 f32, x2 f32
-constexpr int64_t kTcX0 = 22 * 25 * 32 * 2, kTcH1 = 143 * 64 * 2, kTcI1 = 143 * 64 * 4, kTcH2 = 42 * 128 * 2,
-                  kTcI2 = 42 * 128 * 4, kTcX2 = 42 * 128 * 4;
-constexpr int64_t kTcPerClip = kMapElems * 2 + kTcX0 + 2 * kTcH1 + kTcI1 + kTcH2 + kTcI2 + kTcX2;
+// Tensor-core workspace: fixed layout for kTcChunk clips, allocated and zeroed once per handle (the PS
+// buffers rely on their pad rows staying zero).  [maps | x0 | h1 (PS) | idt1 | x1 | h2 (PS, 2 planes) | idt2 | x2]
 constexpr int64_t kTcChunk = 2048;
+using Ps0 = PsLayout<11, 13>;
+using Ps1 = PsLayout<6, 7>;
+constexpr int64_t kPs0Rows = ((kTcChunk * Ps0::RPC + 127) / 128) * 128 + Ps0::ROWS_IN;    // + the last tile's look-ahead
+constexpr int64_t kPs1Rows = ((kTcChunk * Ps1::RPC + 127) / 128) * 128 + Ps1::ROWS_IN;
+constexpr int64_t al256(int64_t x) { return (x + 255) & ~int64_t(255); }
+constexpr int64_t kOffMap = 0;
+constexpr int64_t kOffX0 = kOffMap + al256(kTcChunk * kMapElems * 2);
+constexpr int64_t kOffH1 = kOffX0 + al256(kTcChunk * 22 * 25 * 32 * 2);
+constexpr int64_t kOffI1 = kOffH1 + al256(kPs0Rows * 128);
+constexpr int64_t kOffX1 = kOffI1 + al256(kTcChunk * 143 * 64 * 4);
+constexpr int64_t kOffH2 = kOffX1 + al256(kTcChunk * 143 * 64 * 2);
+constexpr int64_t kOffI2 = kOffH2 + al256(2 * kPs1Rows * 128);
+constexpr int64_t kOffX2 = kOffI2 + al256(kTcChunk * 42 * 128 * 4);
+constexpr int64_t kTcWsBytes = kOffX2 + al256(kTcChunk * 42 * 128 * 4);
 
-size_t cnn_tc_ws_bytes(int64_t B) {
-    const int64_t n = B < kTcChunk ? B : kTcChunk;
-    return (size_t)(n * kTcPerClip) + 8 * 256;
+size_t cnn_tc_ws_bytes(int64_t) { return 0; }      // nothing from the shared workspace
+
+int ensure_tc_ws(cd_handle* h) {
+    if (h->d_ws_tc) return CD_OK;
+    cudaError_t e = cudaMalloc(&h->d_ws_tc, (size_t)kTcWsBytes);
+    if (e != cudaSuccess) return set_err(h, CD_E_NOMEM, "tensor-core workspace allocation", e);
+    CD_CUDA(h, cudaMemset(h->d_ws_tc, 0, (size_t)kTcWsBytes));
+    CD_CUDA(h, cudaDeviceSynchronize());       // callers' streams are non-blocking: order the zero-fill before them
+    return CD_OK;
 }
 
-// the first region of the workspace holds the bf16 maps of the current chunk: the feature kernel
-// writes them there directly in the end-to-end path
-__nv_bfloat16* cnn_tc_map_ptr(cd_handle* h) { return reinterpret_cast<__nv_bfloat16*>(h->d_ws); }
+// the first region holds the bf16 maps of the current chunk: the feature kernel writes them there
+// directly in the end-to-end path (call ensure_tc_ws first)
+__nv_bfloat16* cnn_tc_map_ptr(cd_handle* h) { return reinterpret_cast<__nv_bfloat16*>(h->d_ws_tc + kOffMap); }
 
-template <int CIN, int COUT, int HIN, int WIN, int STRIDE, bool SKIP, bool RESID, bool OUT_F32>
+template <int CIN, int COUT, int HIN, int WIN, int STRIDE, bool SKIP, bool RESID, int OUT_MODE>
 static void launch_tc(cd_handle* h, const TcArgs& a, cudaStream_t s) {
     constexpr int HOUT = (HIN - 1) / STRIDE + 1, WOUT = (WIN - 1) / STRIDE + 1;
     const int64_t M = (int64_t)a.B * HOUT * WOUT;
     const int tiles = (int)((M + 127) / 128);
     const int slots = h->sm_count * TcShape<CIN, COUT>::CTAS_PER_SM;
     const int grid = tiles < slots ? tiles : slots;
-    conv3x3_tc_kernel<CIN, COUT, HIN, WIN, STRIDE, SKIP, RESID, OUT_F32>
+    conv3x3_tc_kernel<CIN, COUT, HIN, WIN, STRIDE, SKIP, RESID, OUT_MODE>
         <<<grid, kTcThreads, TcShape<CIN, COUT>::SMEM, s>>>(a);
     h->launches += 1;
 }
@@ -767,22 +993,19 @@ int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits,
     if (B == 0) return CD_OK;
     if (!d_feat && B > kTcChunk) return set_err(h, CD_E_ARG, "launch_cnn_tc: pre-filled maps hold one chunk only");
     const TcWeights& W = g_tcw[h->device];
+    int rc0 = ensure_tc_ws(h);
+    if (rc0 != CD_OK) return rc0;
+    unsigned char* ws = h->d_ws_tc;
+    __nv_bfloat16* maps = reinterpret_cast<__nv_bfloat16*>(ws + kOffMap);
+    __nv_bfloat16* x0 = reinterpret_cast<__nv_bfloat16*>(ws + kOffX0);
+    __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(ws + kOffH1);
+    float* i1 = reinterpret_cast<float*>(ws + kOffI1);
+    __nv_bfloat16* x1 = reinterpret_cast<__nv_bfloat16*>(ws + kOffX1);
+    __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(ws + kOffH2);
+    float* i2 = reinterpret_cast<float*>(ws + kOffI2);
+    float* x2 = reinterpret_cast<float*>(ws + kOffX2);
     for (int64_t c0 = 0; c0 < B; c0 += kTcChunk) {
         const int n = (int)((B - c0) < kTcChunk ? (B - c0) : kTcChunk);
-        unsigned char* p = reinterpret_cast<unsigned char*>(h->d_ws);
-        auto carve = [&](int64_t bytes) {
-            unsigned char* r = p;
-            p += (bytes * n + 255) & ~int64_t(255);
-            return r;
-        };
-        __nv_bfloat16* maps = reinterpret_cast<__nv_bfloat16*>(carve(kMapElems * 2));
-        __nv_bfloat16* x0 = reinterpret_cast<__nv_bfloat16*>(carve(kTcX0));
-        __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(carve(kTcH1));
-        float* i1 = reinterpret_cast<float*>(carve(kTcI1));
-        __nv_bfloat16* x1 = reinterpret_cast<__nv_bfloat16*>(carve(kTcH1));
-        __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(carve(kTcH2));
-        float* i2 = reinterpret_cast<float*>(carve(kTcI2));
-        float* x2 = reinterpret_cast<float*>(carve(kTcX2));
         if (d_feat) {
             map_from_feat_kernel<<<dim3((kMapElems / 2 + 255) / 256, n), 256, 0, s>>>(d_feat + c0 * kFeatElem, maps, n);
             h->launches += 1;
@@ -792,19 +1015,32 @@ int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits,
         TcArgs a{};
         a.B = n;
         a.x = x0; a.w = W.b0c1; a.wskip = W.b0sk; a.bias = W.b0c1_b; a.bias_skip = W.b0sk_b; a.y_bf16 = h1; a.idt_out = i1;
-        launch_tc<32, 64, 22, 25, 2, true, false, false>(h, a, s);
-        a = TcArgs{};
-        a.B = n;
-        a.x = h1; a.w = W.b0c2; a.bias = W.b0c2_b; a.idt_in = i1; a.y_bf16 = x1;
-        launch_tc<64, 64, 11, 13, 1, false, true, false>(h, a, s);
+        a.ps_plane_elems = 0;
+        launch_tc<32, 64, 22, 25, 2, true, false, 2>(h, a, s);
+        {
+            using S = S1Shape<64, 11, 13>;
+            S1Args q{};
+            q.x = h1; q.w = W.b0c2; q.bias = W.b0c2_b; q.idt = i1; q.y_bf16 = x1; q.ps_plane_elems = 0; q.n = n;
+            const int tiles = (int)(((int64_t)n * Ps0::RPC + 127) / 128);
+            const int grid = (tiles < h->sm_count ? tiles : h->sm_count) * S::HALVES;
+            conv3x3_s1_tc_kernel<64, 11, 13, false><<<grid, kS1Threads, S::SMEM, s>>>(q);
+            h->launches += 1;
+        }
         a = TcArgs{};
         a.B = n;
         a.x = x1; a.w = W.b1c1; a.wskip = W.b1sk; a.bias = W.b1c1_b; a.bias_skip = W.b1sk_b; a.y_bf16 = h2; a.idt_out = i2;
-        launch_tc<64, 128, 11, 13, 2, true, false, false>(h, a, s);
-        a = TcArgs{};
-        a.B = n;
-        a.x = h2; a.w = W.b1c2; a.bias = W.b1c2_b; a.idt_in = i2; a.y_f32 = x2;
-        launch_tc<128, 128, 6, 7, 1, false, true, true>(h, a, s);
+        a.ps_plane_elems = kPs1Rows * 64;
+        launch_tc<64, 128, 11, 13, 2, true, false, 2>(h, a, s);
+        {
+            using S = S1Shape<128, 6, 7>;
+            S1Args q{};
+            q.x = h2; q.w = W.b1c2; q.bias = W.b1c2_b; q.idt = i2; q.y_f32 = x2; q.ps_plane_elems = kPs1Rows * 64; q.n = n;
+            const int tiles = (int)(((int64_t)n * Ps1::RPC + 127) / 128);
+            const int per_half = h->sm_count / S::HALVES;
+            const int grid = (tiles < per_half ? tiles : per_half) * S::HALVES;
+            conv3x3_s1_tc_kernel<128, 6, 7, true><<<grid, kS1Threads, S::SMEM, s>>>(q);
+            h->launches += 1;
+        }
         head_kernel<<<n, 128, 0, s>>>(x2, W.fc_w, W.fc_b, d_logits + c0 * CD_N_CLASSES, n);
         h->launches += 1;
         CD_CUDA(h, cudaGetLastError());
