@@ -478,43 +478,52 @@ conv3x3_tc_kernel(const TcArgs a) {
 // the output channels (C = 128: two halves -> the A rows are read twice, the 288 KB of weights never).
 constexpr int kS1Threads = 192;                   // warp 0: bulk-copy producer, warp 1: MMA, warps 2-5: epilogue
 
+// The block's 1x1/s2 skip projection rides along as a TENTH tap: its operand (the block input sampled at
+// (2y, 2x), written in PS layout by whoever produced that input) is one more 64-channel plane, viewed at
+// the centre shift WP + 1, multiplied by the skip weights into the SAME accumulator -- the identity path
+// never leaves TMEM and no fp32 identity tensor exists.
 template <int C, int H, int W>
 struct S1Shape {
     using PS = PsLayout<H, W>;
-    static constexpr int NPL = C / 64;                            // 64-channel planes of the input
+    static constexpr int NPL = C / 64;                            // 64-channel planes of the conv input
+    static constexpr int NPLT = NPL + 1;                          // + the skip-operand plane
     static constexpr int HALVES = C / 64;                         // 64-wide halves of the output channels
-    static constexpr int A_BYTES = PS::ROWS_IN * 128;             // per plane
-    static constexpr int STAGE_BYTES = NPL * A_BYTES;
-    static constexpr int STAGES = C == 64 ? 4 : 2;
-    static constexpr int W_BYTES = 9 * NPL * 8192;                // resident weights of one half
-    static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + W_BYTES + 64 * 4 + 64;
+    static constexpr int A_BYTES = PS::ROWS_IN * 128;             // one staged plane
+    static constexpr int STAGES = C == 64 ? 3 : 1;                // tiles in flight; every plane has its own barriers,
+                                                                  // so even STAGES = 1 refills plane q while q+1 computes
+    static constexpr int NCHUNK = 9 * NPL + 1;                    // resident weight chunks of one half (last = skip)
+    static constexpr int W_BYTES = NCHUNK * 8192;
+    static constexpr size_t SMEM = 1024 + (size_t)STAGES * NPLT * A_BYTES + W_BYTES + 64 * 4 + 64;
 };
 
 struct S1Args {
-    const __nv_bfloat16* x;        // PS layout, planes ps_plane_elems apart
-    const __nv_bfloat16* w;        // packed chunks [9 * NPL][C rows x 128 B]
-    const float* bias;             // [C]
-    const float* idt;              // [n * H * W][C] fp32
+    const __nv_bfloat16* x;        // PS layout: NPL conv planes then the skip plane, ps_plane_elems apart
+    const __nv_bfloat16* w;        // packed conv chunks [9 * NPL][C rows x 128 B]
+    const __nv_bfloat16* wskip;    // packed skip chunk [C rows x 128 B]
+    const float* bias;             // [C] conv2 bias + skip bias
     __nv_bfloat16* y_bf16;         // [n * H * W][C] bf16 (OUT_F32 == false)
     float* y_f32;                  // [n * H * W][C] fp32
+    __nv_bfloat16* xs_out;         // WRITE_XS: next block's skip plane (PS layout of the (H+1)/2 x (W+1)/2 grid)
     int64_t ps_plane_elems;
     int n;                         // clips
 };
 
-template <int C, int H, int W, bool OUT_F32>
+template <int C, int H, int W, bool OUT_F32, bool WRITE_XS>
 __global__ void __launch_bounds__(kS1Threads, 1)
 conv3x3_s1_tc_kernel(const S1Args a) {
     using S = S1Shape<C, H, W>;
     using PS = PsLayout<H, W>;
+    using PSN = PsLayout<(H + 1) / 2, (W + 1) / 2>;               // the next block's grid (stride 2, pad 1, k 3)
     constexpr int NPOS = H * W;
     constexpr uint32_t IDESC = tc::idesc_bf16(128, 64);
     constexpr int TMEM_COLS = 128;                                // 2 x 64 fp32 columns
+    constexpr int NB = S::STAGES * S::NPLT;
 
     extern __shared__ unsigned char raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
-    unsigned char* s_w = base + (size_t)S::STAGES * S::STAGE_BYTES;
+    unsigned char* s_w = base + (size_t)NB * S::A_BYTES;
     float* s_bias = reinterpret_cast<float*>(s_w + S::W_BYTES);
-    __shared__ uint64_t full_bar[S::STAGES], empty_bar[S::STAGES], tfull_bar[2], tempty_bar[2], w_bar;
+    __shared__ uint64_t full_bar[NB], empty_bar[NB], tfull_bar[2], tempty_bar[2], w_bar;
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -524,7 +533,7 @@ conv3x3_s1_tc_kernel(const S1Args a) {
     const int n_tiles = (int)((rows + 127) / 128);
 
     if (tid == 0) {
-        for (int i = 0; i < S::STAGES; ++i) {
+        for (int i = 0; i < NB; ++i) {
             tc::mbar_init(&full_bar[i], 1);
             tc::mbar_init(&empty_bar[i], 1);
         }
@@ -548,46 +557,62 @@ conv3x3_s1_tc_kernel(const S1Args a) {
             tc::mbar_arrive_expect_tx(&w_bar, S::W_BYTES);
             for (int q = 0; q < 9 * S::NPL; ++q)      // rows [64 half, 64 half + 64) of every packed chunk
                 tc::bulk_g2s(s_w + q * 8192, a.w + (size_t)q * C * 64 + (size_t)half * 64 * 64, 8192, &w_bar);
+            tc::bulk_g2s(s_w + 9 * S::NPL * 8192, a.wskip + (size_t)half * 64 * 64, 8192, &w_bar);
             int it = 0;
             for (int tile = cta; tile < n_tiles; tile += n_cta, ++it) {
                 const int s = it % S::STAGES;
-                tc::mbar_wait(&empty_bar[s], (uint32_t)(((it / S::STAGES) & 1) ^ 1));
-                tc::mbar_arrive_expect_tx(&full_bar[s], S::STAGE_BYTES);
+                const uint32_t par = (uint32_t)(((it / S::STAGES) & 1) ^ 1);
 #pragma unroll
-                for (int q = 0; q < S::NPL; ++q)
-                    tc::bulk_g2s(base + (size_t)s * S::STAGE_BYTES + q * S::A_BYTES,
-                                 a.x + q * a.ps_plane_elems + (int64_t)tile * 128 * 64, S::A_BYTES, &full_bar[s]);
+                for (int q = 0; q < S::NPLT; ++q) {
+                    const int bi = s * S::NPLT + q;
+                    tc::mbar_wait(&empty_bar[bi], par);
+                    tc::mbar_arrive_expect_tx(&full_bar[bi], S::A_BYTES);
+                    tc::bulk_g2s(base + (size_t)bi * S::A_BYTES, a.x + q * a.ps_plane_elems + (int64_t)tile * 128 * 64,
+                                 S::A_BYTES, &full_bar[bi]);
+                }
             }
         }
     } else if (warp == 1) {
-        // ======================= MMA issuer: 9 taps x planes x 4 K-steps per tile ====================
+        // ======================= MMA issuer: per plane 9 taps x 4 K-steps, skip plane 1 tap ===========
         if (lane == 0) {
             tc::mbar_wait(&w_bar, 0);
             int it = 0;
             for (int tile = cta; tile < n_tiles; tile += n_cta, ++it) {
                 const int s = it % S::STAGES, acc = it & 1;
+                const uint32_t par = (uint32_t)((it / S::STAGES) & 1);
                 tc::mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
-                tc::mbar_wait(&full_bar[s], (uint32_t)((it / S::STAGES) & 1));
-                tc::tc_fence_after();
                 const uint32_t d = tmem_base + acc * 64;
-                const uint32_t sa = tc::s32(base + (size_t)s * S::STAGE_BYTES), sw = tc::s32(s_w);
+                const uint32_t sw = tc::s32(s_w);
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
-                    const uint32_t shift = (uint32_t)((tap / 3) * PS::WP + (tap % 3)) * 128;   // rows down the staged image
+                for (int q = 0; q < S::NPLT; ++q) {
+                    const int bi = s * S::NPLT + q;
+                    tc::mbar_wait(&full_bar[bi], par);
+                    tc::tc_fence_after();
+                    const uint32_t sa = tc::s32(base + (size_t)bi * S::A_BYTES);
+                    if (q < S::NPL) {
 #pragma unroll
-                    for (int q = 0; q < S::NPL; ++q)
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint32_t shift = (uint32_t)((tap / 3) * PS::WP + (tap % 3)) * 128;   // rows down the image
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                tc::umma_bf16(d, tc::desc_sw128(sa + shift + k4 * 32),
+                                              tc::desc_sw128(sw + (tap * S::NPL + q) * 8192 + k4 * 32), IDESC,
+                                              (q | tap | k4) != 0);
+                        }
+                    } else {
+                        const uint32_t shift = (uint32_t)(PS::WP + 1) * 128;                          // centre tap
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4)
-                            tc::umma_bf16(d, tc::desc_sw128(sa + q * S::A_BYTES + shift + k4 * 32),
-                                          tc::desc_sw128(sw + (tap * S::NPL + q) * 8192 + k4 * 32), IDESC,
-                                          (tap | q | k4) != 0);
+                            tc::umma_bf16(d, tc::desc_sw128(sa + shift + k4 * 32),
+                                          tc::desc_sw128(sw + 9 * S::NPL * 8192 + k4 * 32), IDESC, 1u);
+                    }
+                    tc::tc_commit(&empty_bar[bi]);        // this plane's slot can be refilled for the next tile
                 }
-                tc::tc_commit(&empty_bar[s]);
                 tc::tc_commit(&tfull_bar[acc]);
             }
         }
     } else {
-        // ======================= epilogue: + bias + identity, ReLU, store the valid pixels ============
+        // ======================= epilogue: + bias, ReLU, store the valid pixels ======================
         const int lane_grp = warp & 3;
         int it = 0;
         for (int tile = cta; tile < n_tiles; tile += n_cta, ++it) {
@@ -597,16 +622,6 @@ conv3x3_s1_tc_kernel(const S1Args a) {
             const int y = rem / PS::WP, x = rem - y * PS::WP;
             const bool live = clip < a.n && y < H && x < W;
             const int64_t m = (int64_t)clip * NPOS + y * W + x;
-            // the identity values do not depend on the accumulator: fetch them before waiting for it
-            float idv[64];
-            if (live) {
-                const float4* ip = reinterpret_cast<const float4*>(a.idt + m * C + half * 64);
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const float4 t = __ldg(ip + q);
-                    idv[4 * q] = t.x; idv[4 * q + 1] = t.y; idv[4 * q + 2] = t.z; idv[4 * q + 3] = t.w;
-                }
-            }
             tc::mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
             tc::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * 64;
@@ -618,8 +633,8 @@ conv3x3_s1_tc_kernel(const S1Args a) {
             if (live) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    v0[i] = fmaxf(v0[i] + idv[i] + s_bias[i], 0.f);
-                    v1[i] = fmaxf(v1[i] + idv[32 + i] + s_bias[32 + i], 0.f);
+                    v0[i] = fmaxf(v0[i] + s_bias[i], 0.f);
+                    v1[i] = fmaxf(v1[i] + s_bias[32 + i], 0.f);
                 }
                 if (OUT_F32) {
                     float4* op = reinterpret_cast<float4*>(a.y_f32 + m * C + half * 64);
@@ -630,13 +645,19 @@ conv3x3_s1_tc_kernel(const S1Args a) {
                     }
                 } else {
                     uint4* op = reinterpret_cast<uint4*>(a.y_bf16 + m * C + half * 64);
+                    // the next block's skip conv reads this activation at (2y', 2x'): emit that sample as a PS row
+                    const bool xs = WRITE_XS && !(y & 1) && !(x & 1);
+                    const int64_t rg2 = (int64_t)clip * PSN::RPC + (y / 2 + 1) * PSN::WP + (x / 2 + 1);
+                    __nv_bfloat16* xrow = a.xs_out + rg2 * 64;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const float* v = q < 4 ? v0 + 8 * q : v1 + 8 * (q - 4);
                         __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
                         __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
-                        op[q] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                                           *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+                        const uint4 pk = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                                                    *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+                        op[q] = pk;
+                        if (xs) *reinterpret_cast<uint4*>(xrow + ((q ^ (int)(rg2 & 7)) << 3)) = pk;
                     }
                 }
             }
@@ -666,7 +687,7 @@ constexpr size_t kStemSmem = 1024 + 2 * kStemABytes + kStemBBytes + 2 * kMapByte
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __restrict__ wq,
-               const float* __restrict__ bias, __nv_bfloat16* __restrict__ x0, int B) {
+               const float* __restrict__ bias, __nv_bfloat16* __restrict__ x0, __nv_bfloat16* __restrict__ xs0, int B) {
     extern __shared__ unsigned char raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sA = base;                                   // [2][3][16384]
@@ -784,6 +805,12 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
                 const int pix = t * 128 + lane_grp * 32 + lane;
                 if (pix < kStemPix) {
                     uint4* op = reinterpret_cast<uint4*>(x0 + ((int64_t)clip * kStemPix + pix) * 32);
+                    // block 0's skip conv reads x0 at (2y, 2x): emit those pixels as PS rows (32 of 64 channels used)
+                    using PSN = PsLayout<11, 13>;
+                    const int py = pix / 25, px = pix - py * 25;
+                    const bool xs = !(py & 1) && !(px & 1);
+                    const int64_t rg = (int64_t)clip * PSN::RPC + (py / 2 + 1) * PSN::WP + (px / 2 + 1);
+                    __nv_bfloat16* xrow = xs0 + rg * 64;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         uint32_t w[4];
@@ -794,6 +821,7 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
                             w[e] = *reinterpret_cast<uint32_t*>(&pk);
                         }
                         op[q] = make_uint4(w[0], w[1], w[2], w[3]);
+                        if (xs) *reinterpret_cast<uint4*>(xrow + ((q ^ (int)(rg & 7)) << 3)) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
             }
@@ -878,11 +906,11 @@ static cudaError_t tc_attr() {
 }
 
 int init_cnn_tc(cd_handle* h) {
-    CD_CUDA(h, (tc_attr<32, 64, 22, 25, 2, true, false, 2>()));
-    CD_CUDA(h, (tc_attr<64, 128, 11, 13, 2, true, false, 2>()));
-    CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s1_tc_kernel<64, 11, 13, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CD_CUDA(h, (tc_attr<32, 64, 22, 25, 2, false, false, 2>()));
+    CD_CUDA(h, (tc_attr<64, 128, 11, 13, 2, false, false, 2>()));
+    CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s1_tc_kernel<64, 11, 13, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)S1Shape<64, 11, 13>::SMEM));
-    CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s1_tc_kernel<128, 6, 7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s1_tc_kernel<128, 6, 7, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)S1Shape<128, 6, 7>::SMEM));
     CD_CUDA(h, cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStemSmem));
     CD_CUDA(h, cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -918,8 +946,12 @@ int upload_cnn_tc(cd_handle* h, const std::vector<std::vector<float>>& wf, const
         while (fblob.size() % 4) fblob.push_back(0.f);
         return off;
     };
+    // the skip projection is accumulated into conv2's tile (tenth tap), so its bias folds into conv2's
+    std::vector<float> b0c2s(bf[3]), b1c2s(bf[6]);
+    for (size_t i = 0; i < b0c2s.size(); ++i) b0c2s[i] += bf[2][i];
+    for (size_t i = 0; i < b1c2s.size(); ++i) b1c2s[i] += bf[5][i];
     const size_t o_stem_b = push(bf[0]), o_b0c1 = push(bf[1]), o_b0sk = push(bf[2]),
-                 o_b0c2 = push(bf[3]), o_b1c1 = push(bf[4]), o_b1sk = push(bf[5]), o_b1c2 = push(bf[6]),
+                 o_b0c2 = push(b0c2s), o_b1c1 = push(bf[4]), o_b1sk = push(bf[5]), o_b1c2 = push(b1c2s),
                  o_fcw = push(wf[7]), o_fcb = push(bf[7]);
     const size_t bf_bytes = total_bf * sizeof(__nv_bfloat16), f_bytes = fblob.size() * sizeof(float);
     if (!h->d_wblob_bf16) CD_CUDA(h, cudaMalloc(&h->d_wblob_bf16, bf_bytes + f_bytes));
@@ -943,7 +975,8 @@ int upload_cnn_tc(cd_handle* h, const std::vector<std::vector<float>>& wf, const
 }
 
 // Tensor-core workspace: fixed layout for kTcChunk clips, allocated and zeroed once per handle (the PS
-// buffers rely on their pad rows staying zero).  [maps | x0 | h1 (PS) | idt1 | x1 | h2 (PS, 2 planes) | idt2 | x2]
+// buffers rely on their pad rows staying zero).
+// [maps | x0 | h1 PS: conv plane + skip plane | x1 | h2 PS: 2 conv planes + skip plane | x2]
 constexpr int64_t kTcChunk = 2048;
 using Ps0 = PsLayout<11, 13>;
 using Ps1 = PsLayout<6, 7>;
@@ -953,11 +986,9 @@ constexpr int64_t al256(int64_t x) { return (x + 255) & ~int64_t(255); }
 constexpr int64_t kOffMap = 0;
 constexpr int64_t kOffX0 = kOffMap + al256(kTcChunk * kMapElems * 2);
 constexpr int64_t kOffH1 = kOffX0 + al256(kTcChunk * 22 * 25 * 32 * 2);
-constexpr int64_t kOffI1 = kOffH1 + al256(kPs0Rows * 128);
-constexpr int64_t kOffX1 = kOffI1 + al256(kTcChunk * 143 * 64 * 4);
+constexpr int64_t kOffX1 = kOffH1 + al256(2 * kPs0Rows * 128);
 constexpr int64_t kOffH2 = kOffX1 + al256(kTcChunk * 143 * 64 * 2);
-constexpr int64_t kOffI2 = kOffH2 + al256(2 * kPs1Rows * 128);
-constexpr int64_t kOffX2 = kOffI2 + al256(kTcChunk * 42 * 128 * 4);
+constexpr int64_t kOffX2 = kOffH2 + al256(3 * kPs1Rows * 128);
 constexpr int64_t kTcWsBytes = kOffX2 + al256(kTcChunk * 42 * 128 * 4);
 
 size_t cnn_tc_ws_bytes(int64_t) { return 0; }      // nothing from the shared workspace
@@ -998,47 +1029,46 @@ int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits,
     unsigned char* ws = h->d_ws_tc;
     __nv_bfloat16* maps = reinterpret_cast<__nv_bfloat16*>(ws + kOffMap);
     __nv_bfloat16* x0 = reinterpret_cast<__nv_bfloat16*>(ws + kOffX0);
-    __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(ws + kOffH1);
-    float* i1 = reinterpret_cast<float*>(ws + kOffI1);
+    __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(ws + kOffH1);      // plane 0: conv1 output, plane 1: x0 at (2y, 2x)
     __nv_bfloat16* x1 = reinterpret_cast<__nv_bfloat16*>(ws + kOffX1);
-    __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(ws + kOffH2);
-    float* i2 = reinterpret_cast<float*>(ws + kOffI2);
+    __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(ws + kOffH2);      // planes 0, 1: conv1 output, plane 2: x1 at (2y, 2x)
     float* x2 = reinterpret_cast<float*>(ws + kOffX2);
+    constexpr int64_t kPl0 = kPs0Rows * 64, kPl1 = kPs1Rows * 64;
     for (int64_t c0 = 0; c0 < B; c0 += kTcChunk) {
         const int n = (int)((B - c0) < kTcChunk ? (B - c0) : kTcChunk);
         if (d_feat) {
             map_from_feat_kernel<<<dim3((kMapElems / 2 + 255) / 256, n), 256, 0, s>>>(d_feat + c0 * kFeatElem, maps, n);
             h->launches += 1;
         }
-        stem_tc_kernel<<<n < h->sm_count ? n : h->sm_count, kTcThreads, kStemSmem, s>>>(maps, W.stem_w, W.stem_b, x0, n);
+        stem_tc_kernel<<<n < h->sm_count ? n : h->sm_count, kTcThreads, kStemSmem, s>>>(maps, W.stem_w, W.stem_b, x0,
+                                                                                         h1 + kPl0, n);
         h->launches += 1;
         TcArgs a{};
         a.B = n;
-        a.x = x0; a.w = W.b0c1; a.wskip = W.b0sk; a.bias = W.b0c1_b; a.bias_skip = W.b0sk_b; a.y_bf16 = h1; a.idt_out = i1;
-        a.ps_plane_elems = 0;
-        launch_tc<32, 64, 22, 25, 2, true, false, 2>(h, a, s);
+        a.x = x0; a.w = W.b0c1; a.bias = W.b0c1_b; a.y_bf16 = h1; a.ps_plane_elems = kPl0;
+        launch_tc<32, 64, 22, 25, 2, false, false, 2>(h, a, s);
         {
             using S = S1Shape<64, 11, 13>;
             S1Args q{};
-            q.x = h1; q.w = W.b0c2; q.bias = W.b0c2_b; q.idt = i1; q.y_bf16 = x1; q.ps_plane_elems = 0; q.n = n;
+            q.x = h1; q.w = W.b0c2; q.wskip = W.b0sk; q.bias = W.b0c2_b; q.y_bf16 = x1; q.xs_out = h2 + 2 * kPl1;
+            q.ps_plane_elems = kPl0; q.n = n;
             const int tiles = (int)(((int64_t)n * Ps0::RPC + 127) / 128);
             const int grid = (tiles < h->sm_count ? tiles : h->sm_count) * S::HALVES;
-            conv3x3_s1_tc_kernel<64, 11, 13, false><<<grid, kS1Threads, S::SMEM, s>>>(q);
+            conv3x3_s1_tc_kernel<64, 11, 13, false, true><<<grid, kS1Threads, S::SMEM, s>>>(q);
             h->launches += 1;
         }
         a = TcArgs{};
         a.B = n;
-        a.x = x1; a.w = W.b1c1; a.wskip = W.b1sk; a.bias = W.b1c1_b; a.bias_skip = W.b1sk_b; a.y_bf16 = h2; a.idt_out = i2;
-        a.ps_plane_elems = kPs1Rows * 64;
-        launch_tc<64, 128, 11, 13, 2, true, false, 2>(h, a, s);
+        a.x = x1; a.w = W.b1c1; a.bias = W.b1c1_b; a.y_bf16 = h2; a.ps_plane_elems = kPl1;
+        launch_tc<64, 128, 11, 13, 2, false, false, 2>(h, a, s);
         {
             using S = S1Shape<128, 6, 7>;
             S1Args q{};
-            q.x = h2; q.w = W.b1c2; q.bias = W.b1c2_b; q.idt = i2; q.y_f32 = x2; q.ps_plane_elems = kPs1Rows * 64; q.n = n;
+            q.x = h2; q.w = W.b1c2; q.wskip = W.b1sk; q.bias = W.b1c2_b; q.y_f32 = x2; q.ps_plane_elems = kPl1; q.n = n;
             const int tiles = (int)(((int64_t)n * Ps1::RPC + 127) / 128);
             const int per_half = h->sm_count / S::HALVES;
             const int grid = (tiles < per_half ? tiles : per_half) * S::HALVES;
-            conv3x3_s1_tc_kernel<128, 6, 7, true><<<grid, kS1Threads, S::SMEM, s>>>(q);
+            conv3x3_s1_tc_kernel<128, 6, 7, true, false><<<grid, kS1Threads, S::SMEM, s>>>(q);
             h->launches += 1;
         }
         head_kernel<<<n, 128, 0, s>>>(x2, W.fc_w, W.fc_b, d_logits + c0 * CD_N_CLASSES, n);
