@@ -125,6 +125,10 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// Advance a descriptor's start address by `bytes` (multiple of 16; the 14-bit field holds addr >> 4 and
+// shared memory is < 256 KB, so the add never carries out of the field).  One 64-bit add per MMA operand
+// instead of rebuilding the descriptor keeps the single issuing thread off the critical path.
+__device__ __forceinline__ uint64_t desc_adv(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 __device__ __forceinline__ uint32_t swz128(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
 }  // namespace tc
@@ -361,11 +365,10 @@ conv3x3_tc_kernel(const TcArgs a) {
                     tc::mbar_wait(&full_bar[s], (uint32_t)((it / kTcStages) & 1));
                     tc::tc_fence_after();
                     const uint32_t sa = tc::s32(base + (size_t)s * S::STAGE_BYTES);
-                    const uint32_t sb = sa + S::A_BYTES;
+                    const uint64_t da = tc::desc_sw128(sa), db = tc::desc_sw128(sa + S::A_BYTES);
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4)
-                        tc::umma_bf16(d_conv, tc::desc_sw128(sa + k4 * 32), tc::desc_sw128(sb + k4 * 32), IDESC,
-                                      (kc | k4) != 0);
+                        tc::umma_bf16(d_conv, tc::desc_adv(da, k4 * 32), tc::desc_adv(db, k4 * 32), IDESC, (kc | k4) != 0);
                     if (SKIP) {
                         // centre tap (ky = kx = 1, tap 4) = K range [4*CIN, 5*CIN)
                         constexpr int KC_C = (4 * CIN) / 64, K4_0 = ((4 * CIN) % 64) / 16, NK4 = S::SKIP_K / 16;
@@ -582,29 +585,29 @@ conv3x3_s1_tc_kernel(const S1Args a) {
                 const uint32_t par = (uint32_t)((it / S::STAGES) & 1);
                 tc::mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
                 const uint32_t d = tmem_base + acc * 64;
-                const uint32_t sw = tc::s32(s_w);
+                const uint64_t dw = tc::desc_sw128(tc::s32(s_w));
 #pragma unroll
                 for (int q = 0; q < S::NPLT; ++q) {
                     const int bi = s * S::NPLT + q;
                     tc::mbar_wait(&full_bar[bi], par);
                     tc::tc_fence_after();
-                    const uint32_t sa = tc::s32(base + (size_t)bi * S::A_BYTES);
+                    const uint64_t da = tc::desc_sw128(tc::s32(base + (size_t)bi * S::A_BYTES));
                     if (q < S::NPL) {
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
                             const uint32_t shift = (uint32_t)((tap / 3) * PS::WP + (tap % 3)) * 128;   // rows down the image
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4)
-                                tc::umma_bf16(d, tc::desc_sw128(sa + shift + k4 * 32),
-                                              tc::desc_sw128(sw + (tap * S::NPL + q) * 8192 + k4 * 32), IDESC,
+                                tc::umma_bf16(d, tc::desc_adv(da, shift + k4 * 32),
+                                              tc::desc_adv(dw, (tap * S::NPL + q) * 8192 + k4 * 32), IDESC,
                                               (q | tap | k4) != 0);
                         }
                     } else {
                         const uint32_t shift = (uint32_t)(PS::WP + 1) * 128;                          // centre tap
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4)
-                            tc::umma_bf16(d, tc::desc_sw128(sa + shift + k4 * 32),
-                                          tc::desc_sw128(sw + 9 * S::NPL * 8192 + k4 * 32), IDESC, 1u);
+                            tc::umma_bf16(d, tc::desc_adv(da, shift + k4 * 32),
+                                          tc::desc_adv(dw, 9 * S::NPL * 8192 + k4 * 32), IDESC, 1u);
                     }
                     tc::tc_commit(&empty_bar[bi]);        // this plane's slot can be refilled for the next tile
                 }
@@ -771,11 +774,11 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
                     tc::mbar_wait(&full_bar[s], (uint32_t)((it >> 1) & 1));
                     tc::tc_fence_after();
                     const uint32_t d = tmem_base + s * 128;
-                    const uint32_t sa = tc::s32(sA + s * kStemABytes), sb = tc::s32(sB);
+                    const uint64_t da = tc::desc_sw128(tc::s32(sA + s * kStemABytes)), db = tc::desc_sw128(tc::s32(sB));
 #pragma unroll
                     for (int q = 0; q < 9; ++q) {                // K = 144 = 9 x 16
                         const uint32_t off = (q >> 2) * 16384 + (q & 3) * 32;
-                        tc::umma_bf16(d, tc::desc_sw128(sa + off), tc::desc_sw128(sb + off), IDESC, q != 0);
+                        tc::umma_bf16(d, tc::desc_adv(da, off), tc::desc_adv(db, off), IDESC, q != 0);
                     }
                     tc::tc_commit(&empty_bar[s]);
                     tc::tc_commit(&tfull_bar[s]);
