@@ -288,7 +288,7 @@ static int e2e_impl(cd_handle* h, const float* d_audio, int64_t stride_or_hop, i
     // process in slabs so a slab's features stay L2-resident between the two stages.  bf16: the
     // feature kernel writes the stem's bf16 map straight into the CNN workspace (fp32 features only
     // if the caller asked for them); fp32: features go through an fp32 buffer.
-    const int64_t slab = 2048;
+    const int64_t slab = 8192;
     const bool tcp = precision == CD_PRECISION_BF16;
     const size_t cnn_ws = tcp ? cnn_tc_ws_bytes(slab) : cnn_fp32_ws_bytes(slab);
     const size_t feat_bytes = (tcp || d_feat_opt) ? 0 : (size_t)slab * kFeatElem * sizeof(float);
@@ -342,7 +342,7 @@ int cd_e2e_forward_host(cd_handle* h, const float* h_audio, int64_t B, float* h_
         return set_err(h, CD_E_ARG, "precision must be CD_PRECISION_FP32 or CD_PRECISION_BF16");
     if (B == 0) return CD_OK;
     DeviceGuard g(h->device);
-    const int64_t chunk = 2048;
+    const int64_t chunk = 4096;                 // copy/compute overlap granularity (<= the CNN workspace chunk)
     if (!h->pipe_streams[0]) {
         for (int i = 0; i < 3; ++i) {
             CD_CUDA(h, cudaStreamCreateWithFlags(&h->pipe_streams[i], cudaStreamNonBlocking));
