@@ -144,6 +144,7 @@ int cd_destroy(cd_handle* h) {
     cudaFree(h->d_wblob);
     cudaFree(h->d_wblob_bf16);
     cudaFree(h->d_ws_tc);
+    cudaFree(h->d_ws_stream);
     cudaFree(h->d_ws);
     for (int i = 0; i < 3; ++i) {
         if (h->pipe_streams[i]) cudaStreamDestroy(h->pipe_streams[i]);

@@ -69,6 +69,9 @@ struct cd_handle {
     __nv_bfloat16* d_wblob_bf16 = nullptr;
     unsigned char* d_ws_tc = nullptr;    // tensor-core path activations (fixed layout, zero-initialised pads)
 
+    float* d_ws_stream = nullptr;        // shared-STFT streaming: mel power of the global frames + block maxima
+    size_t ws_stream_bytes = 0;
+
     // workspace (grown on demand, never shrunk)
     float* d_ws = nullptr;
     size_t ws_bytes = 0;

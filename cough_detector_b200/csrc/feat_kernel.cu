@@ -130,6 +130,11 @@ __device__ __forceinline__ float block_reduce(float v, float* red) {
     return r;
 }
 
+// AmplitudeToDB('power'): 10 log10(max(x, 1e-10)) (torchaudio functional.py:390) via MUFU.LG2
+__device__ __forceinline__ float power_to_db(float x) {
+    return 3.01029995663981195f * __log2f(fmaxf(x, 1e-10f));      // 10 * log10(2) * log2(x)
+}
+
 // One windowed sample pair for FFT point n of the frame pair starting at sample `base0`.
 template <bool EDGE>
 __device__ __forceinline__ float2 load_point(const float* __restrict__ clip, float w, int n, int base0, bool second) {
@@ -147,13 +152,14 @@ __device__ __forceinline__ float2 load_point(const float* __restrict__ clip, flo
 
 // The per-warp work item: frames 2p and 2p+1 -> 2 x 64 dB values in the tile.  Returns the lane's
 // running max of the dB values it produced.
-template <bool EDGE>
-__device__ __forceinline__ float frame_pair(FeatSmem& S, const float* __restrict__ clip, float2* __restrict__ xb,
+// RAW = false: dB values go to dst[band * band_stride + {0, frame_stride}] (the smem tile).
+// RAW = true : un-logged mel POWER goes there instead (shared STFT frames of the streaming path).
+template <bool EDGE, bool RAW, class SM>
+__device__ __forceinline__ float frame_pair(SM& S, const float* __restrict__ clip, float2* __restrict__ xb,
                                             const float (&wA)[7], const float (&wB)[6],
-                                            const float (&mw)[kMelSlots], int bin_lo, int bin_hi, int p, int lane) {
-    const int c = lane & 7, j = lane >> 3;
-    const int base0 = 2 * kHop * p - kWin / 2;      // sample index of window tap 0 of frame 2p
-    const bool second = (2 * p + 1) < kFrames;
+                                            const float (&mw)[kMelSlots], int bin_lo, int bin_hi, int base0, bool second,
+                                            int lane, float* __restrict__ dst, int band_stride, int frame_stride) {
+    const int c = lane & 7, j = lane >> 3;             // base0: sample index of window tap 0 of the first frame
 
     // ---- stage 1: radix-8 over a (n = 64a + m), m = lane and lane + 32 ------------------------
     float2 A[8], B[8];
@@ -275,19 +281,25 @@ __device__ __forceinline__ float frame_pair(FeatSmem& S, const float* __restrict
     __syncwarp();                                    // xb is rewritten by the next pair
 
     // ---- AmplitudeToDB: 10 log10(max(x, 1e-10)) (torchaudio functional.py:390) ------------------
-    const float kDb = 3.01029995663981195f;          // 10 * log10(2)
-    const float d0 = kDb * __log2f(fmaxf(lo.x, 1e-10f));
-    const float d2 = kDb * __log2f(fmaxf(hi.x, 1e-10f));
-    float* row_lo = S.db + lane * kFrames + 2 * p;
-    float* row_hi = S.db + (lane + 32) * kFrames + 2 * p;
+    float* row_lo = dst + lane * band_stride;
+    float* row_hi = dst + (lane + 32) * band_stride;
+    if (RAW) {
+        row_lo[0] = lo.x;
+        row_hi[0] = hi.x;
+        if (second) {
+            row_lo[frame_stride] = lo.y;
+            row_hi[frame_stride] = hi.y;
+        }
+        return 0.f;
+    }
+    const float d0 = power_to_db(lo.x), d2 = power_to_db(hi.x);
     row_lo[0] = d0;
     row_hi[0] = d2;
     float m = fmaxf(d0, d2);
     if (second) {
-        const float d1 = kDb * __log2f(fmaxf(lo.y, 1e-10f));
-        const float d3 = kDb * __log2f(fmaxf(hi.y, 1e-10f));
-        row_lo[1] = d1;
-        row_hi[1] = d3;
+        const float d1 = power_to_db(lo.y), d3 = power_to_db(hi.y);
+        row_lo[frame_stride] = d1;
+        row_hi[frame_stride] = d3;
         m = fmaxf(m, fmaxf(d1, d3));
     }
     return m;
@@ -316,6 +328,77 @@ __device__ __forceinline__ float mfcc_par(const float* __restrict__ db, float* _
         s += acc[i];
     }
     return s;
+}
+
+// Everything after the dB tile is complete: top_db floor, mel01 rows, DCT-13, mean / unbiased std
+// normalisation, deltas; fp32 features to `out` and/or the stem's bf16 map to `mo` (either may be null).
+// Ends with the block in sync except for the final stores.
+template <class SM>
+__device__ __forceinline__ void feat_tail(SM& S, float wmax, float* __restrict__ out, __nv_bfloat16* __restrict__ mo, int tid) {
+    const float top = block_reduce<true>(wmax, S.red);             // barrier: dB tile complete
+    const float floor_db = top - 80.0f;                            // top_db = 80
+
+    // ---- mel block rows 0..63: max(dB, floor) -> (dB + 80) / 80 -> clamp ------------------------
+    // The CNN stem's operand rides along: the same values rounded to bf16 in a zero-padded
+    // [93 rows: -3..89][112 cols: -3..108] map, so the stem stages a clip with one bulk copy.
+    for (int i = tid; i < kMels * kFrames; i += kFeatThreads) {
+        const float v = fmaxf(S.db[i], floor_db);
+        S.db[i] = v;
+        const float x01 = fminf(fmaxf((v + 80.0f) * 0.0125f, 0.f), 1.f);
+        if (out) out[i] = x01;
+        if (mo) {
+            const int r = i / kFrames;
+            mo[(r + 3) * kMapPitch + (i - r * kFrames) + 3] = __float2bfloat16_rn(x01);
+        }
+    }
+    if (mo) {       // zero padding: rows -3..-1 whole, cols -3..-1 and 101..108 of the 90 data rows
+        for (int i = tid; i < 3 * kMapPitch + kFeat * 11; i += kFeatThreads) {
+            int idx = i;
+            if (i >= 3 * kMapPitch) {
+                const int q = i - 3 * kMapPitch, row = q / 11, e = q - row * 11;
+                idx = (row + 3) * kMapPitch + (e < 3 ? e : kFrames + e);
+            }
+            mo[idx] = __float2bfloat16_rn(0.f);
+        }
+    }
+    __syncthreads();
+
+    // ---- MFCC = DCT-II(13 x 64) of the floored dB, then (x - mean) / (std + 1e-8) ---------------
+    float* mf = reinterpret_cast<float*>(&S.xb[0][0]);             // [13][101], FFT scratch is idle now
+    float part = 0.f;
+    {
+        static_assert(kFeatThreads == 256, "two parity groups of 128 threads");
+        const int t = tid & 127;
+        if (t < kFrames) part = (tid >> 7) ? mfcc_par<1>(S.db, mf, t) : mfcc_par<0>(S.db, mf, t);
+    }
+    constexpr int kN = kMfcc * kFrames;                            // 1313
+    const float mean = block_reduce<false>(part, S.red) * (1.0f / kN);
+    float ss = 0.f;
+    for (int i = tid; i < kN; i += kFeatThreads) {
+        const float dlt = mf[i] - mean;
+        ss = fmaf(dlt, dlt, ss);
+    }
+    ss = block_reduce<false>(ss, S.red);
+    const float inv_std = 1.0f / (sqrtf(ss * (1.0f / (kN - 1))) + 1e-8f);
+    {
+        for (int i = tid; i < kN; i += kFeatThreads) {
+            const int cidx = i / kFrames, t = i - cidx * kFrames;
+            const float* row = mf + cidx * kFrames;
+            // __fmul_rn: never contracted into an FMA, so the bf16 map below sees identical values
+            const float x0 = __fmul_rn(row[t] - mean, inv_std);
+            const float xp = __fmul_rn(row[min(t + 1, kFrames - 1)] - mean, inv_std);
+            const float xm = __fmul_rn(row[max(t - 1, 0)] - mean, inv_std);
+            const float dl = (xp - xm) * 0.5f;                             // compute_deltas (:353-355)
+            if (out) {
+                out[(kMels + cidx) * kFrames + t] = x0;
+                out[(kMels + kMfcc + cidx) * kFrames + t] = dl;
+            }
+            if (mo) {
+                mo[(kMels + cidx + 3) * kMapPitch + t + 3] = __float2bfloat16_rn(x0);
+                mo[(kMels + kMfcc + cidx + 3) * kMapPitch + t + 3] = __float2bfloat16_rn(dl);
+            }
+        }
+    }
 }
 
 struct ClipDesc {
@@ -428,76 +511,132 @@ feat_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offs, c
         float wmax = -INFINITY;
         for (int p = warp; p < kPairs; p += kFeatWarps) {
             const bool edge = (p == 0) || (p >= 49);
-            wmax = fmaxf(wmax, edge ? frame_pair<true>(S, clip, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, p, lane)
-                                    : frame_pair<false>(S, clip, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, p, lane));
+            float* dst = S.db + 2 * p;
+            const int base0 = 2 * kHop * p - kWin / 2;
+            const bool second = (2 * p + 1) < kFrames;
+            wmax = fmaxf(wmax, edge ? frame_pair<true, false>(S, clip, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, base0, second, lane, dst, kFrames, 1)
+                                    : frame_pair<false, false>(S, clip, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, base0, second, lane, dst, kFrames, 1));
         }
-        const float top = block_reduce<true>(wmax, S.red);             // barrier: dB tile complete
-        const float floor_db = top - 80.0f;                            // top_db = 80
-
-        // ---- mel block rows 0..63: max(dB, floor) -> (dB + 80) / 80 -> clamp ------------------------
-        // The CNN stem's operand rides along: the same values rounded to bf16 in a zero-padded
-        // [93 rows: -3..89][112 cols: -3..108] map, so the stem stages a clip with one bulk copy.
-        float* out = feat ? feat + b * (int64_t)kFeatElem : nullptr;
-        __nv_bfloat16* mo = map_out ? map_out + b * (int64_t)kMapElems : nullptr;
-        for (int i = tid; i < kMels * kFrames; i += kFeatThreads) {
-            const float v = fmaxf(S.db[i], floor_db);
-            S.db[i] = v;
-            const float x01 = fminf(fmaxf((v + 80.0f) * 0.0125f, 0.f), 1.f);
-            if (out) out[i] = x01;
-            if (mo) {
-                const int r = i / kFrames;
-                mo[(r + 3) * kMapPitch + (i - r * kFrames) + 3] = __float2bfloat16_rn(x01);
-            }
-        }
-        if (mo) {       // zero padding: rows -3..-1 whole, cols -3..-1 and 101..108 of the 90 data rows
-            for (int i = tid; i < 3 * kMapPitch + kFeat * 11; i += kFeatThreads) {
-                int idx = i;
-                if (i >= 3 * kMapPitch) {
-                    const int q = i - 3 * kMapPitch, row = q / 11, e = q - row * 11;
-                    idx = (row + 3) * kMapPitch + (e < 3 ? e : kFrames + e);
-                }
-                mo[idx] = __float2bfloat16_rn(0.f);
-            }
-        }
-        __syncthreads();
-
-        // ---- MFCC = DCT-II(13 x 64) of the floored dB, then (x - mean) / (std + 1e-8) ---------------
-        float* mf = reinterpret_cast<float*>(&S.xb[0][0]);             // [13][101], FFT scratch is idle now
-        float part = 0.f;
-        {
-            static_assert(kFeatThreads == 256, "two parity groups of 128 threads");
-            const int t = tid & 127;
-            if (t < kFrames) part = (tid >> 7) ? mfcc_par<1>(S.db, mf, t) : mfcc_par<0>(S.db, mf, t);
-        }
-        constexpr int kN = kMfcc * kFrames;                            // 1313
-        const float mean = block_reduce<false>(part, S.red) * (1.0f / kN);
-        float ss = 0.f;
-        for (int i = tid; i < kN; i += kFeatThreads) {
-            const float dlt = mf[i] - mean;
-            ss = fmaf(dlt, dlt, ss);
-        }
-        ss = block_reduce<false>(ss, S.red);
-        const float inv_std = 1.0f / (sqrtf(ss * (1.0f / (kN - 1))) + 1e-8f);
-        {
-            for (int i = tid; i < kN; i += kFeatThreads) {
-                const int cidx = i / kFrames, t = i - cidx * kFrames;
-                const float* row = mf + cidx * kFrames;
-                // __fmul_rn: never contracted into an FMA, so the bf16 map below sees identical values
-                const float x0 = __fmul_rn(row[t] - mean, inv_std);
-                const float xp = __fmul_rn(row[min(t + 1, kFrames - 1)] - mean, inv_std);
-                const float xm = __fmul_rn(row[max(t - 1, 0)] - mean, inv_std);
-                const float dl = (xp - xm) * 0.5f;                             // compute_deltas (:353-355)
-                if (out) {
-                    out[(kMels + cidx) * kFrames + t] = x0;
-                    out[(kMels + kMfcc + cidx) * kFrames + t] = dl;
-                }
-                if (mo) {
-                    mo[(kMels + cidx + 3) * kMapPitch + t + 3] = __float2bfloat16_rn(x0);
-                    mo[(kMels + kMfcc + cidx + 3) * kMapPitch + t + 3] = __float2bfloat16_rn(dl);
-                }
-            }
-        }
+        feat_tail(S, wmax, feat ? feat + b * (int64_t)kFeatElem : nullptr,
+                  map_out ? map_out + b * (int64_t)kMapElems : nullptr, tid);
         __syncthreads();                                               // xb / db / clip[cur] free again
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// streaming with shared STFT frames (RealtimePreprocessor.add_audio, src/preprocessing.py:582-612)
+// ----------------------------------------------------------------------------------------------
+// With hop = 160 h, window j's frame t is the stream's global frame j h + t (centred at sample
+// 160 (j h + t)); only frames 0, 1, 99, 100 of a window see its reflect padding.  So the mel POWER of
+// every global frame is computed once (stream_mel_kernel), each window takes frames 2..97 from there,
+// scaled by 1/peak^2 (peak normalisation is a scalar on the samples), and recomputes just the pairs
+// (0,1), (98,99), (100,-) from its own samples.  The window peak is the max of 100 per-hop block maxima.
+struct MelSmem {
+    float2 xb[kFeatWarps][kXbElems];
+    float2 tw1[7][64];
+    float2 tw2[7][8];
+};
+struct StreamSmem {
+    float2 xb[kFeatWarps][kXbElems];
+    float  db[kMels * kFrames];
+    float2 tw1[7][64];
+    float2 tw2[7][8];
+    float  red[64];
+};
+
+template <class SM>
+__device__ __forceinline__ void load_lane_tables(SM& S, const FeatTables* __restrict__ tables, float (&mw)[kMelSlots],
+                                                 int& bin_lo, int& bin_hi, int tid, int lane) {
+    const float* src = reinterpret_cast<const float*>(tables);
+    float* dst = reinterpret_cast<float*>(&S.tw1[0][0]);
+    constexpr int n = (sizeof(S.tw1) + sizeof(S.tw2)) / 4;
+    for (int i = tid; i < n; i += kFeatThreads) dst[i] = src[i];
+#pragma unroll
+    for (int s = 0; s < kMelSlots; ++s) mw[s] = tables->melt[s][lane].x;
+    const int p0 = __float_as_int(tables->melt[0][lane].y), p3 = __float_as_int(tables->melt[kMelSlotsLo][lane].y);
+    bin_lo = p0 - p0 / 9;
+    bin_hi = p3 - p3 / 9;
+}
+
+__device__ __forceinline__ void lane_window(const FeatTables* __restrict__ tables, float inv, int lane, float (&wA)[7], float (&wB)[6]) {
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        wA[a] = __ldg(&tables->win[64 * a + lane]) * inv;
+        wB[a] = __ldg(&tables->win[64 * a + lane + 32]) * inv;
+    }
+    wA[6] = lane < 16 ? __ldg(&tables->win[384 + lane]) * inv : 0.f;
+}
+
+// bmax[i] = max |x[160 i .. 160 i + 159]|, one warp per block
+__global__ void __launch_bounds__(256)
+block_max_kernel(const float* __restrict__ audio, int64_t n_blocks, float* __restrict__ bmax) {
+    const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n_blocks) return;
+    const float* p = audio + i * kHop;
+    float m = 0.f;
+    for (int k = threadIdx.x & 31; k < kHop; k += 32) m = fmaxf(m, fabsf(p[k]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) bmax[i] = m;
+}
+
+// melp[f][64] = un-normalised mel power of global frame f, f in [2, F)
+__global__ void __launch_bounds__(kFeatThreads, 2)
+stream_mel_kernel(const float* __restrict__ audio, int64_t F, float* __restrict__ melp, const FeatTables* __restrict__ tables) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    MelSmem& S = *reinterpret_cast<MelSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float mw[kMelSlots], wA[7], wB[6];
+    int bin_lo, bin_hi;
+    load_lane_tables(S, tables, mw, bin_lo, bin_hi, tid, lane);
+    lane_window(tables, 1.0f, lane, wA, wB);
+    __syncthreads();
+    const int64_t n_pairs = (F - 2 + 1) / 2;
+    for (int64_t q = (int64_t)blockIdx.x * kFeatWarps + warp; q < n_pairs; q += (int64_t)gridDim.x * kFeatWarps) {
+        int64_t f0 = 2 + 2 * q;
+        if (f0 + 1 >= F) f0 = F - 2;                  // odd tail: redo (F-2, F-1); both writers store identical values
+        const float* base = audio + f0 * kHop - kWin / 2;
+        frame_pair<false, true>(S, base, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, 0, true, lane, melp + f0 * kMels, 1, kMels);
+    }
+}
+
+__global__ void __launch_bounds__(kFeatThreads, 2)
+stream_window_kernel(const float* __restrict__ audio, int64_t hop, int64_t n_windows, const float* __restrict__ melp,
+                     const float* __restrict__ bmax, float* __restrict__ feat, __nv_bfloat16* __restrict__ map_out,
+                     const FeatTables* __restrict__ tables) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    StreamSmem& S = *reinterpret_cast<StreamSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float mw[kMelSlots];
+    int bin_lo, bin_hi;
+    load_lane_tables(S, tables, mw, bin_lo, bin_hi, tid, lane);
+    __syncthreads();
+    const int64_t h = hop / kHop;
+    for (int64_t j = blockIdx.x; j < n_windows; j += gridDim.x) {
+        float peak = tid < kSeg / kHop ? bmax[j * h + tid] : 0.f;
+        peak = block_reduce<true>(peak, S.red);
+        const float inv = peak > 0.f ? 1.0f / peak : 1.0f;           // normalize(): skipped for silence
+        float wmax = -INFINITY;
+        if (warp < 3) {
+            // frames that touch this window's reflect padding: pairs (0,1), (98,99), (100,-)
+            float wA[7], wB[6];
+            lane_window(tables, inv, lane, wA, wB);
+            const int p = warp == 0 ? 0 : 48 + warp;
+            wmax = frame_pair<true, false>(S, audio + j * hop, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, 2 * kHop * p - kWin / 2,
+                                           (2 * p + 1) < kFrames, lane, S.db + 2 * p, kFrames, 1);
+        } else {
+            // frames 2..97 come from the shared global frames j h + t
+            const float inv2 = inv * inv;
+            const float* src = melp + (j * h + 2) * kMels;
+            for (int i = tid - 96; i < 96 * kMels; i += kFeatThreads - 96) {
+                const int t = i >> 6, m = i & 63;
+                const float d = power_to_db(src[i] * inv2);
+                S.db[m * kFrames + t + 2] = d;
+                wmax = fmaxf(wmax, d);
+            }
+        }
+        feat_tail(S, wmax, feat ? feat + j * (int64_t)kFeatElem : nullptr,
+                  map_out ? map_out + j * (int64_t)kMapElems : nullptr, tid);
+        __syncthreads();
     }
 }
 
@@ -553,6 +692,8 @@ int build_feat_tables(cd_handle* h) {
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_dct, dct, sizeof(dct));
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeatSmem));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(stream_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem));
     delete t;
     if (e != cudaSuccess) return set_err(h, CD_E_CUDA, "feature tables upload", e);
     return CD_OK;
@@ -562,6 +703,33 @@ int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets
                     int64_t stride_or_hop, int mode, int64_t B, float* d_feat, __nv_bfloat16* d_map, cudaStream_t s) {
     if (B == 0) return CD_OK;
     const int64_t slots = 2 * (int64_t)h->sm_count;     // two resident CTAs per SM
+    if ((mode & kModeMask) == kModeStream && stride_or_hop % kHop == 0 && stride_or_hop <= kSeg / 2 && B >= 2) {
+        // overlapping windows on the frame grid: share the STFT frames
+        const int64_t hop = stride_or_hop, hh = hop / kHop;
+        const int64_t F = (B - 1) * hh + 99;                         // global frames 2 .. F-1 are needed
+        const int64_t n_blocks = (B - 1) * hh + kSeg / kHop;
+        const size_t need = ((size_t)F * kMels + (size_t)n_blocks) * sizeof(float);
+        if (need > h->ws_stream_bytes) {
+            CD_CUDA(h, cudaDeviceSynchronize());
+            cudaFree(h->d_ws_stream);
+            h->d_ws_stream = nullptr;
+            h->ws_stream_bytes = 0;
+            cudaError_t e = cudaMalloc(&h->d_ws_stream, need);
+            if (e != cudaSuccess) return set_err(h, CD_E_NOMEM, "stream workspace allocation", e);
+            h->ws_stream_bytes = need;
+        }
+        float* melp = h->d_ws_stream;
+        float* bmax = melp + (size_t)F * kMels;
+        block_max_kernel<<<(unsigned)((n_blocks + 7) / 8), 256, 0, s>>>(d_audio, n_blocks, bmax);
+        const int64_t pair_ctas = ((F - 1) / 2 + kFeatWarps - 1) / kFeatWarps;
+        stream_mel_kernel<<<(int)(pair_ctas < 4 * slots ? pair_ctas : 4 * slots), kFeatThreads, sizeof(MelSmem), s>>>(
+            d_audio, F, melp, h->d_tables);
+        stream_window_kernel<<<(int)(B < slots ? B : slots), kFeatThreads, sizeof(StreamSmem), s>>>(
+            d_audio, hop, B, melp, bmax, d_feat, d_map, h->d_tables);
+        h->launches += 3;
+        CD_CUDA(h, cudaGetLastError());
+        return CD_OK;
+    }
     const int grid = (int)(B < slots ? B : slots);
     feat_kernel<<<grid, kFeatThreads, sizeof(FeatSmem), s>>>(d_audio, d_offsets, d_lengths, stride_or_hop, mode, B,
                                                             d_feat, d_map, h->d_tables);

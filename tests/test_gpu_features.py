@@ -106,12 +106,43 @@ def test_stream_matches_reference_realtime_preprocessor():
         got = torch.stack(got)
         assert got.shape == ref.shape
         assert (got - ref).abs().max().item() <= TOL
+        # one call over the whole stream takes the shared-STFT path (global frames computed once); the
+        # chunked calls above mostly see single windows -> same numbers up to fp32 rounding
         allatonce = rp.stream_features(stream)
-        assert torch.equal(allatonce, got)
+        assert allatonce.shape == ref.shape
+        assert (allatonce - ref).abs().max().item() <= TOL
+        assert (allatonce - got).abs().max().item() <= 2e-5
     odd = RealtimePreprocessor(window_duration=1.0, hop_duration=0.0123, **FLAGS)   # hop 196: unaligned windows
     f = odd.stream_features(stream[:20000])
     want = co.stream_features(stream[:20000], 196)
     assert f.shape == want.shape and (f - want).abs().max().item() <= TOL
+
+
+def test_stream_shared_frames_long_and_sharded():
+    """BASELINE config 4 in miniature: 10 min of audio at 100 ms hop; shared-STFT path vs per-window path,
+    and time-sharded (overlapping shards, as the 8-GPU split does) vs unsharded."""
+    from cough_detector_b200 import sharding
+    h = _lib.get_handle(0)
+    n, hop = 16000 * 600, 1600
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(n, device="cuda", generator=g) * (0.05 + 0.5 * torch.rand(n // 16000, device="cuda", generator=g)).repeat_interleave(16000)
+    shared = h.feat_forward_stream(x, hop)                          # hop % 160 == 0 -> shared frames
+    nw = shared.shape[0]
+    assert nw == sharding.stream_windows(n, hop) == 5991
+    idx = torch.tensor([0, 1, 2, 77, 2999, 5989, 5990])
+    wins = torch.stack([x[i * hop:i * hop + 16000] for i in idx.tolist()])
+    per_window = h.feat_forward(wins)                               # the batch kernel, one clip per window
+    assert (shared[idx.cuda()] - per_window).abs().max().item() <= 2e-5
+    ex = co.Explicit32()
+    for k, i in enumerate(idx.tolist()[:3]):
+        ref = ex.features(co.normalize(wins[k].cpu().reshape(1, -1)))[0]
+        assert (shared[i, 0].cpu() - ref).abs().max().item() <= TOL
+    parts = []
+    for r in range(3):
+        w0, cnt, s0, s1 = sharding.shard_stream(n, hop, r, 3)
+        parts.append(h.feat_forward_stream(x[s0:s1], hop))
+        assert parts[-1].shape[0] == cnt
+    assert torch.equal(torch.cat(parts), shared)                    # shard boundaries do not change any window
 
 
 def test_full_size_config2_properties():
