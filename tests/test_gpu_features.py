@@ -142,7 +142,9 @@ def test_stream_shared_frames_long_and_sharded():
         w0, cnt, s0, s1 = sharding.shard_stream(n, hop, r, 3)
         parts.append(h.feat_forward_stream(x[s0:s1], hop))
         assert parts[-1].shape[0] == cnt
-    assert torch.equal(torch.cat(parts), shared)                    # shard boundaries do not change any window
+    # shard boundaries re-pair the shared frames (a frame may ride in the real or the imaginary half of its
+    # packed FFT), so windows agree to fp32 rounding, not bit for bit
+    assert (torch.cat(parts) - shared).abs().max().item() <= 2e-5
 
 
 def test_full_size_config2_properties():

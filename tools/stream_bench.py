@@ -23,6 +23,9 @@ for name, hp in (("shared_stft_hop1600", 1600), ("per_window_hop1599", 1599)):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     out[name] = {"windows": lg.shape[0], "ms": ms, "windows_per_s": lg.shape[0] / ms * 1e3, "x_realtime": 3600.0 / (ms * 1e-3)}
+    for _ in range(3):
+        ft = h.feat_forward_stream(x[: 16000 + hp * 8191], hp)
+    torch.cuda.synchronize()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(5):
