@@ -688,12 +688,7 @@ constexpr int kMapBytes = kMapElems * 2;          // 20 832
 constexpr int kMapBytesPad = (kMapBytes + 127) & ~127;
 constexpr size_t kStemSmem = 1024 + 2 * kStemABytes + kStemBBytes + 2 * kMapBytesPad + 128;
 
-// Two producer groups and two epilogue groups of 4 warps each take alternate tiles (stage / accumulator =
-// tile parity): building the A tile and draining TMEM are latency-bound per warp, so two tiles are in
-// each phase at once.  warps 0-3 / 4-7: producers, warp 8: MMA, warps 9-12 / 13-16: epilogue.
-constexpr int kStemThreads = 17 * 32;
-
-__global__ void __launch_bounds__(kStemThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, 1)
 stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __restrict__ wq,
                const float* __restrict__ bias, __nv_bfloat16* __restrict__ x0, __nv_bfloat16* __restrict__ xs0, int B) {
     extern __shared__ unsigned char raw[];
@@ -720,15 +715,14 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 32) s_bias[tid] = bias[tid];
-    if (warp == 8) tc::tmem_alloc(&tmem_base_s, TMEM_COLS);
+    if (warp == 4) tc::tmem_alloc(&tmem_base_s, TMEM_COLS);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp < 8) {
+    if (warp < 4) {
         // ======================= producers ===========================================================
-        const int grp = warp >> 2, ptid = tid & 127;
         if (tid == 0) {
             tc::mbar_arrive_expect_tx(&w_bar, kStemBBytes);
             tc::bulk_g2s(sB, wq, kStemBBytes, &w_bar);
@@ -747,9 +741,8 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
             const unsigned char* map = sMap + mb * kMapBytesPad;
             for (int t = 0; t < kStemTilesPerClip; ++t, ++it) {
                 const int s = it & 1;
-                if (s != grp) continue;                         // the other producer group's tile
                 tc::mbar_wait(&empty_bar[s], (uint32_t)(((it >> 1) & 1) ^ 1));
-                const int pix = t * 128 + ptid;
+                const int pix = t * 128 + tid;
                 if (pix < kStemPix) {
                     const int py = pix / 25, px = pix - py * 25;
                     const unsigned char* src = map + (4 * py) * (kMapPitch * 2) + px * 8;
@@ -760,16 +753,16 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
                         const uint2 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3];
                         unsigned char* d = dstA + (ry >> 2) * 16384;
                         const int j0 = (ry & 3) * 2;
-                        *reinterpret_cast<uint4*>(d + tc::swz128(ptid, j0)) = make_uint4(v0.x, v0.y, v1.x, v1.y);
-                        *reinterpret_cast<uint4*>(d + tc::swz128(ptid, j0 + 1)) = make_uint4(v2.x, v2.y, v3.x, v3.y);
+                        *reinterpret_cast<uint4*>(d + tc::swz128(tid, j0)) = make_uint4(v0.x, v0.y, v1.x, v1.y);
+                        *reinterpret_cast<uint4*>(d + tc::swz128(tid, j0 + 1)) = make_uint4(v2.x, v2.y, v3.x, v3.y);
                     }
                 }
                 tc::fence_proxy_async();
                 tc::mbar_arrive(&full_bar[s]);
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");      // every producer is done with map[mb]
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // every producer is done with map[mb]
         }
-    } else if (warp == 8) {
+    } else if (warp == 4) {
         // ======================= MMA issuer ==========================================================
         if (lane == 0) {
             tc::mbar_wait(&w_bar, 0);
@@ -794,12 +787,11 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
         }
     } else {
         // ======================= epilogue: pool max over the 4 column groups, bias, ReLU, bf16 ========
-        const int lane_grp = warp & 3, grp = (warp - 9) >> 2;
+        const int lane_grp = warp & 3;
         int it = 0;
         for (int clip = blockIdx.x; clip < B; clip += gridDim.x) {
             for (int t = 0; t < kStemTilesPerClip; ++t, ++it) {
                 const int s = it & 1;
-                if (s != grp) continue;                         // the other epilogue group's tile
                 tc::mbar_wait(&tfull_bar[s], (uint32_t)((it >> 1) & 1));
                 tc::tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + s * 128;
@@ -840,7 +832,7 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 8) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == 4) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // fp32 features (B, 90, 101) -> the stem's zero-padded bf16 map (for callers that hand features in)
@@ -1051,7 +1043,7 @@ int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits,
             map_from_feat_kernel<<<dim3((kMapElems / 2 + 255) / 256, n), 256, 0, s>>>(d_feat + c0 * kFeatElem, maps, n);
             h->launches += 1;
         }
-        stem_tc_kernel<<<n < h->sm_count ? n : h->sm_count, kStemThreads, kStemSmem, s>>>(maps, W.stem_w, W.stem_b, x0,
+        stem_tc_kernel<<<n < h->sm_count ? n : h->sm_count, kTcThreads, kStemSmem, s>>>(maps, W.stem_w, W.stem_b, x0,
                                                                                          h1 + kPl0, n);
         h->launches += 1;
         TcArgs a{};
