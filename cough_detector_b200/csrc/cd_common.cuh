@@ -24,8 +24,10 @@ constexpr int kWin      = 400;
 constexpr int kHop      = 160;
 // bf16 copy of the features as the stem consumes it: rows -3..89, cols -3..108, zero padded
 constexpr int kMapRows  = 93;
-constexpr int kMapPitch = 112;
-constexpr int kMapElems = kMapRows * kMapPitch;   // 10 416 bf16 = 20 832 B per clip
+constexpr int kMapPitch = 120;                    // >= 112 (cols -3..108); 120 makes 4 rows = 16 banks apart, so the
+                                                  // stem's 25-pixel rows do not collide when a warp wraps to the next row
+constexpr int kMapPad   = kMapPitch - kFrames;    // zero columns per row: 3 left + the rest right
+constexpr int kMapElems = kMapRows * kMapPitch;   // 11 160 bf16 = 22 320 B per clip
 
 // mel contraction as executed by a lane: slots 0..2 = band `lane` (<= 3 taps for bands 0..31),
 // slots 3..10 = band `lane+32` (<= 8 taps).  idx is the bin index minus 4 (0..123).

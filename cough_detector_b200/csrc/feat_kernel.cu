@@ -340,7 +340,7 @@ __device__ __forceinline__ void feat_tail(SM& S, float wmax, float* __restrict__
 
     // ---- mel block rows 0..63: max(dB, floor) -> (dB + 80) / 80 -> clamp ------------------------
     // The CNN stem's operand rides along: the same values rounded to bf16 in a zero-padded
-    // [93 rows: -3..89][112 cols: -3..108] map, so the stem stages a clip with one bulk copy.
+    // [kMapRows: -3..89][kMapPitch cols: -3..] map, so the stem stages a clip with one bulk copy.
     for (int i = tid; i < kMels * kFrames; i += kFeatThreads) {
         const float v = fmaxf(S.db[i], floor_db);
         S.db[i] = v;
@@ -352,10 +352,10 @@ __device__ __forceinline__ void feat_tail(SM& S, float wmax, float* __restrict__
         }
     }
     if (mo) {       // zero padding: rows -3..-1 whole, cols -3..-1 and 101..108 of the 90 data rows
-        for (int i = tid; i < 3 * kMapPitch + kFeat * 11; i += kFeatThreads) {
+        for (int i = tid; i < 3 * kMapPitch + kFeat * kMapPad; i += kFeatThreads) {
             int idx = i;
             if (i >= 3 * kMapPitch) {
-                const int q = i - 3 * kMapPitch, row = q / 11, e = q - row * 11;
+                const int q = i - 3 * kMapPitch, row = q / kMapPad, e = q - row * kMapPad;
                 idx = (row + 3) * kMapPitch + (e < 3 ? e : kFrames + e);
             }
             mo[idx] = __float2bfloat16_rn(0.f);
