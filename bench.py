@@ -28,6 +28,7 @@ BATCH = 16384
 AUDIO_BYTES = 64000           # 16000 fp32 samples
 FEAT_BYTES = 36360            # 90 x 101 fp32
 CNN_FLOPS = 42_865_600        # 2 x 21 432 800 MAC per clip
+NCU_TRAFFIC_PER_CLIP = 98_530  # feat_kernel dram__bytes_read+write per clip, one ncu --set full capture (profiles/)
 METRIC = "1-s clips/sec (mel+MFCC+CNN)"
 
 
@@ -288,7 +289,9 @@ def run_gpu_arm(args):
                     "api": "cd_e2e_forward_host (pinned host audio in, host logits out)"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "feat_kernel", "bound": "hbm", "achieved": feat_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": feat_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": feat_gbs / hbm_peak, "traffic": B * NCU_TRAFFIC_PER_CLIP, "peak_source": peak_src,
+                         "traffic_source": "ncu --set full (profiles/r1_ncu_feat_kernel_16384.csv): dram read+write "
+                                           "1.614 GB per 16 384-clip launch, scaled by the batch",
                          "algorithmic_bytes_per_clip": AUDIO_BYTES + FEAT_BYTES, "launch_ms": feat_ms,
                          "clips_per_s": B / (feat_ms * 1e-3),
                          "note": "timed alone over the same resident batch right after the e2e region"},
