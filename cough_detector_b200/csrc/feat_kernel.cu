@@ -244,8 +244,9 @@ __device__ __forceinline__ float frame_pair(SM& S, const float* __restrict__ cli
             pB[sidx].y = __shfl_sync(0xffffffffu, sendB.y, srcB);
         }
         if (lane == 0) pA[1] = A[7];                 // k = 64: 512 - 64 = 448 = Z of this very lane (carry case)
-        // float2 {P_frame0, P_frame1} at padded bin index k + k/8
-        const int o = 9 * c + j;
+        // float2 {P_frame0, P_frame1} at padded bin index pidx(k) = k + 2 (k / 16): the padding found (offline
+        // search over the real band tables) to cost the fewest wavefronts for these stores + the mel reads
+        const int o = 8 * c + 2 * (c >> 1) + j;
 #pragma unroll
         for (int sidx = 0; sidx < 2; ++sidx) {
             {
@@ -267,14 +268,14 @@ __device__ __forceinline__ float frame_pair(SM& S, const float* __restrict__ cli
 #pragma unroll
     for (int s = 0; s < kMelSlotsLo; ++s) {
         const int bin = min(bin_lo + s, 127);            // taps past the band carry zero weight
-        const float2 pw = xb[bin + (bin >> 3)];
+        const float2 pw = xb[bin + 2 * (bin >> 4)];
         lo.x = fmaf(mw[s], pw.x, lo.x);
         lo.y = fmaf(mw[s], pw.y, lo.y);
     }
 #pragma unroll
     for (int s = 0; s < kMelSlotsHi; ++s) {
         const int bin = min(bin_hi + s, 127);
-        const float2 pw = xb[bin + (bin >> 3)];
+        const float2 pw = xb[bin + 2 * (bin >> 4)];
         hi.x = fmaf(mw[kMelSlotsLo + s], pw.x, hi.x);
         hi.y = fmaf(mw[kMelSlotsLo + s], pw.y, hi.y);
     }
@@ -444,8 +445,8 @@ feat_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offs, c
 #pragma unroll
         for (int s = 0; s < kMelSlots; ++s) mw[s] = tables->melt[s][lane].x;
         const int p0 = __float_as_int(tables->melt[0][lane].y), p3 = __float_as_int(tables->melt[kMelSlotsLo][lane].y);
-        bin_lo = p0 - p0 / 9;                          // undo the k + k/8 padding
-        bin_hi = p3 - p3 / 9;
+        bin_lo = p0;
+        bin_hi = p3;
     }
     if (tid == 0) {
         mbar_init(&S.bar, 1);
@@ -554,8 +555,8 @@ __device__ __forceinline__ void load_lane_tables(SM& S, const FeatTables* __rest
 #pragma unroll
     for (int s = 0; s < kMelSlots; ++s) mw[s] = tables->melt[s][lane].x;
     const int p0 = __float_as_int(tables->melt[0][lane].y), p3 = __float_as_int(tables->melt[kMelSlotsLo][lane].y);
-    bin_lo = p0 - p0 / 9;
-    bin_hi = p3 - p3 / 9;
+    bin_lo = p0;
+    bin_hi = p3;
 }
 
 __device__ __forceinline__ void lane_window(const FeatTables* __restrict__ tables, float inv, int lane, float (&wA)[7], float (&wB)[6]) {
@@ -672,9 +673,9 @@ int build_feat_tables(cd_handle* h) {
             if (tap < CD_MEL_COUNT[band]) {
                 w = bits2f(CD_MEL_W_BITS[band * CD_MEL_MAX_TAPS + tap]);
                 const int bin = CD_MEL_START[band] + tap;
-                idx = bin + (bin >> 3);                    // padded bin index used by frame_pair
+                idx = bin;                                 // plain FFT bin; frame_pair pads the index
             } else {
-                idx = 4 + (4 >> 3);                        // zero weight: any initialised entry
+                idx = 4;                                   // zero weight: any initialised entry
             }
             float fi;
             memcpy(&fi, &idx, 4);
