@@ -5,7 +5,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
 SRC_DIR   := cough_detector_b200/csrc
 OUT_DIR   := cough_detector_b200/lib
-SRCS      := $(SRC_DIR)/api.cu $(SRC_DIR)/feat_kernel.cu $(SRC_DIR)/cnn_fp32.cu $(SRC_DIR)/cnn_tc.cu
+SRCS      := $(SRC_DIR)/api.cu $(SRC_DIR)/feat_kernel.cu $(SRC_DIR)/cnn_fp32.cu $(SRC_DIR)/cnn_tc.cu $(SRC_DIR)/resample.cu
 OBJS      := $(patsubst $(SRC_DIR)/%.cu,build/%.o,$(SRCS))
 LIB       := $(OUT_DIR)/libcough_b200.so
 

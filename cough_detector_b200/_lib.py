@@ -44,6 +44,8 @@ SYMBOLS = {
     "cd_feat_forward_var": (_I, [_VP, _VP, _VP, _VP, _I64, _VP, _VP]),
     "cd_feat_forward_stream": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
     "cd_stream_windows": (_I64, [_I64, _I64]),
+    "cd_resample_length": (_I64, [_I64, _I, _I]),
+    "cd_resample": (_I, [_VP, _VP, _I64, _I64, _I, _I, _VP, _VP]),
     "cd_cnn_load": (_I, [_VP, C.POINTER(_ResidualWeights)]),
     "cd_cnn_forward": (_I, [_VP, _VP, _I64, _VP, _I, _VP]),
     "cd_predict": (_I, [_VP, _VP, _I64, C.c_float, _VP, _VP, _VP, _VP]),
@@ -158,6 +160,19 @@ class Handle:
         out = torch.empty(nw, 1, N_FEATURES, N_FRAMES, device=audio.device, dtype=torch.float32)
         self._check(self.lib.cd_feat_forward_stream(self._h, _ptr(audio), n, hop, nw, _ptr(out), self._stream()),
                     "cd_feat_forward_stream")
+        return out
+
+    # ---- resampling -------------------------------------------------------------------------
+    def resample(self, wave: torch.Tensor, orig_sr: int, new_sr: int = 16000) -> torch.Tensor:
+        """(rows, n) cuda fp32 -> (rows, ceil(new_sr * n / orig_sr)), torchaudio T.Resample defaults."""
+        wave = self._dev_f32(wave, "waveform")
+        if wave.dim() == 1:
+            wave = wave.unsqueeze(0)
+        rows, n = wave.shape
+        n_out = int(self.lib.cd_resample_length(n, int(orig_sr), int(new_sr)))
+        out = torch.empty(rows, n_out, device=wave.device, dtype=torch.float32)
+        self._check(self.lib.cd_resample(self._h, _ptr(wave), rows, n, int(orig_sr), int(new_sr), _ptr(out), self._stream()),
+                    "cd_resample")
         return out
 
     # ---- model ------------------------------------------------------------------------------

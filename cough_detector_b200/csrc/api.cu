@@ -43,6 +43,9 @@ int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits,
 size_t cnn_tc_ws_bytes(int64_t B);
 __nv_bfloat16* cnn_tc_map_ptr(cd_handle* h);
 int ensure_tc_ws(cd_handle* h);
+int64_t resample_length(int64_t n_in, int orig_sr, int new_sr);
+int launch_resample(cd_handle* h, const float* d_in, int64_t rows, int64_t n_in, int orig_sr, int new_sr, float* d_out,
+                    cudaStream_t s);
 void get_host_tables(float* hann, float* fb, float* dct);
 int umma_selftest(cd_handle* h, int N, int K, int shift, int mode, const float* hA, const float* hB, float* hD);
 
@@ -186,6 +189,22 @@ int cd_feat_forward_stream(cd_handle* h, const float* d_audio, int64_t n_samples
         return set_err(h, CD_E_ARG, "cd_feat_forward_stream: hop must be > 0 and n_windows == cd_stream_windows()");
     DeviceGuard g(h->device);
     return launch_features(h, d_audio, nullptr, nullptr, hop, kModeStream, n_windows, d_feat, nullptr, (cudaStream_t)stream);
+}
+
+// ---- resampling ------------------------------------------------------------------------------
+
+int64_t cd_resample_length(int64_t n_in, int orig_sr, int new_sr) {
+    if (n_in < 0 || orig_sr <= 0 || new_sr <= 0) return 0;
+    return resample_length(n_in, orig_sr, new_sr);
+}
+
+int cd_resample(cd_handle* h, const float* d_in, int64_t rows, int64_t n_in, int orig_sr, int new_sr, float* d_out,
+                void* stream) {
+    if (!h) return CD_E_ARG;
+    if (rows < 0 || n_in < 0 || orig_sr <= 0 || new_sr <= 0 || (rows * n_in > 0 && (!d_in || !d_out)))
+        return set_err(h, CD_E_ARG, "cd_resample: bad argument");
+    DeviceGuard g(h->device);
+    return launch_resample(h, d_in, rows, n_in, orig_sr, new_sr, d_out, (cudaStream_t)stream);
 }
 
 // ---- model -----------------------------------------------------------------------------------

@@ -1,0 +1,113 @@
+// Sample-rate conversion on the GPU: AudioPreprocessor.resample (src/preprocessing.py:168-183), i.e.
+// torchaudio T.Resample with its defaults (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99;
+// torchaudio/functional/functional.py:1305-1432).  The polyphase filter bank is built on the host with
+// the same arithmetic (float64, the phase term -j/new rounded through float32 like torch's int64/int
+// division) and stored compactly: for output phase j only the taps inside the +-6 zero-crossing window
+// are non-zero (about 34 of the 2*width+orig taps torchaudio's dense conv1d multiplies through).
+#include <math.h>
+#include <vector>
+
+#include "cd_common.cuh"
+
+namespace cd {
+
+struct ResampleTable {
+    int orig, neu, width, support;     // reduced rates, torchaudio's `width`, taps kept per phase
+    int* d_k0;                         // [neu] first kept tap (index into the padded input window)
+    float* d_taps;                     // [neu][support]
+};
+static std::vector<ResampleTable> g_tables[64];
+
+static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
+
+static int get_table(cd_handle* h, int orig_sr, int new_sr, ResampleTable* out) {
+    const int g = gcd_i(orig_sr, new_sr), orig = orig_sr / g, neu = new_sr / g;
+    for (const ResampleTable& t : g_tables[h->device])
+        if (t.orig == orig && t.neu == neu) {
+            *out = t;
+            return CD_OK;
+        }
+    const int lpw = 6;
+    const double base = (double)(orig < neu ? orig : neu) * 0.99;
+    const int width = (int)ceil(lpw * (double)orig / base);
+    const int ntap = 2 * width + orig;
+    std::vector<double> full((size_t)neu * ntap);
+    std::vector<int> k0(neu), k1(neu);
+    int support = 1;
+    for (int j = 0; j < neu; ++j) {
+        const double phase = (double)((float)(-j) / (float)neu);       // torch: int64 arange / int -> float32
+        int lo = ntap, hi = -1;
+        for (int k = 0; k < ntap; ++k) {
+            double t = (phase + (double)(k - width) / (double)orig) * base;
+            if (t < -lpw) t = -lpw;
+            if (t > lpw) t = lpw;
+            const double c = cos(t * M_PI / lpw / 2.0);
+            const double window = c * c;
+            const double tp = t * M_PI;
+            const double v = (tp == 0.0 ? 1.0 : sin(tp) / tp) * window * (base / (double)orig);
+            full[(size_t)j * ntap + k] = v;
+            if (fabs(t) < lpw) {                                       // outside: window = cos(pi/2)^2 ~ 4e-33
+                if (k < lo) lo = k;
+                if (k > hi) hi = k;
+            }
+        }
+        k0[j] = lo;
+        k1[j] = hi;
+        if (hi - lo + 1 > support) support = hi - lo + 1;
+    }
+    std::vector<float> taps((size_t)neu * support, 0.f);
+    for (int j = 0; j < neu; ++j)
+        for (int s = 0; s < support && k0[j] + s <= k1[j]; ++s) taps[(size_t)j * support + s] = (float)full[(size_t)j * ntap + k0[j] + s];
+    ResampleTable t{orig, neu, width, support, nullptr, nullptr};
+    CD_CUDA(h, cudaMalloc(&t.d_k0, neu * sizeof(int)));
+    CD_CUDA(h, cudaMalloc(&t.d_taps, taps.size() * sizeof(float)));
+    CD_CUDA(h, cudaMemcpy(t.d_k0, k0.data(), neu * sizeof(int), cudaMemcpyHostToDevice));
+    CD_CUDA(h, cudaMemcpy(t.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+    g_tables[h->device].push_back(t);
+    *out = t;
+    return CD_OK;
+}
+
+// y[f * neu + j] = sum_s taps[j][s] * x[f * orig + k0[j] + s - width]   (x = 0 outside [0, n_in))
+__global__ void __launch_bounds__(256)
+resample_kernel(const float* __restrict__ x, int64_t n_in, int64_t n_out, int orig, int neu, int width, int support,
+                const int* __restrict__ k0, const float* __restrict__ taps, float* __restrict__ y) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t row = blockIdx.y;
+    if (i >= n_out) return;
+    const int64_t f = i / neu;
+    const int j = (int)(i - f * neu);
+    const float* xr = x + row * n_in;
+    const float* tp = taps + (size_t)j * support;
+    const int64_t base = f * orig + k0[j] - width;
+    float acc = 0.f;
+    for (int s = 0; s < support; ++s) {
+        const int64_t k = base + s;
+        const float v = (k >= 0 && k < n_in) ? __ldg(xr + k) : 0.f;
+        acc = fmaf(__ldg(tp + s), v, acc);
+    }
+    y[row * n_out + i] = acc;
+}
+
+int64_t resample_length(int64_t n_in, int orig_sr, int new_sr) {
+    const int g = gcd_i(orig_sr, new_sr);
+    const int64_t orig = orig_sr / g, neu = new_sr / g;
+    return (neu * n_in + orig - 1) / orig;                            // ceil(new * length / orig)
+}
+
+int launch_resample(cd_handle* h, const float* d_in, int64_t rows, int64_t n_in, int orig_sr, int new_sr, float* d_out,
+                    cudaStream_t s) {
+    if (h->device >= 64) return set_err(h, CD_E_ARG, "device index >= 64");
+    ResampleTable t;
+    int rc = get_table(h, orig_sr, new_sr, &t);
+    if (rc != CD_OK) return rc;
+    const int64_t n_out = resample_length(n_in, orig_sr, new_sr);
+    if (n_out == 0 || rows == 0) return CD_OK;
+    dim3 grid((unsigned)((n_out + 255) / 256), (unsigned)rows);
+    resample_kernel<<<grid, 256, 0, s>>>(d_in, n_in, n_out, t.orig, t.neu, t.width, t.support, t.d_k0, t.d_taps, d_out);
+    h->launches += 1;
+    CD_CUDA(h, cudaGetLastError());
+    return CD_OK;
+}
+
+}  // namespace cd

@@ -73,10 +73,14 @@ class AudioPreprocessor:
         return torchaudio.load(path)
 
     def resample(self, waveform: torch.Tensor, orig_sr: int) -> torch.Tensor:
-        """Identity at 16 kHz (the in-scope case, :179-180); other rates are §8f rank 3."""
+        """T.Resample(orig_sr, 16000) with torchaudio's defaults on the GPU (:168-183); identity at 16 kHz."""
         if orig_sr == self.sample_rate:
             return waveform
-        raise NotImplementedError(f"on-device resampling from {orig_sr} Hz is not built yet; feed 16 kHz audio")
+        if int(orig_sr) != orig_sr or orig_sr <= 0:
+            raise ValueError("sample rates must be positive integers")
+        h = self._gpu()
+        x = waveform.to(device=f"cuda:{h.device}", dtype=torch.float32)
+        return self._back(h.resample(x, int(orig_sr), self.sample_rate), waveform)
 
     def to_mono(self, waveform: torch.Tensor) -> torch.Tensor:
         """(C, n) -> (1, n) channel mean (:185-197)."""

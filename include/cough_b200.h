@@ -116,6 +116,17 @@ int cd_feat_forward_stream(cd_handle* h, const float* d_audio, int64_t n_samples
 /* Number of windows add_audio emits for n_samples buffered samples (0 if n_samples < 16000). */
 int64_t cd_stream_windows(int64_t n_samples, int64_t hop);
 
+/* ---- resampling: AudioPreprocessor.resample ------------------------------------------------- */
+
+/* Output length torchaudio's resample produces: ceil(new_sr * n_in / orig_sr) (rates reduced by their gcd). */
+int64_t cd_resample_length(int64_t n_in, int orig_sr, int new_sr);
+
+/* T.Resample(orig_sr, new_sr) with torchaudio's defaults (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99),
+ * as src/preprocessing.py:146-183 applies it.  d_in: rows x n_in fp32 (e.g. one row per channel), d_out: rows x
+ * cd_resample_length(n_in, ...).  The polyphase table of a rate pair is built on first use (synchronous upload). */
+int cd_resample(cd_handle* h, const float* d_in, int64_t rows, int64_t n_in, int orig_sr, int new_sr,
+                float* d_out, void* stream);
+
 /* ---- model: CoughDetectorResidual ------------------------------------------------------ */
 
 /* Fold BatchNorm (eval mode, eps 1e-5) into the convolutions, repack for the kernels and upload.

@@ -355,3 +355,35 @@ def decisions_stream(probs: Sequence[float], hop_s: float, threshold: float = 0.
                 continue
         j += 1
     return fired
+
+
+# --------------------------------------------------------------------------
+# resampling (src/preprocessing.py:146-183 -> torchaudio T.Resample defaults)
+# --------------------------------------------------------------------------
+def resample_kernel(orig_sr: int, new_sr: int):
+    """(kernel (new, 2*width+orig) fp32, width, orig, new): torchaudio/functional/functional.py:1305-1404 with
+    sinc_interp_hann, lowpass_filter_width=6, rolloff=0.99, dtype=None (float64 maths, the phase term through
+    float32 as torch's int64-arange / int division produces it)."""
+    g = math.gcd(int(orig_sr), int(new_sr))
+    orig, new = int(orig_sr) // g, int(new_sr) // g
+    lpw = 6
+    base = min(orig, new) * 0.99
+    width = math.ceil(lpw * orig / base)
+    idx = torch.arange(-width, width + orig, dtype=torch.float64)[None, :] / orig
+    t = (torch.arange(0, -new, -1)[:, None] / new).double() + idx
+    t = (t * base).clamp_(-lpw, lpw)
+    window = torch.cos(t * math.pi / lpw / 2) ** 2
+    t = t * math.pi
+    k = torch.where(t == 0, torch.tensor(1.0, dtype=torch.float64), t.sin() / t) * window * (base / orig)
+    return k.float(), width, orig, new
+
+
+def resample(w: torch.Tensor, orig_sr: int, new_sr: int = SAMPLE_RATE) -> torch.Tensor:
+    """(rows, n) -> (rows, ceil(new*n/orig)); torchaudio/functional/functional.py:1406-1432 (pad, strided conv1d, trim)."""
+    if orig_sr == new_sr:
+        return w
+    k, width, orig, new = resample_kernel(orig_sr, new_sr)
+    rows, n = w.shape
+    x = F.pad(w, (width, width + orig))
+    y = F.conv1d(x[:, None], k[:, None], stride=orig).transpose(1, 2).reshape(rows, -1)
+    return y[:, : math.ceil(new * n / orig)]

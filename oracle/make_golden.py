@@ -104,6 +104,21 @@ def main():
         st[f"feat_hop{int(hop * 1000)}"] = torch.stack(got).numpy()
     np.savez_compressed(os.path.join(GOLD, "stream.npz"), **st)
 
+    # ---- resampling: AudioPreprocessor.resample (T.Resample defaults) from the rates the datasets use ----
+    g = torch.Generator().manual_seed(11)
+    rs = {"meta": meta}
+    for sr in (44100, 48000, 8000, 22050, 32000):
+        n = int(0.37 * sr) + 13
+        t = torch.arange(n) / sr
+        xw = torch.stack([0.4 * torch.sin(2 * 3.14159265 * 431.0 * t) + 0.05 * torch.randn(n, generator=g),
+                          0.3 * torch.randn(n, generator=g)])
+        mq, sq = quantize_clip(xw.reshape(-1))
+        xw = dequantize_clip(mq, sq).reshape(2, n)
+        rs[f"in_{sr}_mant"] = mq
+        rs[f"in_{sr}_scale"] = np.float32(sq)
+        rs[f"out_{sr}"] = pp.resample(xw, sr).numpy()
+    np.savez_compressed(os.path.join(GOLD, "resample.npz"), **rs)
+
     # ---- inference engine: checkpoint round trip + process_audio_chunk (debounce 0 -> deterministic) ----
     cfg = dict(model_type="residual", sample_rate=16000, n_mels=64, n_fft=512, hop_length=160, win_length=400,
                f_min=100.0, f_max=4000.0, segment_duration=1.0, n_mfcc=13, use_mfcc=True, n_contrast_bands=6,

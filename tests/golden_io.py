@@ -35,3 +35,14 @@ def load_stream():
 
 def load_engine():
     return np.load(os.path.join(GOLD, "engine.npz"))
+
+
+def load_resample():
+    z = np.load(os.path.join(GOLD, "resample.npz"))
+    out = {}
+    for k in z.files:
+        if k.startswith("out_"):
+            sr = int(k[4:])
+            x = _deq(z[f"in_{sr}_mant"], z[f"in_{sr}_scale"]).reshape(2, -1)
+            out[sr] = (x, torch.from_numpy(z[k]))
+    return out

@@ -163,3 +163,21 @@ def test_full_size_config2_properties():
     assert torch.equal(b, a[idx.cuda()])
     checksum = a.double().sum().item()
     assert checksum == h.feat_forward(x).double().sum().item()
+
+
+def test_resample_matches_reference_and_feeds_process():
+    """AudioPreprocessor.resample on the GPU vs the reference goldens, then process() from 44.1 / 48 kHz."""
+    pp = AudioPreprocessor(**FLAGS)
+    gold = gio.load_resample()
+    for sr, (x, ref) in gold.items():
+        got = pp.resample(x, sr)
+        assert got.shape == ref.shape and got.device.type == "cpu"
+        assert (got - ref).abs().max().item() <= 2e-6, sr
+    ex = co.Explicit32()
+    g = torch.Generator().manual_seed(5)
+    for sr in (44100, 48000):
+        w = torch.stack([synth._burst(g, int(1.3 * sr)), synth._sines(g, int(1.3 * sr))])      # stereo, 1.3 s
+        feat = pp.process(w, sr)
+        ref = ex.process(co.resample(w, sr))                   # resample -> mono -> normalize -> trim -> features
+        assert feat.shape == (1, 90, 101)
+        assert (feat - ref).abs().max().item() <= TOL, sr

@@ -150,3 +150,11 @@ def test_tcgen05_tile_selftest_bf16(n, k):
     ref = a.bfloat16().double() @ b.bfloat16().double().t()
     err, scale = (d.double() - ref).abs().max().item(), ref.abs().max().item()
     assert err <= 2e-3 * scale
+
+
+def test_every_entry_point_on_small_shapes():
+    """tools/sanitize_case.py: all kernels / C-ABI entry points on tiny, ragged inputs (the case written for
+    compute-sanitizer; that tool is closed on this pool, so it runs as a plain smoke test)."""
+    import runpy
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    runpy.run_path(os.path.join(root, "tools", "sanitize_case.py"), run_name="__main__")

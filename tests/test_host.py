@@ -28,6 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in lib.cd_version()
     assert lib.cd_stream_windows(57_600_000, 1600) == 35991
     assert lib.cd_stream_windows(15999, 1600) == 0 and lib.cd_stream_windows(16000, 0) == 0
+    assert lib.cd_resample_length(16330, 44100, 16000) == 5925 and lib.cd_resample_length(2973, 8000, 16000) == 5946
 
 
 def test_library_tables_are_the_reference_tables():
@@ -59,8 +60,8 @@ def test_preprocessor_surface_and_errors():
         AudioPreprocessor()                      # reference defaults = 110-feature config: not built, no fallback
     with pytest.raises(NotImplementedError):
         AudioPreprocessor(n_mels=80, **FLAGS)
-    with pytest.raises(NotImplementedError):
-        pp.resample(torch.zeros(1, 10), 44100)
+    with pytest.raises(ValueError):
+        pp.resample(torch.zeros(1, 10), 44100.5)
     assert pp.resample(torch.ones(1, 4), 16000).shape == (1, 4)
     assert isinstance(create_preprocessor(True, hop_duration=0.1, **FLAGS), RealtimePreprocessor)
     with pytest.raises(ValueError):

@@ -106,3 +106,10 @@ def test_engine_decisions_match_reference():
     ref_idx = [i - 3 for i in np.nonzero(e["fired"])[0]]
     assert [j for j, _ in fired] == ref_idx
     assert np.allclose([c for _, c in fired], e["confs"][e["fired"]], atol=1e-6)
+
+
+def test_resample_is_bit_identical_to_reference():
+    for sr, (x, ref) in gio.load_resample().items():
+        got = co.resample(x, sr)
+        assert got.shape == ref.shape and torch.equal(got, ref), sr
+    assert co.resample(torch.ones(1, 5), 16000) .shape == (1, 5)
