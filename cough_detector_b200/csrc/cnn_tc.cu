@@ -239,6 +239,13 @@ struct PsLayout {
     static constexpr int ROWS_IN = (128 + 2 * WP + 2 + 7) & ~7;     // rows one 128-row tile reads
 };
 
+// Phase-split variant for the INPUT of a stride-2 convolution (see conv3x3_s2_tc_kernel)
+template <int H, int W>
+struct Ps2Layout {
+    static constexpr int A2 = (H + 3) / 2, B2 = (W + 3) / 2, RPC = A2 * B2;
+    static constexpr int ROWS_IN = (128 + B2 + 1 + 7) & ~7;
+};
+
 // OUT_MODE: 0 = bf16 NHWC rows [M][COUT]; 1 = fp32 rows; 2 = bf16 in the padded + swizzled layout the
 // stride-1 kernel bulk-copies (see PsLayout)
 template <int CIN, int COUT, int HIN, int WIN, int STRIDE, bool SKIP, bool RESID, int OUT_MODE>
@@ -507,6 +514,7 @@ struct S1Args {
     __nv_bfloat16* y_bf16;         // [n * H * W][C] bf16 (OUT_F32 == false)
     float* y_f32;                  // [n * H * W][C] fp32
     __nv_bfloat16* xs_out;         // WRITE_XS: next block's skip plane (PS layout of the (H+1)/2 x (W+1)/2 grid)
+    int64_t y_plane_elems;         // WRITE_XS: y_bf16 is written phase-split (Ps2Layout<H, W>, 4 planes this far apart)
     int64_t ps_plane_elems;
     int n;                         // clips
 };
@@ -647,6 +655,11 @@ conv3x3_s1_tc_kernel(const S1Args a) {
                         op[8 + q] = make_float4(v1[4 * q], v1[4 * q + 1], v1[4 * q + 2], v1[4 * q + 3]);
                     }
                 } else {
+                    // WRITE_XS (block 0): the activation feeds the next block's stride-2 conv, so it is stored
+                    // phase-split (Ps2Layout<H, W>); otherwise plain NHWC rows
+                    using P2 = Ps2Layout<H, W>;
+                    const int64_t r2 = (int64_t)clip * P2::RPC + ((y + 1) >> 1) * P2::B2 + ((x + 1) >> 1);
+                    __nv_bfloat16* op2 = a.y_bf16 + (int64_t)(((y + 1) & 1) * 2 + ((x + 1) & 1)) * a.y_plane_elems + r2 * 64;
                     uint4* op = reinterpret_cast<uint4*>(a.y_bf16 + m * C + half * 64);
                     // the next block's skip conv reads this activation at (2y', 2x'): emit that sample as a PS row
                     const bool xs = WRITE_XS && !(y & 1) && !(x & 1);
@@ -659,8 +672,190 @@ conv3x3_s1_tc_kernel(const S1Args a) {
                         __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
                         const uint4 pk = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
                                                     *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
-                        op[q] = pk;
+                        if (WRITE_XS) *reinterpret_cast<uint4*>(op2 + ((q ^ (int)(r2 & 7)) << 3)) = pk;
+                        else op[q] = pk;
                         if (xs) *reinterpret_cast<uint4*>(xrow + ((q ^ (int)(rg2 & 7)) << 3)) = pk;
+                    }
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ----------------------------------------------------------------------------------------------
+// stride-2 3x3 convolution without im2col: phase-split PS input ("PS2") + shifted descriptor views
+// ----------------------------------------------------------------------------------------------
+// With padded coordinates iy' = iy + 1, ix' = ix + 1 the tap (ky, kx) of output (oy, ox) reads
+// iy' = 2 oy + ky, ix' = 2 ox + kx.  Splitting the padded image by the parities (iy' & 1, ix' & 1) gives
+// four phase images of ceil((H+2)/2) x ceil((W+2)/2) pixels in which that tap is the pixel
+// (oy + (ky >> 1), ox + (kx >> 1)) of phase (ky & 1, kx & 1): a unit-stride shifted view again.
+// Rows of a phase image are 128 bytes: C = 64 -> one phase per plane (4 planes); C = 32 -> the two ix'
+// parities of one iy' parity share a row (2 planes, the kx parity selects the 64-byte half = K offset).
+template <int CIN, int COUT, int H, int W>
+struct S2Shape {
+    using P2 = Ps2Layout<H, W>;
+    static constexpr int NPL = CIN == 32 ? 2 : 4;
+    static constexpr int A_BYTES = P2::ROWS_IN * 128;
+    static constexpr int NCH = (9 * CIN + 63) / 64;               // packed weight chunks [COUT rows x 128 B]
+    static constexpr int W_BYTES = NCH * COUT * 128;
+    static constexpr int STAGES = CIN == 32 ? 4 : 1;              // per-plane barriers keep even 1 stage overlapped
+    static constexpr size_t SMEM = 1024 + (size_t)STAGES * NPL * A_BYTES + W_BYTES + COUT * 4 + 64;
+};
+
+struct S2Args {
+    const __nv_bfloat16* x;        // PS2 planes, in_plane_elems apart
+    const __nv_bfloat16* w;        // packed chunks [NCH][COUT rows x 128 B]
+    const float* bias;             // [COUT]
+    __nv_bfloat16* y;              // PS layout of the (HO, WO) output, COUT/64 planes out_plane_elems apart
+    int64_t in_plane_elems, out_plane_elems;
+    int n;
+};
+
+template <int CIN, int COUT, int H, int W>
+__global__ void __launch_bounds__(kS1Threads, 1)
+conv3x3_s2_tc_kernel(const S2Args a) {
+    using S = S2Shape<CIN, COUT, H, W>;
+    using P2 = Ps2Layout<H, W>;
+    constexpr int HO = (H - 1) / 2 + 1, WO = (W - 1) / 2 + 1;
+    using PSO = PsLayout<HO, WO>;
+    constexpr uint32_t IDESC = tc::idesc_bf16(128, COUT);
+    constexpr int TMEM_COLS = 2 * COUT <= 128 ? 128 : 256;
+    constexpr int NB = S::STAGES * S::NPL;
+
+    extern __shared__ unsigned char raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* s_w = base + (size_t)NB * S::A_BYTES;
+    float* s_bias = reinterpret_cast<float*>(s_w + S::W_BYTES);
+    __shared__ uint64_t full_bar[NB], empty_bar[NB], tfull_bar[2], tempty_bar[2], w_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t rows = (int64_t)a.n * P2::RPC;
+    const int n_tiles = (int)((rows + 127) / 128);
+
+    if (tid == 0) {
+        for (int i = 0; i < NB; ++i) {
+            tc::mbar_init(&full_bar[i], 1);
+            tc::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&tfull_bar[i], 1);
+            tc::mbar_init(&tempty_bar[i], 128);
+        }
+        tc::mbar_init(&w_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < COUT) s_bias[tid] = a.bias[tid];
+    if (warp == 1) tc::tmem_alloc(&tmem_base_s, TMEM_COLS);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ======================= producer ============================================================
+        if (lane == 0) {
+            tc::mbar_arrive_expect_tx(&w_bar, S::W_BYTES);
+            for (int q = 0; q < S::NCH; ++q)
+                tc::bulk_g2s(s_w + (size_t)q * COUT * 128, a.w + (size_t)q * COUT * 64, COUT * 128, &w_bar);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int s = it % S::STAGES;
+                const uint32_t par = (uint32_t)(((it / S::STAGES) & 1) ^ 1);
+#pragma unroll
+                for (int q = 0; q < S::NPL; ++q) {
+                    const int bi = s * S::NPL + q;
+                    tc::mbar_wait(&empty_bar[bi], par);
+                    tc::mbar_arrive_expect_tx(&full_bar[bi], S::A_BYTES);
+                    tc::bulk_g2s(base + (size_t)bi * S::A_BYTES, a.x + q * a.in_plane_elems + (int64_t)tile * 128 * 64,
+                                 S::A_BYTES, &full_bar[bi]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= MMA issuer: taps grouped by the plane (phase) they read =============
+        if (lane == 0) {
+            tc::mbar_wait(&w_bar, 0);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int s = it % S::STAGES, acc = it & 1;
+                const uint32_t par = (uint32_t)((it / S::STAGES) & 1);
+                tc::mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+                const uint32_t d = tmem_base + acc * COUT;
+                const uint64_t dw = tc::desc_sw128(tc::s32(s_w));
+                uint32_t accum = 0;
+#pragma unroll
+                for (int q = 0; q < S::NPL; ++q) {
+                    const int bi = s * S::NPL + q;
+                    tc::mbar_wait(&full_bar[bi], par);
+                    tc::tc_fence_after();
+                    const uint64_t da = tc::desc_sw128(tc::s32(base + (size_t)bi * S::A_BYTES));
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int ky = tap / 3, kx = tap % 3;
+                        const int plane = CIN == 32 ? (ky & 1) : (ky & 1) * 2 + (kx & 1);
+                        if (plane != q) continue;
+                        const uint32_t shift = (uint32_t)((ky >> 1) * P2::B2 + (kx >> 1)) * 128;
+                        if (CIN == 32) {      // 32 channels = 2 K-steps in the (kx & 1) half of the row
+#pragma unroll
+                            for (int hk = 0; hk < 2; ++hk) {
+                                tc::umma_bf16(d, tc::desc_adv(da, shift + (kx & 1) * 64 + hk * 32),
+                                              tc::desc_adv(dw, (tap >> 1) * COUT * 128 + ((tap & 1) * 2 + hk) * 32), IDESC, accum);
+                                accum = 1;
+                            }
+                        } else {
+#pragma unroll
+                            for (int hk = 0; hk < 4; ++hk) {
+                                tc::umma_bf16(d, tc::desc_adv(da, shift + hk * 32), tc::desc_adv(dw, tap * COUT * 128 + hk * 32),
+                                              IDESC, accum);
+                                accum = 1;
+                            }
+                        }
+                    }
+                    tc::tc_commit(&empty_bar[bi]);
+                }
+                tc::tc_commit(&tfull_bar[acc]);
+            }
+        }
+    } else {
+        // ======================= epilogue: + bias, ReLU, bf16 rows in the PS layout of the output ======
+        const int lane_grp = warp & 3;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const int64_t mp = (int64_t)tile * 128 + lane_grp * 32 + lane;
+            const int clip = (int)(mp / P2::RPC), rem = (int)(mp - (int64_t)clip * P2::RPC);
+            const int oy = rem / P2::B2, ox = rem - oy * P2::B2;
+            const bool live = clip < a.n && oy < HO && ox < WO;
+            const int64_t rg = (int64_t)clip * PSO::RPC + (oy + 1) * PSO::WP + (ox + 1);
+            tc::mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * COUT;
+#pragma unroll 1
+            for (int c0 = 0; c0 < COUT; c0 += 32) {
+                float v[32];
+                tc::tmem_ld32(taddr + c0, v);
+                if (c0 + 32 >= COUT) {                 // last read of this accumulator: hand it back early
+                    tc::tc_fence_before();
+                    tc::mbar_arrive(&tempty_bar[acc]);
+                }
+                if (live) {
+                    __nv_bfloat16* prow = a.y + (int64_t)(c0 / 64) * a.out_plane_elems + rg * 64;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int c = 8 * q + 2 * e;
+                            __nv_bfloat162 pk = __floats2bfloat162_rn(fmaxf(v[c] + s_bias[c0 + c], 0.f),
+                                                                      fmaxf(v[c + 1] + s_bias[c0 + c + 1], 0.f));
+                            w[e] = *reinterpret_cast<uint32_t*>(&pk);
+                        }
+                        const int jch = (c0 & 63) / 8 + q;
+                        *reinterpret_cast<uint4*>(prow + ((jch ^ (int)(rg & 7)) << 3)) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
             }
@@ -690,7 +885,8 @@ constexpr size_t kStemSmem = 1024 + 2 * kStemABytes + kStemBBytes + 2 * kMapByte
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __restrict__ wq,
-               const float* __restrict__ bias, __nv_bfloat16* __restrict__ x0, __nv_bfloat16* __restrict__ xs0, int B) {
+               const float* __restrict__ bias, __nv_bfloat16* __restrict__ x0, int64_t x0_plane_elems,
+               __nv_bfloat16* __restrict__ xs0, int B) {
     extern __shared__ unsigned char raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sA = base;                                   // [2][3][16384]
@@ -807,10 +1003,15 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
                 tc::mbar_arrive(&tempty_bar[s]);
                 const int pix = t * 128 + lane_grp * 32 + lane;
                 if (pix < kStemPix) {
-                    uint4* op = reinterpret_cast<uint4*>(x0 + ((int64_t)clip * kStemPix + pix) * 32);
-                    // block 0's skip conv reads x0 at (2y, 2x): emit those pixels as PS rows (32 of 64 channels used)
+                    // x0 goes out phase-split (Ps2Layout<22, 25>): plane = (py+1) & 1, row = ((py+1)/2, (px+1)/2),
+                    // the (px+1) parity picks the 64-byte half of the 128-byte row
+                    using P2 = Ps2Layout<22, 25>;
                     using PSN = PsLayout<11, 13>;
                     const int py = pix / 25, px = pix - py * 25;
+                    const int64_t r2 = (int64_t)clip * P2::RPC + ((py + 1) >> 1) * P2::B2 + ((px + 1) >> 1);
+                    __nv_bfloat16* op = x0 + (int64_t)((py + 1) & 1) * x0_plane_elems + r2 * 64;
+                    const int jb = ((px + 1) & 1) * 4;
+                    // block 0's skip conv reads x0 at (2y, 2x): emit those pixels as PS rows (32 of 64 channels used)
                     const bool xs = !(py & 1) && !(px & 1);
                     const int64_t rg = (int64_t)clip * PSN::RPC + (py / 2 + 1) * PSN::WP + (px / 2 + 1);
                     __nv_bfloat16* xrow = xs0 + rg * 64;
@@ -823,7 +1024,7 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
                             __nv_bfloat162 pk = __floats2bfloat162_rn(fmaxf(m[c] + s_bias[c], 0.f), fmaxf(m[c + 1] + s_bias[c + 1], 0.f));
                             w[e] = *reinterpret_cast<uint32_t*>(&pk);
                         }
-                        op[q] = make_uint4(w[0], w[1], w[2], w[3]);
+                        *reinterpret_cast<uint4*>(op + (((jb + q) ^ (int)(r2 & 7)) << 3)) = make_uint4(w[0], w[1], w[2], w[3]);
                         if (xs) *reinterpret_cast<uint4*>(xrow + ((q ^ (int)(rg & 7)) << 3)) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
@@ -909,8 +1110,10 @@ static cudaError_t tc_attr() {
 }
 
 int init_cnn_tc(cd_handle* h) {
-    CD_CUDA(h, (tc_attr<32, 64, 22, 25, 2, false, false, 2>()));
-    CD_CUDA(h, (tc_attr<64, 128, 11, 13, 2, false, false, 2>()));
+    CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s2_tc_kernel<32, 64, 22, 25>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)S2Shape<32, 64, 22, 25>::SMEM));
+    CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s2_tc_kernel<64, 128, 11, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)S2Shape<64, 128, 11, 13>::SMEM));
     CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s1_tc_kernel<64, 11, 13, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)S1Shape<64, 11, 13>::SMEM));
     CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s1_tc_kernel<128, 6, 7, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -988,9 +1191,13 @@ constexpr int64_t kPs1Rows = ((kTcChunk * Ps1::RPC + 127) / 128) * 128 + Ps1::RO
 constexpr int64_t al256(int64_t x) { return (x + 255) & ~int64_t(255); }
 constexpr int64_t kOffMap = 0;
 constexpr int64_t kOffX0 = kOffMap + al256(kTcChunk * kMapElems * 2);
-constexpr int64_t kOffH1 = kOffX0 + al256(kTcChunk * 22 * 25 * 32 * 2);
+using P20 = Ps2Layout<22, 25>;
+using P21 = Ps2Layout<11, 13>;
+constexpr int64_t kP20Rows = ((kTcChunk * P20::RPC + 127) / 128) * 128 + P20::ROWS_IN;    // x0, 2 planes
+constexpr int64_t kP21Rows = ((kTcChunk * P21::RPC + 127) / 128) * 128 + P21::ROWS_IN;    // x1, 4 planes
+constexpr int64_t kOffH1 = kOffX0 + al256(2 * kP20Rows * 128);
 constexpr int64_t kOffX1 = kOffH1 + al256(2 * kPs0Rows * 128);
-constexpr int64_t kOffH2 = kOffX1 + al256(kTcChunk * 143 * 64 * 2);
+constexpr int64_t kOffH2 = kOffX1 + al256(4 * kP21Rows * 128);
 constexpr int64_t kOffX2 = kOffH2 + al256(3 * kPs1Rows * 128);
 constexpr int64_t kTcWsBytes = kOffX2 + al256(kTcChunk * 42 * 128 * 4);
 
@@ -1044,26 +1251,34 @@ int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits,
             h->launches += 1;
         }
         stem_tc_kernel<<<n < h->sm_count ? n : h->sm_count, kTcThreads, kStemSmem, s>>>(maps, W.stem_w, W.stem_b, x0,
-                                                                                         h1 + kPl0, n);
+                                                                                         kP20Rows * 64, h1 + kPl0, n);
         h->launches += 1;
-        TcArgs a{};
-        a.B = n;
-        a.x = x0; a.w = W.b0c1; a.bias = W.b0c1_b; a.y_bf16 = h1; a.ps_plane_elems = kPl0;
-        launch_tc<32, 64, 22, 25, 2, false, false, 2>(h, a, s);
+        {
+            using S = S2Shape<32, 64, 22, 25>;
+            S2Args q{};
+            q.x = x0; q.w = W.b0c1; q.bias = W.b0c1_b; q.y = h1; q.in_plane_elems = kP20Rows * 64; q.out_plane_elems = kPl0; q.n = n;
+            const int tiles = (int)(((int64_t)n * P20::RPC + 127) / 128);
+            conv3x3_s2_tc_kernel<32, 64, 22, 25><<<tiles < h->sm_count ? tiles : h->sm_count, kS1Threads, S::SMEM, s>>>(q);
+            h->launches += 1;
+        }
         {
             using S = S1Shape<64, 11, 13>;
             S1Args q{};
             q.x = h1; q.w = W.b0c2; q.wskip = W.b0sk; q.bias = W.b0c2_b; q.y_bf16 = x1; q.xs_out = h2 + 2 * kPl1;
-            q.ps_plane_elems = kPl0; q.n = n;
+            q.y_plane_elems = kP21Rows * 64; q.ps_plane_elems = kPl0; q.n = n;
             const int tiles = (int)(((int64_t)n * Ps0::RPC + 127) / 128);
             const int grid = (tiles < h->sm_count ? tiles : h->sm_count) * S::HALVES;
             conv3x3_s1_tc_kernel<64, 11, 13, false, true><<<grid, kS1Threads, S::SMEM, s>>>(q);
             h->launches += 1;
         }
-        a = TcArgs{};
-        a.B = n;
-        a.x = x1; a.w = W.b1c1; a.bias = W.b1c1_b; a.y_bf16 = h2; a.ps_plane_elems = kPl1;
-        launch_tc<64, 128, 11, 13, 2, false, false, 2>(h, a, s);
+        {
+            using S = S2Shape<64, 128, 11, 13>;
+            S2Args q{};
+            q.x = x1; q.w = W.b1c1; q.bias = W.b1c1_b; q.y = h2; q.in_plane_elems = kP21Rows * 64; q.out_plane_elems = kPl1; q.n = n;
+            const int tiles = (int)(((int64_t)n * P21::RPC + 127) / 128);
+            conv3x3_s2_tc_kernel<64, 128, 11, 13><<<tiles < h->sm_count ? tiles : h->sm_count, kS1Threads, S::SMEM, s>>>(q);
+            h->launches += 1;
+        }
         {
             using S = S1Shape<128, 6, 7>;
             S1Args q{};
