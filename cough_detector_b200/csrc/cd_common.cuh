@@ -22,12 +22,18 @@ constexpr int kFeatElem = CD_FEAT_ELEMS; // 9090
 constexpr int kNfft     = 512;
 constexpr int kWin      = 400;
 constexpr int kHop      = 160;
-// bf16 copy of the features as the stem consumes it: rows -3..89, cols -3..108, zero padded
-constexpr int kMapRows  = 93;
-constexpr int kMapPitch = 120;                    // >= 112 (cols -3..108); 120 makes 4 rows = 16 banks apart, so the
-                                                  // stem's 25-pixel rows do not collide when a warp wraps to the next row
-constexpr int kMapPad   = kMapPitch - kFrames;    // zero columns per row: 3 left + the rest right
-constexpr int kMapElems = kMapRows * kMapPitch;   // 11 160 bf16 = 22 320 B per clip
+// bf16 copy of the features as the stem consumes it ("blocked map"): the zero-padded image (feature rows
+// -3..92, time cols -3..104) cut into 4x4 blocks; block (a, b) is one 32-byte row (16 bf16, k = 4 r + c) of a
+// SWIZZLE_32B K-major operand, row index a * kBmapB + b, so the stem's nine 4x4-block taps are shifted views.
+constexpr int kBmapA     = 24;                    // block rows  (map rows 0..95  = feature rows -3..92)
+constexpr int kBmapB     = 27;                    // block cols  (map cols 0..107 = time cols   -3..104)
+constexpr int kBmapRows  = kBmapA * kBmapB;       // 648 operand rows per clip
+constexpr int kMapElems  = kBmapRows * 16;        // 10 368 bf16 = 20 736 B per clip
+// element offset of map pixel (R, C) (R = feature row + 3, C = time col + 3) inside a clip's blocked map
+__host__ __device__ inline int bmap_offset(int R, int C) {
+    const int row = (R >> 2) * kBmapB + (C >> 2), r = R & 3, c = C & 3;
+    return row * 16 + ((((r >> 1) ^ ((row >> 2) & 1)) << 3) | ((r & 1) * 4 + c));   // 16-byte chunk ^= row bit 2
+}
 
 // mel contraction as executed by a lane: slots 0..2 = band `lane` (<= 3 taps for bands 0..31),
 // slots 3..10 = band `lane+32` (<= 8 taps).  idx is the bin index minus 4 (0..123).

@@ -129,6 +129,17 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
 // shared memory is < 256 KB, so the add never carries out of the field).  One 64-bit add per MMA operand
 // instead of rebuilding the descriptor keeps the single issuing thread off the critical path.
 __device__ __forceinline__ uint64_t desc_adv(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
+// SWIZZLE_32B K-major: rows of 16 bf16 = 32 B (exactly one K16 step), 8-row groups 256 B apart, 16-byte chunk c
+// of row r at c ^ ((r >> 2) & 1) (Swizzle<1,4,3>: address bit 4 ^= bit 7).  layout_type = 6, SBO = 256 B.
+__device__ __forceinline__ uint64_t desc_sw32(uint32_t saddr) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)16 << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t swz32(int row, int chunk) { return (uint32_t)(row * 32 + ((chunk ^ ((row >> 2) & 1)) << 4)); }
 __device__ __forceinline__ uint32_t swz128(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
 }  // namespace tc
@@ -151,7 +162,11 @@ umma_selftest_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* _
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < (128 + shift) * (K / 8); i += 128) {
         const int row = i / (K / 8), ch = i % (K / 8), kc = ch >> 3, j = ch & 7;
-        *reinterpret_cast<uint4*>(sA + kc * a_chunk + tc::swz128(row, j)) = *reinterpret_cast<const uint4*>(A + (size_t)row * K + ch * 8);
+        const uint4 v = *reinterpret_cast<const uint4*>(A + (size_t)row * K + ch * 8);
+        if (mode == 2)      // sub-tile per K16 step: [rowsA][32 B], 16-byte chunk c of row r at c ^ ((r >> 2) & 1)
+            *reinterpret_cast<uint4*>(sA + (ch >> 1) * (rowsA * 32) + tc::swz32(row, ch & 1)) = v;
+        else
+            *reinterpret_cast<uint4*>(sA + kc * a_chunk + tc::swz128(row, j)) = v;
     }
     for (int i = tid; i < N * (K / 8); i += 128) {
         const int row = i / (K / 8), ch = i % (K / 8), kc = ch >> 3, j = ch & 7;
@@ -174,6 +189,7 @@ umma_selftest_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* _
                 // shifted view: start the A operand `shift` rows (128 B each) into the tile
                 uint64_t ad = tc::desc_sw128(tc::s32(sA + kc * a_chunk) + shift * 128 + k4 * 32);
                 if (mode == 1) ad |= (uint64_t)(shift & 7) << 49;      // base_offset variant
+                if (mode == 2) ad = tc::desc_sw32(tc::s32(sA + (kc * 4 + k4) * (rowsA * 32)) + shift * 32);
                 tc::umma_bf16(tm, ad, tc::desc_sw128(tc::s32(sB + (size_t)kc * N * 128) + k4 * 32), idesc, (kc | k4) != 0);
             }
         tc::tc_commit(&bar);
@@ -869,189 +885,172 @@ conv3x3_s2_tc_kernel(const S2Args a) {
 // ----------------------------------------------------------------------------------------------
 // stem on tcgen05: 7x7/s2 conv (1 -> 32) + bias + ReLU + MaxPool2d(2) as ONE GEMM per pooled pixel
 // ----------------------------------------------------------------------------------------------
-// Row m = (clip, pooled pixel (py, px)), 550 per clip.  The 2x2 pool window's four conv outputs
-// share a 9 x 9 input patch (rows 4py-3.., cols 4px-3..), so N = 4 pool members x 32 channels = 128
-// and K = 9 patch rows x 16 columns (9 used, 7 zero-weight) = 144: the max-pool becomes an
-// in-register max over four 32-column groups of the accumulator row, and the un-pooled
-// (32, 45, 51) activation never exists.  A rows are 9 contiguous 32-byte runs of the clip's
-// zero-padded bf16 feature map (kMapRows x kMapPitch), staged per clip with one bulk copy.
-constexpr int kStemPix = 22 * 25;                 // 550 pooled pixels per clip
-constexpr int kStemTilesPerClip = 5;              // 4 x 128 + 38
-constexpr int kStemABytes = 3 * 16384;            // 3 K-chunks of 128 rows x 128 B (third: 32 B per row used)
-constexpr int kStemBBytes = 3 * 16384;            // 128 weight rows x 3 chunks
-constexpr int kMapBytes = kMapElems * 2;          // 20 832
-constexpr int kMapBytesPad = (kMapBytes + 127) & ~127;
-constexpr size_t kStemSmem = 1024 + 2 * kStemABytes + kStemBBytes + 2 * kMapBytesPad + 128;
+// Row m' = (clip, pooled pixel (py, px)).  The 2x2 pool window's four conv outputs share the 9 x 9 input
+// patch at rows 4py-3.., cols 4px-3.., so N = 4 pool members x 32 channels = 128 and the max-pool is an
+// in-register max over four 32-column groups of the accumulator row; the un-pooled (32, 45, 51) activation
+// never exists.  The patch is covered by 3 x 3 blocks of 4 x 4 pixels, and the feature kernel writes the
+// clip as exactly those blocks (cd_common.cuh "blocked map": one 32-byte SWIZZLE_32B row per block, row
+// index a * 27 + b), so K = 9 blocks x 16 pixels = 144 and the A operand of block (i, j) is the staged rows
+// viewed (27 i + j) rows further down: no A tile is ever built -- one 5.9 KB bulk copy per 128 pooled pixels.
+constexpr int kStemPix = 22 * 25;                 // 550 pooled pixels per clip (of kBmapRows = 648 GEMM rows)
+constexpr int kStemRowsIn = (128 + 2 * kBmapB + 2 + 7) & ~7;      // 184 rows a tile reads
+constexpr int kStemABytes = ((kStemRowsIn * 32 + 255) / 256) * 256;   // 5888 -> 6144 per stage
+constexpr int kStemStages = 4;
+constexpr int kStemBBytes = 3 * 16384;            // 128 weight rows x 3 chunks of 64 K-elements (144 used)
+constexpr size_t kStemSmem = 1024 + kStemStages * kStemABytes + kStemBBytes + 128;
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kS1Threads, 1)
 stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __restrict__ wq,
                const float* __restrict__ bias, __nv_bfloat16* __restrict__ x0, int64_t x0_plane_elems,
                __nv_bfloat16* __restrict__ xs0, int B) {
     extern __shared__ unsigned char raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
-    unsigned char* sA = base;                                   // [2][3][16384]
-    unsigned char* sB = base + 2 * kStemABytes;                 // [3][16384]
-    unsigned char* sMap = sB + kStemBBytes;                     // [2][kMapBytesPad]
-    float* s_bias = reinterpret_cast<float*>(sMap + 2 * kMapBytesPad);
-    __shared__ uint64_t full_bar[2], empty_bar[2], tfull_bar[2], tempty_bar[2], map_bar[2], w_bar;
+    unsigned char* sA = base;                                   // [kStemStages][kStemABytes]
+    unsigned char* sB = base + kStemStages * kStemABytes;       // [3][16384]
+    float* s_bias = reinterpret_cast<float*>(sB + kStemBBytes);
+    __shared__ uint64_t full_bar[kStemStages], empty_bar[kStemStages], tfull_bar[2], tempty_bar[2], w_bar;
     __shared__ uint32_t tmem_base_s;
     constexpr uint32_t IDESC = tc::idesc_bf16(128, 128);
     constexpr int TMEM_COLS = 256;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t rows = (int64_t)B * kBmapRows;
+    const int n_tiles = (int)((rows + 127) / 128);
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(&full_bar[i], kTcProducers);
+        for (int i = 0; i < kStemStages; ++i) {
+            tc::mbar_init(&full_bar[i], 1);
             tc::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&tfull_bar[i], 1);
-            tc::mbar_init(&tempty_bar[i], kTcEpilogue);
-            tc::mbar_init(&map_bar[i], 1);
+            tc::mbar_init(&tempty_bar[i], 128);
         }
         tc::mbar_init(&w_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 32) s_bias[tid] = bias[tid];
-    if (warp == 4) tc::tmem_alloc(&tmem_base_s, TMEM_COLS);
+    if (warp == 1) tc::tmem_alloc(&tmem_base_s, TMEM_COLS);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp < 4) {
-        // ======================= producers ===========================================================
-        if (tid == 0) {
+    if (warp == 0) {
+        // ======================= producer: weights once, one bulk copy per tile =====================
+        if (lane == 0) {
             tc::mbar_arrive_expect_tx(&w_bar, kStemBBytes);
             tc::bulk_g2s(sB, wq, kStemBBytes, &w_bar);
-            tc::mbar_arrive_expect_tx(&map_bar[0], kMapBytes);
-            tc::bulk_g2s(sMap, maps + (int64_t)blockIdx.x * kMapElems, kMapBytes, &map_bar[0]);
-        }
-        int it = 0, ci = 0;
-        for (int clip = blockIdx.x; clip < B; clip += gridDim.x, ++ci) {
-            const int mb = ci & 1;
-            if (tid == 0 && clip + (int)gridDim.x < B) {       // prefetch the next clip's map
-                tc::mbar_arrive_expect_tx(&map_bar[mb ^ 1], kMapBytes);
-                tc::bulk_g2s(sMap + (mb ^ 1) * kMapBytesPad, maps + (int64_t)(clip + gridDim.x) * kMapElems, kMapBytes,
-                             &map_bar[mb ^ 1]);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int s = it % kStemStages;
+                tc::mbar_wait(&empty_bar[s], (uint32_t)(((it / kStemStages) & 1) ^ 1));
+                tc::mbar_arrive_expect_tx(&full_bar[s], kStemRowsIn * 32);
+                tc::bulk_g2s(sA + s * kStemABytes, maps + (int64_t)tile * 128 * 16, kStemRowsIn * 32, &full_bar[s]);
             }
-            tc::mbar_wait(&map_bar[mb], (uint32_t)((ci >> 1) & 1));
-            const unsigned char* map = sMap + mb * kMapBytesPad;
-            for (int t = 0; t < kStemTilesPerClip; ++t, ++it) {
-                const int s = it & 1;
-                tc::mbar_wait(&empty_bar[s], (uint32_t)(((it >> 1) & 1) ^ 1));
-                const int pix = t * 128 + tid;
-                if (pix < kStemPix) {
-                    const int py = pix / 25, px = pix - py * 25;
-                    const unsigned char* src = map + (4 * py) * (kMapPitch * 2) + px * 8;
-                    unsigned char* dstA = sA + s * kStemABytes;
-#pragma unroll
-                    for (int ry = 0; ry < 9; ++ry) {
-                        const uint2* q = reinterpret_cast<const uint2*>(src + ry * (kMapPitch * 2));
-                        const uint2 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3];
-                        unsigned char* d = dstA + (ry >> 2) * 16384;
-                        const int j0 = (ry & 3) * 2;
-                        *reinterpret_cast<uint4*>(d + tc::swz128(tid, j0)) = make_uint4(v0.x, v0.y, v1.x, v1.y);
-                        *reinterpret_cast<uint4*>(d + tc::swz128(tid, j0 + 1)) = make_uint4(v2.x, v2.y, v3.x, v3.y);
-                    }
-                }
-                tc::fence_proxy_async();
-                tc::mbar_arrive(&full_bar[s]);
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");      // every producer is done with map[mb]
         }
-    } else if (warp == 4) {
-        // ======================= MMA issuer ==========================================================
+    } else if (warp == 1) {
+        // ======================= MMA issuer: nine 4x4-block taps as shifted SWIZZLE_32B views =========
         if (lane == 0) {
             tc::mbar_wait(&w_bar, 0);
+            const uint64_t db = tc::desc_sw128(tc::s32(sB));
             int it = 0;
-            for (int clip = blockIdx.x; clip < B; clip += gridDim.x) {
-                for (int t = 0; t < kStemTilesPerClip; ++t, ++it) {
-                    const int s = it & 1;
-                    tc::mbar_wait(&tempty_bar[s], (uint32_t)(((it >> 1) & 1) ^ 1));
-                    tc::mbar_wait(&full_bar[s], (uint32_t)((it >> 1) & 1));
-                    tc::tc_fence_after();
-                    const uint32_t d = tmem_base + s * 128;
-                    const uint64_t da = tc::desc_sw128(tc::s32(sA + s * kStemABytes)), db = tc::desc_sw128(tc::s32(sB));
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int s = it % kStemStages, acc = it & 1;
+                tc::mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+                tc::mbar_wait(&full_bar[s], (uint32_t)((it / kStemStages) & 1));
+                tc::tc_fence_after();
+                const uint32_t d = tmem_base + acc * 128;
+                const uint64_t da = tc::desc_sw32(tc::s32(sA + s * kStemABytes));
 #pragma unroll
-                    for (int q = 0; q < 9; ++q) {                // K = 144 = 9 x 16
-                        const uint32_t off = (q >> 2) * 16384 + (q & 3) * 32;
-                        tc::umma_bf16(d, tc::desc_adv(da, off), tc::desc_adv(db, off), IDESC, q != 0);
-                    }
-                    tc::tc_commit(&empty_bar[s]);
-                    tc::tc_commit(&tfull_bar[s]);
-                }
+                for (int q = 0; q < 9; ++q)                      // block (i, j) = (q / 3, q % 3); K step q of the weights
+                    tc::umma_bf16(d, tc::desc_adv(da, ((q / 3) * kBmapB + (q % 3)) * 32),
+                                  tc::desc_adv(db, (q >> 2) * 16384 + (q & 3) * 32), IDESC, q != 0);
+                tc::tc_commit(&empty_bar[s]);
+                tc::tc_commit(&tfull_bar[acc]);
             }
         }
     } else {
         // ======================= epilogue: pool max over the 4 column groups, bias, ReLU, bf16 ========
         const int lane_grp = warp & 3;
         int it = 0;
-        for (int clip = blockIdx.x; clip < B; clip += gridDim.x) {
-            for (int t = 0; t < kStemTilesPerClip; ++t, ++it) {
-                const int s = it & 1;
-                tc::mbar_wait(&tfull_bar[s], (uint32_t)((it >> 1) & 1));
-                tc::tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + s * 128;
-                float m[32], v[32];
-                tc::tmem_ld32(taddr, m);
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const int64_t mp = (int64_t)tile * 128 + lane_grp * 32 + lane;
+            const int clip = (int)(mp / kBmapRows), rem = (int)(mp - (int64_t)clip * kBmapRows);
+            const int py = rem / kBmapB, px = rem - py * kBmapB;
+            const bool live = clip < B && py < 22 && px < 25;
+            tc::mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * 128;
+            float m[32], v[32];
+            tc::tmem_ld32(taddr, m);
 #pragma unroll
-                for (int g = 1; g < 4; ++g) {
-                    tc::tmem_ld32(taddr + g * 32, v);
+            for (int g = 1; g < 4; ++g) {
+                tc::tmem_ld32(taddr + g * 32, v);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) m[i] = fmaxf(m[i], v[i]);
-                }
-                tc::tc_fence_before();
-                tc::mbar_arrive(&tempty_bar[s]);
-                const int pix = t * 128 + lane_grp * 32 + lane;
-                if (pix < kStemPix) {
-                    // x0 goes out phase-split (Ps2Layout<22, 25>): plane = (py+1) & 1, row = ((py+1)/2, (px+1)/2),
-                    // the (px+1) parity picks the 64-byte half of the 128-byte row
-                    using P2 = Ps2Layout<22, 25>;
-                    using PSN = PsLayout<11, 13>;
-                    const int py = pix / 25, px = pix - py * 25;
-                    const int64_t r2 = (int64_t)clip * P2::RPC + ((py + 1) >> 1) * P2::B2 + ((px + 1) >> 1);
-                    __nv_bfloat16* op = x0 + (int64_t)((py + 1) & 1) * x0_plane_elems + r2 * 64;
-                    const int jb = ((px + 1) & 1) * 4;
-                    // block 0's skip conv reads x0 at (2y, 2x): emit those pixels as PS rows (32 of 64 channels used)
-                    const bool xs = !(py & 1) && !(px & 1);
-                    const int64_t rg = (int64_t)clip * PSN::RPC + (py / 2 + 1) * PSN::WP + (px / 2 + 1);
-                    __nv_bfloat16* xrow = xs0 + rg * 64;
+                for (int i = 0; i < 32; ++i) m[i] = fmaxf(m[i], v[i]);
+            }
+            tc::tc_fence_before();
+            tc::mbar_arrive(&tempty_bar[acc]);
+            if (live) {
+                // x0 goes out phase-split (Ps2Layout<22, 25>): plane = (py+1) & 1, row = ((py+1)/2, (px+1)/2),
+                // the (px+1) parity picks the 64-byte half of the 128-byte row
+                using P2 = Ps2Layout<22, 25>;
+                using PSN = PsLayout<11, 13>;
+                const int64_t r2 = (int64_t)clip * P2::RPC + ((py + 1) >> 1) * P2::B2 + ((px + 1) >> 1);
+                __nv_bfloat16* op = x0 + (int64_t)((py + 1) & 1) * x0_plane_elems + r2 * 64;
+                const int jb = ((px + 1) & 1) * 4;
+                // block 0's skip conv reads x0 at (2y, 2x): emit those pixels as PS rows (32 of 64 channels used)
+                const bool xs = !(py & 1) && !(px & 1);
+                const int64_t rg = (int64_t)clip * PSN::RPC + (py / 2 + 1) * PSN::WP + (px / 2 + 1);
+                __nv_bfloat16* xrow = xs0 + rg * 64;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint32_t w[4];
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t w[4];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int c = 8 * q + 2 * e;
-                            __nv_bfloat162 pk = __floats2bfloat162_rn(fmaxf(m[c] + s_bias[c], 0.f), fmaxf(m[c + 1] + s_bias[c + 1], 0.f));
-                            w[e] = *reinterpret_cast<uint32_t*>(&pk);
-                        }
-                        *reinterpret_cast<uint4*>(op + (((jb + q) ^ (int)(r2 & 7)) << 3)) = make_uint4(w[0], w[1], w[2], w[3]);
-                        if (xs) *reinterpret_cast<uint4*>(xrow + ((q ^ (int)(rg & 7)) << 3)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = 8 * q + 2 * e;
+                        __nv_bfloat162 pk = __floats2bfloat162_rn(fmaxf(m[c] + s_bias[c], 0.f), fmaxf(m[c + 1] + s_bias[c + 1], 0.f));
+                        w[e] = *reinterpret_cast<uint32_t*>(&pk);
                     }
+                    *reinterpret_cast<uint4*>(op + (((jb + q) ^ (int)(r2 & 7)) << 3)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    if (xs) *reinterpret_cast<uint4*>(xrow + ((q ^ (int)(rg & 7)) << 3)) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
         }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 4) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// fp32 features (B, 90, 101) -> the stem's zero-padded bf16 map (for callers that hand features in)
+// fp32 features (B, 90, 101) -> the stem's blocked bf16 map (for callers that hand features in): one thread
+// per 4x4 block = one 32-byte operand row
 __global__ void __launch_bounds__(256)
 map_from_feat_kernel(const float* __restrict__ feat, __nv_bfloat16* __restrict__ maps, int64_t B) {
     const int64_t b = blockIdx.y;
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= kMapElems / 2) return;
+    const int row = blockIdx.x * 256 + threadIdx.x;
+    if (row >= kBmapRows) return;
     const float* f = feat + b * (int64_t)kFeatElem;
-    const int r = (2 * i) / kMapPitch - 3, c0 = (2 * i) % kMapPitch - 3;
-    float v[2];
+    const int ba = row / kBmapB, bb = row - ba * kBmapB;
+    uint32_t w[8];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-        const int c = c0 + e;
-        v[e] = (r >= 0 && c >= 0 && c < kFrames) ? f[r * kFrames + c] : 0.f;
+    for (int r = 0; r < 4; ++r) {
+        const int fr = 4 * ba + r - 3;
+        float v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int t = 4 * bb + c - 3;
+            v[c] = (fr >= 0 && fr < kFeat && t >= 0 && t < kFrames) ? f[fr * kFrames + t] : 0.f;
+        }
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+        w[2 * r] = *reinterpret_cast<uint32_t*>(&p0);
+        w[2 * r + 1] = *reinterpret_cast<uint32_t*>(&p1);
     }
-    __nv_bfloat162 pk = __floats2bfloat162_rn(v[0], v[1]);
-    reinterpret_cast<uint32_t*>(maps + b * (int64_t)kMapElems)[i] = *reinterpret_cast<uint32_t*>(&pk);
+    uint4* dst = reinterpret_cast<uint4*>(maps + (b * kBmapRows + row) * 16);
+    const int sw = (row >> 2) & 1;                   // chunk (r >> 1) lives at (r >> 1) ^ ((row >> 2) & 1)
+    dst[0 ^ sw] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1 ^ sw] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
 // AdaptiveAvgPool2d(1) + Flatten + Linear(128 -> 2); x2 is [B][42][128] fp32; fixed summation order
@@ -1133,15 +1132,18 @@ int upload_cnn_tc(cd_handle* h, const std::vector<std::vector<float>>& wf, const
         pack_weights(wf[1 + i], spec[i][0], spec[i][1], spec[i][2], packs[i]);
         total_bf += (packs[i].size() + 63) & ~size_t(63);
     }
-    {   // stem as a pooled GEMM: W2[k = ry*16 + cx][n = (dy*2+dx)*32 + co] = w[co][ry - 2dy][cx - 2dx]
+    {   // stem as a pooled GEMM over 3x3 blocks of 4x4 pixels: patch pixel (ry, rx) = (2dy + ky, 2dx + kx) lives in
+        // block (ry / 4, rx / 4) at k16 = 4 (ry % 4) + rx % 4:  W2[k][n = (dy*2+dx)*32 + co] = w[co][ky][kx]
         std::vector<float> w2((size_t)192 * 128, 0.f);
         for (int dy = 0; dy < 2; ++dy)
             for (int dx = 0; dx < 2; ++dx)
                 for (int ky = 0; ky < 7; ++ky)
                     for (int kx = 0; kx < 7; ++kx)
-                        for (int co = 0; co < 32; ++co)
-                            w2[(size_t)((2 * dy + ky) * 16 + 2 * dx + kx) * 128 + (dy * 2 + dx) * 32 + co] =
-                                wf[0][(size_t)(ky * 7 + kx) * 32 + co];
+                        for (int co = 0; co < 32; ++co) {
+                            const int ry = 2 * dy + ky, rx = 2 * dx + kx;
+                            const int k = ((ry >> 2) * 3 + (rx >> 2)) * 16 + (ry & 3) * 4 + (rx & 3);
+                            w2[(size_t)k * 128 + (dy * 2 + dx) * 32 + co] = wf[0][(size_t)(ky * 7 + kx) * 32 + co];
+                        }
         pack_weights(w2, 192, 1, 128, packs[6]);
         total_bf += (packs[6].size() + 63) & ~size_t(63);
     }
@@ -1190,7 +1192,7 @@ constexpr int64_t kPs0Rows = ((kTcChunk * Ps0::RPC + 127) / 128) * 128 + Ps0::RO
 constexpr int64_t kPs1Rows = ((kTcChunk * Ps1::RPC + 127) / 128) * 128 + Ps1::ROWS_IN;
 constexpr int64_t al256(int64_t x) { return (x + 255) & ~int64_t(255); }
 constexpr int64_t kOffMap = 0;
-constexpr int64_t kOffX0 = kOffMap + al256(kTcChunk * kMapElems * 2);
+constexpr int64_t kOffX0 = kOffMap + al256((kTcChunk * kBmapRows + 128 + kStemRowsIn) * 32);   // + last tile's look-ahead
 using P20 = Ps2Layout<22, 25>;
 using P21 = Ps2Layout<11, 13>;
 constexpr int64_t kP20Rows = ((kTcChunk * P20::RPC + 127) / 128) * 128 + P20::ROWS_IN;    // x0, 2 planes
@@ -1247,11 +1249,14 @@ int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits,
     for (int64_t c0 = 0; c0 < B; c0 += kTcChunk) {
         const int n = (int)((B - c0) < kTcChunk ? (B - c0) : kTcChunk);
         if (d_feat) {
-            map_from_feat_kernel<<<dim3((kMapElems / 2 + 255) / 256, n), 256, 0, s>>>(d_feat + c0 * kFeatElem, maps, n);
+            map_from_feat_kernel<<<dim3((kBmapRows + 255) / 256, n), 256, 0, s>>>(d_feat + c0 * kFeatElem, maps, n);
             h->launches += 1;
         }
-        stem_tc_kernel<<<n < h->sm_count ? n : h->sm_count, kTcThreads, kStemSmem, s>>>(maps, W.stem_w, W.stem_b, x0,
-                                                                                         kP20Rows * 64, h1 + kPl0, n);
+        {
+            const int tiles = (int)(((int64_t)n * kBmapRows + 127) / 128);
+            stem_tc_kernel<<<tiles < h->sm_count ? tiles : h->sm_count, kS1Threads, kStemSmem, s>>>(
+                maps, W.stem_w, W.stem_b, x0, kP20Rows * 64, h1 + kPl0, n);
+        }
         h->launches += 1;
         {
             using S = S2Shape<32, 64, 22, 25>;

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cough_detector_b200 import _lib
 h = _lib.get_handle(0)
 g = torch.Generator().manual_seed(0)
-for mode in (0, 1):
+for mode in (0, 2):
     for shift in (0, 1, 2, 7, 8, 9, 15, 16, 17, 30, 31, 32):
         a = torch.randn(128 + shift, 128, generator=g)
         b = torch.randn(64, 128, generator=g)
