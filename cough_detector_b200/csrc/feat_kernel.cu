@@ -335,19 +335,14 @@ __device__ __forceinline__ float mfcc_par(const float* __restrict__ db, float* _
 // normalisation, deltas; fp32 features to `out` and/or the stem's bf16 map to `mo` (either may be null).
 // Ends with the block in sync except for the final stores.
 template <class SM>
-__device__ __forceinline__ void feat_tail(SM& S, float wmax, float* __restrict__ out, __nv_bfloat16* __restrict__ mo,
-                                          __nv_bfloat16* __restrict__ smap, int tid) {
+__device__ __forceinline__ void feat_tail(SM& S, float wmax, float* __restrict__ out, __nv_bfloat16* __restrict__ mo, int tid) {
     const float top = block_reduce<true>(wmax, S.red);             // barrier: dB tile complete, clip buffer dead
-    if (mo) {                                                      // blocked map image: start from zeros (padding)
-        uint4* z = reinterpret_cast<uint4*>(smap);
-        for (int i = tid; i < kMapElems / 8; i += kFeatThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
-        __syncthreads();
-    }
     const float floor_db = top - 80.0f;                            // top_db = 80
 
     // ---- mel block rows 0..63: max(dB, floor) -> (dB + 80) / 80 -> clamp ------------------------
-    // The CNN stem's operand rides along: the same values rounded to bf16, scattered into the blocked map
-    // image in shared memory (cd_common.cuh: bmap_offset) and copied out in one coalesced pass at the end.
+    // The CNN stem's operand rides along: the same values rounded to bf16, scattered straight into the clip's
+    // blocked map (cd_common.cuh: bmap_offset).  Its padding elements are never written by anyone: the map
+    // lives in the tensor-core workspace, which is zeroed once at allocation.
     for (int i = tid; i < kMels * kFrames; i += kFeatThreads) {
         const float v = fmaxf(S.db[i], floor_db);
         S.db[i] = v;
@@ -355,7 +350,7 @@ __device__ __forceinline__ void feat_tail(SM& S, float wmax, float* __restrict__
         if (out) out[i] = x01;
         if (mo) {
             const int r = i / kFrames;
-            smap[bmap_offset(r + 3, i - r * kFrames + 3)] = __float2bfloat16_rn(x01);
+            mo[bmap_offset(r + 3, i - r * kFrames + 3)] = __float2bfloat16_rn(x01);
         }
     }
     __syncthreads();
@@ -391,17 +386,12 @@ __device__ __forceinline__ void feat_tail(SM& S, float wmax, float* __restrict__
                 out[(kMels + kMfcc + cidx) * kFrames + t] = dl;
             }
             if (mo) {
-                smap[bmap_offset(kMels + cidx + 3, t + 3)] = __float2bfloat16_rn(x0);
-                smap[bmap_offset(kMels + kMfcc + cidx + 3, t + 3)] = __float2bfloat16_rn(dl);
+                mo[bmap_offset(kMels + cidx + 3, t + 3)] = __float2bfloat16_rn(x0);
+                mo[bmap_offset(kMels + kMfcc + cidx + 3, t + 3)] = __float2bfloat16_rn(dl);
             }
         }
     }
-    if (mo) {
-        __syncthreads();
-        const uint4* src = reinterpret_cast<const uint4*>(smap);
-        uint4* dst = reinterpret_cast<uint4*>(mo);
-        for (int i = tid; i < kMapElems / 8; i += kFeatThreads) dst[i] = src[i];
-    }
+
 }
 
 struct ClipDesc {
@@ -521,7 +511,7 @@ feat_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offs, c
                                     : frame_pair<false, false>(S, clip, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, base0, second, lane, dst, kFrames, 1));
         }
         feat_tail(S, wmax, feat ? feat + b * (int64_t)kFeatElem : nullptr,
-                  map_out ? map_out + b * (int64_t)kMapElems : nullptr, reinterpret_cast<__nv_bfloat16*>(S.clip), tid);
+                  map_out ? map_out + b * (int64_t)kMapElems : nullptr, tid);
         __syncthreads();                                               // xb / db / clip[cur] free again
     }
 }
@@ -541,7 +531,6 @@ struct MelSmem {
 };
 struct StreamSmem {
     float2 xb[kFeatWarps][kXbElems];
-    __align__(16) __nv_bfloat16 bmap[kMapElems];
     float  db[kMels * kFrames];
     float2 tw1[7][64];
     float2 tw2[7][8];
@@ -639,7 +628,7 @@ stream_window_kernel(const float* __restrict__ audio, int64_t hop, int64_t n_win
             }
         }
         feat_tail(S, wmax, feat ? feat + j * (int64_t)kFeatElem : nullptr,
-                  map_out ? map_out + j * (int64_t)kMapElems : nullptr, S.bmap, tid);
+                  map_out ? map_out + j * (int64_t)kMapElems : nullptr, tid);
         __syncthreads();
     }
 }
