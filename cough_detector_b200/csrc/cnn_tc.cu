@@ -1,21 +1,22 @@
 // CoughDetectorResidual forward on the 5th-generation tensor cores (CD_PRECISION_BF16).
 //
-// Replaces src/model.py:253-293 (forward of the stem + two ResidualBlocks + head) in eval mode
-// with BatchNorm folded into bf16 weights.  The four 3x3 convolutions and the two 1x1 skip
-// projections are implicit GEMMs: M = (clip, output pixel) rows in tiles of 128, N = C_out,
-// K = 9*C_in walked in 64-element (128-byte) chunks.
+// Replaces src/model.py:253-293 (forward of the stem + two ResidualBlocks + head) in eval mode with
+// BatchNorm folded into bf16 weights.  Every convolution is a GEMM whose A operand is never built:
+// activations live in global memory as rows that are ALREADY shared-memory operand images (pixel = one
+// swizzled K-major row), a tile of 128 output pixels is staged with one cp.async.bulk per 64-channel plane,
+// and each filter tap is the same staged rows seen through a descriptor whose start address is shifted by
+// whole rows (the tensor core swizzles on absolute address bits; cd_selftest_umma checks that).
 //
-//   producer warps 0-3 : gather the im2col A tile with cp.async (16-byte channel groups of the
-//                        NHWC bf16 activation, zero-fill for padding) straight into the
-//                        SWIZZLE_128B K-major layout tcgen05 reads; thread 0 streams the
-//                        pre-swizzled weight chunk with one cp.async.bulk (TMA engine)
-//   MMA warp 4         : one elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32)
-//                        into TMEM; the 1x1/s2 skip conv re-uses the centre-tap A chunk into a
-//                        second accumulator; tcgen05.commit frees smem stages / publishes tiles
-//   epilogue warps 5-8 : tcgen05.ld the accumulators, + folded bias, ReLU / residual add, store
-//                        bf16 NHWC (or fp32 for the last layer); accumulators are double
-//                        buffered in TMEM so the epilogue of tile i overlaps the MMAs of i+1
-// The stem (C_in = 1) and the 42-pixel average pool + Linear(128->2) run on CUDA cores for now.
+//   producer warp 0   : weights once (resident), then one bulk copy (TMA engine) per plane per tile
+//   MMA warp 1        : one elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32, M = 128) into
+//                       TMEM; tcgen05.commit frees operand slots / publishes accumulators
+//   epilogue warps 2-5: tcgen05.ld, + folded bias, ReLU (stem: 2x2 max-pool first), store bf16 rows in the
+//                       layout the next kernel stages; accumulators are double buffered in TMEM
+//
+//   stem_tc_kernel            7x7/s2 + ReLU + maxpool as ONE GEMM per pooled pixel over 4x4-pixel blocks
+//   conv3x3_s2_tc_kernel x2   conv1 of each block (stride 2) over the phase-split input
+//   conv3x3_s1_tc_kernel x2   conv2 of each block (stride 1) + the block's 1x1/s2 skip conv as a tenth tap
+//   head_kernel               42-pixel average pool + Linear(128->2) on CUDA cores (fixed summation order)
 #include <vector>
 
 #include "cd_common.cuh"
@@ -61,13 +62,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(s32(dst)), "l"(src), "r"(bytes), "r"(s32(bar)) : "memory");
 }
-// 16-byte async copy, src_bytes = 0 zero-fills (implicit-GEMM padding)
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -207,41 +201,8 @@ umma_selftest_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* _
 }
 
 // ----------------------------------------------------------------------------------------------
-// implicit-GEMM 3x3 convolution (pad 1) on tcgen05
+// activation layouts of the convolution kernels
 // ----------------------------------------------------------------------------------------------
-constexpr int kTcProducers = 128, kTcEpilogue = 128;
-constexpr int kTcThreads = kTcProducers + 32 + kTcEpilogue;     // 288
-
-// Pipeline depth: the im2col gather is L2-latency bound, so the number of chunks in flight per SM is
-// what matters.  C_out = 64: 4 stages of 24 KB and two CTAs per SM; C_out = 128: 6 stages of 32 KB.
-template <int CIN, int COUT>
-struct TcShape {
-    static constexpr int STAGES = COUT <= 64 ? 4 : 6;
-    static constexpr int LAG = COUT <= 64 ? 3 : 4;               // chunks issued ahead of the one being published
-    static constexpr int CTAS_PER_SM = COUT <= 64 ? 2 : 1;
-    static constexpr int KTOT = 9 * CIN;
-    static constexpr int NKC = (KTOT + 63) / 64;                 // 64-element K chunks (5 / 9 / 18)
-    static constexpr int A_BYTES = 128 * 128;                    // 128 rows x 128 B
-    static constexpr int B_BYTES = COUT * 128;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int SKIP_K = CIN < 64 ? CIN : 64;           // K of the 1x1 projection (per 64-chunk)
-    static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + B_BYTES /*skip W*/ + 2 * COUT * 4 + 256;
-};
-
-struct TcArgs {
-    const __nv_bfloat16* x;        // NHWC bf16 input  [B][HIN][WIN][CIN]
-    const __nv_bfloat16* w;        // pre-swizzled weight chunks [NKC][COUT x 128 B]
-    const __nv_bfloat16* wskip;    // pre-swizzled skip weights [COUT x 128 B] (SKIP)
-    const float* bias;             // [COUT]
-    const float* bias_skip;        // [COUT] (SKIP)
-    const float* idt_in;           // [M][COUT] fp32 (RESID)
-    __nv_bfloat16* y_bf16;         // [M][COUT]
-    float* y_f32;                  // [M][COUT] (OUT_F32)
-    float* idt_out;                // [M][COUT] fp32 (SKIP)
-    int64_t ps_plane_elems;        // OUT_MODE 2: elements between the 64-channel planes
-    int B;
-};
-
 // Padded + swizzled ("PS") activation layout consumed by the stride-1 kernel: every clip is a zero-padded
 // (H+2) x (W+2) image whose pixels are 128-byte rows of 64 channels (C = 128: two such planes); global row
 // rg = clip * RPC + (y+1) * WP + (x+1); the 16-byte chunk j of a row is stored at chunk j ^ (rg & 7), i.e.
@@ -261,237 +222,6 @@ struct Ps2Layout {
     static constexpr int A2 = (H + 3) / 2, B2 = (W + 3) / 2, RPC = A2 * B2;
     static constexpr int ROWS_IN = (128 + B2 + 1 + 7) & ~7;
 };
-
-// OUT_MODE: 0 = bf16 NHWC rows [M][COUT]; 1 = fp32 rows; 2 = bf16 in the padded + swizzled layout the
-// stride-1 kernel bulk-copies (see PsLayout)
-template <int CIN, int COUT, int HIN, int WIN, int STRIDE, bool SKIP, bool RESID, int OUT_MODE>
-__global__ void __launch_bounds__(kTcThreads, TcShape<CIN, COUT>::CTAS_PER_SM)
-conv3x3_tc_kernel(const TcArgs a) {
-    using S = TcShape<CIN, COUT>;
-    constexpr int kTcStages = S::STAGES, kLag = S::LAG;
-    constexpr int HOUT = (HIN - 1) / STRIDE + 1, WOUT = (WIN - 1) / STRIDE + 1, NPOS = HOUT * WOUT;
-    constexpr int ACC_COLS = SKIP ? 2 * COUT : COUT;             // conv accumulator [+ skip accumulator]
-    constexpr int TMEM_COLS = 2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512);
-    static_assert(2 * ACC_COLS <= 512, "TMEM");
-    constexpr uint32_t IDESC = tc::idesc_bf16(128, COUT);
-
-    extern __shared__ unsigned char raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
-    unsigned char* s_skipw = base + (size_t)kTcStages * S::STAGE_BYTES;
-    float* s_bias = reinterpret_cast<float*>(s_skipw + S::B_BYTES);      // [2][COUT]
-    __shared__ uint64_t full_bar[kTcStages], empty_bar[kTcStages], tfull_bar[2], tempty_bar[2], skipw_bar;
-    __shared__ uint32_t tmem_base_s;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t M = (int64_t)a.B * NPOS;
-    const int n_tiles = (int)((M + 127) / 128);
-
-    if (tid == 0) {
-        for (int s = 0; s < kTcStages; ++s) {
-            tc::mbar_init(&full_bar[s], kTcProducers);
-            tc::mbar_init(&empty_bar[s], 1);
-        }
-        for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(&tfull_bar[i], 1);
-            tc::mbar_init(&tempty_bar[i], kTcEpilogue);
-        }
-        tc::mbar_init(&skipw_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = tid; i < COUT; i += kTcThreads) {
-        s_bias[i] = a.bias[i];
-        s_bias[COUT + i] = SKIP ? a.bias_skip[i] : 0.f;
-    }
-    if (warp == 4) tc::tmem_alloc(&tmem_base_s, TMEM_COLS);
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    const uint32_t tmem_base = tmem_base_s;
-
-    if (warp < 4) {
-        // ======================= producers: im2col gather + weight stream ==========================
-        if (SKIP && tid == 0) {
-            tc::mbar_arrive_expect_tx(&skipw_bar, S::B_BYTES);
-            tc::bulk_g2s(s_skipw, a.wskip, S::B_BYTES, &skipw_bar);
-        }
-        const int j = tid & 7;                       // 16-byte chunk within the 128-byte K row
-        const int r0 = tid >> 3;                     // rows r0 + 16 i
-        const uint32_t dst_off = tc::swz128(r0, j);  // (r0 + 16 i) & 7 == r0 & 7
-        int it = 0;                                  // global chunk counter -> stage / parity
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            int pix_off[8];                          // element offset of input pixel (oy*S-1, ox*S-1), channel 0
-            int iyx[8];                              // (iy0 + 1) << 16 | (ix0 + 1), or -1 for rows past M
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int64_t m = (int64_t)tile * 128 + r0 + 16 * i;
-                if (m < M) {
-                    const int b = (int)(m / NPOS), pos = (int)(m - (int64_t)b * NPOS);
-                    const int oy = pos / WOUT, ox = pos - oy * WOUT;
-                    const int iy0 = oy * STRIDE - 1, ix0 = ox * STRIDE - 1;
-                    pix_off[i] = ((b * HIN + iy0) * WIN + ix0) * CIN;
-                    iyx[i] = ((iy0 + 1) << 16) | (ix0 + 1);
-                } else {
-                    pix_off[i] = 0;
-                    iyx[i] = -1;
-                }
-            }
-            for (int kc = 0; kc < S::NKC; ++kc, ++it) {
-                const int s = it % kTcStages;
-                const uint32_t par = (uint32_t)((it / kTcStages) & 1);
-                tc::mbar_wait(&empty_bar[s], par ^ 1u);
-                unsigned char* stage = base + (size_t)s * S::STAGE_BYTES;
-                if (tid == 0) {
-                    tc::mbar_expect_tx(&full_bar[s], S::B_BYTES);
-                    tc::bulk_g2s(stage + S::A_BYTES, reinterpret_cast<const unsigned char*>(a.w) + (size_t)kc * S::B_BYTES,
-                                 S::B_BYTES, &full_bar[s]);
-                }
-                // K index of this thread's chunk -> (tap, first channel)
-                const int k = kc * 64 + j * 8;
-                const int tap = k / CIN, c0 = k - tap * CIN;
-                const int ky = tap / 3, kx = tap - ky * 3;
-                const int tap_off = (ky * WIN + kx) * CIN + c0;
-                const uint32_t sdst = tc::s32(stage) + dst_off;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int iy = (iyx[i] >> 16) - 1 + ky, ix = (iyx[i] & 0xffff) - 1 + kx;
-                    const bool ok = iyx[i] >= 0 && tap < 9 && iy >= 0 && iy < HIN && ix >= 0 && ix < WIN;
-                    const __nv_bfloat16* src = ok ? a.x + pix_off[i] + tap_off : a.x;
-                    tc::cp_async16(sdst + i * 16 * 128, src, ok ? 16u : 0u);
-                }
-                tc::cp_async_commit();
-                if (it >= kLag) {                     // publish the stage filled kLag chunks ago
-                    tc::cp_async_wait<kLag>();
-                    tc::fence_proxy_async();
-                    tc::mbar_arrive(&full_bar[(it - kLag) % kTcStages]);
-                }
-            }
-        }
-        // drain
-        tc::cp_async_wait<0>();
-        tc::fence_proxy_async();
-#pragma unroll
-        for (int q = kLag; q >= 1; --q)
-            if (it >= q) tc::mbar_arrive(&full_bar[(it - q) % kTcStages]);
-    } else if (warp == 4) {
-        // ======================= MMA issuer ==========================================================
-        if (lane == 0) {
-            if (SKIP) tc::mbar_wait(&skipw_bar, 0);
-            int it = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-                const int acc = tcount & 1;
-                tc::mbar_wait(&tempty_bar[acc], (uint32_t)(((tcount >> 1) & 1) ^ 1));
-                tc::tc_fence_after();
-                const uint32_t d_conv = tmem_base + acc * ACC_COLS;
-                const uint32_t d_skip = d_conv + COUT;
-                for (int kc = 0; kc < S::NKC; ++kc, ++it) {
-                    const int s = it % kTcStages;
-                    tc::mbar_wait(&full_bar[s], (uint32_t)((it / kTcStages) & 1));
-                    tc::tc_fence_after();
-                    const uint32_t sa = tc::s32(base + (size_t)s * S::STAGE_BYTES);
-                    const uint64_t da = tc::desc_sw128(sa), db = tc::desc_sw128(sa + S::A_BYTES);
-#pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4)
-                        tc::umma_bf16(d_conv, tc::desc_adv(da, k4 * 32), tc::desc_adv(db, k4 * 32), IDESC, (kc | k4) != 0);
-                    if (SKIP) {
-                        // centre tap (ky = kx = 1, tap 4) = K range [4*CIN, 5*CIN)
-                        constexpr int KC_C = (4 * CIN) / 64, K4_0 = ((4 * CIN) % 64) / 16, NK4 = S::SKIP_K / 16;
-                        if (CIN <= 64) {
-                            if (kc == KC_C) {
-#pragma unroll
-                                for (int q = 0; q < NK4; ++q)
-                                    tc::umma_bf16(d_skip, tc::desc_sw128(sa + (K4_0 + q) * 32),
-                                                  tc::desc_sw128(tc::s32(s_skipw) + q * 32), IDESC, q != 0);
-                            }
-                        }
-                    }
-                    tc::tc_commit(&empty_bar[s]);       // frees the stage when these MMAs retire
-                }
-                tc::tc_commit(&tfull_bar[acc]);         // accumulators of this tile complete
-            }
-        }
-    } else {
-        // ======================= epilogue ============================================================
-        const int ew = warp - 5;                        // 0..3
-        const int lane_grp = warp & 3;                  // TMEM lanes 32*(warp%4) .. +31 are this warp's
-        const int row = lane_grp * 32 + lane;
-        (void)ew;
-        int tcount = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-            const int acc = tcount & 1;
-            tc::mbar_wait(&tfull_bar[acc], (uint32_t)((tcount >> 1) & 1));
-            tc::tc_fence_after();
-            const int64_t m = (int64_t)tile * 128 + row;
-            const bool live = m < M;
-            const uint32_t t_conv = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * ACC_COLS;
-#pragma unroll 1
-            for (int c0 = 0; c0 < COUT; c0 += 32) {
-                float v[32];
-                tc::tmem_ld32(t_conv + c0, v);
-                if (live) {
-                    if (RESID) {
-                        const float4* ip = reinterpret_cast<const float4*>(a.idt_in + m * COUT + c0);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 t = __ldg(ip + q);
-                            v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + s_bias[c0 + i], 0.f);
-                    if (OUT_MODE == 1) {
-                        float4* op = reinterpret_cast<float4*>(a.y_f32 + m * COUT + c0);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                    } else {
-                        using PS = PsLayout<HOUT, WOUT>;
-                        const int bq = (int)(m / NPOS), pos = (int)(m - (int64_t)bq * NPOS);
-                        const int oy = pos / WOUT, ox = pos - oy * WOUT;
-                        const int64_t rg = (int64_t)bq * PS::RPC + (oy + 1) * PS::WP + (ox + 1);
-                        __nv_bfloat16* prow = a.y_bf16 + (int64_t)(c0 / 64) * a.ps_plane_elems + rg * 64;
-                        uint4* op = reinterpret_cast<uint4*>(a.y_bf16 + m * COUT + c0);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * q], v[8 * q + 1]);
-                            __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
-                            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
-                            __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
-                            uint4 pk;
-                            pk.x = *reinterpret_cast<uint32_t*>(&p0);
-                            pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&p2);
-                            pk.w = *reinterpret_cast<uint32_t*>(&p3);
-                            if (OUT_MODE == 2) {
-                                const int jch = (c0 & 63) / 8 + q;           // 16-byte chunk within the 64-channel plane
-                                *reinterpret_cast<uint4*>(prow + ((jch ^ (int)(rg & 7)) << 3)) = pk;
-                            } else {
-                                op[q] = pk;
-                            }
-                        }
-                    }
-                }
-            }
-            if (SKIP) {
-#pragma unroll 1
-                for (int c0 = 0; c0 < COUT; c0 += 32) {
-                    float v[32];
-                    tc::tmem_ld32(t_conv + COUT + c0, v);
-                    if (live) {
-                        float4* op = reinterpret_cast<float4*>(a.idt_out + m * COUT + c0);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            op[q] = make_float4(v[4 * q] + s_bias[COUT + c0 + 4 * q], v[4 * q + 1] + s_bias[COUT + c0 + 4 * q + 1],
-                                                v[4 * q + 2] + s_bias[COUT + c0 + 4 * q + 2], v[4 * q + 3] + s_bias[COUT + c0 + 4 * q + 3]);
-                    }
-                }
-            }
-            tc::tc_fence_before();
-            tc::mbar_arrive(&tempty_bar[acc]);
-        }
-    }
-    tc::tc_fence_before();
-    __syncthreads();
-    if (warp == 4) tc::tmem_dealloc(tmem_base, TMEM_COLS);
-}
 
 // ----------------------------------------------------------------------------------------------
 // stride-1 3x3 convolution without im2col: shifted descriptor views over PS-layout rows
@@ -1088,8 +818,6 @@ struct TcWeights {                 // device pointers into h->d_wblob_bf16 (bf16
 };
 static TcWeights g_tcw[64];        // per device index
 
-static float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
-
 // folded weights [tap][cin][cout] fp32 -> [kc][cout rows x 128 B] bf16, SWIZZLE_128B K-major, K padded to 64
 static void pack_weights(const std::vector<float>& wf, int taps, int cin, int cout, std::vector<__nv_bfloat16>& out) {
     const int ktot = taps * cin, nkc = (ktot + 63) / 64;
@@ -1100,12 +828,6 @@ static void pack_weights(const std::vector<float>& wf, int taps, int cin, int co
             const size_t off = (size_t)kc * cout * 64 + (size_t)n * 64 + (size_t)((ch ^ (n & 7)) * 8) + e;
             out[off] = __float2bfloat16_rn(wf[(size_t)k * cout + n]);      // k = tap*cin + ci
         }
-}
-
-template <int CIN, int COUT, int HIN, int WIN, int STRIDE, bool SKIP, bool RESID, int OUT_MODE>
-static cudaError_t tc_attr() {
-    return cudaFuncSetAttribute(conv3x3_tc_kernel<CIN, COUT, HIN, WIN, STRIDE, SKIP, RESID, OUT_MODE>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcShape<CIN, COUT>::SMEM);
 }
 
 int init_cnn_tc(cd_handle* h) {
@@ -1217,18 +939,6 @@ int ensure_tc_ws(cd_handle* h) {
 // the first region holds the bf16 maps of the current chunk: the feature kernel writes them there
 // directly in the end-to-end path (call ensure_tc_ws first)
 __nv_bfloat16* cnn_tc_map_ptr(cd_handle* h) { return reinterpret_cast<__nv_bfloat16*>(h->d_ws_tc + kOffMap); }
-
-template <int CIN, int COUT, int HIN, int WIN, int STRIDE, bool SKIP, bool RESID, int OUT_MODE>
-static void launch_tc(cd_handle* h, const TcArgs& a, cudaStream_t s) {
-    constexpr int HOUT = (HIN - 1) / STRIDE + 1, WOUT = (WIN - 1) / STRIDE + 1;
-    const int64_t M = (int64_t)a.B * HOUT * WOUT;
-    const int tiles = (int)((M + 127) / 128);
-    const int slots = h->sm_count * TcShape<CIN, COUT>::CTAS_PER_SM;
-    const int grid = tiles < slots ? tiles : slots;
-    conv3x3_tc_kernel<CIN, COUT, HIN, WIN, STRIDE, SKIP, RESID, OUT_MODE>
-        <<<grid, kTcThreads, TcShape<CIN, COUT>::SMEM, s>>>(a);
-    h->launches += 1;
-}
 
 // d_feat != nullptr: features come in as fp32 and are converted chunk by chunk; d_feat == nullptr:
 // the maps of the (single, <= kTcChunk clips) chunk are already in the workspace.
