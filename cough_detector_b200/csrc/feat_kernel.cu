@@ -343,24 +343,15 @@ __device__ __forceinline__ void feat_tail(SM& S, float wmax, float* __restrict__
     // The CNN stem's operand rides along: the same values rounded to bf16, scattered straight into the clip's
     // blocked map (cd_common.cuh: bmap_offset).  Its padding elements are never written by anyone: the map
     // lives in the tensor-core workspace, which is zeroed once at allocation.
-    // Work items are (row, column pair): time columns (2u - 1, 2u) share one 4-byte slot of a map block
-    // (map column 2u + 2 is even), so the map gets bf16x2 stores; column -1 is padding and stores 0.
-    constexpr int kPairsT = (kFrames + 1) / 2;                         // 51
-    for (int i = tid; i < kMels * kPairsT; i += kFeatThreads) {
-        const int r = i / kPairsT, u = i - r * kPairsT, t0 = 2 * u - 1;
-        float x01[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int t = t0 + e;
-            x01[e] = 0.f;
-            if (t >= 0) {
-                const float v = fmaxf(S.db[r * kFrames + t], floor_db);
-                S.db[r * kFrames + t] = v;
-                x01[e] = fminf(fmaxf((v + 80.0f) * 0.0125f, 0.f), 1.f);
-                if (out) out[r * kFrames + t] = x01[e];
-            }
+    for (int i = tid; i < kMels * kFrames; i += kFeatThreads) {
+        const float v = fmaxf(S.db[i], floor_db);
+        S.db[i] = v;
+        const float x01 = fminf(fmaxf((v + 80.0f) * 0.0125f, 0.f), 1.f);
+        if (out) out[i] = x01;
+        if (mo) {
+            const int r = i / kFrames;
+            mo[bmap_offset(r + 3, i - r * kFrames + 3)] = __float2bfloat16_rn(x01);
         }
-        if (mo) *reinterpret_cast<__nv_bfloat162*>(mo + bmap_offset(r + 3, t0 + 3)) = __floats2bfloat162_rn(x01[0], x01[1]);
     }
     __syncthreads();
 
@@ -381,30 +372,26 @@ __device__ __forceinline__ void feat_tail(SM& S, float wmax, float* __restrict__
     }
     ss = block_reduce<false>(ss, S.red);
     const float inv_std = 1.0f / (sqrtf(ss * (1.0f / (kN - 1))) + 1e-8f);
-    for (int i = tid; i < kMfcc * kPairsT; i += kFeatThreads) {
-        const int cidx = i / kPairsT, u = i - cidx * kPairsT, t0 = 2 * u - 1;
-        const float* row = mf + cidx * kFrames;
-        // normalised values at t0-1 .. t0+2 (clamped = replicate padding of compute_deltas, :353-355);
-        // __fmul_rn is never contracted into an FMA, so every consumer of a value sees the same bits
-        float xn[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) xn[e] = __fmul_rn(row[min(max(t0 - 1 + e, 0), kFrames - 1)] - mean, inv_std);
-        float x0[2], dl[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int t = t0 + e;
-            x0[e] = t >= 0 ? xn[e + 1] : 0.f;
-            dl[e] = t >= 0 ? (xn[e + 2] - xn[e]) * 0.5f : 0.f;
-            if (out && t >= 0) {
-                out[(kMels + cidx) * kFrames + t] = x0[e];
-                out[(kMels + kMfcc + cidx) * kFrames + t] = dl[e];
+    {
+        for (int i = tid; i < kN; i += kFeatThreads) {
+            const int cidx = i / kFrames, t = i - cidx * kFrames;
+            const float* row = mf + cidx * kFrames;
+            // __fmul_rn: never contracted into an FMA, so the bf16 map below sees identical values
+            const float x0 = __fmul_rn(row[t] - mean, inv_std);
+            const float xp = __fmul_rn(row[min(t + 1, kFrames - 1)] - mean, inv_std);
+            const float xm = __fmul_rn(row[max(t - 1, 0)] - mean, inv_std);
+            const float dl = (xp - xm) * 0.5f;                             // compute_deltas (:353-355)
+            if (out) {
+                out[(kMels + cidx) * kFrames + t] = x0;
+                out[(kMels + kMfcc + cidx) * kFrames + t] = dl;
+            }
+            if (mo) {
+                mo[bmap_offset(kMels + cidx + 3, t + 3)] = __float2bfloat16_rn(x0);
+                mo[bmap_offset(kMels + kMfcc + cidx + 3, t + 3)] = __float2bfloat16_rn(dl);
             }
         }
-        if (mo) {
-            *reinterpret_cast<__nv_bfloat162*>(mo + bmap_offset(kMels + cidx + 3, t0 + 3)) = __floats2bfloat162_rn(x0[0], x0[1]);
-            *reinterpret_cast<__nv_bfloat162*>(mo + bmap_offset(kMels + kMfcc + cidx + 3, t0 + 3)) = __floats2bfloat162_rn(dl[0], dl[1]);
-        }
     }
+
 }
 
 struct ClipDesc {
