@@ -231,8 +231,9 @@ class Handle:
         """a[shift:shift+128] (K) x b (N, K)^T on one tcgen05 tile; CPU fp32 tensors in, CPU fp32 (128, N) out."""
         a = a.to("cpu", torch.float32).contiguous()
         b = b.to("cpu", torch.float32).contiguous()
-        assert a.shape[0] == 128 + shift
-        d = torch.empty(128, b.shape[0], dtype=torch.float32)
+        rows = 256 if mode == 3 else 128                    # mode 3: one cta_group::2 MMA stream over a CTA pair
+        assert a.shape[0] == rows + shift
+        d = torch.empty(rows, b.shape[0], dtype=torch.float32)
         self._check(self.lib.cd_selftest_umma(self._h, b.shape[0], a.shape[1], shift, mode, _ptr(a), _ptr(b), _ptr(d)),
                     "cd_selftest_umma")
         return d

@@ -84,6 +84,40 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: one MMA spans two SMs (M = 256: 128 rows from each CTA's shared memory,
+// each CTA supplies half of the N rows of B), issued by the even ("leader") CTA of a 2-CTA cluster.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive (when all MMAs issued so far have retired) on the barrier at this shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit2(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(s32(bar)), "h"((uint16_t)3) : "memory");
+}
+// plain arrive on the LEADER CTA's copy of a barrier (bit 24 of a shared::cluster address selects the odd CTA of a pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(s32(bar) & 0xFEFFFFFFu) : "memory");
+}
+
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane = tile row)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -198,6 +232,62 @@ umma_selftest_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* _
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tm, 256);
+}
+
+// CTA-pair self-test: D[256 x N] = A[256 x K] * B[N x K]^T with one cta_group::2 MMA stream; CTA r of the
+// cluster holds A rows [128 r, 128 r + 128) and B rows [N/2 r, N/2 r + N/2), and reads back its 128 rows of D.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
+umma_pair_selftest_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ Bm, float* __restrict__ D,
+                          int N, int K) {
+    extern __shared__ unsigned char raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    const int kc_n = K / 64, nh = N / 2;
+    unsigned char* sA = base;                             // [kc][128 rows][128 B]
+    unsigned char* sB = base + (size_t)kc_n * 16384;      // [kc][N/2 rows][128 B]
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t rank = tc::cluster_ctarank();
+    for (int i = tid; i < 128 * (K / 8); i += 128) {
+        const int row = i / (K / 8), ch = i % (K / 8), kc = ch >> 3, j = ch & 7;
+        *reinterpret_cast<uint4*>(sA + kc * 16384 + tc::swz128(row, j)) =
+            *reinterpret_cast<const uint4*>(A + (size_t)(rank * 128 + row) * K + ch * 8);
+    }
+    for (int i = tid; i < nh * (K / 8); i += 128) {
+        const int row = i / (K / 8), ch = i % (K / 8), kc = ch >> 3, j = ch & 7;
+        *reinterpret_cast<uint4*>(sB + (size_t)kc * nh * 128 + tc::swz128(row, j)) =
+            *reinterpret_cast<const uint4*>(Bm + (size_t)(rank * nh + row) * K + ch * 8);
+    }
+    tc::fence_proxy_async();
+    if (warp == 0) tc::tmem_alloc2(&tmem_base, 256);
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::cluster_sync();                                   // both CTAs' operands, barriers and TMEM are ready
+    tc::tc_fence_after();
+    const uint32_t tm = tmem_base;
+    if (rank == 0 && tid == 0) {
+        const uint32_t idesc = tc::idesc_bf16(256, N);
+        for (int kc = 0; kc < kc_n; ++kc)
+            for (int k4 = 0; k4 < 4; ++k4)
+                tc::umma2_bf16(tm, tc::desc_sw128(tc::s32(sA + kc * 16384) + k4 * 32),
+                               tc::desc_sw128(tc::s32(sB + (size_t)kc * nh * 128) + k4 * 32), idesc, (kc | k4) != 0);
+        tc::tc_commit2(&bar);
+    }
+    tc::mbar_wait(&bar, 0);
+    tc::tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        float v[32];
+        tc::tmem_ld32(tm + ((uint32_t)(warp * 32) << 16) + c0, v);
+        for (int i = 0; i < 32; ++i) D[(size_t)(rank * 128 + tid) * N + c0 + i] = v[i];
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::cluster_sync();
+    if (warp == 0) tc::tmem_dealloc2(tm, 256);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -841,6 +931,7 @@ int init_cnn_tc(cd_handle* h) {
                                     (int)S1Shape<128, 6, 7>::SMEM));
     CD_CUDA(h, cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStemSmem));
     CD_CUDA(h, cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CD_CUDA(h, cudaFuncSetAttribute(umma_pair_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return CD_OK;
 }
 
@@ -1013,6 +1104,30 @@ int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits,
 
 // D = A * B^T for 128 x K by N x K bf16-rounded inputs (host fp32 in/out); exercises descriptor encodings
 int umma_selftest(cd_handle* h, int N, int K, int shift, int mode, const float* hA, const float* hB, float* hD) {
+    if (mode == 3) {        // CTA pair: A is 256 x K, D is 256 x N
+        const size_t smem2 = (size_t)(128 + N / 2) * K * 2 + 2048;
+        if (N < 32 || N > 256 || N % 32 || K < 64 || K % 64 || shift != 0 || smem2 > 200 * 1024)
+            return set_err(h, CD_E_ARG, "umma_selftest(pair): need N in [32,256] step 32, K multiple of 64, shift 0");
+        std::vector<__nv_bfloat16> a((size_t)256 * K), b((size_t)N * K);
+        for (size_t i = 0; i < a.size(); ++i) a[i] = __float2bfloat16_rn(hA[i]);
+        for (size_t i = 0; i < b.size(); ++i) b[i] = __float2bfloat16_rn(hB[i]);
+        __nv_bfloat16 *dA = nullptr, *dB = nullptr;
+        float* dD = nullptr;
+        CD_CUDA(h, cudaMalloc(&dA, a.size() * 2));
+        CD_CUDA(h, cudaMalloc(&dB, b.size() * 2));
+        CD_CUDA(h, cudaMalloc(&dD, (size_t)256 * N * 4));
+        CD_CUDA(h, cudaMemcpy(dA, a.data(), a.size() * 2, cudaMemcpyHostToDevice));
+        CD_CUDA(h, cudaMemcpy(dB, b.data(), b.size() * 2, cudaMemcpyHostToDevice));
+        umma_pair_selftest_kernel<<<2, 128, smem2>>>(dA, dB, dD, N, K);
+        h->launches += 1;
+        CD_CUDA(h, cudaGetLastError());
+        CD_CUDA(h, cudaDeviceSynchronize());
+        CD_CUDA(h, cudaMemcpy(hD, dD, (size_t)256 * N * 4, cudaMemcpyDeviceToHost));
+        cudaFree(dA);
+        cudaFree(dB);
+        cudaFree(dD);
+        return CD_OK;
+    }
     const size_t smem = (size_t)(136 + shift + N) * K * 2 + 2048;
     if (N < 32 || N > 256 || N % 32 || K < 64 || K % 64 || shift < 0 || shift > 64 || smem > 200 * 1024)
         return set_err(h, CD_E_ARG, "umma_selftest: need N in [32,256] step 32, K multiple of 64, shift in [0,64], tiles within 200 KB");
