@@ -113,9 +113,25 @@ __device__ __forceinline__ void tc_commit2(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(s32(bar)), "h"((uint16_t)3) : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(s32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// wait on a barrier that threads of the OTHER CTA of the pair arrive on (cluster-scope acquire), bounded
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
 // plain arrive on the LEADER CTA's copy of a barrier (bit 24 of a shared::cluster address selects the odd CTA of a pair)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(s32(bar) & 0xFEFFFFFFu) : "memory");
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(s32(bar) & 0xFEFFFFFFu) : "memory");
 }
 
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane = tile row)
@@ -519,6 +535,179 @@ conv3x3_s1_tc_kernel(const S1Args a) {
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ----------------------------------------------------------------------------------------------
+// stride-1 convolution of block 1 (C = 128) on CTA PAIRS (cta_group::2)
+// ----------------------------------------------------------------------------------------------
+// The single-CTA kernel above keeps only one 64-channel half of the 288 KB of weights resident, so every tile
+// is staged and multiplied twice.  A 2-CTA cluster does it once: CTA r of the pair stages ITS OWN tile (128 rows)
+// and holds weight rows [64 r, 64 r + 64) of every chunk; one tcgen05.mma.cta_group::2 (M = 256, N = 128), issued
+// by the even CTA, multiplies both tiles by all 128 output channels, reading A from each CTA's shared memory and
+// half of B from each.  Per 128 x 128 x 16 MACs a CTA fetches 4 KB of A + 2 KB of B instead of 2 x (4 + 2) KB --
+// the tensor pipe here is bound by operand fetch from shared memory (about 64 B/clk/SM measured), not by math.
+//   leader (rank 0) warp 1: MMA issuer; waits its own slots AND the peer's (peer warp 1 relays its slot-full
+//   barriers with a remote arrive); tcgen05.commit multicasts "slot free" / "accumulator ready" to both CTAs;
+//   both epilogues hand accumulators back by arriving on the leader's barrier.
+template <int H, int W>
+struct S1PairShape {
+    using PS = PsLayout<H, W>;
+    static constexpr int NPLT = 3;                                // two conv planes + the skip-operand plane
+    static constexpr int A_BYTES = PS::ROWS_IN * 128;
+    static constexpr int NCHUNK = 19;                             // 9 taps x 2 planes + skip, 64 weight rows each
+    static constexpr int W_BYTES = NCHUNK * 8192;
+    static constexpr size_t SMEM = 1024 + (size_t)NPLT * A_BYTES + W_BYTES + 128 * 4 + 64;
+};
+
+template <int H, int W>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kS1Threads, 1)
+conv3x3_s1_pair_tc_kernel(const S1Args a) {
+    constexpr int C = 128;
+    using S = S1PairShape<H, W>;
+    using PS = PsLayout<H, W>;
+    constexpr int NPOS = H * W;
+    constexpr uint32_t IDESC = tc::idesc_bf16(256, 128);
+    constexpr int TMEM_COLS = 256;                                // 2 accumulators x 128 fp32 columns
+    constexpr int NB = S::NPLT;
+
+    extern __shared__ unsigned char raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* s_w = base + (size_t)NB * S::A_BYTES;
+    float* s_bias = reinterpret_cast<float*>(s_w + S::W_BYTES);
+    __shared__ uint64_t full_bar[NB], peer_full_bar[NB], empty_bar[NB], tfull_bar[2], tempty_bar[2], w_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int64_t rows = (int64_t)a.n * PS::RPC;
+    const int n_tiles = (int)((rows + 127) / 128);
+    const int n_tp = (n_tiles + 1) / 2;                           // tile pairs; CTA r takes tile 2 tp + r
+
+    if (tid == 0) {
+        for (int i = 0; i < NB; ++i) {
+            tc::mbar_init(&full_bar[i], 1);
+            tc::mbar_init(&peer_full_bar[i], 1);
+            tc::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&tfull_bar[i], 1);
+            tc::mbar_init(&tempty_bar[i], 256);                   // the epilogue threads of BOTH CTAs
+        }
+        tc::mbar_init(&w_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 128) s_bias[tid] = a.bias[tid];
+    if (warp == 1) tc::tmem_alloc2(&tmem_base_s, TMEM_COLS);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::cluster_sync();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ======================= producer (both CTAs): my weight half once, my tile's planes ==========
+        if (lane == 0) {
+            tc::mbar_arrive_expect_tx(&w_bar, S::W_BYTES);
+            for (int q = 0; q < 18; ++q)
+                tc::bulk_g2s(s_w + q * 8192, a.w + (size_t)q * C * 64 + (size_t)rank * 64 * 64, 8192, &w_bar);
+            tc::bulk_g2s(s_w + 18 * 8192, a.wskip + (size_t)rank * 64 * 64, 8192, &w_bar);
+            int it = 0;
+            for (int tp = pair; tp < n_tp; tp += n_pairs, ++it) {
+                const int64_t tile = 2 * (int64_t)tp + rank;
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    tc::mbar_wait(&empty_bar[q], (uint32_t)((it & 1) ^ 1));
+                    tc::mbar_arrive_expect_tx(&full_bar[q], S::A_BYTES);
+                    tc::bulk_g2s(base + (size_t)q * S::A_BYTES, a.x + q * a.ps_plane_elems + tile * 128 * 64, S::A_BYTES,
+                                 &full_bar[q]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            tc::mbar_wait(&w_bar, 0);
+            if (rank == 0) {
+                // ======================= MMA issuer (leader) ==============================================
+                const uint64_t dw = tc::desc_sw128(tc::s32(s_w));
+                int it = 0;
+                for (int tp = pair; tp < n_tp; tp += n_pairs, ++it) {
+                    const int acc = it & 1;
+                    tc::mbar_wait_cluster(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+                    const uint32_t d = tmem_base + acc * 128;
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) {
+                        tc::mbar_wait(&full_bar[q], (uint32_t)(it & 1));
+                        tc::mbar_wait_cluster(&peer_full_bar[q], (uint32_t)(it & 1));
+                        tc::tc_fence_after();
+                        const uint64_t da = tc::desc_sw128(tc::s32(base + (size_t)q * S::A_BYTES));
+                        if (q < 2) {
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint32_t shift = (uint32_t)((tap / 3) * PS::WP + (tap % 3)) * 128;
+#pragma unroll
+                                for (int k4 = 0; k4 < 4; ++k4)
+                                    tc::umma2_bf16(d, tc::desc_adv(da, shift + k4 * 32),
+                                                   tc::desc_adv(dw, (tap * 2 + q) * 8192 + k4 * 32), IDESC, (q | tap | k4) != 0);
+                            }
+                        } else {
+                            const uint32_t shift = (uint32_t)(PS::WP + 1) * 128;
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                tc::umma2_bf16(d, tc::desc_adv(da, shift + k4 * 32), tc::desc_adv(dw, 18 * 8192 + k4 * 32), IDESC, 1u);
+                        }
+                        tc::tc_commit2(&empty_bar[q]);           // slot q is free again in BOTH CTAs
+                    }
+                    tc::tc_commit2(&tfull_bar[acc]);
+                }
+            } else {
+                // ======================= relay (peer): tell the leader when my slots are full ============
+                int it = 0;
+                for (int tp = pair; tp < n_tp; tp += n_pairs, ++it) {
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) {
+                        tc::mbar_wait(&full_bar[q], (uint32_t)(it & 1));
+                        tc::mbar_arrive_leader(&peer_full_bar[q]);
+                    }
+                }
+            }
+        }
+    } else {
+        // ======================= epilogue (both CTAs): my 128 rows x all 128 channels ================
+        const int lane_grp = warp & 3;
+        int it = 0;
+        for (int tp = pair; tp < n_tp; tp += n_pairs, ++it) {
+            const int acc = it & 1;
+            const int64_t mp = (2 * (int64_t)tp + rank) * 128 + lane_grp * 32 + lane;
+            const int clip = (int)(mp / PS::RPC), rem = (int)(mp - (int64_t)clip * PS::RPC);
+            const int y = rem / PS::WP, x = rem - y * PS::WP;
+            const bool live = clip < a.n && y < H && x < W;
+            const int64_t m = (int64_t)clip * NPOS + y * W + x;
+            tc::mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * 128;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                float v[32];
+                tc::tmem_ld32(taddr + c0, v);
+                if (c0 == 96) {                                   // accumulator drained: hand it back to the leader
+                    tc::tc_fence_before();
+                    tc::mbar_arrive_leader(&tempty_bar[acc]);
+                }
+                if (live) {
+                    float4* op = reinterpret_cast<float4*>(a.y_f32 + m * C + c0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        op[q] = make_float4(fmaxf(v[4 * q] + s_bias[c0 + 4 * q], 0.f), fmaxf(v[4 * q + 1] + s_bias[c0 + 4 * q + 1], 0.f),
+                                            fmaxf(v[4 * q + 2] + s_bias[c0 + 4 * q + 2], 0.f), fmaxf(v[4 * q + 3] + s_bias[c0 + 4 * q + 3], 0.f));
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::cluster_sync();
+    if (warp == 1) tc::tmem_dealloc2(tmem_base, TMEM_COLS);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -927,8 +1116,8 @@ int init_cnn_tc(cd_handle* h) {
                                     (int)S2Shape<64, 128, 11, 13>::SMEM));
     CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s1_tc_kernel<64, 11, 13, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)S1Shape<64, 11, 13>::SMEM));
-    CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s1_tc_kernel<128, 6, 7, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)S1Shape<128, 6, 7>::SMEM));
+    CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s1_pair_tc_kernel<6, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)S1PairShape<6, 7>::SMEM));
     CD_CUDA(h, cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStemSmem));
     CD_CUDA(h, cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CD_CUDA(h, cudaFuncSetAttribute(umma_pair_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1002,7 +1191,7 @@ constexpr int64_t kTcChunk = 8192;
 using Ps0 = PsLayout<11, 13>;
 using Ps1 = PsLayout<6, 7>;
 constexpr int64_t kPs0Rows = ((kTcChunk * Ps0::RPC + 127) / 128) * 128 + Ps0::ROWS_IN;    // + the last tile's look-ahead
-constexpr int64_t kPs1Rows = ((kTcChunk * Ps1::RPC + 127) / 128) * 128 + Ps1::ROWS_IN;
+constexpr int64_t kPs1Rows = ((kTcChunk * Ps1::RPC + 127) / 128) * 128 + 128 + Ps1::ROWS_IN;   // + the pair kernel's odd tile
 constexpr int64_t al256(int64_t x) { return (x + 255) & ~int64_t(255); }
 constexpr int64_t kOffMap = 0;
 constexpr int64_t kOffX0 = kOffMap + al256((kTcChunk * kBmapRows + 128 + kStemRowsIn) * 32);   // + last tile's look-ahead
@@ -1086,13 +1275,12 @@ int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits,
             h->launches += 1;
         }
         {
-            using S = S1Shape<128, 6, 7>;
+            using S = S1PairShape<6, 7>;
             S1Args q{};
             q.x = h2; q.w = W.b1c2; q.wskip = W.b1sk; q.bias = W.b1c2_b; q.y_f32 = x2; q.ps_plane_elems = kPl1; q.n = n;
             const int tiles = (int)(((int64_t)n * Ps1::RPC + 127) / 128);
-            const int per_half = h->sm_count / S::HALVES;
-            const int grid = (tiles < per_half ? tiles : per_half) * S::HALVES;
-            conv3x3_s1_tc_kernel<128, 6, 7, true, false><<<grid, kS1Threads, S::SMEM, s>>>(q);
+            const int tp = (tiles + 1) / 2, max_pairs = h->sm_count / 2;
+            conv3x3_s1_pair_tc_kernel<6, 7><<<2 * (tp < max_pairs ? tp : max_pairs), kS1Threads, S::SMEM, s>>>(q);
             h->launches += 1;
         }
         head_kernel<<<n, 128, 0, s>>>(x2, W.fc_w, W.fc_b, d_logits + c0 * CD_N_CLASSES, n);
