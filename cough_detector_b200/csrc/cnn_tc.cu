@@ -908,102 +908,83 @@ constexpr int kStemStages = 4;
 constexpr int kStemBBytes = 3 * 16384;            // 128 weight rows x 3 chunks of 64 K-elements (144 used)
 constexpr size_t kStemSmem = 1024 + kStemStages * kStemABytes + kStemBBytes + 128;
 
-// Runs on CTA pairs (cta_group::2, see conv3x3_s1_pair_tc_kernel): CTA r stages its own tile and holds weight rows
-// [64 r, 64 r + 64) (pool members 2r, 2r+1); one M = 256, N = 128 MMA serves both tiles.
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kS1Threads, 1)
+__global__ void __launch_bounds__(kS1Threads, 1)
 stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __restrict__ wq,
                const float* __restrict__ bias, __nv_bfloat16* __restrict__ x0, int64_t x0_plane_elems,
                __nv_bfloat16* __restrict__ xs0, int B) {
     extern __shared__ unsigned char raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sA = base;                                   // [kStemStages][kStemABytes]
-    unsigned char* sB = base + kStemStages * kStemABytes;       // [3][64 rows x 128 B]: my half of the weight rows
-    float* s_bias = reinterpret_cast<float*>(sB + kStemBBytes / 2);
-    __shared__ uint64_t full_bar[kStemStages], peer_full_bar[kStemStages], empty_bar[kStemStages], tfull_bar[2], tempty_bar[2], w_bar;
+    unsigned char* sB = base + kStemStages * kStemABytes;       // [3][16384]
+    float* s_bias = reinterpret_cast<float*>(sB + kStemBBytes);
+    __shared__ uint64_t full_bar[kStemStages], empty_bar[kStemStages], tfull_bar[2], tempty_bar[2], w_bar;
     __shared__ uint32_t tmem_base_s;
-    constexpr uint32_t IDESC = tc::idesc_bf16(256, 128);
+    constexpr uint32_t IDESC = tc::idesc_bf16(128, 128);
     constexpr int TMEM_COLS = 256;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t rank = tc::cluster_ctarank();
-    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     const int64_t rows = (int64_t)B * kBmapRows;
     const int n_tiles = (int)((rows + 127) / 128);
-    const int n_tp = (n_tiles + 1) / 2;
     if (tid == 0) {
         for (int i = 0; i < kStemStages; ++i) {
             tc::mbar_init(&full_bar[i], 1);
-            tc::mbar_init(&peer_full_bar[i], 1);
             tc::mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&tfull_bar[i], 1);
-            tc::mbar_init(&tempty_bar[i], 256);
+            tc::mbar_init(&tempty_bar[i], 128);
         }
         tc::mbar_init(&w_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 32) s_bias[tid] = bias[tid];
-    if (warp == 1) tc::tmem_alloc2(&tmem_base_s, TMEM_COLS);
+    if (warp == 1) tc::tmem_alloc(&tmem_base_s, TMEM_COLS);
     tc::tc_fence_before();
     __syncthreads();
-    tc::cluster_sync();
     tc::tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp == 0) {
-        // ======================= producer: my weight half once, one bulk copy per tile ================
+        // ======================= producer: weights once, one bulk copy per tile =====================
         if (lane == 0) {
-            tc::mbar_arrive_expect_tx(&w_bar, kStemBBytes / 2);
-            for (int q = 0; q < 3; ++q)
-                tc::bulk_g2s(sB + q * 8192, wq + (size_t)q * 128 * 64 + (size_t)rank * 64 * 64, 8192, &w_bar);
+            tc::mbar_arrive_expect_tx(&w_bar, kStemBBytes);
+            tc::bulk_g2s(sB, wq, kStemBBytes, &w_bar);
             int it = 0;
-            for (int tp = pair; tp < n_tp; tp += n_pairs, ++it) {
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 const int s = it % kStemStages;
                 tc::mbar_wait(&empty_bar[s], (uint32_t)(((it / kStemStages) & 1) ^ 1));
                 tc::mbar_arrive_expect_tx(&full_bar[s], kStemRowsIn * 32);
-                tc::bulk_g2s(sA + s * kStemABytes, maps + (2 * (int64_t)tp + rank) * 128 * 16, kStemRowsIn * 32, &full_bar[s]);
+                tc::bulk_g2s(sA + s * kStemABytes, maps + (int64_t)tile * 128 * 16, kStemRowsIn * 32, &full_bar[s]);
             }
         }
     } else if (warp == 1) {
+        // ======================= MMA issuer: nine 4x4-block taps as shifted SWIZZLE_32B views =========
         if (lane == 0) {
             tc::mbar_wait(&w_bar, 0);
-            if (rank == 0) {
-                // ======================= MMA issuer: nine 4x4-block taps as shifted SWIZZLE_32B views ====
-                const uint64_t db = tc::desc_sw128(tc::s32(sB));
-                int it = 0;
-                for (int tp = pair; tp < n_tp; tp += n_pairs, ++it) {
-                    const int s = it % kStemStages, acc = it & 1;
-                    const uint32_t par = (uint32_t)((it / kStemStages) & 1);
-                    tc::mbar_wait_cluster(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
-                    tc::mbar_wait(&full_bar[s], par);
-                    tc::mbar_wait_cluster(&peer_full_bar[s], par);
-                    tc::tc_fence_after();
-                    const uint32_t d = tmem_base + acc * 128;
-                    const uint64_t da = tc::desc_sw32(tc::s32(sA + s * kStemABytes));
+            const uint64_t db = tc::desc_sw128(tc::s32(sB));
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int s = it % kStemStages, acc = it & 1;
+                tc::mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+                tc::mbar_wait(&full_bar[s], (uint32_t)((it / kStemStages) & 1));
+                tc::tc_fence_after();
+                const uint32_t d = tmem_base + acc * 128;
+                const uint64_t da = tc::desc_sw32(tc::s32(sA + s * kStemABytes));
 #pragma unroll
-                    for (int q = 0; q < 9; ++q)                  // block (i, j) = (q / 3, q % 3); K step q of the weights
-                        tc::umma2_bf16(d, tc::desc_adv(da, ((q / 3) * kBmapB + (q % 3)) * 32),
-                                       tc::desc_adv(db, (q >> 2) * 8192 + (q & 3) * 32), IDESC, q != 0);
-                    tc::tc_commit2(&empty_bar[s]);
-                    tc::tc_commit2(&tfull_bar[acc]);
-                }
-            } else {
-                int it = 0;                                      // relay: my stage is full -> tell the leader
-                for (int tp = pair; tp < n_tp; tp += n_pairs, ++it) {
-                    const int s = it % kStemStages;
-                    tc::mbar_wait(&full_bar[s], (uint32_t)((it / kStemStages) & 1));
-                    tc::mbar_arrive_leader(&peer_full_bar[s]);
-                }
+                for (int q = 0; q < 9; ++q)                      // block (i, j) = (q / 3, q % 3); K step q of the weights
+                    tc::umma_bf16(d, tc::desc_adv(da, ((q / 3) * kBmapB + (q % 3)) * 32),
+                                  tc::desc_adv(db, (q >> 2) * 16384 + (q & 3) * 32), IDESC, q != 0);
+                tc::tc_commit(&empty_bar[s]);
+                tc::tc_commit(&tfull_bar[acc]);
             }
         }
     } else {
         // ======================= epilogue: pool max over the 4 column groups, bias, ReLU, bf16 ========
         const int lane_grp = warp & 3;
         int it = 0;
-        for (int tp = pair; tp < n_tp; tp += n_pairs, ++it) {
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
-            const int64_t mp = (2 * (int64_t)tp + rank) * 128 + lane_grp * 32 + lane;
+            const int64_t mp = (int64_t)tile * 128 + lane_grp * 32 + lane;
             const int clip = (int)(mp / kBmapRows), rem = (int)(mp - (int64_t)clip * kBmapRows);
             const int py = rem / kBmapB, px = rem - py * kBmapB;
             const bool live = clip < B && py < 22 && px < 25;
@@ -1019,7 +1000,7 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
                 for (int i = 0; i < 32; ++i) m[i] = fmaxf(m[i], v[i]);
             }
             tc::tc_fence_before();
-            tc::mbar_arrive_leader(&tempty_bar[acc]);
+            tc::mbar_arrive(&tempty_bar[acc]);
             if (live) {
                 // x0 goes out phase-split (Ps2Layout<22, 25>): plane = (py+1) & 1, row = ((py+1)/2, (px+1)/2),
                 // the (px+1) parity picks the 64-byte half of the 128-byte row
@@ -1049,8 +1030,7 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
     }
     tc::tc_fence_before();
     __syncthreads();
-    tc::cluster_sync();
-    if (warp == 1) tc::tmem_dealloc2(tmem_base, TMEM_COLS);
+    if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // fp32 features (B, 90, 101) -> the stem's blocked bf16 map (for callers that hand features in): one thread
@@ -1214,7 +1194,7 @@ constexpr int64_t kPs0Rows = ((kTcChunk * Ps0::RPC + 127) / 128) * 128 + Ps0::RO
 constexpr int64_t kPs1Rows = ((kTcChunk * Ps1::RPC + 127) / 128) * 128 + 128 + Ps1::ROWS_IN;   // + the pair kernel's odd tile
 constexpr int64_t al256(int64_t x) { return (x + 255) & ~int64_t(255); }
 constexpr int64_t kOffMap = 0;
-constexpr int64_t kOffX0 = kOffMap + al256((kTcChunk * kBmapRows + 256 + kStemRowsIn) * 32);   // + odd tile + look-ahead
+constexpr int64_t kOffX0 = kOffMap + al256((kTcChunk * kBmapRows + 128 + kStemRowsIn) * 32);   // + last tile's look-ahead
 using P20 = Ps2Layout<22, 25>;
 using P21 = Ps2Layout<11, 13>;
 constexpr int64_t kP20Rows = ((kTcChunk * P20::RPC + 127) / 128) * 128 + P20::ROWS_IN;    // x0, 2 planes
@@ -1264,8 +1244,7 @@ int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits,
         }
         {
             const int tiles = (int)(((int64_t)n * kBmapRows + 127) / 128);
-            const int tp = (tiles + 1) / 2, max_pairs = h->sm_count / 2;
-            stem_tc_kernel<<<2 * (tp < max_pairs ? tp : max_pairs), kS1Threads, kStemSmem, s>>>(
+            stem_tc_kernel<<<tiles < h->sm_count ? tiles : h->sm_count, kS1Threads, kStemSmem, s>>>(
                 maps, W.stem_w, W.stem_b, x0, kP20Rows * 64, h1 + kPl0, n);
         }
         h->launches += 1;
