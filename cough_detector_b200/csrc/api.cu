@@ -308,7 +308,7 @@ static int e2e_impl(cd_handle* h, const float* d_audio, int64_t stride_or_hop, i
     // process in slabs so a slab's features stay L2-resident between the two stages.  bf16: the
     // feature kernel writes the stem's bf16 map straight into the CNN workspace (fp32 features only
     // if the caller asked for them); fp32: features go through an fp32 buffer.
-    const int64_t slab = 8192;
+    const int64_t slab = 16384;
     const bool tcp = precision == CD_PRECISION_BF16;
     const size_t cnn_ws = tcp ? cnn_tc_ws_bytes(slab) : cnn_fp32_ws_bytes(slab);
     const size_t feat_bytes = (tcp || d_feat_opt) ? 0 : (size_t)slab * kFeatElem * sizeof(float);

@@ -1187,7 +1187,7 @@ int upload_cnn_tc(cd_handle* h, const std::vector<std::vector<float>>& wf, const
 // Tensor-core workspace: fixed layout for kTcChunk clips, allocated and zeroed once per handle (the PS
 // buffers rely on their pad rows staying zero).
 // [maps | x0 | h1 PS: conv plane + skip plane | x1 | h2 PS: 2 conv planes + skip plane | x2]
-constexpr int64_t kTcChunk = 8192;
+constexpr int64_t kTcChunk = 16384;
 using Ps0 = PsLayout<11, 13>;
 using Ps1 = PsLayout<6, 7>;
 constexpr int64_t kPs0Rows = ((kTcChunk * Ps0::RPC + 127) / 128) * 128 + Ps0::ROWS_IN;    // + the last tile's look-ahead
