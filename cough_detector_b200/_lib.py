@@ -41,6 +41,7 @@ SYMBOLS = {
     "cd_version": (C.c_char_p, []),
     "cd_get_tables": (_I, [_VP, _VP, _VP]),
     "cd_feat_forward": (_I, [_VP, _VP, _I64, _I64, _VP, _I, _VP]),
+    "cd_feat_forward_i16": (_I, [_VP, _VP, _I64, _I64, _VP, _I, _VP]),
     "cd_feat_forward_var": (_I, [_VP, _VP, _VP, _VP, _I64, _VP, _VP]),
     "cd_feat_forward_stream": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
     "cd_stream_windows": (_I64, [_I64, _I64]),
@@ -52,6 +53,7 @@ SYMBOLS = {
     "cd_e2e_forward": (_I, [_VP, _VP, _I64, _I64, _VP, _VP, _I, _VP]),
     "cd_e2e_forward_stream": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _I, _VP]),
     "cd_e2e_forward_host": (_I, [_VP, _VP, _I64, _VP, _I]),
+    "cd_e2e_forward_host_i16": (_I, [_VP, _VP, _I64, _VP, _I]),
     "cd_selftest_umma": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP]),
     "cd_launch_count": (_I64, [_VP]),
 }
@@ -138,6 +140,17 @@ class Handle:
         B = audio.shape[0]
         out = torch.empty(B, 1, N_FEATURES, N_FRAMES, device=audio.device, dtype=torch.float32)
         self._check(self.lib.cd_feat_forward(self._h, _ptr(audio), SEGMENT, B, _ptr(out), 1 if normalize else 0, self._stream()), "cd_feat_forward")
+        return out
+
+    def feat_forward_i16(self, audio: torch.Tensor, normalize: bool = True) -> torch.Tensor:
+        """(B, 16000) cuda int16 PCM -> (B, 1, 90, 101); equals feat_forward(audio / 32768) bit for bit."""
+        if not (audio.is_cuda and audio.dtype == torch.int16 and audio.dim() == 2 and audio.shape[1] == SEGMENT):
+            raise CoughB200Error("feat_forward_i16 wants a cuda int16 (B, 16000) tensor")
+        audio = audio.contiguous()
+        B = audio.shape[0]
+        out = torch.empty(B, 1, N_FEATURES, N_FRAMES, device=audio.device, dtype=torch.float32)
+        self._check(self.lib.cd_feat_forward_i16(self._h, _ptr(audio), SEGMENT, B, _ptr(out), 1 if normalize else 0,
+                                                 self._stream()), "cd_feat_forward_i16")
         return out
 
     def feat_forward_var(self, flat: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:
@@ -261,13 +274,14 @@ class Handle:
 
     def e2e_forward_host(self, audio: torch.Tensor, precision: int = PRECISION_BF16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Host (B, 16000) fp32 tensor (ideally pinned) -> host (B, 2) logits; copies are inside the call."""
-        if audio.is_cuda or audio.dtype != torch.float32 or audio.dim() != 2 or audio.shape[1] != SEGMENT:
-            raise CoughB200Error("e2e_forward_host wants a CPU float32 (B, 16000) tensor")
+        if audio.is_cuda or audio.dtype not in (torch.float32, torch.int16) or audio.dim() != 2 or audio.shape[1] != SEGMENT:
+            raise CoughB200Error("e2e_forward_host wants a CPU float32 or int16 (B, 16000) tensor")
         audio = audio.contiguous()
         B = audio.shape[0]
         if out is None:
             out = torch.empty(B, 2, dtype=torch.float32).pin_memory()
-        self._check(self.lib.cd_e2e_forward_host(self._h, _ptr(audio), B, _ptr(out), precision), "cd_e2e_forward_host")
+        fn = self.lib.cd_e2e_forward_host_i16 if audio.dtype == torch.int16 else self.lib.cd_e2e_forward_host
+        self._check(fn(self._h, _ptr(audio), B, _ptr(out), precision), "cd_e2e_forward_host")
         return out
 
 

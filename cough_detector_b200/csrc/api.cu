@@ -43,6 +43,8 @@ int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits,
 size_t cnn_tc_ws_bytes(int64_t B);
 __nv_bfloat16* cnn_tc_map_ptr(cd_handle* h);
 int ensure_tc_ws(cd_handle* h);
+int launch_features_i16(cd_handle* h, const int16_t* d_audio, int64_t stride, int mode, int64_t B, float* d_feat,
+                        __nv_bfloat16* d_map, cudaStream_t s);
 int64_t resample_length(int64_t n_in, int orig_sr, int new_sr);
 int launch_resample(cd_handle* h, const float* d_in, int64_t rows, int64_t n_in, int orig_sr, int new_sr, float* d_out,
                     cudaStream_t s);
@@ -171,6 +173,16 @@ int cd_feat_forward(cd_handle* h, const float* d_audio, int64_t stride, int64_t 
     DeviceGuard g(h->device);
     const int mode = kModeFixed | ((flags & CD_FEAT_NORMALIZE) ? 0 : kModeNoNormalize);
     return launch_features(h, d_audio, nullptr, nullptr, stride, mode, B, d_feat, nullptr, (cudaStream_t)stream);
+}
+
+int cd_feat_forward_i16(cd_handle* h, const int16_t* d_audio, int64_t stride, int64_t B, float* d_feat, int flags,
+                        void* stream) {
+    if (!h) return CD_E_ARG;
+    if (B < 0 || stride < kSeg || (stride & 7) || (B > 0 && (!d_audio || !d_feat)))
+        return set_err(h, CD_E_ARG, "cd_feat_forward_i16: bad argument (need stride >= 16000 and a multiple of 8)");
+    DeviceGuard g(h->device);
+    const int mode = kModeFixed | ((flags & CD_FEAT_NORMALIZE) ? 0 : kModeNoNormalize);
+    return launch_features_i16(h, d_audio, stride, mode, B, d_feat, nullptr, (cudaStream_t)stream);
 }
 
 int cd_feat_forward_var(cd_handle* h, const float* d_audio, const int64_t* d_offsets, const int32_t* d_lengths,
@@ -354,7 +366,17 @@ int cd_e2e_forward_stream(cd_handle* h, const float* d_audio, int64_t n_samples,
 // Host buffers in, host logits out.  Three-deep pipeline: chunk i is copied host->pinned->device
 // on stream i%3 while chunk i-1 computes and chunk i-2's logits drain.  All three streams share
 // the handle's workspace, so compute of consecutive chunks is serialised with events; copies overlap.
+static int e2e_host_impl(cd_handle* h, const void* h_audio, bool i16, int64_t B, float* h_logits, int precision);
+
 int cd_e2e_forward_host(cd_handle* h, const float* h_audio, int64_t B, float* h_logits, int precision) {
+    return e2e_host_impl(h, h_audio, false, B, h_logits, precision);
+}
+
+int cd_e2e_forward_host_i16(cd_handle* h, const int16_t* h_audio, int64_t B, float* h_logits, int precision) {
+    return e2e_host_impl(h, h_audio, true, B, h_logits, precision);
+}
+
+static int e2e_host_impl(cd_handle* h, const void* h_audio, bool i16, int64_t B, float* h_logits, int precision) {
     if (!h) return CD_E_ARG;
     if (B < 0 || (B > 0 && (!h_audio || !h_logits))) return set_err(h, CD_E_ARG, "cd_e2e_forward_host: bad argument");
     if (!h->weights_loaded) return set_err(h, CD_E_STATE, "cd_e2e_forward_host: call cd_cnn_load first");
@@ -390,11 +412,14 @@ int cd_e2e_forward_host(cd_handle* h, const float* h_audio, int64_t B, float* h_
     for (int64_t b0 = 0; b0 < B; b0 += chunk, k = (k + 1) % 3) {
         const int64_t n = (B - b0) < chunk ? (B - b0) : chunk;
         cudaStream_t s = h->pipe_streams[k];
-        CD_CUDA(h, cudaMemcpyAsync(h->dev_in[k], h_audio + b0 * kSeg, (size_t)n * kSeg * sizeof(float),
+        const size_t esz = i16 ? sizeof(int16_t) : sizeof(float);
+        CD_CUDA(h, cudaMemcpyAsync(h->dev_in[k], static_cast<const char*>(h_audio) + (size_t)b0 * kSeg * esz, (size_t)n * kSeg * esz,
                                    cudaMemcpyHostToDevice, s));
         if (prev_compute) CD_CUDA(h, cudaStreamWaitEvent(s, prev_compute, 0));   // shared workspace
-        rc = launch_features(h, h->dev_in[k], nullptr, nullptr, kSeg, kModeFixed, n, feat,
-                             tcp ? cnn_tc_map_ptr(h) : nullptr, s);
+        rc = i16 ? launch_features_i16(h, reinterpret_cast<const int16_t*>(h->dev_in[k]), kSeg, kModeFixed, n, feat,
+                                       tcp ? cnn_tc_map_ptr(h) : nullptr, s)
+                 : launch_features(h, h->dev_in[k], nullptr, nullptr, kSeg, kModeFixed, n, feat,
+                                   tcp ? cnn_tc_map_ptr(h) : nullptr, s);
         if (rc != CD_OK) return rc;
         rc = tcp ? launch_cnn_tc(h, nullptr, n, h->dev_logits + b0 * CD_N_CLASSES, s)
                  : launch_cnn_fp32(h, feat, n, h->dev_logits + b0 * CD_N_CLASSES, s);

@@ -146,8 +146,10 @@ __device__ __forceinline__ float power_to_db(float x) {
 }
 
 // One windowed sample pair for FFT point n of the frame pair starting at sample `base0`.
-template <bool EDGE>
-__device__ __forceinline__ float2 load_point(const float* __restrict__ clip, float w, int n, int base0, bool second) {
+// T = float (the reference's waveform type) or int16_t (PCM as stored in wav files: x / 32768 is exact in fp32 and the
+// peak normalisation cancels the power-of-two scale, so both types give bit-identical features)
+template <bool EDGE, class T>
+__device__ __forceinline__ float2 load_point(const T* __restrict__ clip, float w, int n, int base0, bool second) {
     int i0 = base0 + n;
     int i1 = i0 + kHop;
     if (EDGE) {   // reflect padding of torch.stft(center=True, pad_mode="reflect")
@@ -155,17 +157,17 @@ __device__ __forceinline__ float2 load_point(const float* __restrict__ clip, flo
         i0 = i0 >= kSeg ? 2 * (kSeg - 1) - i0 : i0;
         i1 = i1 < 0 ? -i1 : i1;
         i1 = i1 >= kSeg ? 2 * (kSeg - 1) - i1 : i1;
-        return make_float2(w * clip[i0], second ? w * clip[i1] : 0.f);
+        return make_float2(w * (float)clip[i0], second ? w * (float)clip[i1] : 0.f);
     }
-    return make_float2(w * clip[i0], w * clip[i1]);
+    return make_float2(w * (float)clip[i0], w * (float)clip[i1]);
 }
 
 // The per-warp work item: frames 2p and 2p+1 -> 2 x 64 dB values in the tile.  Returns the lane's
 // running max of the dB values it produced.
 // RAW = false: dB values go to dst[band * band_stride + {0, frame_stride}] (the smem tile).
 // RAW = true : un-logged mel POWER goes there instead (shared STFT frames of the streaming path).
-template <bool EDGE, bool RAW, class SM>
-__device__ __forceinline__ float frame_pair(SM& S, const float* __restrict__ clip, float2* __restrict__ xb,
+template <bool EDGE, bool RAW, class SM, class T>
+__device__ __forceinline__ float frame_pair(SM& S, const T* __restrict__ clip, float2* __restrict__ xb,
                                             const float (&wA)[7], const float (&wB)[6],
                                             const float (&mw)[kMelSlots], int bin_lo, int bin_hi, int base0, bool second,
                                             int lane, float* __restrict__ dst, int band_stride, int frame_stride) {
@@ -175,10 +177,10 @@ __device__ __forceinline__ float frame_pair(SM& S, const float* __restrict__ cli
     float2 A[8], B[8];
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
-        A[a] = load_point<EDGE>(clip, wA[a], 64 * a + lane, base0, second);
-        B[a] = load_point<EDGE>(clip, wB[a], 64 * a + lane + 32, base0, second);
+        A[a] = load_point<EDGE, T>(clip, wA[a], 64 * a + lane, base0, second);
+        B[a] = load_point<EDGE, T>(clip, wB[a], 64 * a + lane + 32, base0, second);
     }
-    A[6] = lane < 16 ? load_point<EDGE>(clip, wA[6], 384 + lane, base0, second) : make_float2(0.f, 0.f);
+    A[6] = lane < 16 ? load_point<EDGE, T>(clip, wA[6], 384 + lane, base0, second) : make_float2(0.f, 0.f);
     A[7] = make_float2(0.f, 0.f);                   // n >= 400: zero padding of the 512-point frame
     B[6] = make_float2(0.f, 0.f);
     B[7] = make_float2(0.f, 0.f);
@@ -411,14 +413,16 @@ __device__ __forceinline__ void feat_tail(SM& S, float wmax, float* __restrict__
 
 }
 
+template <class T>
 struct ClipDesc {
-    const float* src;     // first sample of the clip
+    const T* src;         // first sample of the clip
     int len;              // samples available
 };
 
-__device__ __forceinline__ ClipDesc clip_desc(const float* audio, const int64_t* offs, const int32_t* lens,
+template <class T>
+__device__ __forceinline__ ClipDesc<T> clip_desc(const T* audio, const int64_t* offs, const int32_t* lens,
                                               int64_t stride_or_hop, int mode, int64_t b) {
-    ClipDesc d;
+    ClipDesc<T> d;
     if ((mode & kModeMask) == kModeVar) {
         d.src = audio + offs[b];
         d.len = lens[b];
@@ -428,12 +432,14 @@ __device__ __forceinline__ ClipDesc clip_desc(const float* audio, const int64_t*
     }
     return d;
 }
-__device__ __forceinline__ bool bulk_ok(const ClipDesc& d) {
+template <class T>
+__device__ __forceinline__ bool bulk_ok(const ClipDesc<T>& d) {
     return d.len == kSeg && ((reinterpret_cast<uintptr_t>(d.src) & 15) == 0);
 }
 
+template <class T>
 __global__ void __launch_bounds__(kFeatThreads, 2)
-feat_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offs, const int32_t* __restrict__ lens,
+feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const int32_t* __restrict__ lens,
             int64_t stride_or_hop, int mode, int64_t B, float* __restrict__ feat,
             __nv_bfloat16* __restrict__ map_out, const FeatTables* __restrict__ tables) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -464,23 +470,24 @@ feat_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offs, c
     __syncthreads();
 
     uint32_t phase = 0u;
-    float* clip = S.clip;
+    T* clip = reinterpret_cast<T*>(S.clip);
+    constexpr uint32_t kClipBytes = kSeg * sizeof(T);
     for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
-        const ClipDesc d = clip_desc(audio, offs, lens, stride_or_hop, mode, b);
+        const ClipDesc<T> d = clip_desc(audio, offs, lens, stride_or_hop, mode, b);
 
         // ---- one bulk copy (TMA engine) brings the clip in; the co-resident CTA computes meanwhile.
         //      The next clip is pulled into L2 now so that copy will be an L2 hit. -----------------------
         if (tid == 0) {
             if (bulk_ok(d)) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses -> async proxy
-                mbar_expect_tx(&S.bar, kSeg * 4);
-                bulk_g2s(clip, d.src, kSeg * 4, &S.bar);
+                mbar_expect_tx(&S.bar, kClipBytes);
+                bulk_g2s(clip, d.src, kClipBytes, &S.bar);
             }
             const int64_t bn = b + gridDim.x;
             if (bn < B) {
-                const ClipDesc dn = clip_desc(audio, offs, lens, stride_or_hop, mode, bn);
+                const ClipDesc<T> dn = clip_desc(audio, offs, lens, stride_or_hop, mode, bn);
                 if (bulk_ok(dn))
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(dn.src), "r"(kSeg * 4) : "memory");
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(dn.src), "r"(kClipBytes) : "memory");
             }
         }
 
@@ -489,20 +496,28 @@ feat_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offs, c
         if (bulk_ok(d)) {
             mbar_wait(&S.bar, phase);
             phase ^= 1u;
-            const float4* c4 = reinterpret_cast<const float4*>(clip);
-            for (int i = tid; i < kSeg / 4; i += kFeatThreads) {
-                const float4 v = c4[i];
-                peak = fmaxf(peak, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+            if (sizeof(T) == 4) {
+                const float4* c4 = reinterpret_cast<const float4*>(clip);
+                for (int i = tid; i < kSeg / 4; i += kFeatThreads) {
+                    const float4 v = c4[i];
+                    peak = fmaxf(peak, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+                }
+            } else {
+                const short4* c4 = reinterpret_cast<const short4*>(clip);
+                for (int i = tid; i < kSeg / 4; i += kFeatThreads) {
+                    const short4 v = c4[i];
+                    peak = fmaxf(peak, fmaxf(fmaxf(fabsf((float)v.x), fabsf((float)v.y)), fmaxf(fabsf((float)v.z), fabsf((float)v.w))));
+                }
             }
         } else {
             // AudioPreprocessor.process: normalise over the WHOLE clip, then centre-trim / zero-pad
             const int n = d.len;
-            for (int i = tid; i < n; i += kFeatThreads) peak = fmaxf(peak, fabsf(d.src[i]));
+            for (int i = tid; i < n; i += kFeatThreads) peak = fmaxf(peak, fabsf((float)d.src[i]));
             const int start = n > kSeg ? (n - kSeg) / 2 : 0;          // trim offset (src/preprocessing.py:378)
             const int padl = n < kSeg ? (kSeg - n) / 2 : 0;           // left zero pad (:383)
             for (int i = tid; i < kSeg; i += kFeatThreads) {
                 const int sidx = i - padl;
-                clip[i] = (sidx >= 0 && sidx < n) ? d.src[start + sidx] : 0.f;
+                clip[i] = (sidx >= 0 && sidx < n) ? d.src[start + sidx] : (T)0;
             }
         }
         peak = block_reduce<true>(peak, S.red);                        // its barriers also order the generic stores
@@ -701,7 +716,9 @@ int build_feat_tables(cd_handle* h) {
     for (int i = 0; i < kMfcc * kMels; ++i) dct[i] = bits2f(CD_DCT_BITS[i]);
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_dct, dct, sizeof(dct));
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeatSmem));
+        e = cudaFuncSetAttribute(feat_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeatSmem));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(feat_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeatSmem));
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(stream_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem));
     delete t;
@@ -741,8 +758,20 @@ int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets
         return CD_OK;
     }
     const int grid = (int)(B < slots ? B : slots);
-    feat_kernel<<<grid, kFeatThreads, sizeof(FeatSmem), s>>>(d_audio, d_offsets, d_lengths, stride_or_hop, mode, B,
+    feat_kernel<float><<<grid, kFeatThreads, sizeof(FeatSmem), s>>>(d_audio, d_offsets, d_lengths, stride_or_hop, mode, B,
                                                             d_feat, d_map, h->d_tables);
+    h->launches += 1;
+    CD_CUDA(h, cudaGetLastError());
+    return CD_OK;
+}
+
+// int16 PCM clips (fixed length): same kernel, 32 000-byte bulk copies
+int launch_features_i16(cd_handle* h, const int16_t* d_audio, int64_t stride, int mode, int64_t B, float* d_feat,
+                        __nv_bfloat16* d_map, cudaStream_t s) {
+    if (B == 0) return CD_OK;
+    const int64_t slots = 2 * (int64_t)h->sm_count;
+    feat_kernel<int16_t><<<(int)(B < slots ? B : slots), kFeatThreads, sizeof(FeatSmem), s>>>(
+        d_audio, nullptr, nullptr, stride, mode, B, d_feat, d_map, h->d_tables);
     h->launches += 1;
     CD_CUDA(h, cudaGetLastError());
     return CD_OK;

@@ -100,6 +100,13 @@ int cd_get_tables(float* hann, float* fb, float* dct);
 int cd_feat_forward(cd_handle* h, const float* d_audio, int64_t stride, int64_t B,
                     float* d_feat, int flags, void* stream);
 
+/* Same as cd_feat_forward for int16 PCM clips (the sample format of wav files; torchaudio.load divides by 32768,
+ * which is exact in fp32 and cancels in the peak normalisation, so with CD_FEAT_NORMALIZE the features are
+ * bit-identical to the fp32 path on x / 32768).  stride in samples, a multiple of 8.  Additive: the reference has
+ * no int16 entry point; it halves the bytes that have to reach the GPU. */
+int cd_feat_forward_i16(cd_handle* h, const int16_t* d_audio, int64_t stride, int64_t B,
+                        float* d_feat, int flags, void* stream);
+
 /* B clips of arbitrary length described by (offset, length) into one device buffer:
  * clip i = d_audio[d_offsets[i] .. d_offsets[i]+d_lengths[i]).  Per clip: normalize over the
  * WHOLE clip -> pad_or_trim to 16000 (centre trim / symmetric zero pad, :358-385) ->
@@ -165,6 +172,10 @@ int cd_e2e_forward_stream(cd_handle* h, const float* d_audio, int64_t n_samples,
  * bench's end-to-end number times. */
 int cd_e2e_forward_host(cd_handle* h, const float* h_audio, int64_t B, float* h_logits,
                         int precision);
+
+/* cd_e2e_forward_host for int16 PCM host buffers (B x 16000 int16): half the host->device bytes. */
+int cd_e2e_forward_host_i16(cd_handle* h, const int16_t* h_audio, int64_t B, float* h_logits,
+                            int precision);
 
 /* Diagnostic: D[i][n] = sum_k A[i + shift][k] * B[n][k] (i < 128) on one tcgen05 tile through the same
  * shared-memory / instruction descriptors the convolution kernels use (operands rounded to bf16, fp32

@@ -181,3 +181,21 @@ def test_resample_matches_reference_and_feeds_process():
         ref = ex.process(co.resample(w, sr))                   # resample -> mono -> normalize -> trim -> features
         assert feat.shape == (1, 90, 101)
         assert (feat - ref).abs().max().item() <= TOL, sr
+
+
+def test_int16_pcm_ingestion_is_bit_identical_to_float_path():
+    """int16 PCM in (device and host-pipeline entry points) == the fp32 path on x / 32768, bit for bit."""
+    from cough_detector_b200 import create_model
+    h = _lib.get_handle(0)
+    x = torch.stack(synth.synth_clips(300, seed=17, fixed_length=True))
+    pcm = (x / x.abs().amax(dim=1, keepdim=True).clamp(min=1e-9) * 30000.0).round().clamp(-32768, 32767).to(torch.int16)
+    pcm[7] = 0                                                   # silence
+    xf = pcm.float() / 32768.0
+    a = h.feat_forward_i16(pcm.cuda())
+    b = h.feat_forward(xf.cuda())
+    assert torch.equal(a, b)
+    torch.manual_seed(0)
+    m = create_model("residual").eval()
+    h.load_state_dict(synth.randomized_state_dict(m, seed=1), key="i16")
+    for prec in (0, 1):
+        assert torch.equal(h.e2e_forward_host(pcm.pin_memory(), prec), h.e2e_forward_host(xf.pin_memory(), prec))
