@@ -221,19 +221,25 @@ def run_gpu_arm(args):
         ms = float(t.item())
     value = world * B * args.steps / (ms * 1e-3)
 
-    # ---- per-stage timing for the roofline objects: the feature kernel alone, same inputs -----------
-    feat = torch.empty(B, 1, 90, 101, device=audio.device)
+    # ---- per-stage timing for the roofline objects ----------------------------------------------------
+    # feature kernel alone on BASELINE configs[1]: 65 536 resident clips (4.2 GB in, 2.4 GB out), fp32 features out
+    FB = args.feat_batch
+    faudio = synth.synth_batch(FB, seed=200 + rank, device=f"cuda:{local_rank}")
+    ffeat = torch.empty(FB, 1, 90, 101, device=audio.device)
     for _ in range(2):
-        h.lib.cd_feat_forward(h._h, audio.data_ptr(), 16000, B, feat.data_ptr(), 1, h._stream())
+        h.lib.cd_feat_forward(h._h, faudio.data_ptr(), 16000, FB, ffeat.data_ptr(), 1, h._stream())
     torch.cuda.synchronize()
     fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    nrep = max(3, args.steps)
+    nrep = max(3, min(args.steps, 10))
     fe0.record()
     for _ in range(nrep):
-        h.lib.cd_feat_forward(h._h, audio.data_ptr(), 16000, B, feat.data_ptr(), 1, h._stream())
+        h.lib.cd_feat_forward(h._h, faudio.data_ptr(), 16000, FB, ffeat.data_ptr(), 1, h._stream())
     fe1.record()
     torch.cuda.synchronize()
     feat_ms = fe0.elapsed_time(fe1) / nrep
+    del faudio, ffeat
+    feat = h.feat_forward(audio)
+    torch.cuda.synchronize()
     ce0, ce1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     h.cnn_forward(feat, prec)
     torch.cuda.synchronize()
@@ -264,6 +270,22 @@ def run_gpu_arm(args):
     e2e_value = world * B * args.steps / e2e_s
     same = bool(torch.equal(out, logits.cpu()))
 
+    # additive: the same call fed int16 PCM (the wav sample format) -- half the host->device bytes
+    pcm = (host / host.abs().amax(dim=1, keepdim=True).clamp(min=1e-9) * 30000.0).round().to(torch.int16).pin_memory()
+    out16 = torch.empty(B, 2).pin_memory()
+    h.e2e_forward_host(pcm, prec, out16)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        h.e2e_forward_host(pcm, prec, out16)
+    torch.cuda.synchronize()
+    i16_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([i16_s], device=audio.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        i16_s = float(t.item())
+    e2e_i16 = world * B * args.steps / i16_s
+
     if rank == 0:
         peaks = {}
         try:
@@ -273,7 +295,7 @@ def run_gpu_arm(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        feat_gbs = B * (AUDIO_BYTES + FEAT_BYTES) / (feat_ms * 1e-3) / 1e9
+        feat_gbs = FB * (AUDIO_BYTES + FEAT_BYTES) / (feat_ms * 1e-3) / 1e9
         cnn_tfs = B * CNN_FLOPS / (cnn_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
@@ -289,15 +311,17 @@ def run_gpu_arm(args):
                     "api": "cd_e2e_forward_host (pinned host audio in, host logits out)"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "feat_kernel", "bound": "hbm", "achieved": feat_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": feat_gbs / hbm_peak, "traffic": B * NCU_TRAFFIC_PER_CLIP, "peak_source": peak_src,
+                         "frac": feat_gbs / hbm_peak, "traffic": FB * NCU_TRAFFIC_PER_CLIP, "peak_source": peak_src,
                          "traffic_source": "ncu --set full (profiles/r1_ncu_feat_kernel_16384.csv): dram read+write "
-                                           "1.614 GB per 16 384-clip launch, scaled by the batch",
+                                           "98 530 B per clip (1.614 GB per 16 384-clip launch), scaled by the launch size",
                          "algorithmic_bytes_per_clip": AUDIO_BYTES + FEAT_BYTES, "launch_ms": feat_ms,
-                         "clips_per_s": B / (feat_ms * 1e-3),
-                         "note": "timed alone over the same resident batch right after the e2e region"},
+                         "clips_per_s": FB / (feat_ms * 1e-3), "clips_per_launch": FB,
+                         "note": "BASELINE configs[1]: timed alone over 65 536 resident clips right after the e2e region"},
             "roofline_cnn": {"kernel": "cnn (stem + 2 residual blocks + head)", "bound": "tensor", "achieved": cnn_tfs,
                              "peak": tc_peak, "unit": "TFLOP/s", "frac": cnn_tfs / tc_peak, "launch_ms": cnn_ms,
                              "algorithmic_flops_per_clip": CNN_FLOPS, "clips_per_s": B / (cnn_ms * 1e-3)},
+            "e2e_int16": {"value": e2e_i16, "unit": "clips/s", "h2d_bytes_per_step": B * 32000, "d2h_bytes_per_step": B * 8,
+                          "api": "cd_e2e_forward_host_i16 (pinned int16 PCM in; additive entry point, not in the reference)"},
             "cpu_baseline": cpu,
             "wall_s": w1 - w0,
         }
@@ -313,6 +337,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--feat-batch", type=int, default=65536)
     ap.add_argument("--precision", default=None, choices=[None, "fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
