@@ -269,6 +269,18 @@ def run_gpu_arm(args):
         e2e_s = float(t.item())
     e2e_value = world * B * args.steps / e2e_s
     same = bool(torch.equal(out, logits.cpu()))
+    # what the link itself does: a bare pinned host->device copy of the same buffer (the e2e path's floor)
+    dev_copy = torch.empty_like(audio)
+    dev_copy.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for _ in range(3):
+        dev_copy.copy_(host, non_blocking=True)
+    pe1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 3 * B * AUDIO_BYTES / (pe0.elapsed_time(pe1) * 1e-3) / 1e9
+    del dev_copy
 
     # additive: the same call fed int16 PCM (the wav sample format) -- half the host->device bytes
     pcm = (host / host.abs().amax(dim=1, keepdim=True).clamp(min=1e-9) * 30000.0).round().to(torch.int16).pin_memory()
@@ -308,6 +320,7 @@ def run_gpu_arm(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": B * AUDIO_BYTES,
                     "d2h_bytes_per_step": B * 8, "bit_identical_to_device_path": same,
+                    "h2d_gbs": e2e_value / world * AUDIO_BYTES / 1e9, "h2d_gbs_bare_copy": h2d_gbs,
                     "api": "cd_e2e_forward_host (pinned host audio in, host logits out)"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "feat_kernel", "bound": "hbm", "achieved": feat_gbs, "peak": hbm_peak, "unit": "GB/s",

@@ -35,17 +35,21 @@ __host__ __device__ inline int bmap_offset(int R, int C) {
     return row * 16 + ((((r >> 1) ^ ((row >> 2) & 1)) << 3) | ((r & 1) * 4 + c));   // 16-byte chunk ^= row bit 2
 }
 
-// mel contraction as executed by a lane: slots 0..2 = band `lane` (<= 3 taps for bands 0..31),
-// slots 3..10 = band `lane+32` (<= 8 taps).  idx is the bin index minus 4 (0..123).
-constexpr int kMelSlotsLo = 3;
-constexpr int kMelSlotsHi = 8;
+// mel contraction as executed by a lane.  Every FFT bin feeds at most two adjacent triangular bands (m, m + 1); the
+// bins are cut into 64 segments, segment m = the bins whose LOWER band is m (the falling side of band m = the rising
+// side of band m + 1; <= 2 bins for m < 32, <= 4 above), and lane l owns segments l and l + 32.  It reads each of its
+// bins once and forms own = sum W[m][k] P[k] and up = sum W[m+1][k] P[k]; band m = own(m) + up(m - 1), the second term
+// arriving by one shuffle from the lane below -- 124 bin reads per frame instead of the filterbank's 244 taps.
+constexpr int kMelSlotsLo = 2;
+constexpr int kMelSlotsHi = 4;
 constexpr int kMelSlots   = kMelSlotsLo + kMelSlotsHi;
 
 struct FeatTables {                 // lives in device global memory, copied to smem per CTA
     float2 tw1[7][64];              // W512^(m*r), r = 1..7, m = 0..63   (stage-1 twiddles)
     float2 tw2[7][8];               // W64^(c*u),  u = 1..7, c = 0..7    (stage-2 twiddles)
     float  win[kWin];               // 0.5 * hann (the 0.5 makes |Z +- conj Z'|^2 the power directly)
-    float2 melt[kMelSlots][32];     // {weight, __int_as_float(bin - 4)}
+    float2 melt[kMelSlots][32];     // {W[m][k], W[m+1][k]} of the lane's s-th bin (slots 0-1: segment l, 2-5: segment l+32)
+    int    melb[2][32];             // first bin of the lane's lo / hi segment | (bins in it) << 8
 };
 
 // Folded network, fp32 (CUDA-core path).  Layouts chosen for the direct-conv kernels:

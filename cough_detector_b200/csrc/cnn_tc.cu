@@ -981,6 +981,9 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
     } else {
         // ======================= epilogue: pool max over the 4 column groups, bias, ReLU, bf16 ========
         const int lane_grp = warp & 3;
+        float bq[32];                                           // folded bias, resident in registers
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bq[i] = __ldg(bias + i);
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -1019,7 +1022,7 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int c = 8 * q + 2 * e;
-                        __nv_bfloat162 pk = __floats2bfloat162_rn(fmaxf(m[c] + s_bias[c], 0.f), fmaxf(m[c + 1] + s_bias[c + 1], 0.f));
+                        __nv_bfloat162 pk = __floats2bfloat162_rn(fmaxf(m[c] + bq[c], 0.f), fmaxf(m[c + 1] + bq[c + 1], 0.f));
                         w[e] = *reinterpret_cast<uint32_t*>(&pk);
                     }
                     *reinterpret_cast<uint4*>(op + (((jb + q) ^ (int)(r2 & 7)) << 3)) = make_uint4(w[0], w[1], w[2], w[3]);

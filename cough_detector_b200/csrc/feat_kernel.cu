@@ -169,7 +169,7 @@ __device__ __forceinline__ float2 load_point(const T* __restrict__ clip, float w
 template <bool EDGE, bool RAW, class SM, class T>
 __device__ __forceinline__ float frame_pair(SM& S, const T* __restrict__ clip, float2* __restrict__ xb,
                                             const float (&wA)[7], const float (&wB)[6],
-                                            const float (&mw)[kMelSlots], int bin_lo, int bin_hi, int base0, bool second,
+                                            const float2 (&mw)[kMelSlots], int bin_lo, int bin_hi, int base0, bool second,
                                             int lane, float* __restrict__ dst, int band_stride, int frame_stride) {
     const int c = lane & 7, j = lane >> 3;             // base0: sample index of window tap 0 of the first frame
 
@@ -282,21 +282,43 @@ __device__ __forceinline__ float frame_pair(SM& S, const T* __restrict__ clip, f
     }
     __syncwarp();
 
-    // ---- banded mel contraction: lane owns bands `lane` and `lane + 32` for both frames --------
-    float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+    // ---- banded mel contraction (cd_common.cuh): the lane reads the bins of its two segments once, for both
+    //      frames, and hands the rising-side sums to the lane above ----------------------------------------
+    float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f), ulo = lo, uhi = lo;
+    {
+        const int b0 = bin_lo & 0xff, n0 = bin_lo >> 8;
 #pragma unroll
-    for (int s = 0; s < kMelSlotsLo; ++s) {
-        const int bin = min(bin_lo + s, 127);            // taps past the band carry zero weight
-        const float2 pw = xb[bin + 2 * (bin >> 4)];
-        lo.x = fmaf(mw[s], pw.x, lo.x);
-        lo.y = fmaf(mw[s], pw.y, lo.y);
-    }
+        for (int s = 0; s < kMelSlotsLo; ++s)
+            if (s < n0) {
+                const int bin = b0 + s;
+                const float2 pw = xb[bin + 2 * (bin >> 4)];
+                lo.x = fmaf(mw[s].x, pw.x, lo.x);
+                lo.y = fmaf(mw[s].x, pw.y, lo.y);
+                ulo.x = fmaf(mw[s].y, pw.x, ulo.x);
+                ulo.y = fmaf(mw[s].y, pw.y, ulo.y);
+            }
+        const int b1 = bin_hi & 0xff, n1 = bin_hi >> 8;
 #pragma unroll
-    for (int s = 0; s < kMelSlotsHi; ++s) {
-        const int bin = min(bin_hi + s, 127);
-        const float2 pw = xb[bin + 2 * (bin >> 4)];
-        hi.x = fmaf(mw[kMelSlotsLo + s], pw.x, hi.x);
-        hi.y = fmaf(mw[kMelSlotsLo + s], pw.y, hi.y);
+        for (int s = 0; s < kMelSlotsHi; ++s)
+            if (s < n1) {
+                const int bin = b1 + s;
+                const float2 pw = xb[bin + 2 * (bin >> 4)];
+                hi.x = fmaf(mw[kMelSlotsLo + s].x, pw.x, hi.x);
+                hi.y = fmaf(mw[kMelSlotsLo + s].x, pw.y, hi.y);
+                uhi.x = fmaf(mw[kMelSlotsLo + s].y, pw.x, uhi.x);
+                uhi.y = fmaf(mw[kMelSlotsLo + s].y, pw.y, uhi.y);
+            }
+        // band m += up(m - 1): lanes 1..31 take both sums from lane - 1; lane 0's band 32 takes up(31) from lane 31's
+        // lo segment (its band 0 has nothing below it, and up(63) is identically zero)
+        const int below = (lane + 31) & 31;
+        const float ax = __shfl_sync(0xffffffffu, ulo.x, below), ay = __shfl_sync(0xffffffffu, ulo.y, below);
+        const float bx = __shfl_sync(0xffffffffu, uhi.x, below), by = __shfl_sync(0xffffffffu, uhi.y, below);
+        if (lane) {
+            lo.x += ax; lo.y += ay;
+            hi.x += bx; hi.y += by;
+        } else {
+            hi.x += ax; hi.y += ay;
+        }
     }
     __syncwarp();                                    // xb is rewritten by the next pair
 
@@ -354,8 +376,8 @@ __device__ __forceinline__ float mfcc_par(const float* __restrict__ db, float* _
 // normalisation, deltas; fp32 features to `out` and/or the stem's bf16 map to `mo` (either may be null).
 // Ends with the block in sync except for the final stores.
 template <class SM>
-__device__ __forceinline__ void feat_tail(SM& S, float wmax, float* __restrict__ out, __nv_bfloat16* __restrict__ mo, int tid) {
-    const float top = block_reduce<true>(wmax, S.red);             // barrier: dB tile complete, clip buffer dead
+__device__ __forceinline__ void feat_tail(SM& S, float top, float* __restrict__ out, __nv_bfloat16* __restrict__ mo, int tid) {
+    // `top` = block max of the dB tile (the caller's block_reduce is the barrier that completes the tile)
     const float floor_db = top - 80.0f;                            // top_db = 80
 
     // ---- mel block rows 0..63: max(dB, floor) -> (dB + 80) / 80 -> clamp ------------------------
@@ -454,15 +476,10 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
         static_assert(offsetof(FeatTables, tw2) == sizeof(S.tw1) && offsetof(FeatSmem, tw2) - offsetof(FeatSmem, tw1) == sizeof(S.tw1), "layout");
         for (int i = tid; i < n; i += kFeatThreads) dst[i] = src[i];
     }
-    float mw[kMelSlots];
-    int bin_lo, bin_hi;
-    {
+    float2 mw[kMelSlots];
 #pragma unroll
-        for (int s = 0; s < kMelSlots; ++s) mw[s] = tables->melt[s][lane].x;
-        const int p0 = __float_as_int(tables->melt[0][lane].y), p3 = __float_as_int(tables->melt[kMelSlotsLo][lane].y);
-        bin_lo = p0;
-        bin_hi = p3;
-    }
+    for (int s = 0; s < kMelSlots; ++s) mw[s] = tables->melt[s][lane];
+    const int bin_lo = tables->melb[0][lane], bin_hi = tables->melb[1][lane];
     if (tid == 0) {
         mbar_init(&S.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -472,24 +489,27 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
     uint32_t phase = 0u;
     T* clip = reinterpret_cast<T*>(S.clip);
     constexpr uint32_t kClipBytes = kSeg * sizeof(T);
-    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
-        const ClipDesc<T> d = clip_desc(audio, offs, lens, stride_or_hop, mode, b);
-
-        // ---- one bulk copy (TMA engine) brings the clip in; the co-resident CTA computes meanwhile.
-        //      The next clip is pulled into L2 now so that copy will be an L2 hit. -----------------------
-        if (tid == 0) {
-            if (bulk_ok(d)) {
+    // One bulk copy (TMA engine) brings a clip in.  It is issued as soon as the previous clip's samples are dead
+    // (after its last FFT), so it lands under that clip's tail; the clip after that is pulled into L2 meanwhile.
+    auto fetch = [&](int64_t bf) {                                  // thread 0 only
+        if (bf < B) {
+            const ClipDesc<T> df = clip_desc(audio, offs, lens, stride_or_hop, mode, bf);
+            if (bulk_ok(df)) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses -> async proxy
                 mbar_expect_tx(&S.bar, kClipBytes);
-                bulk_g2s(clip, d.src, kClipBytes, &S.bar);
-            }
-            const int64_t bn = b + gridDim.x;
-            if (bn < B) {
-                const ClipDesc<T> dn = clip_desc(audio, offs, lens, stride_or_hop, mode, bn);
-                if (bulk_ok(dn))
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(dn.src), "r"(kClipBytes) : "memory");
+                bulk_g2s(clip, df.src, kClipBytes, &S.bar);
             }
         }
+        const int64_t bn = bf + gridDim.x;
+        if (bn < B) {
+            const ClipDesc<T> dn = clip_desc(audio, offs, lens, stride_or_hop, mode, bn);
+            if (bulk_ok(dn))
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(dn.src), "r"(kClipBytes) : "memory");
+        }
+    };
+    if (tid == 0) fetch(blockIdx.x);
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        const ClipDesc<T> d = clip_desc(audio, offs, lens, stride_or_hop, mode, b);
 
         // ---- stage the clip + peak ------------------------------------------------------------------
         float peak = 0.f;
@@ -542,9 +562,11 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
             wmax = fmaxf(wmax, edge ? frame_pair<true, false>(S, clip, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, base0, second, lane, dst, kFrames, 1)
                                     : frame_pair<false, false>(S, clip, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, base0, second, lane, dst, kFrames, 1));
         }
-        feat_tail(S, wmax, feat ? feat + b * (int64_t)kFeatElem : nullptr,
+        const float top = block_reduce<true>(wmax, S.red);             // barrier: dB tile complete, clip buffer dead
+        if (tid == 0) fetch(b + gridDim.x);
+        feat_tail(S, top, feat ? feat + b * (int64_t)kFeatElem : nullptr,
                   map_out ? map_out + b * (int64_t)kMapElems : nullptr, tid);
-        __syncthreads();                                               // xb / db / clip[cur] free again
+        __syncthreads();                                               // xb / db free again
     }
 }
 
@@ -570,17 +592,16 @@ struct StreamSmem {
 };
 
 template <class SM>
-__device__ __forceinline__ void load_lane_tables(SM& S, const FeatTables* __restrict__ tables, float (&mw)[kMelSlots],
+__device__ __forceinline__ void load_lane_tables(SM& S, const FeatTables* __restrict__ tables, float2 (&mw)[kMelSlots],
                                                  int& bin_lo, int& bin_hi, int tid, int lane) {
     const float* src = reinterpret_cast<const float*>(tables);
     float* dst = reinterpret_cast<float*>(&S.tw1[0][0]);
     constexpr int n = (sizeof(S.tw1) + sizeof(S.tw2)) / 4;
     for (int i = tid; i < n; i += kFeatThreads) dst[i] = src[i];
 #pragma unroll
-    for (int s = 0; s < kMelSlots; ++s) mw[s] = tables->melt[s][lane].x;
-    const int p0 = __float_as_int(tables->melt[0][lane].y), p3 = __float_as_int(tables->melt[kMelSlotsLo][lane].y);
-    bin_lo = p0;
-    bin_hi = p3;
+    for (int s = 0; s < kMelSlots; ++s) mw[s] = tables->melt[s][lane];
+    bin_lo = tables->melb[0][lane];
+    bin_hi = tables->melb[1][lane];
 }
 
 __device__ __forceinline__ void lane_window(const FeatTables* __restrict__ tables, float inv, int lane, float (&wA)[7], float (&wB)[6]) {
@@ -610,7 +631,8 @@ stream_mel_kernel(const float* __restrict__ audio, int64_t F, float* __restrict_
     extern __shared__ __align__(128) unsigned char smem_raw[];
     MelSmem& S = *reinterpret_cast<MelSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float mw[kMelSlots], wA[7], wB[6];
+    float2 mw[kMelSlots];
+    float wA[7], wB[6];
     int bin_lo, bin_hi;
     load_lane_tables(S, tables, mw, bin_lo, bin_hi, tid, lane);
     lane_window(tables, 1.0f, lane, wA, wB);
@@ -631,7 +653,7 @@ stream_window_kernel(const float* __restrict__ audio, int64_t hop, int64_t n_win
     extern __shared__ __align__(128) unsigned char smem_raw[];
     StreamSmem& S = *reinterpret_cast<StreamSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float mw[kMelSlots];
+    float2 mw[kMelSlots];
     int bin_lo, bin_hi;
     load_lane_tables(S, tables, mw, bin_lo, bin_hi, tid, lane);
     __syncthreads();
@@ -659,7 +681,7 @@ stream_window_kernel(const float* __restrict__ audio, int64_t hop, int64_t n_win
                 wmax = fmaxf(wmax, d);
             }
         }
-        feat_tail(S, wmax, feat ? feat + j * (int64_t)kFeatElem : nullptr,
+        feat_tail(S, block_reduce<true>(wmax, S.red), feat ? feat + j * (int64_t)kFeatElem : nullptr,
                   map_out ? map_out + j * (int64_t)kMapElems : nullptr, tid);
         __syncthreads();
     }
@@ -688,27 +710,33 @@ int build_feat_tables(cd_handle* h) {
             t->tw2[u - 1][c] = make_float2((float)cos(a), (float)sin(a));
         }
     for (int n = 0; n < kWin; ++n) t->win[n] = 0.5f * bits2f(CD_HANN_BITS[n]);   // exact (power of two)
-    for (int lane = 0; lane < 32; ++lane) {
-        for (int s = 0; s < kMelSlots; ++s) {
-            const int band = s < kMelSlotsLo ? lane : lane + 32;
-            const int tap = s < kMelSlotsLo ? s : s - kMelSlotsLo;
-            float w = 0.f;
-            int idx = 0;
-            if (tap < CD_MEL_COUNT[band]) {
-                w = bits2f(CD_MEL_W_BITS[band * CD_MEL_MAX_TAPS + tap]);
-                const int bin = CD_MEL_START[band] + tap;
-                idx = bin;                                 // plain FFT bin; frame_pair pads the index
-            } else {
-                idx = 4;                                   // zero weight: any initialised entry
+    {
+        // bin -> the (at most two, adjacent) bands it feeds; segment m = bins whose lower band is m
+        float w_of[64][129];
+        int lower[129];
+        memset(w_of, 0, sizeof(w_of));
+        for (int k = 0; k < 129; ++k) lower[k] = -1;
+        for (int m = 0; m < 64; ++m)
+            for (int tp = 0; tp < CD_MEL_COUNT[m]; ++tp) {
+                const int k = CD_MEL_START[m] + tp;
+                w_of[m][k] = bits2f(CD_MEL_W_BITS[m * CD_MEL_MAX_TAPS + tp]);
+                if (lower[k] < 0) lower[k] = m;
+                else if (m != lower[k] + 1) { delete t; return set_err(h, CD_E_STATE, "mel bands are not adjacent triangles"); }
             }
-            float fi;
-            memcpy(&fi, &idx, 4);
-            t->melt[s][lane] = make_float2(w, fi);
-        }
-        if (CD_MEL_COUNT[lane] > kMelSlotsLo || CD_MEL_COUNT[lane + 32] > kMelSlotsHi) {
-            delete t;
-            return set_err(h, CD_E_STATE, "mel table does not fit the slot layout");
-        }
+        for (int lane = 0; lane < 32; ++lane)
+            for (int half = 0; half < 2; ++half) {
+                const int m = lane + 32 * half, slots = half ? kMelSlotsHi : kMelSlotsLo, s0 = half ? kMelSlotsLo : 0;
+                int first = -1, n = 0;
+                for (int k = 0; k < 129; ++k)
+                    if (lower[k] == m) {
+                        if (first < 0) first = k;
+                        if (k != first + n || n >= slots || k > 127) { delete t; return set_err(h, CD_E_STATE, "mel table does not fit the slot layout"); }
+                        t->melt[s0 + n][lane] = make_float2(w_of[m][k], m < 63 ? w_of[m + 1][k] : 0.f);
+                        ++n;
+                    }
+                for (int s = n; s < slots; ++s) t->melt[s0 + s][lane] = make_float2(0.f, 0.f);
+                t->melb[half][lane] = (first < 0 ? 4 : first) | (n << 8);
+            }
     }
     cudaError_t e = cudaMalloc(&h->d_tables, sizeof(FeatTables));
     if (e == cudaSuccess) e = cudaMemcpy(h->d_tables, t, sizeof(FeatTables), cudaMemcpyHostToDevice);
