@@ -35,10 +35,12 @@ struct FeatSmem {
     float  db[kMels * kFrames];               //  25 856 B, dB tile [band][frame]
     float2 tw1[7][64];                        //   3 584 B
     float2 tw2[7][8];                         //     448 B
+    float2 zero2;                             // what the mel contraction reads for a lane's unused bin slots
     float  red[64];
     unsigned long long bar;
-};                                            // 112 640 B -> two CTAs per SM
+};                                            // 112 592 B -> two CTAs per SM
 static_assert(sizeof(FeatSmem) <= 113 * 1024, "two CTAs per SM");
+static_assert(offsetof(FeatSmem, xb) % 128 == 0 && offsetof(FeatSmem, zero2) % 128 == 64, "zero2 sits in bank pair 8 of xb's numbering");
 
 // ----------------------------------------------------------------------------------------------
 // small PTX wrappers
@@ -61,26 +63,61 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    return v;
+}
 // 1-D bulk async copy global -> shared (TMA engine), completion signalled on an mbarrier.
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// complex add / sub as ONE packed instruction (add.f32x2 / sub.f32x2 -> FADD2 on sm_100): the butterflies are
-// 3/4 of the FFT's floating-point instructions, so this takes ~1/3 off the kernel's issue slots
+// Packed fp32 pairs (add/sub/mul/fma.f32x2 -> FADD2 / FMUL2 / FFMA2 on sm_100): a complex value is one 64-bit register
+// pair, so a complex add is ONE instruction and a complex multiply TWO (ptxas folds the half swaps, the per-half
+// negation and the scalar broadcasts into operand modifiers).  Butterflies, twiddles, the window and the power
+// spectrum are ~2/3 of the kernel's instructions, which is issue-bound -- this halves them.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 up(u64 v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) {
-    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
-    asm("add.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
-    return *reinterpret_cast<float2*>(&rd);
+    u64 rd;
+    asm("add.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(pk(a.x, a.y)), "l"(pk(b.x, b.y)));
+    return up(rd);
 }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) {
-    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
-    asm("sub.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
-    return *reinterpret_cast<float2*>(&rd);
+    u64 rd;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(pk(a.x, a.y)), "l"(pk(b.x, b.y)));
+    return up(rd);
 }
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+// s * a
+__device__ __forceinline__ float2 scale2(float s, float2 a) {
+    u64 rd;
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(pk(s, s)), "l"(pk(a.x, a.y)));
+    return up(rd);
+}
+// s * a + c
+__device__ __forceinline__ float2 fma2s(float s, float2 a, float2 c) {
+    u64 rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(pk(s, s)), "l"(pk(a.x, a.y)), "l"(pk(c.x, c.y)));
+    return up(rd);
+}
+// a * t = t.x (a.x, a.y) + t.y (-a.y, a.x)
+__device__ __forceinline__ float2 cmul(float2 a, float2 t) {
+    u64 m, rd;
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(m) : "l"(pk(t.y, t.y)), "l"(pk(a.y, a.x)));
+    const float2 mm = up(m);
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(pk(t.x, t.x)), "l"(pk(a.x, a.y)), "l"(pk(-mm.x, mm.y)));
+    return up(rd);
 }
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
 
@@ -93,9 +130,9 @@ __device__ __forceinline__ void fft8(float2 (&x)[8]) {
     float2 t1 = cadd(x[1], x[5]), t5 = csub(x[1], x[5]);
     float2 t2 = cadd(x[2], x[6]), t6 = csub(x[2], x[6]);
     float2 t3 = cadd(x[3], x[7]), t7 = csub(x[3], x[7]);
-    t5 = make_float2((t5.x + t5.y) * h, (t5.y - t5.x) * h);       // * W8^1
+    t5 = scale2(h, cadd(t5, mul_mi(t5)));                          // * W8^1 = h (1 - i)
     t6 = mul_mi(t6);                                               // * W8^2
-    t7 = make_float2((t7.y - t7.x) * h, -(t7.x + t7.y) * h);      // * W8^3
+    t7 = scale2(h, csub(mul_mi(t7), t7));                          // * W8^3 = -h (1 + i)
     float2 u0 = cadd(t0, t2), u2 = csub(t0, t2);
     float2 u1 = cadd(t1, t3), u3 = mul_mi(csub(t1, t3));
     float2 u4 = cadd(t4, t6), u6 = csub(t4, t6);
@@ -145,6 +182,16 @@ __device__ __forceinline__ float power_to_db(float x) {
     return 3.01029995663981195f * __log2f(fmaxf(x, 1e-10f));      // 10 * log10(2) * log2(x)
 }
 
+// za = Z[k], zb = Z[512 - k] of z = x1 + i x2: {|Z + conj Z'|^2, |Z - conj Z'|^2} = the two frames' power at bin k
+// (the window carries the factor 1/2).  S = za + zb = (sr, di), D = za - zb = (dr, si).
+__device__ __forceinline__ float2 pair_power(float2 za, float2 zb) {
+    const float2 S = cadd(za, zb), D = csub(za, zb);
+    u64 t, rd;
+    asm("mul.f32x2 %0, %1, %1;" : "=l"(t) : "l"(pk(D.y, D.x)));                         // (si^2, dr^2)
+    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(rd) : "l"(pk(S.x, S.y)), "l"(t));          // (sr^2 + si^2, di^2 + dr^2)
+    return up(rd);
+}
+
 // One windowed sample pair for FFT point n of the frame pair starting at sample `base0`.
 // T = float (the reference's waveform type) or int16_t (PCM as stored in wav files: x / 32768 is exact in fp32 and the
 // peak normalisation cancels the power-of-two scale, so both types give bit-identical features)
@@ -157,9 +204,9 @@ __device__ __forceinline__ float2 load_point(const T* __restrict__ clip, float w
         i0 = i0 >= kSeg ? 2 * (kSeg - 1) - i0 : i0;
         i1 = i1 < 0 ? -i1 : i1;
         i1 = i1 >= kSeg ? 2 * (kSeg - 1) - i1 : i1;
-        return make_float2(w * (float)clip[i0], second ? w * (float)clip[i1] : 0.f);
+        return scale2(w, make_float2((float)clip[i0], second ? (float)clip[i1] : 0.f));
     }
-    return make_float2(w * (float)clip[i0], w * (float)clip[i1]);
+    return scale2(w, make_float2((float)clip[i0], (float)clip[i1]));
 }
 
 // The per-warp work item: frames 2p and 2p+1 -> 2 x 64 dB values in the tile.  Returns the lane's
@@ -268,16 +315,8 @@ __device__ __forceinline__ float frame_pair(SM& S, const T* __restrict__ clip, f
         const int o = 8 * c + 2 * (c >> 1) + j;
 #pragma unroll
         for (int sidx = 0; sidx < 2; ++sidx) {
-            {
-                const float2 za = A[sidx], zb = pA[sidx];
-                const float sr = za.x + zb.x, si = za.y - zb.y, dr = za.x - zb.x, di = za.y + zb.y;
-                xb[72 * sidx + o] = make_float2(sr * sr + si * si, dr * dr + di * di);
-            }
-            {
-                const float2 za = B[sidx], zb = pB[sidx];
-                const float sr = za.x + zb.x, si = za.y - zb.y, dr = za.x - zb.x, di = za.y + zb.y;
-                xb[72 * sidx + o + 4] = make_float2(sr * sr + si * si, dr * dr + di * di);
-            }
+            xb[72 * sidx + o] = pair_power(A[sidx], pA[sidx]);
+            xb[72 * sidx + o + 4] = pair_power(B[sidx], pB[sidx]);
         }
     }
     __syncwarp();
@@ -286,28 +325,25 @@ __device__ __forceinline__ float frame_pair(SM& S, const T* __restrict__ clip, f
     //      frames, and hands the rising-side sums to the lane above ----------------------------------------
     float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f), ulo = lo, uhi = lo;
     {
+        // unused slots read the shared zero instead of being predicated off: one broadcast address in a bank pair
+        // (8) the live ones rarely touch -- 19 wavefronts for the six loads, no predicates, no conditional moves
+        const uint32_t xb_s = smem_u32(xb), zero_s = smem_u32(&S.zero2);
         const int b0 = bin_lo & 0xff, n0 = bin_lo >> 8;
 #pragma unroll
-        for (int s = 0; s < kMelSlotsLo; ++s)
-            if (s < n0) {
-                const int bin = b0 + s;
-                const float2 pw = xb[bin + 2 * (bin >> 4)];
-                lo.x = fmaf(mw[s].x, pw.x, lo.x);
-                lo.y = fmaf(mw[s].x, pw.y, lo.y);
-                ulo.x = fmaf(mw[s].y, pw.x, ulo.x);
-                ulo.y = fmaf(mw[s].y, pw.y, ulo.y);
-            }
+        for (int s = 0; s < kMelSlotsLo; ++s) {
+            const int bin = b0 + s;
+            const float2 pw = lds64(s < n0 ? xb_s + 8u * (uint32_t)(bin + 2 * (bin >> 4)) : zero_s);
+            lo = fma2s(mw[s].x, pw, lo);
+            ulo = fma2s(mw[s].y, pw, ulo);
+        }
         const int b1 = bin_hi & 0xff, n1 = bin_hi >> 8;
 #pragma unroll
-        for (int s = 0; s < kMelSlotsHi; ++s)
-            if (s < n1) {
-                const int bin = b1 + s;
-                const float2 pw = xb[bin + 2 * (bin >> 4)];
-                hi.x = fmaf(mw[kMelSlotsLo + s].x, pw.x, hi.x);
-                hi.y = fmaf(mw[kMelSlotsLo + s].x, pw.y, hi.y);
-                uhi.x = fmaf(mw[kMelSlotsLo + s].y, pw.x, uhi.x);
-                uhi.y = fmaf(mw[kMelSlotsLo + s].y, pw.y, uhi.y);
-            }
+        for (int s = 0; s < kMelSlotsHi; ++s) {
+            const int bin = b1 + s;
+            const float2 pw = lds64(s < n1 ? xb_s + 8u * (uint32_t)(bin + 2 * (bin >> 4)) : zero_s);
+            hi = fma2s(mw[kMelSlotsLo + s].x, pw, hi);
+            uhi = fma2s(mw[kMelSlotsLo + s].y, pw, uhi);
+        }
         // band m += up(m - 1): lanes 1..31 take both sums from lane - 1; lane 0's band 32 takes up(31) from lane 31's
         // lo segment (its band 0 has nothing below it, and up(63) is identically zero)
         const int below = (lane + 31) & 31;
@@ -475,6 +511,7 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
         constexpr int n = (sizeof(S.tw1) + sizeof(S.tw2)) / 4;
         static_assert(offsetof(FeatTables, tw2) == sizeof(S.tw1) && offsetof(FeatSmem, tw2) - offsetof(FeatSmem, tw1) == sizeof(S.tw1), "layout");
         for (int i = tid; i < n; i += kFeatThreads) dst[i] = src[i];
+        if (tid == 0) S.zero2 = make_float2(0.f, 0.f);
     }
     float2 mw[kMelSlots];
 #pragma unroll
@@ -582,14 +619,18 @@ struct MelSmem {
     float2 xb[kFeatWarps][kXbElems];
     float2 tw1[7][64];
     float2 tw2[7][8];
+    float2 zero2;
 };
+static_assert(offsetof(MelSmem, xb) % 128 == 0 && offsetof(MelSmem, zero2) % 128 == 64, "zero2 sits in bank pair 8 of xb's numbering");
 struct StreamSmem {
     float2 xb[kFeatWarps][kXbElems];
     float  db[kMels * kFrames];
     float2 tw1[7][64];
     float2 tw2[7][8];
+    float2 zero2;
     float  red[64];
 };
+static_assert(offsetof(StreamSmem, xb) % 128 == 0 && offsetof(StreamSmem, zero2) % 128 == 64, "zero2 sits in bank pair 8 of xb's numbering");
 
 template <class SM>
 __device__ __forceinline__ void load_lane_tables(SM& S, const FeatTables* __restrict__ tables, float2 (&mw)[kMelSlots],
@@ -598,6 +639,7 @@ __device__ __forceinline__ void load_lane_tables(SM& S, const FeatTables* __rest
     float* dst = reinterpret_cast<float*>(&S.tw1[0][0]);
     constexpr int n = (sizeof(S.tw1) + sizeof(S.tw2)) / 4;
     for (int i = tid; i < n; i += kFeatThreads) dst[i] = src[i];
+    if (tid == 0) S.zero2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int s = 0; s < kMelSlots; ++s) mw[s] = tables->melt[s][lane];
     bin_lo = tables->melb[0][lane];
