@@ -28,7 +28,7 @@ BATCH = 16384
 AUDIO_BYTES = 64000           # 16000 fp32 samples
 FEAT_BYTES = 36360            # 90 x 101 fp32
 CNN_FLOPS = 42_865_600        # 2 x 21 432 800 MAC per clip
-NCU_TRAFFIC_PER_CLIP = 98_530  # feat_kernel dram__bytes_read+write per clip, one ncu --set full capture (profiles/)
+NCU_TRAFFIC_PER_CLIP = 100_195 # feat_kernel dram__bytes_read+write per clip, one ncu --set full capture (profiles/)
 METRIC = "1-s clips/sec (mel+MFCC+CNN)"
 
 
@@ -170,6 +170,8 @@ def run_gpu_arm(args):
     from cough_detector_b200.model import _PREC, DEFAULT_PRECISION
 
     torch.cuda.set_device(local_rank)
+    from cough_detector_b200.sharding import bind_to_gpu_numa
+    numa_bound = bind_to_gpu_numa(local_rank)         # pinned host buffers on the GPU's own socket (e2e path is PCIe-bound)
     if world > 1:
         os.environ["NCCL_DEBUG"] = os.environ.get("CD_BENCH_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -269,7 +271,9 @@ def run_gpu_arm(args):
         e2e_s = float(t.item())
     e2e_value = world * B * args.steps / e2e_s
     same = bool(torch.equal(out, logits.cpu()))
-    # what the link itself does: a bare pinned host->device copy of the same buffer (the e2e path's floor)
+    # what the link itself does: a bare pinned host->device copy of the same buffer, all ranks at once (the e2e
+    # path's floor; on a multi-GPU box the ranks share the host's memory and PCIe fabric)
+    barrier()
     dev_copy = torch.empty_like(audio)
     dev_copy.copy_(host, non_blocking=True)
     torch.cuda.synchronize()
@@ -321,12 +325,13 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": B * AUDIO_BYTES,
                     "d2h_bytes_per_step": B * 8, "bit_identical_to_device_path": same,
                     "h2d_gbs": e2e_value / world * AUDIO_BYTES / 1e9, "h2d_gbs_bare_copy": h2d_gbs,
+                    "host_numa_bound": numa_bound,
                     "api": "cd_e2e_forward_host (pinned host audio in, host logits out)"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "feat_kernel", "bound": "hbm", "achieved": feat_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": feat_gbs / hbm_peak, "traffic": FB * NCU_TRAFFIC_PER_CLIP, "peak_source": peak_src,
-                         "traffic_source": "ncu --set full (profiles/r1_ncu_feat_kernel_16384.csv): dram read+write "
-                                           "98 530 B per clip (1.614 GB per 16 384-clip launch), scaled by the launch size",
+                         "traffic_source": "ncu --set full of this launch (profiles/r1_ncu_feat_kernel_65536.csv): dram read 4.214 GB "
+                                           "+ write 2.352 GB per 65 536-clip launch = 100 195 B per clip, scaled by the launch size",
                          "algorithmic_bytes_per_clip": AUDIO_BYTES + FEAT_BYTES, "launch_ms": feat_ms,
                          "clips_per_s": FB / (feat_ms * 1e-3), "clips_per_launch": FB,
                          "note": "BASELINE configs[1]: timed alone over 65 536 resident clips right after the e2e region"},

@@ -16,6 +16,26 @@ import torch.distributed as dist
 WINDOW = 16000
 
 
+def bind_to_gpu_numa(device_index: int) -> bool:
+    """Pin the calling process to the CPU cores NVML reports as local to `device_index` (the socket its PCIe root
+    hangs off), so the pinned host buffers it allocates afterwards live on that NUMA node.  The host-buffer path is
+    PCIe-bound; with one process per GPU and no binding, ranks end up pulling their audio across the socket link.
+    Returns False (and changes nothing) when NVML or the topology is not available."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return True
+    except Exception:
+        return False
+
+
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous [start, end) of n items for `rank`; sizes differ by at most one."""
     base, rem = divmod(n, world)
