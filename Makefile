@@ -19,7 +19,15 @@ $(LIB): $(OBJS)
 	@mkdir -p $(OUT_DIR)
 	$(NVCC) -shared $(ARCH) -o $@ $(OBJS)
 
+# feature-kernel ablations (cost breakdown; see feat_kernel.cu CD_EXP and profiles/r1_feat_ablation.txt)
+ablations: $(OBJS)
+	@mkdir -p build/exp
+	for e in 1 2 3 4 5; do \
+	  $(NVCC) $(NVCCFLAGS) -DCD_EXP=$$e -c $(SRC_DIR)/feat_kernel.cu -o build/exp/feat_$$e.o 2> /dev/null && \
+	  $(NVCC) -shared $(ARCH) -o build/exp/libexp$$e.so build/api.o build/exp/feat_$$e.o build/cnn_fp32.o build/cnn_tc.o build/resample.o; \
+	done
+
 clean:
 	rm -rf build $(LIB)
 
-.PHONY: all clean
+.PHONY: all clean ablations

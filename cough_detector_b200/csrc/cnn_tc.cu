@@ -15,7 +15,8 @@
 //
 //   stem_tc_kernel            7x7/s2 + ReLU + maxpool as ONE GEMM per pooled pixel over 4x4-pixel blocks
 //   conv3x3_s2_tc_kernel x2   conv1 of each block (stride 2) over the phase-split input
-//   conv3x3_s1_tc_kernel x2   conv2 of each block (stride 1) + the block's 1x1/s2 skip conv as a tenth tap
+//   conv3x3_s1_tc_kernel      conv2 of block 0 (stride 1) + the block's 1x1/s2 skip conv as a tenth tap
+//   conv3x3_s1_pair_tc_kernel the same for block 1 on CTA pairs (cta_group::2, M = 256)
 //   head_kernel               42-pixel average pool + Linear(128->2) on CUDA cores (fixed summation order)
 #include <vector>
 

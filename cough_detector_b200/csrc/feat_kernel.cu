@@ -1,4 +1,4 @@
-// Fused feature kernel: clip -> (90, 101) features, one persistent CTA per SM.
+// Fused feature kernel: clip -> (90, 101) features, persistent, two 256-thread CTAs per SM.
 //
 // Replaces, per clip, AudioPreprocessor.normalize (src/preprocessing.py:199-212), pad_or_trim
 // (:358-385) and extract_features (:432-489): T.MelSpectrogram (reflect pad, 400-sample periodic
@@ -7,18 +7,24 @@
 // and the replicate-padded central-difference deltas.  The reference computes the mel
 // spectrogram twice (extract_mel_spectrogram and again inside T.MFCC); here it is computed once.
 //
-// Data flow per clip (all on chip between the 64 000 B read and the 36 360 B write):
-//   global --cp.async.bulk (TMA 1-D, double buffered)--> smem clip[16000]
-//   block max|x| -> in-place scale by 1/max
-//   16 warps x frame PAIRS: z = w*(x_2p + i x_2p+1), complex 512-point FFT as 8x8x8 radix-8
-//       (16 points per lane in registers, two smem exchanges), Z[k], Z[512-k] -> the two power
-//       spectra for bins 4..127 only, banded mel (244 taps), 10 log10 -> smem dB tile [64][101]
+// Data flow per clip (all on chip between the 64 000 B read and the feature / operand-map write):
+//   global --one cp.async.bulk (TMA 1-D), issued under the previous clip's tail--> smem clip[16000]
+//   block max|x| -> 1/max folded into the lane's 13 window weights (the clip is never rewritten)
+//   8 warps x frame PAIRS: z = w*(x_2p + i x_2p+1), complex 512-point FFT as 8x8x8 radix-8
+//       (16 points per lane in registers, packed f32x2 math, two smem exchanges), Z[k], Z[512-k] -> the two
+//       power spectra for bins 4..127 only, segment-owned banded mel, 10 log10 -> smem dB tile [64][101]
 //   block max(dB) -> floor; mel01 rows written; DCT-13 from the floored tile; block mean / std;
-//   normalised MFCC + deltas written.
+//   normalised MFCC + deltas written (fp32 features and/or the CNN stem's blocked bf16 map).
 // The power spectrum is invariant to a circular shift of the frame, so the 400 windowed samples
 // sit at n = 0..399 of the 512-point frame instead of torch.stft's 56..455.
 #include "cd_common.cuh"
 #include "cd_tables.h"
+// Ablation switches (never set in the shipped library; `make ablations` builds build/exp/libexp<n>.so and
+// tools/feat_time.py times them -- results are WRONG by construction, only the time is of interest):
+//   1 no second shared-memory exchange   2 no exchanges   3 no STFT at all   4 no tail   5 one mel slot per segment
+#ifndef CD_EXP
+#define CD_EXP 0
+#endif
 
 namespace cd {
 
@@ -248,6 +254,10 @@ __device__ __forceinline__ float frame_pair(SM& S, const T* __restrict__ clip, f
 
     // ---- exchange 1 (two halves of r) + stage 2: radix-8 over b (m = 8b + c) -------------------
     float2 C[8], D[8];
+#if CD_EXP == 2       // experiment: no exchanges at all
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { C[q] = A[q]; D[q] = B[q]; }
+#else
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         xb[r * kXbRow + lane] = A[r];
@@ -266,6 +276,7 @@ __device__ __forceinline__ float frame_pair(SM& S, const T* __restrict__ clip, f
 #pragma unroll
     for (int b = 0; b < 8; ++b) D[b] = xb[j * kXbRow + 8 * b + c];      // r = j + 4
     __syncwarp();
+#endif
     fft8<false>(C);
     fft8<false>(D);
 #pragma unroll
@@ -276,6 +287,10 @@ __device__ __forceinline__ float frame_pair(SM& S, const T* __restrict__ clip, f
     }
 
     // ---- exchange 2 + stage 3: radix-8 over c', pruned to s in {0,1,6,7} -----------------------
+#if CD_EXP == 1 || CD_EXP == 2        // experiment: no second exchange (wrong results; measures what the exchange costs)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { A[q] = C[q]; B[q] = D[q]; }
+#else
 #pragma unroll
     for (int u = 0; u < 8; ++u) xb[j * kXbRow + 9 * u + c] = C[u];
     __syncwarp();
@@ -288,6 +303,7 @@ __device__ __forceinline__ float frame_pair(SM& S, const T* __restrict__ clip, f
 #pragma unroll
     for (int q = 0; q < 8; ++q) B[q] = xb[j * kXbRow + 9 * c + q];
     __syncwarp();
+#endif
     fft8<true>(A);      // A[s] = Z[64 s + 8 c + j]
     fft8<true>(B);      // B[s] = Z[64 s + 8 c + j + 4]
 
@@ -330,7 +346,7 @@ __device__ __forceinline__ float frame_pair(SM& S, const T* __restrict__ clip, f
         const uint32_t xb_s = smem_u32(xb), zero_s = smem_u32(&S.zero2);
         const int b0 = bin_lo & 0xff, n0 = bin_lo >> 8;
 #pragma unroll
-        for (int s = 0; s < kMelSlotsLo; ++s) {
+        for (int s = 0; s < (CD_EXP == 5 ? 1 : kMelSlotsLo); ++s) {
             const int bin = b0 + s;
             const float2 pw = lds64(s < n0 ? xb_s + 8u * (uint32_t)(bin + 2 * (bin >> 4)) : zero_s);
             lo = fma2s(mw[s].x, pw, lo);
@@ -338,7 +354,7 @@ __device__ __forceinline__ float frame_pair(SM& S, const T* __restrict__ clip, f
         }
         const int b1 = bin_hi & 0xff, n1 = bin_hi >> 8;
 #pragma unroll
-        for (int s = 0; s < kMelSlotsHi; ++s) {
+        for (int s = 0; s < (CD_EXP == 5 ? 1 : kMelSlotsHi); ++s) {
             const int bin = b1 + s;
             const float2 pw = lds64(s < n1 ? xb_s + 8u * (uint32_t)(bin + 2 * (bin >> 4)) : zero_s);
             hi = fma2s(mw[kMelSlotsLo + s].x, pw, hi);
@@ -591,7 +607,7 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
 
         // ---- STFT -> mel -> dB, one frame pair per warp per round -----------------------------------
         float wmax = -INFINITY;
-        for (int p = warp; p < kPairs; p += kFeatWarps) {
+        for (int p = warp; p < (CD_EXP == 3 ? 0 : kPairs); p += kFeatWarps) {
             const bool edge = (p == 0) || (p >= 49);
             float* dst = S.db + 2 * p;
             const int base0 = 2 * kHop * p - kWin / 2;
@@ -601,8 +617,13 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
         }
         const float top = block_reduce<true>(wmax, S.red);             // barrier: dB tile complete, clip buffer dead
         if (tid == 0) fetch(b + gridDim.x);
+#if CD_EXP == 4       // experiment: no tail (keeps one store per thread so nothing upstream is dead code)
+        if (feat) feat[b * (int64_t)kFeatElem + tid] = top + S.db[tid * 25];
+        if (map_out) map_out[b * (int64_t)kMapElems + tid] = __float2bfloat16_rn(top + S.db[tid * 25]);
+#else
         feat_tail(S, top, feat ? feat + b * (int64_t)kFeatElem : nullptr,
                   map_out ? map_out + b * (int64_t)kMapElems : nullptr, tid);
+#endif
         __syncthreads();                                               // xb / db free again
     }
 }

@@ -56,7 +56,6 @@ class CoughDetectorResidual(nn.Module):
         self.global_pool = nn.AdaptiveAvgPool2d((1, 1))
         self.fc = nn.Sequential(nn.Flatten(), nn.Dropout(dropout), nn.Linear(channels[-1], num_classes))
         self.precision = precision or DEFAULT_PRECISION
-        self._uploaded = {}
 
     # ---- weight upload, once per (device, parameter version) -----------------------------------------
     def _weights_key(self):

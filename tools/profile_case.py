@@ -1,5 +1,6 @@
-"""Small fixed case for ncu: two e2e passes over 4096 clips (pass 1 = warm-up).  Launch order per
-2048-clip slab: feat_kernel, stem_bf16_kernel, 4 x conv3x3_tc_kernel, head_kernel (7 launches)."""
+"""Small fixed case for ncu: two e2e passes over B clips (pass 1 = warm-up).  Launch order per 16 384-clip slab:
+feat_kernel, stem_tc_kernel, conv3x3_s2_tc_kernel, conv3x3_s1_tc_kernel, conv3x3_s2_tc_kernel, conv3x3_s1_pair_tc_kernel,
+head_kernel (7 launches)."""
 import os
 import sys
 
