@@ -117,3 +117,15 @@ def test_decision_postpass_matches_oracle_and_reference():
     p = rng.random(500)
     for thr, win, deb in ((0.7, 3, 0.5), (0.5, 1, 0.0), (0.6, 5, 2.0)):
         assert smooth_and_debounce(p, 0.1, thr, win, deb) == co.decisions_stream(p, 0.1, thr, win, deb)
+
+
+def test_bind_to_gpu_numa_is_harmless_without_nvml():
+    # no GPU / no NVML here: must report False and leave the process affinity alone
+    import os
+
+    from cough_detector_b200 import sharding
+
+    before = os.sched_getaffinity(0)
+    assert sharding.bind_to_gpu_numa(0) in (False, True)
+    if not __import__("torch").cuda.is_available():
+        assert os.sched_getaffinity(0) == before
