@@ -310,23 +310,29 @@ umma_pair_selftest_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat
 // ----------------------------------------------------------------------------------------------
 // activation layouts of the convolution kernels
 // ----------------------------------------------------------------------------------------------
-// Padded + swizzled ("PS") activation layout consumed by the stride-1 kernel: every clip is a zero-padded
-// (H+2) x (W+2) image whose pixels are 128-byte rows of 64 channels (C = 128: two such planes); global row
+// Padded + swizzled ("PS") activation layout consumed by the stride-1 kernel: pixels are 128-byte rows of 64
+// channels (C = 128: two such planes) on a grid of pitch WP = W + 1 with H + 1 rows per clip; global row
 // rg = clip * RPC + (y+1) * WP + (x+1); the 16-byte chunk j of a row is stored at chunk j ^ (rg & 7), i.e.
 // already in the SWIZZLE_128B pattern of a tile that starts at a multiple of 8 rows.  With that, the A
 // operand of tap (ky, kx) for 128 consecutive output rows m' = y * WP + x is the SAME staged rows viewed
-// (ky * WP + kx) rows further down -- no im2col copy; pad rows are zero because the buffer is zeroed once
-// and only interior pixels are ever written.
+// (ky * WP + kx) rows further down -- no im2col copy.  The zero padding is SHARED: column 0 of a grid row is the
+// left pad of that row and, being the next index after column W of the row above, also the right pad of that
+// one; grid row 0 of a clip is its top pad and the bottom pad of the clip before it.  So a clip costs
+// (H+1)(W+1) GEMM rows instead of (H+2)(W+2) (block 0: 168 vs 195, block 1: 56 vs 72).  Pad rows are zero
+// because the buffer is zeroed once and only interior pixels are ever written.
 template <int H, int W>
 struct PsLayout {
-    static constexpr int HP = H + 2, WP = W + 2, RPC = HP * WP;
+    static constexpr int HP = H + 1, WP = W + 1, RPC = HP * WP;
     static constexpr int ROWS_IN = (128 + 2 * WP + 2 + 7) & ~7;     // rows one 128-row tile reads
 };
 
-// Phase-split variant for the INPUT of a stride-2 convolution (see conv3x3_s2_tc_kernel)
+// Phase-split variant for the INPUT of a stride-2 convolution (see conv3x3_s2_tc_kernel): phase (py, px) holds the
+// padded pixels (2a + py, 2b + px).  Taps read (oy + (ky >> 1), ox + (kx >> 1)), i.e. offset +1 only in the even
+// phases, whose element 0 is padding -- so here too the last column / row wraps onto the next row's / clip's
+// pad: A2 = (H + 2) / 2 rows of pitch B2 = (W + 2) / 2 (22 x 25 -> 12 x 13, 11 x 13 -> 6 x 7 = exactly the outputs).
 template <int H, int W>
 struct Ps2Layout {
-    static constexpr int A2 = (H + 3) / 2, B2 = (W + 3) / 2, RPC = A2 * B2;
+    static constexpr int A2 = (H + 2) / 2, B2 = (W + 2) / 2, RPC = A2 * B2;
     static constexpr int ROWS_IN = (128 + B2 + 1 + 7) & ~7;
 };
 
@@ -334,8 +340,8 @@ struct Ps2Layout {
 // stride-1 3x3 convolution without im2col: shifted descriptor views over PS-layout rows
 // ----------------------------------------------------------------------------------------------
 // conv2 of each residual block (C -> C, pad 1) + bias + identity add + ReLU.  GEMM rows are the padded
-// pixel rows m' of PsLayout (valid outputs: x < W, y < H; the rest are computed and dropped, 27 % / 42 %
-// of the MMA rows -- the tensor pipe has the headroom, L2 does not).  Per 128-row tile ONE bulk copy per
+// pixel rows m' of PsLayout (valid outputs: x < W, y < H; the rest are computed and dropped, 15 % / 25 %
+// of the MMA rows).  Per 128-row tile ONE bulk copy per
 // 64-channel plane stages ROWS_IN rows (20 KB) instead of nine im2col chunks (144 KB), and the weights
 // (9 taps x C/64 planes x [64 x 128 B]) stay resident in shared memory: a CTA owns one 64-wide half of
 // the output channels (C = 128: two halves -> the A rows are read twice, the 288 KB of weights never).
