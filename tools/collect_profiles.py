@@ -36,6 +36,15 @@ def main():
         w = csv.writer(f)
         for r in rows:
             w.writerow([r[i] for i in keep])
+    lb = os.path.join(SRC, "launches_bench.csv")
+    if os.path.exists(lb):
+        rows_b = [r for r in csv.reader(open(lb)) if len(r) > 10]
+        hb = rows_b[0]
+        keep_b = [hb.index(k) for k in ("ID", "Kernel Name", "Block Size", "Grid Size", "Metric Name", "Metric Unit", "Metric Value")]
+        with open(os.path.join(DST, f"{R}_launches_bench.csv"), "w", newline="") as f:
+            w = csv.writer(f)
+            for r in rows_b:
+                w.writerow([r[i] for i in keep_b])
     tool = os.path.join(ROOT, "tools", "ncu_summary.py")
     subprocess.run([sys.executable, tool, os.path.join(SRC, "prof_full.ncu-rep"), os.path.join(DST, f"{R}_ncu_full_summary.csv")], check=True)
     subprocess.run([sys.executable, tool, os.path.join(SRC, "prof_feat.ncu-rep"), os.path.join(DST, f"{R}_ncu_feat_kernel_65536.csv"), "feat_kernel"], check=True)

@@ -10,6 +10,9 @@ python bench.py --impl reference > $O/bench_ref.json 2> $O/bench_ref.err; echo r
 python bench.py > $O/bench.json 2> $O/bench.err; echo bench=$?
 python bench.py --precision fp32 --no-cpu-baseline > $O/bench_fp32.json 2> $O/bench_fp32.err; echo fp32=$?
 python tools/stream_bench.py > $O/stream.json 2> $O/stream.err; echo stream=$?
+# launch list of the bench command itself (it exited 0 plainly just above)
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"feat|stem|conv3x3|head|map_from|predict" -c 400 --csv \
+    --log-file $O/launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/ncu0.log 2>&1; echo launches_bench=$?
 python tools/profile_case.py 16384 > $O/pc.log 2>&1 && \
   ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"feat|stem|conv3x3|head" --csv \
       --log-file $O/launches.csv python tools/profile_case.py 16384 > $O/ncu1.log 2>&1; echo launches=$?
