@@ -180,9 +180,12 @@ int cd_e2e_forward_host_i16(cd_handle* h, const int16_t* h_audio, int64_t B, flo
 /* Diagnostic: D[i][n] = sum_k A[i + shift][k] * B[n][k] (i < 128) on one tcgen05 tile through the same
  * shared-memory / instruction descriptors the convolution kernels use (operands rounded to bf16, fp32
  * accumulate).  `shift` starts the A operand that many 128-byte rows into the swizzled tile -- the
- * "shifted view" the stride-1 convolutions use for their nine taps (mode 0: plain address offset; mode 1:
- * additionally sets the descriptor's base_offset field).  Host pointers; A has 128 + shift rows; N multiple
- * of 32 in [32, 256], K multiple of 64, shift in [0, 64].  Synchronous. */
+ * "shifted view" the convolutions use for their taps.  mode 0: SWIZZLE_128B rows, plain address offset (what the
+ * 3x3 kernels do); mode 1: same plus the descriptor's base_offset field (kept as the negative control: it is NOT what
+ * the hardware wants and gives wrong results for shifts that are not multiples of 8); mode 2: SWIZZLE_32B rows (the
+ * stem's 4x4-pixel blocks); mode 3: one cta_group::2 MMA stream over a CTA pair (A has 256 rows, shift must be 0).
+ * Host pointers; A has 128 + shift rows; N multiple of 32 in [32, 256], K multiple of 64, shift in [0, 64].
+ * Synchronous. */
 int cd_selftest_umma(cd_handle* h, int N, int K, int shift, int mode, const float* h_A, const float* h_B,
                      float* h_D);
 

@@ -152,6 +152,34 @@ def test_tcgen05_tile_selftest_bf16(n, k):
     assert err <= 2e-3 * scale
 
 
+@pytest.mark.parametrize("mode,shift", [(0, 1), (0, 7), (0, 17), (0, 32), (2, 1), (2, 9), (2, 27), (2, 31)])
+def test_tcgen05_shifted_descriptor_views(mode, shift):
+    """The convolutions never build an A tile: tap (ky, kx) is the staged rows viewed `shift` rows further down, i.e. an
+    operand descriptor whose start address is not a multiple of the 8-row swizzle atom.  mode 0: SWIZZLE_128B rows
+    (3x3 convs), mode 2: SWIZZLE_32B rows (the stem's 4x4-pixel blocks; K = 16 per row, so K is fixed by the tile)."""
+    k = 128
+    g = torch.Generator().manual_seed(100 * mode + shift)
+    a = torch.randn(128 + shift, k, generator=g)
+    b = torch.randn(64, k, generator=g)
+    d = _lib.get_handle(0).selftest_umma(a, b, shift, mode)
+    ref = a[shift:shift + 128].bfloat16().double() @ b.bfloat16().double().t()
+    err, scale = (d.double() - ref).abs().max().item(), ref.abs().max().item()
+    assert err <= 2e-3 * scale
+
+
+@pytest.mark.parametrize("n,k", [(128, 64), (128, 256), (64, 128), (256, 128)])
+def test_tcgen05_cta_pair_tile(n, k):
+    """cta_group::2: one MMA stream over a CTA pair (M = 256; each CTA holds its own 128 A rows and N/2 of the B rows),
+    the mode block 1's conv2 runs in."""
+    g = torch.Generator().manual_seed(7 * n + k)
+    a = torch.randn(256, k, generator=g)
+    b = torch.randn(n, k, generator=g)
+    d = _lib.get_handle(0).selftest_umma(a, b, 0, 3)
+    ref = a.bfloat16().double() @ b.bfloat16().double().t()
+    err, scale = (d.double() - ref).abs().max().item(), ref.abs().max().item()
+    assert err <= 2e-3 * scale
+
+
 def test_every_entry_point_on_small_shapes():
     """tools/sanitize_case.py: all kernels / C-ABI entry points on tiny, ragged inputs (the case written for
     compute-sanitizer; that tool is closed on this pool, so it runs as a plain smoke test)."""
