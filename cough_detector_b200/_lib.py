@@ -19,6 +19,9 @@ N_FEATURES = 90
 N_FRAMES = 101
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
+FEAT_NORMALIZE = 1
+FEAT_PRE_EMPHASIS = 2
+FEAT_PCEN = 4
 
 _f32p = C.POINTER(C.c_float)
 
@@ -40,6 +43,7 @@ SYMBOLS = {
     "cd_last_error": (C.c_char_p, [_VP]),
     "cd_version": (C.c_char_p, []),
     "cd_get_tables": (_I, [_VP, _VP, _VP]),
+    "cd_feat_options": (_I, [_VP, _I, C.c_float]),
     "cd_feat_forward": (_I, [_VP, _VP, _I64, _I64, _VP, _I, _VP]),
     "cd_feat_forward_i16": (_I, [_VP, _VP, _I64, _I64, _VP, _I, _VP]),
     "cd_feat_forward_var": (_I, [_VP, _VP, _VP, _VP, _I64, _VP, _VP]),
@@ -132,6 +136,14 @@ class Handle:
         return int(self.lib.cd_launch_count(self._h))
 
     # ---- features ---------------------------------------------------------------------------
+    def set_feat_options(self, use_pre_emphasis: bool = False, pre_emphasis_coef: float = 0.97, use_pcen: bool = False):
+        """Handle defaults for every later feature launch (cd_feat_options); (False, ., False) is the training config."""
+        key = (bool(use_pre_emphasis), float(pre_emphasis_coef), bool(use_pcen))
+        if getattr(self, "_feat_opts", (False, 0.97, False)) != key:
+            flags = (FEAT_PRE_EMPHASIS if key[0] else 0) | (FEAT_PCEN if key[2] else 0)
+            self._check(self.lib.cd_feat_options(self._h, flags, key[1]), "cd_feat_options")
+            self._feat_opts = key
+
     def feat_forward(self, audio: torch.Tensor, normalize: bool = True) -> torch.Tensor:
         """(B, 16000) cuda fp32 -> (B, 1, 90, 101)."""
         audio = self._dev_f32(audio, "audio")

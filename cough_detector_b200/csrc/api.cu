@@ -165,13 +165,29 @@ int cd_destroy(cd_handle* h) {
 
 // ---- features --------------------------------------------------------------------------------
 
+static int feat_mode_bits(int flags) {
+    return ((flags & CD_FEAT_NORMALIZE) ? 0 : kModeNoNormalize) | ((flags & CD_FEAT_PRE_EMPHASIS) ? kModePreEmph : 0) |
+           ((flags & CD_FEAT_PCEN) ? kModePcen : 0);
+}
+
+int cd_feat_options(cd_handle* h, int flags, float pre_emphasis_coef) {
+    if (!h) return CD_E_ARG;
+    if (flags & ~(CD_FEAT_PRE_EMPHASIS | CD_FEAT_PCEN))
+        return set_err(h, CD_E_ARG, "cd_feat_options: only CD_FEAT_PRE_EMPHASIS and CD_FEAT_PCEN can be made handle defaults");
+    if (!(pre_emphasis_coef >= 0.f && pre_emphasis_coef <= 1.f))
+        return set_err(h, CD_E_ARG, "cd_feat_options: pre_emphasis_coef must be in [0, 1]");
+    h->feat_opts = feat_mode_bits(flags | CD_FEAT_NORMALIZE);
+    h->pre_coef = pre_emphasis_coef;
+    return CD_OK;
+}
+
 int cd_feat_forward(cd_handle* h, const float* d_audio, int64_t stride, int64_t B, float* d_feat, int flags,
                     void* stream) {
     if (!h) return CD_E_ARG;
     if (B < 0 || stride < kSeg || (B > 0 && (!d_audio || !d_feat)))
         return set_err(h, CD_E_ARG, "cd_feat_forward: bad argument (need stride >= 16000, non-NULL buffers)");
     DeviceGuard g(h->device);
-    const int mode = kModeFixed | ((flags & CD_FEAT_NORMALIZE) ? 0 : kModeNoNormalize);
+    const int mode = kModeFixed | feat_mode_bits(flags);
     return launch_features(h, d_audio, nullptr, nullptr, stride, mode, B, d_feat, nullptr, (cudaStream_t)stream);
 }
 
@@ -181,7 +197,7 @@ int cd_feat_forward_i16(cd_handle* h, const int16_t* d_audio, int64_t stride, in
     if (B < 0 || stride < kSeg || (stride & 7) || (B > 0 && (!d_audio || !d_feat)))
         return set_err(h, CD_E_ARG, "cd_feat_forward_i16: bad argument (need stride >= 16000 and a multiple of 8)");
     DeviceGuard g(h->device);
-    const int mode = kModeFixed | ((flags & CD_FEAT_NORMALIZE) ? 0 : kModeNoNormalize);
+    const int mode = kModeFixed | feat_mode_bits(flags);
     return launch_features_i16(h, d_audio, stride, mode, B, d_feat, nullptr, (cudaStream_t)stream);
 }
 

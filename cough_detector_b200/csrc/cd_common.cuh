@@ -74,6 +74,8 @@ struct cd_handle {
     int64_t launches = 0;
 
     cd::FeatTables* d_tables = nullptr;
+    int feat_opts = 0;                   // kModePreEmph | kModePcen, OR-ed into every feature launch (cd_feat_options)
+    float pre_coef = 0.97f;              // pre_emphasis_coef (src/preprocessing.py:44)
 
     bool weights_loaded = false;
     float* d_wblob = nullptr;            // one allocation holding every folded fp32 tensor
@@ -116,6 +118,7 @@ int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets
 int launch_cnn_fp32(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, cudaStream_t s);
 size_t cnn_fp32_ws_bytes(int64_t B);
 
-enum FeatMode { kModeFixed = 0, kModeVar = 1, kModeStream = 2, kModeMask = 3, kModeNoNormalize = 4 };
+enum FeatMode { kModeFixed = 0, kModeVar = 1, kModeStream = 2, kModeMask = 3, kModeNoNormalize = 4,
+                kModePreEmph = 8, kModePcen = 16 };
 
 }  // namespace cd

@@ -201,8 +201,18 @@ __device__ __forceinline__ float2 pair_power(float2 za, float2 zb) {
 // One windowed sample pair for FFT point n of the frame pair starting at sample `base0`.
 // T = float (the reference's waveform type) or int16_t (PCM as stored in wav files: x / 32768 is exact in fp32 and the
 // peak normalisation cancels the power-of-two scale, so both types give bit-identical features)
-template <bool EDGE, class T>
-__device__ __forceinline__ float2 load_point(const T* __restrict__ clip, float w, int n, int base0, bool second) {
+// PRE: the sample is the pre-emphasised one, y[i] = x[i] - coef * x[i-1], y[0] = x[0] (apply_pre_emphasis,
+// src/preprocessing.py:213-239; product and difference rounded separately like the reference's tensor ops).  Only the
+// edge pairs can touch i = 0; the shared stream frames never do (they start >= 120 samples into every window).
+template <bool EDGE, bool PRE, class T>
+__device__ __forceinline__ float sample_at(const T* __restrict__ clip, int i, float coef) {
+    const float x = (float)clip[i];
+    if (!PRE) return x;
+    if (EDGE && i == 0) return x;
+    return __fsub_rn(x, __fmul_rn(coef, (float)clip[i - 1]));
+}
+template <bool EDGE, bool PRE, class T>
+__device__ __forceinline__ float2 load_point(const T* __restrict__ clip, float w, int n, int base0, bool second, float coef) {
     int i0 = base0 + n;
     int i1 = i0 + kHop;
     if (EDGE) {   // reflect padding of torch.stft(center=True, pad_mode="reflect")
@@ -210,30 +220,31 @@ __device__ __forceinline__ float2 load_point(const T* __restrict__ clip, float w
         i0 = i0 >= kSeg ? 2 * (kSeg - 1) - i0 : i0;
         i1 = i1 < 0 ? -i1 : i1;
         i1 = i1 >= kSeg ? 2 * (kSeg - 1) - i1 : i1;
-        return scale2(w, make_float2((float)clip[i0], second ? (float)clip[i1] : 0.f));
+        return scale2(w, make_float2(sample_at<EDGE, PRE, T>(clip, i0, coef), second ? sample_at<EDGE, PRE, T>(clip, i1, coef) : 0.f));
     }
-    return scale2(w, make_float2((float)clip[i0], (float)clip[i1]));
+    return scale2(w, make_float2(sample_at<EDGE, PRE, T>(clip, i0, coef), sample_at<EDGE, PRE, T>(clip, i1, coef)));
 }
 
 // The per-warp work item: frames 2p and 2p+1 -> 2 x 64 dB values in the tile.  Returns the lane's
 // running max of the dB values it produced.
 // RAW = false: dB values go to dst[band * band_stride + {0, frame_stride}] (the smem tile).
 // RAW = true : un-logged mel POWER goes there instead (shared STFT frames of the streaming path).
-template <bool EDGE, bool RAW, class SM, class T>
+template <bool EDGE, bool RAW, bool PRE, class SM, class T>
 __device__ __forceinline__ float frame_pair(SM& S, const T* __restrict__ clip, float2* __restrict__ xb,
                                             const float (&wA)[7], const float (&wB)[6],
                                             const float2 (&mw)[kMelSlots], int bin_lo, int bin_hi, int base0, bool second,
-                                            int lane, float* __restrict__ dst, int band_stride, int frame_stride) {
+                                            int lane, float* __restrict__ dst, int band_stride, int frame_stride,
+                                            float coef = 0.f) {
     const int c = lane & 7, j = lane >> 3;             // base0: sample index of window tap 0 of the first frame
 
     // ---- stage 1: radix-8 over a (n = 64a + m), m = lane and lane + 32 ------------------------
     float2 A[8], B[8];
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
-        A[a] = load_point<EDGE, T>(clip, wA[a], 64 * a + lane, base0, second);
-        B[a] = load_point<EDGE, T>(clip, wB[a], 64 * a + lane + 32, base0, second);
+        A[a] = load_point<EDGE, PRE, T>(clip, wA[a], 64 * a + lane, base0, second, coef);
+        B[a] = load_point<EDGE, PRE, T>(clip, wB[a], 64 * a + lane + 32, base0, second, coef);
     }
-    A[6] = lane < 16 ? load_point<EDGE, T>(clip, wA[6], 384 + lane, base0, second) : make_float2(0.f, 0.f);
+    A[6] = lane < 16 ? load_point<EDGE, PRE, T>(clip, wA[6], 384 + lane, base0, second, coef) : make_float2(0.f, 0.f);
     A[7] = make_float2(0.f, 0.f);                   // n >= 400: zero padding of the 512-point frame
     B[6] = make_float2(0.f, 0.f);
     B[7] = make_float2(0.f, 0.f);
@@ -380,11 +391,13 @@ __device__ __forceinline__ float frame_pair(SM& S, const T* __restrict__ clip, f
     if (RAW) {
         row_lo[0] = lo.x;
         row_hi[0] = hi.x;
+        float m = fmaxf(lo.x, hi.x);
         if (second) {
             row_lo[frame_stride] = lo.y;
             row_hi[frame_stride] = hi.y;
+            m = fmaxf(m, fmaxf(lo.y, hi.y));
         }
-        return 0.f;
+        return m;                                    // running max of the mel POWER (the PCEN variant's top_db needs it)
     }
     const float d0 = power_to_db(lo.x), d2 = power_to_db(hi.x);
     row_lo[0] = d0;
@@ -402,15 +415,20 @@ __device__ __forceinline__ float frame_pair(SM& S, const T* __restrict__ clip, f
 // DCT-II of the floored dB tile for frame t, coefficients of one parity (PAR = 0: c = 0,2,..,12;
 // PAR = 1: c = 1,3,..,11).  cos(pi (m + 1/2) c / 64) is even (c even) or odd (c odd) about m = 31.5, so
 // each coefficient is a 32-term sum over d[m] +- d[63 - m], shared by all coefficients of that parity.
-template <int PAR>
-__device__ __forceinline__ float mfcc_par(const float* __restrict__ db, float* __restrict__ mf, int t) {
+// POWER: the tile holds mel power (PCEN variant); dB and its top_db floor are applied on the way in.
+template <int PAR, bool POWER>
+__device__ __forceinline__ float mfcc_par(const float* __restrict__ db, float* __restrict__ mf, int t, float floor_db) {
     constexpr int NC = PAR ? 6 : 7;
     float acc[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) acc[i] = 0.f;
 #pragma unroll
     for (int m = 0; m < kMels / 2; ++m) {
-        const float lo = db[m * kFrames + t], hi = db[(kMels - 1 - m) * kFrames + t];
+        float lo = db[m * kFrames + t], hi = db[(kMels - 1 - m) * kFrames + t];
+        if (POWER) {
+            lo = fmaxf(power_to_db(lo), floor_db);
+            hi = fmaxf(power_to_db(hi), floor_db);
+        }
         const float d = PAR ? lo - hi : lo + hi;
 #pragma unroll
         for (int i = 0; i < NC; ++i) acc[i] = fmaf(c_dct[(PAR + 2 * i) * kMels + m], d, acc[i]);
@@ -424,29 +442,33 @@ __device__ __forceinline__ float mfcc_par(const float* __restrict__ db, float* _
     return s;
 }
 
-// Everything after the dB tile is complete: top_db floor, mel01 rows, DCT-13, mean / unbiased std
+// Everything after the tile is complete: top_db floor, mel rows, DCT-13, mean / unbiased std
 // normalisation, deltas; fp32 features to `out` and/or the stem's bf16 map to `mo` (either may be null).
+// PCEN = false: the tile holds dB, `top` is its block max; rows 0..63 are clamp((dB + 80) / 80).
+// PCEN = true : the tile holds mel POWER, `top` is its block max; rows 0..63 are apply_pcen (src/preprocessing.py:
+//               305-340) scaled to [0, 1] by the clip's min / max (:400-404); the MFCC rows still come from the dB.
 // Ends with the block in sync except for the final stores.
-template <class SM>
+template <bool PCEN, class SM>
 __device__ __forceinline__ void feat_tail(SM& S, float top, float* __restrict__ out, __nv_bfloat16* __restrict__ mo, int tid) {
-    // `top` = block max of the dB tile (the caller's block_reduce is the barrier that completes the tile)
-    const float floor_db = top - 80.0f;                            // top_db = 80
+    const float floor_db = (PCEN ? power_to_db(top) : top) - 80.0f;    // top_db = 80
 
-    // ---- mel block rows 0..63: max(dB, floor) -> (dB + 80) / 80 -> clamp ------------------------
-    // The CNN stem's operand rides along: the same values rounded to bf16, scattered straight into the clip's
-    // blocked map (cd_common.cuh: bmap_offset).  Its padding elements are never written by anyone: the map
-    // lives in the tensor-core workspace, which is zeroed once at allocation.
-    for (int i = tid; i < kMels * kFrames; i += kFeatThreads) {
-        const float v = fmaxf(S.db[i], floor_db);
-        S.db[i] = v;
-        const float x01 = fminf(fmaxf((v + 80.0f) * 0.0125f, 0.f), 1.f);
-        if (out) out[i] = x01;
-        if (mo) {
-            const int r = i / kFrames;
-            mo[bmap_offset(r + 3, i - r * kFrames + 3)] = __float2bfloat16_rn(x01);
+    if (!PCEN) {
+        // ---- mel block rows 0..63: max(dB, floor) -> (dB + 80) / 80 -> clamp ------------------------
+        // The CNN stem's operand rides along: the same values rounded to bf16, scattered straight into the clip's
+        // blocked map (cd_common.cuh: bmap_offset).  Its padding elements are never written by anyone: the map
+        // lives in the tensor-core workspace, which is zeroed once at allocation.
+        for (int i = tid; i < kMels * kFrames; i += kFeatThreads) {
+            const float v = fmaxf(S.db[i], floor_db);
+            S.db[i] = v;
+            const float x01 = fminf(fmaxf((v + 80.0f) * 0.0125f, 0.f), 1.f);
+            if (out) out[i] = x01;
+            if (mo) {
+                const int r = i / kFrames;
+                mo[bmap_offset(r + 3, i - r * kFrames + 3)] = __float2bfloat16_rn(x01);
+            }
         }
+        __syncthreads();
     }
-    __syncthreads();
 
     // ---- MFCC = DCT-II(13 x 64) of the floored dB, then (x - mean) / (std + 1e-8) ---------------
     float* mf = reinterpret_cast<float*>(&S.xb[0][0]);             // [13][101], FFT scratch is idle now
@@ -454,7 +476,7 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float* __restrict__ 
     {
         static_assert(kFeatThreads == 256, "two parity groups of 128 threads");
         const int t = tid & 127;
-        if (t < kFrames) part = (tid >> 7) ? mfcc_par<1>(S.db, mf, t) : mfcc_par<0>(S.db, mf, t);
+        if (t < kFrames) part = (tid >> 7) ? mfcc_par<1, PCEN>(S.db, mf, t, floor_db) : mfcc_par<0, PCEN>(S.db, mf, t, floor_db);
     }
     constexpr int kN = kMfcc * kFrames;                            // 1313
     const float mean = block_reduce<false>(part, S.red) * (1.0f / kN);
@@ -485,6 +507,45 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float* __restrict__ 
         }
     }
 
+    if (PCEN) {
+        // ---- PCEN rows 0..63 from the power tile: smoother = zero-padded mean of frames t-5 .. t+4 (avg_pool2d
+        //      kernel (1, 10), padding (0, 5), cut to 101 columns); (P / (eps + M)^0.98 + 2)^0.5 - 2^0.5 ------------
+        constexpr int kPer = (kMels * kFrames + kFeatThreads - 1) / kFeatThreads;      // 26
+        float val[kPer];
+        float vmin = INFINITY, vmax = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int i = tid + k * kFeatThreads;
+            float v = 0.f;
+            if (i < kMels * kFrames) {
+                const int r = i / kFrames, t = i - r * kFrames;
+                const float* row = S.db + r * kFrames;
+                float sm = 0.f;
+#pragma unroll
+                for (int j = -5; j <= 4; ++j) sm += (t + j >= 0 && t + j < kFrames) ? row[t + j] : 0.f;
+                sm *= 0.1f;
+                v = sqrtf(__fdiv_rn(row[t], powf(1e-6f + sm, 0.98f)) + 2.0f) - 1.41421354f;
+                vmin = fminf(vmin, v);
+                vmax = fmaxf(vmax, v);
+            }
+            val[k] = v;
+        }
+        vmax = block_reduce<true>(vmax, S.red);
+        vmin = -block_reduce<true>(-vmin, S.red);
+        const float range = (vmax - vmin) + 1e-8f;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int i = tid + k * kFeatThreads;
+            if (i < kMels * kFrames) {
+                const float x01 = __fdiv_rn(val[k] - vmin, range);
+                if (out) out[i] = x01;
+                if (mo) {
+                    const int r = i / kFrames;
+                    mo[bmap_offset(r + 3, i - r * kFrames + 3)] = __float2bfloat16_rn(x01);
+                }
+            }
+        }
+    }
 }
 
 template <class T>
@@ -511,11 +572,13 @@ __device__ __forceinline__ bool bulk_ok(const ClipDesc<T>& d) {
     return d.len == kSeg && ((reinterpret_cast<uintptr_t>(d.src) & 15) == 0);
 }
 
-template <class T>
+// PRE / PCEN: the use_pre_emphasis / use_pcen variants of the 90-feature path (the part that keeps
+// the CNN input at 90 rows); <false, false> is the training configuration (src/train.py:264-287) and the benchmark.
+template <class T, bool PRE, bool PCEN>
 __global__ void __launch_bounds__(kFeatThreads, 2)
 feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const int32_t* __restrict__ lens,
             int64_t stride_or_hop, int mode, int64_t B, float* __restrict__ feat,
-            __nv_bfloat16* __restrict__ map_out, const FeatTables* __restrict__ tables) {
+            __nv_bfloat16* __restrict__ map_out, const FeatTables* __restrict__ tables, float coef) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FeatSmem& S = *reinterpret_cast<FeatSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -612,8 +675,8 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
             float* dst = S.db + 2 * p;
             const int base0 = 2 * kHop * p - kWin / 2;
             const bool second = (2 * p + 1) < kFrames;
-            wmax = fmaxf(wmax, edge ? frame_pair<true, false>(S, clip, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, base0, second, lane, dst, kFrames, 1)
-                                    : frame_pair<false, false>(S, clip, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, base0, second, lane, dst, kFrames, 1));
+            wmax = fmaxf(wmax, edge ? frame_pair<true, PCEN, PRE>(S, clip, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, base0, second, lane, dst, kFrames, 1, coef)
+                                    : frame_pair<false, PCEN, PRE>(S, clip, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, base0, second, lane, dst, kFrames, 1, coef));
         }
         const float top = block_reduce<true>(wmax, S.red);             // barrier: dB tile complete, clip buffer dead
         if (tid == 0) fetch(b + gridDim.x);
@@ -621,8 +684,8 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
         if (feat) feat[b * (int64_t)kFeatElem + tid] = top + S.db[tid * 25];
         if (map_out) map_out[b * (int64_t)kMapElems + tid] = __float2bfloat16_rn(top + S.db[tid * 25]);
 #else
-        feat_tail(S, top, feat ? feat + b * (int64_t)kFeatElem : nullptr,
-                  map_out ? map_out + b * (int64_t)kMapElems : nullptr, tid);
+        feat_tail<PCEN>(S, top, feat ? feat + b * (int64_t)kFeatElem : nullptr,
+                        map_out ? map_out + b * (int64_t)kMapElems : nullptr, tid);
 #endif
         __syncthreads();                                               // xb / db free again
     }
@@ -689,8 +752,10 @@ block_max_kernel(const float* __restrict__ audio, int64_t n_blocks, float* __res
 }
 
 // melp[f][64] = un-normalised mel power of global frame f, f in [2, F)
+template <bool PRE>
 __global__ void __launch_bounds__(kFeatThreads, 2)
-stream_mel_kernel(const float* __restrict__ audio, int64_t F, float* __restrict__ melp, const FeatTables* __restrict__ tables) {
+stream_mel_kernel(const float* __restrict__ audio, int64_t F, float* __restrict__ melp, const FeatTables* __restrict__ tables,
+                  float coef) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     MelSmem& S = *reinterpret_cast<MelSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -705,14 +770,15 @@ stream_mel_kernel(const float* __restrict__ audio, int64_t F, float* __restrict_
         int64_t f0 = 2 + 2 * q;
         if (f0 + 1 >= F) f0 = F - 2;                  // odd tail: redo (F-2, F-1); both writers store identical values
         const float* base = audio + f0 * kHop - kWin / 2;
-        frame_pair<false, true>(S, base, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, 0, true, lane, melp + f0 * kMels, 1, kMels);
+        frame_pair<false, true, PRE>(S, base, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, 0, true, lane, melp + f0 * kMels, 1, kMels, coef);
     }
 }
 
+template <bool PRE, bool PCEN>
 __global__ void __launch_bounds__(kFeatThreads, 2)
 stream_window_kernel(const float* __restrict__ audio, int64_t hop, int64_t n_windows, const float* __restrict__ melp,
                      const float* __restrict__ bmax, float* __restrict__ feat, __nv_bfloat16* __restrict__ map_out,
-                     const FeatTables* __restrict__ tables) {
+                     const FeatTables* __restrict__ tables, float coef) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     StreamSmem& S = *reinterpret_cast<StreamSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -731,21 +797,21 @@ stream_window_kernel(const float* __restrict__ audio, int64_t hop, int64_t n_win
             float wA[7], wB[6];
             lane_window(tables, inv, lane, wA, wB);
             const int p = warp == 0 ? 0 : 48 + warp;
-            wmax = frame_pair<true, false>(S, audio + j * hop, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, 2 * kHop * p - kWin / 2,
-                                           (2 * p + 1) < kFrames, lane, S.db + 2 * p, kFrames, 1);
+            wmax = frame_pair<true, PCEN, PRE>(S, audio + j * hop, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, 2 * kHop * p - kWin / 2,
+                                               (2 * p + 1) < kFrames, lane, S.db + 2 * p, kFrames, 1, coef);
         } else {
             // frames 2..97 come from the shared global frames j h + t
             const float inv2 = inv * inv;
             const float* src = melp + (j * h + 2) * kMels;
             for (int i = tid - 96; i < 96 * kMels; i += kFeatThreads - 96) {
                 const int t = i >> 6, m = i & 63;
-                const float d = power_to_db(src[i] * inv2);
+                const float d = PCEN ? src[i] * inv2 : power_to_db(src[i] * inv2);     // PCEN keeps the tile in power
                 S.db[m * kFrames + t + 2] = d;
                 wmax = fmaxf(wmax, d);
             }
         }
-        feat_tail(S, block_reduce<true>(wmax, S.red), feat ? feat + j * (int64_t)kFeatElem : nullptr,
-                  map_out ? map_out + j * (int64_t)kMapElems : nullptr, tid);
+        feat_tail<PCEN>(S, block_reduce<true>(wmax, S.red), feat ? feat + j * (int64_t)kFeatElem : nullptr,
+                        map_out ? map_out + j * (int64_t)kMapElems : nullptr, tid);
         __syncthreads();
     }
 }
@@ -806,20 +872,44 @@ int build_feat_tables(cd_handle* h) {
     float dct[kMfcc * kMels];
     for (int i = 0; i < kMfcc * kMels; ++i) dct[i] = bits2f(CD_DCT_BITS[i]);
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_dct, dct, sizeof(dct));
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(feat_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeatSmem));
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(feat_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeatSmem));
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(stream_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem));
+    auto big = [&](auto kernel, size_t bytes) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    };
+    big(feat_kernel<float, false, false>, sizeof(FeatSmem));
+    big(feat_kernel<float, true, false>, sizeof(FeatSmem));
+    big(feat_kernel<float, false, true>, sizeof(FeatSmem));
+    big(feat_kernel<float, true, true>, sizeof(FeatSmem));
+    big(feat_kernel<int16_t, false, false>, sizeof(FeatSmem));
+    big(feat_kernel<int16_t, true, false>, sizeof(FeatSmem));
+    big(feat_kernel<int16_t, false, true>, sizeof(FeatSmem));
+    big(feat_kernel<int16_t, true, true>, sizeof(FeatSmem));
+    big(stream_window_kernel<false, false>, sizeof(StreamSmem));
+    big(stream_window_kernel<true, false>, sizeof(StreamSmem));
+    big(stream_window_kernel<false, true>, sizeof(StreamSmem));
+    big(stream_window_kernel<true, true>, sizeof(StreamSmem));
     delete t;
     if (e != cudaSuccess) return set_err(h, CD_E_CUDA, "feature tables upload", e);
     return CD_OK;
 }
 
+// the four (pre-emphasis, PCEN) variants of a kernel template, picked by the handle's options
+#define CD_FEAT_VARIANT(pre, pcen, CALL)           \
+    do {                                           \
+        if (pre) {                                 \
+            if (pcen) { CALL(true, true); }        \
+            else      { CALL(true, false); }       \
+        } else {                                   \
+            if (pcen) { CALL(false, true); }       \
+            else      { CALL(false, false); }      \
+        }                                          \
+    } while (0)
+
 int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets, const int32_t* d_lengths,
                     int64_t stride_or_hop, int mode, int64_t B, float* d_feat, __nv_bfloat16* d_map, cudaStream_t s) {
     if (B == 0) return CD_OK;
+    mode |= h->feat_opts;
+    const bool pre = (mode & kModePreEmph) != 0, pcen = (mode & kModePcen) != 0;
+    const float coef = h->pre_coef;
     const int64_t slots = 2 * (int64_t)h->sm_count;     // two resident CTAs per SM
     if ((mode & kModeMask) == kModeStream && stride_or_hop % kHop == 0 && stride_or_hop <= kSeg / 2 && B >= 2) {
         // overlapping windows on the frame grid: share the STFT frames
@@ -840,17 +930,26 @@ int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets
         float* bmax = melp + (size_t)F * kMels;
         block_max_kernel<<<(unsigned)((n_blocks + 7) / 8), 256, 0, s>>>(d_audio, n_blocks, bmax);
         const int64_t pair_ctas = ((F - 1) / 2 + kFeatWarps - 1) / kFeatWarps;
-        stream_mel_kernel<<<(int)(pair_ctas < 4 * slots ? pair_ctas : 4 * slots), kFeatThreads, sizeof(MelSmem), s>>>(
-            d_audio, F, melp, h->d_tables);
-        stream_window_kernel<<<(int)(B < slots ? B : slots), kFeatThreads, sizeof(StreamSmem), s>>>(
-            d_audio, hop, B, melp, bmax, d_feat, d_map, h->d_tables);
+        const int mel_grid = (int)(pair_ctas < 4 * slots ? pair_ctas : 4 * slots);
+        if (pre)
+            stream_mel_kernel<true><<<mel_grid, kFeatThreads, sizeof(MelSmem), s>>>(d_audio, F, melp, h->d_tables, coef);
+        else
+            stream_mel_kernel<false><<<mel_grid, kFeatThreads, sizeof(MelSmem), s>>>(d_audio, F, melp, h->d_tables, coef);
+#define CD_CALL(P, Q)                                                                                   \
+    stream_window_kernel<P, Q><<<(int)(B < slots ? B : slots), kFeatThreads, sizeof(StreamSmem), s>>>(   \
+        d_audio, hop, B, melp, bmax, d_feat, d_map, h->d_tables, coef)
+        CD_FEAT_VARIANT(pre, pcen, CD_CALL);
+#undef CD_CALL
         h->launches += 3;
         CD_CUDA(h, cudaGetLastError());
         return CD_OK;
     }
     const int grid = (int)(B < slots ? B : slots);
-    feat_kernel<float><<<grid, kFeatThreads, sizeof(FeatSmem), s>>>(d_audio, d_offsets, d_lengths, stride_or_hop, mode, B,
-                                                            d_feat, d_map, h->d_tables);
+#define CD_CALL(P, Q)                                                                                          \
+    feat_kernel<float, P, Q><<<grid, kFeatThreads, sizeof(FeatSmem), s>>>(d_audio, d_offsets, d_lengths, stride_or_hop, \
+                                                                          mode, B, d_feat, d_map, h->d_tables, coef)
+    CD_FEAT_VARIANT(pre, pcen, CD_CALL);
+#undef CD_CALL
     h->launches += 1;
     CD_CUDA(h, cudaGetLastError());
     return CD_OK;
@@ -861,8 +960,14 @@ int launch_features_i16(cd_handle* h, const int16_t* d_audio, int64_t stride, in
                         __nv_bfloat16* d_map, cudaStream_t s) {
     if (B == 0) return CD_OK;
     const int64_t slots = 2 * (int64_t)h->sm_count;
-    feat_kernel<int16_t><<<(int)(B < slots ? B : slots), kFeatThreads, sizeof(FeatSmem), s>>>(
-        d_audio, nullptr, nullptr, stride, mode, B, d_feat, d_map, h->d_tables);
+    mode |= h->feat_opts;
+    const bool pre = (mode & kModePreEmph) != 0, pcen = (mode & kModePcen) != 0;
+    const float coef = h->pre_coef;
+#define CD_CALL(P, Q)                                                                                            \
+    feat_kernel<int16_t, P, Q><<<(int)(B < slots ? B : slots), kFeatThreads, sizeof(FeatSmem), s>>>(              \
+        d_audio, nullptr, nullptr, stride, mode, B, d_feat, d_map, h->d_tables, coef)
+    CD_FEAT_VARIANT(pre, pcen, CD_CALL);
+#undef CD_CALL
     h->launches += 1;
     CD_CUDA(h, cudaGetLastError());
     return CD_OK;

@@ -86,11 +86,17 @@ class CoughDetectorResidual(nn.Module):
         preds, probs, _ = h.predict(logits.to(f"cuda:{h.device}"))
         return (preds, probs) if x.is_cuda else (preds.to(x.device), probs.to(x.device))
 
-    def forward_audio(self, audio: torch.Tensor, return_features: bool = False):
-        """Additive fused entry: (B, 16000) waveforms -> logits, features never leave the GPU."""
+    def forward_audio(self, audio: torch.Tensor, return_features: bool = False, preprocessor=None):
+        """Additive fused entry: (B, 16000) waveforms -> logits, features never leave the GPU.  `preprocessor`
+        (an AudioPreprocessor) supplies the use_pre_emphasis / use_pcen options; without one the training
+        configuration (both off) is used."""
         if self.training:
             raise RuntimeError("cough_detector_b200 is inference-only: call model.eval() before forward_audio()")
         h = self._handle(audio)
+        if preprocessor is not None:
+            preprocessor._apply_options(h)
+        else:
+            h.set_feat_options()
         xd = audio.detach().to(device=f"cuda:{h.device}", dtype=torch.float32, non_blocking=True)
         out = h.e2e_forward(xd, _PREC[self.precision], return_features)
         if audio.is_cuda:

@@ -1,12 +1,13 @@
 """AudioPreprocessor / RealtimePreprocessor on the B200 feature kernel.
 
 Host-side mirror of the reference's ``src/preprocessing.py`` (class and method names, argument
-meaning, return shapes, error behaviour) for the 90-feature configuration the reference trains
-with (``src/train.py:264-287``): ``use_pcen=False, use_pre_emphasis=False,
-use_delta_delta=False, use_spectral_contrast=False``.  All feature arithmetic runs in
-``libcough_b200.so`` (csrc/feat_kernel.cu); there is no torchaudio/CPU path here.  Flag
-combinations the kernel does not implement raise ``NotImplementedError`` instead of falling
-back (the 110-feature constructor defaults are SURVEY.md §8f rank 1, "next").
+meaning, return shapes, error behaviour) for the 90-feature configurations: the one the reference
+trains with (``src/train.py:264-287``: ``use_pcen=False, use_pre_emphasis=False,
+use_delta_delta=False, use_spectral_contrast=False``) and its ``use_pre_emphasis`` / ``use_pcen``
+variants (same 90 rows, so the CNN is unchanged).  All feature arithmetic runs in
+``libcough_b200.so`` (csrc/feat_kernel.cu); there is no torchaudio/CPU path here.  ``use_delta_delta``
+and ``use_spectral_contrast`` (103 / 97 / 110 rows) raise ``NotImplementedError`` instead of falling
+back; the latter is NaN in the reference itself.
 
 Additive, batched entry points (the reference API is strictly per clip):
 ``extract_features_batch``, ``process_batch`` and ``RealtimePreprocessor.stream_features``.
@@ -40,13 +41,14 @@ class AudioPreprocessor:
             raise NotImplementedError(
                 f"the B200 feature kernel is built for {_FIXED}, segment_duration=1.0, use_mfcc=True; got {bad or ''} "
                 f"segment_duration={segment_duration} use_mfcc={use_mfcc}")
-        on = [n for n, v in (("use_pcen", use_pcen), ("use_pre_emphasis", use_pre_emphasis),
-                             ("use_delta_delta", use_delta_delta), ("use_spectral_contrast", use_spectral_contrast)) if v]
+        on = [n for n, v in (("use_delta_delta", use_delta_delta), ("use_spectral_contrast", use_spectral_contrast)) if v]
         if on:
             raise NotImplementedError(
-                f"{on} not implemented on the GPU path yet; construct with the reference training config "
-                "(use_pcen=False, use_pre_emphasis=False, use_delta_delta=False, use_spectral_contrast=False, "
-                "src/train.py:264-287).  There is deliberately no CPU fallback.")
+                f"{on} not implemented on the GPU path (they change the number of feature rows); construct with "
+                "use_delta_delta=False, use_spectral_contrast=False as the reference training config does "
+                "(src/train.py:264-287).  There is deliberately no CPU fallback.")
+        if not 0.0 <= float(pre_emphasis_coef) <= 1.0:
+            raise ValueError(f"pre_emphasis_coef must be in [0, 1], got {pre_emphasis_coef}")
         self.sample_rate, self.n_mels, self.n_fft = sample_rate, n_mels, n_fft
         self.hop_length, self.win_length, self.f_min, self.f_max = hop_length, win_length, f_min, f_max
         self.segment_duration = segment_duration
@@ -60,7 +62,12 @@ class AudioPreprocessor:
     # ---- plumbing ------------------------------------------------------------------------------
     def _gpu(self) -> "_lib.Handle":
         dev = torch.device(self.device)
-        return _lib.get_handle(dev if dev.type == "cuda" else None)
+        return self._apply_options(_lib.get_handle(dev if dev.type == "cuda" else None))
+
+    def _apply_options(self, h: "_lib.Handle") -> "_lib.Handle":
+        """Make this preprocessor's optional stages the handle's defaults (handles are shared per device)."""
+        h.set_feat_options(self.use_pre_emphasis, self.pre_emphasis_coef, self.use_pcen)
+        return h
 
     @staticmethod
     def _back(out: torch.Tensor, like: torch.Tensor) -> torch.Tensor:

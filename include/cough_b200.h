@@ -38,7 +38,9 @@ extern "C" {
 #define CD_E_STATE      -4       /* call order (e.g. CNN forward before weights were loaded) */
 #define CD_E_NOMEM      -5
 
-#define CD_FEAT_NORMALIZE 1      /* peak-normalise each clip before the features */
+#define CD_FEAT_NORMALIZE    1   /* peak-normalise each clip before the features */
+#define CD_FEAT_PRE_EMPHASIS 2   /* use_pre_emphasis: y[n] = x[n] - coef x[n-1] ahead of both feature blocks (:213-239, :452) */
+#define CD_FEAT_PCEN         4   /* use_pcen: rows 0..63 are apply_pcen + per-clip min/max (:305-340, :400-404) instead of dB */
 
 #define CD_PRECISION_FP32 0      /* direct convolution on CUDA cores, fp32 weights + activations */
 #define CD_PRECISION_BF16 1      /* implicit-GEMM tcgen05 tiles, bf16 operands, fp32 accumulate */
@@ -99,6 +101,14 @@ int cd_get_tables(float* hann, float* fb, float* dct);
  * 77..89 (:342-356). */
 int cd_feat_forward(cd_handle* h, const float* d_audio, int64_t stride, int64_t B,
                     float* d_feat, int flags, void* stream);
+
+/* Handle defaults for the two optional stages of the 90-feature path (AudioPreprocessor(use_pre_emphasis=...,
+ * pre_emphasis_coef=..., use_pcen=...), src/preprocessing.py:32-51): OR-ed into EVERY later feature launch of this handle,
+ * including the fused cd_e2e_* calls, which carry no flags of their own.  flags: CD_FEAT_PRE_EMPHASIS | CD_FEAT_PCEN or 0
+ * (the training configuration, src/train.py:264-287, and the state of a fresh handle).  use_delta_delta and
+ * use_spectral_contrast change the number of feature rows and are not built (the latter returns NaN rows in the
+ * reference itself). */
+int cd_feat_options(cd_handle* h, int flags, float pre_emphasis_coef);
 
 /* Same as cd_feat_forward for int16 PCM clips (the sample format of wav files; torchaudio.load divides by 32768,
  * which is exact in fp32 and cancels in the peak normalisation, so with CD_FEAT_NORMALIZE the features are

@@ -127,10 +127,26 @@ def pad_or_trim(w: torch.Tensor, length: int = SEGMENT) -> torch.Tensor:
 # --------------------------------------------------------------------------
 # features, fp32 explicit restatement (src/preprocessing.py:387-489)
 # --------------------------------------------------------------------------
-class Explicit32:
-    """fp32 restatement of extract_features for the 90-feature (train.py:264-287) config."""
+def pre_emphasis(w: torch.Tensor, coef: float = 0.97) -> torch.Tensor:
+    """apply_pre_emphasis (src/preprocessing.py:213-239): y[0] = x[0], y[n] = x[n] - coef * x[n-1].  (1, n)."""
+    return torch.cat([w[:, :1], w[:, 1:] - coef * w[:, :-1]], dim=1)
 
-    def __init__(self):
+
+def pcen01(mel: torch.Tensor, alpha: float = 0.98, delta: float = 2.0, r: float = 0.5, eps: float = 1e-6) -> torch.Tensor:
+    """apply_pcen (src/preprocessing.py:305-340) + the per-clip min/max scaling of extract_mel_spectrogram (:400-404).
+    (64, frames) mel POWER -> (64, frames) in [0, 1].  The smoother is avg_pool2d(kernel (1, 10), stride 1, padding
+    (0, 5)) cut back to `frames` columns: the zero-padded mean of columns t-5 .. t+4 (count_include_pad)."""
+    sm = F.avg_pool2d(mel[None, None], kernel_size=(1, 10), stride=(1, 1), padding=(0, 5))[0, 0][:, :mel.shape[1]]
+    pc = (mel / (eps + sm).pow(alpha) + delta).pow(r) - delta ** r
+    return (pc - pc.min()) / (pc.max() - pc.min() + 1e-8)
+
+
+class Explicit32:
+    """fp32 restatement of extract_features for the 90-feature configs: the training config (train.py:264-287) and,
+    additionally, its use_pre_emphasis / use_pcen variants (same 90 rows; SURVEY.md 8f rank 1, partial)."""
+
+    def __init__(self, use_pcen: bool = False, use_pre_emphasis: bool = False, pre_emphasis_coef: float = 0.97):
+        self.use_pcen, self.use_pre_emphasis, self.coef = use_pcen, use_pre_emphasis, pre_emphasis_coef
         self.win512 = torch.zeros(N_FFT)
         off = (N_FFT - WIN_LENGTH) // 2  # torch.stft centres the 400-window in 512 (offset 56)
         self.win512[off:off + WIN_LENGTH] = hann_window()
@@ -154,8 +170,14 @@ class Explicit32:
 
     def features(self, w: torch.Tensor) -> torch.Tensor:
         """(1, 16000) normalised clip -> (1, 90, frames)."""
-        db = self.to_db(self.mel_power(w))                             # :398,407 and again :425
-        mel01 = ((db + 80.0) / 80.0).clamp(0.0, 1.0)                   # :409-410
+        if self.use_pre_emphasis:
+            w = pre_emphasis(w, self.coef)                             # :452, both blocks use the emphasised signal
+        mel = self.mel_power(w)
+        db = self.to_db(mel)                                           # :398,407 and again :425
+        if self.use_pcen:
+            mel01 = pcen01(mel)                                        # :400-404
+        else:
+            mel01 = ((db + 80.0) / 80.0).clamp(0.0, 1.0)               # :409-410
         mf = (db.t() @ self.dct).t()                                   # torchaudio _transforms.py:716
         mf = (mf - mf.mean()) / (mf.std() + 1e-8)                      # :428 (unbiased std)
         pad = F.pad(mf.unsqueeze(0), (1, 1), mode="replicate").squeeze(0)
@@ -167,7 +189,7 @@ class Explicit32:
         return self.features(pad_or_trim(normalize(to_mono(w))))
 
 
-def features_fp64(w: np.ndarray) -> np.ndarray:
+def features_fp64(w: np.ndarray, use_pcen: bool = False, use_pre_emphasis: bool = False, coef: float = 0.97) -> np.ndarray:
     """float64 ground truth: (n,) raw clip -> (90, 101).  Same steps as Explicit32.process."""
     x = np.asarray(w, dtype=np.float64).reshape(-1)
     peak = np.abs(x).max() if x.size else 0.0
@@ -180,11 +202,13 @@ def features_fp64(w: np.ndarray) -> np.ndarray:
     elif n < SEGMENT:
         p = SEGMENT - n
         x = np.pad(x, (p // 2, p - p // 2))
-    return features_fp64_window(x)
+    return features_fp64_window(x, use_pcen, use_pre_emphasis, coef)
 
 
-def features_fp64_window(x: np.ndarray) -> np.ndarray:
+def features_fp64_window(x: np.ndarray, use_pcen: bool = False, use_pre_emphasis: bool = False, coef: float = 0.97) -> np.ndarray:
     """float64 features of an already conditioned 16000-sample window."""
+    if use_pre_emphasis:
+        x = np.concatenate([x[:1], x[1:] - coef * x[:-1]])
     xp = np.pad(x, (N_FFT // 2, N_FFT // 2), mode="reflect")
     nfr = (xp.size - N_FFT) // HOP_LENGTH + 1
     idx = np.arange(N_FFT)[None, :] + HOP_LENGTH * np.arange(nfr)[:, None]
@@ -198,7 +222,14 @@ def features_fp64_window(x: np.ndarray) -> np.ndarray:
     mel = power @ mel_filterbank(torch.float32).double().numpy()               # (frames, 64)
     db = 10.0 * np.log10(np.maximum(mel, AMIN))
     db = np.maximum(db, db.max() - TOP_DB)
-    mel01 = np.clip((db + 80.0) / 80.0, 0.0, 1.0).T
+    if use_pcen:
+        mp = np.pad(mel, ((5, 5), (0, 0)))                                     # (frames + 10, 64), zero padded
+        cs = np.concatenate([np.zeros((1, mel.shape[1])), np.cumsum(mp, axis=0)])
+        sm = (cs[10:10 + mel.shape[0]] - cs[:mel.shape[0]]) / 10.0             # mean of frames t-5 .. t+4
+        pc = (mel / (1e-6 + sm) ** 0.98 + 2.0) ** 0.5 - 2.0 ** 0.5
+        mel01 = ((pc - pc.min()) / (pc.max() - pc.min() + 1e-8)).T
+    else:
+        mel01 = np.clip((db + 80.0) / 80.0, 0.0, 1.0).T
     mf = (db @ dct_matrix(torch.float32).double().numpy()).T                   # (13, frames)
     mf = (mf - mf.mean()) / (mf.std(ddof=1) + 1e-8)
     pad = np.pad(mf, ((0, 0), (1, 1)), mode="edge")

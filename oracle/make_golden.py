@@ -36,7 +36,43 @@ def dequantize_clip(m: np.ndarray, scale) -> torch.Tensor:
     return torch.from_numpy(m.astype(np.float32) * np.float32(scale))
 
 
+FLAG_COMBOS = {"pre": dict(use_pcen=False, use_pre_emphasis=True), "pcen": dict(use_pcen=True, use_pre_emphasis=False),
+               "pre_pcen": dict(use_pcen=True, use_pre_emphasis=True)}
+
+
+def flag_goldens():
+    """tests/golden/features_flags.npz: the reference's process() with use_pre_emphasis / use_pcen (90 rows each) on the
+    clips of features.npz, and its RealtimePreprocessor with both flags on the stream of stream.npz (hop 0.1 s)."""
+    sys.path.insert(0, REF)
+    import torchaudio
+    from src.preprocessing import AudioPreprocessor, RealtimePreprocessor  # the reference
+
+    torch.set_num_threads(1)
+    z = np.load(os.path.join(GOLD, "features.npz"))
+    clips, o = [], 0
+    for n, sc in zip(z["lens"], z["scales"]):
+        clips.append(dequantize_clip(z["mant"][o:o + n], sc))
+        o += int(n)
+    out = {"meta": np.array([torch.__version__, torchaudio.__version__])}
+    for name, fl in FLAG_COMBOS.items():
+        pp = AudioPreprocessor(use_delta_delta=False, use_spectral_contrast=False, **fl)
+        assert pp.get_num_features() == 90
+        out[f"features_{name}"] = np.stack([pp.process(x.reshape(1, -1), 16000)[0].numpy() for x in clips]).astype(np.float32)
+    zs = np.load(os.path.join(GOLD, "stream.npz"))
+    stream = dequantize_clip(zs["mant"], zs["scale"])
+    rp = RealtimePreprocessor(window_duration=1.0, hop_duration=0.1, use_delta_delta=False, use_spectral_contrast=False,
+                              **FLAG_COMBOS["pre_pcen"])
+    got = []
+    for c in range(0, stream.numel(), 1600):
+        got += rp.add_audio(stream[c:c + 1600])
+    out["stream_pre_pcen_hop100"] = torch.stack(got).numpy()
+    np.savez_compressed(os.path.join(GOLD, "features_flags.npz"), **out)
+    print("features_flags.npz", os.path.getsize(os.path.join(GOLD, "features_flags.npz")))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "flags":
+        return flag_goldens()
     sys.path.insert(0, REF)
     import torchaudio
     from src.preprocessing import AudioPreprocessor, RealtimePreprocessor  # the reference
@@ -139,6 +175,7 @@ def main():
             probs.append(eng.predict(torch.from_numpy(f))[1])
     np.savez_compressed(os.path.join(GOLD, "engine.npz"), fired=np.array(fired), confs=np.array(confs, dtype=np.float64),
                         probs=np.array(probs, dtype=np.float64), meta=meta)
+    flag_goldens()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

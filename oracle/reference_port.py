@@ -24,7 +24,8 @@ from . import cough_oracle as co
 
 
 class PortPreprocessor:
-    def __init__(self):
+    def __init__(self, use_pcen: bool = False, use_pre_emphasis: bool = False, pre_emphasis_coef: float = 0.97):
+        self.use_pcen, self.use_pre_emphasis, self.coef = use_pcen, use_pre_emphasis, pre_emphasis_coef
         mk = dict(n_fft=co.N_FFT, win_length=co.WIN_LENGTH, hop_length=co.HOP_LENGTH,
                   n_mels=co.N_MELS, f_min=co.F_MIN, f_max=co.F_MAX)
         self.mel = T.MelSpectrogram(sample_rate=co.SAMPLE_RATE, power=2.0, normalized=False,
@@ -33,7 +34,12 @@ class PortPreprocessor:
         self.mfcc = T.MFCC(sample_rate=co.SAMPLE_RATE, n_mfcc=co.N_MFCC, melkwargs=mk)
 
     def features(self, w: torch.Tensor) -> torch.Tensor:
-        mel01 = ((self.to_db(self.mel(w)) + 80) / 80).clamp(0, 1)
+        if self.use_pre_emphasis:
+            w = co.pre_emphasis(w, self.coef)
+        if self.use_pcen:
+            mel01 = co.pcen01(self.mel(w)[0]).unsqueeze(0)
+        else:
+            mel01 = ((self.to_db(self.mel(w)) + 80) / 80).clamp(0, 1)
         mf = self.mfcc(w)
         mf = (mf - mf.mean()) / (mf.std() + 1e-8)
         pad = F.pad(mf, (1, 1), mode="replicate")

@@ -46,3 +46,10 @@ def load_resample():
             x = _deq(z[f"in_{sr}_mant"], z[f"in_{sr}_scale"]).reshape(2, -1)
             out[sr] = (x, torch.from_numpy(z[k]))
     return out
+
+
+def load_feature_flags():
+    """{"pre" | "pcen" | "pre_pcen": (32, 90, 101)} for the clips of load_features(), plus the both-flags stream case."""
+    z = np.load(os.path.join(GOLD, "features_flags.npz"))
+    return {k[len("features_"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("features_")}, \
+        torch.from_numpy(z["stream_pre_pcen_hop100"])

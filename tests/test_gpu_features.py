@@ -199,3 +199,64 @@ def test_int16_pcm_ingestion_is_bit_identical_to_float_path():
     h.load_state_dict(synth.randomized_state_dict(m, seed=1), key="i16")
     for prec in (0, 1):
         assert torch.equal(h.e2e_forward_host(pcm.pin_memory(), prec), h.e2e_forward_host(xf.pin_memory(), prec))
+
+
+COMBOS = {"pre": dict(use_pcen=False, use_pre_emphasis=True), "pcen": dict(use_pcen=True, use_pre_emphasis=False),
+          "pre_pcen": dict(use_pcen=True, use_pre_emphasis=True)}
+
+
+@pytest.mark.parametrize("name", list(COMBOS))
+def test_pre_emphasis_and_pcen_variants_vs_reference_goldens(name):
+    """use_pre_emphasis / use_pcen (the 90-row part): reference process() outputs for the golden clips."""
+    clips, base, _ = gio.load_features()
+    want, _ = gio.load_feature_flags()
+    pp = AudioPreprocessor(use_delta_delta=False, use_spectral_contrast=False, **COMBOS[name])
+    got = pp.process_batch(clips)[:, 0]
+    assert got.shape == want[name].shape and torch.isfinite(got).all()
+    worst = 0.0
+    for i, x in enumerate(clips):
+        d = (got[i] - want[name][i]).abs().max().item()
+        if _ill(x):
+            assert d <= TOL_ILL, (name, i, d)
+        else:
+            worst = max(worst, d)
+            assert d <= TOL, (name, i, len(x), d)
+    print("%s: worst well-conditioned |err| = %.3e" % (name, worst))
+    # the options live on the (shared) handle: a default preprocessor used next must get the default kernel back
+    again = AudioPreprocessor(**FLAGS).process_batch(clips[:4])[:, 0]
+    for i in range(4):
+        assert (again[i] - base[i]).abs().max().item() <= (TOL_ILL if _ill(clips[i]) else TOL)
+    assert (again - got[:4]).abs().max().item() > 1e-3
+
+
+def test_variants_stream_int16_and_fused_paths_agree():
+    """Both options through every entry point: shared-STFT stream vs the reference RealtimePreprocessor, per-window
+    stream, int16 PCM vs fp32 (bit-identical), and the fused audio -> logits call vs features -> model."""
+    from cough_detector_b200 import create_model
+    stream, _ = gio.load_stream()
+    _, ref = gio.load_feature_flags()
+    kw = dict(use_delta_delta=False, use_spectral_contrast=False, **COMBOS["pre_pcen"])
+    rp = RealtimePreprocessor(window_duration=1.0, hop_duration=0.1, **kw)
+    chunks = []
+    for c in range(0, stream.numel(), 1600):
+        chunks += rp.add_audio(stream[c:c + 1600])
+    chunks = torch.stack(chunks)
+    shared = rp.stream_features(stream)
+    assert chunks.shape == ref.shape == shared.shape
+    assert (chunks - ref).abs().max().item() <= TOL and (shared - ref).abs().max().item() <= TOL
+    h = _lib.get_handle(0)
+    pp = AudioPreprocessor(**kw)
+    x = torch.stack(synth.synth_clips(64, seed=21, fixed_length=True)).cuda()
+    pcm = (x / x.abs().amax(dim=1, keepdim=True).clamp(min=1e-9) * 32767.0).round().to(torch.int16)
+    pp._apply_options(h)
+    assert torch.equal(h.feat_forward_i16(pcm), h.feat_forward(pcm.float() / 32768.0))
+    f = h.feat_forward(x)
+    m = create_model("residual").eval()
+    m.load_state_dict(synth.randomized_state_dict(m, seed=3))
+    fused, ffeat = m.forward_audio(x, return_features=True, preprocessor=pp)
+    assert torch.equal(ffeat, f)
+    pp._apply_options(h)
+    assert torch.equal(fused, m(f))
+    plain = m.forward_audio(x)                               # no preprocessor: the training configuration again
+    assert torch.equal(plain, m(AudioPreprocessor(**FLAGS).extract_features_batch(x)))
+    assert (plain - fused).abs().max().item() > 1e-3

@@ -60,6 +60,13 @@ def test_preprocessor_surface_and_errors():
         AudioPreprocessor()                      # reference defaults = 110-feature config: not built, no fallback
     with pytest.raises(NotImplementedError):
         AudioPreprocessor(n_mels=80, **FLAGS)
+    for bad in (dict(use_delta_delta=True), dict(use_spectral_contrast=True)):      # they change the row count
+        with pytest.raises(NotImplementedError):
+            AudioPreprocessor(**{**FLAGS, **bad})
+    both = AudioPreprocessor(**{**FLAGS, "use_pcen": True, "use_pre_emphasis": True, "pre_emphasis_coef": 0.95})
+    assert both.get_num_features() == 90 and both.use_pcen and both.use_pre_emphasis and both.pre_emphasis_coef == 0.95
+    with pytest.raises(ValueError):
+        AudioPreprocessor(**{**FLAGS, "use_pre_emphasis": True, "pre_emphasis_coef": 1.5})
     with pytest.raises(ValueError):
         pp.resample(torch.zeros(1, 10), 44100.5)
     assert pp.resample(torch.ones(1, 4), 16000).shape == (1, 4)

@@ -113,3 +113,24 @@ def test_resample_is_bit_identical_to_reference():
         got = co.resample(x, sr)
         assert got.shape == ref.shape and torch.equal(got, ref), sr
     assert co.resample(torch.ones(1, 5), 16000) .shape == (1, 5)
+
+
+def test_pre_emphasis_and_pcen_oracles_match_reference_goldens():
+    """features_flags.npz (reference process() with use_pre_emphasis / use_pcen): the port is bit-identical, the explicit
+    fp32 restatement within 2e-6, float64 within 1e-4 on well-conditioned clips."""
+    from oracle.reference_port import PortPreprocessor
+    clips, _, _ = gio.load_features()
+    want, stream_ref = gio.load_feature_flags()
+    combos = {"pre": (False, True), "pcen": (True, False), "pre_pcen": (True, True)}
+    for name, (pcen, pre) in combos.items():
+        port, ex = PortPreprocessor(pcen, pre), co.Explicit32(pcen, pre)
+        for i in range(0, len(clips), 3):
+            x = clips[i].reshape(1, -1)
+            assert torch.equal(port.process(x)[0], want[name][i]), (name, i)
+            assert (ex.process(x)[0] - want[name][i]).abs().max().item() <= 2e-6, (name, i)
+            if co.ill_conditioned_fraction(co.conditioned_window(clips[i].numpy())) == 0:
+                d = np.abs(co.features_fp64(clips[i].numpy(), pcen, pre) - want[name][i].numpy()).max()
+                assert d <= 1e-4, (name, i, d)
+    stream, _ = gio.load_stream()
+    got = co.stream_features(stream, 1600, co.Explicit32(True, True))
+    assert got.shape == stream_ref.shape and (got - stream_ref).abs().max().item() <= 2e-6

@@ -21,6 +21,17 @@ for prec in (0, 1):
     lg = h.e2e_forward(x, prec)
     lg2 = h.cnn_forward(f2, prec)
     ls = h.e2e_forward_stream(s.cuda(), 1600, prec)
+for opts in (dict(use_pcen=True, use_pre_emphasis=False), dict(use_pcen=False, use_pre_emphasis=True),
+             dict(use_pcen=True, use_pre_emphasis=True)):        # the optional stages, every entry point again
+    kw = dict(use_delta_delta=False, use_spectral_contrast=False, **opts)
+    po = AudioPreprocessor(**kw)
+    g1 = po.process_batch(clips)
+    g2 = po.extract_features_batch(x)
+    g3 = RealtimePreprocessor(window_duration=1.0, hop_duration=0.1, **kw).stream_features(s)
+    g4 = RealtimePreprocessor(window_duration=1.0, hop_duration=0.0485625, **kw).stream_features(s[:20000])
+    g5 = m.forward_audio(x, preprocessor=po)
+    assert all(torch.isfinite(t).all() for t in (g1, g2, g3, g4, g5))
+h.set_feat_options()
 host = h.e2e_forward_host(x.cpu().pin_memory(), 1)
 d = h.selftest_umma(torch.randn(128 + 9, 128), torch.randn(64, 128), 9, 0)
 torch.cuda.synchronize()
