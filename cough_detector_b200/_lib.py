@@ -22,6 +22,8 @@ PRECISION_BF16 = 1
 FEAT_NORMALIZE = 1
 FEAT_PRE_EMPHASIS = 2
 FEAT_PCEN = 4
+FEAT_DELTA_DELTA = 8
+N_FEATURES_DD = 103
 
 _f32p = C.POINTER(C.c_float)
 
@@ -136,13 +138,20 @@ class Handle:
         return int(self.lib.cd_launch_count(self._h))
 
     # ---- features ---------------------------------------------------------------------------
-    def set_feat_options(self, use_pre_emphasis: bool = False, pre_emphasis_coef: float = 0.97, use_pcen: bool = False):
-        """Handle defaults for every later feature launch (cd_feat_options); (False, ., False) is the training config."""
-        key = (bool(use_pre_emphasis), float(pre_emphasis_coef), bool(use_pcen))
-        if getattr(self, "_feat_opts", (False, 0.97, False)) != key:
-            flags = (FEAT_PRE_EMPHASIS if key[0] else 0) | (FEAT_PCEN if key[2] else 0)
+    def set_feat_options(self, use_pre_emphasis: bool = False, pre_emphasis_coef: float = 0.97, use_pcen: bool = False,
+                         use_delta_delta: bool = False):
+        """Handle defaults for every later feature launch (cd_feat_options); all off is the training config.
+        use_delta_delta makes the feature calls return 103 rows and the fused audio -> logits calls fail."""
+        key = (bool(use_pre_emphasis), float(pre_emphasis_coef), bool(use_pcen), bool(use_delta_delta))
+        if getattr(self, "_feat_opts", (False, 0.97, False, False)) != key:
+            flags = (FEAT_PRE_EMPHASIS if key[0] else 0) | (FEAT_PCEN if key[2] else 0) | (FEAT_DELTA_DELTA if key[3] else 0)
             self._check(self.lib.cd_feat_options(self._h, flags, key[1]), "cd_feat_options")
             self._feat_opts = key
+
+    @property
+    def n_features(self) -> int:
+        """Feature rows the handle's current options produce (90, or 103 with use_delta_delta)."""
+        return N_FEATURES_DD if getattr(self, "_feat_opts", (False, 0.97, False, False))[3] else N_FEATURES
 
     def feat_forward(self, audio: torch.Tensor, normalize: bool = True) -> torch.Tensor:
         """(B, 16000) cuda fp32 -> (B, 1, 90, 101)."""
@@ -150,7 +159,7 @@ class Handle:
         if audio.dim() != 2 or audio.shape[1] != SEGMENT:
             raise CoughB200Error(f"audio must be (B, {SEGMENT}), got {tuple(audio.shape)}")
         B = audio.shape[0]
-        out = torch.empty(B, 1, N_FEATURES, N_FRAMES, device=audio.device, dtype=torch.float32)
+        out = torch.empty(B, 1, self.n_features, N_FRAMES, device=audio.device, dtype=torch.float32)
         self._check(self.lib.cd_feat_forward(self._h, _ptr(audio), SEGMENT, B, _ptr(out), 1 if normalize else 0, self._stream()), "cd_feat_forward")
         return out
 
@@ -160,7 +169,7 @@ class Handle:
             raise CoughB200Error("feat_forward_i16 wants a cuda int16 (B, 16000) tensor")
         audio = audio.contiguous()
         B = audio.shape[0]
-        out = torch.empty(B, 1, N_FEATURES, N_FRAMES, device=audio.device, dtype=torch.float32)
+        out = torch.empty(B, 1, self.n_features, N_FRAMES, device=audio.device, dtype=torch.float32)
         self._check(self.lib.cd_feat_forward_i16(self._h, _ptr(audio), SEGMENT, B, _ptr(out), 1 if normalize else 0,
                                                  self._stream()), "cd_feat_forward_i16")
         return out
@@ -170,7 +179,7 @@ class Handle:
         offsets = offsets.to(device=flat.device, dtype=torch.int64).contiguous()
         lengths = lengths.to(device=flat.device, dtype=torch.int32).contiguous()
         B = offsets.numel()
-        out = torch.empty(B, 1, N_FEATURES, N_FRAMES, device=flat.device, dtype=torch.float32)
+        out = torch.empty(B, 1, self.n_features, N_FRAMES, device=flat.device, dtype=torch.float32)
         self._check(self.lib.cd_feat_forward_var(self._h, _ptr(flat), _ptr(offsets), _ptr(lengths), B, _ptr(out),
                                                  self._stream()), "cd_feat_forward_var")
         return out
@@ -182,7 +191,7 @@ class Handle:
         audio = self._dev_f32(audio.reshape(-1), "audio")
         n = audio.numel()
         nw = self.stream_windows(n, hop)
-        out = torch.empty(nw, 1, N_FEATURES, N_FRAMES, device=audio.device, dtype=torch.float32)
+        out = torch.empty(nw, 1, self.n_features, N_FRAMES, device=audio.device, dtype=torch.float32)
         self._check(self.lib.cd_feat_forward_stream(self._h, _ptr(audio), n, hop, nw, _ptr(out), self._stream()),
                     "cd_feat_forward_stream")
         return out

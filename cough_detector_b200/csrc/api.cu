@@ -167,13 +167,13 @@ int cd_destroy(cd_handle* h) {
 
 static int feat_mode_bits(int flags) {
     return ((flags & CD_FEAT_NORMALIZE) ? 0 : kModeNoNormalize) | ((flags & CD_FEAT_PRE_EMPHASIS) ? kModePreEmph : 0) |
-           ((flags & CD_FEAT_PCEN) ? kModePcen : 0);
+           ((flags & CD_FEAT_PCEN) ? kModePcen : 0) | ((flags & CD_FEAT_DELTA_DELTA) ? kModeDeltaDelta : 0);
 }
 
 int cd_feat_options(cd_handle* h, int flags, float pre_emphasis_coef) {
     if (!h) return CD_E_ARG;
-    if (flags & ~(CD_FEAT_PRE_EMPHASIS | CD_FEAT_PCEN))
-        return set_err(h, CD_E_ARG, "cd_feat_options: only CD_FEAT_PRE_EMPHASIS and CD_FEAT_PCEN can be made handle defaults");
+    if (flags & ~(CD_FEAT_PRE_EMPHASIS | CD_FEAT_PCEN | CD_FEAT_DELTA_DELTA))
+        return set_err(h, CD_E_ARG, "cd_feat_options: flags are CD_FEAT_PRE_EMPHASIS | CD_FEAT_PCEN | CD_FEAT_DELTA_DELTA");
     if (!(pre_emphasis_coef >= 0.f && pre_emphasis_coef <= 1.f))
         return set_err(h, CD_E_ARG, "cd_feat_options: pre_emphasis_coef must be in [0, 1]");
     h->feat_opts = feat_mode_bits(flags | CD_FEAT_NORMALIZE);
@@ -332,6 +332,8 @@ int cd_predict(cd_handle* h, const float* d_logits, int64_t B, float threshold, 
 static int e2e_impl(cd_handle* h, const float* d_audio, int64_t stride_or_hop, int mode, int64_t B, float* d_logits,
                     float* d_feat_opt, int precision, cudaStream_t s) {
     if (!h->weights_loaded) return set_err(h, CD_E_STATE, "cd_e2e_forward: call cd_cnn_load first");
+    if (h->feat_opts & kModeDeltaDelta)
+        return set_err(h, CD_E_ARG, "use_delta_delta (103 feature rows) is a features-only option: the CNN kernels take 90 rows");
     if (B == 0) return CD_OK;
     // process in slabs so a slab's features stay L2-resident between the two stages.  bf16: the
     // feature kernel writes the stem's bf16 map straight into the CNN workspace (fp32 features only
@@ -396,6 +398,8 @@ static int e2e_host_impl(cd_handle* h, const void* h_audio, bool i16, int64_t B,
     if (!h) return CD_E_ARG;
     if (B < 0 || (B > 0 && (!h_audio || !h_logits))) return set_err(h, CD_E_ARG, "cd_e2e_forward_host: bad argument");
     if (!h->weights_loaded) return set_err(h, CD_E_STATE, "cd_e2e_forward_host: call cd_cnn_load first");
+    if (h->feat_opts & kModeDeltaDelta)
+        return set_err(h, CD_E_ARG, "use_delta_delta (103 feature rows) is a features-only option: the CNN kernels take 90 rows");
     if (precision != CD_PRECISION_FP32 && precision != CD_PRECISION_BF16)
         return set_err(h, CD_E_ARG, "precision must be CD_PRECISION_FP32 or CD_PRECISION_BF16");
     if (B == 0) return CD_OK;

@@ -119,6 +119,8 @@ int launch_cnn_fp32(cd_handle* h, const float* d_feat, int64_t B, float* d_logit
 size_t cnn_fp32_ws_bytes(int64_t B);
 
 enum FeatMode { kModeFixed = 0, kModeVar = 1, kModeStream = 2, kModeMask = 3, kModeNoNormalize = 4,
-                kModePreEmph = 8, kModePcen = 16 };
+                kModePreEmph = 8, kModePcen = 16, kModeDeltaDelta = 32 };
+constexpr int kFeatDD     = CD_N_FEATURES + 13;            // 103 rows with use_delta_delta (features only)
+constexpr int kFeatElemDD = kFeatDD * 101;
 
 }  // namespace cd

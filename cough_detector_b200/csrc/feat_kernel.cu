@@ -448,8 +448,10 @@ __device__ __forceinline__ float mfcc_par(const float* __restrict__ db, float* _
 // PCEN = true : the tile holds mel POWER, `top` is its block max; rows 0..63 are apply_pcen (src/preprocessing.py:
 //               305-340) scaled to [0, 1] by the clip's min / max (:400-404); the MFCC rows still come from the dB.
 // Ends with the block in sync except for the final stores.
+// dd: also emit the delta-delta rows 90..102 = compute_deltas(compute_deltas(mfcc)) (:463-466; fp32 output only).
 template <bool PCEN, class SM>
-__device__ __forceinline__ void feat_tail(SM& S, float top, float* __restrict__ out, __nv_bfloat16* __restrict__ mo, int tid) {
+__device__ __forceinline__ void feat_tail(SM& S, float top, float* __restrict__ out, __nv_bfloat16* __restrict__ mo, int tid,
+                                          bool dd = false) {
     const float floor_db = (PCEN ? power_to_db(top) : top) - 80.0f;    // top_db = 80
 
     if (!PCEN) {
@@ -499,6 +501,11 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float* __restrict__ 
             if (out) {
                 out[(kMels + cidx) * kFrames + t] = x0;
                 out[(kMels + kMfcc + cidx) * kFrames + t] = dl;
+                if (dd) {
+                    auto xn = [&](int u) { return __fmul_rn(row[min(max(u, 0), kFrames - 1)] - mean, inv_std); };
+                    auto d1 = [&](int u) { u = min(max(u, 0), kFrames - 1); return (xn(u + 1) - xn(u - 1)) * 0.5f; };
+                    out[(kMels + 2 * kMfcc + cidx) * kFrames + t] = (d1(t + 1) - d1(t - 1)) * 0.5f;
+                }
             }
             if (mo) {
                 mo[bmap_offset(kMels + cidx + 3, t + 3)] = __float2bfloat16_rn(x0);
@@ -684,8 +691,9 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
         if (feat) feat[b * (int64_t)kFeatElem + tid] = top + S.db[tid * 25];
         if (map_out) map_out[b * (int64_t)kMapElems + tid] = __float2bfloat16_rn(top + S.db[tid * 25]);
 #else
-        feat_tail<PCEN>(S, top, feat ? feat + b * (int64_t)kFeatElem : nullptr,
-                        map_out ? map_out + b * (int64_t)kMapElems : nullptr, tid);
+        const bool dd = (mode & kModeDeltaDelta) != 0;
+        feat_tail<PCEN>(S, top, feat ? feat + b * (int64_t)(dd ? kFeatElemDD : kFeatElem) : nullptr,
+                        map_out ? map_out + b * (int64_t)kMapElems : nullptr, tid, dd);
 #endif
         __syncthreads();                                               // xb / db free again
     }
@@ -778,7 +786,7 @@ template <bool PRE, bool PCEN>
 __global__ void __launch_bounds__(kFeatThreads, 2)
 stream_window_kernel(const float* __restrict__ audio, int64_t hop, int64_t n_windows, const float* __restrict__ melp,
                      const float* __restrict__ bmax, float* __restrict__ feat, __nv_bfloat16* __restrict__ map_out,
-                     const FeatTables* __restrict__ tables, float coef) {
+                     const FeatTables* __restrict__ tables, float coef, int dd) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     StreamSmem& S = *reinterpret_cast<StreamSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -810,8 +818,8 @@ stream_window_kernel(const float* __restrict__ audio, int64_t hop, int64_t n_win
                 wmax = fmaxf(wmax, d);
             }
         }
-        feat_tail<PCEN>(S, block_reduce<true>(wmax, S.red), feat ? feat + j * (int64_t)kFeatElem : nullptr,
-                        map_out ? map_out + j * (int64_t)kMapElems : nullptr, tid);
+        feat_tail<PCEN>(S, block_reduce<true>(wmax, S.red), feat ? feat + j * (int64_t)(dd ? kFeatElemDD : kFeatElem) : nullptr,
+                        map_out ? map_out + j * (int64_t)kMapElems : nullptr, tid, dd != 0);
         __syncthreads();
     }
 }
@@ -908,6 +916,8 @@ int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets
                     int64_t stride_or_hop, int mode, int64_t B, float* d_feat, __nv_bfloat16* d_map, cudaStream_t s) {
     if (B == 0) return CD_OK;
     mode |= h->feat_opts;
+    if ((mode & kModeDeltaDelta) && (d_map || !d_feat))
+        return set_err(h, CD_E_ARG, "use_delta_delta (103 feature rows) is a features-only option: the CNN kernels take 90 rows");
     const bool pre = (mode & kModePreEmph) != 0, pcen = (mode & kModePcen) != 0;
     const float coef = h->pre_coef;
     const int64_t slots = 2 * (int64_t)h->sm_count;     // two resident CTAs per SM
@@ -937,7 +947,7 @@ int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets
             stream_mel_kernel<false><<<mel_grid, kFeatThreads, sizeof(MelSmem), s>>>(d_audio, F, melp, h->d_tables, coef);
 #define CD_CALL(P, Q)                                                                                   \
     stream_window_kernel<P, Q><<<(int)(B < slots ? B : slots), kFeatThreads, sizeof(StreamSmem), s>>>(   \
-        d_audio, hop, B, melp, bmax, d_feat, d_map, h->d_tables, coef)
+        d_audio, hop, B, melp, bmax, d_feat, d_map, h->d_tables, coef, (mode & kModeDeltaDelta) ? 1 : 0)
         CD_FEAT_VARIANT(pre, pcen, CD_CALL);
 #undef CD_CALL
         h->launches += 3;
@@ -961,6 +971,8 @@ int launch_features_i16(cd_handle* h, const int16_t* d_audio, int64_t stride, in
     if (B == 0) return CD_OK;
     const int64_t slots = 2 * (int64_t)h->sm_count;
     mode |= h->feat_opts;
+    if ((mode & kModeDeltaDelta) && (d_map || !d_feat))
+        return set_err(h, CD_E_ARG, "use_delta_delta (103 feature rows) is a features-only option: the CNN kernels take 90 rows");
     const bool pre = (mode & kModePreEmph) != 0, pcen = (mode & kModePcen) != 0;
     const float coef = h->pre_coef;
 #define CD_CALL(P, Q)                                                                                            \

@@ -74,6 +74,9 @@ class CoughDetectorResidual(nn.Module):
             raise RuntimeError("cough_detector_b200 is inference-only: call model.eval() before forward()")
         if self.precision not in _PREC:
             raise ValueError(f"precision must be one of {list(_PREC)}, got {self.precision!r}")
+        if x.dim() == 4 and x.shape[2] != _lib.N_FEATURES:
+            raise NotImplementedError(f"the B200 CNN kernels are built for {_lib.N_FEATURES} feature rows, got {x.shape[2]} "
+                                      "(use_delta_delta / use_spectral_contrast inputs have no kernels; no fallback)")
         h = self._handle(x)
         xd = x.detach().to(device=f"cuda:{h.device}", dtype=torch.float32, non_blocking=True)
         logits = h.cnn_forward(xd, _PREC[self.precision])

@@ -4,10 +4,11 @@ Host-side mirror of the reference's ``src/preprocessing.py`` (class and method n
 meaning, return shapes, error behaviour) for the 90-feature configurations: the one the reference
 trains with (``src/train.py:264-287``: ``use_pcen=False, use_pre_emphasis=False,
 use_delta_delta=False, use_spectral_contrast=False``) and its ``use_pre_emphasis`` / ``use_pcen``
-variants (same 90 rows, so the CNN is unchanged).  All feature arithmetic runs in
-``libcough_b200.so`` (csrc/feat_kernel.cu); there is no torchaudio/CPU path here.  ``use_delta_delta``
-and ``use_spectral_contrast`` (103 / 97 / 110 rows) raise ``NotImplementedError`` instead of falling
-back; the latter is NaN in the reference itself.
+variants (same 90 rows, so the CNN is unchanged), plus ``use_delta_delta`` as a features-only option
+(103 rows: for feature caching / training pipelines; the CNN kernels take 90 rows).  All feature
+arithmetic runs in ``libcough_b200.so`` (csrc/feat_kernel.cu); there is no torchaudio/CPU path here.
+``use_spectral_contrast`` raises ``NotImplementedError`` instead of falling back; its rows are NaN in
+the reference itself.
 
 Additive, batched entry points (the reference API is strictly per clip):
 ``extract_features_batch``, ``process_batch`` and ``RealtimePreprocessor.stream_features``.
@@ -41,11 +42,10 @@ class AudioPreprocessor:
             raise NotImplementedError(
                 f"the B200 feature kernel is built for {_FIXED}, segment_duration=1.0, use_mfcc=True; got {bad or ''} "
                 f"segment_duration={segment_duration} use_mfcc={use_mfcc}")
-        on = [n for n, v in (("use_delta_delta", use_delta_delta), ("use_spectral_contrast", use_spectral_contrast)) if v]
-        if on:
+        if use_spectral_contrast:
             raise NotImplementedError(
-                f"{on} not implemented on the GPU path (they change the number of feature rows); construct with "
-                "use_delta_delta=False, use_spectral_contrast=False as the reference training config does "
+                "use_spectral_contrast is not implemented on the GPU path (and its rows are NaN in the reference itself: "
+                "DESIGN.md §6); construct with use_spectral_contrast=False as the reference training config does "
                 "(src/train.py:264-287).  There is deliberately no CPU fallback.")
         if not 0.0 <= float(pre_emphasis_coef) <= 1.0:
             raise ValueError(f"pre_emphasis_coef must be in [0, 1], got {pre_emphasis_coef}")
@@ -66,7 +66,7 @@ class AudioPreprocessor:
 
     def _apply_options(self, h: "_lib.Handle") -> "_lib.Handle":
         """Make this preprocessor's optional stages the handle's defaults (handles are shared per device)."""
-        h.set_feat_options(self.use_pre_emphasis, self.pre_emphasis_coef, self.use_pcen)
+        h.set_feat_options(self.use_pre_emphasis, self.pre_emphasis_coef, self.use_pcen, self.use_delta_delta)
         return h
 
     @staticmethod
@@ -149,7 +149,7 @@ class AudioPreprocessor:
     def process_batch(self, waveforms: Sequence[torch.Tensor], orig_sr: int = 16000) -> torch.Tensor:
         """Variable-length clips [(C_i, n_i) or (n_i,)] -> (B, 1, 90, 101); per clip identical to ``process``."""
         if not len(waveforms):
-            return torch.zeros(0, 1, _lib.N_FEATURES, _lib.N_FRAMES)
+            return torch.zeros(0, 1, self.get_num_features(), _lib.N_FRAMES)
         h = self._gpu()
         dev = f"cuda:{h.device}"
         mono = []

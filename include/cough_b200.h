@@ -41,6 +41,9 @@ extern "C" {
 #define CD_FEAT_NORMALIZE    1   /* peak-normalise each clip before the features */
 #define CD_FEAT_PRE_EMPHASIS 2   /* use_pre_emphasis: y[n] = x[n] - coef x[n-1] ahead of both feature blocks (:213-239, :452) */
 #define CD_FEAT_PCEN         4   /* use_pcen: rows 0..63 are apply_pcen + per-clip min/max (:305-340, :400-404) instead of dB */
+#define CD_FEAT_DELTA_DELTA  8   /* use_delta_delta: 13 more rows, compute_deltas(compute_deltas(mfcc)) (:463-466): d_feat is
+                                    B x 103 x 101.  Features only -- the CNN entry points take 90 rows and refuse this option. */
+#define CD_N_FEATURES_DD 103
 
 #define CD_PRECISION_FP32 0      /* direct convolution on CUDA cores, fp32 weights + activations */
 #define CD_PRECISION_BF16 1      /* implicit-GEMM tcgen05 tiles, bf16 operands, fp32 accumulate */
@@ -104,10 +107,10 @@ int cd_feat_forward(cd_handle* h, const float* d_audio, int64_t stride, int64_t 
 
 /* Handle defaults for the two optional stages of the 90-feature path (AudioPreprocessor(use_pre_emphasis=...,
  * pre_emphasis_coef=..., use_pcen=...), src/preprocessing.py:32-51): OR-ed into EVERY later feature launch of this handle,
- * including the fused cd_e2e_* calls, which carry no flags of their own.  flags: CD_FEAT_PRE_EMPHASIS | CD_FEAT_PCEN or 0
- * (the training configuration, src/train.py:264-287, and the state of a fresh handle).  use_delta_delta and
- * use_spectral_contrast change the number of feature rows and are not built (the latter returns NaN rows in the
- * reference itself). */
+ * including the fused cd_e2e_* calls, which carry no flags of their own.  flags: any of CD_FEAT_PRE_EMPHASIS,
+ * CD_FEAT_PCEN, CD_FEAT_DELTA_DELTA, or 0 (the training configuration, src/train.py:264-287, and the state of a fresh
+ * handle).  With CD_FEAT_DELTA_DELTA every feature call writes 103 rows per clip and the cd_e2e_* calls fail with
+ * CD_E_ARG.  use_spectral_contrast is not built (it returns NaN rows in the reference itself). */
 int cd_feat_options(cd_handle* h, int flags, float pre_emphasis_coef);
 
 /* Same as cd_feat_forward for int16 PCM clips (the sample format of wav files; torchaudio.load divides by 32768,

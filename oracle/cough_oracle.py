@@ -145,8 +145,10 @@ class Explicit32:
     """fp32 restatement of extract_features for the 90-feature configs: the training config (train.py:264-287) and,
     additionally, its use_pre_emphasis / use_pcen variants (same 90 rows; SURVEY.md 8f rank 1, partial)."""
 
-    def __init__(self, use_pcen: bool = False, use_pre_emphasis: bool = False, pre_emphasis_coef: float = 0.97):
+    def __init__(self, use_pcen: bool = False, use_pre_emphasis: bool = False, pre_emphasis_coef: float = 0.97,
+                 use_delta_delta: bool = False):
         self.use_pcen, self.use_pre_emphasis, self.coef = use_pcen, use_pre_emphasis, pre_emphasis_coef
+        self.use_delta_delta = use_delta_delta
         self.win512 = torch.zeros(N_FFT)
         off = (N_FFT - WIN_LENGTH) // 2  # torch.stft centres the 400-window in 512 (offset 56)
         self.win512[off:off + WIN_LENGTH] = hann_window()
@@ -182,14 +184,19 @@ class Explicit32:
         mf = (mf - mf.mean()) / (mf.std() + 1e-8)                      # :428 (unbiased std)
         pad = F.pad(mf.unsqueeze(0), (1, 1), mode="replicate").squeeze(0)
         delta = (pad[:, 2:] - pad[:, :-2]) / 2                         # :353-355
-        return torch.cat([mel01, mf, delta], dim=0).unsqueeze(0)      # :487
+        rows = [mel01, mf, delta]
+        if self.use_delta_delta:                                       # :463-466: deltas of the deltas
+            pad2 = F.pad(delta.unsqueeze(0), (1, 1), mode="replicate").squeeze(0)
+            rows.append((pad2[:, 2:] - pad2[:, :-2]) / 2)
+        return torch.cat(rows, dim=0).unsqueeze(0)                     # :487
 
     def process(self, w: torch.Tensor) -> torch.Tensor:
         """normalize -> pad_or_trim -> extract_features (src/preprocessing.py:508-515, 16 kHz mono)."""
         return self.features(pad_or_trim(normalize(to_mono(w))))
 
 
-def features_fp64(w: np.ndarray, use_pcen: bool = False, use_pre_emphasis: bool = False, coef: float = 0.97) -> np.ndarray:
+def features_fp64(w: np.ndarray, use_pcen: bool = False, use_pre_emphasis: bool = False, coef: float = 0.97,
+                  use_delta_delta: bool = False) -> np.ndarray:
     """float64 ground truth: (n,) raw clip -> (90, 101).  Same steps as Explicit32.process."""
     x = np.asarray(w, dtype=np.float64).reshape(-1)
     peak = np.abs(x).max() if x.size else 0.0
@@ -202,10 +209,11 @@ def features_fp64(w: np.ndarray, use_pcen: bool = False, use_pre_emphasis: bool 
     elif n < SEGMENT:
         p = SEGMENT - n
         x = np.pad(x, (p // 2, p - p // 2))
-    return features_fp64_window(x, use_pcen, use_pre_emphasis, coef)
+    return features_fp64_window(x, use_pcen, use_pre_emphasis, coef, use_delta_delta)
 
 
-def features_fp64_window(x: np.ndarray, use_pcen: bool = False, use_pre_emphasis: bool = False, coef: float = 0.97) -> np.ndarray:
+def features_fp64_window(x: np.ndarray, use_pcen: bool = False, use_pre_emphasis: bool = False, coef: float = 0.97,
+                         use_delta_delta: bool = False) -> np.ndarray:
     """float64 features of an already conditioned 16000-sample window."""
     if use_pre_emphasis:
         x = np.concatenate([x[:1], x[1:] - coef * x[:-1]])
@@ -234,7 +242,11 @@ def features_fp64_window(x: np.ndarray, use_pcen: bool = False, use_pre_emphasis
     mf = (mf - mf.mean()) / (mf.std(ddof=1) + 1e-8)
     pad = np.pad(mf, ((0, 0), (1, 1)), mode="edge")
     delta = (pad[:, 2:] - pad[:, :-2]) / 2
-    return np.concatenate([mel01, mf, delta], axis=0)
+    rows = [mel01, mf, delta]
+    if use_delta_delta:
+        pad2 = np.pad(delta, ((0, 0), (1, 1)), mode="edge")
+        rows.append((pad2[:, 2:] - pad2[:, :-2]) / 2)
+    return np.concatenate(rows, axis=0)
 
 
 def ill_conditioned_fraction(x: np.ndarray, rel: float = 1e-9) -> float:

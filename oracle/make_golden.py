@@ -58,6 +58,14 @@ def flag_goldens():
         pp = AudioPreprocessor(use_delta_delta=False, use_spectral_contrast=False, **fl)
         assert pp.get_num_features() == 90
         out[f"features_{name}"] = np.stack([pp.process(x.reshape(1, -1), 16000)[0].numpy() for x in clips]).astype(np.float32)
+    # use_delta_delta: rows 0..89 are the 90-row features again (checked here), so only rows 90..102 are stored
+    for name, fl in (("dd", dict(use_pcen=False, use_pre_emphasis=False)), ("pre_pcen_dd", FLAG_COMBOS["pre_pcen"])):
+        pp = AudioPreprocessor(use_delta_delta=True, use_spectral_contrast=False, **fl)
+        assert pp.get_num_features() == 103
+        full = np.stack([pp.process(x.reshape(1, -1), 16000)[0].numpy() for x in clips]).astype(np.float32)
+        base = z["features"] if name == "dd" else out["features_pre_pcen"]
+        assert np.array_equal(full[:, :90], base)
+        out[f"ddrows_{name}"] = full[:, 90:]
     zs = np.load(os.path.join(GOLD, "stream.npz"))
     stream = dequantize_clip(zs["mant"], zs["scale"])
     rp = RealtimePreprocessor(window_duration=1.0, hop_duration=0.1, use_delta_delta=False, use_spectral_contrast=False,

@@ -24,8 +24,10 @@ from . import cough_oracle as co
 
 
 class PortPreprocessor:
-    def __init__(self, use_pcen: bool = False, use_pre_emphasis: bool = False, pre_emphasis_coef: float = 0.97):
+    def __init__(self, use_pcen: bool = False, use_pre_emphasis: bool = False, pre_emphasis_coef: float = 0.97,
+                 use_delta_delta: bool = False):
         self.use_pcen, self.use_pre_emphasis, self.coef = use_pcen, use_pre_emphasis, pre_emphasis_coef
+        self.use_delta_delta = use_delta_delta
         mk = dict(n_fft=co.N_FFT, win_length=co.WIN_LENGTH, hop_length=co.HOP_LENGTH,
                   n_mels=co.N_MELS, f_min=co.F_MIN, f_max=co.F_MAX)
         self.mel = T.MelSpectrogram(sample_rate=co.SAMPLE_RATE, power=2.0, normalized=False,
@@ -44,7 +46,11 @@ class PortPreprocessor:
         mf = (mf - mf.mean()) / (mf.std() + 1e-8)
         pad = F.pad(mf, (1, 1), mode="replicate")
         delta = (pad[:, :, 2:] - pad[:, :, :-2]) / 2
-        return torch.cat([mel01, mf, delta], dim=1)
+        rows = [mel01, mf, delta]
+        if self.use_delta_delta:
+            pad2 = F.pad(delta, (1, 1), mode="replicate")
+            rows.append((pad2[:, :, 2:] - pad2[:, :, :-2]) / 2)
+        return torch.cat(rows, dim=1)
 
     def process(self, w: torch.Tensor) -> torch.Tensor:
         return self.features(co.pad_or_trim(co.normalize(co.to_mono(w))))

@@ -53,3 +53,9 @@ def load_feature_flags():
     z = np.load(os.path.join(GOLD, "features_flags.npz"))
     return {k[len("features_"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("features_")}, \
         torch.from_numpy(z["stream_pre_pcen_hop100"])
+
+
+def load_delta_delta_rows():
+    """{"dd" | "pre_pcen_dd": (32, 13, 101)}: rows 90..102 of the reference's 103-row output (rows 0..89 equal the 90-row case)."""
+    z = np.load(os.path.join(GOLD, "features_flags.npz"))
+    return {k[len("ddrows_"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("ddrows_")}

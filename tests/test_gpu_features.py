@@ -260,3 +260,34 @@ def test_variants_stream_int16_and_fused_paths_agree():
     plain = m.forward_audio(x)                               # no preprocessor: the training configuration again
     assert torch.equal(plain, m(AudioPreprocessor(**FLAGS).extract_features_batch(x)))
     assert (plain - fused).abs().max().item() > 1e-3
+
+
+@pytest.mark.parametrize("name", ["dd", "pre_pcen_dd"])
+def test_delta_delta_rows_vs_reference_goldens(name):
+    """use_delta_delta is a features-only option (103 rows): rows 90..102 against the reference, rows 0..89 unchanged,
+    and the CNN entry points refuse it instead of reading a 103-row tensor as 90 rows."""
+    from cough_detector_b200 import create_model
+    clips, base, _ = gio.load_features()
+    flags, _ = gio.load_feature_flags()
+    want90 = base if name == "dd" else flags["pre_pcen"]
+    want = gio.load_delta_delta_rows()[name]
+    kw = dict(use_spectral_contrast=False, use_delta_delta=True, use_pcen=name != "dd", use_pre_emphasis=name != "dd")
+    pp = AudioPreprocessor(**kw)
+    assert pp.get_num_features() == 103
+    got = pp.process_batch(clips)[:, 0]
+    assert got.shape == (len(clips), 103, 101) and torch.isfinite(got).all()
+    for i, x in enumerate(clips):
+        tol = TOL_ILL if _ill(x) else TOL
+        assert (got[i, :90] - want90[i]).abs().max().item() <= tol, (name, i)
+        assert (got[i, 90:] - want[i]).abs().max().item() <= tol, (name, i)
+    fixed = torch.stack(synth.synth_clips(8, seed=2, fixed_length=True))
+    one = pp.extract_features_batch(fixed)
+    rt = RealtimePreprocessor(window_duration=1.0, hop_duration=0.1, **kw).stream_features(torch.cat(list(fixed[:3])))
+    assert one.shape == (8, 1, 103, 101) and rt.shape[1:] == (1, 103, 101)
+    m = create_model("residual").eval()
+    with pytest.raises(NotImplementedError):
+        m(one.cuda())
+    with pytest.raises(_lib.CoughB200Error):
+        m.forward_audio(fixed.cuda(), preprocessor=pp)
+    # and the handle goes back to 90 rows for the next default user
+    assert AudioPreprocessor(**FLAGS).extract_features_batch(fixed).shape == (8, 1, 90, 101)

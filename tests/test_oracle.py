@@ -134,3 +134,21 @@ def test_pre_emphasis_and_pcen_oracles_match_reference_goldens():
     stream, _ = gio.load_stream()
     got = co.stream_features(stream, 1600, co.Explicit32(True, True))
     assert got.shape == stream_ref.shape and (got - stream_ref).abs().max().item() <= 2e-6
+
+
+def test_delta_delta_oracles_match_reference_goldens():
+    from oracle.reference_port import PortPreprocessor
+    clips, base, _ = gio.load_features()
+    ddrows = gio.load_delta_delta_rows()
+    for name, (pcen, pre) in {"dd": (False, False), "pre_pcen_dd": (True, True)}.items():
+        port, ex = PortPreprocessor(pcen, pre, use_delta_delta=True), co.Explicit32(pcen, pre, use_delta_delta=True)
+        for i in range(0, len(clips), 4):
+            x = clips[i].reshape(1, -1)
+            p = port.process(x)[0]
+            assert p.shape == (103, 101) and torch.equal(p[90:], ddrows[name][i]), (name, i)
+            if name == "dd":
+                assert torch.equal(p[:90], base[i])
+            assert (ex.process(x)[0][90:] - ddrows[name][i]).abs().max().item() <= 2e-6
+            if co.ill_conditioned_fraction(co.conditioned_window(clips[i].numpy())) == 0:
+                d = np.abs(co.features_fp64(clips[i].numpy(), pcen, pre, use_delta_delta=True)[90:] - ddrows[name][i].numpy()).max()
+                assert d <= 1e-4, (name, i, d)
