@@ -183,6 +183,26 @@ __device__ __forceinline__ float block_reduce(float v, float* red) {
     return r;
 }
 
+// Sum of a float2 over the block; every thread gets the result.  `red` needs >= 16 floats.
+__device__ __forceinline__ float2 block_reduce_sum2(float2 v, float* red) {
+    v.x = warp_sum(v.x);
+    v.y = warp_sum(v.y);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        red[warp] = v.x;
+        red[kFeatWarps + warp] = v.y;
+    }
+    __syncthreads();
+    float a = red[lane & (kFeatWarps - 1)], b = red[kFeatWarps + (lane & (kFeatWarps - 1))];
+#pragma unroll
+    for (int o = kFeatWarps / 2; o; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    __syncthreads();
+    return make_float2(a, b);
+}
+
 // AmplitudeToDB('power'): 10 log10(max(x, 1e-10)) (torchaudio functional.py:390) via MUFU.LG2
 __device__ __forceinline__ float power_to_db(float x) {
     return 3.01029995663981195f * __log2f(fmaxf(x, 1e-10f));      // 10 * log10(2) * log2(x)
@@ -416,8 +436,9 @@ __device__ __forceinline__ float frame_pair(SM& S, const T* __restrict__ clip, f
 // PAR = 1: c = 1,3,..,11).  cos(pi (m + 1/2) c / 64) is even (c even) or odd (c odd) about m = 31.5, so
 // each coefficient is a 32-term sum over d[m] +- d[63 - m], shared by all coefficients of that parity.
 // POWER: the tile holds mel power (PCEN variant); dB and its top_db floor are applied on the way in.
+// Returns {sum, sum of squares} of the coefficients it wrote (the block's mean / std come from one reduction).
 template <int PAR, bool POWER>
-__device__ __forceinline__ float mfcc_par(const float* __restrict__ db, float* __restrict__ mf, int t, float floor_db) {
+__device__ __forceinline__ float2 mfcc_par(const float* __restrict__ db, float* __restrict__ mf, int t, float floor_db) {
     constexpr int NC = PAR ? 6 : 7;
     float acc[NC];
 #pragma unroll
@@ -433,13 +454,14 @@ __device__ __forceinline__ float mfcc_par(const float* __restrict__ db, float* _
 #pragma unroll
         for (int i = 0; i < NC; ++i) acc[i] = fmaf(c_dct[(PAR + 2 * i) * kMels + m], d, acc[i]);
     }
-    float s = 0.f;
+    float s = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
         mf[(PAR + 2 * i) * kFrames + t] = acc[i];
         s += acc[i];
+        s2 = fmaf(acc[i], acc[i], s2);
     }
-    return s;
+    return make_float2(s, s2);
 }
 
 // Everything after the tile is complete: top_db floor, mel rows, DCT-13, mean / unbiased std
@@ -474,21 +496,19 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float* __restrict__ 
 
     // ---- MFCC = DCT-II(13 x 64) of the floored dB, then (x - mean) / (std + 1e-8) ---------------
     float* mf = reinterpret_cast<float*>(&S.xb[0][0]);             // [13][101], FFT scratch is idle now
-    float part = 0.f;
+    float2 part = make_float2(0.f, 0.f);
     {
         static_assert(kFeatThreads == 256, "two parity groups of 128 threads");
         const int t = tid & 127;
         if (t < kFrames) part = (tid >> 7) ? mfcc_par<1, PCEN>(S.db, mf, t, floor_db) : mfcc_par<0, PCEN>(S.db, mf, t, floor_db);
     }
+    // mean and unbiased variance from one reduction of {sum, sum of squares}: |mean| is a fraction of the spread
+    // here (c0 dominates both), so the one-pass form loses nothing in fp32 (checked against float64 on the goldens)
     constexpr int kN = kMfcc * kFrames;                            // 1313
-    const float mean = block_reduce<false>(part, S.red) * (1.0f / kN);
-    float ss = 0.f;
-    for (int i = tid; i < kN; i += kFeatThreads) {
-        const float dlt = mf[i] - mean;
-        ss = fmaf(dlt, dlt, ss);
-    }
-    ss = block_reduce<false>(ss, S.red);
-    const float inv_std = 1.0f / (sqrtf(ss * (1.0f / (kN - 1))) + 1e-8f);
+    const float2 tot = block_reduce_sum2(part, S.red);
+    const float mean = tot.x * (1.0f / kN);
+    const float var = fmaxf(tot.y - tot.x * mean, 0.f) * (1.0f / (kN - 1));
+    const float inv_std = 1.0f / (sqrtf(var) + 1e-8f);
     {
         for (int i = tid; i < kN; i += kFeatThreads) {
             const int cidx = i / kFrames, t = i - cidx * kFrames;
