@@ -55,6 +55,7 @@ SYMBOLS = {
     "cd_resample": (_I, [_VP, _VP, _I64, _I64, _I, _I, _VP, _VP]),
     "cd_cnn_load": (_I, [_VP, C.POINTER(_ResidualWeights)]),
     "cd_cnn_forward": (_I, [_VP, _VP, _I64, _VP, _I, _VP]),
+    "cd_cnn_forward_rows": (_I, [_VP, _VP, _I, _I64, _VP, _I, _VP]),
     "cd_predict": (_I, [_VP, _VP, _I64, C.c_float, _VP, _VP, _VP, _VP]),
     "cd_e2e_forward": (_I, [_VP, _VP, _I64, _I64, _VP, _VP, _I, _VP]),
     "cd_e2e_forward_stream": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _I, _VP]),
@@ -141,7 +142,7 @@ class Handle:
     def set_feat_options(self, use_pre_emphasis: bool = False, pre_emphasis_coef: float = 0.97, use_pcen: bool = False,
                          use_delta_delta: bool = False):
         """Handle defaults for every later feature launch (cd_feat_options); all off is the training config.
-        use_delta_delta makes the feature calls return 103 rows and the fused audio -> logits calls fail."""
+        use_delta_delta makes the feature calls return 103 rows and the fused audio -> logits calls run the 103-row network."""
         key = (bool(use_pre_emphasis), float(pre_emphasis_coef), bool(use_pcen), bool(use_delta_delta))
         if getattr(self, "_feat_opts", (False, 0.97, False, False)) != key:
             flags = (FEAT_PRE_EMPHASIS if key[0] else 0) | (FEAT_PCEN if key[2] else 0) | (FEAT_DELTA_DELTA if key[3] else 0)
@@ -244,11 +245,12 @@ class Handle:
         feat = self._dev_f32(feat, "features")
         if feat.dim() == 3:
             feat = feat.unsqueeze(0)
-        if tuple(feat.shape[1:]) != (1, N_FEATURES, N_FRAMES):
-            raise CoughB200Error(f"features must be (B, 1, {N_FEATURES}, {N_FRAMES}), got {tuple(feat.shape)}")
-        B = feat.shape[0]
+        if feat.dim() != 4 or feat.shape[1] != 1 or feat.shape[2] not in (N_FEATURES, N_FEATURES_DD) or feat.shape[3] != N_FRAMES:
+            raise CoughB200Error(f"features must be (B, 1, {N_FEATURES} | {N_FEATURES_DD}, {N_FRAMES}), got {tuple(feat.shape)}")
+        B, rows = feat.shape[0], int(feat.shape[2])
         logits = torch.empty(B, 2, device=feat.device, dtype=torch.float32)
-        self._check(self.lib.cd_cnn_forward(self._h, _ptr(feat), B, _ptr(logits), precision, self._stream()), "cd_cnn_forward")
+        self._check(self.lib.cd_cnn_forward_rows(self._h, _ptr(feat), rows, B, _ptr(logits), precision, self._stream()),
+                    "cd_cnn_forward_rows")
         return logits
 
     def predict(self, logits: torch.Tensor, threshold: float = 0.5):
@@ -279,7 +281,7 @@ class Handle:
             raise CoughB200Error(f"audio must be (B, {SEGMENT}), got {tuple(audio.shape)}")
         B = audio.shape[0]
         logits = torch.empty(B, 2, device=audio.device, dtype=torch.float32)
-        feat = torch.empty(B, 1, N_FEATURES, N_FRAMES, device=audio.device, dtype=torch.float32) if return_features else None
+        feat = torch.empty(B, 1, self.n_features, N_FRAMES, device=audio.device, dtype=torch.float32) if return_features else None
         self._check(self.lib.cd_e2e_forward(self._h, _ptr(audio), SEGMENT, B, _ptr(logits), _ptr(feat), precision,
                                             self._stream()), "cd_e2e_forward")
         return (logits, feat) if return_features else logits

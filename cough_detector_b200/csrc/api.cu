@@ -39,10 +39,10 @@ int build_feat_tables(cd_handle* h);
 int init_cnn_fp32(cd_handle* h);
 int init_cnn_tc(cd_handle* h);
 int upload_cnn_tc(cd_handle* h, const std::vector<std::vector<float>>& wf, const std::vector<std::vector<float>>& bf);
-int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, cudaStream_t s);
+int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, cudaStream_t s, int nf = kFeat);
 size_t cnn_tc_ws_bytes(int64_t B);
 __nv_bfloat16* cnn_tc_map_ptr(cd_handle* h);
-int ensure_tc_ws(cd_handle* h);
+int ensure_tc_ws(cd_handle* h, int nf = kFeat);
 int launch_features_i16(cd_handle* h, const int16_t* d_audio, int64_t stride, int mode, int64_t B, float* d_feat,
                         __nv_bfloat16* d_map, cudaStream_t s);
 int64_t resample_length(int64_t n_in, int orig_sr, int new_sr);
@@ -289,18 +289,20 @@ int cd_cnn_load(cd_handle* h, const cd_residual_weights* w) {
     return CD_OK;
 }
 
-static int cnn_forward_impl(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, int precision,
+static int cnn_forward_impl(cd_handle* h, const float* d_feat, int n_rows, int64_t B, float* d_logits, int precision,
                             cudaStream_t s) {
     if (!h->weights_loaded) return set_err(h, CD_E_STATE, "cd_cnn_forward: call cd_cnn_load first");
+    if (n_rows != kFeat && n_rows != kFeatDD)
+        return set_err(h, CD_E_ARG, "cd_cnn_forward: the network is built for 90 or 103 (use_delta_delta) feature rows");
     if (precision == CD_PRECISION_FP32) {
         int rc = ensure_ws(h, cnn_fp32_ws_bytes(B));
         if (rc != CD_OK) return rc;
-        return launch_cnn_fp32(h, d_feat, B, d_logits, s);
+        return launch_cnn_fp32(h, d_feat, B, d_logits, s, n_rows);
     }
     if (precision == CD_PRECISION_BF16) {
         int rc = ensure_ws(h, cnn_tc_ws_bytes(B));
         if (rc != CD_OK) return rc;
-        return launch_cnn_tc(h, d_feat, B, d_logits, s);
+        return launch_cnn_tc(h, d_feat, B, d_logits, s, n_rows);
     }
     return set_err(h, CD_E_ARG, "precision must be CD_PRECISION_FP32 or CD_PRECISION_BF16");
 }
@@ -309,7 +311,15 @@ int cd_cnn_forward(cd_handle* h, const float* d_feat, int64_t B, float* d_logits
     if (!h) return CD_E_ARG;
     if (B < 0 || (B > 0 && (!d_feat || !d_logits))) return set_err(h, CD_E_ARG, "cd_cnn_forward: bad argument");
     DeviceGuard g(h->device);
-    return cnn_forward_impl(h, d_feat, B, d_logits, precision, (cudaStream_t)stream);
+    return cnn_forward_impl(h, d_feat, kFeat, B, d_logits, precision, (cudaStream_t)stream);
+}
+
+int cd_cnn_forward_rows(cd_handle* h, const float* d_feat, int n_rows, int64_t B, float* d_logits, int precision,
+                        void* stream) {
+    if (!h) return CD_E_ARG;
+    if (B < 0 || (B > 0 && (!d_feat || !d_logits))) return set_err(h, CD_E_ARG, "cd_cnn_forward_rows: bad argument");
+    DeviceGuard g(h->device);
+    return cnn_forward_impl(h, d_feat, n_rows, B, d_logits, precision, (cudaStream_t)stream);
 }
 
 int cd_predict(cd_handle* h, const float* d_logits, int64_t B, float threshold, float* d_probs, int64_t* d_preds,
@@ -332,28 +342,28 @@ int cd_predict(cd_handle* h, const float* d_logits, int64_t B, float threshold, 
 static int e2e_impl(cd_handle* h, const float* d_audio, int64_t stride_or_hop, int mode, int64_t B, float* d_logits,
                     float* d_feat_opt, int precision, cudaStream_t s) {
     if (!h->weights_loaded) return set_err(h, CD_E_STATE, "cd_e2e_forward: call cd_cnn_load first");
-    if (h->feat_opts & kModeDeltaDelta)
-        return set_err(h, CD_E_ARG, "use_delta_delta (103 feature rows) is a features-only option: the CNN kernels take 90 rows");
     if (B == 0) return CD_OK;
+    const int nf = (h->feat_opts & kModeDeltaDelta) ? kFeatDD : kFeat;      // shape family of this handle's features
+    const int64_t felems = (int64_t)nf * kFrames;
     // process in slabs so a slab's features stay L2-resident between the two stages.  bf16: the
     // feature kernel writes the stem's bf16 map straight into the CNN workspace (fp32 features only
     // if the caller asked for them); fp32: features go through an fp32 buffer.
     const int64_t slab = 16384;
     const bool tcp = precision == CD_PRECISION_BF16;
     const size_t cnn_ws = tcp ? cnn_tc_ws_bytes(slab) : cnn_fp32_ws_bytes(slab);
-    const size_t feat_bytes = (tcp || d_feat_opt) ? 0 : (size_t)slab * kFeatElem * sizeof(float);
+    const size_t feat_bytes = (tcp || d_feat_opt) ? 0 : (size_t)slab * felems * sizeof(float);
     int rc = ensure_ws(h, cnn_ws + feat_bytes);
-    if (rc == CD_OK && tcp) rc = ensure_tc_ws(h);
+    if (rc == CD_OK && tcp) rc = ensure_tc_ws(h, nf);
     if (rc != CD_OK) return rc;
     for (int64_t b0 = 0; b0 < B; b0 += slab) {
         const int64_t n = (B - b0) < slab ? (B - b0) : slab;
-        float* feat = d_feat_opt ? d_feat_opt + b0 * kFeatElem
+        float* feat = d_feat_opt ? d_feat_opt + b0 * felems
                                  : (tcp ? nullptr : reinterpret_cast<float*>(reinterpret_cast<char*>(h->d_ws) + cnn_ws));
         rc = launch_features(h, d_audio + b0 * stride_or_hop, nullptr, nullptr, stride_or_hop, mode, n, feat,
                              tcp ? cnn_tc_map_ptr(h) : nullptr, s);
         if (rc != CD_OK) return rc;
-        rc = tcp ? launch_cnn_tc(h, nullptr, n, d_logits + b0 * CD_N_CLASSES, s)
-                 : launch_cnn_fp32(h, feat, n, d_logits + b0 * CD_N_CLASSES, s);
+        rc = tcp ? launch_cnn_tc(h, nullptr, n, d_logits + b0 * CD_N_CLASSES, s, nf)
+                 : launch_cnn_fp32(h, feat, n, d_logits + b0 * CD_N_CLASSES, s, nf);
         if (rc != CD_OK) return rc;
     }
     return CD_OK;
@@ -398,8 +408,7 @@ static int e2e_host_impl(cd_handle* h, const void* h_audio, bool i16, int64_t B,
     if (!h) return CD_E_ARG;
     if (B < 0 || (B > 0 && (!h_audio || !h_logits))) return set_err(h, CD_E_ARG, "cd_e2e_forward_host: bad argument");
     if (!h->weights_loaded) return set_err(h, CD_E_STATE, "cd_e2e_forward_host: call cd_cnn_load first");
-    if (h->feat_opts & kModeDeltaDelta)
-        return set_err(h, CD_E_ARG, "use_delta_delta (103 feature rows) is a features-only option: the CNN kernels take 90 rows");
+    const int nf = (h->feat_opts & kModeDeltaDelta) ? kFeatDD : kFeat;
     if (precision != CD_PRECISION_FP32 && precision != CD_PRECISION_BF16)
         return set_err(h, CD_E_ARG, "precision must be CD_PRECISION_FP32 or CD_PRECISION_BF16");
     if (B == 0) return CD_OK;
@@ -423,8 +432,8 @@ static int e2e_host_impl(cd_handle* h, const void* h_audio, bool i16, int64_t B,
     // is the caller's buffer pinned?  (pageable memory is staged by the driver; still correct)
     const bool tcp = precision == CD_PRECISION_BF16;
     const size_t cnn_ws = tcp ? cnn_tc_ws_bytes(chunk) : cnn_fp32_ws_bytes(chunk);
-    int rc = ensure_ws(h, cnn_ws + (tcp ? 0 : (size_t)chunk * kFeatElem * sizeof(float)));
-    if (rc == CD_OK && tcp) rc = ensure_tc_ws(h);
+    int rc = ensure_ws(h, cnn_ws + (tcp ? 0 : (size_t)chunk * nf * kFrames * sizeof(float)));
+    if (rc == CD_OK && tcp) rc = ensure_tc_ws(h, nf);
     if (rc != CD_OK) return rc;
     float* feat = tcp ? nullptr : reinterpret_cast<float*>(reinterpret_cast<char*>(h->d_ws) + cnn_ws);
     int k = 0;
@@ -441,8 +450,8 @@ static int e2e_host_impl(cd_handle* h, const void* h_audio, bool i16, int64_t B,
                  : launch_features(h, h->dev_in[k], nullptr, nullptr, kSeg, kModeFixed, n, feat,
                                    tcp ? cnn_tc_map_ptr(h) : nullptr, s);
         if (rc != CD_OK) return rc;
-        rc = tcp ? launch_cnn_tc(h, nullptr, n, h->dev_logits + b0 * CD_N_CLASSES, s)
-                 : launch_cnn_fp32(h, feat, n, h->dev_logits + b0 * CD_N_CLASSES, s);
+        rc = tcp ? launch_cnn_tc(h, nullptr, n, h->dev_logits + b0 * CD_N_CLASSES, s, nf)
+                 : launch_cnn_fp32(h, feat, n, h->dev_logits + b0 * CD_N_CLASSES, s, nf);
         if (rc != CD_OK) return rc;
         CD_CUDA(h, cudaEventRecord(h->pipe_events[k], s));
         prev_compute = h->pipe_events[k];

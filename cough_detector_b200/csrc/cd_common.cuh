@@ -19,6 +19,8 @@ constexpr int kMels     = 64;
 constexpr int kMfcc     = 13;
 constexpr int kFeat     = CD_N_FEATURES; // 90
 constexpr int kFeatElem = CD_FEAT_ELEMS; // 9090
+constexpr int kFeatDD     = CD_N_FEATURES_DD;   // 103 rows with use_delta_delta
+constexpr int kFeatElemDD = kFeatDD * 101;
 constexpr int kNfft     = 512;
 constexpr int kWin      = 400;
 constexpr int kHop      = 160;
@@ -52,6 +54,23 @@ struct FeatTables {                 // lives in device global memory, copied to 
     int    melb[2][32];             // first bin of the lane's lo / hi segment | (bins in it) << 8
 };
 
+// Spatial shapes of the network for NF feature rows (101 frames): 90 (the training configuration and its
+// pre-emphasis / PCEN variants) or 103 (use_delta_delta).  The width chain 101 -> 25 -> 13 -> 7 is fixed.
+template <int NF>
+struct NetShape {
+    static_assert(NF == kFeat || NF == kFeatDD, "90 or 103 feature rows");
+    static constexpr int H0 = ((NF - 1) / 2 + 1) / 2;     // stem: 7x7/s2 pad 3, then 2x2 max-pool (floor)   22 | 26
+    static constexpr int H1 = (H0 - 1) / 2 + 1;           // block 0 (3x3/s2 pad 1)                          11 | 13
+    static constexpr int H2 = (H1 - 1) / 2 + 1;           // block 1                                          6 | 7
+    static constexpr int W0 = 25, W1 = 13, W2 = 7;
+    static constexpr int BA = H0 + 2;                     // 4x4-pixel block rows of the stem's map          24 | 28
+    static constexpr int BROWS = (BA * kBmapB + 7) & ~7;  // operand rows per clip, a multiple of 8 so that the SWIZZLE_32B
+                                                          // pattern (row bit 2) is the same for every clip      648 | 760
+    static constexpr int MAP_ELEMS = BROWS * 16;
+    static constexpr int FEAT_ELEMS = NF * kFrames;
+};
+static_assert(NetShape<kFeat>::BA == kBmapA && NetShape<kFeat>::MAP_ELEMS == kMapElems, "90-row shapes");
+
 // Folded network, fp32 (CUDA-core path).  Layouts chosen for the direct-conv kernels:
 // weights [k*k*cin][cout] (cout fastest) so a warp reads them as broadcast float4s.
 struct CnnWeightsF32 {
@@ -82,6 +101,7 @@ struct cd_handle {
     cd::CnnWeightsF32 w32{};
     __nv_bfloat16* d_wblob_bf16 = nullptr;
     unsigned char* d_ws_tc = nullptr;    // tensor-core path activations (fixed layout, zero-initialised pads)
+    int tc_plan_nf = 0;                  // shape family (feature rows) that layout was zeroed for
 
     float* d_ws_stream = nullptr;        // shared-STFT streaming: mel power of the global frames + block maxima
     size_t ws_stream_bytes = 0;
@@ -115,12 +135,10 @@ int ensure_ws(cd_handle* h, size_t bytes);
 // kernels' host launchers (each returns a CD_* code and bumps h->launches)
 int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets, const int32_t* d_lengths,
                     int64_t stride_or_hop, int mode, int64_t B, float* d_feat, __nv_bfloat16* d_map, cudaStream_t s);
-int launch_cnn_fp32(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, cudaStream_t s);
+int launch_cnn_fp32(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, cudaStream_t s, int nf = kFeat);
 size_t cnn_fp32_ws_bytes(int64_t B);
 
 enum FeatMode { kModeFixed = 0, kModeVar = 1, kModeStream = 2, kModeMask = 3, kModeNoNormalize = 4,
                 kModePreEmph = 8, kModePcen = 16, kModeDeltaDelta = 32 };
-constexpr int kFeatDD     = CD_N_FEATURES + 13;            // 103 rows with use_delta_delta (features only)
-constexpr int kFeatElemDD = kFeatDD * 101;
 
 }  // namespace cd

@@ -19,22 +19,30 @@ constexpr int kCnnThreads = 256;
 // ---------------------------------------------------------------------------------------------
 // stem: 7x7 stride 2 pad 3, 1 -> 32, ReLU, MaxPool2d(2) (floor mode: conv row 44 / col 50 unused)
 // ---------------------------------------------------------------------------------------------
-constexpr int kStemRows = 94;      // input rows -3 .. 89 (+1 so the weight table after it stays 16-byte aligned)
 constexpr int kStemPitch = 106;    // input cols -3 .. 101 (+1)
-constexpr int kPoolH = 22, kPoolW = 25;
+constexpr int kPoolW = 25;
+template <int NF>
+struct StemF32 {
+    static constexpr int POOLH = NetShape<NF>::H0;
+    static constexpr int ROWS = (4 * POOLH + 5 + 1) & ~1; // rows 4 py + ky + 2 (second pool row) <= 4 POOLH + 4; even, so the
+                                                          // weight table after the tile stays 16-byte aligned (94 | 110)
+    static constexpr size_t SMEM = (size_t)(ROWS * kStemPitch + 49 * 32) * 4;
+};
 
+template <int NF>
 __global__ void __launch_bounds__(kCnnThreads)
 stem_kernel(const float* __restrict__ feat, const float* __restrict__ w /*[49][32]*/, const float* __restrict__ bias,
-            float* __restrict__ x0 /*[B][32][22][25]*/) {
+            float* __restrict__ x0 /*[B][32][H0][25]*/) {
+    constexpr int kStemRows = StemF32<NF>::ROWS, kPoolH = StemF32<NF>::POOLH;
     extern __shared__ __align__(16) float sm[];
-    float* tile = sm;                                   // [93][106]
+    float* tile = sm;                                   // [ROWS][106]
     float* ws = sm + kStemRows * kStemPitch;            // [49][32]
     const int tid = threadIdx.x;
     const int64_t b = blockIdx.x;
-    const float* f = feat + b * (int64_t)kFeatElem;
+    const float* f = feat + b * (int64_t)NetShape<NF>::FEAT_ELEMS;
     for (int i = tid; i < kStemRows * kStemPitch; i += kCnnThreads) {
         const int r = i / kStemPitch - 3, c = i % kStemPitch - 3;
-        tile[i] = (r >= 0 && r < kFeat && c >= 0 && c < kFrames) ? f[r * kFrames + c] : 0.f;
+        tile[i] = (r >= 0 && r < NF && c >= 0 && c < kFrames) ? f[r * kFrames + c] : 0.f;
     }
     for (int i = tid; i < 49 * 32; i += kCnnThreads) ws[i] = w[i];
     __syncthreads();
@@ -189,13 +197,21 @@ conv3x3_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
 }
 
 // per-clip fp32 workspace (floats)
-constexpr int64_t kX0 = 32 * 22 * 25, kH1 = 64 * 11 * 13, kH2 = 128 * 6 * 7;
-constexpr int64_t kWsPerClip = kX0 + 3 * kH1 + 2 * kH2;
+template <int NF>
+struct PlanF32 {
+    using N = NetShape<NF>;
+    static constexpr int64_t X0 = 32 * N::H0 * N::W0, H1 = 64 * N::H1 * N::W1, H2 = 128 * N::H2 * N::W2;
+    static constexpr int64_t PER_CLIP = X0 + 3 * H1 + 2 * H2;
+    static constexpr size_t smA0 = (size_t)(32 * (N::H0 + 2) * (N::W0 + 2)) * 4;
+    static constexpr size_t smB0 = (size_t)(64 * (N::H1 + 2) * (N::W1 + 2)) * 4;
+    static constexpr size_t smA1 = (size_t)(64 * (N::H1 + 2) * (N::W1 + 2)) * 4;
+    static constexpr size_t smB1 = (size_t)(128 * (N::H2 + 2) * (N::W2 + 2) + 128 * N::H2 * N::W2) * 4;
+};
 constexpr int64_t kCnnChunk = 4096;
 
 size_t cnn_fp32_ws_bytes(int64_t B) {
     const int64_t n = B < kCnnChunk ? B : kCnnChunk;
-    return (size_t)(n * kWsPerClip) * sizeof(float);
+    return (size_t)(n * PlanF32<kFeatDD>::PER_CLIP) * sizeof(float);       // the larger of the two shapes
 }
 
 template <typename K>
@@ -203,48 +219,57 @@ static cudaError_t opt_in_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-static constexpr size_t smStem = (size_t)(kStemRows * kStemPitch + 49 * 32) * 4;
-static constexpr size_t smA0 = (size_t)(32 * 24 * 27) * 4;
-static constexpr size_t smB0 = (size_t)(64 * 13 * 15) * 4;
-static constexpr size_t smA1 = (size_t)(64 * 13 * 15) * 4;
-static constexpr size_t smB1 = (size_t)(128 * 8 * 9 + 128 * 42) * 4;
-
-// per-device function attributes (called from cd_create with the device current)
-int init_cnn_fp32(cd_handle* h) {
-    CD_CUDA(h, opt_in_smem(stem_kernel, smStem));
-    CD_CUDA(h, opt_in_smem(conv3x3_kernel<32, 64, 22, 25, 2, true, false, false>, smA0));
-    CD_CUDA(h, opt_in_smem(conv3x3_kernel<64, 64, 11, 13, 1, false, true, false>, smB0));
-    CD_CUDA(h, opt_in_smem(conv3x3_kernel<64, 128, 11, 13, 2, true, false, false>, smA1));
-    CD_CUDA(h, opt_in_smem(conv3x3_kernel<128, 128, 6, 7, 1, false, true, true>, smB1));
+template <int NF>
+static int init_cnn_fp32_nf(cd_handle* h) {
+    using N = NetShape<NF>;
+    using P = PlanF32<NF>;
+    CD_CUDA(h, opt_in_smem(stem_kernel<NF>, StemF32<NF>::SMEM));
+    CD_CUDA(h, opt_in_smem(conv3x3_kernel<32, 64, N::H0, N::W0, 2, true, false, false>, P::smA0));
+    CD_CUDA(h, opt_in_smem(conv3x3_kernel<64, 64, N::H1, N::W1, 1, false, true, false>, P::smB0));
+    CD_CUDA(h, opt_in_smem(conv3x3_kernel<64, 128, N::H1, N::W1, 2, true, false, false>, P::smA1));
+    CD_CUDA(h, opt_in_smem(conv3x3_kernel<128, 128, N::H2, N::W2, 1, false, true, true>, P::smB1));
     return CD_OK;
 }
 
-int launch_cnn_fp32(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, cudaStream_t s) {
-    if (B == 0) return CD_OK;
-    auto kA0 = conv3x3_kernel<32, 64, 22, 25, 2, true, false, false>;
-    auto kB0 = conv3x3_kernel<64, 64, 11, 13, 1, false, true, false>;
-    auto kA1 = conv3x3_kernel<64, 128, 11, 13, 2, true, false, false>;
-    auto kB1 = conv3x3_kernel<128, 128, 6, 7, 1, false, true, true>;
+// per-device function attributes (called from cd_create with the device current)
+int init_cnn_fp32(cd_handle* h) {
+    const int rc = init_cnn_fp32_nf<kFeat>(h);
+    return rc != CD_OK ? rc : init_cnn_fp32_nf<kFeatDD>(h);
+}
+
+template <int NF>
+static int launch_cnn_fp32_nf(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, cudaStream_t s) {
+    using N = NetShape<NF>;
+    using P = PlanF32<NF>;
+    auto kA0 = conv3x3_kernel<32, 64, N::H0, N::W0, 2, true, false, false>;
+    auto kB0 = conv3x3_kernel<64, 64, N::H1, N::W1, 1, false, true, false>;
+    auto kA1 = conv3x3_kernel<64, 128, N::H1, N::W1, 2, true, false, false>;
+    auto kB1 = conv3x3_kernel<128, 128, N::H2, N::W2, 1, false, true, true>;
     const CnnWeightsF32& W = h->w32;
     for (int64_t c0 = 0; c0 < B; c0 += kCnnChunk) {
         const int64_t n = (B - c0) < kCnnChunk ? (B - c0) : kCnnChunk;
         float* x0 = h->d_ws;
-        float* h1 = x0 + n * kX0;
-        float* i1 = h1 + n * kH1;
-        float* x1 = i1 + n * kH1;
-        float* h2 = x1 + n * kH1;
-        float* i2 = h2 + n * kH2;
+        float* h1 = x0 + n * P::X0;
+        float* i1 = h1 + n * P::H1;
+        float* x1 = i1 + n * P::H1;
+        float* h2 = x1 + n * P::H1;
+        float* i2 = h2 + n * P::H2;
         const int g = (int)n;
-        stem_kernel<<<g, kCnnThreads, smStem, s>>>(d_feat + c0 * kFeatElem, W.stem_w, W.stem_b, x0);
-        kA0<<<g, kCnnThreads, smA0, s>>>(x0, W.b0c1_w, W.b0c1_b, W.b0sk_w, W.b0sk_b, nullptr, h1, i1, nullptr, nullptr, nullptr);
-        kB0<<<g, kCnnThreads, smB0, s>>>(h1, W.b0c2_w, W.b0c2_b, nullptr, nullptr, i1, x1, nullptr, nullptr, nullptr, nullptr);
-        kA1<<<g, kCnnThreads, smA1, s>>>(x1, W.b1c1_w, W.b1c1_b, W.b1sk_w, W.b1sk_b, nullptr, h2, i2, nullptr, nullptr, nullptr);
-        kB1<<<g, kCnnThreads, smB1, s>>>(h2, W.b1c2_w, W.b1c2_b, nullptr, nullptr, i2, nullptr, nullptr, W.fc_w, W.fc_b,
-                                         d_logits + c0 * CD_N_CLASSES);
+        stem_kernel<NF><<<g, kCnnThreads, StemF32<NF>::SMEM, s>>>(d_feat + c0 * N::FEAT_ELEMS, W.stem_w, W.stem_b, x0);
+        kA0<<<g, kCnnThreads, P::smA0, s>>>(x0, W.b0c1_w, W.b0c1_b, W.b0sk_w, W.b0sk_b, nullptr, h1, i1, nullptr, nullptr, nullptr);
+        kB0<<<g, kCnnThreads, P::smB0, s>>>(h1, W.b0c2_w, W.b0c2_b, nullptr, nullptr, i1, x1, nullptr, nullptr, nullptr, nullptr);
+        kA1<<<g, kCnnThreads, P::smA1, s>>>(x1, W.b1c1_w, W.b1c1_b, W.b1sk_w, W.b1sk_b, nullptr, h2, i2, nullptr, nullptr, nullptr);
+        kB1<<<g, kCnnThreads, P::smB1, s>>>(h2, W.b1c2_w, W.b1c2_b, nullptr, nullptr, i2, nullptr, nullptr, W.fc_w, W.fc_b,
+                                           d_logits + c0 * CD_N_CLASSES);
         h->launches += 5;
         CD_CUDA(h, cudaGetLastError());
     }
     return CD_OK;
+}
+
+int launch_cnn_fp32(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, cudaStream_t s, int nf) {
+    if (B == 0) return CD_OK;
+    return nf == kFeatDD ? launch_cnn_fp32_nf<kFeatDD>(h, d_feat, B, d_logits, s) : launch_cnn_fp32_nf<kFeat>(h, d_feat, B, d_logits, s);
 }
 
 }  // namespace cd

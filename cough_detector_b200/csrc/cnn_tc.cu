@@ -908,17 +908,20 @@ conv3x3_s2_tc_kernel(const S2Args a) {
 // clip as exactly those blocks (cd_common.cuh "blocked map": one 32-byte SWIZZLE_32B row per block, row
 // index a * 27 + b), so K = 9 blocks x 16 pixels = 144 and the A operand of block (i, j) is the staged rows
 // viewed (27 i + j) rows further down: no A tile is ever built -- one 5.9 KB bulk copy per 128 pooled pixels.
-constexpr int kStemPix = 22 * 25;                 // 550 pooled pixels per clip (of kBmapRows = 648 GEMM rows)
+// NF = 90: 22 x 25 = 550 pooled pixels per clip of 648 GEMM rows; NF = 103 (use_delta_delta): 26 x 25 = 650 of 760.
 constexpr int kStemRowsIn = (128 + 2 * kBmapB + 2 + 7) & ~7;      // 184 rows a tile reads
 constexpr int kStemABytes = ((kStemRowsIn * 32 + 255) / 256) * 256;   // 5888 -> 6144 per stage
 constexpr int kStemStages = 4;
 constexpr int kStemBBytes = 3 * 16384;            // 128 weight rows x 3 chunks of 64 K-elements (144 used)
 constexpr size_t kStemSmem = 1024 + kStemStages * kStemABytes + kStemBBytes + 128;
 
+template <int NF>
 __global__ void __launch_bounds__(kS1Threads, 1)
 stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __restrict__ wq,
                const float* __restrict__ bias, __nv_bfloat16* __restrict__ x0, int64_t x0_plane_elems,
                __nv_bfloat16* __restrict__ xs0, int B) {
+    using NS = NetShape<NF>;
+    constexpr int kRows = NS::BROWS;                            // GEMM rows per clip
     extern __shared__ unsigned char raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sA = base;                                   // [kStemStages][kStemABytes]
@@ -930,7 +933,7 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
     constexpr int TMEM_COLS = 256;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t rows = (int64_t)B * kBmapRows;
+    const int64_t rows = (int64_t)B * kRows;
     const int n_tiles = (int)((rows + 127) / 128);
     if (tid == 0) {
         for (int i = 0; i < kStemStages; ++i) {
@@ -995,9 +998,9 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const int64_t mp = (int64_t)tile * 128 + lane_grp * 32 + lane;
-            const int clip = (int)(mp / kBmapRows), rem = (int)(mp - (int64_t)clip * kBmapRows);
+            const int clip = (int)(mp / kRows), rem = (int)(mp - (int64_t)clip * kRows);
             const int py = rem / kBmapB, px = rem - py * kBmapB;
-            const bool live = clip < B && py < 22 && px < 25;
+            const bool live = clip < B && py < NS::H0 && px < NS::W0;
             tc::mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
             tc::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * 128;
@@ -1014,8 +1017,8 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
             if (live) {
                 // x0 goes out phase-split (Ps2Layout<22, 25>): plane = (py+1) & 1, row = ((py+1)/2, (px+1)/2),
                 // the (px+1) parity picks the 64-byte half of the 128-byte row
-                using P2 = Ps2Layout<22, 25>;
-                using PSN = PsLayout<11, 13>;
+                using P2 = Ps2Layout<NS::H0, NS::W0>;
+                using PSN = PsLayout<NS::H1, NS::W1>;
                 const int64_t r2 = (int64_t)clip * P2::RPC + ((py + 1) >> 1) * P2::B2 + ((px + 1) >> 1);
                 __nv_bfloat16* op = x0 + (int64_t)((py + 1) & 1) * x0_plane_elems + r2 * 64;
                 const int jb = ((px + 1) & 1) * 4;
@@ -1045,12 +1048,14 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
 
 // fp32 features (B, 90, 101) -> the stem's blocked bf16 map (for callers that hand features in): one thread
 // per 4x4 block = one 32-byte operand row
+template <int NF>
 __global__ void __launch_bounds__(256)
 map_from_feat_kernel(const float* __restrict__ feat, __nv_bfloat16* __restrict__ maps, int64_t B) {
+    constexpr int kRows = NetShape<NF>::BROWS;
     const int64_t b = blockIdx.y;
     const int row = blockIdx.x * 256 + threadIdx.x;
-    if (row >= kBmapRows) return;
-    const float* f = feat + b * (int64_t)kFeatElem;
+    if (row >= kRows) return;
+    const float* f = feat + b * (int64_t)NetShape<NF>::FEAT_ELEMS;
     const int ba = row / kBmapB, bb = row - ba * kBmapB;
     uint32_t w[8];
 #pragma unroll
@@ -1060,29 +1065,30 @@ map_from_feat_kernel(const float* __restrict__ feat, __nv_bfloat16* __restrict__
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int t = 4 * bb + c - 3;
-            v[c] = (fr >= 0 && fr < kFeat && t >= 0 && t < kFrames) ? f[fr * kFrames + t] : 0.f;
+            v[c] = (fr >= 0 && fr < NF && t >= 0 && t < kFrames) ? f[fr * kFrames + t] : 0.f;
         }
         __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
         w[2 * r] = *reinterpret_cast<uint32_t*>(&p0);
         w[2 * r + 1] = *reinterpret_cast<uint32_t*>(&p1);
     }
-    uint4* dst = reinterpret_cast<uint4*>(maps + (b * kBmapRows + row) * 16);
+    uint4* dst = reinterpret_cast<uint4*>(maps + (b * kRows + row) * 16);
     const int sw = (row >> 2) & 1;                   // chunk (r >> 1) lives at (r >> 1) ^ ((row >> 2) & 1)
     dst[0 ^ sw] = make_uint4(w[0], w[1], w[2], w[3]);
     dst[1 ^ sw] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
-// AdaptiveAvgPool2d(1) + Flatten + Linear(128 -> 2); x2 is [B][42][128] fp32; fixed summation order
+// AdaptiveAvgPool2d(1) + Flatten + Linear(128 -> 2); x2 is [B][NPOS][128] fp32 (NPOS = 42 | 49); fixed summation order
+template <int NPOS>
 __global__ void __launch_bounds__(128)
 head_kernel(const float* __restrict__ x2, const float* __restrict__ fcw, const float* __restrict__ fcb,
             float* __restrict__ logits, int B) {
     __shared__ float part[2][4];
     const int b = blockIdx.x, c = threadIdx.x;
-    const float* p = x2 + (int64_t)b * 42 * 128 + c;
+    const float* p = x2 + (int64_t)b * NPOS * 128 + c;
     float s = 0.f;
-#pragma unroll 6
-    for (int i = 0; i < 42; ++i) s += p[i * 128];
-    s *= (1.0f / 42.0f);
+#pragma unroll 7
+    for (int i = 0; i < NPOS; ++i) s += p[i * 128];
+    s *= (1.0f / (float)NPOS);
     float a0 = s * fcw[c], a1 = s * fcw[128 + c];
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -1119,19 +1125,12 @@ static void pack_weights(const std::vector<float>& wf, int taps, int cin, int co
         }
 }
 
+template <int NF> static int init_cnn_tc_nf(cd_handle* h);
 int init_cnn_tc(cd_handle* h) {
-    CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s2_tc_kernel<32, 64, 22, 25>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)S2Shape<32, 64, 22, 25>::SMEM));
-    CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s2_tc_kernel<64, 128, 11, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)S2Shape<64, 128, 11, 13>::SMEM));
-    CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s1_tc_kernel<64, 11, 13, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)S1Shape<64, 11, 13>::SMEM));
-    CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s1_pair_tc_kernel<6, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)S1PairShape<6, 7>::SMEM));
-    CD_CUDA(h, cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStemSmem));
     CD_CUDA(h, cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CD_CUDA(h, cudaFuncSetAttribute(umma_pair_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    return CD_OK;
+    const int rc = init_cnn_tc_nf<kFeat>(h);
+    return rc != CD_OK ? rc : init_cnn_tc_nf<kFeatDD>(h);
 }
 
 // wf/bf: [stem, b0c1, b0sk, b0c2, b1c1, b1sk, b1c2, fc] folded fp32, conv weights as [tap][cin][cout]
@@ -1194,110 +1193,144 @@ int upload_cnn_tc(cd_handle* h, const std::vector<std::vector<float>>& wf, const
     return CD_OK;
 }
 
-// Tensor-core workspace: fixed layout for kTcChunk clips, allocated and zeroed once per handle (the PS
-// buffers rely on their pad rows staying zero).
+// Tensor-core workspace: fixed layout for kTcChunk clips of one shape family, allocated once per handle for the larger
+// family and zeroed whenever the family changes (the PS buffers rely on their pad rows staying zero, and the two
+// families put their pads in different places).
 // [maps | x0 | h1 PS: conv plane + skip plane | x1 | h2 PS: 2 conv planes + skip plane | x2]
 constexpr int64_t kTcChunk = 16384;
-using Ps0 = PsLayout<11, 13>;
-using Ps1 = PsLayout<6, 7>;
-constexpr int64_t kPs0Rows = ((kTcChunk * Ps0::RPC + 127) / 128) * 128 + Ps0::ROWS_IN;    // + the last tile's look-ahead
-constexpr int64_t kPs1Rows = ((kTcChunk * Ps1::RPC + 127) / 128) * 128 + 128 + Ps1::ROWS_IN;   // + the pair kernel's odd tile
 constexpr int64_t al256(int64_t x) { return (x + 255) & ~int64_t(255); }
-constexpr int64_t kOffMap = 0;
-constexpr int64_t kOffX0 = kOffMap + al256((kTcChunk * kBmapRows + 128 + kStemRowsIn) * 32);   // + last tile's look-ahead
-using P20 = Ps2Layout<22, 25>;
-using P21 = Ps2Layout<11, 13>;
-constexpr int64_t kP20Rows = ((kTcChunk * P20::RPC + 127) / 128) * 128 + P20::ROWS_IN;    // x0, 2 planes
-constexpr int64_t kP21Rows = ((kTcChunk * P21::RPC + 127) / 128) * 128 + P21::ROWS_IN;    // x1, 4 planes
-constexpr int64_t kOffH1 = kOffX0 + al256(2 * kP20Rows * 128);
-constexpr int64_t kOffX1 = kOffH1 + al256(2 * kPs0Rows * 128);
-constexpr int64_t kOffH2 = kOffX1 + al256(4 * kP21Rows * 128);
-constexpr int64_t kOffX2 = kOffH2 + al256(3 * kPs1Rows * 128);
-constexpr int64_t kTcWsBytes = kOffX2 + al256(kTcChunk * 42 * 128 * 4);
+template <int NF>
+struct TcPlan {
+    using N = NetShape<NF>;
+    using Ps0 = PsLayout<N::H1, N::W1>;
+    using Ps1 = PsLayout<N::H2, N::W2>;
+    using P20 = Ps2Layout<N::H0, N::W0>;
+    using P21 = Ps2Layout<N::H1, N::W1>;
+    static constexpr int NPOS = N::H2 * N::W2;
+    static constexpr int64_t kPs0Rows = ((kTcChunk * Ps0::RPC + 127) / 128) * 128 + Ps0::ROWS_IN;          // + the last tile's look-ahead
+    static constexpr int64_t kPs1Rows = ((kTcChunk * Ps1::RPC + 127) / 128) * 128 + 128 + Ps1::ROWS_IN;    // + the pair kernel's odd tile
+    static constexpr int64_t kP20Rows = ((kTcChunk * P20::RPC + 127) / 128) * 128 + P20::ROWS_IN;          // x0, 2 planes
+    static constexpr int64_t kP21Rows = ((kTcChunk * P21::RPC + 127) / 128) * 128 + P21::ROWS_IN;          // x1, 4 planes
+    static constexpr int64_t kOffMap = 0;
+    static constexpr int64_t kOffX0 = kOffMap + al256((kTcChunk * N::BROWS + 128 + kStemRowsIn) * 32);     // + last tile's look-ahead
+    static constexpr int64_t kOffH1 = kOffX0 + al256(2 * kP20Rows * 128);
+    static constexpr int64_t kOffX1 = kOffH1 + al256(2 * kPs0Rows * 128);
+    static constexpr int64_t kOffH2 = kOffX1 + al256(4 * kP21Rows * 128);
+    static constexpr int64_t kOffX2 = kOffH2 + al256(3 * kPs1Rows * 128);
+    static constexpr int64_t kBytes = kOffX2 + al256(kTcChunk * NPOS * 128 * 4);
+};
+constexpr int64_t kTcWsBytes = TcPlan<kFeatDD>::kBytes > TcPlan<kFeat>::kBytes ? TcPlan<kFeatDD>::kBytes : TcPlan<kFeat>::kBytes;
 
 size_t cnn_tc_ws_bytes(int64_t) { return 0; }      // nothing from the shared workspace
 
-int ensure_tc_ws(cd_handle* h) {
-    if (h->d_ws_tc) return CD_OK;
-    cudaError_t e = cudaMalloc(&h->d_ws_tc, (size_t)kTcWsBytes);
-    if (e != cudaSuccess) return set_err(h, CD_E_NOMEM, "tensor-core workspace allocation", e);
+// nf: the shape family (90 | 103 feature rows) the next launches will use
+int ensure_tc_ws(cd_handle* h, int nf) {
+    if (h->d_ws_tc && h->tc_plan_nf == nf) return CD_OK;
+    CD_CUDA(h, cudaDeviceSynchronize());       // callers' streams are non-blocking: nothing may still read the old layout
+    if (!h->d_ws_tc) {
+        cudaError_t e = cudaMalloc(&h->d_ws_tc, (size_t)kTcWsBytes);
+        if (e != cudaSuccess) return set_err(h, CD_E_NOMEM, "tensor-core workspace allocation", e);
+    }
     CD_CUDA(h, cudaMemset(h->d_ws_tc, 0, (size_t)kTcWsBytes));
-    CD_CUDA(h, cudaDeviceSynchronize());       // callers' streams are non-blocking: order the zero-fill before them
+    CD_CUDA(h, cudaDeviceSynchronize());       // ... and the zero-fill is ordered before them
+    h->tc_plan_nf = nf;
     return CD_OK;
 }
 
 // the first region holds the bf16 maps of the current chunk: the feature kernel writes them there
 // directly in the end-to-end path (call ensure_tc_ws first)
-__nv_bfloat16* cnn_tc_map_ptr(cd_handle* h) { return reinterpret_cast<__nv_bfloat16*>(h->d_ws_tc + kOffMap); }
+__nv_bfloat16* cnn_tc_map_ptr(cd_handle* h) { return reinterpret_cast<__nv_bfloat16*>(h->d_ws_tc); }
+
+template <int NF>
+static int init_cnn_tc_nf(cd_handle* h) {
+    using N = NetShape<NF>;
+    CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s2_tc_kernel<32, 64, N::H0, N::W0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)S2Shape<32, 64, N::H0, N::W0>::SMEM));
+    CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s2_tc_kernel<64, 128, N::H1, N::W1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)S2Shape<64, 128, N::H1, N::W1>::SMEM));
+    CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s1_tc_kernel<64, N::H1, N::W1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)S1Shape<64, N::H1, N::W1>::SMEM));
+    CD_CUDA(h, cudaFuncSetAttribute(conv3x3_s1_pair_tc_kernel<N::H2, N::W2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)S1PairShape<N::H2, N::W2>::SMEM));
+    CD_CUDA(h, cudaFuncSetAttribute(stem_tc_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStemSmem));
+    return CD_OK;
+}
 
 // d_feat != nullptr: features come in as fp32 and are converted chunk by chunk; d_feat == nullptr:
 // the maps of the (single, <= kTcChunk clips) chunk are already in the workspace.
-int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, cudaStream_t s) {
-    if (B == 0) return CD_OK;
-    if (!d_feat && B > kTcChunk) return set_err(h, CD_E_ARG, "launch_cnn_tc: pre-filled maps hold one chunk only");
+template <int NF>
+static int launch_cnn_tc_nf(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, cudaStream_t s) {
+    using N = NetShape<NF>;
+    using P = TcPlan<NF>;
     const TcWeights& W = g_tcw[h->device];
-    int rc0 = ensure_tc_ws(h);
+    int rc0 = ensure_tc_ws(h, NF);
     if (rc0 != CD_OK) return rc0;
     unsigned char* ws = h->d_ws_tc;
-    __nv_bfloat16* maps = reinterpret_cast<__nv_bfloat16*>(ws + kOffMap);
-    __nv_bfloat16* x0 = reinterpret_cast<__nv_bfloat16*>(ws + kOffX0);
-    __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(ws + kOffH1);      // plane 0: conv1 output, plane 1: x0 at (2y, 2x)
-    __nv_bfloat16* x1 = reinterpret_cast<__nv_bfloat16*>(ws + kOffX1);
-    __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(ws + kOffH2);      // planes 0, 1: conv1 output, plane 2: x1 at (2y, 2x)
-    float* x2 = reinterpret_cast<float*>(ws + kOffX2);
-    constexpr int64_t kPl0 = kPs0Rows * 64, kPl1 = kPs1Rows * 64;
+    __nv_bfloat16* maps = reinterpret_cast<__nv_bfloat16*>(ws + P::kOffMap);
+    __nv_bfloat16* x0 = reinterpret_cast<__nv_bfloat16*>(ws + P::kOffX0);
+    __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(ws + P::kOffH1);   // plane 0: conv1 output, plane 1: x0 at (2y, 2x)
+    __nv_bfloat16* x1 = reinterpret_cast<__nv_bfloat16*>(ws + P::kOffX1);
+    __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(ws + P::kOffH2);   // planes 0, 1: conv1 output, plane 2: x1 at (2y, 2x)
+    float* x2 = reinterpret_cast<float*>(ws + P::kOffX2);
+    constexpr int64_t kPl0 = P::kPs0Rows * 64, kPl1 = P::kPs1Rows * 64;
     for (int64_t c0 = 0; c0 < B; c0 += kTcChunk) {
         const int n = (int)((B - c0) < kTcChunk ? (B - c0) : kTcChunk);
         if (d_feat) {
-            map_from_feat_kernel<<<dim3((kBmapRows + 255) / 256, n), 256, 0, s>>>(d_feat + c0 * kFeatElem, maps, n);
+            map_from_feat_kernel<NF><<<dim3((N::BROWS + 255) / 256, n), 256, 0, s>>>(d_feat + c0 * N::FEAT_ELEMS, maps, n);
             h->launches += 1;
         }
         {
-            const int tiles = (int)(((int64_t)n * kBmapRows + 127) / 128);
-            stem_tc_kernel<<<tiles < h->sm_count ? tiles : h->sm_count, kS1Threads, kStemSmem, s>>>(
-                maps, W.stem_w, W.stem_b, x0, kP20Rows * 64, h1 + kPl0, n);
+            const int tiles = (int)(((int64_t)n * N::BROWS + 127) / 128);
+            stem_tc_kernel<NF><<<tiles < h->sm_count ? tiles : h->sm_count, kS1Threads, kStemSmem, s>>>(
+                maps, W.stem_w, W.stem_b, x0, P::kP20Rows * 64, h1 + kPl0, n);
         }
         h->launches += 1;
         {
-            using S = S2Shape<32, 64, 22, 25>;
+            using S = S2Shape<32, 64, N::H0, N::W0>;
             S2Args q{};
-            q.x = x0; q.w = W.b0c1; q.bias = W.b0c1_b; q.y = h1; q.in_plane_elems = kP20Rows * 64; q.out_plane_elems = kPl0; q.n = n;
-            const int tiles = (int)(((int64_t)n * P20::RPC + 127) / 128);
-            conv3x3_s2_tc_kernel<32, 64, 22, 25><<<tiles < h->sm_count ? tiles : h->sm_count, kS1Threads, S::SMEM, s>>>(q);
+            q.x = x0; q.w = W.b0c1; q.bias = W.b0c1_b; q.y = h1; q.in_plane_elems = P::kP20Rows * 64; q.out_plane_elems = kPl0; q.n = n;
+            const int tiles = (int)(((int64_t)n * P::P20::RPC + 127) / 128);
+            conv3x3_s2_tc_kernel<32, 64, N::H0, N::W0><<<tiles < h->sm_count ? tiles : h->sm_count, kS1Threads, S::SMEM, s>>>(q);
             h->launches += 1;
         }
         {
-            using S = S1Shape<64, 11, 13>;
+            using S = S1Shape<64, N::H1, N::W1>;
             S1Args q{};
             q.x = h1; q.w = W.b0c2; q.wskip = W.b0sk; q.bias = W.b0c2_b; q.y_bf16 = x1; q.xs_out = h2 + 2 * kPl1;
-            q.y_plane_elems = kP21Rows * 64; q.ps_plane_elems = kPl0; q.n = n;
-            const int tiles = (int)(((int64_t)n * Ps0::RPC + 127) / 128);
+            q.y_plane_elems = P::kP21Rows * 64; q.ps_plane_elems = kPl0; q.n = n;
+            const int tiles = (int)(((int64_t)n * P::Ps0::RPC + 127) / 128);
             const int grid = (tiles < h->sm_count ? tiles : h->sm_count) * S::HALVES;
-            conv3x3_s1_tc_kernel<64, 11, 13, false, true><<<grid, kS1Threads, S::SMEM, s>>>(q);
+            conv3x3_s1_tc_kernel<64, N::H1, N::W1, false, true><<<grid, kS1Threads, S::SMEM, s>>>(q);
             h->launches += 1;
         }
         {
-            using S = S2Shape<64, 128, 11, 13>;
+            using S = S2Shape<64, 128, N::H1, N::W1>;
             S2Args q{};
-            q.x = x1; q.w = W.b1c1; q.bias = W.b1c1_b; q.y = h2; q.in_plane_elems = kP21Rows * 64; q.out_plane_elems = kPl1; q.n = n;
-            const int tiles = (int)(((int64_t)n * P21::RPC + 127) / 128);
-            conv3x3_s2_tc_kernel<64, 128, 11, 13><<<tiles < h->sm_count ? tiles : h->sm_count, kS1Threads, S::SMEM, s>>>(q);
+            q.x = x1; q.w = W.b1c1; q.bias = W.b1c1_b; q.y = h2; q.in_plane_elems = P::kP21Rows * 64; q.out_plane_elems = kPl1; q.n = n;
+            const int tiles = (int)(((int64_t)n * P::P21::RPC + 127) / 128);
+            conv3x3_s2_tc_kernel<64, 128, N::H1, N::W1><<<tiles < h->sm_count ? tiles : h->sm_count, kS1Threads, S::SMEM, s>>>(q);
             h->launches += 1;
         }
         {
-            using S = S1PairShape<6, 7>;
+            using S = S1PairShape<N::H2, N::W2>;
             S1Args q{};
             q.x = h2; q.w = W.b1c2; q.wskip = W.b1sk; q.bias = W.b1c2_b; q.y_f32 = x2; q.ps_plane_elems = kPl1; q.n = n;
-            const int tiles = (int)(((int64_t)n * Ps1::RPC + 127) / 128);
+            const int tiles = (int)(((int64_t)n * P::Ps1::RPC + 127) / 128);
             const int tp = (tiles + 1) / 2, max_pairs = h->sm_count / 2;
-            conv3x3_s1_pair_tc_kernel<6, 7><<<2 * (tp < max_pairs ? tp : max_pairs), kS1Threads, S::SMEM, s>>>(q);
+            conv3x3_s1_pair_tc_kernel<N::H2, N::W2><<<2 * (tp < max_pairs ? tp : max_pairs), kS1Threads, S::SMEM, s>>>(q);
             h->launches += 1;
         }
-        head_kernel<<<n, 128, 0, s>>>(x2, W.fc_w, W.fc_b, d_logits + c0 * CD_N_CLASSES, n);
+        head_kernel<P::NPOS><<<n, 128, 0, s>>>(x2, W.fc_w, W.fc_b, d_logits + c0 * CD_N_CLASSES, n);
         h->launches += 1;
         CD_CUDA(h, cudaGetLastError());
     }
     return CD_OK;
+}
+
+int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, cudaStream_t s, int nf) {
+    if (B == 0) return CD_OK;
+    if (!d_feat && B > kTcChunk) return set_err(h, CD_E_ARG, "launch_cnn_tc: pre-filled maps hold one chunk only");
+    return nf == kFeatDD ? launch_cnn_tc_nf<kFeatDD>(h, d_feat, B, d_logits, s) : launch_cnn_tc_nf<kFeat>(h, d_feat, B, d_logits, s);
 }
 
 // D = A * B^T for 128 x K by N x K bf16-rounded inputs (host fp32 in/out); exercises descriptor encodings

@@ -470,7 +470,7 @@ __device__ __forceinline__ float2 mfcc_par(const float* __restrict__ db, float* 
 // PCEN = true : the tile holds mel POWER, `top` is its block max; rows 0..63 are apply_pcen (src/preprocessing.py:
 //               305-340) scaled to [0, 1] by the clip's min / max (:400-404); the MFCC rows still come from the dB.
 // Ends with the block in sync except for the final stores.
-// dd: also emit the delta-delta rows 90..102 = compute_deltas(compute_deltas(mfcc)) (:463-466; fp32 output only).
+// dd: also emit the delta-delta rows 90..102 = compute_deltas(compute_deltas(mfcc)) (:463-466).
 template <bool PCEN, class SM>
 __device__ __forceinline__ void feat_tail(SM& S, float top, float* __restrict__ out, __nv_bfloat16* __restrict__ mo, int tid,
                                           bool dd = false) {
@@ -518,18 +518,21 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float* __restrict__ 
             const float xp = __fmul_rn(row[min(t + 1, kFrames - 1)] - mean, inv_std);
             const float xm = __fmul_rn(row[max(t - 1, 0)] - mean, inv_std);
             const float dl = (xp - xm) * 0.5f;                             // compute_deltas (:353-355)
+            float d2 = 0.f;
+            if (dd) {
+                auto xn = [&](int u) { return __fmul_rn(row[min(max(u, 0), kFrames - 1)] - mean, inv_std); };
+                auto d1 = [&](int u) { u = min(max(u, 0), kFrames - 1); return (xn(u + 1) - xn(u - 1)) * 0.5f; };
+                d2 = (d1(t + 1) - d1(t - 1)) * 0.5f;
+            }
             if (out) {
                 out[(kMels + cidx) * kFrames + t] = x0;
                 out[(kMels + kMfcc + cidx) * kFrames + t] = dl;
-                if (dd) {
-                    auto xn = [&](int u) { return __fmul_rn(row[min(max(u, 0), kFrames - 1)] - mean, inv_std); };
-                    auto d1 = [&](int u) { u = min(max(u, 0), kFrames - 1); return (xn(u + 1) - xn(u - 1)) * 0.5f; };
-                    out[(kMels + 2 * kMfcc + cidx) * kFrames + t] = (d1(t + 1) - d1(t - 1)) * 0.5f;
-                }
+                if (dd) out[(kMels + 2 * kMfcc + cidx) * kFrames + t] = d2;
             }
             if (mo) {
                 mo[bmap_offset(kMels + cidx + 3, t + 3)] = __float2bfloat16_rn(x0);
                 mo[bmap_offset(kMels + kMfcc + cidx + 3, t + 3)] = __float2bfloat16_rn(dl);
+                if (dd) mo[bmap_offset(kMels + 2 * kMfcc + cidx + 3, t + 3)] = __float2bfloat16_rn(d2);
             }
         }
     }
@@ -713,7 +716,7 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
 #else
         const bool dd = (mode & kModeDeltaDelta) != 0;
         feat_tail<PCEN>(S, top, feat ? feat + b * (int64_t)(dd ? kFeatElemDD : kFeatElem) : nullptr,
-                        map_out ? map_out + b * (int64_t)kMapElems : nullptr, tid, dd);
+                        map_out ? map_out + b * (int64_t)(dd ? NetShape<kFeatDD>::MAP_ELEMS : kMapElems) : nullptr, tid, dd);
 #endif
         __syncthreads();                                               // xb / db free again
     }
@@ -839,7 +842,7 @@ stream_window_kernel(const float* __restrict__ audio, int64_t hop, int64_t n_win
             }
         }
         feat_tail<PCEN>(S, block_reduce<true>(wmax, S.red), feat ? feat + j * (int64_t)(dd ? kFeatElemDD : kFeatElem) : nullptr,
-                        map_out ? map_out + j * (int64_t)kMapElems : nullptr, tid, dd != 0);
+                        map_out ? map_out + j * (int64_t)(dd ? NetShape<kFeatDD>::MAP_ELEMS : kMapElems) : nullptr, tid, dd != 0);
         __syncthreads();
     }
 }
@@ -936,8 +939,6 @@ int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets
                     int64_t stride_or_hop, int mode, int64_t B, float* d_feat, __nv_bfloat16* d_map, cudaStream_t s) {
     if (B == 0) return CD_OK;
     mode |= h->feat_opts;
-    if ((mode & kModeDeltaDelta) && (d_map || !d_feat))
-        return set_err(h, CD_E_ARG, "use_delta_delta (103 feature rows) is a features-only option: the CNN kernels take 90 rows");
     const bool pre = (mode & kModePreEmph) != 0, pcen = (mode & kModePcen) != 0;
     const float coef = h->pre_coef;
     const int64_t slots = 2 * (int64_t)h->sm_count;     // two resident CTAs per SM
@@ -991,8 +992,6 @@ int launch_features_i16(cd_handle* h, const int16_t* d_audio, int64_t stride, in
     if (B == 0) return CD_OK;
     const int64_t slots = 2 * (int64_t)h->sm_count;
     mode |= h->feat_opts;
-    if ((mode & kModeDeltaDelta) && (d_map || !d_feat))
-        return set_err(h, CD_E_ARG, "use_delta_delta (103 feature rows) is a features-only option: the CNN kernels take 90 rows");
     const bool pre = (mode & kModePreEmph) != 0, pcen = (mode & kModePcen) != 0;
     const float coef = h->pre_coef;
 #define CD_CALL(P, Q)                                                                                            \

@@ -56,10 +56,6 @@ class CoughDetectorInference:
             use_delta_delta=cfg.get("use_delta_delta", True),
             use_spectral_contrast=cfg.get("use_spectral_contrast", True),
             n_contrast_bands=cfg.get("n_contrast_bands", 6), device=str(self.device))
-        if self.preprocessor.get_num_features() != _lib.N_FEATURES:
-            raise NotImplementedError(
-                f"this checkpoint's config yields {self.preprocessor.get_num_features()} feature rows (use_delta_delta); the "
-                f"B200 CNN kernels take {_lib.N_FEATURES}.  There is deliberately no CPU fallback.")
         self.prediction_history = deque(maxlen=smoothing_window)
         self.last_detection_time = 0
         self.on_cough_detected: Optional[Callable[[datetime, float], None]] = None

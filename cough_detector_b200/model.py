@@ -69,14 +69,14 @@ class CoughDetectorResidual(nn.Module):
         return h
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """(B, 1, 90, 101) -> logits (B, 2) (reference :253-259)."""
+        """(B, 1, 90, 101) -- or (B, 1, 103, 101) for use_delta_delta features -- -> logits (B, 2) (reference :253-259)."""
         if self.training:
             raise RuntimeError("cough_detector_b200 is inference-only: call model.eval() before forward()")
         if self.precision not in _PREC:
             raise ValueError(f"precision must be one of {list(_PREC)}, got {self.precision!r}")
-        if x.dim() == 4 and x.shape[2] != _lib.N_FEATURES:
-            raise NotImplementedError(f"the B200 CNN kernels are built for {_lib.N_FEATURES} feature rows, got {x.shape[2]} "
-                                      "(use_delta_delta / use_spectral_contrast inputs have no kernels; no fallback)")
+        if x.dim() == 4 and x.shape[2] not in (_lib.N_FEATURES, _lib.N_FEATURES_DD):
+            raise NotImplementedError(f"the B200 CNN kernels are built for {_lib.N_FEATURES} or {_lib.N_FEATURES_DD} feature rows, "
+                                      f"got {x.shape[2]} (spectral-contrast inputs have no kernels; no fallback)")
         h = self._handle(x)
         xd = x.detach().to(device=f"cuda:{h.device}", dtype=torch.float32, non_blocking=True)
         logits = h.cnn_forward(xd, _PREC[self.precision])

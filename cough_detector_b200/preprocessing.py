@@ -4,8 +4,8 @@ Host-side mirror of the reference's ``src/preprocessing.py`` (class and method n
 meaning, return shapes, error behaviour) for the 90-feature configurations: the one the reference
 trains with (``src/train.py:264-287``: ``use_pcen=False, use_pre_emphasis=False,
 use_delta_delta=False, use_spectral_contrast=False``) and its ``use_pre_emphasis`` / ``use_pcen``
-variants (same 90 rows, so the CNN is unchanged), plus ``use_delta_delta`` as a features-only option
-(103 rows: for feature caching / training pipelines; the CNN kernels take 90 rows).  All feature
+variants (same 90 rows), and ``use_delta_delta`` (103 rows; the CNN kernels are instantiated for both
+heights).  All feature
 arithmetic runs in ``libcough_b200.so`` (csrc/feat_kernel.cu); there is no torchaudio/CPU path here.
 ``use_spectral_contrast`` raises ``NotImplementedError`` instead of falling back; its rows are NaN in
 the reference itself.

@@ -42,7 +42,7 @@ extern "C" {
 #define CD_FEAT_PRE_EMPHASIS 2   /* use_pre_emphasis: y[n] = x[n] - coef x[n-1] ahead of both feature blocks (:213-239, :452) */
 #define CD_FEAT_PCEN         4   /* use_pcen: rows 0..63 are apply_pcen + per-clip min/max (:305-340, :400-404) instead of dB */
 #define CD_FEAT_DELTA_DELTA  8   /* use_delta_delta: 13 more rows, compute_deltas(compute_deltas(mfcc)) (:463-466): d_feat is
-                                    B x 103 x 101.  Features only -- the CNN entry points take 90 rows and refuse this option. */
+                                    B x 103 x 101; the network then runs on 103 rows (cd_cnn_forward_rows / cd_e2e_*) */
 #define CD_N_FEATURES_DD 103
 
 #define CD_PRECISION_FP32 0      /* direct convolution on CUDA cores, fp32 weights + activations */
@@ -109,8 +109,9 @@ int cd_feat_forward(cd_handle* h, const float* d_audio, int64_t stride, int64_t 
  * pre_emphasis_coef=..., use_pcen=...), src/preprocessing.py:32-51): OR-ed into EVERY later feature launch of this handle,
  * including the fused cd_e2e_* calls, which carry no flags of their own.  flags: any of CD_FEAT_PRE_EMPHASIS,
  * CD_FEAT_PCEN, CD_FEAT_DELTA_DELTA, or 0 (the training configuration, src/train.py:264-287, and the state of a fresh
- * handle).  With CD_FEAT_DELTA_DELTA every feature call writes 103 rows per clip and the cd_e2e_* calls fail with
- * CD_E_ARG.  use_spectral_contrast is not built (it returns NaN rows in the reference itself). */
+ * handle).  With CD_FEAT_DELTA_DELTA every feature call writes 103 rows per clip and the cd_e2e_* calls run the
+ * network on 103 rows.  use_spectral_contrast is not built (it returns NaN rows in the reference itself, DESIGN.md
+ * section 6). */
 int cd_feat_options(cd_handle* h, int flags, float pre_emphasis_coef);
 
 /* Same as cd_feat_forward for int16 PCM clips (the sample format of wav files; torchaudio.load divides by 32768,
@@ -159,6 +160,12 @@ int cd_cnn_load(cd_handle* h, const cd_residual_weights* w);
  * precision: CD_PRECISION_FP32 or CD_PRECISION_BF16. */
 int cd_cnn_forward(cd_handle* h, const float* d_feat, int64_t B, float* d_logits,
                    int precision, void* stream);
+
+/* The same forward() for an input of n_rows feature rows: 90, or 103 for a use_delta_delta feature set (the network is
+ * fully convolutional up to its global average pool, src/model.py:236-259; the kernels are instantiated for these two
+ * heights).  d_feat B x 1 x n_rows x 101 fp32. */
+int cd_cnn_forward_rows(cd_handle* h, const float* d_feat, int n_rows, int64_t B, float* d_logits,
+                        int precision, void* stream);
 
 /* predict() on logits: softmax probabilities (B x 2), argmax class (B, int64) as in
  * src/model.py:261-265, and the batched decision P(cough) >= threshold (B, uint8) that stands in

@@ -66,6 +66,18 @@ def flag_goldens():
         base = z["features"] if name == "dd" else out["features_pre_pcen"]
         assert np.array_equal(full[:, :90], base)
         out[f"ddrows_{name}"] = full[:, 90:]
+        if name == "dd":
+            # the reference network on the 103-row input (it is fully convolutional up to its global pool), both weight sets
+            from src.model import create_model
+            zm = np.load(os.path.join(GOLD, "model.npz"))
+            sd0 = {k[4:]: torch.from_numpy(zm[k]) for k in zm.files if k.startswith("sd0/")}
+            sd1 = dict(sd0)
+            sd1.update({k[4:]: torch.from_numpy(zm[k]) for k in zm.files if k.startswith("sd1/")})
+            model = create_model("residual", n_mels=103, num_classes=2, in_channels=1).eval()
+            with torch.no_grad():
+                for wname, sd in (("default", sd0), ("random", sd1)):
+                    model.load_state_dict(sd)
+                    out[f"logits_dd_{wname}"] = model(torch.from_numpy(full).unsqueeze(1)).numpy()
     zs = np.load(os.path.join(GOLD, "stream.npz"))
     stream = dequantize_clip(zs["mant"], zs["scale"])
     rp = RealtimePreprocessor(window_duration=1.0, hop_duration=0.1, use_delta_delta=False, use_spectral_contrast=False,

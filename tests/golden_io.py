@@ -59,3 +59,9 @@ def load_delta_delta_rows():
     """{"dd" | "pre_pcen_dd": (32, 13, 101)}: rows 90..102 of the reference's 103-row output (rows 0..89 equal the 90-row case)."""
     z = np.load(os.path.join(GOLD, "features_flags.npz"))
     return {k[len("ddrows_"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("ddrows_")}
+
+
+def load_delta_delta_logits():
+    """Reference logits of the 103-row ("dd") golden features, default-init and randomised weights: {name: (32, 2)}."""
+    z = np.load(os.path.join(GOLD, "features_flags.npz"))
+    return {k[len("logits_dd_"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("logits_dd_")}

@@ -264,9 +264,7 @@ def test_variants_stream_int16_and_fused_paths_agree():
 
 @pytest.mark.parametrize("name", ["dd", "pre_pcen_dd"])
 def test_delta_delta_rows_vs_reference_goldens(name):
-    """use_delta_delta is a features-only option (103 rows): rows 90..102 against the reference, rows 0..89 unchanged,
-    and the CNN entry points refuse it instead of reading a 103-row tensor as 90 rows."""
-    from cough_detector_b200 import create_model
+    """use_delta_delta (103 rows): rows 90..102 against the reference, rows 0..89 unchanged, every feature entry point."""
     clips, base, _ = gio.load_features()
     flags, _ = gio.load_feature_flags()
     want90 = base if name == "dd" else flags["pre_pcen"]
@@ -282,12 +280,10 @@ def test_delta_delta_rows_vs_reference_goldens(name):
         assert (got[i, 90:] - want[i]).abs().max().item() <= tol, (name, i)
     fixed = torch.stack(synth.synth_clips(8, seed=2, fixed_length=True))
     one = pp.extract_features_batch(fixed)
-    rt = RealtimePreprocessor(window_duration=1.0, hop_duration=0.1, **kw).stream_features(torch.cat(list(fixed[:3])))
+    s3 = torch.cat(list(fixed[:3]))
+    rt = RealtimePreprocessor(window_duration=1.0, hop_duration=0.1, **kw).stream_features(s3)
     assert one.shape == (8, 1, 103, 101) and rt.shape[1:] == (1, 103, 101)
-    m = create_model("residual").eval()
-    with pytest.raises(NotImplementedError):
-        m(one.cuda())
-    with pytest.raises(_lib.CoughB200Error):
-        m.forward_audio(fixed.cuda(), preprocessor=pp)
+    want_rt = co.stream_features(s3, 1600, co.Explicit32(kw["use_pcen"], kw["use_pre_emphasis"], use_delta_delta=True))
+    assert (rt - want_rt).abs().max().item() <= TOL
     # and the handle goes back to 90 rows for the next default user
     assert AudioPreprocessor(**FLAGS).extract_features_batch(fixed).shape == (8, 1, 90, 101)

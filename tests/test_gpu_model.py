@@ -180,6 +180,53 @@ def test_tcgen05_cta_pair_tile(n, k):
     assert err <= 2e-3 * scale
 
 
+def _dd_features():
+    _, base, _ = gio.load_features()
+    return torch.cat([base, gio.load_delta_delta_rows()["dd"]], dim=1).unsqueeze(1)        # (32, 1, 103, 101)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_103_row_network_vs_reference_goldens(precision):
+    """use_delta_delta feature sets: the same network on 103 rows (heights 26 / 13 / 7), reference logits as goldens."""
+    sd0, sd1, _ = gio.load_model()
+    want = gio.load_delta_delta_logits()
+    x = _dd_features()
+    for name, sd in (("default", sd0), ("random", sd1)):
+        got = _model(sd, precision)(x)
+        ref = want[name]
+        scale = max(1.0, ref.abs().max().item())
+        tol = TOL_FP32 * scale if precision == "fp32" else TOL_BF16_REL * scale
+        assert got.shape == ref.shape and (got - ref).abs().max().item() <= tol, (name, (got - ref).abs().max().item(), scale)
+        if precision == "bf16":
+            emu = co.cnn_forward_bf16(sd, x)
+            assert (got - emu).abs().max().item() <= 5e-3 * scale, (name, (got - emu).abs().max().item())
+        print(f"103 rows {name}/{precision}: logit err {(got - ref).abs().max().item():.3e} (scale {scale:.2f})")
+
+
+def test_switching_between_90_and_103_row_networks():
+    """The tensor-core workspace is laid out per shape family and its zero padding sits in different places: going
+    90 -> 103 -> 90 rows (and a big batch in between) must reproduce the first answers bit for bit."""
+    from cough_detector_b200 import AudioPreprocessor
+    _, sd1, _ = gio.load_model()
+    m = _model(sd1, "bf16")
+    _, base, _ = gio.load_features()
+    x90, x103 = base.unsqueeze(1).cuda(), _dd_features().cuda()
+    a90, a103 = m(x90), m(x103)
+    big = torch.stack(synth.synth_clips(700, seed=8, fixed_length=True)).cuda()
+    kw = dict(use_pcen=False, use_pre_emphasis=False, use_spectral_contrast=False)
+    f103 = m.forward_audio(big, preprocessor=AudioPreprocessor(use_delta_delta=True, **kw))
+    f90 = m.forward_audio(big)
+    assert torch.equal(m(x90), a90) and torch.equal(m(x103), a103)
+    # fused audio -> logits equals features -> network for both families
+    pp = AudioPreprocessor(use_delta_delta=True, **kw)
+    feats = pp.extract_features_batch(big)
+    assert feats.shape[2] == 103 and torch.equal(m(feats), f103)
+    assert torch.equal(m.forward_audio(big), f90) and (f90 - f103).abs().max().item() > 1e-4
+    # fp32 path and the host-buffer path take the family from the handle options too
+    m32 = _model(sd1, "fp32")
+    assert (m32.forward_audio(big[:64], preprocessor=pp) - f103[:64]).abs().max().item() <= 3e-2 * f103.abs().max().item()
+
+
 def test_every_entry_point_on_small_shapes():
     """tools/sanitize_case.py: all kernels / C-ABI entry points on tiny, ragged inputs (the case written for
     compute-sanitizer; that tool is closed on this pool, so it runs as a plain smoke test)."""

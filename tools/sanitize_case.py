@@ -22,8 +22,9 @@ for prec in (0, 1):
     lg2 = h.cnn_forward(f2, prec)
     ls = h.e2e_forward_stream(s.cuda(), 1600, prec)
 for opts in (dict(use_pcen=True, use_pre_emphasis=False), dict(use_pcen=False, use_pre_emphasis=True),
-             dict(use_pcen=True, use_pre_emphasis=True)):        # the optional stages, every entry point again
-    kw = dict(use_delta_delta=False, use_spectral_contrast=False, **opts)
+             dict(use_pcen=True, use_pre_emphasis=True), dict(use_pcen=False, use_pre_emphasis=False, use_delta_delta=True),
+             dict(use_pcen=True, use_pre_emphasis=True, use_delta_delta=True)):   # the optional stages, every entry point again
+    kw = dict(use_spectral_contrast=False, **{"use_delta_delta": False, **opts})
     po = AudioPreprocessor(**kw)
     g1 = po.process_batch(clips)
     g2 = po.extract_features_batch(x)
