@@ -140,6 +140,35 @@ def test_engine_checkpoint_roundtrip_and_chunk_loop():
             CoughDetectorInference(path, device="cuda", verbose=False)
 
 
+def test_engine_with_all_supported_feature_flags():
+    """A checkpoint whose config turns on pre-emphasis, PCEN and delta-delta (103 rows): the engine's window
+    probabilities (chunk loop, fused stream call) against the oracle pipeline (explicit fp32 features -> functional CNN)."""
+    stream, _ = gio.load_stream()
+    _, sd1, _ = gio.load_model()
+    cfg = dict(model_type="residual", use_pcen=True, use_pre_emphasis=True, pre_emphasis_coef=0.95, use_delta_delta=True,
+               use_spectral_contrast=False)
+    ex = co.Explicit32(True, True, 0.95, use_delta_delta=True)
+    feats = co.stream_features(stream, 4000, ex)
+    assert feats.shape[1:] == (1, 103, 101)
+    want = torch.softmax(co.cnn_forward(sd1, feats), dim=1)[:, 1].numpy()
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "best_model.pt")
+        torch.save({"epoch": 0, "model_state_dict": sd1, "optimizer_state_dict": {}, "metrics": {}, "config": cfg}, path)
+        eng = CoughDetectorInference(path, device="cuda", confidence_threshold=0.5, smoothing_window=1,
+                                     debounce_seconds=0.0, verbose=False)
+        assert eng.preprocessor.get_num_features() == 103
+        eng.model.precision = "fp32"
+        got = eng.stream_probabilities(stream, 0.25).cpu().numpy()
+        assert got.shape == want.shape and np.abs(got - want).max() <= 2e-4
+        loop = []
+        for c in range(0, stream.numel(), 4000):
+            for f in eng.preprocessor.add_audio(stream[c:c + 4000]):
+                loop.append(eng.predict(f)[1])
+        assert np.abs(np.array(loop) - want).max() <= 2e-4
+        eng.model.precision = "bf16"
+        assert np.abs(eng.stream_probabilities(stream, 0.25).cpu().numpy() - want).max() <= 3e-2
+
+
 @pytest.mark.parametrize("n,k", [(64, 64), (64, 320), (128, 256), (256, 128), (32, 64)])
 def test_tcgen05_tile_selftest_bf16(n, k):
     """One UMMA tile through the conv kernels' descriptor / swizzle helpers vs a float matmul of bf16-rounded operands."""
