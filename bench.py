@@ -28,7 +28,7 @@ BATCH = 16384
 AUDIO_BYTES = 64000           # 16000 fp32 samples
 FEAT_BYTES = 36360            # 90 x 101 fp32
 CNN_FLOPS = 42_865_600        # 2 x 21 432 800 MAC per clip
-NCU_TRAFFIC_PER_CLIP = 100_225 # feat_kernel dram__bytes_read+write per clip, one ncu --set full capture (profiles/)
+NCU_TRAFFIC_PER_CLIP = 100_154 # feat_kernel dram__bytes_read+write per clip, one ncu --set full capture (profiles/)
 METRIC = "1-s clips/sec (mel+MFCC+CNN)"
 
 
@@ -330,8 +330,8 @@ def run_gpu_arm(args):
             "gpu_launches": int(launches),
             "roofline": {"kernel": "feat_kernel", "bound": "hbm", "achieved": feat_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": feat_gbs / hbm_peak, "traffic": FB * NCU_TRAFFIC_PER_CLIP, "peak_source": peak_src,
-                         "traffic_source": "ncu --set full of this launch (profiles/r1_ncu_feat_kernel_65536.csv): dram read + write 6.568 GB "
-                                           "per 65 536-clip launch = 100 225 B per clip, scaled by the launch size",
+                         "traffic_source": "ncu --set full of this launch (profiles/r1_ncu_feat_kernel_65536.csv): dram read + write 6.564 GB "
+                                           "per 65 536-clip launch = 100 154 B per clip, scaled by the launch size",
                          "algorithmic_bytes_per_clip": AUDIO_BYTES + FEAT_BYTES, "launch_ms": feat_ms,
                          "clips_per_s": FB / (feat_ms * 1e-3), "clips_per_launch": FB,
                          "note": "BASELINE configs[1]: timed alone over 65 536 resident clips right after the e2e region"},
