@@ -140,6 +140,23 @@ def test_engine_checkpoint_roundtrip_and_chunk_loop():
             CoughDetectorInference(path, device="cuda", verbose=False)
 
 
+@pytest.mark.parametrize("rows", [90, 103])
+def test_ragged_batch_sizes_are_prefixes_of_a_big_batch(rows):
+    """Last-tile handling of every persistent kernel (tiles of 128 GEMM rows over clips of 648 / 168 / 56 ... rows, the
+    CTA pair's odd tile, zero padding shared between neighbouring clips): a batch of n clips must give exactly the first n
+    logits of a larger batch, whatever n is."""
+    _, sd1, _ = gio.load_model()
+    m = _model(sd1, "bf16")
+    g = torch.Generator().manual_seed(rows)
+    x = torch.rand(1031, 1, rows, 101, generator=g).cuda()
+    x[:, :, 64:] = (x[:, :, 64:] - 0.5) * 6.0                 # MFCC-like rows are signed
+    big = m(x)
+    for n in (1, 2, 3, 5, 7, 16, 31, 33, 127, 129, 255, 257, 1000):
+        assert torch.equal(m(x[:n]), big[:n]), n
+    ref = co.cnn_forward(sd1, x[:64].cpu())
+    assert (big[:64].cpu() - ref).abs().max().item() <= TOL_BF16_REL * max(1.0, ref.abs().max().item())
+
+
 def test_engine_with_all_supported_feature_flags():
     """A checkpoint whose config turns on pre-emphasis, PCEN and delta-delta (103 rows): the engine's window
     probabilities (chunk loop, fused stream call) against the oracle pipeline (explicit fp32 features -> functional CNN)."""
