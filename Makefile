@@ -27,7 +27,11 @@ ablations: $(OBJS)
 	  $(NVCC) -shared $(ARCH) -o build/exp/libexp$$e.so build/api.o build/exp/feat_$$e.o build/cnn_fp32.o build/cnn_tc.o build/resample.o; \
 	done
 
+# C++ callers of the C ABI (no Python, no torch)
+examples: $(LIB)
+	$(NVCC) -O2 -std=c++17 $(ARCH) -Iinclude examples/e2e_minimal.cu -o build/e2e_minimal -L$(OUT_DIR) -lcough_b200 -Xlinker -rpath,'$$ORIGIN/../$(OUT_DIR)'
+
 clean:
 	rm -rf build $(LIB)
 
-.PHONY: all clean ablations
+.PHONY: all clean ablations examples

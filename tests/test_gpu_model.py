@@ -279,3 +279,13 @@ def test_every_entry_point_on_small_shapes():
     import runpy
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     runpy.run_path(os.path.join(root, "tools", "sanitize_case.py"), run_name="__main__")
+
+
+def test_cpp_example_runs():
+    """The torch-free C++ caller: cd_create -> cd_cnn_load -> cd_e2e_forward -> cd_e2e_forward_host, both paths bit-identical."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert subprocess.run(["make", "-C", root, "examples"], capture_output=True, text=True).returncode == 0
+    r = subprocess.run([os.path.join(root, "build", "e2e_minimal")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "host path agrees: bit for bit" in r.stdout, r.stdout

@@ -136,3 +136,12 @@ def test_bind_to_gpu_numa_is_harmless_without_nvml():
     assert sharding.bind_to_gpu_numa(0) in (False, True)
     if not __import__("torch").cuda.is_available():
         assert os.sched_getaffinity(0) == before
+
+
+def test_cpp_example_builds_against_the_c_abi():
+    """examples/e2e_minimal.cu is a torch-free C++ caller of include/cough_b200.h; it must compile and link here."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["make", "-C", root, "examples"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert os.path.exists(os.path.join(root, "build", "e2e_minimal"))
