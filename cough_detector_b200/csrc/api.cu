@@ -413,7 +413,9 @@ static int e2e_host_impl(cd_handle* h, const void* h_audio, bool i16, int64_t B,
         return set_err(h, CD_E_ARG, "precision must be CD_PRECISION_FP32 or CD_PRECISION_BF16");
     if (B == 0) return CD_OK;
     DeviceGuard g(h->device);
-    const int64_t chunk = 4096;                 // copy/compute overlap granularity (<= the CNN workspace chunk)
+    // copy/compute overlap granularity: a chunk's compute (~0.15 ms) hides under its own copy (1.2 ms of fp32), and only
+    // the last chunk's compute is exposed -- measured 51.99 / 53.18 / 53.95 / 54.05 / 54.21 GB/s at 8192 / 4096 / 2048 / 1024 / 512
+    const int64_t chunk = 1024;
     if (!h->pipe_streams[0]) {
         for (int i = 0; i < 3; ++i) {
             CD_CUDA(h, cudaStreamCreateWithFlags(&h->pipe_streams[i], cudaStreamNonBlocking));
