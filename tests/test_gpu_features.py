@@ -287,3 +287,34 @@ def test_delta_delta_rows_vs_reference_goldens(name):
     assert (rt - want_rt).abs().max().item() <= TOL
     # and the handle goes back to 90 rows for the next default user
     assert AudioPreprocessor(**FLAGS).extract_features_batch(fixed).shape == (8, 1, 90, 101)
+
+
+def test_random_lengths_scales_and_offsets_vs_oracle():
+    """process(): 96 clips of random length (1 .. 50 000 samples: heavy zero padding up to 3x trimming), amplitude
+    (1e-6 .. 1e3: the peak normalisation must cancel it) and DC offset, through the variable-length descriptor path,
+    for the plain and the all-options feature sets."""
+    g = torch.Generator().manual_seed(1234)
+    clips = []
+    for i in range(96):
+        n = int(torch.randint(1, 50001, (1,), generator=g)) if i % 5 else [1, 2, 399, 16000, 15999][i // 5 % 5]
+        x = torch.randn(n, generator=g) * (0.2 + 0.8 * torch.rand(1, generator=g))
+        if i % 3 == 0:
+            t = torch.arange(n) / 16000.0
+            x = x * 0.05 + torch.sin(2 * 3.14159265 * float(torch.randint(80, 3900, (1,), generator=g)) * t)
+        x = x * 10.0 ** float(torch.empty(1).uniform_(-6, 3, generator=g)) + (0.1 * float(torch.randn(1, generator=g)) if i % 4 == 0 else 0.0)
+        clips.append(x.float())
+    for kw, ex in ((FLAGS, co.Explicit32()),
+                   (dict(use_pcen=True, use_pre_emphasis=True, use_delta_delta=True, use_spectral_contrast=False),
+                    co.Explicit32(True, True, use_delta_delta=True))):
+        got = AudioPreprocessor(**kw).process_batch(clips)[:, 0]
+        assert torch.isfinite(got).all()
+        worst = 0.0
+        for i, x in enumerate(clips):
+            ref = ex.process(x.reshape(1, -1))[0]
+            d = (got[i] - ref).abs().max().item()
+            if _ill(x):
+                assert d <= TOL_ILL, (i, len(x), d)
+            else:
+                worst = max(worst, d)
+                assert d <= TOL, (i, len(x), d)
+        print("random lengths/scales: worst well-conditioned |err| = %.3e" % worst)
