@@ -229,13 +229,13 @@ def run_gpu_arm(args):
     faudio = synth.synth_batch(FB, seed=200 + rank, device=f"cuda:{local_rank}")
     ffeat = torch.empty(FB, 1, 90, 101, device=audio.device)
     for _ in range(2):
-        h.lib.cd_feat_forward(h._h, faudio.data_ptr(), 16000, FB, ffeat.data_ptr(), 1, h._stream())
+        h.lib.cd_feat_forward(h._h, faudio.data_ptr(), 16000, FB, ffeat.data_ptr(), 1, 0.97, h._stream())
     torch.cuda.synchronize()
     fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nrep = max(3, min(args.steps, 10))
     fe0.record()
     for _ in range(nrep):
-        h.lib.cd_feat_forward(h._h, faudio.data_ptr(), 16000, FB, ffeat.data_ptr(), 1, h._stream())
+        h.lib.cd_feat_forward(h._h, faudio.data_ptr(), 16000, FB, ffeat.data_ptr(), 1, 0.97, h._stream())
     fe1.record()
     torch.cuda.synchronize()
     feat_ms = fe0.elapsed_time(fe1) / nrep

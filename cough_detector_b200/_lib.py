@@ -8,6 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import threading
+from dataclasses import dataclass
 from typing import Dict, Optional
 
 import torch
@@ -28,6 +29,28 @@ N_FEATURES_DD = 103
 _f32p = C.POINTER(C.c_float)
 
 
+@dataclass(frozen=True)
+class FeatOptions:
+    """The optional feature stages of one AudioPreprocessor (src/preprocessing.py:32-51).  Passed with EVERY call
+    (``flags`` / ``pre_emphasis_coef`` of the C ABI): the handle remembers nothing, so objects with different
+    flags can share a handle.  The default is the training configuration (src/train.py:264-287)."""
+    use_pre_emphasis: bool = False
+    pre_emphasis_coef: float = 0.97
+    use_pcen: bool = False
+    use_delta_delta: bool = False
+
+    def flags(self, normalize: bool = True) -> int:
+        return ((FEAT_NORMALIZE if normalize else 0) | (FEAT_PRE_EMPHASIS if self.use_pre_emphasis else 0)
+                | (FEAT_PCEN if self.use_pcen else 0) | (FEAT_DELTA_DELTA if self.use_delta_delta else 0))
+
+    @property
+    def n_features(self) -> int:
+        return N_FEATURES_DD if self.use_delta_delta else N_FEATURES
+
+
+TRAINING_CONFIG = FeatOptions()
+
+
 class _ConvBn(C.Structure):
     _fields_ = [(n, _f32p) for n in ("weight", "bias", "bn_weight", "bn_bias", "bn_running_mean", "bn_running_var")]
 
@@ -38,18 +61,17 @@ class _ResidualWeights(C.Structure):
 
 
 # every symbol include/cough_b200.h declares: name -> (restype, argtypes)
-_VP, _I64, _I = C.c_void_p, C.c_int64, C.c_int
+_VP, _I64, _I, _F = C.c_void_p, C.c_int64, C.c_int, C.c_float
 SYMBOLS = {
     "cd_create": (_I, [_I, C.POINTER(_VP)]),
     "cd_destroy": (_I, [_VP]),
     "cd_last_error": (C.c_char_p, [_VP]),
     "cd_version": (C.c_char_p, []),
     "cd_get_tables": (_I, [_VP, _VP, _VP]),
-    "cd_feat_options": (_I, [_VP, _I, C.c_float]),
-    "cd_feat_forward": (_I, [_VP, _VP, _I64, _I64, _VP, _I, _VP]),
-    "cd_feat_forward_i16": (_I, [_VP, _VP, _I64, _I64, _VP, _I, _VP]),
-    "cd_feat_forward_var": (_I, [_VP, _VP, _VP, _VP, _I64, _VP, _VP]),
-    "cd_feat_forward_stream": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
+    "cd_feat_forward": (_I, [_VP, _VP, _I64, _I64, _VP, _I, _F, _VP]),
+    "cd_feat_forward_i16": (_I, [_VP, _VP, _I64, _I64, _VP, _I, _F, _VP]),
+    "cd_feat_forward_var": (_I, [_VP, _VP, _VP, _VP, _I64, _VP, _I, _F, _VP]),
+    "cd_feat_forward_stream": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _I, _F, _VP]),
     "cd_stream_windows": (_I64, [_I64, _I64]),
     "cd_resample_length": (_I64, [_I64, _I, _I]),
     "cd_resample": (_I, [_VP, _VP, _I64, _I64, _I, _I, _VP, _VP]),
@@ -57,10 +79,10 @@ SYMBOLS = {
     "cd_cnn_forward": (_I, [_VP, _VP, _I64, _VP, _I, _VP]),
     "cd_cnn_forward_rows": (_I, [_VP, _VP, _I, _I64, _VP, _I, _VP]),
     "cd_predict": (_I, [_VP, _VP, _I64, C.c_float, _VP, _VP, _VP, _VP]),
-    "cd_e2e_forward": (_I, [_VP, _VP, _I64, _I64, _VP, _VP, _I, _VP]),
-    "cd_e2e_forward_stream": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _I, _VP]),
-    "cd_e2e_forward_host": (_I, [_VP, _VP, _I64, _VP, _I]),
-    "cd_e2e_forward_host_i16": (_I, [_VP, _VP, _I64, _VP, _I]),
+    "cd_e2e_forward": (_I, [_VP, _VP, _I64, _I64, _VP, _VP, _I, _F, _I, _VP]),
+    "cd_e2e_forward_stream": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _I, _F, _I, _VP]),
+    "cd_e2e_forward_host": (_I, [_VP, _VP, _I64, _VP, _I, _F, _I]),
+    "cd_e2e_forward_host_i16": (_I, [_VP, _VP, _I64, _VP, _I, _F, _I]),
     "cd_selftest_umma": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP]),
     "cd_launch_count": (_I64, [_VP]),
 }
@@ -139,62 +161,50 @@ class Handle:
         return int(self.lib.cd_launch_count(self._h))
 
     # ---- features ---------------------------------------------------------------------------
-    def set_feat_options(self, use_pre_emphasis: bool = False, pre_emphasis_coef: float = 0.97, use_pcen: bool = False,
-                         use_delta_delta: bool = False):
-        """Handle defaults for every later feature launch (cd_feat_options); all off is the training config.
-        use_delta_delta makes the feature calls return 103 rows and the fused audio -> logits calls run the 103-row network."""
-        key = (bool(use_pre_emphasis), float(pre_emphasis_coef), bool(use_pcen), bool(use_delta_delta))
-        if getattr(self, "_feat_opts", (False, 0.97, False, False)) != key:
-            flags = (FEAT_PRE_EMPHASIS if key[0] else 0) | (FEAT_PCEN if key[2] else 0) | (FEAT_DELTA_DELTA if key[3] else 0)
-            self._check(self.lib.cd_feat_options(self._h, flags, key[1]), "cd_feat_options")
-            self._feat_opts = key
-
-    @property
-    def n_features(self) -> int:
-        """Feature rows the handle's current options produce (90, or 103 with use_delta_delta)."""
-        return N_FEATURES_DD if getattr(self, "_feat_opts", (False, 0.97, False, False))[3] else N_FEATURES
-
-    def feat_forward(self, audio: torch.Tensor, normalize: bool = True) -> torch.Tensor:
-        """(B, 16000) cuda fp32 -> (B, 1, 90, 101)."""
+    # Every call takes the feature options explicitly (``opts``: FeatOptions); the handle keeps none.
+    def feat_forward(self, audio: torch.Tensor, normalize: bool = True, opts: FeatOptions = TRAINING_CONFIG) -> torch.Tensor:
+        """(B, 16000) cuda fp32 -> (B, 1, 90 | 103, 101)."""
         audio = self._dev_f32(audio, "audio")
         if audio.dim() != 2 or audio.shape[1] != SEGMENT:
             raise CoughB200Error(f"audio must be (B, {SEGMENT}), got {tuple(audio.shape)}")
         B = audio.shape[0]
-        out = torch.empty(B, 1, self.n_features, N_FRAMES, device=audio.device, dtype=torch.float32)
-        self._check(self.lib.cd_feat_forward(self._h, _ptr(audio), SEGMENT, B, _ptr(out), 1 if normalize else 0, self._stream()), "cd_feat_forward")
+        out = torch.empty(B, 1, opts.n_features, N_FRAMES, device=audio.device, dtype=torch.float32)
+        self._check(self.lib.cd_feat_forward(self._h, _ptr(audio), SEGMENT, B, _ptr(out), opts.flags(normalize),
+                                             opts.pre_emphasis_coef, self._stream()), "cd_feat_forward")
         return out
 
-    def feat_forward_i16(self, audio: torch.Tensor, normalize: bool = True) -> torch.Tensor:
-        """(B, 16000) cuda int16 PCM -> (B, 1, 90, 101); equals feat_forward(audio / 32768) bit for bit."""
+    def feat_forward_i16(self, audio: torch.Tensor, normalize: bool = True, opts: FeatOptions = TRAINING_CONFIG) -> torch.Tensor:
+        """(B, 16000) cuda int16 PCM -> (B, 1, 90 | 103, 101); equals feat_forward(audio / 32768) bit for bit."""
         if not (audio.is_cuda and audio.dtype == torch.int16 and audio.dim() == 2 and audio.shape[1] == SEGMENT):
             raise CoughB200Error("feat_forward_i16 wants a cuda int16 (B, 16000) tensor")
         audio = audio.contiguous()
         B = audio.shape[0]
-        out = torch.empty(B, 1, self.n_features, N_FRAMES, device=audio.device, dtype=torch.float32)
-        self._check(self.lib.cd_feat_forward_i16(self._h, _ptr(audio), SEGMENT, B, _ptr(out), 1 if normalize else 0,
-                                                 self._stream()), "cd_feat_forward_i16")
+        out = torch.empty(B, 1, opts.n_features, N_FRAMES, device=audio.device, dtype=torch.float32)
+        self._check(self.lib.cd_feat_forward_i16(self._h, _ptr(audio), SEGMENT, B, _ptr(out), opts.flags(normalize),
+                                                 opts.pre_emphasis_coef, self._stream()), "cd_feat_forward_i16")
         return out
 
-    def feat_forward_var(self, flat: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:
+    def feat_forward_var(self, flat: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor,
+                         opts: FeatOptions = TRAINING_CONFIG) -> torch.Tensor:
         flat = self._dev_f32(flat, "audio")
         offsets = offsets.to(device=flat.device, dtype=torch.int64).contiguous()
         lengths = lengths.to(device=flat.device, dtype=torch.int32).contiguous()
         B = offsets.numel()
-        out = torch.empty(B, 1, self.n_features, N_FRAMES, device=flat.device, dtype=torch.float32)
+        out = torch.empty(B, 1, opts.n_features, N_FRAMES, device=flat.device, dtype=torch.float32)
         self._check(self.lib.cd_feat_forward_var(self._h, _ptr(flat), _ptr(offsets), _ptr(lengths), B, _ptr(out),
-                                                 self._stream()), "cd_feat_forward_var")
+                                                 opts.flags(), opts.pre_emphasis_coef, self._stream()), "cd_feat_forward_var")
         return out
 
     def stream_windows(self, n: int, hop: int) -> int:
         return int(self.lib.cd_stream_windows(n, hop))
 
-    def feat_forward_stream(self, audio: torch.Tensor, hop: int) -> torch.Tensor:
+    def feat_forward_stream(self, audio: torch.Tensor, hop: int, opts: FeatOptions = TRAINING_CONFIG) -> torch.Tensor:
         audio = self._dev_f32(audio.reshape(-1), "audio")
         n = audio.numel()
         nw = self.stream_windows(n, hop)
-        out = torch.empty(nw, 1, self.n_features, N_FRAMES, device=audio.device, dtype=torch.float32)
-        self._check(self.lib.cd_feat_forward_stream(self._h, _ptr(audio), n, hop, nw, _ptr(out), self._stream()),
-                    "cd_feat_forward_stream")
+        out = torch.empty(nw, 1, opts.n_features, N_FRAMES, device=audio.device, dtype=torch.float32)
+        self._check(self.lib.cd_feat_forward_stream(self._h, _ptr(audio), n, hop, nw, _ptr(out), opts.flags(),
+                                                    opts.pre_emphasis_coef, self._stream()), "cd_feat_forward_stream")
         return out
 
     # ---- resampling -------------------------------------------------------------------------
@@ -275,28 +285,31 @@ class Handle:
         return d
 
     # ---- end to end -------------------------------------------------------------------------
-    def e2e_forward(self, audio: torch.Tensor, precision: int = PRECISION_BF16, return_features: bool = False):
+    def e2e_forward(self, audio: torch.Tensor, precision: int = PRECISION_BF16, return_features: bool = False,
+                    opts: FeatOptions = TRAINING_CONFIG, normalize: bool = True):
         audio = self._dev_f32(audio, "audio")
         if audio.dim() != 2 or audio.shape[1] != SEGMENT:
             raise CoughB200Error(f"audio must be (B, {SEGMENT}), got {tuple(audio.shape)}")
         B = audio.shape[0]
         logits = torch.empty(B, 2, device=audio.device, dtype=torch.float32)
-        feat = torch.empty(B, 1, self.n_features, N_FRAMES, device=audio.device, dtype=torch.float32) if return_features else None
-        self._check(self.lib.cd_e2e_forward(self._h, _ptr(audio), SEGMENT, B, _ptr(logits), _ptr(feat), precision,
-                                            self._stream()), "cd_e2e_forward")
+        feat = torch.empty(B, 1, opts.n_features, N_FRAMES, device=audio.device, dtype=torch.float32) if return_features else None
+        self._check(self.lib.cd_e2e_forward(self._h, _ptr(audio), SEGMENT, B, _ptr(logits), _ptr(feat), opts.flags(normalize),
+                                            opts.pre_emphasis_coef, precision, self._stream()), "cd_e2e_forward")
         return (logits, feat) if return_features else logits
 
-    def e2e_forward_stream(self, audio: torch.Tensor, hop: int, precision: int = PRECISION_BF16) -> torch.Tensor:
+    def e2e_forward_stream(self, audio: torch.Tensor, hop: int, precision: int = PRECISION_BF16,
+                           opts: FeatOptions = TRAINING_CONFIG) -> torch.Tensor:
         audio = self._dev_f32(audio.reshape(-1), "audio")
         n = audio.numel()
         nw = self.stream_windows(n, hop)
         logits = torch.empty(nw, 2, device=audio.device, dtype=torch.float32)
-        self._check(self.lib.cd_e2e_forward_stream(self._h, _ptr(audio), n, hop, nw, _ptr(logits), precision,
-                                                   self._stream()), "cd_e2e_forward_stream")
+        self._check(self.lib.cd_e2e_forward_stream(self._h, _ptr(audio), n, hop, nw, _ptr(logits), opts.flags(),
+                                                   opts.pre_emphasis_coef, precision, self._stream()), "cd_e2e_forward_stream")
         return logits
 
-    def e2e_forward_host(self, audio: torch.Tensor, precision: int = PRECISION_BF16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Host (B, 16000) fp32 tensor (ideally pinned) -> host (B, 2) logits; copies are inside the call."""
+    def e2e_forward_host(self, audio: torch.Tensor, precision: int = PRECISION_BF16, out: Optional[torch.Tensor] = None,
+                         opts: FeatOptions = TRAINING_CONFIG, normalize: bool = True) -> torch.Tensor:
+        """Host (B, 16000) fp32 or int16 tensor (ideally pinned) -> host (B, 2) logits; copies are inside the call."""
         if audio.is_cuda or audio.dtype not in (torch.float32, torch.int16) or audio.dim() != 2 or audio.shape[1] != SEGMENT:
             raise CoughB200Error("e2e_forward_host wants a CPU float32 or int16 (B, 16000) tensor")
         audio = audio.contiguous()
@@ -304,11 +317,13 @@ class Handle:
         if out is None:
             out = torch.empty(B, 2, dtype=torch.float32).pin_memory()
         fn = self.lib.cd_e2e_forward_host_i16 if audio.dtype == torch.int16 else self.lib.cd_e2e_forward_host
-        self._check(fn(self._h, _ptr(audio), B, _ptr(out), precision), "cd_e2e_forward_host")
+        self._check(fn(self._h, _ptr(audio), B, _ptr(out), opts.flags(normalize), opts.pre_emphasis_coef, precision),
+                    "cd_e2e_forward_host")
         return out
 
 
 _handles: Dict[int, Handle] = {}
+_handles_lock = threading.Lock()              # not _lock: Handle() takes that one in load_library()
 
 
 def get_handle(device=None) -> Handle:
@@ -321,12 +336,10 @@ def get_handle(device=None) -> Handle:
     if isinstance(device, torch.device):
         device = device.index if device.index is not None else torch.cuda.current_device()
     device = int(device)
-    with _lock:
+    with _handles_lock:                       # check-and-create under one lock: never two shared handles per device
         h = _handles.get(device)
-    if h is None:
-        h = Handle(device)
-        with _lock:
-            _handles[device] = h
+        if h is None:
+            h = _handles[device] = Handle(device)
     return h
 
 

@@ -35,6 +35,18 @@ int ensure_ws(cd_handle* h, size_t bytes) {
     return CD_OK;
 }
 
+// Successive users of the handle's workspaces on different streams are ordered with one event (cd_common.cuh).
+static int ws_acquire(cd_handle* h, cudaStream_t s) {
+    if (h->ws_busy && h->ws_stream != s) CD_CUDA(h, cudaStreamWaitEvent(s, h->ws_event, 0));
+    return CD_OK;
+}
+static int ws_release(cd_handle* h, cudaStream_t s) {
+    CD_CUDA(h, cudaEventRecord(h->ws_event, s));
+    h->ws_stream = s;
+    h->ws_busy = true;
+    return CD_OK;
+}
+
 int build_feat_tables(cd_handle* h);
 int init_cnn_fp32(cd_handle* h);
 int init_cnn_tc(cd_handle* h);
@@ -43,8 +55,9 @@ int launch_cnn_tc(cd_handle* h, const float* d_feat, int64_t B, float* d_logits,
 size_t cnn_tc_ws_bytes(int64_t B);
 __nv_bfloat16* cnn_tc_map_ptr(cd_handle* h);
 int ensure_tc_ws(cd_handle* h, int nf = kFeat);
-int launch_features_i16(cd_handle* h, const int16_t* d_audio, int64_t stride, int mode, int64_t B, float* d_feat,
-                        __nv_bfloat16* d_map, cudaStream_t s);
+int launch_features_i16(cd_handle* h, const int16_t* d_audio, int64_t stride, int mode, float coef, int64_t B,
+                        float* d_feat, __nv_bfloat16* d_map, cudaStream_t s);
+void free_resample_tables(cd_handle* h);
 int64_t resample_length(int64_t n_in, int orig_sr, int new_sr);
 int launch_resample(cd_handle* h, const float* d_in, int64_t rows, int64_t n_in, int orig_sr, int new_sr, float* d_out,
                     cudaStream_t s);
@@ -130,6 +143,8 @@ int cd_create(int device, cd_handle** out) {
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
     int rc = build_feat_tables(h);
+    if (rc == CD_OK && cudaEventCreateWithFlags(&h->ws_event, cudaEventDisableTiming) != cudaSuccess)
+        rc = set_err(h, CD_E_CUDA, "cudaEventCreate");
     if (rc == CD_OK) rc = init_cnn_fp32(h);
     if (rc == CD_OK) rc = init_cnn_tc(h);
     if (rc != CD_OK) {
@@ -148,75 +163,87 @@ int cd_destroy(cd_handle* h) {
     cudaFree(h->d_tables);
     cudaFree(h->d_wblob);
     cudaFree(h->d_wblob_bf16);
-    cudaFree(h->d_ws_tc);
+    cudaFree(h->d_ws_tc_fam[0]);
+    cudaFree(h->d_ws_tc_fam[1]);
     cudaFree(h->d_ws_stream);
     cudaFree(h->d_ws);
     for (int i = 0; i < 3; ++i) {
         if (h->pipe_streams[i]) cudaStreamDestroy(h->pipe_streams[i]);
         if (h->pipe_events[i]) cudaEventDestroy(h->pipe_events[i]);
-        if (h->pinned_in[i]) cudaFreeHost(h->pinned_in[i]);
         cudaFree(h->dev_in[i]);
     }
     cudaFree(h->dev_logits);
-    if (h->pinned_logits) cudaFreeHost(h->pinned_logits);
+    free_resample_tables(h);
+    if (h->ws_event) cudaEventDestroy(h->ws_event);
     delete h;
     return CD_OK;
 }
 
 // ---- features --------------------------------------------------------------------------------
 
+// CD_FEAT_* flags of a call -> FeatMode bits of the kernels; nothing is taken from the handle.
+static bool feat_flags_ok(cd_handle* h, int flags, float coef, const char* who) {
+    if (flags & ~(CD_FEAT_NORMALIZE | CD_FEAT_PRE_EMPHASIS | CD_FEAT_PCEN | CD_FEAT_DELTA_DELTA)) {
+        set_err(h, CD_E_ARG, (std::string(who) + ": flags are CD_FEAT_NORMALIZE | CD_FEAT_PRE_EMPHASIS | CD_FEAT_PCEN | CD_FEAT_DELTA_DELTA").c_str());
+        return false;
+    }
+    if ((flags & CD_FEAT_PRE_EMPHASIS) && !(coef >= 0.f && coef <= 1.f)) {
+        set_err(h, CD_E_ARG, (std::string(who) + ": pre_emphasis_coef must be in [0, 1]").c_str());
+        return false;
+    }
+    return true;
+}
 static int feat_mode_bits(int flags) {
     return ((flags & CD_FEAT_NORMALIZE) ? 0 : kModeNoNormalize) | ((flags & CD_FEAT_PRE_EMPHASIS) ? kModePreEmph : 0) |
            ((flags & CD_FEAT_PCEN) ? kModePcen : 0) | ((flags & CD_FEAT_DELTA_DELTA) ? kModeDeltaDelta : 0);
 }
 
-int cd_feat_options(cd_handle* h, int flags, float pre_emphasis_coef) {
-    if (!h) return CD_E_ARG;
-    if (flags & ~(CD_FEAT_PRE_EMPHASIS | CD_FEAT_PCEN | CD_FEAT_DELTA_DELTA))
-        return set_err(h, CD_E_ARG, "cd_feat_options: flags are CD_FEAT_PRE_EMPHASIS | CD_FEAT_PCEN | CD_FEAT_DELTA_DELTA");
-    if (!(pre_emphasis_coef >= 0.f && pre_emphasis_coef <= 1.f))
-        return set_err(h, CD_E_ARG, "cd_feat_options: pre_emphasis_coef must be in [0, 1]");
-    h->feat_opts = feat_mode_bits(flags | CD_FEAT_NORMALIZE);
-    h->pre_coef = pre_emphasis_coef;
-    return CD_OK;
-}
-
 int cd_feat_forward(cd_handle* h, const float* d_audio, int64_t stride, int64_t B, float* d_feat, int flags,
-                    void* stream) {
+                    float pre_emphasis_coef, void* stream) {
     if (!h) return CD_E_ARG;
     if (B < 0 || stride < kSeg || (B > 0 && (!d_audio || !d_feat)))
         return set_err(h, CD_E_ARG, "cd_feat_forward: bad argument (need stride >= 16000, non-NULL buffers)");
+    if (!feat_flags_ok(h, flags, pre_emphasis_coef, "cd_feat_forward")) return CD_E_ARG;
     DeviceGuard g(h->device);
-    const int mode = kModeFixed | feat_mode_bits(flags);
-    return launch_features(h, d_audio, nullptr, nullptr, stride, mode, B, d_feat, nullptr, (cudaStream_t)stream);
+    return launch_features(h, d_audio, nullptr, nullptr, stride, kModeFixed | feat_mode_bits(flags), pre_emphasis_coef, B,
+                           d_feat, nullptr, (cudaStream_t)stream);
 }
 
 int cd_feat_forward_i16(cd_handle* h, const int16_t* d_audio, int64_t stride, int64_t B, float* d_feat, int flags,
-                        void* stream) {
+                        float pre_emphasis_coef, void* stream) {
     if (!h) return CD_E_ARG;
     if (B < 0 || stride < kSeg || (stride & 7) || (B > 0 && (!d_audio || !d_feat)))
         return set_err(h, CD_E_ARG, "cd_feat_forward_i16: bad argument (need stride >= 16000 and a multiple of 8)");
+    if (!feat_flags_ok(h, flags, pre_emphasis_coef, "cd_feat_forward_i16")) return CD_E_ARG;
     DeviceGuard g(h->device);
-    const int mode = kModeFixed | feat_mode_bits(flags);
-    return launch_features_i16(h, d_audio, stride, mode, B, d_feat, nullptr, (cudaStream_t)stream);
+    return launch_features_i16(h, d_audio, stride, kModeFixed | feat_mode_bits(flags), pre_emphasis_coef, B, d_feat, nullptr,
+                               (cudaStream_t)stream);
 }
 
 int cd_feat_forward_var(cd_handle* h, const float* d_audio, const int64_t* d_offsets, const int32_t* d_lengths,
-                        int64_t B, float* d_feat, void* stream) {
+                        int64_t B, float* d_feat, int flags, float pre_emphasis_coef, void* stream) {
     if (!h) return CD_E_ARG;
     if (B < 0 || (B > 0 && (!d_audio || !d_offsets || !d_lengths || !d_feat)))
         return set_err(h, CD_E_ARG, "cd_feat_forward_var: bad argument");
+    if (!feat_flags_ok(h, flags, pre_emphasis_coef, "cd_feat_forward_var")) return CD_E_ARG;
     DeviceGuard g(h->device);
-    return launch_features(h, d_audio, d_offsets, d_lengths, 0, kModeVar, B, d_feat, nullptr, (cudaStream_t)stream);
+    return launch_features(h, d_audio, d_offsets, d_lengths, 0, kModeVar | feat_mode_bits(flags | CD_FEAT_NORMALIZE),
+                           pre_emphasis_coef, B, d_feat, nullptr, (cudaStream_t)stream);
 }
 
 int cd_feat_forward_stream(cd_handle* h, const float* d_audio, int64_t n_samples, int64_t hop, int64_t n_windows,
-                           float* d_feat, void* stream) {
+                           float* d_feat, int flags, float pre_emphasis_coef, void* stream) {
     if (!h) return CD_E_ARG;
     if (hop <= 0 || n_windows != cd_stream_windows(n_samples, hop) || (n_windows > 0 && (!d_audio || !d_feat)))
         return set_err(h, CD_E_ARG, "cd_feat_forward_stream: hop must be > 0 and n_windows == cd_stream_windows()");
+    if (!feat_flags_ok(h, flags, pre_emphasis_coef, "cd_feat_forward_stream")) return CD_E_ARG;
     DeviceGuard g(h->device);
-    return launch_features(h, d_audio, nullptr, nullptr, hop, kModeStream, n_windows, d_feat, nullptr, (cudaStream_t)stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = ws_acquire(h, s);                               // the shared-STFT path keeps its frames in d_ws_stream
+    if (rc == CD_OK)
+        rc = launch_features(h, d_audio, nullptr, nullptr, hop, kModeStream | feat_mode_bits(flags | CD_FEAT_NORMALIZE),
+                             pre_emphasis_coef, n_windows, d_feat, nullptr, s);
+    return rc == CD_OK ? ws_release(h, s) : rc;
 }
 
 // ---- resampling ------------------------------------------------------------------------------
@@ -294,17 +321,14 @@ static int cnn_forward_impl(cd_handle* h, const float* d_feat, int n_rows, int64
     if (!h->weights_loaded) return set_err(h, CD_E_STATE, "cd_cnn_forward: call cd_cnn_load first");
     if (n_rows != kFeat && n_rows != kFeatDD)
         return set_err(h, CD_E_ARG, "cd_cnn_forward: the network is built for 90 or 103 (use_delta_delta) feature rows");
-    if (precision == CD_PRECISION_FP32) {
-        int rc = ensure_ws(h, cnn_fp32_ws_bytes(B));
-        if (rc != CD_OK) return rc;
-        return launch_cnn_fp32(h, d_feat, B, d_logits, s, n_rows);
-    }
-    if (precision == CD_PRECISION_BF16) {
-        int rc = ensure_ws(h, cnn_tc_ws_bytes(B));
-        if (rc != CD_OK) return rc;
-        return launch_cnn_tc(h, d_feat, B, d_logits, s, n_rows);
-    }
-    return set_err(h, CD_E_ARG, "precision must be CD_PRECISION_FP32 or CD_PRECISION_BF16");
+    if (precision != CD_PRECISION_FP32 && precision != CD_PRECISION_BF16)
+        return set_err(h, CD_E_ARG, "precision must be CD_PRECISION_FP32 or CD_PRECISION_BF16");
+    if (B == 0) return CD_OK;
+    const bool tcp = precision == CD_PRECISION_BF16;
+    int rc = ensure_ws(h, tcp ? cnn_tc_ws_bytes(B) : cnn_fp32_ws_bytes(B));
+    if (rc == CD_OK) rc = ws_acquire(h, s);
+    if (rc == CD_OK) rc = tcp ? launch_cnn_tc(h, d_feat, B, d_logits, s, n_rows) : launch_cnn_fp32(h, d_feat, B, d_logits, s, n_rows);
+    return rc == CD_OK ? ws_release(h, s) : rc;
 }
 
 int cd_cnn_forward(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, int precision, void* stream) {
@@ -338,12 +362,12 @@ int cd_predict(cd_handle* h, const float* d_logits, int64_t B, float threshold, 
 // ---- end to end ------------------------------------------------------------------------------
 
 // Features for the CNN live in a second, separately grown buffer so the CNN workspace can be
-// re-used chunk by chunk.
-static int e2e_impl(cd_handle* h, const float* d_audio, int64_t stride_or_hop, int mode, int64_t B, float* d_logits,
-                    float* d_feat_opt, int precision, cudaStream_t s) {
+// re-used chunk by chunk.  `mode`: FeatMode bits of this call (entry kind + options).
+static int e2e_impl(cd_handle* h, const float* d_audio, int64_t stride_or_hop, int mode, float coef, int64_t B,
+                    float* d_logits, float* d_feat_opt, int precision, cudaStream_t s) {
     if (!h->weights_loaded) return set_err(h, CD_E_STATE, "cd_e2e_forward: call cd_cnn_load first");
     if (B == 0) return CD_OK;
-    const int nf = (h->feat_opts & kModeDeltaDelta) ? kFeatDD : kFeat;      // shape family of this handle's features
+    const int nf = (mode & kModeDeltaDelta) ? kFeatDD : kFeat;              // shape family of this call's features
     const int64_t felems = (int64_t)nf * kFrames;
     // process in slabs so a slab's features stay L2-resident between the two stages.  bf16: the
     // feature kernel writes the stem's bf16 map straight into the CNN workspace (fp32 features only
@@ -354,63 +378,74 @@ static int e2e_impl(cd_handle* h, const float* d_audio, int64_t stride_or_hop, i
     const size_t feat_bytes = (tcp || d_feat_opt) ? 0 : (size_t)slab * felems * sizeof(float);
     int rc = ensure_ws(h, cnn_ws + feat_bytes);
     if (rc == CD_OK && tcp) rc = ensure_tc_ws(h, nf);
+    if (rc == CD_OK) rc = ws_acquire(h, s);
     if (rc != CD_OK) return rc;
     for (int64_t b0 = 0; b0 < B; b0 += slab) {
         const int64_t n = (B - b0) < slab ? (B - b0) : slab;
         float* feat = d_feat_opt ? d_feat_opt + b0 * felems
                                  : (tcp ? nullptr : reinterpret_cast<float*>(reinterpret_cast<char*>(h->d_ws) + cnn_ws));
-        rc = launch_features(h, d_audio + b0 * stride_or_hop, nullptr, nullptr, stride_or_hop, mode, n, feat,
+        rc = launch_features(h, d_audio + b0 * stride_or_hop, nullptr, nullptr, stride_or_hop, mode, coef, n, feat,
                              tcp ? cnn_tc_map_ptr(h) : nullptr, s);
         if (rc != CD_OK) return rc;
         rc = tcp ? launch_cnn_tc(h, nullptr, n, d_logits + b0 * CD_N_CLASSES, s, nf)
                  : launch_cnn_fp32(h, feat, n, d_logits + b0 * CD_N_CLASSES, s, nf);
         if (rc != CD_OK) return rc;
     }
-    return CD_OK;
+    return ws_release(h, s);
 }
 
 int cd_e2e_forward(cd_handle* h, const float* d_audio, int64_t stride, int64_t B, float* d_logits, float* d_feat_opt,
-                   int precision, void* stream) {
+                   int flags, float pre_emphasis_coef, int precision, void* stream) {
     if (!h) return CD_E_ARG;
     if (B < 0 || stride < kSeg || (B > 0 && (!d_audio || !d_logits)))
         return set_err(h, CD_E_ARG, "cd_e2e_forward: bad argument");
     if (precision != CD_PRECISION_FP32 && precision != CD_PRECISION_BF16)
         return set_err(h, CD_E_ARG, "precision must be CD_PRECISION_FP32 or CD_PRECISION_BF16");
+    if (!feat_flags_ok(h, flags, pre_emphasis_coef, "cd_e2e_forward")) return CD_E_ARG;
     DeviceGuard g(h->device);
-    return e2e_impl(h, d_audio, stride, kModeFixed, B, d_logits, d_feat_opt, precision, (cudaStream_t)stream);
+    return e2e_impl(h, d_audio, stride, kModeFixed | feat_mode_bits(flags), pre_emphasis_coef, B, d_logits, d_feat_opt,
+                    precision, (cudaStream_t)stream);
 }
 
 int cd_e2e_forward_stream(cd_handle* h, const float* d_audio, int64_t n_samples, int64_t hop, int64_t n_windows,
-                          float* d_logits, int precision, void* stream) {
+                          float* d_logits, int flags, float pre_emphasis_coef, int precision, void* stream) {
     if (!h) return CD_E_ARG;
     if (hop <= 0 || n_windows != cd_stream_windows(n_samples, hop) || (n_windows > 0 && (!d_audio || !d_logits)))
         return set_err(h, CD_E_ARG, "cd_e2e_forward_stream: bad argument");
     if (precision != CD_PRECISION_FP32 && precision != CD_PRECISION_BF16)
         return set_err(h, CD_E_ARG, "precision must be CD_PRECISION_FP32 or CD_PRECISION_BF16");
+    if (!feat_flags_ok(h, flags, pre_emphasis_coef, "cd_e2e_forward_stream")) return CD_E_ARG;
     DeviceGuard g(h->device);
-    return e2e_impl(h, d_audio, hop, kModeStream, n_windows, d_logits, nullptr, precision, (cudaStream_t)stream);
+    return e2e_impl(h, d_audio, hop, kModeStream | feat_mode_bits(flags | CD_FEAT_NORMALIZE), pre_emphasis_coef, n_windows,
+                    d_logits, nullptr, precision, (cudaStream_t)stream);
 }
 
-// Host buffers in, host logits out.  Three-deep pipeline: chunk i is copied host->pinned->device
-// on stream i%3 while chunk i-1 computes and chunk i-2's logits drain.  All three streams share
-// the handle's workspace, so compute of consecutive chunks is serialised with events; copies overlap.
-static int e2e_host_impl(cd_handle* h, const void* h_audio, bool i16, int64_t B, float* h_logits, int precision);
+// Host buffers in, host logits out.  Three-deep pipeline: chunk i is copied host->device on stream i%3 while
+// chunk i-1 computes and chunk i-2's logits drain.  All three streams share the handle's workspace, so
+// compute of consecutive chunks is serialised with events; copies overlap.
+static int e2e_host_impl(cd_handle* h, const void* h_audio, bool i16, int64_t B, float* h_logits, int flags, float coef,
+                         int precision);
 
-int cd_e2e_forward_host(cd_handle* h, const float* h_audio, int64_t B, float* h_logits, int precision) {
-    return e2e_host_impl(h, h_audio, false, B, h_logits, precision);
+int cd_e2e_forward_host(cd_handle* h, const float* h_audio, int64_t B, float* h_logits, int flags,
+                        float pre_emphasis_coef, int precision) {
+    return e2e_host_impl(h, h_audio, false, B, h_logits, flags, pre_emphasis_coef, precision);
 }
 
-int cd_e2e_forward_host_i16(cd_handle* h, const int16_t* h_audio, int64_t B, float* h_logits, int precision) {
-    return e2e_host_impl(h, h_audio, true, B, h_logits, precision);
+int cd_e2e_forward_host_i16(cd_handle* h, const int16_t* h_audio, int64_t B, float* h_logits, int flags,
+                            float pre_emphasis_coef, int precision) {
+    return e2e_host_impl(h, h_audio, true, B, h_logits, flags, pre_emphasis_coef, precision);
 }
 
-static int e2e_host_impl(cd_handle* h, const void* h_audio, bool i16, int64_t B, float* h_logits, int precision) {
+static int e2e_host_impl(cd_handle* h, const void* h_audio, bool i16, int64_t B, float* h_logits, int flags, float coef,
+                         int precision) {
     if (!h) return CD_E_ARG;
     if (B < 0 || (B > 0 && (!h_audio || !h_logits))) return set_err(h, CD_E_ARG, "cd_e2e_forward_host: bad argument");
     if (!h->weights_loaded) return set_err(h, CD_E_STATE, "cd_e2e_forward_host: call cd_cnn_load first");
-    const int nf = (h->feat_opts & kModeDeltaDelta) ? kFeatDD : kFeat;
     if (precision != CD_PRECISION_FP32 && precision != CD_PRECISION_BF16)
         return set_err(h, CD_E_ARG, "precision must be CD_PRECISION_FP32 or CD_PRECISION_BF16");
+    if (!feat_flags_ok(h, flags, coef, "cd_e2e_forward_host")) return CD_E_ARG;
+    const int mode = kModeFixed | feat_mode_bits(flags);
+    const int nf = (mode & kModeDeltaDelta) ? kFeatDD : kFeat;
     if (B == 0) return CD_OK;
     DeviceGuard g(h->device);
     // copy/compute overlap granularity: a chunk's compute (~0.15 ms) hides under its own copy (1.2 ms of fp32), and only
@@ -422,16 +457,15 @@ static int e2e_host_impl(cd_handle* h, const void* h_audio, bool i16, int64_t B,
             CD_CUDA(h, cudaEventCreateWithFlags(&h->pipe_events[i], cudaEventDisableTiming));
             CD_CUDA(h, cudaMalloc(&h->dev_in[i], (size_t)chunk * kSeg * sizeof(float)));
         }
-        h->pipe_chunk = chunk;
     }
     if (h->pipe_logits_cap < B) {
         CD_CUDA(h, cudaDeviceSynchronize());
         cudaFree(h->dev_logits);
         h->dev_logits = nullptr;
+        h->pipe_logits_cap = 0;
         CD_CUDA(h, cudaMalloc(&h->dev_logits, (size_t)B * CD_N_CLASSES * sizeof(float)));
         h->pipe_logits_cap = B;
     }
-    // is the caller's buffer pinned?  (pageable memory is staged by the driver; still correct)
     const bool tcp = precision == CD_PRECISION_BF16;
     const size_t cnn_ws = tcp ? cnn_tc_ws_bytes(chunk) : cnn_fp32_ws_bytes(chunk);
     int rc = ensure_ws(h, cnn_ws + (tcp ? 0 : (size_t)chunk * nf * kFrames * sizeof(float)));
@@ -447,9 +481,10 @@ static int e2e_host_impl(cd_handle* h, const void* h_audio, bool i16, int64_t B,
         CD_CUDA(h, cudaMemcpyAsync(h->dev_in[k], static_cast<const char*>(h_audio) + (size_t)b0 * kSeg * esz, (size_t)n * kSeg * esz,
                                    cudaMemcpyHostToDevice, s));
         if (prev_compute) CD_CUDA(h, cudaStreamWaitEvent(s, prev_compute, 0));   // shared workspace
-        rc = i16 ? launch_features_i16(h, reinterpret_cast<const int16_t*>(h->dev_in[k]), kSeg, kModeFixed, n, feat,
+        else if ((rc = ws_acquire(h, s)) != CD_OK) return rc;                     // ... whoever used it before this call
+        rc = i16 ? launch_features_i16(h, reinterpret_cast<const int16_t*>(h->dev_in[k]), kSeg, mode, coef, n, feat,
                                        tcp ? cnn_tc_map_ptr(h) : nullptr, s)
-                 : launch_features(h, h->dev_in[k], nullptr, nullptr, kSeg, kModeFixed, n, feat,
+                 : launch_features(h, h->dev_in[k], nullptr, nullptr, kSeg, mode, coef, n, feat,
                                    tcp ? cnn_tc_map_ptr(h) : nullptr, s);
         if (rc != CD_OK) return rc;
         rc = tcp ? launch_cnn_tc(h, nullptr, n, h->dev_logits + b0 * CD_N_CLASSES, s, nf)
@@ -461,6 +496,7 @@ static int e2e_host_impl(cd_handle* h, const void* h_audio, bool i16, int64_t B,
                                    (size_t)n * CD_N_CLASSES * sizeof(float), cudaMemcpyDeviceToHost, s));
     }
     for (int i = 0; i < 3; ++i) CD_CUDA(h, cudaStreamSynchronize(h->pipe_streams[i]));
+    h->ws_busy = false;                                      // everything this call enqueued has completed
     return CD_OK;
 }
 

@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <vector>
 
 #include "../../include/cough_b200.h"
 
@@ -84,6 +85,21 @@ struct CnnWeightsF32 {
     float* fc_w;    float* fc_b;        // [2][128], [2]
 };
 
+// Folded network as the tensor-core kernels read it: device pointers into cd_handle::d_wblob_bf16 (packed bf16 operand
+// images followed by an fp32 blob of biases and the classifier).  Owned by the handle, rewritten by cd_cnn_load.
+struct TcWeights {
+    __nv_bfloat16 *b0c1, *b0sk, *b0c2, *b1c1, *b1sk, *b1c2;
+    __nv_bfloat16* stem_w;
+    float *stem_b, *b0c1_b, *b0sk_b, *b0c2_b, *b1c1_b, *b1sk_b, *b1c2_b, *fc_w, *fc_b;
+};
+
+// Polyphase filter bank of one (orig, new) rate pair (resample.cu); device buffers owned by the handle.
+struct ResampleTable {
+    int orig, neu, width, support;     // reduced rates, torchaudio's `width`, taps kept per phase
+    int* d_k0;                         // [neu] first kept tap (index into the padded input window)
+    float* d_taps;                     // [neu][support]
+};
+
 }  // namespace cd
 
 struct cd_handle {
@@ -93,15 +109,16 @@ struct cd_handle {
     int64_t launches = 0;
 
     cd::FeatTables* d_tables = nullptr;
-    int feat_opts = 0;                   // kModePreEmph | kModePcen, OR-ed into every feature launch (cd_feat_options)
-    float pre_coef = 0.97f;              // pre_emphasis_coef (src/preprocessing.py:44)
+    std::vector<cd::ResampleTable> resample_tables;   // built on first use of a rate pair, freed by cd_destroy
 
     bool weights_loaded = false;
     float* d_wblob = nullptr;            // one allocation holding every folded fp32 tensor
     cd::CnnWeightsF32 w32{};
     __nv_bfloat16* d_wblob_bf16 = nullptr;
-    unsigned char* d_ws_tc = nullptr;    // tensor-core path activations (fixed layout, zero-initialised pads)
-    int tc_plan_nf = 0;                  // shape family (feature rows) that layout was zeroed for
+    cd::TcWeights tcw{};                 // pointers into d_wblob_bf16
+    unsigned char* d_ws_tc_fam[2] = {nullptr, nullptr};   // tensor-core path activations per shape family (90 | 103 rows):
+                                                          // fixed layout, pads zeroed once at allocation
+    unsigned char* d_ws_tc = nullptr;    // the family the current call uses (set by ensure_tc_ws)
 
     float* d_ws_stream = nullptr;        // shared-STFT streaming: mel power of the global frames + block maxima
     size_t ws_stream_bytes = 0;
@@ -109,15 +126,18 @@ struct cd_handle {
     // workspace (grown on demand, never shrunk)
     float* d_ws = nullptr;
     size_t ws_bytes = 0;
+    // The workspaces (d_ws, d_ws_tc, d_ws_stream) are shared by every call on this handle.  Each launch sequence that
+    // touches them ends by recording ws_event on its stream; the next one, if it runs on a DIFFERENT stream, first
+    // makes that stream wait for the event (ws_acquire / ws_release in api.cu), so callers may alternate streams.
+    cudaEvent_t ws_event = nullptr;
+    cudaStream_t ws_stream = nullptr;
+    bool ws_busy = false;
 
     // host-pipeline state for cd_e2e_forward_host
     cudaStream_t pipe_streams[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t pipe_events[3] = {nullptr, nullptr, nullptr};
-    float* pinned_in[3] = {nullptr, nullptr, nullptr};
     float* dev_in[3] = {nullptr, nullptr, nullptr};
     float* dev_logits = nullptr;
-    float* pinned_logits = nullptr;
-    int64_t pipe_chunk = 0;
     int64_t pipe_logits_cap = 0;
 };
 
@@ -133,8 +153,10 @@ int ensure_ws(cd_handle* h, size_t bytes);
     } while (0)
 
 // kernels' host launchers (each returns a CD_* code and bumps h->launches)
+// mode: FeatMode bits, every option explicit per launch (nothing is remembered on the handle); coef: pre_emphasis_coef
 int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets, const int32_t* d_lengths,
-                    int64_t stride_or_hop, int mode, int64_t B, float* d_feat, __nv_bfloat16* d_map, cudaStream_t s);
+                    int64_t stride_or_hop, int mode, float coef, int64_t B, float* d_feat, __nv_bfloat16* d_map,
+                    cudaStream_t s);
 int launch_cnn_fp32(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, cudaStream_t s, int nf = kFeat);
 size_t cnn_fp32_ws_bytes(int64_t B);
 

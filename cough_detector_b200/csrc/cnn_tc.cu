@@ -1106,13 +1106,6 @@ head_kernel(const float* __restrict__ x2, const float* __restrict__ fcw, const f
 // ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
-struct TcWeights {                 // device pointers into h->d_wblob_bf16 (bf16 parts) and a float blob
-    __nv_bfloat16 *b0c1, *b0sk, *b0c2, *b1c1, *b1sk, *b1c2;
-    __nv_bfloat16* stem_w;
-    float *stem_b, *b0c1_b, *b0sk_b, *b0c2_b, *b1c1_b, *b1sk_b, *b1c2_b, *fc_w, *fc_b;
-};
-static TcWeights g_tcw[64];        // per device index
-
 // folded weights [tap][cin][cout] fp32 -> [kc][cout rows x 128 B] bf16, SWIZZLE_128B K-major, K padded to 64
 static void pack_weights(const std::vector<float>& wf, int taps, int cin, int cout, std::vector<__nv_bfloat16>& out) {
     const int ktot = taps * cin, nkc = (ktot + 63) / 64;
@@ -1135,7 +1128,6 @@ int init_cnn_tc(cd_handle* h) {
 
 // wf/bf: [stem, b0c1, b0sk, b0c2, b1c1, b1sk, b1c2, fc] folded fp32, conv weights as [tap][cin][cout]
 int upload_cnn_tc(cd_handle* h, const std::vector<std::vector<float>>& wf, const std::vector<std::vector<float>>& bf) {
-    if (h->device >= 64) return set_err(h, CD_E_ARG, "device index >= 64");
     std::vector<__nv_bfloat16> packs[7];
     const int spec[6][3] = {{9, 32, 64}, {1, 32, 64}, {9, 64, 64}, {9, 64, 128}, {1, 64, 128}, {9, 128, 128}};
     size_t total_bf = 0;
@@ -1185,7 +1177,7 @@ int upload_cnn_tc(cd_handle* h, const std::vector<std::vector<float>>& wf, const
     memcpy(host.data() + bf_bytes, fblob.data(), f_bytes);
     CD_CUDA(h, cudaMemcpy(h->d_wblob_bf16, host.data(), host.size(), cudaMemcpyHostToDevice));
     float* fbase = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(h->d_wblob_bf16) + bf_bytes);
-    TcWeights& W = g_tcw[h->device];
+    TcWeights& W = h->tcw;
     W.b0c1 = dptr[0]; W.b0sk = dptr[1]; W.b0c2 = dptr[2]; W.b1c1 = dptr[3]; W.b1sk = dptr[4]; W.b1c2 = dptr[5];
     W.stem_w = dptr[6]; W.stem_b = fbase + o_stem_b; W.b0c1_b = fbase + o_b0c1; W.b0sk_b = fbase + o_b0sk;
     W.b0c2_b = fbase + o_b0c2; W.b1c1_b = fbase + o_b1c1; W.b1sk_b = fbase + o_b1sk; W.b1c2_b = fbase + o_b1c2;
@@ -1223,17 +1215,19 @@ constexpr int64_t kTcWsBytes = TcPlan<kFeatDD>::kBytes > TcPlan<kFeat>::kBytes ?
 
 size_t cnn_tc_ws_bytes(int64_t) { return 0; }      // nothing from the shared workspace
 
-// nf: the shape family (90 | 103 feature rows) the next launches will use
+// nf: the shape family (90 | 103 feature rows) the next launches will use.  Each family has its own workspace
+// (allocated and zeroed on first use, 2.9 / 3.4 GB of 180), so switching families costs nothing and calls of
+// different families never share padding.
 int ensure_tc_ws(cd_handle* h, int nf) {
-    if (h->d_ws_tc && h->tc_plan_nf == nf) return CD_OK;
-    CD_CUDA(h, cudaDeviceSynchronize());       // callers' streams are non-blocking: nothing may still read the old layout
-    if (!h->d_ws_tc) {
-        cudaError_t e = cudaMalloc(&h->d_ws_tc, (size_t)kTcWsBytes);
+    const int fam = nf == kFeatDD ? 1 : 0;
+    if (!h->d_ws_tc_fam[fam]) {
+        const size_t bytes = (size_t)(fam ? TcPlan<kFeatDD>::kBytes : TcPlan<kFeat>::kBytes);
+        cudaError_t e = cudaMalloc(&h->d_ws_tc_fam[fam], bytes);
         if (e != cudaSuccess) return set_err(h, CD_E_NOMEM, "tensor-core workspace allocation", e);
+        CD_CUDA(h, cudaMemset(h->d_ws_tc_fam[fam], 0, bytes));
+        CD_CUDA(h, cudaDeviceSynchronize());       // callers' streams are non-blocking: order the zero-fill before them
     }
-    CD_CUDA(h, cudaMemset(h->d_ws_tc, 0, (size_t)kTcWsBytes));
-    CD_CUDA(h, cudaDeviceSynchronize());       // ... and the zero-fill is ordered before them
-    h->tc_plan_nf = nf;
+    h->d_ws_tc = h->d_ws_tc_fam[fam];
     return CD_OK;
 }
 
@@ -1262,7 +1256,7 @@ template <int NF>
 static int launch_cnn_tc_nf(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, cudaStream_t s) {
     using N = NetShape<NF>;
     using P = TcPlan<NF>;
-    const TcWeights& W = g_tcw[h->device];
+    const TcWeights& W = h->tcw;
     int rc0 = ensure_tc_ws(h, NF);
     if (rc0 != CD_OK) return rc0;
     unsigned char* ws = h->d_ws_tc;

@@ -60,14 +60,22 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t coun
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded like the tensor-core kernels' waits: a bulk copy that never lands traps (-> a launch error the host
+// reports) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();     // ~2 s at 1.9 GHz
+    }
 }
 __device__ __forceinline__ float2 lds64(uint32_t addr) {
     float2 v;
@@ -936,11 +944,10 @@ int build_feat_tables(cd_handle* h) {
     } while (0)
 
 int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets, const int32_t* d_lengths,
-                    int64_t stride_or_hop, int mode, int64_t B, float* d_feat, __nv_bfloat16* d_map, cudaStream_t s) {
+                    int64_t stride_or_hop, int mode, float coef, int64_t B, float* d_feat, __nv_bfloat16* d_map,
+                    cudaStream_t s) {
     if (B == 0) return CD_OK;
-    mode |= h->feat_opts;
     const bool pre = (mode & kModePreEmph) != 0, pcen = (mode & kModePcen) != 0;
-    const float coef = h->pre_coef;
     const int64_t slots = 2 * (int64_t)h->sm_count;     // two resident CTAs per SM
     if ((mode & kModeMask) == kModeStream && stride_or_hop % kHop == 0 && stride_or_hop <= kSeg / 2 && B >= 2) {
         // overlapping windows on the frame grid: share the STFT frames
@@ -987,13 +994,11 @@ int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets
 }
 
 // int16 PCM clips (fixed length): same kernel, 32 000-byte bulk copies
-int launch_features_i16(cd_handle* h, const int16_t* d_audio, int64_t stride, int mode, int64_t B, float* d_feat,
-                        __nv_bfloat16* d_map, cudaStream_t s) {
+int launch_features_i16(cd_handle* h, const int16_t* d_audio, int64_t stride, int mode, float coef, int64_t B,
+                        float* d_feat, __nv_bfloat16* d_map, cudaStream_t s) {
     if (B == 0) return CD_OK;
     const int64_t slots = 2 * (int64_t)h->sm_count;
-    mode |= h->feat_opts;
     const bool pre = (mode & kModePreEmph) != 0, pcen = (mode & kModePcen) != 0;
-    const float coef = h->pre_coef;
 #define CD_CALL(P, Q)                                                                                            \
     feat_kernel<int16_t, P, Q><<<(int)(B < slots ? B : slots), kFeatThreads, sizeof(FeatSmem), s>>>(              \
         d_audio, nullptr, nullptr, stride, mode, B, d_feat, d_map, h->d_tables, coef)

@@ -11,18 +11,20 @@
 
 namespace cd {
 
-struct ResampleTable {
-    int orig, neu, width, support;     // reduced rates, torchaudio's `width`, taps kept per phase
-    int* d_k0;                         // [neu] first kept tap (index into the padded input window)
-    float* d_taps;                     // [neu][support]
-};
-static std::vector<ResampleTable> g_tables[64];
+// The filter banks live in the handle (cd_handle::resample_tables): no process-wide state, freed by cd_destroy.
+void free_resample_tables(cd_handle* h) {
+    for (ResampleTable& t : h->resample_tables) {
+        cudaFree(t.d_k0);
+        cudaFree(t.d_taps);
+    }
+    h->resample_tables.clear();
+}
 
 static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 
 static int get_table(cd_handle* h, int orig_sr, int new_sr, ResampleTable* out) {
     const int g = gcd_i(orig_sr, new_sr), orig = orig_sr / g, neu = new_sr / g;
-    for (const ResampleTable& t : g_tables[h->device])
+    for (const ResampleTable& t : h->resample_tables)
         if (t.orig == orig && t.neu == neu) {
             *out = t;
             return CD_OK;
@@ -63,7 +65,7 @@ static int get_table(cd_handle* h, int orig_sr, int new_sr, ResampleTable* out) 
     CD_CUDA(h, cudaMalloc(&t.d_taps, taps.size() * sizeof(float)));
     CD_CUDA(h, cudaMemcpy(t.d_k0, k0.data(), neu * sizeof(int), cudaMemcpyHostToDevice));
     CD_CUDA(h, cudaMemcpy(t.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
-    g_tables[h->device].push_back(t);
+    h->resample_tables.push_back(t);
     *out = t;
     return CD_OK;
 }
@@ -97,7 +99,6 @@ int64_t resample_length(int64_t n_in, int orig_sr, int new_sr) {
 
 int launch_resample(cd_handle* h, const float* d_in, int64_t rows, int64_t n_in, int orig_sr, int new_sr, float* d_out,
                     cudaStream_t s) {
-    if (h->device >= 64) return set_err(h, CD_E_ARG, "device index >= 64");
     ResampleTable t;
     int rc = get_table(h, orig_sr, new_sr, &t);
     if (rc != CD_OK) return rc;

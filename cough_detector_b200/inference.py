@@ -115,9 +115,9 @@ class CoughDetectorInference:
     def stream_probabilities(self, audio: torch.Tensor, hop_duration: float = 0.25) -> torch.Tensor:
         """P(cough) of every 1-s window of a 16 kHz mono stream at the given hop, one fused call."""
         hop = int(16000 * hop_duration)
-        h = self.preprocessor._apply_options(self.model._handle(torch.empty(0, device=self.device)))
+        h = self.model._handle(torch.empty(0, device=self.device))
         x = audio.reshape(-1).to(device=self.device, dtype=torch.float32)
-        logits = h.e2e_forward_stream(x, hop, _PREC[self.model.precision])
+        logits = h.e2e_forward_stream(x, hop, _PREC[self.model.precision], opts=self.preprocessor.feat_options)
         _, probs, _ = h.predict(logits)
         return probs[:, 1]
 

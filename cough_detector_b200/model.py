@@ -91,17 +91,14 @@ class CoughDetectorResidual(nn.Module):
 
     def forward_audio(self, audio: torch.Tensor, return_features: bool = False, preprocessor=None):
         """Additive fused entry: (B, 16000) waveforms -> logits, features never leave the GPU.  `preprocessor`
-        (an AudioPreprocessor) supplies the use_pre_emphasis / use_pcen options; without one the training
-        configuration (both off) is used."""
+        (an AudioPreprocessor) supplies the use_pre_emphasis / use_pcen / use_delta_delta options for this call;
+        without one the training configuration (all off) is used."""
         if self.training:
             raise RuntimeError("cough_detector_b200 is inference-only: call model.eval() before forward_audio()")
         h = self._handle(audio)
-        if preprocessor is not None:
-            preprocessor._apply_options(h)
-        else:
-            h.set_feat_options()
+        opts = preprocessor.feat_options if preprocessor is not None else _lib.TRAINING_CONFIG
         xd = audio.detach().to(device=f"cuda:{h.device}", dtype=torch.float32, non_blocking=True)
-        out = h.e2e_forward(xd, _PREC[self.precision], return_features)
+        out = h.e2e_forward(xd, _PREC[self.precision], return_features, opts=opts)
         if audio.is_cuda:
             return out
         return tuple(o.to(audio.device) for o in out) if return_features else out.to(audio.device)

@@ -62,12 +62,14 @@ class AudioPreprocessor:
     # ---- plumbing ------------------------------------------------------------------------------
     def _gpu(self) -> "_lib.Handle":
         dev = torch.device(self.device)
-        return self._apply_options(_lib.get_handle(dev if dev.type == "cuda" else None))
+        return _lib.get_handle(dev if dev.type == "cuda" else None)
 
-    def _apply_options(self, h: "_lib.Handle") -> "_lib.Handle":
-        """Make this preprocessor's optional stages the handle's defaults (handles are shared per device)."""
-        h.set_feat_options(self.use_pre_emphasis, self.pre_emphasis_coef, self.use_pcen, self.use_delta_delta)
-        return h
+    @property
+    def feat_options(self) -> "_lib.FeatOptions":
+        """This object's optional stages, as passed with every library call.  The flags belong to the preprocessor
+        (reference :32-51), never to the shared per-device handle."""
+        return _lib.FeatOptions(bool(self.use_pre_emphasis), float(self.pre_emphasis_coef), bool(self.use_pcen),
+                                bool(self.use_delta_delta))
 
     @staticmethod
     def _back(out: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
@@ -140,7 +142,7 @@ class AudioPreprocessor:
             raise ValueError(f"expected (B, {self.segment_samples}), got {tuple(waveforms.shape)}")
         h = self._gpu()
         x = waveforms.to(device=f"cuda:{h.device}", dtype=torch.float32, non_blocking=True)
-        return self._back(h.feat_forward(x, normalize=normalize), waveforms)
+        return self._back(h.feat_forward(x, normalize=normalize, opts=self.feat_options), waveforms)
 
     def process(self, waveform: torch.Tensor, orig_sr: int) -> torch.Tensor:
         """resample -> mono -> normalize -> pad/trim -> features, one kernel (:491-517).  (C, n) -> (1, 90, 101)."""
@@ -163,7 +165,7 @@ class AudioPreprocessor:
         flat = torch.zeros(int((lens + pad).sum()) + 4, dtype=torch.float32, device=dev)
         for m, o in zip(mono, offs.tolist()):
             flat[o:o + m.numel()] = m.to(dev, non_blocking=True)
-        out = h.feat_forward_var(flat, offs, lens.to(torch.int32))
+        out = h.feat_forward_var(flat, offs, lens.to(torch.int32), opts=self.feat_options)
         return self._back(out, waveforms[0])
 
     def process_file(self, path: str) -> torch.Tensor:
@@ -200,7 +202,7 @@ class RealtimePreprocessor(AudioPreprocessor):
         """All complete windows of a 1-D stream at once: (n,) -> (windows, 1, 90, 101)."""
         h = self._gpu()
         x = audio.reshape(-1).to(device=f"cuda:{h.device}", dtype=torch.float32)
-        return self._back(h.feat_forward_stream(x, self.hop_samples), audio)
+        return self._back(h.feat_forward_stream(x, self.hop_samples, opts=self.feat_options), audio)
 
     def add_audio(self, audio_chunk: torch.Tensor) -> List[torch.Tensor]:
         """Append a chunk; return the features of every window that became complete (:582-612)."""

@@ -60,14 +60,14 @@ int main() {
     cudaMalloc(&d_audio, audio.size() * sizeof(float));
     cudaMalloc(&d_logits, B * CD_N_CLASSES * sizeof(float));
     cudaMemcpy(d_audio, audio.data(), audio.size() * sizeof(float), cudaMemcpyHostToDevice);
-    CK(cd_e2e_forward(h, d_audio, CD_SEGMENT, B, d_logits, nullptr, CD_PRECISION_BF16, nullptr));
+    CK(cd_e2e_forward(h, d_audio, CD_SEGMENT, B, d_logits, nullptr, CD_FEAT_NORMALIZE, 0.f, CD_PRECISION_BF16, nullptr));
     std::vector<float> logits(B * CD_N_CLASSES);
     cudaMemcpy(logits.data(), d_logits, logits.size() * sizeof(float), cudaMemcpyDeviceToHost);
     std::printf("%s: clip 0 logits %.4f %.4f, %lld kernel launches\n", cd_version(), logits[0], logits[1],
                 (long long)cd_launch_count(h));
     // the same from host memory, copies pipelined inside the library
     std::vector<float> host_logits(B * CD_N_CLASSES);
-    CK(cd_e2e_forward_host(h, audio.data(), B, host_logits.data(), CD_PRECISION_BF16));
+    CK(cd_e2e_forward_host(h, audio.data(), B, host_logits.data(), CD_FEAT_NORMALIZE, 0.f, CD_PRECISION_BF16));
     std::printf("host path agrees: %s\n", host_logits == logits ? "bit for bit" : "NO");
     cudaFree(d_audio);
     cudaFree(d_logits);

@@ -11,8 +11,11 @@
  *
  * Ownership: pointers are borrowed for the duration of the call (device pointers: until the
  * enqueued work completes).  Inputs are never written.  A handle owns its constant tables,
- * folded weights and workspace; one handle per GPU (or per thread), calls on one handle are not
- * thread-safe, calls on different handles are independent.
+ * folded weights (fp32 and bf16), resampling filters and workspaces; there is no per-device or
+ * process-wide state, so calls on different handles -- also two handles on one GPU -- are
+ * independent.  Calls on one handle are not thread-safe; they may use different streams (the
+ * library orders successive users of the shared workspace with an event).  The only state a
+ * handle carries between calls is its weights (cd_cnn_load): feature options travel with each call.
  */
 #ifndef COUGH_B200_H
 #define COUGH_B200_H
@@ -95,45 +98,46 @@ int cd_get_tables(float* hann, float* fb, float* dct);
 
 /* ---- features: AudioPreprocessor ------------------------------------------------------- */
 
+/* Feature options.  Every feature-computing call carries its own `flags` (CD_FEAT_* bits) and `pre_emphasis_coef`;
+ * nothing is remembered on the handle, so two AudioPreprocessor objects with different flags (src/preprocessing.py:32-51:
+ * the flags belong to each object) can share one handle and interleave calls freely.  flags = CD_FEAT_NORMALIZE with
+ * coef ignored is the training configuration (src/train.py:264-287).  CD_FEAT_PRE_EMPHASIS / CD_FEAT_PCEN keep 90 rows;
+ * with CD_FEAT_DELTA_DELTA a call writes 103 rows per clip and the cd_e2e_* calls run the network on 103 rows.
+ * pre_emphasis_coef must be in [0, 1] when CD_FEAT_PRE_EMPHASIS is set.  use_spectral_contrast is not built (its rows
+ * are NaN in the reference itself). */
+
 /* B fixed-length clips.  d_audio: device, B rows of 16000 fp32 samples, row pitch `stride`
- * samples (>= 16000).  d_feat: device, B x 90 x 101 fp32, row-major (feature, time).
- * flags: CD_FEAT_NORMALIZE applies normalize() (src/preprocessing.py:199-212) first, as
- * dataset.__getitem__ / process() / add_audio() do; 0 is bare extract_features().
+ * samples (>= 16000).  d_feat: device, B x 90 (103) x 101 fp32, row-major (feature, time).
+ * CD_FEAT_NORMALIZE applies normalize() (src/preprocessing.py:199-212) first, as
+ * dataset.__getitem__ / process() / add_audio() do; without it this is bare extract_features().
  * Per clip: [normalize] -> extract_features (:432-489):
  * mel dB [0,1] rows 0..63 (:387-412), normalised MFCC rows 64..76 (:414-430), deltas rows
  * 77..89 (:342-356). */
 int cd_feat_forward(cd_handle* h, const float* d_audio, int64_t stride, int64_t B,
-                    float* d_feat, int flags, void* stream);
-
-/* Handle defaults for the two optional stages of the 90-feature path (AudioPreprocessor(use_pre_emphasis=...,
- * pre_emphasis_coef=..., use_pcen=...), src/preprocessing.py:32-51): OR-ed into EVERY later feature launch of this handle,
- * including the fused cd_e2e_* calls, which carry no flags of their own.  flags: any of CD_FEAT_PRE_EMPHASIS,
- * CD_FEAT_PCEN, CD_FEAT_DELTA_DELTA, or 0 (the training configuration, src/train.py:264-287, and the state of a fresh
- * handle).  With CD_FEAT_DELTA_DELTA every feature call writes 103 rows per clip and the cd_e2e_* calls run the
- * network on 103 rows.  use_spectral_contrast is not built (it returns NaN rows in the reference itself, DESIGN.md
- * section 6). */
-int cd_feat_options(cd_handle* h, int flags, float pre_emphasis_coef);
+                    float* d_feat, int flags, float pre_emphasis_coef, void* stream);
 
 /* Same as cd_feat_forward for int16 PCM clips (the sample format of wav files; torchaudio.load divides by 32768,
  * which is exact in fp32 and cancels in the peak normalisation, so with CD_FEAT_NORMALIZE the features are
  * bit-identical to the fp32 path on x / 32768).  stride in samples, a multiple of 8.  Additive: the reference has
  * no int16 entry point; it halves the bytes that have to reach the GPU. */
 int cd_feat_forward_i16(cd_handle* h, const int16_t* d_audio, int64_t stride, int64_t B,
-                        float* d_feat, int flags, void* stream);
+                        float* d_feat, int flags, float pre_emphasis_coef, void* stream);
 
 /* B clips of arbitrary length described by (offset, length) into one device buffer:
  * clip i = d_audio[d_offsets[i] .. d_offsets[i]+d_lengths[i]).  Per clip: normalize over the
  * WHOLE clip -> pad_or_trim to 16000 (centre trim / symmetric zero pad, :358-385) ->
- * extract_features, i.e. AudioPreprocessor.process (:491-517) at 16 kHz mono.
+ * extract_features, i.e. AudioPreprocessor.process (:491-517) at 16 kHz mono (CD_FEAT_NORMALIZE is implied).
  * d_offsets / d_lengths are device arrays.  length 0 is allowed (all-zero clip). */
 int cd_feat_forward_var(cd_handle* h, const float* d_audio, const int64_t* d_offsets,
-                        const int32_t* d_lengths, int64_t B, float* d_feat, void* stream);
+                        const int32_t* d_lengths, int64_t B, float* d_feat, int flags,
+                        float pre_emphasis_coef, void* stream);
 
 /* Sliding windows over one stream: window j = d_audio[j*hop .. j*hop+16000), per-window peak
- * normalisation, no pad/trim: RealtimePreprocessor.add_audio (:582-612).  n_windows must be
- * cd_stream_windows(n_samples, hop).  d_feat: n_windows x 90 x 101. */
+ * normalisation (CD_FEAT_NORMALIZE is implied), no pad/trim: RealtimePreprocessor.add_audio (:582-612).
+ * n_windows must be cd_stream_windows(n_samples, hop).  d_feat: n_windows x 90 (103) x 101. */
 int cd_feat_forward_stream(cd_handle* h, const float* d_audio, int64_t n_samples, int64_t hop,
-                           int64_t n_windows, float* d_feat, void* stream);
+                           int64_t n_windows, float* d_feat, int flags, float pre_emphasis_coef,
+                           void* stream);
 /* Number of windows add_audio emits for n_samples buffered samples (0 if n_samples < 16000). */
 int64_t cd_stream_windows(int64_t n_samples, int64_t hop);
 
@@ -176,26 +180,28 @@ int cd_predict(cd_handle* h, const float* d_logits, int64_t B, float threshold,
 /* ---- end to end ------------------------------------------------------------------------ */
 
 /* audio -> logits in one call: cd_feat_forward + cd_cnn_forward without the features leaving
- * the GPU.  d_feat_opt may be NULL (features go to the handle's workspace) or a B x 90 x 101
- * buffer that receives them. */
+ * the GPU.  d_feat_opt may be NULL or a B x 90 (103) x 101 buffer that receives the features.
+ * flags / pre_emphasis_coef as for cd_feat_forward. */
 int cd_e2e_forward(cd_handle* h, const float* d_audio, int64_t stride, int64_t B,
-                   float* d_logits, float* d_feat_opt, int precision, void* stream);
+                   float* d_logits, float* d_feat_opt, int flags, float pre_emphasis_coef,
+                   int precision, void* stream);
 
 /* Same, over sliding windows of one stream (window j = d_audio[j*hop ..)); d_logits is
  * n_windows x 2. */
 int cd_e2e_forward_stream(cd_handle* h, const float* d_audio, int64_t n_samples, int64_t hop,
-                          int64_t n_windows, float* d_logits, int precision, void* stream);
+                          int64_t n_windows, float* d_logits, int flags, float pre_emphasis_coef,
+                          int precision, void* stream);
 
 /* HOST buffers: h_audio B x 16000 fp32 (pageable or pinned), h_logits B x 2 fp32.  The library
  * pipelines chunked host->device copies, the kernels and the device->host copy of the logits on
  * its own streams, and returns when h_logits is complete (synchronous).  This is the call the
  * bench's end-to-end number times. */
 int cd_e2e_forward_host(cd_handle* h, const float* h_audio, int64_t B, float* h_logits,
-                        int precision);
+                        int flags, float pre_emphasis_coef, int precision);
 
 /* cd_e2e_forward_host for int16 PCM host buffers (B x 16000 int16): half the host->device bytes. */
 int cd_e2e_forward_host_i16(cd_handle* h, const int16_t* h_audio, int64_t B, float* h_logits,
-                            int precision);
+                            int flags, float pre_emphasis_coef, int precision);
 
 /* Diagnostic: D[i][n] = sum_k A[i + shift][k] * B[n][k] (i < 128) on one tcgen05 tile through the same
  * shared-memory / instruction descriptors the convolution kernels use (operands rounded to bf16, fp32

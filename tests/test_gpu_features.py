@@ -222,7 +222,7 @@ def test_pre_emphasis_and_pcen_variants_vs_reference_goldens(name):
             worst = max(worst, d)
             assert d <= TOL, (name, i, len(x), d)
     print("%s: worst well-conditioned |err| = %.3e" % (name, worst))
-    # the options live on the (shared) handle: a default preprocessor used next must get the default kernel back
+    # the options travel with each call: a default preprocessor used next gets the default kernel
     again = AudioPreprocessor(**FLAGS).process_batch(clips[:4])[:, 0]
     for i in range(4):
         assert (again[i] - base[i]).abs().max().item() <= (TOL_ILL if _ill(clips[i]) else TOL)
@@ -248,14 +248,13 @@ def test_variants_stream_int16_and_fused_paths_agree():
     pp = AudioPreprocessor(**kw)
     x = torch.stack(synth.synth_clips(64, seed=21, fixed_length=True)).cuda()
     pcm = (x / x.abs().amax(dim=1, keepdim=True).clamp(min=1e-9) * 32767.0).round().to(torch.int16)
-    pp._apply_options(h)
-    assert torch.equal(h.feat_forward_i16(pcm), h.feat_forward(pcm.float() / 32768.0))
-    f = h.feat_forward(x)
+    o = pp.feat_options
+    assert torch.equal(h.feat_forward_i16(pcm, opts=o), h.feat_forward(pcm.float() / 32768.0, opts=o))
+    f = h.feat_forward(x, opts=o)
     m = create_model("residual").eval()
     m.load_state_dict(synth.randomized_state_dict(m, seed=3))
     fused, ffeat = m.forward_audio(x, return_features=True, preprocessor=pp)
     assert torch.equal(ffeat, f)
-    pp._apply_options(h)
     assert torch.equal(fused, m(f))
     plain = m.forward_audio(x)                               # no preprocessor: the training configuration again
     assert torch.equal(plain, m(AudioPreprocessor(**FLAGS).extract_features_batch(x)))
@@ -285,7 +284,7 @@ def test_delta_delta_rows_vs_reference_goldens(name):
     assert one.shape == (8, 1, 103, 101) and rt.shape[1:] == (1, 103, 101)
     want_rt = co.stream_features(s3, 1600, co.Explicit32(kw["use_pcen"], kw["use_pre_emphasis"], use_delta_delta=True))
     assert (rt - want_rt).abs().max().item() <= TOL
-    # and the handle goes back to 90 rows for the next default user
+    # and the next default user of the shared handle gets 90 rows
     assert AudioPreprocessor(**FLAGS).extract_features_batch(fixed).shape == (8, 1, 90, 101)
 
 
@@ -318,3 +317,45 @@ def test_random_lengths_scales_and_offsets_vs_oracle():
                 worst = max(worst, d)
                 assert d <= TOL, (i, len(x), d)
         print("random lengths/scales: worst well-conditioned |err| = %.3e" % worst)
+
+
+def test_feature_flags_belong_to_each_preprocessor_not_to_the_handle():
+    """src/preprocessing.py:32-51: every AudioPreprocessor owns its flags.  Objects with different flags share the
+    per-device handle here, so interleave them -- and raw handle calls -- in every order and demand the answers of
+    the objects used alone (round 1 kept the options on the handle and this is the test that would have caught it)."""
+    from cough_detector_b200 import create_model
+    h = _lib.get_handle(0)
+    x = torch.stack(synth.synth_clips(48, seed=31, fixed_length=True)).cuda()
+    stream = torch.cat(list(x[:3].cpu()))
+    kw_all = dict(use_pcen=True, use_pre_emphasis=True, pre_emphasis_coef=0.9, use_delta_delta=True, use_spectral_contrast=False)
+    kw_pre = dict(use_pcen=False, use_pre_emphasis=True, pre_emphasis_coef=0.5, use_delta_delta=False, use_spectral_contrast=False)
+    plain, full, pre = AudioPreprocessor(**FLAGS), AudioPreprocessor(**kw_all), AudioPreprocessor(**kw_pre)
+    alone = {}
+    for name, pp in (("plain", plain), ("full", full), ("pre", pre)):      # each object on its own first
+        alone[name] = pp.extract_features_batch(x).clone()
+    assert alone["plain"].shape[2] == 90 and alone["full"].shape[2] == 103 and alone["pre"].shape[2] == 90
+    raw = h.feat_forward(x).clone()                                        # raw handle call = training configuration
+    assert torch.equal(raw, alone["plain"])
+    m = create_model("residual").eval()
+    m.load_state_dict(synth.randomized_state_dict(m, seed=5))
+    fused_plain = m.forward_audio(x).clone()
+    order = ["full", "plain", "pre", "full", "pre", "plain", "plain", "full"]
+    objs = {"plain": plain, "full": full, "pre": pre}
+    rt = RealtimePreprocessor(window_duration=1.0, hop_duration=0.1, **kw_all)
+    rt_first = rt.stream_features(stream).clone()
+    for i, name in enumerate(order):
+        assert torch.equal(objs[name].extract_features_batch(x), alone[name]), (i, name)
+        assert torch.equal(h.feat_forward(x), raw), (i, name)             # whatever ran last, the raw call is unchanged
+        assert torch.equal(h.e2e_forward(x), fused_plain), (i, name)
+        assert torch.equal(m.forward_audio(x), fused_plain), (i, name)
+        assert torch.equal(rt.stream_features(stream), rt_first), (i, name)
+        got = objs[name].process_batch([c for c in x[:5].cpu()])
+        assert torch.equal(got.cuda(), alone[name][:5]), (i, name)
+    # flags changed on a live object follow the object (the reference reads self.use_* at call time)
+    plain.use_delta_delta = True
+    assert plain.extract_features_batch(x).shape[2] == 103 and h.feat_forward(x).shape[2] == 90
+    plain.use_delta_delta = False
+    # the C ABI refuses flag bits it does not know and coefficients outside [0, 1]
+    out = torch.empty(1, 1, 90, 101, device="cuda")
+    assert h.lib.cd_feat_forward(h._h, x.data_ptr(), 16000, 1, out.data_ptr(), 64, 0.97, None) == -1
+    assert h.lib.cd_feat_forward(h._h, x.data_ptr(), 16000, 1, out.data_ptr(), 1 | 2, 1.5, None) == -1

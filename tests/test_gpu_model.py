@@ -12,9 +12,16 @@ from oracle import cough_oracle as co
 from tests import golden_io as gio
 
 pytestmark = pytest.mark.gpu
-# stated tolerances: fp32 path vs reference fp32 logits; bf16 path relative to the logit scale
+# Stated tolerances (north_star: "logits within a stated bf16 tolerance, decisions at 0.7 identical outside the band").
+#   fp32 path : |logit - ref| <= TOL_FP32 * scale,  scale = max(1, max|ref logit|)
+#   bf16 path : |logit - ref| <= TOL_BF16_REL * scale  (bf16 weights + activations, fp32 accumulate; the measured worst
+#               case over the goldens and the 4 096-clip seeded batch is printed by the tests, the bound is ~3x that)
+#   decisions : P(cough) >= 0.7 must equal the fp32 reference's wherever |p_ref - 0.7| > TOL_P_BF16 (fixed band, not
+#               derived from the measured error); the number of clips inside the band is printed and bounded.
 TOL_FP32 = 2e-4
-TOL_BF16_REL = 3e-2
+TOL_BF16_REL = 1e-2
+TOL_P_FP32 = 1e-4
+TOL_P_BF16 = 2e-2
 PRECISIONS = ["fp32", "bf16"]
 
 
@@ -42,8 +49,9 @@ def test_golden_logits_and_decisions(precision):
         preds, probs = m.predict(x)
         assert preds.dtype == torch.int64 and probs.shape == (x.shape[0], 2)
         pref = z[f"probs_{name}"]
-        # decisions at 0.7 identical outside the tolerance band |p - 0.7| <= band
-        band = 1e-4 if precision == "fp32" else float(np.abs(probs.numpy() - pref).max()) + 1e-6
+        # decisions at 0.7 identical outside the FIXED tolerance band |p_ref - 0.7| <= band
+        band = TOL_P_FP32 if precision == "fp32" else TOL_P_BF16
+        assert float(np.abs(probs.numpy() - pref).max()) <= band, (name, precision)
         dec, dref = probs[:, 1].numpy() >= 0.7, pref[:, 1] >= 0.7
         outside = np.abs(pref[:, 1] - 0.7) > band
         assert np.array_equal(dec[outside], dref[outside])
@@ -81,7 +89,7 @@ def test_bf16_within_emulated_bf16_band():
     emu = co.cnn_forward_bf16(sd1, x)
     got = _model(sd1, "bf16")(x)
     scale = max(1.0, emu.abs().max().item())
-    assert (got - emu).abs().max().item() <= 5e-3 * scale
+    assert (got - emu).abs().max().item() <= 1e-3 * scale
 
 
 def test_weight_swap_and_reload():
@@ -268,7 +276,7 @@ def test_switching_between_90_and_103_row_networks():
     feats = pp.extract_features_batch(big)
     assert feats.shape[2] == 103 and torch.equal(m(feats), f103)
     assert torch.equal(m.forward_audio(big), f90) and (f90 - f103).abs().max().item() > 1e-4
-    # fp32 path and the host-buffer path take the family from the handle options too
+    # fp32 path takes the family from the call's options too
     m32 = _model(sd1, "fp32")
     assert (m32.forward_audio(big[:64], preprocessor=pp) - f103[:64]).abs().max().item() <= 3e-2 * f103.abs().max().item()
 
@@ -289,3 +297,100 @@ def test_cpp_example_runs():
     r = subprocess.run([os.path.join(root, "build", "e2e_minimal")], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "host path agrees: bit for bit" in r.stdout, r.stdout
+
+
+def test_bf16_decisions_at_0p7_on_4096_seeded_clips():
+    """End to end on the SURVEY section-8d mixture: audio -> fp32 oracle features -> fp32 oracle network is the reference;
+    the GPU runs audio -> fused bf16 path.  The classifier is re-centred (synth.spread_fc) so that P(cough) straddles
+    0.7 -- with raw random weights every clip lands on one side and 'identical decisions' says nothing."""
+    _, sd1, _ = gio.load_model()
+    n = 4096
+    x = synth.synth_batch(n, seed=77, device="cpu")
+    ex = co.Explicit32()
+    feats = torch.stack([ex.process(c.reshape(1, -1)) for c in x])           # (n, 1, 90, 101), fp32 oracle
+    sd = synth.spread_fc(sd1, co.cnn_forward(sd1, feats))
+    ref = co.cnn_forward(sd, feats)
+    p_ref = torch.softmax(ref, dim=1)[:, 1].numpy()
+    scale = max(1.0, ref.abs().max().item())
+    h = _lib.get_handle(0)
+    for precision, tol_l, tol_p in (("fp32", TOL_FP32, TOL_P_FP32), ("bf16", TOL_BF16_REL, TOL_P_BF16)):
+        m = _model(sd, precision)
+        logits = m.forward_audio(x.cuda())
+        _, probs, dec = h.predict(logits, threshold=0.7)
+        p = probs[:, 1].cpu().numpy()
+        lerr = (logits.cpu() - ref).abs().max().item()
+        perr = float(np.abs(p - p_ref).max())
+        outside = np.abs(p_ref - 0.7) > tol_p
+        inside = int((~outside).sum())
+        flips_in = int((dec.cpu().numpy()[~outside] != (p_ref[~outside] >= 0.7)).sum())
+        print(f"{precision}: {n} clips, logit err {lerr:.3e} (scale {scale:.2f}, rel {lerr / scale:.2e}), prob err {perr:.3e}, "
+              f"{inside} clips inside |p-0.7| <= {tol_p} ({flips_in} flipped there), "
+              f"{int((p_ref >= 0.7).sum())} positive / {int((p_ref < 0.7).sum())} negative")
+        assert lerr <= tol_l * scale, (precision, lerr, scale)
+        assert perr <= tol_p, (precision, perr)
+        assert np.array_equal(dec.cpu().numpy()[outside], p_ref[outside] >= 0.7)
+        # the check is not vacuous: both classes are well populated and the band holds few clips
+        assert (p_ref[outside] >= 0.7).sum() >= n // 5 and (p_ref[outside] < 0.7).sum() >= n // 5
+        assert inside <= n // 20
+
+
+def test_two_handles_on_one_gpu_are_independent():
+    """include/cough_b200.h: calls on different handles are independent -- also two handles on the same GPU.  Round 1
+    kept the bf16 weights and the resampling tables per device index; here two private handles load different weights,
+    are used alternately, and one outlives the other."""
+    sd0, sd1, z = gio.load_model()
+    _, feats, _ = gio.load_features()
+    x = feats.unsqueeze(1).cuda()
+    shared = _lib.get_handle(0)
+    h0, h1 = _lib.Handle(0), _lib.Handle(0)
+    try:
+        h0.load_state_dict(sd0)
+        h1.load_state_dict(sd1)                                  # must not touch h0's weights (either precision)
+        want = {}
+        for prec in (0, 1):
+            want[prec] = (h0.cnn_forward(x, prec).clone(), h1.cnn_forward(x, prec).clone())
+            assert (want[prec][0].cpu() - torch.from_numpy(z["logits_default"])).abs().max().item() <= (TOL_FP32 if prec == 0 else TOL_BF16_REL)
+            sc = max(1.0, float(np.abs(z["logits_random"]).max()))
+            assert (want[prec][1].cpu() - torch.from_numpy(z["logits_random"])).abs().max().item() <= (TOL_FP32 if prec == 0 else TOL_BF16_REL) * sc
+        for _ in range(3):
+            for prec in (1, 0):
+                assert torch.equal(h1.cnn_forward(x, prec), want[prec][1])
+                assert torch.equal(h0.cnn_forward(x, prec), want[prec][0])
+        w = torch.randn(2, 30000, device="cuda")
+        r0 = h0.resample(w, 44100)
+        assert torch.equal(h1.resample(w, 44100), r0) and torch.equal(shared.resample(w, 44100), r0)
+        h1.close()                                               # frees ITS weights, tables and workspaces only
+        torch.cuda.synchronize()
+        junk = torch.full((64 << 20,), 7.0, device="cuda")       # recycle the freed memory
+        for prec in (0, 1):
+            assert torch.equal(h0.cnn_forward(x, prec), want[prec][0])
+        assert torch.equal(h0.resample(w, 44100), r0)
+        del junk
+    finally:
+        h0.close()
+        h1.close()
+
+
+def test_calls_on_different_streams_share_the_workspace_safely():
+    """One handle, several caller streams and the host pipeline's private streams: the library orders successive users
+    of its workspace with an event, so un-synchronised back-to-back calls give the serial answers."""
+    _, sd1, _ = gio.load_model()
+    h = _lib.get_handle(0)
+    m = _model(sd1, "bf16")
+    a = synth.synth_batch(6000, seed=5, device="cuda")
+    b = synth.synth_batch(6000, seed=6, device="cuda")
+    want_a, want_b = m.forward_audio(a).clone(), m.forward_audio(b).clone()
+    feat_b = h.feat_forward(b)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    host_a = a.cpu().pin_memory()
+    for _ in range(5):
+        with torch.cuda.stream(s1):
+            la = h.e2e_forward(a, 1)
+        with torch.cuda.stream(s2):
+            lb = h.e2e_forward(b, 1)                             # no sync in between: same workspace, other stream
+            lc = h.cnn_forward(feat_b, 1)
+        lh = h.e2e_forward_host(host_a, 1)                       # private pipeline streams, right behind both
+        torch.cuda.synchronize()
+        assert torch.equal(la, want_a) and torch.equal(lb, want_b) and torch.equal(lc, want_b)
+        assert torch.equal(lh.cuda(), want_a)

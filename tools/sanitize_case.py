@@ -32,7 +32,6 @@ for opts in (dict(use_pcen=True, use_pre_emphasis=False), dict(use_pcen=False, u
     g4 = RealtimePreprocessor(window_duration=1.0, hop_duration=0.0485625, **kw).stream_features(s[:20000])
     g5 = m.forward_audio(x, preprocessor=po)
     assert all(torch.isfinite(t).all() for t in (g1, g2, g3, g4, g5))
-h.set_feat_options()
 host = h.e2e_forward_host(x.cpu().pin_memory(), 1)
 d = h.selftest_umma(torch.randn(128 + 9, 128), torch.randn(64, 128), 9, 0)
 torch.cuda.synchronize()
