@@ -19,12 +19,14 @@ $(LIB): $(OBJS)
 	@mkdir -p $(OUT_DIR)
 	$(NVCC) -shared $(ARCH) -o $@ $(OBJS)
 
-# feature-kernel ablations (cost breakdown; see feat_kernel.cu CD_EXP and profiles/r1_feat_ablation.txt)
-ablations: $(OBJS)
-	@mkdir -p build/exp
-	for e in 1 2 3 4 5; do \
-	  $(NVCC) $(NVCCFLAGS) -DCD_EXP=$$e -c $(SRC_DIR)/feat_kernel.cu -o build/exp/feat_$$e.o 2> /dev/null && \
-	  $(NVCC) -shared $(ARCH) -o build/exp/libexp$$e.so build/api.o build/exp/feat_$$e.o build/cnn_fp32.o build/cnn_tc.o build/resample.o; \
+# experimental builds of the feature kernel (occupancy / register trade-offs): lib/exp/lib<tag>.so, timed by
+# `CD_LIB=... python tools/feat_time.py`.  EXP="tag1:-DFLAG=.. tag2:-DFLAG=.." (lib/ travels to the GPU box, build/ does not)
+EXP ?= c2:-DCD_FEAT_CTAS=2 c3:-DCD_FEAT_CTAS=3
+exp: $(OBJS)
+	@mkdir -p build/exp $(OUT_DIR)/exp
+	for e in $(EXP); do tag=$${e%%:*}; flags=$$(echo $${e#*:} | tr ',' ' '); \
+	  $(NVCC) $(NVCCFLAGS) $$flags -c $(SRC_DIR)/feat_kernel.cu -o build/exp/feat_$$tag.o 2> build/exp/feat_$$tag.ptxas.log && \
+	  $(NVCC) -shared $(ARCH) -o $(OUT_DIR)/exp/lib$$tag.so build/api.o build/exp/feat_$$tag.o build/cnn_fp32.o build/cnn_tc.o build/resample.o; \
 	done
 
 # C++ callers of the C ABI (no Python, no torch)
@@ -34,4 +36,4 @@ examples: $(LIB)
 clean:
 	rm -rf build $(LIB)
 
-.PHONY: all clean ablations examples
+.PHONY: all clean exp examples

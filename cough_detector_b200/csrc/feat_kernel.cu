@@ -1,4 +1,4 @@
-// Fused feature kernel: clip -> (90, 101) features, persistent, two 256-thread CTAs per SM.
+// Fused feature kernel: clip -> (90 | 103, 101) features, persistent, three 256-thread CTAs per SM.
 //
 // Replaces, per clip, AudioPreprocessor.normalize (src/preprocessing.py:199-212), pad_or_trim
 // (:358-385) and extract_features (:432-489): T.MelSpectrogram (reflect pad, 400-sample periodic
@@ -7,46 +7,64 @@
 // and the replicate-padded central-difference deltas.  The reference computes the mel
 // spectrogram twice (extract_mel_spectrogram and again inside T.MFCC); here it is computed once.
 //
-// Data flow per clip (all on chip between the 64 000 B read and the feature / operand-map write):
-//   global --one cp.async.bulk (TMA 1-D), issued under the previous clip's tail--> smem clip[16000]
-//   block max|x| -> 1/max folded into the lane's 13 window weights (the clip is never rewritten)
-//   8 warps x frame PAIRS: z = w*(x_2p + i x_2p+1), complex 512-point FFT as 8x8x8 radix-8
-//       (16 points per lane in registers, packed f32x2 math, two smem exchanges), Z[k], Z[512-k] -> the two
-//       power spectra for bins 4..127 only, segment-owned banded mel, 10 log10 -> smem dB tile [64][101]
-//   block max(dB) -> floor; mel01 rows written; DCT-13 from the floored tile; block mean / std;
-//   normalised MFCC + deltas written (fp32 features and/or the CNN stem's blocked bf16 map).
+// What bounds it (round-1 ncu + tools/ubench.cu): the shared-memory data pipe (128 B/clk/SM, shuffles included)
+// and the FMA pipe (packed f32x2 instructions issue at half rate, so they save issue slots, not FMA cycles).
+// The design therefore minimises shared-memory wavefronts per clip:
+//   * the clip is NOT staged in shared memory: lane m of a warp reads samples s0 + 32 q + m straight from
+//     global memory (one coalesced 128-byte line per load) and a warp walks CONSECUTIVE frame pairs, so 8 of the
+//     18 sample registers of a pair are carried over from the previous pair (10 loads per pair instead of 26);
+//   * two frames ride in one complex 512-point FFT, z = w (x_2p + i x_2p+1), decomposed 16 x 16 x 2:
+//     a radix-16 DFT in registers (n = 32 a + m), twiddles, ONE exchange through shared memory (16 STS.64 +
+//     8 LDS.128, conflict-free), a second radix-16 DFT in registers, and a final radix-2 across lane pairs
+//     by shuffle, pruned to the outputs that feed bins 4..127 (tools/fft_lane_model.py is the numpy model of
+//     this index arithmetic);
+//   * peak normalisation never touches the samples: the peak is tracked while the samples are loaded and
+//     1 / peak^2 is applied to the mel POWER in the tail (exact for power-of-two gains; clips whose peak is
+//     outside 2^+-24 are redone with a power-of-two pre-scale so nothing under- or overflows);
+//   * the 64 x 101 tile holds mel power; scaling, dB, top_db floor, DCT, mean / std, deltas happen in the tail.
 // The power spectrum is invariant to a circular shift of the frame, so the 400 windowed samples
 // sit at n = 0..399 of the 512-point frame instead of torch.stft's 56..455.
 #include "cd_common.cuh"
 #include "cd_tables.h"
-// Ablation switches (never set in the shipped library; `make ablations` builds build/exp/libexp<n>.so and
-// tools/feat_time.py times them -- results are WRONG by construction, only the time is of interest):
-//   1 no second shared-memory exchange   2 no exchanges   3 no STFT at all   4 no tail   5 one mel slot per segment
-#ifndef CD_EXP
-#define CD_EXP 0
-#endif
 
 namespace cd {
 
-constexpr int kFeatWarps   = 8;                // two CTAs per SM: one CTA's tail overlaps the other's FFTs
+// Occupancy configuration (make exp builds the alternatives: tools/feat_time.py compares them):
+//   CD_FEAT_WARPS x CD_FEAT_CTAS = warps per CTA x CTAs per SM.  Registers per thread follow from the product
+//   (16 warps: 128, 21: 96, 24: 80); the FFT alone holds 32, the lane's window 13.
+#ifndef CD_FEAT_WARPS
+#define CD_FEAT_WARPS 8
+#endif
+#ifndef CD_FEAT_CTAS
+#define CD_FEAT_CTAS 2
+#endif
+// CD_TW: where the lane's stage-1 twiddles live.  0: six base twiddles in registers;  1: W^m, W^2m, W^3m in registers,
+// W^4m, W^8m, W^12m read from shared memory per pair (6 fewer registers, 6 more wavefronts per pair).
+#ifndef CD_TW
+#define CD_TW 0
+#endif
+constexpr int kFeatWarps   = CD_FEAT_WARPS;
 constexpr int kFeatThreads = kFeatWarps * 32;
-constexpr int kXbElems     = 288;             // float2 per warp: 4 rows x 72 (64 + 8 pad)
-constexpr int kXbRow       = 72;
+constexpr int kFeatCtasPerSm = CD_FEAT_CTAS;  // one CTA's reductions / tail overlap the others' FFTs
+constexpr int kXchRow      = 34;              // float2 per row of the exchange tile (16 rows: r = k mod 16)
+constexpr int kXchElems    = 16 * kXchRow;    // 544
+constexpr int kPowElems    = 160;             // the pair's power spectra at padded bin index < 146, zero slot at 152
+constexpr int kPowZero     = 152;
+constexpr int kXbElems     = kXchElems + kPowElems;   // 704 float2 = 5632 B per warp
+constexpr int kTilePitch   = 102;             // floats per band row of the power tile: even, so a frame PAIR is one 8-byte access
+static_assert(kFeatWarps >= 4 && kFeatWarps <= 8, "tail: two DCT groups of two warps; block reductions over <= 8 warps");
 
 __constant__ float c_dct[kMfcc * kMels];      // [13][64], ortho DCT-II rows
 
 struct FeatSmem {
-    float  clip[kSeg];                        //  64 000 B, filled by one bulk copy per clip
-    float2 xb[kFeatWarps][kXbElems];          //  18 432 B, per-warp FFT exchange; MFCC scratch in the tail
-    float  db[kMels * kFrames];               //  25 856 B, dB tile [band][frame]
-    float2 tw1[7][64];                        //   3 584 B
-    float2 tw2[7][8];                         //     448 B
-    float2 zero2;                             // what the mel contraction reads for a lane's unused bin slots
+    float2 xb[kFeatWarps][kXbElems];          //  5 632 B per warp: FFT exchange + power spectra; MFCC scratch in the tail
+    float  db[kMels * kTilePitch];            //  26 112 B, mel POWER tile [band][frame] (dB after the tail's first pass)
+    float2 tw4[3][32];                        //  W512^(4 m), ^(8 m), ^(12 m) per lane m (CD_TW = 1)
     float  red[64];
-    unsigned long long bar;
-};                                            // 112 592 B -> two CTAs per SM
-static_assert(sizeof(FeatSmem) <= 113 * 1024, "two CTAs per SM");
-static_assert(offsetof(FeatSmem, xb) % 128 == 0 && offsetof(FeatSmem, zero2) % 128 == 64, "zero2 sits in bank pair 8 of xb's numbering");
+};                                            //  8 warps: 72 192 B
+static_assert(kFeatCtasPerSm * (sizeof(FeatSmem) + 1024) <= 227 * 1024, "CTAs per SM");
+static_assert(sizeof(float2) * kXbElems % 128 == 0 && kPowZero % 16 == 8, "zero slot sits in bank pair 8 of the power region");
+static_assert(sizeof(float) * kMfcc * kFrames <= sizeof(float2) * kXbElems, "MFCC scratch fits one warp's region");
 
 // ----------------------------------------------------------------------------------------------
 // small PTX wrappers
@@ -54,44 +72,16 @@ static_assert(offsetof(FeatSmem, xb) % 128 == 0 && offsetof(FeatSmem, zero2) % 1
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Bounded like the tensor-core kernels' waits: a bulk copy that never lands traps (-> a launch error the host
-// reports) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();     // ~2 s at 1.9 GHz
-    }
-}
 __device__ __forceinline__ float2 lds64(uint32_t addr) {
     float2 v;
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
     return v;
 }
-// 1-D bulk async copy global -> shared (TMA engine), completion signalled on an mbarrier.
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 
 // Packed fp32 pairs (add/sub/mul/fma.f32x2 -> FADD2 / FMUL2 / FFMA2 on sm_100): a complex value is one 64-bit register
 // pair, so a complex add is ONE instruction and a complex multiply TWO (ptxas folds the half swaps, the per-half
-// negation and the scalar broadcasts into operand modifiers).  Butterflies, twiddles, the window and the power
-// spectrum are ~2/3 of the kernel's instructions, which is issue-bound -- this halves them.
+// negation and the scalar broadcasts into operand modifiers).  They issue at half the scalar rate (tools/ubench.cu:
+// 1.8 vs 3.4 warp-instructions/clk/SM), i.e. the same FMA-pipe cycles per flop, but half the issue slots.
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk(float lo, float hi) {
     u64 r;
@@ -133,34 +123,59 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 t) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(pk(t.x, t.x)), "l"(pk(a.x, a.y)), "l"(pk(-mm.x, mm.y)));
     return up(rd);
 }
+__device__ __forceinline__ float2 cmulc(float2 a, float tx, float ty) { return cmul(a, make_float2(tx, ty)); }
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
 
-// 8-point forward DFT, natural order in and out (decimation in frequency, 3 radix-2 levels).
-// PRUNE: only outputs 0, 1, 6, 7 are produced (the last stage feeds bins 4..127 and 385..508 only).
-template <bool PRUNE>
-__device__ __forceinline__ void fft8(float2 (&x)[8]) {
-    const float h = 0.70710678118654752440f;
-    float2 t0 = cadd(x[0], x[4]), t4 = csub(x[0], x[4]);
-    float2 t1 = cadd(x[1], x[5]), t5 = csub(x[1], x[5]);
-    float2 t2 = cadd(x[2], x[6]), t6 = csub(x[2], x[6]);
-    float2 t3 = cadd(x[3], x[7]), t7 = csub(x[3], x[7]);
-    t5 = scale2(h, cadd(t5, mul_mi(t5)));                          // * W8^1 = h (1 - i)
-    t6 = mul_mi(t6);                                               // * W8^2
-    t7 = scale2(h, csub(mul_mi(t7), t7));                          // * W8^3 = -h (1 + i)
-    float2 u0 = cadd(t0, t2), u2 = csub(t0, t2);
-    float2 u1 = cadd(t1, t3), u3 = mul_mi(csub(t1, t3));
-    float2 u4 = cadd(t4, t6), u6 = csub(t4, t6);
-    float2 u5 = cadd(t5, t7), u7 = mul_mi(csub(t5, t7));
-    x[0] = cadd(u0, u1);
-    x[1] = cadd(u4, u5);
-    x[6] = csub(u2, u3);
-    x[7] = csub(u6, u7);
-    if (!PRUNE) {
-        x[4] = csub(u0, u1);
-        x[2] = cadd(u2, u3);
-        x[5] = csub(u4, u5);
-        x[3] = cadd(u6, u7);
+// ----------------------------------------------------------------------------------------------
+// 16-point DFT in registers, radix 4 x 4
+// ----------------------------------------------------------------------------------------------
+constexpr float kC1 = 0.92387953251128674f;     // cos(pi / 8)
+constexpr float kS1 = 0.38268343236508977f;     // sin(pi / 8)
+constexpr float kH  = 0.70710678118654752f;
+
+// y_k = sum_j x_j (-i)^(j k), in place.  Z3: x3 is known to be zero (and is only written).
+template <bool Z3>
+__device__ __forceinline__ void r4(float2& x0, float2& x1, float2& x2, float2& x3) {
+    const float2 t0 = cadd(x0, x2), t1 = csub(x0, x2);
+    if (Z3) {
+        const float2 j = mul_mi(x1);
+        x0 = cadd(t0, x1);
+        x2 = csub(t0, x1);
+        x1 = cadd(t1, j);
+        x3 = csub(t1, j);
+    } else {
+        const float2 t2 = cadd(x1, x3), t3 = mul_mi(csub(x1, x3));
+        x0 = cadd(t0, t2);
+        x2 = csub(t0, t2);
+        x1 = cadd(t1, t3);
+        x3 = csub(t1, t3);
     }
+}
+__device__ __forceinline__ float2 w16_2(float2 a) { return scale2(kH, cadd(a, mul_mi(a))); }     // * W16^2 = h (1 - i)
+__device__ __forceinline__ float2 w16_6(float2 a) { return scale2(-kH, csub(a, mul_mi(a))); }    // * W16^6 = -h (1 + i)
+
+// X[t] = sum_a x[a] W16^(a t); input natural order, output X[t] at index F16(t) (the in-place digit reversal).
+// ZPAD: x[13], x[14], x[15] are zero (the 512-point frame holds 400 samples: a = 13..15 is padding).
+#define F16(t) (4 * ((t) & 3) + ((t) >> 2))
+template <bool ZPAD>
+__device__ __forceinline__ void fft16(float2 (&x)[16]) {
+    r4<false>(x[0], x[4], x[8], x[12]);
+    r4<ZPAD>(x[1], x[5], x[9], x[13]);
+    r4<ZPAD>(x[2], x[6], x[10], x[14]);
+    r4<ZPAD>(x[3], x[7], x[11], x[15]);
+    x[5] = cmulc(x[5], kC1, -kS1);            // u[a0][t0] *= W16^(a0 t0), u at index a0 + 4 t0
+    x[9] = w16_2(x[9]);
+    x[13] = cmulc(x[13], kS1, -kC1);
+    x[6] = w16_2(x[6]);
+    x[10] = mul_mi(x[10]);
+    x[14] = w16_6(x[14]);
+    x[7] = cmulc(x[7], kS1, -kC1);
+    x[11] = w16_6(x[11]);
+    x[15] = cmulc(x[15], -kC1, kS1);
+    r4<false>(x[0], x[1], x[2], x[3]);
+    r4<false>(x[4], x[5], x[6], x[7]);
+    r4<false>(x[8], x[9], x[10], x[11]);
+    r4<false>(x[12], x[13], x[14], x[15]);
 }
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -173,39 +188,25 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-// Block-wide reduction over kFeatWarps warps; every thread gets the result.  `red` needs >= 16
-// floats and is safe to reuse after the call returns (two barriers inside).
+// Two block-wide reductions (both max or both sum) over kFeatWarps warps with one pair of barriers; every thread
+// gets the results.  `red` needs >= 16 floats and is safe to reuse after the call returns.
 template <bool IS_MAX>
-__device__ __forceinline__ float block_reduce(float v, float* red) {
-    v = IS_MAX ? warp_max(v) : warp_sum(v);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    float r = red[lane & (kFeatWarps - 1)];
-#pragma unroll
-    for (int o = kFeatWarps / 2; o; o >>= 1) {
-        float other = __shfl_xor_sync(0xffffffffu, r, o);
-        r = IS_MAX ? fmaxf(r, other) : r + other;
-    }
-    __syncthreads();
-    return r;
-}
-
-// Sum of a float2 over the block; every thread gets the result.  `red` needs >= 16 floats.
-__device__ __forceinline__ float2 block_reduce_sum2(float2 v, float* red) {
-    v.x = warp_sum(v.x);
-    v.y = warp_sum(v.y);
+__device__ __forceinline__ float2 block_reduce2(float2 v, float* red) {
+    v.x = IS_MAX ? warp_max(v.x) : warp_sum(v.x);
+    v.y = IS_MAX ? warp_max(v.y) : warp_sum(v.y);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
         red[warp] = v.x;
         red[kFeatWarps + warp] = v.y;
     }
     __syncthreads();
-    float a = red[lane & (kFeatWarps - 1)], b = red[kFeatWarps + (lane & (kFeatWarps - 1))];
+    const int src = lane & 7;                  // every group of 8 lanes reduces the (<= 8) per-warp values
+    float a = red[src < kFeatWarps ? src : 0], b = red[kFeatWarps + (src < kFeatWarps ? src : 0)];
 #pragma unroll
-    for (int o = kFeatWarps / 2; o; o >>= 1) {
-        a += __shfl_xor_sync(0xffffffffu, a, o);
-        b += __shfl_xor_sync(0xffffffffu, b, o);
+    for (int o = 4; o; o >>= 1) {
+        const float oa = __shfl_xor_sync(0xffffffffu, a, o), ob = __shfl_xor_sync(0xffffffffu, b, o);
+        a = IS_MAX ? fmaxf(a, oa) : a + oa;
+        b = IS_MAX ? fmaxf(b, ob) : b + ob;
     }
     __syncthreads();
     return make_float2(a, b);
@@ -217,7 +218,7 @@ __device__ __forceinline__ float power_to_db(float x) {
 }
 
 // za = Z[k], zb = Z[512 - k] of z = x1 + i x2: {|Z + conj Z'|^2, |Z - conj Z'|^2} = the two frames' power at bin k
-// (the window carries the factor 1/2).  S = za + zb = (sr, di), D = za - zb = (dr, si).
+// (the window carries the factor 1/2).  S = za + zb = (sr, di), D = za - zb = (dr, si).  Symmetric in (za, zb).
 __device__ __forceinline__ float2 pair_power(float2 za, float2 zb) {
     const float2 S = cadd(za, zb), D = csub(za, zb);
     u64 t, rd;
@@ -226,178 +227,170 @@ __device__ __forceinline__ float2 pair_power(float2 za, float2 zb) {
     return up(rd);
 }
 
-// One windowed sample pair for FFT point n of the frame pair starting at sample `base0`.
-// T = float (the reference's waveform type) or int16_t (PCM as stored in wav files: x / 32768 is exact in fp32 and the
-// peak normalisation cancels the power-of-two scale, so both types give bit-identical features)
-// PRE: the sample is the pre-emphasised one, y[i] = x[i] - coef * x[i-1], y[0] = x[0] (apply_pre_emphasis,
-// src/preprocessing.py:213-239; product and difference rounded separately like the reference's tensor ops).  Only the
-// edge pairs can touch i = 0; the shared stream frames never do (they start >= 120 samples into every window).
-template <bool EDGE, bool PRE, class T>
-__device__ __forceinline__ float sample_at(const T* __restrict__ clip, int i, float coef) {
-    const float x = (float)clip[i];
-    if (!PRE) return x;
-    if (EDGE && i == 0) return x;
-    return __fsub_rn(x, __fmul_rn(coef, (float)clip[i - 1]));
+// ----------------------------------------------------------------------------------------------
+// per-lane constants of the FFT / mel pipeline (all lane-constant for the life of the kernel)
+// ----------------------------------------------------------------------------------------------
+struct LaneCtx {
+    float2 tw[CD_TW == 1 ? 3 : 6];   // W512^(m r), r = 1, 2, 3 [, 4, 8, 12] (m = lane); the other twiddles are products of these
+    uint32_t tw4_s;          // CD_TW = 1: shared address of this lane's W^4m (W^8m, W^12m follow 256 B apart)
+    float2 mw[kMelSlots];    // mel taps of the lane's two segments (cd_common.cuh)
+    int bin_lo, bin_hi;
+    uint32_t xw_s;           // shared address this lane writes exchange row 0 to
+    uint32_t xr_s;           // shared address this lane reads its 16 stage-2 inputs from (128 B, contiguous)
+    uint32_t pw_s;           // shared address of the warp's power region
+    uint32_t p0_s, pb_s;     // where this lane's four power pairs go: slot 0, and slot j >= 1 at pb_s + j * pstep
+    int pstep;
+    int partner;             // lane holding Z[512 - k] for this lane's Z[k]
+};
+
+__device__ __forceinline__ void lane_ctx_init(LaneCtx& L, const FeatTables* __restrict__ tables, float2* xbw, const float2* tw4, int lane) {
+#pragma unroll
+    for (int i = 0; i < (CD_TW == 1 ? 3 : 6); ++i) L.tw[i] = tables->twl[lane][i];
+    L.tw4_s = smem_u32(tw4 + lane);
+#pragma unroll
+    for (int s = 0; s < kMelSlots; ++s) L.mw[s] = tables->melt[s][lane];
+    L.bin_lo = tables->melb[0][lane];
+    L.bin_hi = tables->melb[1][lane];
+    const int m = lane, c1 = m & 1;
+    // stage-1 lane m = 2 b + c1 writes row r at r * 34 + c1 * 16 + (b ^ 8 c1): the reader of (r, c1) gets 16 contiguous
+    // float2 (c1 = 1: its two halves swapped, which the final butterfly's constants absorb), writes are conflict-free
+    L.xw_s = smem_u32(xbw + c1 * 16 + ((m >> 1) ^ (c1 * 8)));
+    const int r = lane & 15, c = lane >> 4;
+    L.xr_s = smem_u32(xbw + r * kXchRow + c * 16);
+    L.pw_s = smem_u32(xbw + kXchElems);
+    // power pairs {P_frame0, P_frame1} at padded bin index pidx(k) = k + 2 (k / 16):
+    //   c = 0: bins k = r + 16 j (lane 0, j = 0: bin 64);  c = 1: bins 128 - r - 16 j  (r = 0, j = 0: bin 128, never read)
+    int p0, pb, st;
+    if (c == 0) {
+        pb = r; st = 18; p0 = lane == 0 ? 72 : r;
+    } else {
+        pb = r ? 142 - r : 144; st = -18; p0 = pb;
+    }
+    L.p0_s = L.pw_s + 8u * (uint32_t)p0;
+    L.pb_s = L.pw_s + 8u * (uint32_t)pb;
+    L.pstep = 8 * st;
+    L.partner = ((16 - r) & 15) + 16 * (1 - c);
 }
-template <bool EDGE, bool PRE, class T>
-__device__ __forceinline__ float2 load_point(const T* __restrict__ clip, float w, int n, int base0, bool second, float coef) {
-    int i0 = base0 + n;
-    int i1 = i0 + kHop;
-    if (EDGE) {   // reflect padding of torch.stft(center=True, pad_mode="reflect")
-        i0 = i0 < 0 ? -i0 : i0;
-        i0 = i0 >= kSeg ? 2 * (kSeg - 1) - i0 : i0;
-        i1 = i1 < 0 ? -i1 : i1;
-        i1 = i1 >= kSeg ? 2 * (kSeg - 1) - i1 : i1;
-        return scale2(w, make_float2(sample_at<EDGE, PRE, T>(clip, i0, coef), second ? sample_at<EDGE, PRE, T>(clip, i1, coef) : 0.f));
-    }
-    return scale2(w, make_float2(sample_at<EDGE, PRE, T>(clip, i0, coef), sample_at<EDGE, PRE, T>(clip, i1, coef)));
-}
 
-// The per-warp work item: frames 2p and 2p+1 -> 2 x 64 dB values in the tile.  Returns the lane's
-// running max of the dB values it produced.
-// RAW = false: dB values go to dst[band * band_stride + {0, frame_stride}] (the smem tile).
-// RAW = true : un-logged mel POWER goes there instead (shared STFT frames of the streaming path).
-template <bool EDGE, bool RAW, bool PRE, class SM, class T>
-__device__ __forceinline__ float frame_pair(SM& S, const T* __restrict__ clip, float2* __restrict__ xb,
-                                            const float (&wA)[7], const float (&wB)[6],
-                                            const float2 (&mw)[kMelSlots], int bin_lo, int bin_hi, int base0, bool second,
-                                            int lane, float* __restrict__ dst, int band_stride, int frame_stride,
-                                            float coef = 0.f) {
-    const int c = lane & 7, j = lane >> 3;             // base0: sample index of window tap 0 of the first frame
-
-    // ---- stage 1: radix-8 over a (n = 64a + m), m = lane and lane + 32 ------------------------
-    float2 A[8], B[8];
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-        A[a] = load_point<EDGE, PRE, T>(clip, wA[a], 64 * a + lane, base0, second, coef);
-        B[a] = load_point<EDGE, PRE, T>(clip, wB[a], 64 * a + lane + 32, base0, second, coef);
-    }
-    A[6] = lane < 16 ? load_point<EDGE, PRE, T>(clip, wA[6], 384 + lane, base0, second, coef) : make_float2(0.f, 0.f);
-    A[7] = make_float2(0.f, 0.f);                   // n >= 400: zero padding of the 512-point frame
-    B[6] = make_float2(0.f, 0.f);
-    B[7] = make_float2(0.f, 0.f);
-    fft8<false>(A);
-    fft8<false>(B);
-    // twiddles W512^(m r): m = lane from the table, m = lane + 32 as table value * W16^r (a compile-time
-    // constant) -- 4 FP instructions instead of a second shared-memory load per r
-#pragma unroll
-    for (int r = 1; r < 8; ++r) {
-        const float2 tw = S.tw1[r - 1][lane];
-        A[r] = cmul(A[r], tw);
-        constexpr float kC[8] = {1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
-                                 0.f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f};
-        constexpr float kS[8] = {0.f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f,
-                                 -1.f, -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f};
-        B[r] = cmul(B[r], cmul(tw, make_float2(kC[r], kS[r])));      // W16^r = exp(-2 pi i r / 16)
-    }
-
-    // ---- exchange 1 (two halves of r) + stage 2: radix-8 over b (m = 8b + c) -------------------
-    float2 C[8], D[8];
-#if CD_EXP == 2       // experiment: no exchanges at all
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { C[q] = A[q]; D[q] = B[q]; }
-#else
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        xb[r * kXbRow + lane] = A[r];
-        xb[r * kXbRow + lane + 32] = B[r];
-    }
-    __syncwarp();
-#pragma unroll
-    for (int b = 0; b < 8; ++b) C[b] = xb[j * kXbRow + 8 * b + c];      // r = j
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        xb[r * kXbRow + lane] = A[r + 4];
-        xb[r * kXbRow + lane + 32] = B[r + 4];
-    }
-    __syncwarp();
-#pragma unroll
-    for (int b = 0; b < 8; ++b) D[b] = xb[j * kXbRow + 8 * b + c];      // r = j + 4
-    __syncwarp();
-#endif
-    fft8<false>(C);
-    fft8<false>(D);
-#pragma unroll
-    for (int u = 1; u < 8; ++u) {
-        const float2 t = S.tw2[u - 1][c];
-        C[u] = cmul(C[u], t);
-        D[u] = cmul(D[u], t);
-    }
-
-    // ---- exchange 2 + stage 3: radix-8 over c', pruned to s in {0,1,6,7} -----------------------
-#if CD_EXP == 1 || CD_EXP == 2        // experiment: no second exchange (wrong results; measures what the exchange costs)
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { A[q] = C[q]; B[q] = D[q]; }
-#else
-#pragma unroll
-    for (int u = 0; u < 8; ++u) xb[j * kXbRow + 9 * u + c] = C[u];
-    __syncwarp();
-#pragma unroll
-    for (int q = 0; q < 8; ++q) A[q] = xb[j * kXbRow + 9 * c + q];
-    __syncwarp();
-#pragma unroll
-    for (int u = 0; u < 8; ++u) xb[j * kXbRow + 9 * u + c] = D[u];
-    __syncwarp();
-#pragma unroll
-    for (int q = 0; q < 8; ++q) B[q] = xb[j * kXbRow + 9 * c + q];
-    __syncwarp();
-#endif
-    fft8<true>(A);      // A[s] = Z[64 s + 8 c + j]
-    fft8<true>(B);      // B[s] = Z[64 s + 8 c + j + 4]
-
-    // ---- unpack the two real spectra and take |.|^2 for bins < 128 ------------------------------
-    // z = x1 + i x2  =>  Z[k] + conj Z[512-k] = 2 X1[k],  Z[k] - conj Z[512-k] = 2i X2[k].
-    // Z[512-k] of my A[s] (k = 64s + 8c + j) sits in lane (7-c, 4-j) as B[7-s] (j != 0) or in lane
-    // ((8-c)&7, 0) as A[7-s] (j == 0); of my B[s] (k + 4) in lane (7-c, 4-j) as A[7-s] (j != 0) or in
-    // lane (7-c, 0) as B[7-s] (j == 0).  Each lane serves exactly one requester, so the sender selects.
+// One frame pair: x[a] = z[32 a + lane], a = 0..12 (x[13..15] ignored), -> mel POWER of the two frames for bands
+// `lane` (lo) and `lane + 32` (hi); .x = first frame, .y = second frame.  `between` runs once the FFT registers are
+// dead (before the mel contraction): the caller issues the next pair's sample loads there.
+struct NoOp { __device__ __forceinline__ void operator()() const {} };
+template <class Between = NoOp>
+__device__ __forceinline__ void fft_mel_pair(float2 (&x)[16], const LaneCtx& L, int lane, float2& lo, float2& hi,
+                                             Between between = Between()) {
+    // ---- stage 1: DFT16 over a, then twiddles W512^(m r) ---------------------------------------------
+    fft16<true>(x);
     {
-        const int srcA = j ? ((7 - c) | ((4 - j) << 3)) : ((8 - c) & 7);
-        const int srcB = j ? ((7 - c) | ((4 - j) << 3)) : (7 - c);
-        float2 pA[2], pB[2];
+        const float2 w1 = L.tw[0], w2 = L.tw[1], w3 = L.tw[2];
+#if CD_TW == 1
+        const float2 w4 = lds64(L.tw4_s), w8 = lds64(L.tw4_s + 256), w12 = lds64(L.tw4_s + 512);
+#else
+        const float2 w4 = L.tw[3], w8 = L.tw[4], w12 = L.tw[5];
+#endif
+        x[F16(1)] = cmul(x[F16(1)], w1);
+        x[F16(2)] = cmul(x[F16(2)], w2);
+        x[F16(3)] = cmul(x[F16(3)], w3);
+        x[F16(4)] = cmul(x[F16(4)], w4);
+        x[F16(5)] = cmul(x[F16(5)], cmul(w4, w1));
+        x[F16(6)] = cmul(x[F16(6)], cmul(w4, w2));
+        x[F16(7)] = cmul(x[F16(7)], cmul(w4, w3));
+        x[F16(8)] = cmul(x[F16(8)], w8);
+        x[F16(9)] = cmul(x[F16(9)], cmul(w8, w1));
+        x[F16(10)] = cmul(x[F16(10)], cmul(w8, w2));
+        x[F16(11)] = cmul(x[F16(11)], cmul(w8, w3));
+        x[F16(12)] = cmul(x[F16(12)], w12);
+        x[F16(13)] = cmul(x[F16(13)], cmul(w12, w1));
+        x[F16(14)] = cmul(x[F16(14)], cmul(w12, w2));
+        x[F16(15)] = cmul(x[F16(15)], cmul(w12, w3));
+    }
+    // ---- the one exchange: lane (r, c) gathers Y'[2 b + c][r], b = 0..15 -------------------------------
 #pragma unroll
-        for (int sidx = 0; sidx < 2; ++sidx) {
-            const float2 sendA = j ? B[7 - sidx] : A[7 - sidx];
-            const float2 sendB = j ? A[7 - sidx] : B[7 - sidx];
-            pA[sidx].x = __shfl_sync(0xffffffffu, sendA.x, srcA);
-            pA[sidx].y = __shfl_sync(0xffffffffu, sendA.y, srcA);
-            pB[sidx].x = __shfl_sync(0xffffffffu, sendB.x, srcB);
-            pB[sidx].y = __shfl_sync(0xffffffffu, sendB.y, srcB);
+    for (int r = 0; r < 16; ++r)
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(L.xw_s + r * (kXchRow * 8)), "f"(x[F16(r)].x), "f"(x[F16(r)].y) : "memory");
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(x[2 * j].x), "=f"(x[2 * j].y), "=f"(x[2 * j + 1].x), "=f"(x[2 * j + 1].y) : "r"(L.xr_s + j * 16) : "memory");
+    // ---- stage 2: DFT16 over b.  c = 0: V(t) = E[t];  c = 1: V(t) = (-1)^t O[(t + 8) & 15] (sign flip of the
+    //      lanes m = 3 mod 4 folded into their window + the swapped halves of the c = 1 rows) ----------------
+    fft16<false>(x);
+    // ---- radix 2 across the lane pair (r, 0) <-> (r, 1), pruned: c = 0 keeps Z[r + 16 i], c = 1 Z[384 + r + 16 i] ----
+    float2 Z[8];
+    {
+        float2 R[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            R[i].x = __shfl_xor_sync(0xffffffffu, x[F16(8 + i)].x, 16);
+            R[i].y = __shfl_xor_sync(0xffffffffu, x[F16(8 + i)].y, 16);
         }
-        if (lane == 0) pA[1] = A[7];                 // k = 64: 512 - 64 = 448 = Z of this very lane (carry case)
-        // float2 {P_frame0, P_frame1} at padded bin index pidx(k) = k + 2 (k / 16): the padding found (offline
-        // search over the real band tables) to cost the fewest wavefronts for these stores + the mel reads
-        const int o = 8 * c + 2 * (c >> 1) + j;
+        // T_i = (-1)^i W32^i = (-1)^i (c_i, -s_i);  K_i = i T_i = (-1)^i (s_i, c_i)
+        constexpr float kc[8] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                                 0.70710678118654752f, 0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f};
+        constexpr float ks[8] = {0.f, 0.19509032201612825f, 0.38268343236508977f, 0.55557023301960218f,
+                                 0.70710678118654752f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f};
+        if (lane < 16) {                                   // Z = V(i) + T_i R_i
+            Z[0] = cadd(x[F16(0)], R[0]);
 #pragma unroll
-        for (int sidx = 0; sidx < 2; ++sidx) {
-            xb[72 * sidx + o] = pair_power(A[sidx], pA[sidx]);
-            xb[72 * sidx + o + 4] = pair_power(B[sidx], pB[sidx]);
+            for (int i = 1; i < 8; ++i) {
+                const float sg = (i & 1) ? -1.f : 1.f;
+                Z[i] = i == 4 ? cadd(x[F16(4)], w16_2(R[4])) : cadd(x[F16(i)], cmulc(R[i], sg * kc[i], -sg * ks[i]));
+            }
+        } else {                                           // Z = R_i + K_i V(i)
+            Z[0] = csub(R[0], mul_mi(x[F16(0)]));
+#pragma unroll
+            for (int i = 1; i < 8; ++i) {
+                const float sg = (i & 1) ? -1.f : 1.f;
+                Z[i] = i == 4 ? cadd(R[4], scale2(kH, csub(x[F16(4)], mul_mi(x[F16(4)]))))
+                              : cadd(R[i], cmulc(x[F16(i)], sg * ks[i], sg * kc[i]));
+            }
         }
     }
+    // ---- unpack the two real spectra: Z[512 - k] lives in the partner lane ((16 - r) & 15, 1 - c); the two lanes
+    //      swap their upper four values and each forms four bins' power pairs (tools/fft_lane_model.py) -------------
+    {
+        const bool r0 = (lane & 15) == 0;                  // residue 0: pairing shifted by one, bin 64 in lane 0's free slot
+        float2 rq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 a = Z[4 + q], b = Z[4 + ((q + 1) & 3)];
+            rq[q].x = __shfl_sync(0xffffffffu, r0 ? b.x : a.x, L.partner);
+            rq[q].y = __shfl_sync(0xffffffffu, r0 ? b.y : a.y, L.partner);
+        }
+        const float2 own0 = lane == 0 ? Z[4] : Z[0];
+        const float2 p0 = pair_power(own0, rq[3]), p1 = pair_power(Z[1], rq[2]);
+        const float2 p2 = pair_power(Z[2], rq[1]), p3 = pair_power(Z[3], rq[0]);
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(L.p0_s), "f"(p0.x), "f"(p0.y) : "memory");
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(L.pb_s + L.pstep), "f"(p1.x), "f"(p1.y) : "memory");
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(L.pb_s + 2 * L.pstep), "f"(p2.x), "f"(p2.y) : "memory");
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(L.pb_s + 3 * L.pstep), "f"(p3.x), "f"(p3.y) : "memory");
+    }
+    between();
     __syncwarp();
-
     // ---- banded mel contraction (cd_common.cuh): the lane reads the bins of its two segments once, for both
     //      frames, and hands the rising-side sums to the lane above ----------------------------------------
-    float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f), ulo = lo, uhi = lo;
+    lo = make_float2(0.f, 0.f);
+    hi = lo;
+    float2 ulo = lo, uhi = lo;
     {
-        // unused slots read the shared zero instead of being predicated off: one broadcast address in a bank pair
-        // (8) the live ones rarely touch -- 19 wavefronts for the six loads, no predicates, no conditional moves
-        const uint32_t xb_s = smem_u32(xb), zero_s = smem_u32(&S.zero2);
-        const int b0 = bin_lo & 0xff, n0 = bin_lo >> 8;
+        // unused slots read the region's zero slot instead of being predicated off
+        const uint32_t zero_s = L.pw_s + 8u * kPowZero;
+        const int b0 = L.bin_lo & 0xff, n0 = L.bin_lo >> 8;
 #pragma unroll
-        for (int s = 0; s < (CD_EXP == 5 ? 1 : kMelSlotsLo); ++s) {
+        for (int s = 0; s < kMelSlotsLo; ++s) {
             const int bin = b0 + s;
-            const float2 pw = lds64(s < n0 ? xb_s + 8u * (uint32_t)(bin + 2 * (bin >> 4)) : zero_s);
-            lo = fma2s(mw[s].x, pw, lo);
-            ulo = fma2s(mw[s].y, pw, ulo);
+            const float2 pw = lds64(s < n0 ? L.pw_s + 8u * (uint32_t)(bin + 2 * (bin >> 4)) : zero_s);
+            lo = fma2s(L.mw[s].x, pw, lo);
+            ulo = fma2s(L.mw[s].y, pw, ulo);
         }
-        const int b1 = bin_hi & 0xff, n1 = bin_hi >> 8;
+        const int b1 = L.bin_hi & 0xff, n1 = L.bin_hi >> 8;
 #pragma unroll
-        for (int s = 0; s < (CD_EXP == 5 ? 1 : kMelSlotsHi); ++s) {
+        for (int s = 0; s < kMelSlotsHi; ++s) {
             const int bin = b1 + s;
-            const float2 pw = lds64(s < n1 ? xb_s + 8u * (uint32_t)(bin + 2 * (bin >> 4)) : zero_s);
-            hi = fma2s(mw[kMelSlotsLo + s].x, pw, hi);
-            uhi = fma2s(mw[kMelSlotsLo + s].y, pw, uhi);
+            const float2 pw = lds64(s < n1 ? L.pw_s + 8u * (uint32_t)(bin + 2 * (bin >> 4)) : zero_s);
+            hi = fma2s(L.mw[kMelSlotsLo + s].x, pw, hi);
+            uhi = fma2s(L.mw[kMelSlotsLo + s].y, pw, uhi);
         }
         // band m += up(m - 1): lanes 1..31 take both sums from lane - 1; lane 0's band 32 takes up(31) from lane 31's
         // lo segment (its band 0 has nothing below it, and up(63) is identically zero)
@@ -411,116 +404,155 @@ __device__ __forceinline__ float frame_pair(SM& S, const T* __restrict__ clip, f
             hi.x += ax; hi.y += ay;
         }
     }
-    __syncwarp();                                    // xb is rewritten by the next pair
-
-    // ---- AmplitudeToDB: 10 log10(max(x, 1e-10)) (torchaudio functional.py:390) ------------------
-    float* row_lo = dst + lane * band_stride;
-    float* row_hi = dst + (lane + 32) * band_stride;
-    if (RAW) {
-        row_lo[0] = lo.x;
-        row_hi[0] = hi.x;
-        float m = fmaxf(lo.x, hi.x);
-        if (second) {
-            row_lo[frame_stride] = lo.y;
-            row_hi[frame_stride] = hi.y;
-            m = fmaxf(m, fmaxf(lo.y, hi.y));
-        }
-        return m;                                    // running max of the mel POWER (the PCEN variant's top_db needs it)
-    }
-    const float d0 = power_to_db(lo.x), d2 = power_to_db(hi.x);
-    row_lo[0] = d0;
-    row_hi[0] = d2;
-    float m = fmaxf(d0, d2);
-    if (second) {
-        const float d1 = power_to_db(lo.y), d3 = power_to_db(hi.y);
-        row_lo[frame_stride] = d1;
-        row_hi[frame_stride] = d3;
-        m = fmaxf(m, fmaxf(d1, d3));
-    }
-    return m;
+    // no trailing __syncwarp: the next pair's exchange writes touch another region, and its power stores come
+    // after its own first __syncwarp, which every lane reaches only after these reads
 }
 
-// DCT-II of the floored dB tile for frame t, coefficients of one parity (PAR = 0: c = 0,2,..,12;
+// ----------------------------------------------------------------------------------------------
+// sample access
+// ----------------------------------------------------------------------------------------------
+// The conditioned clip of AudioPreprocessor.process (:508-515) as a view of the caller's buffer: sample i of the
+// 16 000 is src[start + i - padl] when 0 <= i - padl < len (centre trim: start > 0; zero pad: padl > 0), else 0.
+template <class T>
+struct ClipView {
+    const T* src;
+    int len, start, padl;
+};
+template <class T>
+__device__ __forceinline__ float view_at(const ClipView<T>& v, int i) {
+    const int j = i - v.padl;
+    return (j >= 0 && j < v.len) ? (float)v.src[v.start + j] : 0.f;
+}
+// Sample i of the (possibly pre-emphasised) conditioned clip with torch.stft's reflect padding applied to the index.
+// T = float (the reference's waveform type) or int16_t (PCM as stored in wav files: the power-of-two scale cancels in
+// the peak normalisation, so both give bit-identical features).  PRE: y[i] = x[i] - coef x[i-1], y[0] = x[0]
+// (apply_pre_emphasis, src/preprocessing.py:213-239; product and difference rounded separately like the tensor ops).
+template <bool PRE, class T>
+__device__ __forceinline__ float sample_reflect(const ClipView<T>& v, int i, float coef) {
+    i = i < 0 ? -i : i;
+    i = i >= kSeg ? 2 * (kSeg - 1) - i : i;
+    const float x = view_at(v, i);
+    if (!PRE || i == 0) return x;
+    return __fsub_rn(x, __fmul_rn(coef, view_at(v, i - 1)));
+}
+
+// window weights of lane m: w[a] = 0.5 hann[32 a + m] (0 beyond sample 399), times the lane's sign (lanes m = 3 mod 4
+// carry -1: that rotates the second DFT16 of the odd lanes by 8, see fft_mel_pair) and the power-of-two pre-scale
+__device__ __forceinline__ void lane_window(const FeatTables* __restrict__ tables, float scale, int lane, float (&w)[13]) {
+    const float s = (lane & 3) == 3 ? -scale : scale;
+#pragma unroll
+    for (int a = 0; a < 12; ++a) w[a] = __ldg(&tables->win[32 * a + lane]) * s;
+    w[12] = lane < 16 ? __ldg(&tables->win[384 + lane]) * s : 0.f;
+}
+
+// raw[q] = sample s0 + 32 q + lane of the pair's 576-sample span; frame 0 uses q = 0..12, frame 1 q = 5..17
+template <bool MAYBE_SINGLE>
+__device__ __forceinline__ void form_inputs(const float (&raw)[18], const float (&w)[13], bool second, float2 (&x)[16]) {
+#pragma unroll
+    for (int a = 0; a < 13; ++a) x[a] = make_float2(w[a] * raw[a], (!MAYBE_SINGLE || second) ? w[a] * raw[a + 5] : 0.f);
+}
+// the pair's mel power into the tile: frames 2 p, 2 p + 1 of bands lane and lane + 32 as two 8-byte stores
+__device__ __forceinline__ float store_pair(float* db, int lane, int p, bool second, float2 lo, float2 hi) {
+    float2* row_lo = reinterpret_cast<float2*>(db + lane * kTilePitch + 2 * p);
+    float2* row_hi = reinterpret_cast<float2*>(db + (lane + 32) * kTilePitch + 2 * p);
+    if (!second) lo.y = hi.y = 0.f;                                    // column 101 of the tile: never read
+    *row_lo = lo;
+    *row_hi = hi;
+    return fmaxf(fmaxf(lo.x, hi.x), fmaxf(lo.y, hi.y));
+}
+
+// DCT-II of the floored dB tile for the frame pair (2 j, 2 j + 1), coefficients of one parity (PAR = 0: c = 0,2,..,12;
 // PAR = 1: c = 1,3,..,11).  cos(pi (m + 1/2) c / 64) is even (c even) or odd (c odd) about m = 31.5, so
-// each coefficient is a 32-term sum over d[m] +- d[63 - m], shared by all coefficients of that parity.
+// each coefficient is a 32-term sum over d[m] +- d[63 - m], shared by all coefficients of that parity; both frames
+// ride in one packed register pair (one 8-byte tile read per band, FFMA2).
 // POWER: the tile holds mel power (PCEN variant); dB and its top_db floor are applied on the way in.
 // Returns {sum, sum of squares} of the coefficients it wrote (the block's mean / std come from one reduction).
 template <int PAR, bool POWER>
-__device__ __forceinline__ float2 mfcc_par(const float* __restrict__ db, float* __restrict__ mf, int t, float floor_db) {
+__device__ __forceinline__ float2 mfcc_par(const float* __restrict__ db, float* __restrict__ mf, int j, float floor_db) {
     constexpr int NC = PAR ? 6 : 7;
-    float acc[NC];
+    float2 acc[NC];
 #pragma unroll
-    for (int i = 0; i < NC; ++i) acc[i] = 0.f;
+    for (int i = 0; i < NC; ++i) acc[i] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int m = 0; m < kMels / 2; ++m) {
-        float lo = db[m * kFrames + t], hi = db[(kMels - 1 - m) * kFrames + t];
+        float2 lo = *reinterpret_cast<const float2*>(db + m * kTilePitch + 2 * j);
+        float2 hi = *reinterpret_cast<const float2*>(db + (kMels - 1 - m) * kTilePitch + 2 * j);
         if (POWER) {
-            lo = fmaxf(power_to_db(lo), floor_db);
-            hi = fmaxf(power_to_db(hi), floor_db);
+            lo = make_float2(fmaxf(power_to_db(lo.x), floor_db), fmaxf(power_to_db(lo.y), floor_db));
+            hi = make_float2(fmaxf(power_to_db(hi.x), floor_db), fmaxf(power_to_db(hi.y), floor_db));
         }
-        const float d = PAR ? lo - hi : lo + hi;
+        const float2 d = PAR ? csub(lo, hi) : cadd(lo, hi);
 #pragma unroll
-        for (int i = 0; i < NC; ++i) acc[i] = fmaf(c_dct[(PAR + 2 * i) * kMels + m], d, acc[i]);
+        for (int i = 0; i < NC; ++i) acc[i] = fma2s(c_dct[(PAR + 2 * i) * kMels + m], d, acc[i]);
     }
+    const bool two = 2 * j + 1 < kFrames;                              // frame 101 does not exist
     float s = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-        mf[(PAR + 2 * i) * kFrames + t] = acc[i];
-        s += acc[i];
-        s2 = fmaf(acc[i], acc[i], s2);
+        *reinterpret_cast<float2*>(mf + (PAR + 2 * i) * kTilePitch + 2 * j) = acc[i];
+        s += acc[i].x;
+        s2 = fmaf(acc[i].x, acc[i].x, s2);
+        if (two) {
+            s += acc[i].y;
+            s2 = fmaf(acc[i].y, acc[i].y, s2);
+        }
     }
     return make_float2(s, s2);
 }
 
-// Everything after the tile is complete: top_db floor, mel rows, DCT-13, mean / unbiased std
+// Everything after the power tile is complete: peak scaling, dB, top_db floor, mel rows, DCT-13, mean / unbiased std
 // normalisation, deltas; fp32 features to `out` and/or the stem's bf16 map to `mo` (either may be null).
-// PCEN = false: the tile holds dB, `top` is its block max; rows 0..63 are clamp((dB + 80) / 80).
-// PCEN = true : the tile holds mel POWER, `top` is its block max; rows 0..63 are apply_pcen (src/preprocessing.py:
-//               305-340) scaled to [0, 1] by the clip's min / max (:400-404); the MFCC rows still come from the dB.
+// The tile holds un-normalised mel power, `top` is its block max, inv2 = 1 / peak^2 (normalize(), :199-212, applied to
+// the power: the STFT is linear).
+// PCEN = false: rows 0..63 are clamp((dB + 80) / 80) of the floored dB.
+// PCEN = true : rows 0..63 are apply_pcen (src/preprocessing.py:305-340) scaled to [0, 1] by the clip's min / max
+//               (:400-404); the MFCC rows still come from the dB.
 // Ends with the block in sync except for the final stores.
 // dd: also emit the delta-delta rows 90..102 = compute_deltas(compute_deltas(mfcc)) (:463-466).
 template <bool PCEN, class SM>
-__device__ __forceinline__ void feat_tail(SM& S, float top, float* __restrict__ out, __nv_bfloat16* __restrict__ mo, int tid,
-                                          bool dd = false) {
-    const float floor_db = (PCEN ? power_to_db(top) : top) - 80.0f;    // top_db = 80
+__device__ __forceinline__ void feat_tail(SM& S, float top, float inv2, float* __restrict__ out, __nv_bfloat16* __restrict__ mo,
+                                          int tid, bool dd = false) {
+    const float floor_db = power_to_db(top * inv2) - 80.0f;           // top_db = 80 (monotone: the max of the dB)
 
-    if (!PCEN) {
-        // ---- mel block rows 0..63: max(dB, floor) -> (dB + 80) / 80 -> clamp ------------------------
-        // The CNN stem's operand rides along: the same values rounded to bf16, scattered straight into the clip's
-        // blocked map (cd_common.cuh: bmap_offset).  Its padding elements are never written by anyone: the map
-        // lives in the tensor-core workspace, which is zeroed once at allocation.
-        for (int i = tid; i < kMels * kFrames; i += kFeatThreads) {
-            const float v = fmaxf(S.db[i], floor_db);
-            S.db[i] = v;
+    // ---- rows 0..63: P / peak^2 -> dB -> max(dB, floor) -> (dB + 80) / 80 -> clamp ------------------------
+    // The CNN stem's operand rides along: the same values rounded to bf16, scattered straight into the clip's
+    // blocked map (cd_common.cuh: bmap_offset).  Its padding elements are never written by anyone: the map
+    // lives in the tensor-core workspace, which is zeroed once at allocation.
+    for (int i = tid; i < kMels * kFrames; i += kFeatThreads) {
+        const int r = i / kFrames, t = i - r * kFrames;
+        float* cell = S.db + r * kTilePitch + t;
+        const float p = *cell * inv2;
+        if (PCEN) {
+            *cell = p;
+        } else {
+            const float v = fmaxf(power_to_db(p), floor_db);
+            *cell = v;
             const float x01 = fminf(fmaxf((v + 80.0f) * 0.0125f, 0.f), 1.f);
             if (out) out[i] = x01;
-            if (mo) {
-                const int r = i / kFrames;
-                mo[bmap_offset(r + 3, i - r * kFrames + 3)] = __float2bfloat16_rn(x01);
-            }
+            if (mo) mo[bmap_offset(r + 3, t + 3)] = __float2bfloat16_rn(x01);
         }
-        __syncthreads();
     }
+    __syncthreads();
 
     // ---- MFCC = DCT-II(13 x 64) of the floored dB, then (x - mean) / (std + 1e-8) ---------------
-    float* mf = reinterpret_cast<float*>(&S.xb[0][0]);             // [13][101], FFT scratch is idle now
+    float* mf = reinterpret_cast<float*>(&S.xb[0][0]);             // [13][102], FFT scratch is idle now
+    static_assert(sizeof(float) * kMfcc * kTilePitch <= sizeof(float2) * (kXchElems + kPowZero), "MFCC scratch fits under warp 0's zero slot");
     float2 part = make_float2(0.f, 0.f);
     {
-        static_assert(kFeatThreads == 256, "two parity groups of 128 threads");
-        const int t = tid & 127;
-        if (t < kFrames) part = (tid >> 7) ? mfcc_par<1, PCEN>(S.db, mf, t, floor_db) : mfcc_par<0, PCEN>(S.db, mf, t, floor_db);
+        const int j = tid & 63, g = tid >> 6;                      // warps 0-1: even coefficients, warps 2-3: odd ones
+        if (j < kPairs && g < 2) part = g ? mfcc_par<1, PCEN>(S.db, mf, j, floor_db) : mfcc_par<0, PCEN>(S.db, mf, j, floor_db);
     }
     // mean and unbiased variance from one reduction of {sum, sum of squares}: |mean| is a fraction of the spread
     // here (c0 dominates both), so the one-pass form loses nothing in fp32 (checked against float64 on the goldens)
     constexpr int kN = kMfcc * kFrames;                            // 1313
-    const float2 tot = block_reduce_sum2(part, S.red);
+    const float2 tot = block_reduce2<false>(part, S.red);
     const float mean = tot.x * (1.0f / kN);
     const float var = fmaxf(tot.y - tot.x * mean, 0.f) * (1.0f / (kN - 1));
     const float inv_std = 1.0f / (sqrtf(var) + 1e-8f);
     {
         for (int i = tid; i < kN; i += kFeatThreads) {
             const int cidx = i / kFrames, t = i - cidx * kFrames;
-            const float* row = mf + cidx * kFrames;
+            const float* row = mf + cidx * kTilePitch;
             // __fmul_rn: never contracted into an FMA, so the bf16 map below sees identical values
             const float x0 = __fmul_rn(row[t] - mean, inv_std);
             const float xp = __fmul_rn(row[min(t + 1, kFrames - 1)] - mean, inv_std);
@@ -548,7 +580,7 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float* __restrict__ 
     if (PCEN) {
         // ---- PCEN rows 0..63 from the power tile: smoother = zero-padded mean of frames t-5 .. t+4 (avg_pool2d
         //      kernel (1, 10), padding (0, 5), cut to 101 columns); (P / (eps + M)^0.98 + 2)^0.5 - 2^0.5 ------------
-        constexpr int kPer = (kMels * kFrames + kFeatThreads - 1) / kFeatThreads;      // 26
+        constexpr int kPer = (kMels * kFrames + kFeatThreads - 1) / kFeatThreads;      // 26 (8 warps)
         float val[kPer];
         float vmin = INFINITY, vmax = -INFINITY;
 #pragma unroll
@@ -557,7 +589,7 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float* __restrict__ 
             float v = 0.f;
             if (i < kMels * kFrames) {
                 const int r = i / kFrames, t = i - r * kFrames;
-                const float* row = S.db + r * kFrames;
+                const float* row = S.db + r * kTilePitch;
                 float sm = 0.f;
 #pragma unroll
                 for (int j = -5; j <= 4; ++j) sm += (t + j >= 0 && t + j < kFrames) ? row[t + j] : 0.f;
@@ -568,8 +600,9 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float* __restrict__ 
             }
             val[k] = v;
         }
-        vmax = block_reduce<true>(vmax, S.red);
-        vmin = -block_reduce<true>(-vmin, S.red);
+        const float2 mm = block_reduce2<true>(make_float2(vmax, -vmin), S.red);
+        vmax = mm.x;
+        vmin = -mm.y;
         const float range = (vmax - vmin) + 1e-8f;
 #pragma unroll
         for (int k = 0; k < kPer; ++k) {
@@ -587,33 +620,44 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float* __restrict__ 
 }
 
 template <class T>
-struct ClipDesc {
-    const T* src;         // first sample of the clip
-    int len;              // samples available
-};
-
-template <class T>
-__device__ __forceinline__ ClipDesc<T> clip_desc(const T* audio, const int64_t* offs, const int32_t* lens,
-                                              int64_t stride_or_hop, int mode, int64_t b) {
-    ClipDesc<T> d;
+__device__ __forceinline__ ClipView<T> clip_view(const T* audio, const int64_t* offs, const int32_t* lens,
+                                                int64_t stride_or_hop, int mode, int64_t b) {
+    ClipView<T> v;
     if ((mode & kModeMask) == kModeVar) {
-        d.src = audio + offs[b];
-        d.len = lens[b];
+        const int n = lens[b];
+        v.src = audio + offs[b];
+        v.len = n < kSeg ? n : kSeg;                                   // samples that survive pad_or_trim
+        v.start = n > kSeg ? (n - kSeg) / 2 : 0;                       // trim offset (src/preprocessing.py:378)
+        v.padl = n < kSeg ? (kSeg - n) / 2 : 0;                        // left zero pad (:383)
     } else {
-        d.src = audio + b * stride_or_hop;
-        d.len = kSeg;
+        v.src = audio + b * stride_or_hop;
+        v.len = kSeg;
+        v.start = 0;
+        v.padl = 0;
     }
-    return d;
+    return v;
 }
-template <class T>
-__device__ __forceinline__ bool bulk_ok(const ClipDesc<T>& d) {
-    return d.len == kSeg && ((reinterpret_cast<uintptr_t>(d.src) & 15) == 0);
+
+// Frame pairs of a clip are dealt to the warps as CONTIGUOUS runs (8 warps: 6, 6, 7, 7, 7, 6, 6, 6) so that consecutive
+// pairs of a warp share samples in registers; the longer runs go to middle warps (the first and last warp hold the
+// slower reflect-padded pairs 0, 49, 50).
+__device__ __forceinline__ void warp_pair_range(int warp, int& p0, int& p1) {
+    constexpr int base = kPairs / kFeatWarps, rem = kPairs % kFeatWarps, e0 = (kFeatWarps - rem) / 2;
+    const int extra_before = min(max(warp - e0, 0), rem);
+    p0 = warp * base + extra_before;
+    p1 = p0 + base + ((warp >= e0 && warp < e0 + rem) ? 1 : 0);
+}
+
+// one-time per CTA: the per-lane twiddles that live in shared memory (CD_TW = 1)
+template <class SM>
+__device__ __forceinline__ void stage_tables(SM& S, const FeatTables* __restrict__ tables, int tid) {
+    if (tid < 96) S.tw4[tid >> 5][tid & 31] = tables->twl[tid & 31][3 + (tid >> 5)];
 }
 
 // PRE / PCEN: the use_pre_emphasis / use_pcen variants of the 90-feature path (the part that keeps
 // the CNN input at 90 rows); <false, false> is the training configuration (src/train.py:264-287) and the benchmark.
 template <class T, bool PRE, bool PCEN>
-__global__ void __launch_bounds__(kFeatThreads, 2)
+__global__ void __launch_bounds__(kFeatThreads, kFeatCtasPerSm)
 feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const int32_t* __restrict__ lens,
             int64_t stride_or_hop, int mode, int64_t B, float* __restrict__ feat,
             __nv_bfloat16* __restrict__ map_out, const FeatTables* __restrict__ tables, float coef) {
@@ -621,111 +665,138 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
     FeatSmem& S = *reinterpret_cast<FeatSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // ---- one-time per CTA: twiddles -> smem, per-lane mel taps -> registers, barrier ----------------
-    {
-        const float* src = reinterpret_cast<const float*>(tables);
-        float* dst = reinterpret_cast<float*>(&S.tw1[0][0]);
-        constexpr int n = (sizeof(S.tw1) + sizeof(S.tw2)) / 4;
-        static_assert(offsetof(FeatTables, tw2) == sizeof(S.tw1) && offsetof(FeatSmem, tw2) - offsetof(FeatSmem, tw1) == sizeof(S.tw1), "layout");
-        for (int i = tid; i < n; i += kFeatThreads) dst[i] = src[i];
-        if (tid == 0) S.zero2 = make_float2(0.f, 0.f);
-    }
-    float2 mw[kMelSlots];
-#pragma unroll
-    for (int s = 0; s < kMelSlots; ++s) mw[s] = tables->melt[s][lane];
-    const int bin_lo = tables->melb[0][lane], bin_hi = tables->melb[1][lane];
-    if (tid == 0) {
-        mbar_init(&S.bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    LaneCtx L;
+    lane_ctx_init(L, tables, S.xb[warp], &S.tw4[0][0], lane);
+    stage_tables(S, tables, tid);
+    if (lane == 0) S.xb[warp][kXchElems + kPowZero] = make_float2(0.f, 0.f);
     __syncthreads();
+    int wp0, wp1;
+    warp_pair_range(warp, wp0, wp1);
+    const bool var = (mode & kModeMask) == kModeVar;
+    const bool normalize = !(mode & kModeNoNormalize);
 
-    uint32_t phase = 0u;
-    T* clip = reinterpret_cast<T*>(S.clip);
-    constexpr uint32_t kClipBytes = kSeg * sizeof(T);
-    // One bulk copy (TMA engine) brings a clip in.  It is issued as soon as the previous clip's samples are dead
-    // (after its last FFT), so it lands under that clip's tail; the clip after that is pulled into L2 meanwhile.
-    auto fetch = [&](int64_t bf) {                                  // thread 0 only
-        if (bf < B) {
-            const ClipDesc<T> df = clip_desc(audio, offs, lens, stride_or_hop, mode, bf);
-            if (bulk_ok(df)) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses -> async proxy
-                mbar_expect_tx(&S.bar, kClipBytes);
-                bulk_g2s(clip, df.src, kClipBytes, &S.bar);
-            }
-        }
-        const int64_t bn = bf + gridDim.x;
-        if (bn < B) {
-            const ClipDesc<T> dn = clip_desc(audio, offs, lens, stride_or_hop, mode, bn);
-            if (bulk_ok(dn))
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(dn.src), "r"(kClipBytes) : "memory");
-        }
-    };
-    if (tid == 0) fetch(blockIdx.x);
     for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
-        const ClipDesc<T> d = clip_desc(audio, offs, lens, stride_or_hop, mode, b);
-
-        // ---- stage the clip + peak ------------------------------------------------------------------
-        float peak = 0.f;
-        if (bulk_ok(d)) {
-            mbar_wait(&S.bar, phase);
-            phase ^= 1u;
-            if (sizeof(T) == 4) {
-                const float4* c4 = reinterpret_cast<const float4*>(clip);
-                for (int i = tid; i < kSeg / 4; i += kFeatThreads) {
-                    const float4 v = c4[i];
-                    peak = fmaxf(peak, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-                }
-            } else {
-                const short4* c4 = reinterpret_cast<const short4*>(clip);
-                for (int i = tid; i < kSeg / 4; i += kFeatThreads) {
-                    const short4 v = c4[i];
-                    peak = fmaxf(peak, fmaxf(fmaxf(fabsf((float)v.x), fabsf((float)v.y)), fmaxf(fabsf((float)v.z), fabsf((float)v.w))));
-                }
-            }
-        } else {
-            // AudioPreprocessor.process: normalise over the WHOLE clip, then centre-trim / zero-pad
-            const int n = d.len;
-            for (int i = tid; i < n; i += kFeatThreads) peak = fmaxf(peak, fabsf((float)d.src[i]));
-            const int start = n > kSeg ? (n - kSeg) / 2 : 0;          // trim offset (src/preprocessing.py:378)
-            const int padl = n < kSeg ? (kSeg - n) / 2 : 0;           // left zero pad (:383)
-            for (int i = tid; i < kSeg; i += kFeatThreads) {
-                const int sidx = i - padl;
-                clip[i] = (sidx >= 0 && sidx < n) ? d.src[start + sidx] : (T)0;
+        const ClipView<T> v = clip_view(audio, offs, lens, stride_or_hop, mode, b);
+        const bool fast = v.len == kSeg && v.start == 0;               // a whole 16 000-sample clip: direct loads
+        if (tid == 0) {                                                // pull the clip after this one into L2 meanwhile
+            const int64_t bn = b + gridDim.x;
+            if (bn < B) {
+                const ClipView<T> vn = clip_view(audio, offs, lens, stride_or_hop, mode, bn);
+                const T* pn = vn.src + vn.start;
+                if (vn.len == kSeg && (reinterpret_cast<uintptr_t>(pn) & 15) == 0)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pn), "r"((uint32_t)(kSeg * sizeof(T))) : "memory");
             }
         }
-        peak = block_reduce<true>(peak, S.red);                        // its barriers also order the generic stores
-        // normalize() (:199-212): x / max|x|, skipped for silence.  The scale is folded into this lane's
-        // 13 window weights (held in registers for the whole clip) instead of rewriting the clip.
-        const float inv = (peak > 0.f && !(mode & kModeNoNormalize)) ? 1.0f / peak : 1.0f;
-        float wA[7], wB[6];
+        // AudioPreprocessor.process normalises over the WHOLE clip before it trims or pads: clips that do not take the
+        // direct-load path get their peak from a pass of their own
+        float peak_pre = 0.f;
+        if (!fast && normalize) {
+            const int n = var ? lens[b] : kSeg;
+            const T* p = var ? audio + offs[b] : v.src;
+            for (int i = tid; i < n; i += kFeatThreads) peak_pre = fmaxf(peak_pre, fabsf((float)p[i]));
+        }
+
+        float pre = 1.0f, top, peak;
+        for (int pass = 0;; ++pass) {
+            float w[13];
+            lane_window(tables, pre, lane, w);
+            float pmax = 0.f, amax = peak_pre;
+            float raw[18];
+            bool have = false;                                         // raw[] already holds this pair's samples
+            for (int p = wp0; p < wp1; ++p) {
+                const bool edge = (p == 0) || (p >= 49);
+                const int s0 = 2 * kHop * p - kWin / 2 + lane;         // this lane's sample of window tap 0
+                float2 x[16], lo, hi;
+                if (edge || !fast) {
+                    // reflect-padded pairs and clips that are trimmed / padded: every sample through the index mapping
+                    const bool second = (2 * p + 1) < kFrames;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            wA[a] = __ldg(&tables->win[64 * a + lane]) * inv;
-            wB[a] = __ldg(&tables->win[64 * a + lane + 32]) * inv;
+                    for (int q = 0; q < 18; ++q) raw[q] = sample_reflect<PRE>(v, s0 + 32 * q, coef);
+                    if (fast) {                                        // reflected samples are samples: they count for the peak
+#pragma unroll
+                        for (int q = 0; q < 18; ++q) {
+                            if (PRE) {
+                                int i = s0 + 32 * q;
+                                i = i < 0 ? -i : i;
+                                i = i >= kSeg ? 2 * (kSeg - 1) - i : i;
+                                amax = fmaxf(amax, fabsf((float)v.src[i]));
+                            } else {
+                                amax = fmaxf(amax, fabsf(raw[q]));
+                            }
+                        }
+                    }
+                    form_inputs<true>(raw, w, second, x);
+                    have = false;
+                    if (p == 0 && fast && p + 1 < wp1) {               // pair 1 starts from pair 0's last eight sample registers
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) raw[q] = raw[q + 10];
+                        have = true;
+                    }
+                    const bool nxt = have;
+                    fft_mel_pair(x, L, lane, lo, hi, [&]() {
+                        if (nxt) {
+                            const T* ps = v.src + s0 + 2 * kHop;
+#pragma unroll
+                            for (int q = 8; q < 18; ++q) {
+                                const float xq = (float)ps[32 * q];
+                                amax = fmaxf(amax, fabsf(xq));
+                                raw[q] = PRE ? __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1])) : xq;
+                            }
+                        }
+                    });
+                    pmax = fmaxf(pmax, store_pair(S.db, lane, p, second, lo, hi));
+                } else {
+                    if (!have) {                                       // first pair of the warp's run
+                        const T* ps = v.src + s0;
+#pragma unroll
+                        for (int q = 0; q < 18; ++q) {
+                            const float xq = (float)ps[32 * q];
+                            amax = fmaxf(amax, fabsf(xq));
+                            raw[q] = PRE ? __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1])) : xq;
+                        }
+                    }
+                    form_inputs<false>(raw, w, true, x);
+                    // the samples of the next pair: 8 carried in registers, 10 new ones issued once this pair's FFT
+                    // registers are dead, consumed after the mel contraction
+                    have = (p + 1 < wp1) && (p + 1) < 49;
+                    if (have) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) raw[q] = raw[q + 10];
+                    }
+                    const bool nxt = have;
+                    fft_mel_pair(x, L, lane, lo, hi, [&]() {
+                        if (nxt) {
+                            const T* ps = v.src + s0 + 2 * kHop;
+#pragma unroll
+                            for (int q = 8; q < 18; ++q) {
+                                const float xq = (float)ps[32 * q];
+                                amax = fmaxf(amax, fabsf(xq));
+                                raw[q] = PRE ? __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1])) : xq;
+                            }
+                        }
+                    });
+                    pmax = fmaxf(pmax, store_pair(S.db, lane, p, true, lo, hi));
+                }
+            }
+            const float2 mx = block_reduce2<true>(make_float2(pmax, amax), S.red);   // barrier: the power tile is complete
+            top = mx.x;
+            peak = mx.y;
+            // normalize() (:199-212) is x / max|x|, skipped for silence.  A peak far from 1 would push the power out of
+            // fp32's range, so such clips (|log2 peak| > 24) are redone with the window pre-scaled by 2^-e -- exact.
+            if (pass == 0 && normalize && peak > 0.f && (peak < 5.9604645e-8f || peak > 16777216.f)) {
+                pre = ldexpf(1.0f, min(max(-ilogbf(peak), -126), 126));
+                continue;
+            }
+            break;
         }
-        wA[6] = lane < 16 ? __ldg(&tables->win[384 + lane]) * inv : 0.f;
-
-        // ---- STFT -> mel -> dB, one frame pair per warp per round -----------------------------------
-        float wmax = -INFINITY;
-        for (int p = warp; p < (CD_EXP == 3 ? 0 : kPairs); p += kFeatWarps) {
-            const bool edge = (p == 0) || (p >= 49);
-            float* dst = S.db + 2 * p;
-            const int base0 = 2 * kHop * p - kWin / 2;
-            const bool second = (2 * p + 1) < kFrames;
-            wmax = fmaxf(wmax, edge ? frame_pair<true, PCEN, PRE>(S, clip, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, base0, second, lane, dst, kFrames, 1, coef)
-                                    : frame_pair<false, PCEN, PRE>(S, clip, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, base0, second, lane, dst, kFrames, 1, coef));
+        float inv2 = 1.0f;
+        if (normalize && peak > 0.f) {
+            const float inv = 1.0f / (peak * pre);
+            inv2 = inv * inv;
         }
-        const float top = block_reduce<true>(wmax, S.red);             // barrier: dB tile complete, clip buffer dead
-        if (tid == 0) fetch(b + gridDim.x);
-#if CD_EXP == 4       // experiment: no tail (keeps one store per thread so nothing upstream is dead code)
-        if (feat) feat[b * (int64_t)kFeatElem + tid] = top + S.db[tid * 25];
-        if (map_out) map_out[b * (int64_t)kMapElems + tid] = __float2bfloat16_rn(top + S.db[tid * 25]);
-#else
         const bool dd = (mode & kModeDeltaDelta) != 0;
-        feat_tail<PCEN>(S, top, feat ? feat + b * (int64_t)(dd ? kFeatElemDD : kFeatElem) : nullptr,
+        feat_tail<PCEN>(S, top, inv2, feat ? feat + b * (int64_t)(dd ? kFeatElemDD : kFeatElem) : nullptr,
                         map_out ? map_out + b * (int64_t)(dd ? NetShape<kFeatDD>::MAP_ELEMS : kMapElems) : nullptr, tid, dd);
-#endif
         __syncthreads();                                               // xb / db free again
     }
 }
@@ -735,48 +806,14 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
 // ----------------------------------------------------------------------------------------------
 // With hop = 160 h, window j's frame t is the stream's global frame j h + t (centred at sample
 // 160 (j h + t)); only frames 0, 1, 99, 100 of a window see its reflect padding.  So the mel POWER of
-// every global frame is computed once (stream_mel_kernel), each window takes frames 2..97 from there,
-// scaled by 1/peak^2 (peak normalisation is a scalar on the samples), and recomputes just the pairs
-// (0,1), (98,99), (100,-) from its own samples.  The window peak is the max of 100 per-hop block maxima.
+// every global frame is computed once (stream_mel_kernel), each window takes frames 2..97 from there
+// and recomputes just the pairs (0,1), (98,99), (100,-) from its own samples; the peak normalisation is the
+// scalar 1 / peak^2 on the power (feat_tail).  The window peak is the max of 100 per-hop block maxima.
 struct MelSmem {
     float2 xb[kFeatWarps][kXbElems];
-    float2 tw1[7][64];
-    float2 tw2[7][8];
-    float2 zero2;
+    float2 tw4[3][32];
 };
-static_assert(offsetof(MelSmem, xb) % 128 == 0 && offsetof(MelSmem, zero2) % 128 == 64, "zero2 sits in bank pair 8 of xb's numbering");
-struct StreamSmem {
-    float2 xb[kFeatWarps][kXbElems];
-    float  db[kMels * kFrames];
-    float2 tw1[7][64];
-    float2 tw2[7][8];
-    float2 zero2;
-    float  red[64];
-};
-static_assert(offsetof(StreamSmem, xb) % 128 == 0 && offsetof(StreamSmem, zero2) % 128 == 64, "zero2 sits in bank pair 8 of xb's numbering");
-
-template <class SM>
-__device__ __forceinline__ void load_lane_tables(SM& S, const FeatTables* __restrict__ tables, float2 (&mw)[kMelSlots],
-                                                 int& bin_lo, int& bin_hi, int tid, int lane) {
-    const float* src = reinterpret_cast<const float*>(tables);
-    float* dst = reinterpret_cast<float*>(&S.tw1[0][0]);
-    constexpr int n = (sizeof(S.tw1) + sizeof(S.tw2)) / 4;
-    for (int i = tid; i < n; i += kFeatThreads) dst[i] = src[i];
-    if (tid == 0) S.zero2 = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int s = 0; s < kMelSlots; ++s) mw[s] = tables->melt[s][lane];
-    bin_lo = tables->melb[0][lane];
-    bin_hi = tables->melb[1][lane];
-}
-
-__device__ __forceinline__ void lane_window(const FeatTables* __restrict__ tables, float inv, int lane, float (&wA)[7], float (&wB)[6]) {
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-        wA[a] = __ldg(&tables->win[64 * a + lane]) * inv;
-        wB[a] = __ldg(&tables->win[64 * a + lane + 32]) * inv;
-    }
-    wA[6] = lane < 16 ? __ldg(&tables->win[384 + lane]) * inv : 0.f;
-}
+using StreamSmem = FeatSmem;
 
 // bmax[i] = max |x[160 i .. 160 i + 159]|, one warp per block
 __global__ void __launch_bounds__(256)
@@ -792,64 +829,90 @@ block_max_kernel(const float* __restrict__ audio, int64_t n_blocks, float* __res
 
 // melp[f][64] = un-normalised mel power of global frame f, f in [2, F)
 template <bool PRE>
-__global__ void __launch_bounds__(kFeatThreads, 2)
+__global__ void __launch_bounds__(kFeatThreads, kFeatCtasPerSm)
 stream_mel_kernel(const float* __restrict__ audio, int64_t F, float* __restrict__ melp, const FeatTables* __restrict__ tables,
                   float coef) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     MelSmem& S = *reinterpret_cast<MelSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float2 mw[kMelSlots];
-    float wA[7], wB[6];
-    int bin_lo, bin_hi;
-    load_lane_tables(S, tables, mw, bin_lo, bin_hi, tid, lane);
-    lane_window(tables, 1.0f, lane, wA, wB);
+    LaneCtx L;
+    lane_ctx_init(L, tables, S.xb[warp], &S.tw4[0][0], lane);
+    stage_tables(S, tables, tid);
+    if (lane == 0) S.xb[warp][kXchElems + kPowZero] = make_float2(0.f, 0.f);
+    float w[13];
+    lane_window(tables, 1.0f, lane, w);
     __syncthreads();
     const int64_t n_pairs = (F - 2 + 1) / 2;
     for (int64_t q = (int64_t)blockIdx.x * kFeatWarps + warp; q < n_pairs; q += (int64_t)gridDim.x * kFeatWarps) {
         int64_t f0 = 2 + 2 * q;
         if (f0 + 1 >= F) f0 = F - 2;                  // odd tail: redo (F-2, F-1); both writers store identical values
-        const float* base = audio + f0 * kHop - kWin / 2;
-        frame_pair<false, true, PRE>(S, base, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, 0, true, lane, melp + f0 * kMels, 1, kMels, coef);
+        const float* ps = audio + f0 * kHop - kWin / 2 + lane;       // frames >= 2 start >= 120 samples into the stream
+        float raw[18];
+#pragma unroll
+        for (int k = 0; k < 18; ++k) {
+            const float xq = ps[32 * k];
+            raw[k] = PRE ? __fsub_rn(xq, __fmul_rn(coef, ps[32 * k - 1])) : xq;
+        }
+        float2 x[16], lo, hi;
+        form_inputs<false>(raw, w, true, x);
+        fft_mel_pair(x, L, lane, lo, hi);
+        float* o = melp + f0 * kMels + lane;
+        o[0] = lo.x;
+        o[32] = hi.x;
+        o[kMels] = lo.y;
+        o[kMels + 32] = hi.y;
     }
 }
 
 template <bool PRE, bool PCEN>
-__global__ void __launch_bounds__(kFeatThreads, 2)
+__global__ void __launch_bounds__(kFeatThreads, kFeatCtasPerSm)
 stream_window_kernel(const float* __restrict__ audio, int64_t hop, int64_t n_windows, const float* __restrict__ melp,
                      const float* __restrict__ bmax, float* __restrict__ feat, __nv_bfloat16* __restrict__ map_out,
                      const FeatTables* __restrict__ tables, float coef, int dd) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     StreamSmem& S = *reinterpret_cast<StreamSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float2 mw[kMelSlots];
-    int bin_lo, bin_hi;
-    load_lane_tables(S, tables, mw, bin_lo, bin_hi, tid, lane);
+    LaneCtx L;
+    lane_ctx_init(L, tables, S.xb[warp], &S.tw4[0][0], lane);
+    stage_tables(S, tables, tid);
+    if (lane == 0) S.xb[warp][kXchElems + kPowZero] = make_float2(0.f, 0.f);
     __syncthreads();
     const int64_t h = hop / kHop;
     for (int64_t j = blockIdx.x; j < n_windows; j += gridDim.x) {
-        float peak = tid < kSeg / kHop ? bmax[j * h + tid] : 0.f;
-        peak = block_reduce<true>(peak, S.red);
-        const float inv = peak > 0.f ? 1.0f / peak : 1.0f;           // normalize(): skipped for silence
-        float wmax = -INFINITY;
+        const float peak = tid < kSeg / kHop ? bmax[j * h + tid] : 0.f;
+        float wmax = 0.f;
         if (warp < 3) {
             // frames that touch this window's reflect padding: pairs (0,1), (98,99), (100,-)
-            float wA[7], wB[6];
-            lane_window(tables, inv, lane, wA, wB);
+            float w[13];
+            lane_window(tables, 1.0f, lane, w);
             const int p = warp == 0 ? 0 : 48 + warp;
-            wmax = frame_pair<true, PCEN, PRE>(S, audio + j * hop, S.xb[warp], wA, wB, mw, bin_lo, bin_hi, 2 * kHop * p - kWin / 2,
-                                               (2 * p + 1) < kFrames, lane, S.db + 2 * p, kFrames, 1, coef);
+            const bool second = (2 * p + 1) < kFrames;
+            ClipView<float> v;
+            v.src = audio + j * hop;
+            v.len = kSeg;
+            v.start = 0;
+            v.padl = 0;
+            const int s0 = 2 * kHop * p - kWin / 2 + lane;
+            float raw[18];
+#pragma unroll
+            for (int q = 0; q < 18; ++q) raw[q] = sample_reflect<PRE>(v, s0 + 32 * q, coef);
+            float2 x[16], lo, hi;
+            form_inputs<true>(raw, w, second, x);
+            fft_mel_pair(x, L, lane, lo, hi);
+            wmax = store_pair(S.db, lane, p, second, lo, hi);
         } else {
             // frames 2..97 come from the shared global frames j h + t
-            const float inv2 = inv * inv;
             const float* src = melp + (j * h + 2) * kMels;
             for (int i = tid - 96; i < 96 * kMels; i += kFeatThreads - 96) {
                 const int t = i >> 6, m = i & 63;
-                const float d = PCEN ? src[i] * inv2 : power_to_db(src[i] * inv2);     // PCEN keeps the tile in power
-                S.db[m * kFrames + t + 2] = d;
+                const float d = src[i];
+                S.db[m * kTilePitch + t + 2] = d;
                 wmax = fmaxf(wmax, d);
             }
         }
-        feat_tail<PCEN>(S, block_reduce<true>(wmax, S.red), feat ? feat + j * (int64_t)(dd ? kFeatElemDD : kFeatElem) : nullptr,
+        const float2 mx = block_reduce2<true>(make_float2(wmax, peak), S.red);
+        const float inv = mx.y > 0.f ? 1.0f / mx.y : 1.0f;           // normalize(): skipped for silence
+        feat_tail<PCEN>(S, mx.x, inv * inv, feat ? feat + j * (int64_t)(dd ? kFeatElemDD : kFeatElem) : nullptr,
                         map_out ? map_out + j * (int64_t)(dd ? NetShape<kFeatDD>::MAP_ELEMS : kMapElems) : nullptr, tid, dd != 0);
         __syncthreads();
     }
@@ -867,16 +930,14 @@ static float bits2f(uint32_t u) {
 int build_feat_tables(cd_handle* h) {
     FeatTables* t = new FeatTables();
     const double two_pi = 6.283185307179586476925286766559;
-    for (int r = 1; r < 8; ++r)
-        for (int m = 0; m < 64; ++m) {
-            const double a = -two_pi * (double)((m * r) % 512) / 512.0;
-            t->tw1[r - 1][m] = make_float2((float)cos(a), (float)sin(a));
-        }
-    for (int u = 1; u < 8; ++u)
-        for (int c = 0; c < 8; ++c) {
-            const double a = -two_pi * (double)((c * u) % 64) / 64.0;
-            t->tw2[u - 1][c] = make_float2((float)cos(a), (float)sin(a));
-        }
+    {
+        const int rs[6] = {1, 2, 3, 4, 8, 12};
+        for (int m = 0; m < 32; ++m)
+            for (int i = 0; i < 6; ++i) {
+                const double a = -two_pi * (double)((m * rs[i]) % 512) / 512.0;
+                t->twl[m][i] = make_float2((float)cos(a), (float)sin(a));
+            }
+    }
     for (int n = 0; n < kWin; ++n) t->win[n] = 0.5f * bits2f(CD_HANN_BITS[n]);   // exact (power of two)
     {
         // bin -> the (at most two, adjacent) bands it feeds; segment m = bins whose lower band is m
@@ -922,6 +983,8 @@ int build_feat_tables(cd_handle* h) {
     big(feat_kernel<int16_t, true, false>, sizeof(FeatSmem));
     big(feat_kernel<int16_t, false, true>, sizeof(FeatSmem));
     big(feat_kernel<int16_t, true, true>, sizeof(FeatSmem));
+    big(stream_mel_kernel<false>, sizeof(MelSmem));
+    big(stream_mel_kernel<true>, sizeof(MelSmem));
     big(stream_window_kernel<false, false>, sizeof(StreamSmem));
     big(stream_window_kernel<true, false>, sizeof(StreamSmem));
     big(stream_window_kernel<false, true>, sizeof(StreamSmem));
@@ -931,7 +994,7 @@ int build_feat_tables(cd_handle* h) {
     return CD_OK;
 }
 
-// the four (pre-emphasis, PCEN) variants of a kernel template, picked by the handle's options
+// the four (pre-emphasis, PCEN) variants of a kernel template, picked by the call's options
 #define CD_FEAT_VARIANT(pre, pcen, CALL)           \
     do {                                           \
         if (pre) {                                 \
@@ -948,7 +1011,7 @@ int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets
                     cudaStream_t s) {
     if (B == 0) return CD_OK;
     const bool pre = (mode & kModePreEmph) != 0, pcen = (mode & kModePcen) != 0;
-    const int64_t slots = 2 * (int64_t)h->sm_count;     // two resident CTAs per SM
+    const int64_t slots = kFeatCtasPerSm * (int64_t)h->sm_count;     // resident CTAs
     if ((mode & kModeMask) == kModeStream && stride_or_hop % kHop == 0 && stride_or_hop <= kSeg / 2 && B >= 2) {
         // overlapping windows on the frame grid: share the STFT frames
         const int64_t hop = stride_or_hop, hh = hop / kHop;
@@ -993,11 +1056,11 @@ int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets
     return CD_OK;
 }
 
-// int16 PCM clips (fixed length): same kernel, 32 000-byte bulk copies
+// int16 PCM clips (fixed length): same kernel
 int launch_features_i16(cd_handle* h, const int16_t* d_audio, int64_t stride, int mode, float coef, int64_t B,
                         float* d_feat, __nv_bfloat16* d_map, cudaStream_t s) {
     if (B == 0) return CD_OK;
-    const int64_t slots = 2 * (int64_t)h->sm_count;
+    const int64_t slots = kFeatCtasPerSm * (int64_t)h->sm_count;
     const bool pre = (mode & kModePreEmph) != 0, pcen = (mode & kModePcen) != 0;
 #define CD_CALL(P, Q)                                                                                            \
     feat_kernel<int16_t, P, Q><<<(int)(B < slots ? B : slots), kFeatThreads, sizeof(FeatSmem), s>>>(              \
