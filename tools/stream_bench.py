@@ -16,7 +16,6 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner out of the JSON on stdout
 from cough_detector_b200 import _lib, create_model, sharding, synth  # noqa: E402
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
