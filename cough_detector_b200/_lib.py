@@ -75,11 +75,15 @@ SYMBOLS = {
     "cd_stream_windows": (_I64, [_I64, _I64]),
     "cd_resample_length": (_I64, [_I64, _I, _I]),
     "cd_resample": (_I, [_VP, _VP, _I64, _I64, _I, _I, _VP, _VP]),
+    "cd_condition_var": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _VP, _I64, _I64, _I, _I, _VP, _VP]),
+    "cd_host_alloc": (_I, [C.POINTER(_VP), C.c_size_t, _I]),
+    "cd_host_free": (_I, [_VP]),
     "cd_cnn_load": (_I, [_VP, C.POINTER(_ResidualWeights)]),
     "cd_cnn_forward": (_I, [_VP, _VP, _I64, _VP, _I, _VP]),
     "cd_cnn_forward_rows": (_I, [_VP, _VP, _I, _I64, _VP, _I, _VP]),
     "cd_predict": (_I, [_VP, _VP, _I64, C.c_float, _VP, _VP, _VP, _VP]),
     "cd_e2e_forward": (_I, [_VP, _VP, _I64, _I64, _VP, _VP, _I, _F, _I, _VP]),
+    "cd_e2e_forward_i16": (_I, [_VP, _VP, _I64, _I64, _VP, _VP, _I, _F, _I, _VP]),
     "cd_e2e_forward_stream": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _I, _F, _I, _VP]),
     "cd_e2e_forward_host": (_I, [_VP, _VP, _I64, _VP, _I, _F, _I]),
     "cd_e2e_forward_host_i16": (_I, [_VP, _VP, _I64, _VP, _I, _F, _I]),
@@ -220,6 +224,28 @@ class Handle:
                     "cd_resample")
         return out
 
+    def condition_var(self, packed: torch.Tensor, in_offsets, channels, n_in, orig_sr: int, new_sr: int = 16000):
+        """Batched resample + to_mono of clips packed in one device buffer (cd_condition_var).  packed: 1-D cuda fp32 or
+        int16; in_offsets / channels / n_in: per-clip python ints.  Returns (mono fp32 buffer, out_offsets, out_lengths)
+        -- the arguments of feat_forward_var."""
+        if not (packed.is_cuda and packed.device.index == self.device and packed.dtype in (torch.float32, torch.int16)):
+            raise CoughB200Error(f"packed audio must be a float32 or int16 tensor on cuda:{self.device}")
+        packed = packed.contiguous()
+        B = len(n_in)
+        n_out = [int(self.lib.cd_resample_length(int(n), int(orig_sr), int(new_sr))) for n in n_in]
+        out_off, acc = [], 0
+        for n in n_out:
+            out_off.append(acc)
+            acc += (n + 3) & ~3
+        desc = torch.tensor([list(in_offsets), out_off, list(channels), list(n_in)], dtype=torch.int64)
+        d64 = desc[:2].contiguous().to(packed.device, non_blocking=True)
+        d32 = desc[2:].to(torch.int32).contiguous().to(packed.device, non_blocking=True)
+        out = torch.zeros(acc + 4, device=packed.device, dtype=torch.float32)
+        self._check(self.lib.cd_condition_var(self._h, _ptr(packed), 1 if packed.dtype == torch.int16 else 0, _ptr(d64[0]),
+                                              _ptr(d32[0]), _ptr(d32[1]), _ptr(d64[1]), B, max(n_in) if B else 0,
+                                              int(orig_sr), int(new_sr), _ptr(out), self._stream()), "cd_condition_var")
+        return out, d64[1], torch.tensor(n_out, dtype=torch.int32)
+
     # ---- model ------------------------------------------------------------------------------
     def load_state_dict(self, sd: Dict[str, torch.Tensor], key=None):
         """Upload a reference-format CoughDetectorResidual state_dict (BN folded by the library)."""
@@ -287,14 +313,21 @@ class Handle:
     # ---- end to end -------------------------------------------------------------------------
     def e2e_forward(self, audio: torch.Tensor, precision: int = PRECISION_BF16, return_features: bool = False,
                     opts: FeatOptions = TRAINING_CONFIG, normalize: bool = True):
-        audio = self._dev_f32(audio, "audio")
+        i16 = audio.dtype == torch.int16                    # int16 PCM stays int16: cd_e2e_forward_i16
+        if i16:
+            if not (audio.is_cuda and audio.device.index == self.device):
+                raise CoughB200Error(f"audio must live on cuda:{self.device}")
+            audio = audio.contiguous()
+        else:
+            audio = self._dev_f32(audio, "audio")
         if audio.dim() != 2 or audio.shape[1] != SEGMENT:
             raise CoughB200Error(f"audio must be (B, {SEGMENT}), got {tuple(audio.shape)}")
         B = audio.shape[0]
         logits = torch.empty(B, 2, device=audio.device, dtype=torch.float32)
         feat = torch.empty(B, 1, opts.n_features, N_FRAMES, device=audio.device, dtype=torch.float32) if return_features else None
-        self._check(self.lib.cd_e2e_forward(self._h, _ptr(audio), SEGMENT, B, _ptr(logits), _ptr(feat), opts.flags(normalize),
-                                            opts.pre_emphasis_coef, precision, self._stream()), "cd_e2e_forward")
+        fn = self.lib.cd_e2e_forward_i16 if i16 else self.lib.cd_e2e_forward
+        self._check(fn(self._h, _ptr(audio), SEGMENT, B, _ptr(logits), _ptr(feat), opts.flags(normalize),
+                       opts.pre_emphasis_coef, precision, self._stream()), "cd_e2e_forward")
         return (logits, feat) if return_features else logits
 
     def e2e_forward_stream(self, audio: torch.Tensor, hop: int, precision: int = PRECISION_BF16,
@@ -351,3 +384,23 @@ def get_tables():
     dct = torch.empty(64, 13)
     lib.cd_get_tables(hann.data_ptr(), fb.data_ptr(), dct.data_ptr())
     return hann, fb, dct
+
+
+def host_alloc(n_elems: int, dtype=torch.float32, write_combined: bool = False) -> torch.Tensor:
+    """A page-locked (optionally write-combined) host tensor from cd_host_alloc, freed when the tensor dies."""
+    import numpy as np
+    lib = load_library()
+    itemsize = torch.empty(0, dtype=dtype).element_size()
+    p = _VP()
+    rc = lib.cd_host_alloc(C.byref(p), n_elems * itemsize, 1 if write_combined else 0)
+    if rc != 0:
+        raise CoughB200Error(f"cd_host_alloc failed ({rc}): {lib.cd_last_error(None).decode()}")
+    buf = (C.c_char * (n_elems * itemsize)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=np.uint8)
+    t = torch.from_numpy(arr).view(dtype)
+
+    class _Owner:
+        def __del__(self, lib=lib, p=p):
+            lib.cd_host_free(p)
+    t._cd_owner = _Owner()
+    return t

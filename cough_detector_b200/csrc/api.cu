@@ -58,6 +58,9 @@ int ensure_tc_ws(cd_handle* h, int nf = kFeat);
 int launch_features_i16(cd_handle* h, const int16_t* d_audio, int64_t stride, int mode, float coef, int64_t B,
                         float* d_feat, __nv_bfloat16* d_map, cudaStream_t s);
 void free_resample_tables(cd_handle* h);
+int launch_condition_var(cd_handle* h, const void* d_in, bool i16, const int64_t* d_in_off, const int32_t* d_chans,
+                         const int32_t* d_n_in, const int64_t* d_out_off, int64_t B, int64_t max_n_in, int orig_sr, int new_sr,
+                         float* d_out, cudaStream_t s);
 int64_t resample_length(int64_t n_in, int orig_sr, int new_sr);
 int launch_resample(cd_handle* h, const float* d_in, int64_t rows, int64_t n_in, int orig_sr, int new_sr, float* d_out,
                     cudaStream_t s);
@@ -262,6 +265,30 @@ int cd_resample(cd_handle* h, const float* d_in, int64_t rows, int64_t n_in, int
     return launch_resample(h, d_in, rows, n_in, orig_sr, new_sr, d_out, (cudaStream_t)stream);
 }
 
+int cd_condition_var(cd_handle* h, const void* d_in, int sample_type, const int64_t* d_in_offsets, const int32_t* d_channels,
+                     const int32_t* d_n_in, const int64_t* d_out_offsets, int64_t B, int64_t max_n_in, int orig_sr, int new_sr,
+                     float* d_out, void* stream) {
+    if (!h) return CD_E_ARG;
+    if (B < 0 || max_n_in < 0 || orig_sr <= 0 || new_sr <= 0 || (sample_type != 0 && sample_type != 1) ||
+        (B > 0 && (!d_in || !d_in_offsets || !d_channels || !d_n_in || !d_out_offsets || !d_out)))
+        return set_err(h, CD_E_ARG, "cd_condition_var: bad argument");
+    DeviceGuard g(h->device);
+    return launch_condition_var(h, d_in, sample_type == 1, d_in_offsets, d_channels, d_n_in, d_out_offsets, B, max_n_in, orig_sr,
+                                new_sr, d_out, (cudaStream_t)stream);
+}
+
+int cd_host_alloc(void** out, size_t bytes, int flags) {
+    if (!out || (flags != CD_HOST_PINNED && flags != CD_HOST_WRITE_COMBINED)) return CD_E_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes, flags == CD_HOST_WRITE_COMBINED ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+    return e == cudaSuccess ? CD_OK : set_err(nullptr, CD_E_NOMEM, "cudaHostAlloc", e);
+}
+
+int cd_host_free(void* p) {
+    if (!p) return CD_OK;
+    return cudaFreeHost(p) == cudaSuccess ? CD_OK : CD_E_CUDA;
+}
+
 // ---- model -----------------------------------------------------------------------------------
 
 // w' = w * g / sqrt(v + eps), b' = (b - mu) * g / sqrt(v + eps) + beta   (eval-mode BatchNorm2d, eps 1e-5)
@@ -363,8 +390,10 @@ int cd_predict(cd_handle* h, const float* d_logits, int64_t B, float threshold, 
 
 // Features for the CNN live in a second, separately grown buffer so the CNN workspace can be
 // re-used chunk by chunk.  `mode`: FeatMode bits of this call (entry kind + options).
-static int e2e_impl(cd_handle* h, const float* d_audio, int64_t stride_or_hop, int mode, float coef, int64_t B,
+static int e2e_impl(cd_handle* h, const void* d_audio_v, bool i16, int64_t stride_or_hop, int mode, float coef, int64_t B,
                     float* d_logits, float* d_feat_opt, int precision, cudaStream_t s) {
+    const float* d_audio = static_cast<const float*>(d_audio_v);
+    const int16_t* d_audio16 = static_cast<const int16_t*>(d_audio_v);
     if (!h->weights_loaded) return set_err(h, CD_E_STATE, "cd_e2e_forward: call cd_cnn_load first");
     if (B == 0) return CD_OK;
     const int nf = (mode & kModeDeltaDelta) ? kFeatDD : kFeat;              // shape family of this call's features
@@ -384,8 +413,10 @@ static int e2e_impl(cd_handle* h, const float* d_audio, int64_t stride_or_hop, i
         const int64_t n = (B - b0) < slab ? (B - b0) : slab;
         float* feat = d_feat_opt ? d_feat_opt + b0 * felems
                                  : (tcp ? nullptr : reinterpret_cast<float*>(reinterpret_cast<char*>(h->d_ws) + cnn_ws));
-        rc = launch_features(h, d_audio + b0 * stride_or_hop, nullptr, nullptr, stride_or_hop, mode, coef, n, feat,
-                             tcp ? cnn_tc_map_ptr(h) : nullptr, s);
+        rc = i16 ? launch_features_i16(h, d_audio16 + b0 * stride_or_hop, stride_or_hop, mode, coef, n, feat,
+                                       tcp ? cnn_tc_map_ptr(h) : nullptr, s)
+                 : launch_features(h, d_audio + b0 * stride_or_hop, nullptr, nullptr, stride_or_hop, mode, coef, n, feat,
+                                   tcp ? cnn_tc_map_ptr(h) : nullptr, s);
         if (rc != CD_OK) return rc;
         rc = tcp ? launch_cnn_tc(h, nullptr, n, d_logits + b0 * CD_N_CLASSES, s, nf)
                  : launch_cnn_fp32(h, feat, n, d_logits + b0 * CD_N_CLASSES, s, nf);
@@ -403,7 +434,20 @@ int cd_e2e_forward(cd_handle* h, const float* d_audio, int64_t stride, int64_t B
         return set_err(h, CD_E_ARG, "precision must be CD_PRECISION_FP32 or CD_PRECISION_BF16");
     if (!feat_flags_ok(h, flags, pre_emphasis_coef, "cd_e2e_forward")) return CD_E_ARG;
     DeviceGuard g(h->device);
-    return e2e_impl(h, d_audio, stride, kModeFixed | feat_mode_bits(flags), pre_emphasis_coef, B, d_logits, d_feat_opt,
+    return e2e_impl(h, d_audio, false, stride, kModeFixed | feat_mode_bits(flags), pre_emphasis_coef, B, d_logits, d_feat_opt,
+                    precision, (cudaStream_t)stream);
+}
+
+int cd_e2e_forward_i16(cd_handle* h, const int16_t* d_audio, int64_t stride, int64_t B, float* d_logits, float* d_feat_opt,
+                       int flags, float pre_emphasis_coef, int precision, void* stream) {
+    if (!h) return CD_E_ARG;
+    if (B < 0 || stride < kSeg || (stride & 7) || (B > 0 && (!d_audio || !d_logits)))
+        return set_err(h, CD_E_ARG, "cd_e2e_forward_i16: bad argument (need stride >= 16000 and a multiple of 8)");
+    if (precision != CD_PRECISION_FP32 && precision != CD_PRECISION_BF16)
+        return set_err(h, CD_E_ARG, "precision must be CD_PRECISION_FP32 or CD_PRECISION_BF16");
+    if (!feat_flags_ok(h, flags, pre_emphasis_coef, "cd_e2e_forward_i16")) return CD_E_ARG;
+    DeviceGuard g(h->device);
+    return e2e_impl(h, d_audio, true, stride, kModeFixed | feat_mode_bits(flags), pre_emphasis_coef, B, d_logits, d_feat_opt,
                     precision, (cudaStream_t)stream);
 }
 
@@ -416,7 +460,7 @@ int cd_e2e_forward_stream(cd_handle* h, const float* d_audio, int64_t n_samples,
         return set_err(h, CD_E_ARG, "precision must be CD_PRECISION_FP32 or CD_PRECISION_BF16");
     if (!feat_flags_ok(h, flags, pre_emphasis_coef, "cd_e2e_forward_stream")) return CD_E_ARG;
     DeviceGuard g(h->device);
-    return e2e_impl(h, d_audio, hop, kModeStream | feat_mode_bits(flags | CD_FEAT_NORMALIZE), pre_emphasis_coef, n_windows,
+    return e2e_impl(h, d_audio, false, hop, kModeStream | feat_mode_bits(flags | CD_FEAT_NORMALIZE), pre_emphasis_coef, n_windows,
                     d_logits, nullptr, precision, (cudaStream_t)stream);
 }
 

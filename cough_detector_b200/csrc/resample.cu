@@ -21,6 +21,7 @@ void free_resample_tables(cd_handle* h) {
 }
 
 static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
+int64_t resample_length(int64_t n_in, int orig_sr, int new_sr);
 
 static int get_table(cd_handle* h, int orig_sr, int new_sr, ResampleTable* out) {
     const int g = gcd_i(orig_sr, new_sr), orig = orig_sr / g, neu = new_sr / g;
@@ -89,6 +90,75 @@ resample_kernel(const float* __restrict__ x, int64_t n_in, int64_t n_out, int or
         acc = fmaf(__ldg(tp + s), v, acc);
     }
     y[row * n_out + i] = acc;
+}
+
+// Batched conditioning of variable-length clips, one launch: clip b = `chans[b]` rows of `n_in[b]` samples at
+// in + in_off[b] (row-major [C][n]); every row is resampled like resample_kernel, the rows are averaged (to_mono,
+// src/preprocessing.py:185-197: waveform.mean(dim=0) AFTER the resampling, :508-510) and the mono clip goes to
+// out + out_off[b].  orig == neu: plain (convert +) channel mean.  T = float or int16 PCM.
+template <class T>
+__global__ void __launch_bounds__(256)
+condition_var_kernel(const T* __restrict__ in, const int64_t* __restrict__ in_off, const int32_t* __restrict__ chans,
+                     const int32_t* __restrict__ n_in, const int64_t* __restrict__ out_off, int orig, int neu, int width,
+                     int support, const int* __restrict__ k0, const float* __restrict__ taps, float* __restrict__ out) {
+    const int64_t b = blockIdx.y;
+    const int64_t n = n_in[b];
+    const int64_t n_out = (neu * n + orig - 1) / orig;
+    const int C = chans[b];
+    const T* x = in + in_off[b];
+    float* y = out + out_off[b];
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_out; i += (int64_t)gridDim.x * 256) {
+        float sum = 0.f;
+        if (orig == neu) {
+            for (int c = 0; c < C; ++c) sum += (float)x[c * n + i];
+        } else {
+            const int64_t f = i / neu;
+            const int j = (int)(i - f * neu);
+            const float* tp = taps + (size_t)j * support;
+            const int64_t base = f * orig + k0[j] - width;
+            for (int c = 0; c < C; ++c) {
+                const T* xr = x + c * n;
+                float acc = 0.f;
+                for (int s = 0; s < support; ++s) {
+                    const int64_t k = base + s;
+                    const float v = (k >= 0 && k < n) ? (float)xr[k] : 0.f;
+                    acc = fmaf(__ldg(tp + s), v, acc);
+                }
+                sum += acc;
+            }
+        }
+        y[i] = C == 1 ? sum : sum / (float)C;
+    }
+}
+
+int launch_condition_var(cd_handle* h, const void* d_in, bool i16, const int64_t* d_in_off, const int32_t* d_chans,
+                         const int32_t* d_n_in, const int64_t* d_out_off, int64_t B, int64_t max_n_in, int orig_sr, int new_sr,
+                         float* d_out, cudaStream_t s) {
+    if (B == 0) return CD_OK;
+    ResampleTable t{1, 1, 0, 0, nullptr, nullptr};
+    if (orig_sr != new_sr) {
+        int rc = get_table(h, orig_sr, new_sr, &t);
+        if (rc != CD_OK) return rc;
+    }
+    const int64_t max_out = resample_length(max_n_in, orig_sr, new_sr);
+    int64_t gx = (max_out + 255) / 256;
+    if (gx < 1) gx = 1;
+    if (gx > 4096) gx = 4096;
+    for (int64_t b0 = 0; b0 < B; b0 += 65535) {                       // gridDim.y limit
+        const int64_t nb = B - b0 < 65535 ? B - b0 : 65535;
+        dim3 grid((unsigned)gx, (unsigned)nb);
+        if (i16)
+            condition_var_kernel<int16_t><<<grid, 256, 0, s>>>(static_cast<const int16_t*>(d_in), d_in_off + b0, d_chans + b0,
+                                                               d_n_in + b0, d_out_off + b0, t.orig, t.neu, t.width, t.support,
+                                                               t.d_k0, t.d_taps, d_out);
+        else
+            condition_var_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(d_in), d_in_off + b0, d_chans + b0,
+                                                             d_n_in + b0, d_out_off + b0, t.orig, t.neu, t.width, t.support,
+                                                             t.d_k0, t.d_taps, d_out);
+        h->launches += 1;
+    }
+    CD_CUDA(h, cudaGetLastError());
+    return CD_OK;
 }
 
 int64_t resample_length(int64_t n_in, int orig_sr, int new_sr) {

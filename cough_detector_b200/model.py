@@ -97,7 +97,14 @@ class CoughDetectorResidual(nn.Module):
             raise RuntimeError("cough_detector_b200 is inference-only: call model.eval() before forward_audio()")
         h = self._handle(audio)
         opts = preprocessor.feat_options if preprocessor is not None else _lib.TRAINING_CONFIG
-        xd = audio.detach().to(device=f"cuda:{h.device}", dtype=torch.float32, non_blocking=True)
+        if audio.dtype not in (torch.float32, torch.int16):
+            audio = audio.to(torch.float32)
+        if not audio.is_cuda and not return_features:
+            # host audio (float32 or int16 PCM): the library's pipelined host path -- chunked copies overlapped with the
+            # kernels, int16 at half the PCIe bytes -- instead of one blocking upload
+            out = h.e2e_forward_host(audio.detach(), _PREC[self.precision], opts=opts)
+            return out.clone()
+        xd = audio.detach().to(device=f"cuda:{h.device}", non_blocking=True)
         out = h.e2e_forward(xd, _PREC[self.precision], return_features, opts=opts)
         if audio.is_cuda:
             return out

@@ -137,10 +137,14 @@ class AudioPreprocessor:
         return self.extract_features(waveform)[:, self.n_mels: self.n_mels + self.n_mfcc]
 
     def extract_features_batch(self, waveforms: torch.Tensor, normalize: bool = True) -> torch.Tensor:
-        """(B, 16000) -> (B, 1, 90, 101); ``normalize`` applies per-clip peak normalisation first."""
+        """(B, 16000) -> (B, 1, 90, 101); ``normalize`` applies per-clip peak normalisation first.  int16 PCM tensors
+        are taken as they are (half the bytes to the GPU; with ``normalize`` the result equals the float path bit for bit)."""
         if waveforms.dim() != 2 or waveforms.shape[1] != self.segment_samples:
             raise ValueError(f"expected (B, {self.segment_samples}), got {tuple(waveforms.shape)}")
         h = self._gpu()
+        if waveforms.dtype == torch.int16:
+            x = waveforms.to(device=f"cuda:{h.device}", non_blocking=True)
+            return self._back(h.feat_forward_i16(x, normalize=normalize, opts=self.feat_options), waveforms)
         x = waveforms.to(device=f"cuda:{h.device}", dtype=torch.float32, non_blocking=True)
         return self._back(h.feat_forward(x, normalize=normalize, opts=self.feat_options), waveforms)
 
@@ -149,23 +153,42 @@ class AudioPreprocessor:
         return self.process_batch([waveform], orig_sr)[0]
 
     def process_batch(self, waveforms: Sequence[torch.Tensor], orig_sr: int = 16000) -> torch.Tensor:
-        """Variable-length clips [(C_i, n_i) or (n_i,)] -> (B, 1, 90, 101); per clip identical to ``process``."""
+        """Variable-length clips [(C_i, n_i) or (n_i,)], float or int16 PCM, all at ``orig_sr`` -> (B, 1, 90, 101); per clip
+        identical to ``process`` (the per-file pipeline of dataset.__getitem__, src/dataset.py:151-163).
+        Batched end to end: ONE packed host buffer and host->device copy for all clips, ONE resample + to_mono launch
+        over (offset, channels, length) descriptors when any clip needs it, ONE feature launch."""
         if not len(waveforms):
             return torch.zeros(0, 1, self.get_num_features(), _lib.N_FRAMES)
+        if int(orig_sr) != orig_sr or orig_sr <= 0:
+            raise ValueError("sample rates must be positive integers")
         h = self._gpu()
-        dev = f"cuda:{h.device}"
-        mono = []
-        for w in waveforms:
-            w = self.resample(w, orig_sr)
-            w = w.reshape(1, -1) if w.dim() == 1 else self.to_mono(w)
-            mono.append(w.reshape(-1).to(torch.float32))
-        lens = torch.tensor([m.numel() for m in mono], dtype=torch.int64)
-        pad = (-lens) % 4                                    # keep every clip 16-byte aligned for the bulk copy
-        offs = torch.cumsum(torch.cat([torch.zeros(1, dtype=torch.int64), (lens + pad)[:-1]]), 0)
-        flat = torch.zeros(int((lens + pad).sum()) + 4, dtype=torch.float32, device=dev)
-        for m, o in zip(mono, offs.tolist()):
-            flat[o:o + m.numel()] = m.to(dev, non_blocking=True)
-        out = h.feat_forward_var(flat, offs, lens.to(torch.int32), opts=self.feat_options)
+        dev = torch.device(f"cuda:{h.device}")
+        i16 = all(w.dtype == torch.int16 for w in waveforms)
+        dtype = torch.int16 if i16 else torch.float32
+        rows = [w.reshape(1, -1) if w.dim() == 1 else w for w in waveforms]
+        chans = [int(r.shape[0]) for r in rows]
+        n_in = [int(r.shape[1]) for r in rows]
+        # every clip starts 16-byte aligned in the packed buffer
+        pad = 8 if i16 else 4
+        sizes = [((c * n + pad - 1) // pad) * pad for c, n in zip(chans, n_in)]
+        offs = [0]
+        for sz in sizes[:-1]:
+            offs.append(offs[-1] + sz)
+        total = offs[-1] + sizes[-1] + pad
+        if all(r.is_cuda for r in rows):
+            packed = torch.zeros(total, dtype=dtype, device=dev)
+            for r, o in zip(rows, offs):
+                packed[o:o + r.numel()] = r.reshape(-1).to(dtype)
+        else:
+            host = torch.zeros(total, dtype=dtype).pin_memory()
+            for r, o in zip(rows, offs):
+                host[o:o + r.numel()] = r.reshape(-1).to(device="cpu", dtype=dtype)
+            packed = host.to(dev, non_blocking=True)
+        if orig_sr != self.sample_rate or i16 or any(c != 1 for c in chans):
+            flat, out_off, out_len = h.condition_var(packed, offs, chans, n_in, int(orig_sr), self.sample_rate)
+        else:
+            flat, out_off, out_len = packed, torch.tensor(offs, dtype=torch.int64), torch.tensor(n_in, dtype=torch.int32)
+        out = h.feat_forward_var(flat, out_off, out_len, opts=self.feat_options)
         return self._back(out, waveforms[0])
 
     def process_file(self, path: str) -> torch.Tensor:

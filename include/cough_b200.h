@@ -152,6 +152,18 @@ int64_t cd_resample_length(int64_t n_in, int orig_sr, int new_sr);
 int cd_resample(cd_handle* h, const float* d_in, int64_t rows, int64_t n_in, int orig_sr, int new_sr,
                 float* d_out, void* stream);
 
+/* Batched resample() + to_mono() of B variable-length clips packed in ONE device buffer, one launch (the host side of
+ * AudioPreprocessor.process for a list of files, src/preprocessing.py:506-510, src/dataset.py:151-152): clip i is
+ * d_channels[i] rows of d_n_in[i] samples (row-major [C][n]) starting at element d_in_offsets[i] of d_in, all at
+ * orig_sr; every row is resampled to new_sr like cd_resample, the rows are averaged, and the mono clip is written to
+ * d_out + d_out_offsets[i] (cd_resample_length(d_n_in[i]) samples).  sample_type: 0 = fp32, 1 = int16 PCM (converted
+ * on the fly; the scale cancels in the peak normalisation that follows).  orig_sr == new_sr is allowed (mono mix /
+ * conversion only).  max_n_in >= every d_n_in[i] sizes the launch.  The descriptor arrays are device arrays.  The output
+ * feeds cd_feat_forward_var directly. */
+int cd_condition_var(cd_handle* h, const void* d_in, int sample_type, const int64_t* d_in_offsets,
+                     const int32_t* d_channels, const int32_t* d_n_in, const int64_t* d_out_offsets, int64_t B,
+                     int64_t max_n_in, int orig_sr, int new_sr, float* d_out, void* stream);
+
 /* ---- model: CoughDetectorResidual ------------------------------------------------------ */
 
 /* Fold BatchNorm (eval mode, eps 1e-5) into the convolutions, repack for the kernels and upload.
@@ -186,6 +198,11 @@ int cd_e2e_forward(cd_handle* h, const float* d_audio, int64_t stride, int64_t B
                    float* d_logits, float* d_feat_opt, int flags, float pre_emphasis_coef,
                    int precision, void* stream);
 
+/* cd_e2e_forward for int16 PCM clips on the device (stride in samples, a multiple of 8). */
+int cd_e2e_forward_i16(cd_handle* h, const int16_t* d_audio, int64_t stride, int64_t B,
+                       float* d_logits, float* d_feat_opt, int flags, float pre_emphasis_coef,
+                       int precision, void* stream);
+
 /* Same, over sliding windows of one stream (window j = d_audio[j*hop ..)); d_logits is
  * n_windows x 2. */
 int cd_e2e_forward_stream(cd_handle* h, const float* d_audio, int64_t n_samples, int64_t hop,
@@ -202,6 +219,15 @@ int cd_e2e_forward_host(cd_handle* h, const float* h_audio, int64_t B, float* h_
 /* cd_e2e_forward_host for int16 PCM host buffers (B x 16000 int16): half the host->device bytes. */
 int cd_e2e_forward_host_i16(cd_handle* h, const int16_t* h_audio, int64_t B, float* h_logits,
                             int flags, float pre_emphasis_coef, int precision);
+
+/* Page-locked host memory for the host-buffer calls above (callers without their own allocator).  flags:
+ * CD_HOST_PINNED (cudaHostAllocDefault) or CD_HOST_WRITE_COMBINED (cudaHostAllocWriteCombined: faster for the device to
+ * read on some hosts, slow for the CPU to read back -- use it for audio going in, never for logits coming out).
+ * tools/h2d_matrix.py measures both on the box at hand. */
+#define CD_HOST_PINNED         0
+#define CD_HOST_WRITE_COMBINED 1
+int cd_host_alloc(void** out, size_t bytes, int flags);
+int cd_host_free(void* p);
 
 /* Diagnostic: D[i][n] = sum_k A[i + shift][k] * B[n][k] (i < 128) on one tcgen05 tile through the same
  * shared-memory / instruction descriptors the convolution kernels use (operands rounded to bf16, fp32

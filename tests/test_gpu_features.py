@@ -342,3 +342,40 @@ def test_peak_far_from_one_is_rescaled_exactly():
     for i in range(4):
         if not _ill(x[i].cpu()):
             assert (h.feat_forward(tiny[i:i + 1].cuda())[0, 0].cpu() - ex.process(tiny[i].reshape(1, -1))[0]).abs().max().item() <= TOL
+
+
+def test_process_batch_is_one_packed_upload_one_resample_launch():
+    """dataset.__getitem__'s per-file pipeline (resample -> mono -> normalize -> pad/trim -> features, src/dataset.py:151-163)
+    for a LIST of files in three launches: clips of different lengths and channel counts at 44.1 kHz, float and int16 PCM,
+    against the oracle pipeline per clip; and the launch count does not grow with the number of clips."""
+    pp = AudioPreprocessor(**FLAGS)
+    h = _lib.get_handle(0)
+    ex = co.Explicit32()
+    g = torch.Generator().manual_seed(77)
+    clips = []
+    for i in range(24):
+        n = int(torch.randint(9000, 90000, (1,), generator=g))
+        c = 1 + i % 3
+        w = torch.stack([synth._burst(g, n) if (i + k) % 2 else synth._sines(g, n) for k in range(c)])
+        clips.append(w if i % 5 else w[0])                               # some 1-D
+    l0 = h.launches
+    got = pp.process_batch(clips, 44100)
+    assert h.launches - l0 == 2                                          # condition (resample + mono) + features
+    assert got.shape == (24, 1, 90, 101)
+    for i, w in enumerate(clips):
+        w2 = w.reshape(1, -1) if w.dim() == 1 else w
+        ref = ex.process(co.resample(w2, 44100))
+        assert (got[i] - ref).abs().max().item() <= TOL, i
+    # same-rate mono float clips skip the conditioning launch
+    l0 = h.launches
+    mono = [c.reshape(-1)[:20000] if c.dim() == 1 else c[0, :20000] for c in clips[:6]]
+    a = pp.process_batch(mono, 16000)
+    assert h.launches - l0 == 1
+    # int16 PCM clips: converted on the device, same features as the float clips x / 32768 (the scale cancels)
+    pcm = [(c / c.abs().max() * 30000.0).round().to(torch.int16) for c in clips]
+    b16 = pp.process_batch(pcm, 44100)
+    bf = pp.process_batch([p.float() / 32768.0 for p in pcm], 44100)
+    assert (b16 - bf).abs().max().item() <= 2e-5
+    assert torch.equal(pp.extract_features_batch(pcm[0].reshape(-1)[:16000].reshape(1, -1)),
+                       pp.extract_features_batch(pcm[0].reshape(-1)[:16000].reshape(1, -1).float() / 32768.0))
+    assert pp.process_batch([], 44100).shape == (0, 1, 90, 101)

@@ -394,3 +394,23 @@ def test_calls_on_different_streams_share_the_workspace_safely():
         torch.cuda.synchronize()
         assert torch.equal(la, want_a) and torch.equal(lb, want_b) and torch.equal(lc, want_b)
         assert torch.equal(lh.cuda(), want_a)
+
+
+def test_int16_and_host_audio_through_forward_audio():
+    """forward_audio: CPU audio takes the library's pipelined host path, int16 PCM (CPU or CUDA) stays int16 on the wire;
+    all of them give the float device path's logits bit for bit (the 1 / 32768 scale cancels in the peak normalisation).
+    Write-combined host memory from cd_host_alloc works as a source."""
+    _, sd1, _ = gio.load_model()
+    m = _model(sd1, "bf16")
+    x = torch.stack(synth.synth_clips(3000, seed=4, fixed_length=True))
+    pcm = (x / x.abs().amax(dim=1, keepdim=True).clamp(min=1e-9) * 30000.0).round().to(torch.int16)
+    xf = pcm.float() / 32768.0
+    want = m.forward_audio(xf.cuda())
+    assert torch.equal(m.forward_audio(pcm.cuda()), want)
+    assert torch.equal(m.forward_audio(pcm).cuda(), want) and m.forward_audio(pcm).device.type == "cpu"
+    assert torch.equal(m.forward_audio(xf).cuda(), want)
+    wc = _lib.host_alloc(xf.numel(), torch.float32, write_combined=True).view_as(xf)
+    wc.copy_(xf)
+    assert torch.equal(_lib.get_handle(0).e2e_forward_host(wc, 1).cuda(), want)
+    lg, ft = m.forward_audio(xf[:64], return_features=True)
+    assert lg.device.type == "cpu" and ft.shape == (64, 1, 90, 101) and torch.equal(lg.cuda(), want[:64])
