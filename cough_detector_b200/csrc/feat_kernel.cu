@@ -49,7 +49,7 @@ namespace cd {
 #endif
 // CD_PF: where the next pair's 10 new samples are requested.  0: after the mel contraction;  1: before it;  2: before the FFT.
 #ifndef CD_PF
-#define CD_PF 0
+#define CD_PF 2
 #endif
 constexpr int kFeatWarps   = CD_FEAT_WARPS;
 constexpr int kFeatThreads = kFeatWarps * 32;
@@ -194,6 +194,47 @@ __device__ __forceinline__ void fft16(float2 (&x)[16]) {
     r4<false>(x[12], x[13], x[14], x[15]);
 }
 
+// Stage 1 of the 512-point FFT: fft16<true> followed by the twiddles W512^(m r) of lane m, read from the lane's row of
+// the shared-memory table.  The table is stored in the order of the in-place result (entry 4 t0 + t1 = W^(m (t0 + 4 t1))
+// multiplies x[4 t0 + t1] = X[t0 + 4 t1]), and the loads of a group are issued two butterflies ahead of their use.
+__device__ __forceinline__ void lds_tw4(uint32_t addr, float2 (&t)[4]) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t[0].x), "=f"(t[0].y), "=f"(t[1].x), "=f"(t[1].y) : "r"(addr));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t[2].x), "=f"(t[2].y), "=f"(t[3].x), "=f"(t[3].y) : "r"(addr + 16));
+}
+__device__ __forceinline__ void fft16_twiddled(float2 (&x)[16], uint32_t tw_s) {
+    float2 ta[4], tb[4];
+    lds_tw4(tw_s, ta);                          // group 0: r = 0, 4, 8, 12
+    lds_tw4(tw_s + 32, tb);                     // group 1: r = 1, 5, 9, 13
+    r4<false>(x[0], x[4], x[8], x[12]);
+    r4<true>(x[1], x[5], x[9], x[13]);
+    r4<true>(x[2], x[6], x[10], x[14]);
+    r4<true>(x[3], x[7], x[11], x[15]);
+    x[5] = cmulc(x[5], kC1, -kS1);
+    x[9] = w16_2(x[9]);
+    x[13] = cmulc(x[13], kS1, -kC1);
+    x[6] = w16_2(x[6]);
+    x[10] = mul_mi(x[10]);
+    x[14] = w16_6(x[14]);
+    x[7] = cmulc(x[7], kS1, -kC1);
+    x[11] = w16_6(x[11]);
+    x[15] = cmulc(x[15], -kC1, kS1);
+    r4<false>(x[0], x[1], x[2], x[3]);
+    x[1] = cmul(x[1], ta[1]);                   // x[0] = X[0]: W^0 = 1
+    x[2] = cmul(x[2], ta[2]);
+    x[3] = cmul(x[3], ta[3]);
+    lds_tw4(tw_s + 64, ta);                     // group 2
+    r4<false>(x[4], x[5], x[6], x[7]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[4 + i] = cmul(x[4 + i], tb[i]);
+    lds_tw4(tw_s + 96, tb);                     // group 3
+    r4<false>(x[8], x[9], x[10], x[11]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[8 + i] = cmul(x[8 + i], ta[i]);
+    r4<false>(x[12], x[13], x[14], x[15]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[12 + i] = cmul(x[12 + i], tb[i]);
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -231,7 +272,9 @@ __device__ __forceinline__ float2 block_reduce2(float2 v, float* red) {
 
 // AmplitudeToDB('power'): 10 log10(max(x, 1e-10)) (torchaudio functional.py:390) via MUFU.LG2
 __device__ __forceinline__ float power_to_db(float x) {
-    return 3.01029995663981195f * __log2f(fmaxf(x, 1e-10f));      // 10 * log10(2) * log2(x)
+    float lg;                                                      // the argument is >= 1e-10: no denormal handling needed
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(fmaxf(x, 1e-10f)));
+    return 3.01029995663981195f * lg;                              // 10 * log10(2) * log2(x)
 }
 
 // za = Z[k], zb = Z[512 - k] of z = x1 + i x2: {|Z + conj Z'|^2, |Z - conj Z'|^2} = the two frames' power at bin k
@@ -301,16 +344,10 @@ __device__ __forceinline__ void lane_ctx_init(LaneCtx& L, const FeatTables* __re
 // loads between the two (the FFT registers are dead by then).
 __device__ __forceinline__ void fft_pair(float2 (&x)[16], const LaneCtx& L, int lane) {
     // ---- stage 1: DFT16 over a, then twiddles W512^(m r) ---------------------------------------------
-    fft16<true>(x);
 #if CD_TW == 2
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        float2 ta, tb;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ta.x), "=f"(ta.y), "=f"(tb.x), "=f"(tb.y) : "r"(L.tw_s + j * 16));
-        if (j) x[F16(2 * j)] = cmul(x[F16(2 * j)], ta);              // r = 0: W^0 = 1
-        x[F16(2 * j + 1)] = cmul(x[F16(2 * j + 1)], tb);
-    }
+    fft16_twiddled(x, L.tw_s);
 #else
+    fft16<true>(x);
     {
         const float2 w1 = L.tw[0], w2 = L.tw[1], w3 = L.tw[2], w4 = L.tw[3], w8 = L.tw[4], w12 = L.tw[5];
         x[F16(1)] = cmul(x[F16(1)], w1);
@@ -455,13 +492,14 @@ __device__ __forceinline__ float view_at(const ClipView<T>& v, int i) {
 // T = float (the reference's waveform type) or int16_t (PCM as stored in wav files: the power-of-two scale cancels in
 // the peak normalisation, so both give bit-identical features).  PRE: y[i] = x[i] - coef x[i-1], y[0] = x[0]
 // (apply_pre_emphasis, src/preprocessing.py:213-239; product and difference rounded separately like the tensor ops).
-template <bool PRE, class T>
+// WHOLE: the clip is exactly the 16 000 samples at v.src (no trim / pad mapping).
+template <bool PRE, bool WHOLE, class T>
 __device__ __forceinline__ float sample_reflect(const ClipView<T>& v, int i, float coef) {
     i = i < 0 ? -i : i;
     i = i >= kSeg ? 2 * (kSeg - 1) - i : i;
-    const float x = view_at(v, i);
+    const float x = WHOLE ? (float)v.src[i] : view_at(v, i);
     if (!PRE || i == 0) return x;
-    return __fsub_rn(x, __fmul_rn(coef, view_at(v, i - 1)));
+    return __fsub_rn(x, __fmul_rn(coef, WHOLE ? (float)v.src[i - 1] : view_at(v, i - 1)));
 }
 
 // window weights of lane m: w[a] = 0.5 hann[32 a + m] (0 beyond sample 399), times the lane's sign (lanes m = 3 mod 4
@@ -546,18 +584,40 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float inv2, float* _
     // The CNN stem's operand rides along: the same values rounded to bf16, scattered straight into the clip's
     // blocked map (cd_common.cuh: bmap_offset).  Its padding elements are never written by anyone: the map
     // lives in the tensor-core workspace, which is zeroed once at allocation.
-    for (int i = tid; i < kMels * kFrames; i += kFeatThreads) {
-        const int r = i / kFrames, t = i - r * kFrames;
-        float* cell = S.db + r * kTilePitch + t;
-        const float p = *cell * inv2;
-        if (PCEN) {
-            *cell = p;
-        } else {
-            const float v = fmaxf(power_to_db(p), floor_db);
-            *cell = v;
-            const float x01 = fminf(fmaxf((v + 80.0f) * 0.0125f, 0.f), 1.f);
-            if (out) out[i] = x01;
-            if (mo) mo[bmap_offset(r + 3, t + 3)] = __float2bfloat16_rn(x01);
+    {
+        // thread = (row group, frame pair): the tile is read and written as 8-byte pairs, no index division; even rows
+        // of an 8-byte aligned output take one 8-byte store
+        const int j = tid & 63, g = tid >> 6;
+        const bool al8 = out && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
+        if (j < kPairs) {
+            const bool two = 2 * j + 1 < kFrames;
+            for (int r = g; r < kMels; r += kFeatThreads / 64) {
+                float2* cell = reinterpret_cast<float2*>(S.db + r * kTilePitch + 2 * j);
+                float2 p = *cell;
+                p.x *= inv2;
+                p.y *= inv2;
+                if (PCEN) {
+                    *cell = p;
+                } else {
+                    const float2 v = make_float2(fmaxf(power_to_db(p.x), floor_db), fmaxf(power_to_db(p.y), floor_db));
+                    *cell = v;
+                    const float2 x01 = make_float2(fminf(fmaxf((v.x + 80.0f) * 0.0125f, 0.f), 1.f),
+                                                   fminf(fmaxf((v.y + 80.0f) * 0.0125f, 0.f), 1.f));
+                    if (out) {
+                        float* o = out + r * kFrames + 2 * j;
+                        if (al8 && !(r & 1) && two) {
+                            *reinterpret_cast<float2*>(o) = x01;
+                        } else {
+                            o[0] = x01.x;
+                            if (two) o[1] = x01.y;
+                        }
+                    }
+                    if (mo) {
+                        mo[bmap_offset(r + 3, 2 * j + 3)] = __float2bfloat16_rn(x01.x);
+                        if (two) mo[bmap_offset(r + 3, 2 * j + 4)] = __float2bfloat16_rn(x01.y);
+                    }
+                }
+            }
         }
     }
     __syncthreads();
@@ -577,14 +637,15 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float inv2, float* _
     const float mean = tot.x * (1.0f / kN);
     const float var = fmaxf(tot.y - tot.x * mean, 0.f) * (1.0f / (kN - 1));
     const float inv_std = 1.0f / (sqrtf(var) + 1e-8f);
-    {
-        for (int i = tid; i < kN; i += kFeatThreads) {
-            const int cidx = i / kFrames, t = i - cidx * kFrames;
+    for (int t = tid; t < kFrames; t += kFeatThreads) {               // thread = frame, all 13 coefficients
+        const int tp = min(t + 1, kFrames - 1), tm = max(t - 1, 0);
+#pragma unroll 1
+        for (int cidx = 0; cidx < kMfcc; ++cidx) {
             const float* row = mf + cidx * kTilePitch;
             // __fmul_rn: never contracted into an FMA, so the bf16 map below sees identical values
             const float x0 = __fmul_rn(row[t] - mean, inv_std);
-            const float xp = __fmul_rn(row[min(t + 1, kFrames - 1)] - mean, inv_std);
-            const float xm = __fmul_rn(row[max(t - 1, 0)] - mean, inv_std);
+            const float xp = __fmul_rn(row[tp] - mean, inv_std);
+            const float xm = __fmul_rn(row[tm] - mean, inv_std);
             const float dl = (xp - xm) * 0.5f;                             // compute_deltas (:353-355)
             float d2 = 0.f;
             if (dd) {
@@ -666,6 +727,23 @@ __device__ __forceinline__ ClipView<T> clip_view(const T* audio, const int64_t* 
     return v;
 }
 
+// The next pair's ten new samples (raw[8..17]); the loads are only ISSUED here.  Without pre-emphasis nothing
+// consumes them until that pair starts (the peak tracking of these values happens there too, see feat_kernel): a
+// consumer right behind the loads would stall the warp for the whole memory latency.
+template <bool PRE, class T>
+__device__ __forceinline__ void request_next_impl(const T* __restrict__ ps, float (&raw)[18], float& amax, float coef) {
+#pragma unroll
+    for (int q = 8; q < 18; ++q) {
+        const float xq = (float)ps[32 * q];
+        if (PRE) {
+            amax = fmaxf(amax, fabsf(xq));
+            raw[q] = __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1]));
+        } else {
+            raw[q] = xq;
+        }
+    }
+}
+
 // Frame pairs of a clip are dealt to the warps as CONTIGUOUS runs (8 warps: 6, 6, 7, 7, 7, 6, 6, 6) so that consecutive
 // pairs of a warp share samples in registers; the longer runs go to middle warps (the first and last warp hold the
 // slower reflect-padded pairs 0, 49, 50).
@@ -679,7 +757,8 @@ __device__ __forceinline__ void warp_pair_range(int warp, int& p0, int& p1) {
 // one-time per CTA: the per-lane twiddles that live in shared memory (CD_TW = 1)
 template <class SM>
 __device__ __forceinline__ void stage_tables(SM& S, const FeatTables* __restrict__ tables, int tid) {
-    for (int i = tid; i < 32 * 16; i += kFeatThreads) S.twl[i >> 4][i & 15] = tables->twl[i >> 4][i & 15];
+    // entry 4 t0 + t1 of a lane's row = W^(m (t0 + 4 t1)): the order fft16_twiddled consumes them in
+    for (int i = tid; i < 32 * 16; i += kFeatThreads) S.twl[i >> 4][i & 15] = tables->twl[i >> 4][((i & 15) >> 2) + 4 * (i & 3)];
 }
 
 // PRE / PCEN: the use_pre_emphasis / use_pcen variants of the 90-feature path (the part that keeps
@@ -700,6 +779,8 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
     __syncthreads();
     int wp0, wp1;
     warp_pair_range(warp, wp0, wp1);
+    float w[13];                                                       // the lane's window weights, loaded once
+    lane_window(tables, 1.0f, lane, w);
     const bool var = (mode & kModeMask) == kModeVar;
     const bool normalize = !(mode & kModeNoNormalize);
 
@@ -726,8 +807,7 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
 
         float pre = 1.0f, top, peak;
         for (int pass = 0;; ++pass) {
-            float w[13];
-            lane_window(tables, pre, lane, w);
+            if (pass) lane_window(tables, pre, lane, w);               // (rare) pre-scaled second pass
             float pmax = 0.f, amax = peak_pre;
             float raw[18];
             bool have = false;                                         // raw[] already holds this pair's samples
@@ -738,8 +818,13 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
                 if (edge || !fast) {
                     // reflect-padded pairs and clips that are trimmed / padded: every sample through the index mapping
                     const bool second = (2 * p + 1) < kFrames;
+                    if (fast) {
 #pragma unroll
-                    for (int q = 0; q < 18; ++q) raw[q] = sample_reflect<PRE>(v, s0 + 32 * q, coef);
+                        for (int q = 0; q < 18; ++q) raw[q] = sample_reflect<PRE, true>(v, s0 + 32 * q, coef);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 18; ++q) raw[q] = sample_reflect<PRE, false>(v, s0 + 32 * q, coef);
+                    }
                     if (fast) {                                        // reflected samples are samples: they count for the peak
 #pragma unroll
                         for (int q = 0; q < 18; ++q) {
@@ -761,43 +846,24 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
                         have = true;
                     }
 #if CD_PF == 2
-                    if (have) {
-                        const T* ps = v.src + s0 + 2 * kHop;
-#pragma unroll
-                        for (int q = 8; q < 18; ++q) {
-                            const float xq = (float)ps[32 * q];
-                            amax = fmaxf(amax, fabsf(xq));
-                            raw[q] = PRE ? __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1])) : xq;
-                        }
-                    }
+                    if (have) request_next_impl<PRE>(v.src + s0 + 2 * kHop, raw, amax, coef);
 #endif
                     fft_pair(x, L, lane);
 #if CD_PF == 1
-                    if (have) {
-                        const T* ps = v.src + s0 + 2 * kHop;
-#pragma unroll
-                        for (int q = 8; q < 18; ++q) {
-                            const float xq = (float)ps[32 * q];
-                            amax = fmaxf(amax, fabsf(xq));
-                            raw[q] = PRE ? __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1])) : xq;
-                        }
-                    }
+                    if (have) request_next_impl<PRE>(v.src + s0 + 2 * kHop, raw, amax, coef);
 #endif
                     mel_pair(L, lane, lo, hi);
 #if CD_PF == 0
-                    if (have) {
-                        const T* ps = v.src + s0 + 2 * kHop;
-#pragma unroll
-                        for (int q = 8; q < 18; ++q) {
-                            const float xq = (float)ps[32 * q];
-                            amax = fmaxf(amax, fabsf(xq));
-                            raw[q] = PRE ? __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1])) : xq;
-                        }
-                    }
+                    if (have) request_next_impl<PRE>(v.src + s0 + 2 * kHop, raw, amax, coef);
 #endif
                     pmax = fmaxf(pmax, store_pair(S.db, lane, p, second, lo, hi));
                 } else {
-                    if (!have) {                                       // first pair of the warp's run
+                    if (have) {                                        // requested during the previous pair: they arrive about now
+                        if (!PRE) {
+#pragma unroll
+                            for (int q = 8; q < 18; ++q) amax = fmaxf(amax, fabsf(raw[q]));
+                        }
+                    } else {                                           // first pair of the warp's run
                         const T* ps = v.src + s0;
 #pragma unroll
                         for (int q = 0; q < 18; ++q) {
@@ -815,39 +881,15 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
                         for (int q = 0; q < 8; ++q) raw[q] = raw[q + 10];
                     }
 #if CD_PF == 2
-                    if (have) {
-                        const T* ps = v.src + s0 + 2 * kHop;
-#pragma unroll
-                        for (int q = 8; q < 18; ++q) {
-                            const float xq = (float)ps[32 * q];
-                            amax = fmaxf(amax, fabsf(xq));
-                            raw[q] = PRE ? __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1])) : xq;
-                        }
-                    }
+                    if (have) request_next_impl<PRE>(v.src + s0 + 2 * kHop, raw, amax, coef);
 #endif
                     fft_pair(x, L, lane);
 #if CD_PF == 1
-                    if (have) {
-                        const T* ps = v.src + s0 + 2 * kHop;
-#pragma unroll
-                        for (int q = 8; q < 18; ++q) {
-                            const float xq = (float)ps[32 * q];
-                            amax = fmaxf(amax, fabsf(xq));
-                            raw[q] = PRE ? __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1])) : xq;
-                        }
-                    }
+                    if (have) request_next_impl<PRE>(v.src + s0 + 2 * kHop, raw, amax, coef);
 #endif
                     mel_pair(L, lane, lo, hi);
 #if CD_PF == 0
-                    if (have) {
-                        const T* ps = v.src + s0 + 2 * kHop;
-#pragma unroll
-                        for (int q = 8; q < 18; ++q) {
-                            const float xq = (float)ps[32 * q];
-                            amax = fmaxf(amax, fabsf(xq));
-                            raw[q] = PRE ? __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1])) : xq;
-                        }
-                    }
+                    if (have) request_next_impl<PRE>(v.src + s0 + 2 * kHop, raw, amax, coef);
 #endif
                     pmax = fmaxf(pmax, store_pair(S.db, lane, p, true, lo, hi));
                 }
@@ -863,6 +905,7 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
             }
             break;
         }
+        if (pre != 1.0f) lane_window(tables, 1.0f, lane, w);           // back to the plain window for the next clip
         float inv2 = 1.0f;
         if (normalize && peak > 0.f) {
             const float inv = 1.0f / (peak * pre);
@@ -970,7 +1013,7 @@ stream_window_kernel(const float* __restrict__ audio, int64_t hop, int64_t n_win
             const int s0 = 2 * kHop * p - kWin / 2 + lane;
             float raw[18];
 #pragma unroll
-            for (int q = 0; q < 18; ++q) raw[q] = sample_reflect<PRE>(v, s0 + 32 * q, coef);
+            for (int q = 0; q < 18; ++q) raw[q] = sample_reflect<PRE, true>(v, s0 + 32 * q, coef);
             float2 x[16], lo, hi;
             form_inputs<true>(raw, w, second, x);
             fft_pair(x, L, lane);
