@@ -64,6 +64,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(s32(dst)), "l"(src), "r"(bytes), "r"(s32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Programmatic dependent launch: the network's kernels are launched with programmatic stream serialization, so a
+// kernel's prologue (barrier init, TMEM allocation, the resident WEIGHTS going to shared memory) overlaps the tail of the
+// kernel before it.  pdl_launch_dependents: the next kernel may start being scheduled; pdl_wait: everything the
+// previous kernels wrote is complete and visible (must precede the first read of an activation).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(dst_smem)), "r"(ncols) : "memory");
@@ -371,7 +377,8 @@ struct S1Args {
     const __nv_bfloat16* wskip;    // packed skip chunk [C rows x 128 B]
     const float* bias;             // [C] conv2 bias + skip bias
     __nv_bfloat16* y_bf16;         // [n * H * W][C] bf16 (OUT_F32 == false)
-    float* y_f32;                  // [n * H * W][C] fp32
+    float* y_f32;                  // [n * H * W][C] fp32 (single-CTA kernel, OUT_F32)
+    float* psum;                   // pair kernel: [n][H][128] fp32, sums of the block output over the W pixels of an image row
     __nv_bfloat16* xs_out;         // WRITE_XS: next block's skip plane (PS layout of the (H+1)/2 x (W+1)/2 grid)
     int64_t y_plane_elems;         // WRITE_XS: y_bf16 is written phase-split (Ps2Layout<H, W>, 4 planes this far apart)
     int64_t ps_plane_elems;
@@ -419,6 +426,7 @@ conv3x3_s1_tc_kernel(const S1Args a) {
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    tc::pdl_launch_dependents();
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp == 0) {
@@ -428,6 +436,7 @@ conv3x3_s1_tc_kernel(const S1Args a) {
             for (int q = 0; q < 9 * S::NPL; ++q)      // rows [64 half, 64 half + 64) of every packed chunk
                 tc::bulk_g2s(s_w + q * 8192, a.w + (size_t)q * C * 64 + (size_t)half * 64 * 64, 8192, &w_bar);
             tc::bulk_g2s(s_w + 9 * S::NPL * 8192, a.wskip + (size_t)half * 64 * 64, 8192, &w_bar);
+            tc::pdl_wait();                            // weights are in flight; the activations need the previous kernel
             int it = 0;
             for (int tile = cta; tile < n_tiles; tile += n_cta, ++it) {
                 const int s = it % S::STAGES;
@@ -610,6 +619,7 @@ conv3x3_s1_pair_tc_kernel(const S1Args a) {
     __syncthreads();
     tc::cluster_sync();
     tc::tc_fence_after();
+    tc::pdl_launch_dependents();
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp == 0) {
@@ -619,6 +629,7 @@ conv3x3_s1_pair_tc_kernel(const S1Args a) {
             for (int q = 0; q < 18; ++q)
                 tc::bulk_g2s(s_w + q * 8192, a.w + (size_t)q * C * 64 + (size_t)rank * 64 * 64, 8192, &w_bar);
             tc::bulk_g2s(s_w + 18 * 8192, a.wskip + (size_t)rank * 64 * 64, 8192, &w_bar);
+            tc::pdl_wait();
             int it = 0;
             for (int tp = pair; tp < n_tp; tp += n_pairs, ++it) {
                 const int64_t tile = 2 * (int64_t)tp + rank;
@@ -689,10 +700,18 @@ conv3x3_s1_pair_tc_kernel(const S1Args a) {
             const int clip = (int)(mp / PS::RPC), rem = (int)(mp - (int64_t)clip * PS::RPC);
             const int y = rem / PS::WP, x = rem - y * PS::WP;
             const bool live = clip < a.n && y < H && x < W;
-            const int64_t m = (int64_t)clip * NPOS + y * W + x;
             tc::mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
             tc::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * 128;
+            // The global average pool starts here: the eight lanes of a group hold the eight grid columns of ONE image
+            // row (clip rows are multiples of 8 GEMM rows, tiles multiples of 128), so a 3-step transpose-reduce over
+            // the group leaves every lane with the row sums of 4 of the 32 channels -- a fixed tree over the pixel
+            // positions, independent of where the clip sits in the batch.  Only [n][H][128] row sums leave the SM
+            // (3 KB per clip instead of the 21.5 KB fp32 activation); head_kernel adds the H rows and applies fc.
+            const bool up4 = lane & 4, up2 = lane & 2, up1 = lane & 1;
+            const int cbase = (up4 ? 16 : 0) + (up2 ? 8 : 0) + (up1 ? 4 : 0);
+            float* prow = a.psum + ((int64_t)clip * H + y) * C + cbase;
+            const bool row_live = clip < a.n && y < H;
 #pragma unroll 1
             for (int c0 = 0; c0 < 128; c0 += 32) {
                 float v[32];
@@ -701,13 +720,19 @@ conv3x3_s1_pair_tc_kernel(const S1Args a) {
                     tc::tc_fence_before();
                     tc::mbar_arrive_leader(&tempty_bar[acc]);
                 }
-                if (live) {
-                    float4* op = reinterpret_cast<float4*>(a.y_f32 + m * C + c0);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        op[q] = make_float4(fmaxf(v[4 * q] + s_bias[c0 + 4 * q], 0.f), fmaxf(v[4 * q + 1] + s_bias[c0 + 4 * q + 1], 0.f),
-                                            fmaxf(v[4 * q + 2] + s_bias[c0 + 4 * q + 2], 0.f), fmaxf(v[4 * q + 3] + s_bias[c0 + 4 * q + 3], 0.f));
-                }
+                for (int i = 0; i < 32; ++i) v[i] = live ? fmaxf(v[i] + s_bias[c0 + i], 0.f) : 0.f;
+                float r16[16], r8[8], r4[4];
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    r16[i] = (up4 ? v[i + 16] : v[i]) + __shfl_xor_sync(0xffffffffu, up4 ? v[i] : v[i + 16], 4);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    r8[i] = (up2 ? r16[i + 8] : r16[i]) + __shfl_xor_sync(0xffffffffu, up2 ? r16[i] : r16[i + 8], 2);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    r4[i] = (up1 ? r8[i + 4] : r8[i]) + __shfl_xor_sync(0xffffffffu, up1 ? r8[i] : r8[i + 4], 1);
+                if (row_live) *reinterpret_cast<float4*>(prow + c0) = make_float4(r4[0], r4[1], r4[2], r4[3]);
             }
         }
     }
@@ -785,6 +810,7 @@ conv3x3_s2_tc_kernel(const S2Args a) {
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    tc::pdl_launch_dependents();
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp == 0) {
@@ -793,6 +819,7 @@ conv3x3_s2_tc_kernel(const S2Args a) {
             tc::mbar_arrive_expect_tx(&w_bar, S::W_BYTES);
             for (int q = 0; q < S::NCH; ++q)
                 tc::bulk_g2s(s_w + (size_t)q * COUT * 128, a.w + (size_t)q * COUT * 64, COUT * 128, &w_bar);
+            tc::pdl_wait();
             int it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 const int s = it % S::STAGES;
@@ -952,6 +979,7 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    tc::pdl_launch_dependents();
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp == 0) {
@@ -959,6 +987,7 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
         if (lane == 0) {
             tc::mbar_arrive_expect_tx(&w_bar, kStemBBytes);
             tc::bulk_g2s(sB, wq, kStemBBytes, &w_bar);
+            tc::pdl_wait();
             int it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 const int s = it % kStemStages;
@@ -1077,30 +1106,39 @@ map_from_feat_kernel(const float* __restrict__ feat, __nv_bfloat16* __restrict__
     dst[1 ^ sw] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
-// AdaptiveAvgPool2d(1) + Flatten + Linear(128 -> 2); x2 is [B][NPOS][128] fp32 (NPOS = 42 | 49); fixed summation order
-template <int NPOS>
-__global__ void __launch_bounds__(128)
-head_kernel(const float* __restrict__ x2, const float* __restrict__ fcw, const float* __restrict__ fcb,
+// AdaptiveAvgPool2d(1) + Flatten + Linear(128 -> 2) from the block-1 kernel's image-row sums psum [B][H][128] fp32
+// (NPOS = H * W pixels per clip); fixed summation order, two clips per 256-thread CTA
+template <int H, int NPOS>
+__global__ void __launch_bounds__(256)
+head_kernel(const float* __restrict__ psum, const float* __restrict__ fcw, const float* __restrict__ fcb,
             float* __restrict__ logits, int B) {
-    __shared__ float part[2][4];
-    const int b = blockIdx.x, c = threadIdx.x;
-    const float* p = x2 + (int64_t)b * NPOS * 128 + c;
-    float s = 0.f;
-#pragma unroll 7
-    for (int i = 0; i < NPOS; ++i) s += p[i * 128];
-    s *= (1.0f / (float)NPOS);
-    float a0 = s * fcw[c], a1 = s * fcw[128 + c];
+    __shared__ float part[2][2][4];
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
+    const int half = threadIdx.x >> 7, c = threadIdx.x & 127;
+    const int b = blockIdx.x * 2 + half;
+    float a0 = 0.f, a1 = 0.f;
+    if (b < B) {
+        const float* p = psum + (int64_t)b * H * 128 + c;
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < H; ++i) s += p[i * 128];
+        s *= (1.0f / (float)NPOS);
+        a0 = s * fcw[c];
+        a1 = s * fcw[128 + c];
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         a0 += __shfl_xor_sync(0xffffffffu, a0, o);
         a1 += __shfl_xor_sync(0xffffffffu, a1, o);
     }
     if ((c & 31) == 0) {
-        part[0][c >> 5] = a0;
-        part[1][c >> 5] = a1;
+        part[half][0][c >> 5] = a0;
+        part[half][1][c >> 5] = a1;
     }
     __syncthreads();
-    if (c < 2) logits[(int64_t)b * 2 + c] = ((part[c][0] + part[c][1]) + (part[c][2] + part[c][3])) + fcb[c];
+    if (c < 2 && b < B)
+        logits[(int64_t)b * 2 + c] = ((part[half][c][0] + part[half][c][1]) + (part[half][c][2] + part[half][c][3])) + fcb[c];
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1188,7 +1226,7 @@ int upload_cnn_tc(cd_handle* h, const std::vector<std::vector<float>>& wf, const
 // Tensor-core workspace: fixed layout for kTcChunk clips of one shape family, allocated once per handle for the larger
 // family and zeroed whenever the family changes (the PS buffers rely on their pad rows staying zero, and the two
 // families put their pads in different places).
-// [maps | x0 | h1 PS: conv plane + skip plane | x1 | h2 PS: 2 conv planes + skip plane | x2]
+// [maps | x0 | h1 PS: conv plane + skip plane | x1 | h2 PS: 2 conv planes + skip plane | row sums of x2]
 constexpr int64_t kTcChunk = 16384;
 constexpr int64_t al256(int64_t x) { return (x + 255) & ~int64_t(255); }
 template <int NF>
@@ -1209,7 +1247,7 @@ struct TcPlan {
     static constexpr int64_t kOffX1 = kOffH1 + al256(2 * kPs0Rows * 128);
     static constexpr int64_t kOffH2 = kOffX1 + al256(4 * kP21Rows * 128);
     static constexpr int64_t kOffX2 = kOffH2 + al256(3 * kPs1Rows * 128);
-    static constexpr int64_t kBytes = kOffX2 + al256(kTcChunk * NPOS * 128 * 4);
+    static constexpr int64_t kBytes = kOffX2 + al256(kTcChunk * N::H2 * 128 * 4);      // image-row sums of the block-1 output
 };
 constexpr int64_t kTcWsBytes = TcPlan<kFeatDD>::kBytes > TcPlan<kFeat>::kBytes ? TcPlan<kFeatDD>::kBytes : TcPlan<kFeat>::kBytes;
 
@@ -1250,6 +1288,23 @@ static int init_cnn_tc_nf(cd_handle* h) {
     return CD_OK;
 }
 
+// Launch with programmatic stream serialization (see tc::pdl_wait): the kernel may be scheduled while its predecessor
+// in the stream drains; its own griddepcontrol.wait orders the data.
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // d_feat != nullptr: features come in as fp32 and are converted chunk by chunk; d_feat == nullptr:
 // the maps of the (single, <= kTcChunk clips) chunk are already in the workspace.
 template <int NF>
@@ -1275,8 +1330,9 @@ static int launch_cnn_tc_nf(cd_handle* h, const float* d_feat, int64_t B, float*
         }
         {
             const int tiles = (int)(((int64_t)n * N::BROWS + 127) / 128);
-            stem_tc_kernel<NF><<<tiles < h->sm_count ? tiles : h->sm_count, kS1Threads, kStemSmem, s>>>(
-                maps, W.stem_w, W.stem_b, x0, P::kP20Rows * 64, h1 + kPl0, n);
+            CD_CUDA(h, launch_pdl(stem_tc_kernel<NF>, dim3(tiles < h->sm_count ? tiles : h->sm_count), dim3(kS1Threads), kStemSmem, s,
+                                  (const __nv_bfloat16*)maps, (const __nv_bfloat16*)W.stem_w, (const float*)W.stem_b, x0,
+                                  (int64_t)(P::kP20Rows * 64), h1 + kPl0, n));
         }
         h->launches += 1;
         {
@@ -1284,7 +1340,8 @@ static int launch_cnn_tc_nf(cd_handle* h, const float* d_feat, int64_t B, float*
             S2Args q{};
             q.x = x0; q.w = W.b0c1; q.bias = W.b0c1_b; q.y = h1; q.in_plane_elems = P::kP20Rows * 64; q.out_plane_elems = kPl0; q.n = n;
             const int tiles = (int)(((int64_t)n * P::P20::RPC + 127) / 128);
-            conv3x3_s2_tc_kernel<32, 64, N::H0, N::W0><<<tiles < h->sm_count ? tiles : h->sm_count, kS1Threads, S::SMEM, s>>>(q);
+            CD_CUDA(h, launch_pdl(conv3x3_s2_tc_kernel<32, 64, N::H0, N::W0>, dim3(tiles < h->sm_count ? tiles : h->sm_count),
+                                  dim3(kS1Threads), S::SMEM, s, q));
             h->launches += 1;
         }
         {
@@ -1294,7 +1351,7 @@ static int launch_cnn_tc_nf(cd_handle* h, const float* d_feat, int64_t B, float*
             q.y_plane_elems = P::kP21Rows * 64; q.ps_plane_elems = kPl0; q.n = n;
             const int tiles = (int)(((int64_t)n * P::Ps0::RPC + 127) / 128);
             const int grid = (tiles < h->sm_count ? tiles : h->sm_count) * S::HALVES;
-            conv3x3_s1_tc_kernel<64, N::H1, N::W1, false, true><<<grid, kS1Threads, S::SMEM, s>>>(q);
+            CD_CUDA(h, launch_pdl(conv3x3_s1_tc_kernel<64, N::H1, N::W1, false, true>, dim3(grid), dim3(kS1Threads), S::SMEM, s, q));
             h->launches += 1;
         }
         {
@@ -1302,19 +1359,22 @@ static int launch_cnn_tc_nf(cd_handle* h, const float* d_feat, int64_t B, float*
             S2Args q{};
             q.x = x1; q.w = W.b1c1; q.bias = W.b1c1_b; q.y = h2; q.in_plane_elems = P::kP21Rows * 64; q.out_plane_elems = kPl1; q.n = n;
             const int tiles = (int)(((int64_t)n * P::P21::RPC + 127) / 128);
-            conv3x3_s2_tc_kernel<64, 128, N::H1, N::W1><<<tiles < h->sm_count ? tiles : h->sm_count, kS1Threads, S::SMEM, s>>>(q);
+            CD_CUDA(h, launch_pdl(conv3x3_s2_tc_kernel<64, 128, N::H1, N::W1>, dim3(tiles < h->sm_count ? tiles : h->sm_count),
+                                  dim3(kS1Threads), S::SMEM, s, q));
             h->launches += 1;
         }
         {
             using S = S1PairShape<N::H2, N::W2>;
             S1Args q{};
-            q.x = h2; q.w = W.b1c2; q.wskip = W.b1sk; q.bias = W.b1c2_b; q.y_f32 = x2; q.ps_plane_elems = kPl1; q.n = n;
+            q.x = h2; q.w = W.b1c2; q.wskip = W.b1sk; q.bias = W.b1c2_b; q.psum = x2; q.ps_plane_elems = kPl1; q.n = n;
             const int tiles = (int)(((int64_t)n * P::Ps1::RPC + 127) / 128);
             const int tp = (tiles + 1) / 2, max_pairs = h->sm_count / 2;
-            conv3x3_s1_pair_tc_kernel<N::H2, N::W2><<<2 * (tp < max_pairs ? tp : max_pairs), kS1Threads, S::SMEM, s>>>(q);
+            CD_CUDA(h, launch_pdl(conv3x3_s1_pair_tc_kernel<N::H2, N::W2>, dim3(2 * (tp < max_pairs ? tp : max_pairs)),
+                                  dim3(kS1Threads), S::SMEM, s, q));
             h->launches += 1;
         }
-        head_kernel<P::NPOS><<<n, 128, 0, s>>>(x2, W.fc_w, W.fc_b, d_logits + c0 * CD_N_CLASSES, n);
+        CD_CUDA(h, launch_pdl(head_kernel<N::H2, P::NPOS>, dim3((n + 1) / 2), dim3(256), 0, s, (const float*)x2, (const float*)W.fc_w,
+                              (const float*)W.fc_b, d_logits + c0 * CD_N_CLASSES, n));
         h->launches += 1;
         CD_CUDA(h, cudaGetLastError());
     }
