@@ -6,8 +6,9 @@ anything loads ``lib/libcough_b200.so`` and fails loudly if it (or a B200) is mi
 __version__ = "0.1.0"
 
 from .preprocessing import AudioPreprocessor, RealtimePreprocessor, create_preprocessor  # noqa: F401
-from .model import CoughDetectorResidual, ResidualBlock, create_model, count_parameters  # noqa: F401
+from .model import (CoughDetector, CoughDetectorResidual, CoughDetectorSmall, ConvBlock, ResidualBlock, create_model,  # noqa: F401
+                    count_parameters)
 from .inference import CoughDetectorInference, smooth_and_debounce  # noqa: F401
 
 __all__ = ["AudioPreprocessor", "RealtimePreprocessor", "create_preprocessor", "CoughDetectorResidual",
-           "ResidualBlock", "create_model", "count_parameters", "CoughDetectorInference", "smooth_and_debounce"]
+           "ResidualBlock", "CoughDetector", "CoughDetectorSmall", "ConvBlock", "create_model", "count_parameters", "CoughDetectorInference", "smooth_and_debounce"]

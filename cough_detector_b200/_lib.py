@@ -60,6 +60,26 @@ class _ResidualWeights(C.Structure):
         + [("fc_weight", _f32p), ("fc_bias", _f32p)]
 
 
+class _Conv(C.Structure):
+    _fields_ = [("weight", _f32p), ("bias", _f32p)]
+
+
+class _Bn(C.Structure):
+    _fields_ = [(n, _f32p) for n in ("weight", "bias", "running_mean", "running_var")]
+
+
+class _DwPwBlock(C.Structure):
+    _fields_ = [("dw", _Conv), ("pw", _Conv), ("bn", _Bn)]
+
+
+class _SmallWeights(C.Structure):
+    _fields_ = [("conv1", _Conv), ("bn1", _Bn), ("block", _DwPwBlock * 3)] + [(n, _f32p) for n in ("fc1_weight", "fc1_bias", "fc2_weight", "fc2_bias")]
+
+
+class _StandardWeights(C.Structure):
+    _fields_ = [("conv", _Conv * 4), ("bn", _Bn * 4)] + [(n, _f32p) for n in ("fc1_weight", "fc1_bias", "fc2_weight", "fc2_bias")]
+
+
 # every symbol include/cough_b200.h declares: name -> (restype, argtypes)
 _VP, _I64, _I, _F = C.c_void_p, C.c_int64, C.c_int, C.c_float
 SYMBOLS = {
@@ -81,6 +101,10 @@ SYMBOLS = {
     "cd_cnn_load": (_I, [_VP, C.POINTER(_ResidualWeights)]),
     "cd_cnn_forward": (_I, [_VP, _VP, _I64, _VP, _I, _VP]),
     "cd_cnn_forward_rows": (_I, [_VP, _VP, _I, _I64, _VP, _I, _VP]),
+    "cd_small_load": (_I, [_VP, C.POINTER(_SmallWeights)]),
+    "cd_small_forward": (_I, [_VP, _VP, _I, _I64, _VP, _VP]),
+    "cd_standard_load": (_I, [_VP, C.POINTER(_StandardWeights)]),
+    "cd_standard_forward": (_I, [_VP, _VP, _I, _I64, _VP, _VP]),
     "cd_predict": (_I, [_VP, _VP, _I64, C.c_float, _VP, _VP, _VP, _VP]),
     "cd_e2e_forward": (_I, [_VP, _VP, _I64, _I64, _VP, _VP, _I, _F, _I, _VP]),
     "cd_e2e_forward_i16": (_I, [_VP, _VP, _I64, _I64, _VP, _VP, _I, _F, _I, _VP]),
@@ -276,6 +300,47 @@ class Handle:
                 raise CoughB200Error(f"{k}: expected shape {shp}, got {tuple(keep[k].shape)}")
         self._check(self.lib.cd_cnn_load(self._h, C.byref(w)), "cd_cnn_load")
         self._weights_key = key
+
+    def load_plain_state_dict(self, kind: str, sd: Dict[str, torch.Tensor], key=None):
+        """Upload a reference-format CoughDetectorSmall ('small') or CoughDetector ('standard') state_dict."""
+        keep = []
+
+        def f(name):
+            t = sd[name].detach().to("cpu", torch.float32).contiguous()
+            keep.append(t)
+            return C.cast(t.data_ptr(), _f32p)
+
+        def conv(p):
+            return _Conv(f(p + ".weight"), f(p + ".bias"))
+
+        def bn(p):
+            return _Bn(f(p + ".weight"), f(p + ".bias"), f(p + ".running_mean"), f(p + ".running_var"))
+
+        if kind == "small":
+            blocks = (_DwPwBlock * 3)(*[_DwPwBlock(conv(f"features.{a}"), conv(f"features.{a + 1}"), bn(f"features.{a + 2}")) for a in (4, 9, 14)])
+            w = _SmallWeights(conv("features.0"), bn("features.1"), blocks, f("classifier.1.weight"), f("classifier.1.bias"),
+                              f("classifier.4.weight"), f("classifier.4.bias"))
+            self._check(self.lib.cd_small_load(self._h, C.byref(w)), "cd_small_load")
+        elif kind == "standard":
+            w = _StandardWeights((_Conv * 4)(*[conv(f"conv_layers.{i}.conv") for i in range(4)]),
+                                 (_Bn * 4)(*[bn(f"conv_layers.{i}.bn") for i in range(4)]),
+                                 f("fc.0.weight"), f("fc.0.bias"), f("fc.3.weight"), f("fc.3.bias"))
+            self._check(self.lib.cd_standard_load(self._h, C.byref(w)), "cd_standard_load")
+        else:
+            raise CoughB200Error(f"unknown plain model kind {kind!r}")
+        self._plain_keys = dict(getattr(self, "_plain_keys", {}), **{kind: key})
+
+    def plain_forward(self, kind: str, feat: torch.Tensor) -> torch.Tensor:
+        feat = self._dev_f32(feat, "features")
+        if feat.dim() == 3:
+            feat = feat.unsqueeze(0)
+        if feat.dim() != 4 or feat.shape[1] != 1 or feat.shape[3] != N_FRAMES:
+            raise CoughB200Error(f"features must be (B, 1, rows, {N_FRAMES}), got {tuple(feat.shape)}")
+        B, rows = feat.shape[0], int(feat.shape[2])
+        logits = torch.empty(B, 2, device=feat.device, dtype=torch.float32)
+        fn = self.lib.cd_small_forward if kind == "small" else self.lib.cd_standard_forward
+        self._check(fn(self._h, _ptr(feat), rows, B, _ptr(logits), self._stream()), f"cd_{kind}_forward")
+        return logits
 
     def cnn_forward(self, feat: torch.Tensor, precision: int = PRECISION_BF16) -> torch.Tensor:
         feat = self._dev_f32(feat, "features")

@@ -58,6 +58,11 @@ int ensure_tc_ws(cd_handle* h, int nf = kFeat);
 int launch_features_i16(cd_handle* h, const int16_t* d_audio, int64_t stride, int mode, float coef, int64_t B,
                         float* d_feat, __nv_bfloat16* d_map, cudaStream_t s);
 void free_resample_tables(cd_handle* h);
+void free_plain(cd_handle* h);
+int init_cnn_plain(cd_handle* h);
+int load_small(cd_handle* h, const cd_small_weights* w);
+int load_standard(cd_handle* h, const cd_standard_weights* w);
+int launch_plain(cd_handle* h, int slot, const float* d_feat, int n_rows, int64_t B, float* d_logits, cudaStream_t s);
 int launch_condition_var(cd_handle* h, const void* d_in, bool i16, const int64_t* d_in_off, const int32_t* d_chans,
                          const int32_t* d_n_in, const int64_t* d_out_off, int64_t B, int64_t max_n_in, int orig_sr, int new_sr,
                          float* d_out, cudaStream_t s);
@@ -150,6 +155,7 @@ int cd_create(int device, cd_handle** out) {
         rc = set_err(h, CD_E_CUDA, "cudaEventCreate");
     if (rc == CD_OK) rc = init_cnn_fp32(h);
     if (rc == CD_OK) rc = init_cnn_tc(h);
+    if (rc == CD_OK) rc = init_cnn_plain(h);
     if (rc != CD_OK) {
         g_create_err = h->err;
         cd_destroy(h);
@@ -177,6 +183,7 @@ int cd_destroy(cd_handle* h) {
     }
     cudaFree(h->dev_logits);
     free_resample_tables(h);
+    free_plain(h);
     if (h->ws_event) cudaEventDestroy(h->ws_event);
     delete h;
     return CD_OK;
@@ -371,6 +378,36 @@ int cd_cnn_forward_rows(cd_handle* h, const float* d_feat, int n_rows, int64_t B
     if (B < 0 || (B > 0 && (!d_feat || !d_logits))) return set_err(h, CD_E_ARG, "cd_cnn_forward_rows: bad argument");
     DeviceGuard g(h->device);
     return cnn_forward_impl(h, d_feat, n_rows, B, d_logits, precision, (cudaStream_t)stream);
+}
+
+static int plain_forward(cd_handle* h, int slot, const float* d_feat, int n_rows, int64_t B, float* d_logits, void* stream) {
+    if (!h) return CD_E_ARG;
+    if (B < 0 || n_rows < 8 || n_rows > 4096 || (B > 0 && (!d_feat || !d_logits)))
+        return set_err(h, CD_E_ARG, "cd_small_forward / cd_standard_forward: bad argument (need n_rows >= 8)");
+    DeviceGuard g(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = ws_acquire(h, s);
+    if (rc == CD_OK) rc = launch_plain(h, slot, d_feat, n_rows, B, d_logits, s);
+    return rc == CD_OK ? ws_release(h, s) : rc;
+}
+
+int cd_small_load(cd_handle* h, const cd_small_weights* w) {
+    if (!h) return CD_E_ARG;
+    if (!w) return set_err(h, CD_E_ARG, "cd_small_load: NULL weights");
+    DeviceGuard g(h->device);
+    return load_small(h, w);
+}
+int cd_small_forward(cd_handle* h, const float* d_feat, int n_rows, int64_t B, float* d_logits, void* stream) {
+    return plain_forward(h, 0, d_feat, n_rows, B, d_logits, stream);
+}
+int cd_standard_load(cd_handle* h, const cd_standard_weights* w) {
+    if (!h) return CD_E_ARG;
+    if (!w) return set_err(h, CD_E_ARG, "cd_standard_load: NULL weights");
+    DeviceGuard g(h->device);
+    return load_standard(h, w);
+}
+int cd_standard_forward(cd_handle* h, const float* d_feat, int n_rows, int64_t B, float* d_logits, void* stream) {
+    return plain_forward(h, 1, d_feat, n_rows, B, d_logits, stream);
 }
 
 int cd_predict(cd_handle* h, const float* d_logits, int64_t B, float threshold, float* d_probs, int64_t* d_preds,

@@ -101,6 +101,8 @@ struct ResampleTable {
 
 }  // namespace cd
 
+namespace cd { struct PlainNet; }
+
 struct cd_handle {
     int device = 0;
     int sm_count = 0;
@@ -115,6 +117,7 @@ struct cd_handle {
     cd::CnnWeightsF32 w32{};
     __nv_bfloat16* d_wblob_bf16 = nullptr;
     cd::TcWeights tcw{};                 // pointers into d_wblob_bf16
+    cd::PlainNet* plain[2] = {nullptr, nullptr};   // folded 'small' / 'standard' networks (cnn_plain.cu)
     unsigned char* d_ws_tc_fam[2] = {nullptr, nullptr};   // tensor-core path activations per shape family (90 | 103 rows):
                                                           // fixed layout, pads zeroed once at allocation
     unsigned char* d_ws_tc = nullptr;    // the family the current call uses (set by ensure_tc_ws)

@@ -117,7 +117,10 @@ class CoughDetectorInference:
         hop = int(16000 * hop_duration)
         h = self.model._handle(torch.empty(0, device=self.device))
         x = audio.reshape(-1).to(device=self.device, dtype=torch.float32)
-        logits = h.e2e_forward_stream(x, hop, _PREC[self.model.precision], opts=self.preprocessor.feat_options)
+        if not hasattr(self.model, "precision"):            # 'small' / 'standard': features, then the fp32 network
+            logits = self.model(h.feat_forward_stream(x, hop, opts=self.preprocessor.feat_options))
+        else:
+            logits = h.e2e_forward_stream(x, hop, _PREC[self.model.precision], opts=self.preprocessor.feat_options)
         _, probs, _ = h.predict(logits)
         return probs[:, 1]
 

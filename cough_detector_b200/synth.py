@@ -127,20 +127,21 @@ def randomized_state_dict(model: torch.nn.Module, seed: int = 1, fc_scale: float
             sd[p + "bias"] = 0.1 * torch.randn(c, generator=g)
             sd[p + "running_mean"] = 0.1 * torch.randn(c, generator=g)
             sd[p + "running_var"] = 0.5 + torch.rand(c, generator=g)
-    sd["fc.2.weight"] = sd["fc.2.weight"] * fc_scale
+    if "fc.2.weight" in sd:                      # CoughDetectorResidual's classifier
+        sd["fc.2.weight"] = sd["fc.2.weight"] * fc_scale
     return sd
 
 
 def spread_fc(sd: Dict[str, torch.Tensor], logits: torch.Tensor, centre: float = 0.8473,
-              spread: float = 1.5) -> Dict[str, torch.Tensor]:
+              spread: float = 1.5, weight_key: str = "fc.2.weight", bias_key: str = "fc.2.bias") -> Dict[str, torch.Tensor]:
     """Rescale / recentre the classifier so P(cough) straddles 0.7 on the clips ``logits`` (computed
     with ``sd``) came from: logit margin d = l1 - l0 is mapped to spread*(d - median)/std + centre
     (centre = logit(0.7)).  Random-init GAP features barely move with the input, so without this
     every clip lands on the same side of the threshold and 'identical decisions' is vacuous."""
     sd = {k: v.clone() for k, v in sd.items()}
-    b = sd["fc.2.bias"]
+    b = sd[bias_key]
     d = (logits[:, 1] - logits[:, 0]) - (b[1] - b[0])
     s = spread / float(d.std().clamp(min=1e-6))
-    sd["fc.2.weight"] = sd["fc.2.weight"] * s
-    sd["fc.2.bias"] = torch.tensor([0.0, centre - s * float(d.median())])
+    sd[weight_key] = sd[weight_key] * s
+    sd[bias_key] = torch.tensor([0.0, centre - s * float(d.median())])
     return sd

@@ -79,6 +79,47 @@ typedef struct cd_residual_weights {
     const float* fc_bias;          /* fc.2.bias   [2]      */
 } cd_residual_weights;
 
+/* A convolution / a BatchNorm as stored in a state_dict (host pointers, fp32, PyTorch layouts), for the two model types
+ * below whose BatchNorm does not directly follow every convolution. */
+typedef struct cd_conv {
+    const float* weight;           /* [cout][cin / groups][k][k] */
+    const float* bias;             /* [cout] */
+} cd_conv;
+typedef struct cd_bn {
+    const float* weight;           /* gamma */
+    const float* bias;             /* beta */
+    const float* running_mean;
+    const float* running_var;
+} cd_bn;
+
+/* CoughDetectorSmall (src/model.py:146-207; model_type 'small', the reference's default): features.0/.1, then three
+ * depthwise-separable blocks features.{4,5,6} / {9,10,11} / {14,15,16} (depthwise 3x3, pointwise 1x1, BatchNorm),
+ * classifier.1 (Linear 128 -> 64) and classifier.4 (Linear 64 -> 2). */
+typedef struct cd_small_weights {
+    cd_conv conv1;                 /* features.0   3x3 p1, 1 -> 16 */
+    cd_bn bn1;                     /* features.1 */
+    struct {
+        cd_conv dw;                /* depthwise 3x3 p1, groups = channels */
+        cd_conv pw;                /* pointwise 1x1 */
+        cd_bn bn;
+    } block[3];                    /* 16 -> 32, 32 -> 64, 64 -> 128 */
+    const float* fc1_weight;       /* classifier.1.weight [64][128] */
+    const float* fc1_bias;
+    const float* fc2_weight;       /* classifier.4.weight [2][64] */
+    const float* fc2_bias;
+} cd_small_weights;
+
+/* CoughDetector (src/model.py:43-143; model_type 'standard'): conv_layers.{0..3}.conv / .bn (3x3 p1, 1 -> 32 -> 64 -> 128
+ * -> 256, each followed by ReLU and MaxPool2d(2)), fc.0 (Linear 256 -> 128), fc.3 (Linear 128 -> 2). */
+typedef struct cd_standard_weights {
+    cd_conv conv[4];
+    cd_bn bn[4];
+    const float* fc1_weight;       /* fc.0.weight [128][256] */
+    const float* fc1_bias;
+    const float* fc2_weight;       /* fc.3.weight [2][128] */
+    const float* fc2_bias;
+} cd_standard_weights;
+
 /* ---- lifetime ------------------------------------------------------------------------- */
 
 /* Create a handle on CUDA device `device`.  Replaces AudioPreprocessor.__init__ (transform /
@@ -182,6 +223,15 @@ int cd_cnn_forward(cd_handle* h, const float* d_feat, int64_t B, float* d_logits
  * heights).  d_feat B x 1 x n_rows x 101 fp32. */
 int cd_cnn_forward_rows(cd_handle* h, const float* d_feat, int n_rows, int64_t B, float* d_logits,
                         int precision, void* stream);
+
+/* The reference's other two model types, fp32 on CUDA cores (off the north-star path; cnn_plain.cu): load = fold the
+ * BatchNorms + upload (create_model('small' | 'standard') + load_state_dict + eval, src/model.py:296-316), forward =
+ * d_feat B x 1 x n_rows x 101 fp32 -> d_logits B x 2 (src/model.py:198-201, 107-128).  Any n_rows >= 8 works (both
+ * networks are fully convolutional up to their global average pool). */
+int cd_small_load(cd_handle* h, const cd_small_weights* w);
+int cd_small_forward(cd_handle* h, const float* d_feat, int n_rows, int64_t B, float* d_logits, void* stream);
+int cd_standard_load(cd_handle* h, const cd_standard_weights* w);
+int cd_standard_forward(cd_handle* h, const float* d_feat, int n_rows, int64_t B, float* d_logits, void* stream);
 
 /* predict() on logits: softmax probabilities (B x 2), argmax class (B, int64) as in
  * src/model.py:261-265, and the batched decision P(cough) >= threshold (B, uint8) that stands in

@@ -326,6 +326,30 @@ def cnn_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
     return F.linear(x, sd["fc.2.weight"], sd["fc.2.bias"])           # Dropout is identity in eval
 
 
+def cnn_forward_small(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+    """CoughDetectorSmall in eval mode, functional form (src/model.py:160-201): conv + BN + ReLU + pool, three
+    depthwise-separable blocks (depthwise 3x3, pointwise 1x1, BN, ReLU, pool / global pool), Linear 128 -> 64 -> 2."""
+    f = "features."
+    x = F.max_pool2d(F.relu(_bn(F.conv2d(x, sd[f + "0.weight"], sd[f + "0.bias"], padding=1), sd, f + "1")), 2)
+    for a, last in ((4, False), (9, False), (14, True)):
+        c = sd[f"{f}{a}.weight"].shape[0]
+        x = F.conv2d(x, sd[f"{f}{a}.weight"], sd[f"{f}{a}.bias"], padding=1, groups=c)
+        x = F.relu(_bn(F.conv2d(x, sd[f"{f}{a + 1}.weight"], sd[f"{f}{a + 1}.bias"]), sd, f"{f}{a + 2}"))
+        x = x.mean(dim=(2, 3)) if last else F.max_pool2d(x, 2)
+    x = F.relu(F.linear(x, sd["classifier.1.weight"], sd["classifier.1.bias"]))
+    return F.linear(x, sd["classifier.4.weight"], sd["classifier.4.bias"])
+
+
+def cnn_forward_standard(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+    """CoughDetector in eval mode, functional form (src/model.py:86-128): four ConvBlocks (:31-40), GAP, fc."""
+    for i in range(4):
+        p = f"conv_layers.{i}."
+        x = F.max_pool2d(F.relu(_bn(F.conv2d(x, sd[p + "conv.weight"], sd[p + "conv.bias"], padding=1), sd, p + "bn")), 2)
+    x = x.mean(dim=(2, 3))
+    x = F.relu(F.linear(x, sd["fc.0.weight"], sd["fc.0.bias"]))
+    return F.linear(x, sd["fc.3.weight"], sd["fc.3.bias"])
+
+
 def fold_bn(w, b, sd, p) -> Tuple[torch.Tensor, torch.Tensor]:
     """w' = w*g/sqrt(v+eps), b' = (b-mu)*g/sqrt(v+eps)+beta."""
     s = sd[p + ".weight"].double() / torch.sqrt(sd[p + ".running_var"].double() + BN_EPS)

@@ -90,9 +90,44 @@ def flag_goldens():
     print("features_flags.npz", os.path.getsize(os.path.join(GOLD, "features_flags.npz")))
 
 
+def other_model_goldens():
+    """tests/golden/models_other.npz: the reference's 'small' (its default model_type) and 'standard' networks with
+    BatchNorm-randomised weights (seeds 11 / 12 on top of torch.manual_seed(0) init), their logits on the golden
+    features (90 rows) and on the 103-row delta-delta features."""
+    sys.path.insert(0, REF)
+    from src.model import create_model
+    torch.set_num_threads(1)
+    z = np.load(os.path.join(GOLD, "features.npz"))
+    zf = np.load(os.path.join(GOLD, "features_flags.npz"))
+    x90 = torch.from_numpy(z["features"]).unsqueeze(1)
+    x103 = torch.cat([torch.from_numpy(z["features"]), torch.from_numpy(zf["ddrows_dd"])], dim=1).unsqueeze(1)
+    out = {"meta": np.array([torch.__version__])}
+    for kind, seed in (("small", 11), ("standard", 12)):
+        torch.manual_seed(0)
+        model = create_model(kind, n_mels=90, num_classes=2, in_channels=1).eval()
+        sd = synth.randomized_state_dict(model, seed=seed, fc_scale=1.0)
+        last = "classifier.4" if kind == "small" else "fc.3"
+        if kind == "standard":      # big tensors are stored as fp16: everything below uses the SAME rounded weights
+            sd = {k: (v.half().float() if v.numel() > 100000 else v) for k, v in sd.items()}
+        model.load_state_dict(sd)
+        with torch.no_grad():       # random-init networks barely react to the input: spread P(cough) around 0.7
+            sd = synth.spread_fc(sd, model(x90), weight_key=last + ".weight", bias_key=last + ".bias")
+        model.load_state_dict(sd)
+        with torch.no_grad():
+            out[f"{kind}/logits90"] = model(x90).numpy()
+            out[f"{kind}/logits103"] = model(x103).numpy()
+        for k, v in sd.items():
+            if not k.endswith("num_batches_tracked"):
+                out[f"{kind}/sd/{k}"] = v.numpy().astype(np.float16 if v.numel() > 100000 else np.float32)
+    np.savez_compressed(os.path.join(GOLD, "models_other.npz"), **out)
+    print("models_other.npz", os.path.getsize(os.path.join(GOLD, "models_other.npz")))
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "flags":
         return flag_goldens()
+    if len(sys.argv) > 1 and sys.argv[1] == "models":
+        return other_model_goldens()
     sys.path.insert(0, REF)
     import torchaudio
     from src.preprocessing import AudioPreprocessor, RealtimePreprocessor  # the reference

@@ -2,4 +2,4 @@
 implementation, so the reference's entry scripts (run_detection.py, train_with_data.py) import it
 unchanged.  Only the hot-path names are provided."""
 from cough_detector_b200 import (AudioPreprocessor, RealtimePreprocessor, create_preprocessor,  # noqa: F401
-                                 CoughDetectorResidual, create_model, count_parameters)
+                                 CoughDetector, CoughDetectorSmall, CoughDetectorResidual, create_model, count_parameters)

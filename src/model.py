@@ -1,1 +1,2 @@
-from cough_detector_b200.model import CoughDetectorResidual, ResidualBlock, create_model, count_parameters  # noqa: F401
+from cough_detector_b200.model import (CoughDetector, CoughDetectorSmall, CoughDetectorResidual, ConvBlock, ResidualBlock,  # noqa: F401
+                                        create_model, count_parameters)

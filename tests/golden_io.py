@@ -65,3 +65,15 @@ def load_delta_delta_logits():
     """Reference logits of the 103-row ("dd") golden features, default-init and randomised weights: {name: (32, 2)}."""
     z = np.load(os.path.join(GOLD, "features_flags.npz"))
     return {k[len("logits_dd_"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("logits_dd_")}
+
+
+def load_other_model(kind: str):
+    """(state_dict, logits on the 90-row golden features, logits on the 103-row ones) of the reference's 'small' / 'standard'
+    network with randomised BatchNorm statistics (oracle/make_golden.py models)."""
+    z = np.load(os.path.join(GOLD, "models_other.npz"))
+    pre = f"{kind}/sd/"
+    sd = {k[len(pre):]: torch.from_numpy(z[k].astype(np.float32)) for k in z.files if k.startswith(pre)}
+    for k in list(sd):
+        if k.endswith("running_mean"):
+            sd[k[: -len("running_mean")] + "num_batches_tracked"] = torch.zeros((), dtype=torch.int64)
+    return sd, torch.from_numpy(z[f"{kind}/logits90"]), torch.from_numpy(z[f"{kind}/logits103"])

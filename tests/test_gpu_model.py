@@ -414,3 +414,50 @@ def test_int16_and_host_audio_through_forward_audio():
     assert torch.equal(_lib.get_handle(0).e2e_forward_host(wc, 1).cuda(), want)
     lg, ft = m.forward_audio(xf[:64], return_features=True)
     assert lg.device.type == "cpu" and ft.shape == (64, 1, 90, 101) and torch.equal(lg.cuda(), want[:64])
+
+
+@pytest.mark.parametrize("kind", ["small", "standard"])
+def test_other_model_types_vs_reference_goldens(kind):
+    """create_model('small' | 'standard') (src/model.py:43-207; 'small' is the reference's default model_type): fp32
+    CUDA-core kernels against logits recorded from the reference, 90- and 103-row inputs, ragged batch sizes."""
+    sd, l90, l103 = gio.load_other_model(kind)
+    _, feats, _ = gio.load_features()
+    x90 = feats.unsqueeze(1)
+    x103 = _dd_features()
+    m = create_model(kind, n_mels=90, num_classes=2, in_channels=1).eval()
+    m.load_state_dict(sd)
+    scale = max(1.0, l90.abs().max().item())
+    for x, want in ((x90, l90), (x103, l103)):
+        got = m(x)
+        assert got.shape == want.shape and got.device.type == "cpu"
+        assert (got - want).abs().max().item() <= TOL_FP32 * scale, (kind, (got - want).abs().max().item(), scale)
+    preds, probs = m.predict(x90)
+    assert preds.dtype == torch.int64 and torch.equal(preds, torch.softmax(l90, dim=1).argmax(dim=1))
+    big = torch.cat([x90] * 40).cuda()                                   # 1280 clips: more than one workspace chunk
+    out = m(big)
+    assert torch.equal(out[:32], out[1248:]) and (out[:32].cpu() - l90).abs().max().item() <= TOL_FP32 * scale
+    for n in (1, 3, 33):
+        assert torch.equal(m(big[:n]), out[:n])
+    assert m(big[:0]).shape == (0, 2)
+
+
+def test_engine_with_the_reference_default_model_type():
+    """A checkpoint written by the reference's stock command line has no model_type in its config, i.e. 'small'
+    (src/inference.py:146, src/train.py:218): it must load and run, chunk loop and whole-recording call."""
+    stream, _ = gio.load_stream()
+    sd, _, _ = gio.load_other_model("small")
+    cfg = dict(use_pcen=False, use_pre_emphasis=False, use_delta_delta=False, use_spectral_contrast=False)
+    feats = co.stream_features(stream, 4000, co.Explicit32())
+    want = torch.softmax(co.cnn_forward_small(sd, feats), dim=1)[:, 1].numpy()
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "best_model.pt")
+        torch.save({"epoch": 0, "model_state_dict": sd, "optimizer_state_dict": {}, "metrics": {}, "config": cfg}, path)
+        eng = CoughDetectorInference(path, device="cuda", confidence_threshold=0.5, smoothing_window=1, debounce_seconds=0.0, verbose=False)
+        assert type(eng.model).__name__ == "CoughDetectorSmall"
+        got = eng.stream_probabilities(stream, 0.25).cpu().numpy()
+        assert got.shape == want.shape and np.abs(got - want).max() <= 2e-4
+        loop = []
+        for c in range(0, stream.numel(), 4000):
+            for f in eng.preprocessor.add_audio(stream[c:c + 4000]):
+                loop.append(eng.predict(f)[1])
+        assert np.abs(np.array(loop) - want).max() <= 2e-4

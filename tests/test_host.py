@@ -96,8 +96,13 @@ def test_model_surface_matches_reference_state_dict():
     m.load_state_dict(sd1)                       # strict
     with pytest.raises(ValueError):
         create_model("nope")
-    with pytest.raises(NotImplementedError):
-        create_model("small")
+    for kind, n_params in (("small", None), ("standard", None)):        # the reference's other model types: same state_dict
+        ref_sd, _, _ = gio.load_other_model(kind)
+        mk = create_model(kind, n_mels=90, num_classes=2, in_channels=1)
+        assert list(mk.state_dict().keys()) == [k for k in mk.state_dict().keys() if k in ref_sd]
+        assert set(mk.state_dict().keys()) == set(ref_sd.keys())
+        assert all(mk.state_dict()[k].shape == ref_sd[k].shape for k in ref_sd)
+        mk.load_state_dict(ref_sd)                                       # strict
     m.train()
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 1, 90, 101))

@@ -152,3 +152,19 @@ def test_delta_delta_oracles_match_reference_goldens():
             if co.ill_conditioned_fraction(co.conditioned_window(clips[i].numpy())) == 0:
                 d = np.abs(co.features_fp64(clips[i].numpy(), pcen, pre, use_delta_delta=True)[90:] - ddrows[name][i].numpy()).max()
                 assert d <= 1e-4, (name, i, d)
+
+
+def test_other_model_types_oracle_matches_reference_goldens():
+    """'small' (the reference's default model_type) and 'standard': the functional restatements against logits recorded
+    from the reference modules, 90- and 103-row inputs."""
+    from tests import golden_io as gio
+    _, feats, _ = gio.load_features()
+    x90 = feats.unsqueeze(1)
+    x103 = torch.cat([feats, gio.load_delta_delta_rows()["dd"]], dim=1).unsqueeze(1)
+    for kind, fn in (("small", co.cnn_forward_small), ("standard", co.cnn_forward_standard)):
+        sd, l90, l103 = gio.load_other_model(kind)
+        scale = max(1.0, l90.abs().max().item())
+        assert (fn(sd, x90) - l90).abs().max().item() <= 2e-5 * scale, kind
+        assert (fn(sd, x103) - l103).abs().max().item() <= 2e-5 * scale, kind
+        p = torch.softmax(l90, dim=1)[:, 1]
+        assert p.min() < 0.65 and p.max() > 0.75, (kind, p.min(), p.max())     # the goldens straddle the 0.7 threshold
