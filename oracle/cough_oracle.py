@@ -304,6 +304,35 @@ def stream_features(x: torch.Tensor, hop: int, ex: Optional[Explicit32] = None) 
     return torch.stack(out) if out else torch.zeros(0, 1, N_FEATURES, N_FRAMES)
 
 
+def spectral_contrast_band_edges(n_freq: int = N_FFT // 2 + 1, n_bands: int = 6) -> list:
+    """The band edges of extract_spectral_contrast (src/preprocessing.py:268-269): logspace(0, log10(n_freq), n_bands + 2)
+    truncated to int -- [1, 2, 4, 10, 23, 52, 116, 256] (10^log10(257) rounds just below 257) for the default 257 bins / 6 bands."""
+    return torch.clamp(torch.logspace(0, float(np.log10(n_freq)), n_bands + 2).int(), 0, n_freq).tolist()
+
+
+def spectral_contrast(w: torch.Tensor, n_bands: int = 6) -> torch.Tensor:
+    """Restatement of extract_spectral_contrast (src/preprocessing.py:242-303) WITHOUT the spectral centroid row -- kept
+    only to pin down why the reference's 110-feature constructor default is not a parity target: the first band
+    [1, 2) holds ONE bin, so top_idx = max(1, int(0.8)) = 1 and sorted_band[:, 1:, :] is EMPTY, its mean is NaN (:287-291),
+    and the block-wide normalisation (:301) spreads that NaN over every row.  Returns (1, n_bands + 1, frames)."""
+    xp = F.pad(w.unsqueeze(0), (N_FFT // 2, N_FFT // 2), mode="reflect").squeeze(0)
+    frames = xp.unfold(-1, N_FFT, HOP_LENGTH).squeeze(0)
+    win = torch.zeros(N_FFT)
+    off = (N_FFT - WIN_LENGTH) // 2
+    win[off:off + WIN_LENGTH] = hann_window()
+    spec = torch.fft.rfft(frames * win, dim=-1)
+    power = (spec.real ** 2 + spec.imag ** 2).t().unsqueeze(0)           # (1, 257, frames)
+    edges = spectral_contrast_band_edges(power.shape[1], n_bands)
+    out = torch.zeros(1, n_bands + 1, power.shape[2])
+    for i in range(n_bands):
+        lo, hi = edges[i], max(edges[i + 1], edges[i] + 1)
+        band, _ = torch.sort(power[:, lo:min(hi, power.shape[1]), :], dim=1)
+        n = band.shape[1]
+        top, bot = max(1, int(n * 0.8)), max(1, int(n * 0.2))
+        out[:, i, :] = torch.log1p(band[:, top:, :].mean(dim=1)) - torch.log1p(band[:, :bot, :].mean(dim=1))
+    return (out - out.mean()) / (out.std() + 1e-8)
+
+
 # --------------------------------------------------------------------------
 # CoughDetectorResidual forward (src/model.py:210-293), functional form
 # --------------------------------------------------------------------------

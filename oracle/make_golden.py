@@ -123,7 +123,30 @@ def other_model_goldens():
     print("models_other.npz", os.path.getsize(os.path.join(GOLD, "models_other.npz")))
 
 
+def contrast_goldens():
+    """tests/golden/contrast_nan.npz: what the UNMODIFIED reference returns with its constructor defaults (110 rows) on
+    golden clips 0..3 -- the NaN pattern that makes use_spectral_contrast a documented non-target."""
+    sys.path.insert(0, REF)
+    from src.preprocessing import AudioPreprocessor
+    torch.set_num_threads(1)
+    z = np.load(os.path.join(GOLD, "features.npz"))
+    pp = AudioPreprocessor()                               # constructor defaults: PCEN, pre-emphasis, delta-delta, contrast
+    assert pp.get_num_features() == 110
+    nan_rows, finite_rows, o = [], [], 0
+    for n, sc in list(zip(z["lens"], z["scales"]))[:4]:
+        x = dequantize_clip(z["mant"][o:o + n], sc)
+        o += int(n)
+        f = pp.process(x.reshape(1, -1), 16000)[0]
+        nan_rows.append(torch.isnan(f).all(dim=1).numpy())
+        finite_rows.append(torch.isfinite(f).all(dim=1).numpy())
+    np.savez_compressed(os.path.join(GOLD, "contrast_nan.npz"), nan_rows=np.stack(nan_rows), finite_rows=np.stack(finite_rows),
+                        meta=np.array([torch.__version__]))
+    print("contrast_nan.npz", np.stack(nan_rows).sum(axis=1))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "contrast":
+        return contrast_goldens()
     if len(sys.argv) > 1 and sys.argv[1] == "flags":
         return flag_goldens()
     if len(sys.argv) > 1 and sys.argv[1] == "models":

@@ -168,3 +168,20 @@ def test_other_model_types_oracle_matches_reference_goldens():
         assert (fn(sd, x103) - l103).abs().max().item() <= 2e-5 * scale, kind
         p = torch.softmax(l90, dim=1)[:, 1]
         assert p.min() < 0.65 and p.max() > 0.75, (kind, p.min(), p.max())     # the goldens straddle the 0.7 threshold
+
+
+def test_reference_spectral_contrast_rows_are_nan():
+    """Why AudioPreprocessor(use_spectral_contrast=True) -- and with it the 110-feature constructor default -- raises here
+    instead of being built: run unmodified, the reference returns NaN in ALL seven spectral-contrast rows for every input
+    (golden recorded from it), because its first band holds a single FFT bin (restated in oracle.spectral_contrast)."""
+    import os
+    import numpy as np
+    from tests import golden_io as gio
+    z = np.load(os.path.join(gio.GOLD, "contrast_nan.npz"))
+    assert z["nan_rows"].shape == (4, 110)
+    assert z["nan_rows"][:, 103:].all() and not z["nan_rows"][:, :103].any()      # rows 103..109 NaN, the rest fine
+    assert z["finite_rows"][:, :103].all()
+    assert co.spectral_contrast_band_edges() == [1, 2, 4, 10, 23, 52, 116, 256]
+    clips, _, _ = gio.load_features()
+    sc = co.spectral_contrast(co.pad_or_trim(co.normalize(clips[0].reshape(1, -1))))
+    assert sc.shape == (1, 7, 101) and torch.isnan(sc).all()
