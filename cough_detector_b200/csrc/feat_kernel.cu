@@ -581,46 +581,75 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float inv2, float* _
     const float floor_db = power_to_db(top * inv2) - 80.0f;           // top_db = 80 (monotone: the max of the dB)
 
     // ---- rows 0..63: P / peak^2 -> dB -> max(dB, floor) -> (dB + 80) / 80 -> clamp ------------------------
-    // The CNN stem's operand rides along: the same values rounded to bf16, scattered straight into the clip's
-    // blocked map (cd_common.cuh: bmap_offset).  Its padding elements are never written by anyone: the map
-    // lives in the tensor-core workspace, which is zeroed once at allocation.
+    // The CNN stem's operand rides along: the same values rounded to bf16 in the clip's blocked map (cd_common.cuh:
+    // bmap_offset).  A 2-byte store to global memory costs a whole 32-byte sector AND makes the L2 fetch that sector
+    // first (measured: +27 KB of DRAM reads per clip), so the map is STAGED in shared memory -- the FFT exchange
+    // buffers are idle in the tail -- and copied out with 16-byte stores that cover full sectors.  Two stages (the
+    // buffers hold 17 KB beside the MFCC scratch): block rows 0..15 (map rows 0..63: zero rows, mel rows 0..60) here,
+    // the rest (mel rows 61..63, MFCC, deltas, zero rows) after the normalisation.  Every element of a staged block
+    // row is written exactly once, zero padding included.  (PCEN keeps the scattered stores: its rows 0..63 are
+    // known only at the very end.)
+    constexpr int kStageOff = 5376;                                    // bytes into S.xb: behind the MFCC scratch
+    constexpr int kStageRowsA = 16;                                    // block rows in stage A
+    static_assert(kStageOff >= (int)(sizeof(float) * kMfcc * kTilePitch), "stage behind the MFCC scratch");
+    static_assert(kStageOff + kStageRowsA * kBmapB * 32 <= (int)(sizeof(float2) * kXbElems * kFeatWarps), "stage A fits");
+    static_assert(kStageOff + (NetShape<kFeatDD>::BA - kStageRowsA) * kBmapB * 32 <= (int)(sizeof(float2) * kXbElems * kFeatWarps), "stage B fits");
+    __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(&S.xb[0][0]) + kStageOff);
+    const bool staged = !PCEN && mo != nullptr;
+    const __nv_bfloat16 bz = __float2bfloat16_rn(0.f);
     {
         // thread = (row group, frame pair): the tile is read and written as 8-byte pairs, no index division; even rows
-        // of an 8-byte aligned output take one 8-byte store
+        // of an 8-byte aligned output take one 8-byte store.  Map rows R = feature row + 3, map cols C = frame + 3.
         const int j = tid & 63, g = tid >> 6;
         const bool al8 = out && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
         if (j < kPairs) {
             const bool two = 2 * j + 1 < kFrames;
-            for (int r = g; r < kMels; r += kFeatThreads / 64) {
-                float2* cell = reinterpret_cast<float2*>(S.db + r * kTilePitch + 2 * j);
-                float2 p = *cell;
-                p.x *= inv2;
-                p.y *= inv2;
-                if (PCEN) {
-                    *cell = p;
-                } else {
-                    const float2 v = make_float2(fmaxf(power_to_db(p.x), floor_db), fmaxf(power_to_db(p.y), floor_db));
-                    *cell = v;
-                    const float2 x01 = make_float2(fminf(fmaxf((v.x + 80.0f) * 0.0125f, 0.f), 1.f),
-                                                   fminf(fmaxf((v.y + 80.0f) * 0.0125f, 0.f), 1.f));
-                    if (out) {
-                        float* o = out + r * kFrames + 2 * j;
-                        if (al8 && !(r & 1) && two) {
-                            *reinterpret_cast<float2*>(o) = x01;
-                        } else {
-                            o[0] = x01.x;
-                            if (two) o[1] = x01.y;
+            for (int R = g; R < kMels + 3; R += kFeatThreads / 64) {
+                const int r = R - 3;
+                float2 x01 = make_float2(0.f, 0.f);
+                if (r >= 0) {
+                    float2* cell = reinterpret_cast<float2*>(S.db + r * kTilePitch + 2 * j);
+                    float2 p = *cell;
+                    p.x *= inv2;
+                    p.y *= inv2;
+                    if (PCEN) {
+                        *cell = p;
+                    } else {
+                        const float2 v = make_float2(fmaxf(power_to_db(p.x), floor_db), fmaxf(power_to_db(p.y), floor_db));
+                        *cell = v;
+                        x01 = make_float2(fminf(fmaxf((v.x + 80.0f) * 0.0125f, 0.f), 1.f), fminf(fmaxf((v.y + 80.0f) * 0.0125f, 0.f), 1.f));
+                        if (out) {
+                            float* o = out + r * kFrames + 2 * j;
+                            if (al8 && !(r & 1) && two) {
+                                *reinterpret_cast<float2*>(o) = x01;
+                            } else {
+                                o[0] = x01.x;
+                                if (two) o[1] = x01.y;
+                            }
                         }
                     }
-                    if (mo) {
-                        mo[bmap_offset(r + 3, 2 * j + 3)] = __float2bfloat16_rn(x01.x);
-                        if (two) mo[bmap_offset(r + 3, 2 * j + 4)] = __float2bfloat16_rn(x01.y);
+                }
+                if (staged && R < 4 * kStageRowsA) {
+                    stage[bmap_offset(R, 2 * j + 3)] = __float2bfloat16_rn(x01.x);
+                    stage[bmap_offset(R, 2 * j + 4)] = two ? __float2bfloat16_rn(x01.y) : bz;     // C = 104: right padding
+                    if (j == 0) {
+#pragma unroll
+                        for (int C = 0; C < 3; ++C) stage[bmap_offset(R, C)] = bz;
+                    }
+                    if (j == kPairs - 1) {
+#pragma unroll
+                        for (int C = 105; C < 108; ++C) stage[bmap_offset(R, C)] = bz;
                     }
                 }
             }
         }
     }
     __syncthreads();
+    if (staged) {                                                      // stage A -> global, full sectors
+        const uint4* s16 = reinterpret_cast<const uint4*>(stage);
+        uint4* g16 = reinterpret_cast<uint4*>(mo);
+        for (int i = tid; i < kStageRowsA * kBmapB * 2; i += kFeatThreads) g16[i] = s16[i];
+    }
 
     // ---- MFCC = DCT-II(13 x 64) of the floored dB, then (x - mean) / (std + 1e-8) ---------------
     float* mf = reinterpret_cast<float*>(&S.xb[0][0]);             // [13][102], FFT scratch is idle now
@@ -637,6 +666,9 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float inv2, float* _
     const float mean = tot.x * (1.0f / kN);
     const float var = fmaxf(tot.y - tot.x * mean, 0.f) * (1.0f / (kN - 1));
     const float inv_std = 1.0f / (sqrtf(var) + 1e-8f);
+    // stage B holds map rows 64 .. 4 BA - 1 (block rows 16 ..); element (R, C) sits at bmap_offset(R, C) - kStageBase
+    constexpr int kStageBase = kStageRowsA * kBmapB * 16;
+    const int map_rows = dd ? 4 * NetShape<kFeatDD>::BA : 4 * kBmapA;  // 112 | 96
     for (int t = tid; t < kFrames; t += kFeatThreads) {               // thread = frame, all 13 coefficients
         const int tp = min(t + 1, kFrames - 1), tm = max(t - 1, 0);
 #pragma unroll 1
@@ -659,11 +691,35 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float inv2, float* _
                 if (dd) out[(kMels + 2 * kMfcc + cidx) * kFrames + t] = d2;
             }
             if (mo) {
-                mo[bmap_offset(kMels + cidx + 3, t + 3)] = __float2bfloat16_rn(x0);
-                mo[bmap_offset(kMels + kMfcc + cidx + 3, t + 3)] = __float2bfloat16_rn(dl);
-                if (dd) mo[bmap_offset(kMels + 2 * kMfcc + cidx + 3, t + 3)] = __float2bfloat16_rn(d2);
+                __nv_bfloat16* m = staged ? stage - kStageBase : mo;
+                m[bmap_offset(kMels + cidx + 3, t + 3)] = __float2bfloat16_rn(x0);
+                m[bmap_offset(kMels + kMfcc + cidx + 3, t + 3)] = __float2bfloat16_rn(dl);
+                if (dd) m[bmap_offset(kMels + 2 * kMfcc + cidx + 3, t + 3)] = __float2bfloat16_rn(d2);
             }
         }
+        if (staged) {
+            // the rest of this frame's column: mel rows 61..63 (map rows 64..66) and the zero rows below the features
+            __nv_bfloat16* m = stage - kStageBase;
+#pragma unroll
+            for (int r = 4 * kStageRowsA - 3; r < kMels; ++r) {
+                const float v = S.db[r * kTilePitch + t];
+                m[bmap_offset(r + 3, t + 3)] = __float2bfloat16_rn(fminf(fmaxf((v + 80.0f) * 0.0125f, 0.f), 1.f));
+            }
+            for (int R = (dd ? kFeatDD : kFeat) + 3; R < map_rows; ++R) m[bmap_offset(R, t + 3)] = bz;
+        }
+    }
+    if (staged) {
+        // left / right zero columns of stage B: one thread per padding column
+        const int k = tid - (kFeatThreads - 7);                        // the last seven threads (idle above: 101 frames)
+        if (k >= 0) {
+            const int C = k < 3 ? k : 101 + k;                         // 0, 1, 2, 104, 105, 106, 107
+            for (int R = 4 * kStageRowsA; R < map_rows; ++R) stage[bmap_offset(R, C) - kStageBase] = bz;
+        }
+        __syncthreads();
+        const int n16 = (map_rows / 4 - kStageRowsA) * kBmapB * 2;    // 16-byte pieces of stage B
+        const uint4* s16 = reinterpret_cast<const uint4*>(stage);
+        uint4* g16 = reinterpret_cast<uint4*>(mo) + kStageRowsA * kBmapB * 2;
+        for (int i = tid; i < n16; i += kFeatThreads) g16[i] = s16[i];
     }
 
     if (PCEN) {
@@ -785,6 +841,7 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
     const bool normalize = !(mode & kModeNoNormalize);
 
     for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        if (lane == 0) S.xb[warp][kXchElems + kPowZero] = make_float2(0.f, 0.f);   // (the tail's map stage may have used it)
         const ClipView<T> v = clip_view(audio, offs, lens, stride_or_hop, mode, b);
         const bool fast = v.len == kSeg && v.start == 0;               // a whole 16 000-sample clip: direct loads
         if (tid == 0) {                                                // pull the clip after this one into L2 meanwhile
@@ -997,6 +1054,7 @@ stream_window_kernel(const float* __restrict__ audio, int64_t hop, int64_t n_win
     __syncthreads();
     const int64_t h = hop / kHop;
     for (int64_t j = blockIdx.x; j < n_windows; j += gridDim.x) {
+        if (lane == 0) S.xb[warp][kXchElems + kPowZero] = make_float2(0.f, 0.f);   // (the tail's map stage may have used it)
         const float peak = tid < kSeg / kHop ? bmax[j * h + tid] : 0.f;
         float wmax = 0.f;
         if (warp < 3) {

@@ -12,7 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "gpurun_out", "f")
 DST = os.path.join(ROOT, "profiles")
-R = "r" + (sys.argv[1] if len(sys.argv) > 1 else "1")
+R = "r" + (sys.argv[1] if len(sys.argv) > 1 else "2")
 
 
 def copy_json(src, dst):

@@ -8,11 +8,12 @@ python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo smo
 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; echo pytest=$?; tail -3 $O/pytest.log
 python bench.py --impl reference > $O/bench_ref.json 2> $O/bench_ref.err; echo ref=$?
 python bench.py > $O/bench.json 2> $O/bench.err; echo bench=$?
-python bench.py --precision fp32 --no-cpu-baseline > $O/bench_fp32.json 2> $O/bench_fp32.err; echo fp32=$?
-python tools/stream_bench.py > $O/stream.json 2> $O/stream.err; echo stream=$?
+python bench.py --precision fp32 --no-cpu-baseline --no-sweep --no-stream > $O/bench_fp32.json 2> $O/bench_fp32.err; echo fp32=$?
+python tools/h2d_matrix.py > $O/h2d_matrix.json 2> $O/h2d_matrix.err; echo h2d=$?
+python tools/latency_probe.py > $O/latency.json 2> $O/latency.err; echo latency=$?
 # launch list of the bench command itself (it exited 0 plainly just above)
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"feat|stem|conv3x3|head|map_from|predict" -c 400 --csv \
-    --log-file $O/launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/ncu0.log 2>&1; echo launches_bench=$?
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"feat|stem|conv3x3|head|map_from|predict|stream|block_max" -c 600 --csv \
+    --log-file $O/launches_bench.csv python bench.py --steps 2 --warmup 3 --min-seconds 0.01 --no-cpu-baseline --no-sweep > $O/ncu0.log 2>&1; echo launches_bench=$?
 python tools/profile_case.py 16384 > $O/pc.log 2>&1 && \
   ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"feat|stem|conv3x3|head" --csv \
       --log-file $O/launches.csv python tools/profile_case.py 16384 > $O/ncu1.log 2>&1; echo launches=$?
