@@ -5,7 +5,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
 SRC_DIR   := cough_detector_b200/csrc
 OUT_DIR   := cough_detector_b200/lib
-SRCS      := $(SRC_DIR)/api.cu $(SRC_DIR)/feat_kernel.cu $(SRC_DIR)/cnn_fp32.cu $(SRC_DIR)/cnn_tc.cu $(SRC_DIR)/cnn_plain.cu $(SRC_DIR)/resample.cu
+SRCS      := $(SRC_DIR)/api.cu $(SRC_DIR)/feat_kernel.cu $(SRC_DIR)/cnn_fp32.cu $(SRC_DIR)/cnn_tc.cu $(SRC_DIR)/cnn_plain.cu $(SRC_DIR)/resample.cu $(SRC_DIR)/spec_augment.cu
 OBJS      := $(patsubst $(SRC_DIR)/%.cu,build/%.o,$(SRCS))
 LIB       := $(OUT_DIR)/libcough_b200.so
 
@@ -26,7 +26,7 @@ exp: $(OBJS)
 	@mkdir -p build/exp $(OUT_DIR)/exp
 	for e in $(EXP); do tag=$${e%%:*}; flags=$$(echo $${e#*:} | tr ',' ' '); \
 	  $(NVCC) $(NVCCFLAGS) $$flags -c $(SRC_DIR)/feat_kernel.cu -o build/exp/feat_$$tag.o 2> build/exp/feat_$$tag.ptxas.log && \
-	  $(NVCC) -shared $(ARCH) -o $(OUT_DIR)/exp/lib$$tag.so build/api.o build/exp/feat_$$tag.o build/cnn_fp32.o build/cnn_tc.o build/cnn_plain.o build/resample.o; \
+	  $(NVCC) -shared $(ARCH) -o $(OUT_DIR)/exp/lib$$tag.so build/api.o build/exp/feat_$$tag.o build/cnn_fp32.o build/cnn_tc.o build/cnn_plain.o build/resample.o build/spec_augment.o; \
 	done
 
 # C++ callers of the C ABI (no Python, no torch)

@@ -105,6 +105,7 @@ SYMBOLS = {
     "cd_small_forward": (_I, [_VP, _VP, _I, _I64, _VP, _VP]),
     "cd_standard_load": (_I, [_VP, C.POINTER(_StandardWeights)]),
     "cd_standard_forward": (_I, [_VP, _VP, _I, _I64, _VP, _VP]),
+    "cd_spec_augment": (_I, [_VP, _VP, _I, _I64, _VP, _I, _I, _VP]),
     "cd_predict": (_I, [_VP, _VP, _I64, C.c_float, _VP, _VP, _VP, _VP]),
     "cd_e2e_forward": (_I, [_VP, _VP, _I64, _I64, _VP, _VP, _I, _F, _I, _VP]),
     "cd_e2e_forward_i16": (_I, [_VP, _VP, _I64, _I64, _VP, _VP, _I, _F, _I, _VP]),
@@ -363,6 +364,21 @@ class Handle:
         self._check(self.lib.cd_predict(self._h, _ptr(logits), B, threshold, _ptr(probs), _ptr(preds), _ptr(dec),
                                         self._stream()), "cd_predict")
         return preds, probs, dec.bool()
+
+    def spec_augment_(self, feat: torch.Tensor, masks: torch.Tensor, n_freq_masks: int, n_time_masks: int) -> torch.Tensor:
+        """In place: zero the row / column intervals of ``masks`` (B, 2 (n_freq_masks + n_time_masks)) int32 in
+        ``feat`` (B, 1, rows, 101) cuda fp32 (cd_spec_augment)."""
+        if not (feat.is_cuda and feat.device.index == self.device and feat.dtype == torch.float32 and feat.is_contiguous()):
+            raise CoughB200Error(f"features must be a contiguous fp32 tensor on cuda:{self.device}")
+        if feat.dim() != 4 or feat.shape[1] != 1 or feat.shape[3] != N_FRAMES:
+            raise CoughB200Error(f"features must be (B, 1, rows, {N_FRAMES}), got {tuple(feat.shape)}")
+        B = feat.shape[0]
+        masks = masks.to(device=feat.device, dtype=torch.int32).contiguous()
+        if tuple(masks.shape) != (B, 2 * (n_freq_masks + n_time_masks)):
+            raise CoughB200Error(f"masks must be ({B}, {2 * (n_freq_masks + n_time_masks)}), got {tuple(masks.shape)}")
+        self._check(self.lib.cd_spec_augment(self._h, _ptr(feat), int(feat.shape[2]), B, _ptr(masks), n_freq_masks,
+                                             n_time_masks, self._stream()), "cd_spec_augment")
+        return feat
 
     def selftest_umma(self, a: torch.Tensor, b: torch.Tensor, shift: int = 0, mode: int = 0) -> torch.Tensor:
         """a[shift:shift+128] (K) x b (N, K)^T on one tcgen05 tile; CPU fp32 tensors in, CPU fp32 (128, N) out."""

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "cd_common.cuh"
+#include <stdlib.h>
 
 namespace cd {
 
@@ -423,6 +424,15 @@ int cd_predict(cd_handle* h, const float* d_logits, int64_t B, float threshold, 
     return CD_OK;
 }
 
+int cd_spec_augment(cd_handle* h, float* d_feat, int n_rows, int64_t B, const int32_t* d_masks, int n_freq_masks,
+                    int n_time_masks, void* stream) {
+    if (!h) return CD_E_ARG;
+    if (B < 0 || n_rows <= 0 || (B > 0 && (!d_feat || (!d_masks && n_freq_masks + n_time_masks > 0))))
+        return set_err(h, CD_E_ARG, "cd_spec_augment: bad argument");
+    DeviceGuard g(h->device);
+    return launch_spec_augment(h, d_feat, n_rows, kFrames, B, d_masks, n_freq_masks, n_time_masks, (cudaStream_t)stream);
+}
+
 // ---- end to end ------------------------------------------------------------------------------
 
 // Features for the CNN live in a second, separately grown buffer so the CNN workspace can be
@@ -438,7 +448,11 @@ static int e2e_impl(cd_handle* h, const void* d_audio_v, bool i16, int64_t strid
     // process in slabs so a slab's features stay L2-resident between the two stages.  bf16: the
     // feature kernel writes the stem's bf16 map straight into the CNN workspace (fp32 features only
     // if the caller asked for them); fp32: features go through an fp32 buffer.
-    const int64_t slab = 16384;
+    int64_t slab = 16384;
+    if (const char* e = getenv("CD_E2E_SLAB")) {          // experiment knob (tools/slab_sweep.py): smaller slabs keep the
+        const long v = atol(e);                           // activations in L2 but pay the per-launch ramp more often
+        if (v >= 148 && v <= 16384) slab = v;
+    }
     const bool tcp = precision == CD_PRECISION_BF16;
     const size_t cnn_ws = tcp ? cnn_tc_ws_bytes(slab) : cnn_fp32_ws_bytes(slab);
     const size_t feat_bytes = (tcp || d_feat_opt) ? 0 : (size_t)slab * felems * sizeof(float);

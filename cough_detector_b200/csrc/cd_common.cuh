@@ -159,6 +159,8 @@ int ensure_ws(cd_handle* h, size_t bytes);
 int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets, const int32_t* d_lengths,
                     int64_t stride_or_hop, int mode, float coef, int64_t B, float* d_feat, __nv_bfloat16* d_map,
                     cudaStream_t s);
+int launch_spec_augment(cd_handle* h, float* d_feat, int n_rows, int n_cols, int64_t B, const int32_t* d_masks, int nf, int nt,
+                        cudaStream_t s);
 int launch_cnn_fp32(cd_handle* h, const float* d_feat, int64_t B, float* d_logits, cudaStream_t s, int nf = kFeat);
 size_t cnn_fp32_ws_bytes(int64_t B);
 

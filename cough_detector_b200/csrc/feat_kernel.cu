@@ -51,6 +51,23 @@ namespace cd {
 #ifndef CD_PF
 #define CD_PF 2
 #endif
+// CD_L2PF: when the clip after this one is pulled into L2.  0: never;  1: when this clip starts;  2: when this clip's tail
+//   starts (a shorter stay in L2: with 4 x 148 clips in flight a whole-clip lead is ~38 MB of prefetched lines on top of
+//   the ~59 MB that stream through meanwhile);  3: each warp pulls its quarter half-way through its run.
+//   Measured over 65 536 clips (ncu dram__bytes_read, CUDA-event time): 1: 6.54 GB, 52.9 ns/clip -- a third of the prefetched
+//   lines are evicted before they are used and fetched again;  0: 4.19 GB (exactly the audio), 52.5;  2: 4.25 GB, 52.2;
+//   3: 5.21 GB, 55.5.
+#ifndef CD_L2PF
+#define CD_L2PF 2
+#endif
+// CD_STCS: output stores carry the streaming (evict-first) hint
+#ifndef CD_STCS
+#define CD_STCS 1
+#endif
+#ifndef CD_DELTA_UNROLL
+#define CD_DELTA_UNROLL 13
+#endif
+constexpr int kDeltaUnroll = CD_DELTA_UNROLL;     // unroll of the tail's MFCC / delta row loop
 constexpr int kFeatWarps   = CD_FEAT_WARPS;
 constexpr int kFeatThreads = kFeatWarps * 32;
 constexpr int kFeatCtasPerSm = CD_FEAT_CTAS;  // one CTA's reductions / tail overlap the others' FFTs
@@ -141,6 +158,29 @@ __device__ __forceinline__ float2 cfmac(float2 c, float2 a, float tx, float ty) 
     return up(rd);
 }
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+
+// output stores (features / map): written once, never read again by this kernel
+__device__ __forceinline__ void st_out(float* p, float v) {
+#if CD_STCS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+__device__ __forceinline__ void st_out(float2* p, float2 v) {
+#if CD_STCS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+__device__ __forceinline__ void st_out(uint4* p, uint4 v) {
+#if CD_STCS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
 
 // ----------------------------------------------------------------------------------------------
 // 16-point DFT in registers, radix 4 x 4
@@ -597,39 +637,44 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float inv2, float* _
     __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(&S.xb[0][0]) + kStageOff);
     const bool staged = !PCEN && mo != nullptr;
     const __nv_bfloat16 bz = __float2bfloat16_rn(0.f);
-    {
-        // thread = (row group, frame pair): the tile is read and written as 8-byte pairs, no index division; even rows
-        // of an 8-byte aligned output take one 8-byte store.  Map rows R = feature row + 3, map cols C = frame + 3.
-        const int j = tid & 63, g = tid >> 6;
+    if (!PCEN) {
+        // work item = (block row a of the map, frame pair j): four tile rows x two frames, so the blocked-map address
+        // arithmetic is shared by the four rows and no lane idles (17 x 51 items over the CTA).  The top_db floor and the
+        // 1e-10 clamp move to the power side of the logarithm:
+        //   max(10 log10(max(Q, 1e-10)), floor) = kDb lg2(max(Q, qfloor)),  Q = P / peak^2,  qfloor = max(1e-10, top / peak^2 * 1e-8)
+        // (monotone, so exact up to the rounding of the logarithm; Q itself is formed first, which keeps the features
+        // bit-identical under power-of-two gains and between the int16 and fp32 entries), and (dB + 80) / 80 = dB / 80 + 1
+        // is one FFMA.SAT.
+        constexpr float kDb = 3.01029995663981195f;
+        const float qfloor = fmaxf(1e-10f, (top * inv2) * 1e-8f);
         const bool al8 = out && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
-        if (j < kPairs) {
-            const bool two = 2 * j + 1 < kFrames;
-            for (int R = g; R < kMels + 3; R += kFeatThreads / 64) {
-                const int r = R - 3;
+        for (int idx = tid; idx < (kMels / 4 + 1) * kPairs; idx += kFeatThreads) {
+            const int a = idx / kPairs, j = idx - a * kPairs;
+            const bool two = j < kPairs - 1;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int R = 4 * a + rr, r = R - 3;
                 float2 x01 = make_float2(0.f, 0.f);
-                if (r >= 0) {
+                if (r >= 0 && r < kMels) {
                     float2* cell = reinterpret_cast<float2*>(S.db + r * kTilePitch + 2 * j);
-                    float2 p = *cell;
-                    p.x *= inv2;
-                    p.y *= inv2;
-                    if (PCEN) {
-                        *cell = p;
-                    } else {
-                        const float2 v = make_float2(fmaxf(power_to_db(p.x), floor_db), fmaxf(power_to_db(p.y), floor_db));
-                        *cell = v;
-                        x01 = make_float2(fminf(fmaxf((v.x + 80.0f) * 0.0125f, 0.f), 1.f), fminf(fmaxf((v.y + 80.0f) * 0.0125f, 0.f), 1.f));
-                        if (out) {
-                            float* o = out + r * kFrames + 2 * j;
-                            if (al8 && !(r & 1) && two) {
-                                *reinterpret_cast<float2*>(o) = x01;
-                            } else {
-                                o[0] = x01.x;
-                                if (two) o[1] = x01.y;
-                            }
+                    const float2 p = *cell;
+                    float lx, ly;
+                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lx) : "f"(fmaxf(p.x * inv2, qfloor)));
+                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(ly) : "f"(fmaxf(p.y * inv2, qfloor)));
+                    const float2 v = make_float2(kDb * lx, kDb * ly);
+                    *cell = v;
+                    x01 = make_float2(__saturatef(fmaf(v.x, 0.0125f, 1.0f)), __saturatef(fmaf(v.y, 0.0125f, 1.0f)));
+                    if (out) {
+                        float* o = out + r * kFrames + 2 * j;
+                        if (al8 && !(r & 1) && two) {
+                            st_out(reinterpret_cast<float2*>(o), x01);
+                        } else {
+                            st_out(o, x01.x);
+                            if (two) st_out(o + 1, x01.y);
                         }
                     }
                 }
-                if (staged && R < 4 * kStageRowsA) {
+                if (staged && a < kStageRowsA) {
                     stage[bmap_offset(R, 2 * j + 3)] = __float2bfloat16_rn(x01.x);
                     stage[bmap_offset(R, 2 * j + 4)] = two ? __float2bfloat16_rn(x01.y) : bz;     // C = 104: right padding
                     if (j == 0) {
@@ -643,12 +688,22 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float inv2, float* _
                 }
             }
         }
+    } else {
+        // PCEN: the tile keeps the scaled mel POWER (the MFCC rows take their dB from it on the fly)
+        for (int idx = tid; idx < kMels * kPairs; idx += kFeatThreads) {
+            const int r = idx / kPairs, j = idx - r * kPairs;
+            float2* cell = reinterpret_cast<float2*>(S.db + r * kTilePitch + 2 * j);
+            float2 p = *cell;
+            p.x *= inv2;
+            p.y *= inv2;
+            *cell = p;
+        }
     }
     __syncthreads();
     if (staged) {                                                      // stage A -> global, full sectors
         const uint4* s16 = reinterpret_cast<const uint4*>(stage);
         uint4* g16 = reinterpret_cast<uint4*>(mo);
-        for (int i = tid; i < kStageRowsA * kBmapB * 2; i += kFeatThreads) g16[i] = s16[i];
+        for (int i = tid; i < kStageRowsA * kBmapB * 2; i += kFeatThreads) st_out(g16 + i, s16[i]);
     }
 
     // ---- MFCC = DCT-II(13 x 64) of the floored dB, then (x - mean) / (std + 1e-8) ---------------
@@ -671,7 +726,7 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float inv2, float* _
     const int map_rows = dd ? 4 * NetShape<kFeatDD>::BA : 4 * kBmapA;  // 112 | 96
     for (int t = tid; t < kFrames; t += kFeatThreads) {               // thread = frame, all 13 coefficients
         const int tp = min(t + 1, kFrames - 1), tm = max(t - 1, 0);
-#pragma unroll 1
+#pragma unroll kDeltaUnroll
         for (int cidx = 0; cidx < kMfcc; ++cidx) {
             const float* row = mf + cidx * kTilePitch;
             // __fmul_rn: never contracted into an FMA, so the bf16 map below sees identical values
@@ -686,9 +741,9 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float inv2, float* _
                 d2 = (d1(t + 1) - d1(t - 1)) * 0.5f;
             }
             if (out) {
-                out[(kMels + cidx) * kFrames + t] = x0;
-                out[(kMels + kMfcc + cidx) * kFrames + t] = dl;
-                if (dd) out[(kMels + 2 * kMfcc + cidx) * kFrames + t] = d2;
+                st_out(out + (kMels + cidx) * kFrames + t, x0);
+                st_out(out + (kMels + kMfcc + cidx) * kFrames + t, dl);
+                if (dd) st_out(out + (kMels + 2 * kMfcc + cidx) * kFrames + t, d2);
             }
             if (mo) {
                 __nv_bfloat16* m = staged ? stage - kStageBase : mo;
@@ -703,7 +758,7 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float inv2, float* _
 #pragma unroll
             for (int r = 4 * kStageRowsA - 3; r < kMels; ++r) {
                 const float v = S.db[r * kTilePitch + t];
-                m[bmap_offset(r + 3, t + 3)] = __float2bfloat16_rn(fminf(fmaxf((v + 80.0f) * 0.0125f, 0.f), 1.f));
+                m[bmap_offset(r + 3, t + 3)] = __float2bfloat16_rn(__saturatef(fmaf(v, 0.0125f, 1.0f)));   // as the rows pass
             }
             for (int R = (dd ? kFeatDD : kFeat) + 3; R < map_rows; ++R) m[bmap_offset(R, t + 3)] = bz;
         }
@@ -719,7 +774,7 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float inv2, float* _
         const int n16 = (map_rows / 4 - kStageRowsA) * kBmapB * 2;    // 16-byte pieces of stage B
         const uint4* s16 = reinterpret_cast<const uint4*>(stage);
         uint4* g16 = reinterpret_cast<uint4*>(mo) + kStageRowsA * kBmapB * 2;
-        for (int i = tid; i < n16; i += kFeatThreads) g16[i] = s16[i];
+        for (int i = tid; i < n16; i += kFeatThreads) st_out(g16 + i, s16[i]);
     }
 
     if (PCEN) {
@@ -844,15 +899,21 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
         if (lane == 0) S.xb[warp][kXchElems + kPowZero] = make_float2(0.f, 0.f);   // (the tail's map stage may have used it)
         const ClipView<T> v = clip_view(audio, offs, lens, stride_or_hop, mode, b);
         const bool fast = v.len == kSeg && v.start == 0;               // a whole 16 000-sample clip: direct loads
-        if (tid == 0) {                                                // pull the clip after this one into L2 meanwhile
+        // pull the clip after this one into L2 meanwhile (CD_L2PF says when)
+        auto prefetch_next = [&](int part, int parts) {
             const int64_t bn = b + gridDim.x;
             if (bn < B) {
                 const ClipView<T> vn = clip_view(audio, offs, lens, stride_or_hop, mode, bn);
                 const T* pn = vn.src + vn.start;
-                if (vn.len == kSeg && (reinterpret_cast<uintptr_t>(pn) & 15) == 0)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pn), "r"((uint32_t)(kSeg * sizeof(T))) : "memory");
+                if (vn.len == kSeg && (reinterpret_cast<uintptr_t>(pn) & 15) == 0) {
+                    const uint32_t bytes = (uint32_t)(kSeg * sizeof(T)) / parts;          // 64 000 / 4 and 32 000 / 4: multiples of 16
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(pn) + (size_t)part * bytes), "r"(bytes) : "memory");
+                }
             }
-        }
+        };
+#if CD_L2PF == 1
+        if (tid == 0) prefetch_next(0, 1);
+#endif
         // AudioPreprocessor.process normalises over the WHOLE clip before it trims or pads: clips that do not take the
         // direct-load path get their peak from a pass of their own
         float peak_pre = 0.f;
@@ -869,6 +930,9 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
             float raw[18];
             bool have = false;                                         // raw[] already holds this pair's samples
             for (int p = wp0; p < wp1; ++p) {
+#if CD_L2PF == 3
+                if (lane == 0 && pass == 0 && p == (wp0 + wp1) / 2) prefetch_next(warp, kFeatWarps);
+#endif
                 const bool edge = (p == 0) || (p >= 49);
                 const int s0 = 2 * kHop * p - kWin / 2 + lane;         // this lane's sample of window tap 0
                 float2 x[16], lo, hi;
@@ -968,6 +1032,9 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
             const float inv = 1.0f / (peak * pre);
             inv2 = inv * inv;
         }
+#if CD_L2PF == 2
+        if (tid == 0) prefetch_next(0, 1);
+#endif
         const bool dd = (mode & kModeDeltaDelta) != 0;
         feat_tail<PCEN>(S, top, inv2, feat ? feat + b * (int64_t)(dd ? kFeatElemDD : kFeatElem) : nullptr,
                         map_out ? map_out + b * (int64_t)(dd ? NetShape<kFeatDD>::MAP_ELEMS : kMapElems) : nullptr, tid, dd);

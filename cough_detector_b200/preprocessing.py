@@ -152,11 +152,12 @@ class AudioPreprocessor:
         """resample -> mono -> normalize -> pad/trim -> features, one kernel (:491-517).  (C, n) -> (1, 90, 101)."""
         return self.process_batch([waveform], orig_sr)[0]
 
-    def process_batch(self, waveforms: Sequence[torch.Tensor], orig_sr: int = 16000) -> torch.Tensor:
+    def process_batch(self, waveforms: Sequence[torch.Tensor], orig_sr: int = 16000, out_device=None) -> torch.Tensor:
         """Variable-length clips [(C_i, n_i) or (n_i,)], float or int16 PCM, all at ``orig_sr`` -> (B, 1, 90, 101); per clip
         identical to ``process`` (the per-file pipeline of dataset.__getitem__, src/dataset.py:151-163).
         Batched end to end: ONE packed host buffer and host->device copy for all clips, ONE resample + to_mono launch
-        over (offset, channels, length) descriptors when any clip needs it, ONE feature launch."""
+        over (offset, channels, length) descriptors when any clip needs it, ONE feature launch.  The result lands on
+        ``out_device`` (default: the device of the first waveform, like every other method here)."""
         if not len(waveforms):
             return torch.zeros(0, 1, self.get_num_features(), _lib.N_FRAMES)
         if int(orig_sr) != orig_sr or orig_sr <= 0:
@@ -189,6 +190,8 @@ class AudioPreprocessor:
         else:
             flat, out_off, out_len = packed, torch.tensor(offs, dtype=torch.int64), torch.tensor(n_in, dtype=torch.int32)
         out = h.feat_forward_var(flat, out_off, out_len, opts=self.feat_options)
+        if out_device is not None:
+            return out.to(out_device)
         return self._back(out, waveforms[0])
 
     def process_file(self, path: str) -> torch.Tensor:

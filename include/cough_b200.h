@@ -239,6 +239,18 @@ int cd_standard_forward(cd_handle* h, const float* d_feat, int n_rows, int64_t B
 int cd_predict(cd_handle* h, const float* d_logits, int64_t B, float threshold,
                float* d_probs, int64_t* d_preds, uint8_t* d_decisions, void* stream);
 
+/* ---- training-side use of the features ----------------------- */
+
+/* SpecAugment.__call__ (src/augmentation.py:303-331) on a batch of cached features, in place: per clip n_freq_masks row
+ * intervals and n_time_masks column intervals are filled with 0, as T.FrequencyMasking / T.TimeMasking do
+ * (torchaudio functional.py mask_along_axis, mask_value 0).  d_feat: B x n_rows x 101 fp32; d_masks: device,
+ * B x 2 (n_freq_masks + n_time_masks) int32, per clip {start, end} of each row interval, then of each column interval
+ * (end exclusive; end <= start masks nothing -- that is how a clip the reference leaves alone with probability 1 - p is
+ * expressed).  The intervals are sampled by the caller in the reference's random-number order
+ * (cough_detector_b200/augmentation.py); at most 8 masks per axis. */
+int cd_spec_augment(cd_handle* h, float* d_feat, int n_rows, int64_t B, const int32_t* d_masks,
+                    int n_freq_masks, int n_time_masks, void* stream);
+
 /* ---- end to end ------------------------------------------------------------------------ */
 
 /* audio -> logits in one call: cd_feat_forward + cd_cnn_forward without the features leaving

@@ -483,3 +483,41 @@ def resample(w: torch.Tensor, orig_sr: int, new_sr: int = SAMPLE_RATE) -> torch.
     x = F.pad(w, (width, width + orig))
     y = F.conv1d(x[:, None], k[:, None], stride=orig).transpose(1, 2).reshape(rows, -1)
     return y[:, : math.ceil(new * n / orig)]
+
+
+# --------------------------------------------------------------------------
+# SpecAugment (src/augmentation.py:271-331; torchaudio/functional/functional.py mask_along_axis)
+# --------------------------------------------------------------------------
+def spec_augment_intervals(n_rows: int, n_cols: int = N_FRAMES, freq_mask_param: int = 10, time_mask_param: int = 20,
+                           n_freq_masks: int = 2, n_time_masks: int = 2, p: float = 0.5) -> Optional[List[Tuple[int, int]]]:
+    """One SpecAugment.__call__ as its random draws: ``random.random() > p`` -> None (input returned untouched,
+    src/augmentation.py:314-315); otherwise n_freq_masks row intervals then n_time_masks column intervals [start, end),
+    each from ``value = rand(1) * param; min_value = rand(1) * (size - value); start = long(min_value);
+    end = long(min_value) + long(value)`` -- and NO draw when param < 1 (mask_along_axis returns early).  Uses the global
+    ``random`` / ``torch`` generators exactly like the reference."""
+    import random
+    if random.random() > p:
+        return None
+    out = []
+    for param, size, n in ((freq_mask_param, n_rows, n_freq_masks), (time_mask_param, n_cols, n_time_masks)):
+        for _ in range(n):
+            if param < 1:
+                out.append((0, 0))
+                continue
+            value = torch.rand(1) * param
+            min_value = torch.rand(1) * (size - value)
+            out.append((int(min_value.long()), int(min_value.long() + value.long())))
+    return out
+
+
+def spec_augment_apply(x: torch.Tensor, intervals: Optional[Sequence[Tuple[int, int]]], n_freq_masks: int = 2) -> torch.Tensor:
+    """masked_fill(mask, 0.0) of the row intervals (the first n_freq_masks) and the column intervals (the rest) on (..., F, T)."""
+    if intervals is None:
+        return x
+    y = x.clone()
+    for k, (s, e) in enumerate(intervals):
+        if k < n_freq_masks:
+            y[..., s:e, :] = 0.0
+        else:
+            y[..., :, s:e] = 0.0
+    return y

@@ -144,7 +144,43 @@ def contrast_goldens():
     print("contrast_nan.npz", np.stack(nan_rows).sum(axis=1))
 
 
+AUGMENT_CASES = [dict(rows=90, kw=dict(p=0.8)), dict(rows=103, kw=dict(p=0.8)),
+                 dict(rows=90, kw=dict(freq_mask_param=15, time_mask_param=30, n_freq_masks=1, n_time_masks=3, p=1.0)),
+                 dict(rows=90, kw=dict(freq_mask_param=0, time_mask_param=20, n_freq_masks=2, n_time_masks=2, p=1.0))]
+
+
+def augment_goldens():
+    """tests/golden/spec_augment.npz: which cells the UNMODIFIED reference SpecAugment (src/augmentation.py:271-331) zeroes,
+    for 8 consecutive __call__s per case after random.seed(s) / torch.manual_seed(s) -- the inputs are strictly positive
+    (0.5 + rand), so a zero cell is a masked cell.  Stored as packed bits, (case, call, rows * 101)."""
+    import random
+    sys.path.insert(0, REF)
+    from src.augmentation import SpecAugment
+    torch.set_num_threads(1)
+    out = {"meta": np.array([torch.__version__])}
+    for ci, case in enumerate(AUGMENT_CASES):
+        random.seed(40 + ci)
+        torch.manual_seed(40 + ci)
+        sa = SpecAugment(**case["kw"])
+        zs = []
+        for call in range(8):
+            x = 0.5 + torch.rand(1, case["rows"], 101, generator=torch.Generator().manual_seed(1000 + call))
+            y = sa(x)
+            zs.append(np.packbits((y == 0).numpy().reshape(-1)))
+        out[f"zero_{ci}"] = np.stack(zs)
+    # a 4-D batch shares one set of masks (mask_along_axis is not iid)
+    random.seed(77)
+    torch.manual_seed(77)
+    sa = SpecAugment(p=1.0)
+    xb = 0.5 + torch.rand(3, 1, 90, 101, generator=torch.Generator().manual_seed(5))
+    out["zero_batch"] = np.packbits((sa(xb) == 0).numpy().reshape(-1))
+    np.savez_compressed(os.path.join(GOLD, "spec_augment.npz"), **out)
+    print("spec_augment.npz", os.path.getsize(os.path.join(GOLD, "spec_augment.npz")))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "augment":
+        return augment_goldens()
     if len(sys.argv) > 1 and sys.argv[1] == "contrast":
         return contrast_goldens()
     if len(sys.argv) > 1 and sys.argv[1] == "flags":

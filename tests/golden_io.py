@@ -77,3 +77,17 @@ def load_other_model(kind: str):
         if k.endswith("running_mean"):
             sd[k[: -len("running_mean")] + "num_batches_tracked"] = torch.zeros((), dtype=torch.int64)
     return sd, torch.from_numpy(z[f"{kind}/logits90"]), torch.from_numpy(z[f"{kind}/logits103"])
+
+
+def load_spec_augment():
+    """[(rows, SpecAugment kwargs, zero-cell masks (8 calls, rows, 101) bool)] per case, and the shared-mask batch case
+    (3, 1, 90, 101) bool, recorded from the reference's SpecAugment (oracle/make_golden.py augment)."""
+    from oracle.make_golden import AUGMENT_CASES
+    z = np.load(os.path.join(GOLD, "spec_augment.npz"))
+    cases = []
+    for ci, case in enumerate(AUGMENT_CASES):
+        n = case["rows"] * 101
+        bits = np.stack([np.unpackbits(r)[:n] for r in z[f"zero_{ci}"]]).astype(bool).reshape(8, case["rows"], 101)
+        cases.append((case["rows"], case["kw"], bits))
+    batch = np.unpackbits(z["zero_batch"])[: 3 * 90 * 101].astype(bool).reshape(3, 1, 90, 101)
+    return cases, batch

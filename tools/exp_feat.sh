@@ -1,0 +1,18 @@
+#!/bin/bash
+# Times every experimental feature-kernel build (lib/exp/*.so) against the default one and records their DRAM bytes.
+O=gpurun_out/exp
+mkdir -p $O
+N=${1:-65536}
+for lib in default cough_detector_b200/lib/exp/*.so; do
+  tag=$(basename $lib .so)
+  if [ $lib = default ]; then unset CD_LIB; else export CD_LIB=$PWD/$lib; fi
+  python tools/feat_time.py $N >> $O/times.txt 2>&1
+done
+cat $O/times.txt
+for lib in default cough_detector_b200/lib/exp/*.so; do
+  tag=$(basename $lib .so)
+  if [ $lib = default ]; then unset CD_LIB; else export CD_LIB=$PWD/$lib; fi
+  ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum --clock-control none -k regex:feat_kernel -s 1 -c 1 --csv \
+      --log-file $O/dram_$tag.csv python tools/feat_profile_case.py $N > $O/ncu_$tag.log 2>&1
+  echo "$tag: $(tail -6 $O/dram_$tag.csv | cut -d, -f13- | tr '\n' ' ')"
+done

@@ -3,6 +3,8 @@ import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cough_detector_b200 import _lib, synth
+if os.environ.get("CD_LIB"):
+    _lib.LIB_PATH = os.environ["CD_LIB"]
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 h = _lib.get_handle(0)
 x = synth.synth_batch(B, seed=100, device="cuda")
