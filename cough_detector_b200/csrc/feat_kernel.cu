@@ -65,7 +65,7 @@ namespace cd {
 #define CD_STCS 1
 #endif
 #ifndef CD_DELTA_UNROLL
-#define CD_DELTA_UNROLL 13
+#define CD_DELTA_UNROLL 1
 #endif
 constexpr int kDeltaUnroll = CD_DELTA_UNROLL;     // unroll of the tail's MFCC / delta row loop
 constexpr int kFeatWarps   = CD_FEAT_WARPS;
@@ -651,12 +651,22 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float inv2, float* _
         for (int idx = tid; idx < (kMels / 4 + 1) * kPairs; idx += kFeatThreads) {
             const int a = idx / kPairs, j = idx - a * kPairs;
             const bool two = j < kPairs - 1;
+            // blocked-map addresses of the item's two columns (cd_common.cuh bmap_offset, unrolled over the block's four
+            // rows): element (4 a + rr, C) sits at row * 16 + (((rr >> 1) << 3) ^ swz) + (rr & 1) * 4 + (C & 3)
+            const int C0 = 2 * j + 3, C1 = 2 * j + 4;
+            const int row0 = a * kBmapB + (C0 >> 2), row1 = a * kBmapB + (C1 >> 2);
+            __nv_bfloat16* const m0 = stage + row0 * 16 + (C0 & 3);
+            __nv_bfloat16* const m1 = stage + row1 * 16 + (C1 & 3);
+            const int z0 = ((row0 >> 2) & 1) << 3, z1 = ((row1 >> 2) & 1) << 3;
+            const bool do_stage = staged && a < kStageRowsA;
+            float* const o = out + (4 * a - 3) * kFrames + 2 * j;
+            const float2* cellp = reinterpret_cast<const float2*>(S.db + (4 * a - 3) * kTilePitch + 2 * j);
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
-                const int R = 4 * a + rr, r = R - 3;
+                const int r = 4 * a + rr - 3;
                 float2 x01 = make_float2(0.f, 0.f);
                 if (r >= 0 && r < kMels) {
-                    float2* cell = reinterpret_cast<float2*>(S.db + r * kTilePitch + 2 * j);
+                    float2* cell = const_cast<float2*>(cellp) + rr * (kTilePitch / 2);
                     const float2 p = *cell;
                     float lx, ly;
                     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lx) : "f"(fmaxf(p.x * inv2, qfloor)));
@@ -665,25 +675,25 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float inv2, float* _
                     *cell = v;
                     x01 = make_float2(__saturatef(fmaf(v.x, 0.0125f, 1.0f)), __saturatef(fmaf(v.y, 0.0125f, 1.0f)));
                     if (out) {
-                        float* o = out + r * kFrames + 2 * j;
-                        if (al8 && !(r & 1) && two) {
-                            st_out(reinterpret_cast<float2*>(o), x01);
+                        float* orow = o + rr * kFrames;
+                        // row r of an 8-byte aligned output starts 8-byte aligned when r is even (101 floats per row)
+                        if (al8 && !((rr + a * 4 - 3) & 1) && two) {
+                            st_out(reinterpret_cast<float2*>(orow), x01);
                         } else {
-                            st_out(o, x01.x);
-                            if (two) st_out(o + 1, x01.y);
+                            st_out(orow, x01.x);
+                            if (two) st_out(orow + 1, x01.y);
                         }
                     }
                 }
-                if (staged && a < kStageRowsA) {
-                    stage[bmap_offset(R, 2 * j + 3)] = __float2bfloat16_rn(x01.x);
-                    stage[bmap_offset(R, 2 * j + 4)] = two ? __float2bfloat16_rn(x01.y) : bz;     // C = 104: right padding
-                    if (j == 0) {
-#pragma unroll
-                        for (int C = 0; C < 3; ++C) stage[bmap_offset(R, C)] = bz;
+                if (do_stage) {
+                    const int e0 = (((rr >> 1) << 3) ^ z0) + (rr & 1) * 4, e1 = (((rr >> 1) << 3) ^ z1) + (rr & 1) * 4;
+                    m0[e0] = __float2bfloat16_rn(x01.x);
+                    m1[e1] = two ? __float2bfloat16_rn(x01.y) : bz;                                // C = 104: right padding
+                    if (j == 0) {                                                                  // C = 0, 1, 2 sit left of C0 = 3
+                        m0[e0 - 3] = bz; m0[e0 - 2] = bz; m0[e0 - 1] = bz;
                     }
-                    if (j == kPairs - 1) {
-#pragma unroll
-                        for (int C = 105; C < 108; ++C) stage[bmap_offset(R, C)] = bz;
+                    if (j == kPairs - 1) {                                                         // C = 105, 106, 107 right of C1 = 104
+                        m1[e1 + 1] = bz; m1[e1 + 2] = bz; m1[e1 + 3] = bz;
                     }
                 }
             }
