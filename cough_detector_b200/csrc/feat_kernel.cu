@@ -64,10 +64,6 @@ namespace cd {
 #ifndef CD_STCS
 #define CD_STCS 1
 #endif
-#ifndef CD_DELTA_UNROLL
-#define CD_DELTA_UNROLL 1
-#endif
-constexpr int kDeltaUnroll = CD_DELTA_UNROLL;     // unroll of the tail's MFCC / delta row loop
 constexpr int kFeatWarps   = CD_FEAT_WARPS;
 constexpr int kFeatThreads = kFeatWarps * 32;
 constexpr int kFeatCtasPerSm = CD_FEAT_CTAS;  // one CTA's reductions / tail overlap the others' FFTs
@@ -734,37 +730,54 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float inv2, float* _
     // stage B holds map rows 64 .. 4 BA - 1 (block rows 16 ..); element (R, C) sits at bmap_offset(R, C) - kStageBase
     constexpr int kStageBase = kStageRowsA * kBmapB * 16;
     const int map_rows = dd ? 4 * NetShape<kFeatDD>::BA : 4 * kBmapA;  // 112 | 96
-    for (int t = tid; t < kFrames; t += kFeatThreads) {               // thread = frame, all 13 coefficients
-        const int tp = min(t + 1, kFrames - 1), tm = max(t - 1, 0);
-#pragma unroll kDeltaUnroll
-        for (int cidx = 0; cidx < kMfcc; ++cidx) {
+    {
+        // thread = (coefficient, frame pair): normalised MFCC rows 64.., their deltas 77.. (compute_deltas, :342-356:
+        // replicate padding, (x[t+1] - x[t-1]) / 2) and on request the deltas of the deltas 90..; 13 x 51 items, the pair's
+        // four neighbours read once.  __fmul_rn: never contracted into an FMA, so every consumer sees identical values.
+        const bool al8o = out && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
+        __nv_bfloat16* const m = mo ? (staged ? stage - kStageBase : mo) : nullptr;
+        for (int idx = tid; idx < kMfcc * kPairs; idx += kFeatThreads) {
+            const int cidx = idx / kPairs, j = idx - cidx * kPairs, t = 2 * j;
+            const bool two = j < kPairs - 1;
             const float* row = mf + cidx * kTilePitch;
-            // __fmul_rn: never contracted into an FMA, so the bf16 map below sees identical values
-            const float x0 = __fmul_rn(row[t] - mean, inv_std);
-            const float xp = __fmul_rn(row[tp] - mean, inv_std);
-            const float xm = __fmul_rn(row[tm] - mean, inv_std);
-            const float dl = (xp - xm) * 0.5f;                             // compute_deltas (:353-355)
-            float d2 = 0.f;
+            auto nrm = [&](float v) { return __fmul_rn(v - mean, inv_std); };
+            const float2 pr = *reinterpret_cast<const float2*>(row + t);
+            const float xa = nrm(pr.x);                                    // frame t
+            const float xb = two ? nrm(pr.y) : xa;                         // frame t + 1 (replicated past the last frame)
+            const float xm = t ? nrm(row[t - 1]) : xa;                     // frame t - 1 (replicated before the first)
+            const float xq = nrm(row[min(t + 2, kFrames - 1)]);            // frame t + 2
+            const float da = (xb - xm) * 0.5f, db = (xq - xa) * 0.5f;
+            float ea = 0.f, eb = 0.f;
             if (dd) {
-                auto xn = [&](int u) { return __fmul_rn(row[min(max(u, 0), kFrames - 1)] - mean, inv_std); };
+                auto xn = [&](int u) { return nrm(row[min(max(u, 0), kFrames - 1)]); };
                 auto d1 = [&](int u) { u = min(max(u, 0), kFrames - 1); return (xn(u + 1) - xn(u - 1)) * 0.5f; };
-                d2 = (d1(t + 1) - d1(t - 1)) * 0.5f;
+                ea = (d1(t + 1) - d1(t - 1)) * 0.5f;
+                eb = (d1(t + 2) - d1(t)) * 0.5f;
             }
-            if (out) {
-                st_out(out + (kMels + cidx) * kFrames + t, x0);
-                st_out(out + (kMels + kMfcc + cidx) * kFrames + t, dl);
-                if (dd) st_out(out + (kMels + 2 * kMfcc + cidx) * kFrames + t, d2);
-            }
-            if (mo) {
-                __nv_bfloat16* m = staged ? stage - kStageBase : mo;
-                m[bmap_offset(kMels + cidx + 3, t + 3)] = __float2bfloat16_rn(x0);
-                m[bmap_offset(kMels + kMfcc + cidx + 3, t + 3)] = __float2bfloat16_rn(dl);
-                if (dd) m[bmap_offset(kMels + 2 * kMfcc + cidx + 3, t + 3)] = __float2bfloat16_rn(d2);
-            }
+            auto put = [&](int frow, float v0, float v1) {                 // feature row frow, frames t and t + 1
+                if (out) {
+                    float* o = out + frow * kFrames + t;
+                    if (al8o && !(frow & 1) && two) {
+                        st_out(reinterpret_cast<float2*>(o), make_float2(v0, v1));
+                    } else {
+                        st_out(o, v0);
+                        if (two) st_out(o + 1, v1);
+                    }
+                }
+                if (m) {
+                    m[bmap_offset(frow + 3, t + 3)] = __float2bfloat16_rn(v0);
+                    if (two) m[bmap_offset(frow + 3, t + 4)] = __float2bfloat16_rn(v1);
+                }
+            };
+            put(kMels + cidx, xa, xb);
+            put(kMels + kMfcc + cidx, da, db);
+            if (dd) put(kMels + 2 * kMfcc + cidx, ea, eb);
         }
-        if (staged) {
-            // the rest of this frame's column: mel rows 61..63 (map rows 64..66) and the zero rows below the features
-            __nv_bfloat16* m = stage - kStageBase;
+    }
+    if (staged) {
+        // the rest of stage B, thread = frame column: mel rows 61..63 (map rows 64..66) and the zero rows below the features
+        __nv_bfloat16* m = stage - kStageBase;
+        for (int t = tid; t < kFrames; t += kFeatThreads) {
 #pragma unroll
             for (int r = 4 * kStageRowsA - 3; r < kMels; ++r) {
                 const float v = S.db[r * kTilePitch + t];
@@ -775,7 +788,7 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float inv2, float* _
     }
     if (staged) {
         // left / right zero columns of stage B: one thread per padding column
-        const int k = tid - (kFeatThreads - 7);                        // the last seven threads (idle above: 101 frames)
+        const int k = tid - (kFeatThreads - 7);                        // the last seven threads
         if (k >= 0) {
             const int C = k < 3 ? k : 101 + k;                         // 0, 1, 2, 104, 105, 106, 107
             for (int R = 4 * kStageRowsA; R < map_rows; ++R) stage[bmap_offset(R, C) - kStageBase] = bz;
