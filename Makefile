@@ -29,6 +29,10 @@ exp: $(OBJS)
 	  $(NVCC) -shared $(ARCH) -o $(OUT_DIR)/exp/lib$$tag.so build/api.o build/exp/feat_$$tag.o build/cnn_fp32.o build/cnn_tc.o build/cnn_plain.o build/resample.o build/spec_augment.o; \
 	done
 
+# timing-only ablations of the feature kernel (profiles/r2_feat_ablation.txt): CD_LIB=.../libab<N>.so python tools/feat_time.py
+ablations:
+	$(MAKE) exp EXP="ab1:-DCD_ABLATE=1 ab2:-DCD_ABLATE=2 ab3:-DCD_ABLATE=3 ab4:-DCD_ABLATE=4"
+
 # C++ callers of the C ABI (no Python, no torch)
 examples: $(LIB)
 	$(NVCC) -O2 -std=c++17 $(ARCH) -Iinclude examples/e2e_minimal.cu -o build/e2e_minimal -L$(OUT_DIR) -lcough_b200 -Xlinker -rpath,'$$ORIGIN/../$(OUT_DIR)'
@@ -36,4 +40,4 @@ examples: $(LIB)
 clean:
 	rm -rf build $(LIB)
 
-.PHONY: all clean exp examples
+.PHONY: all clean exp examples ablations

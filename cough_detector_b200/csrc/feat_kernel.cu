@@ -64,6 +64,11 @@ namespace cd {
 #ifndef CD_STCS
 #define CD_STCS 1
 #endif
+// CD_ABLATE: timing-only builds (`make ablations`; their RESULTS ARE WRONG by construction, only the time matters).
+//   1: no tail;  2: no mel contraction;  3: no FFT and no mel (loads, window, peak and tail only);  4: FFT without its exchange.
+#ifndef CD_ABLATE
+#define CD_ABLATE 0
+#endif
 constexpr int kFeatWarps   = CD_FEAT_WARPS;
 constexpr int kFeatThreads = kFeatWarps * 32;
 constexpr int kFeatCtasPerSm = CD_FEAT_CTAS;  // one CTA's reductions / tail overlap the others' FFTs
@@ -379,6 +384,16 @@ __device__ __forceinline__ void lane_ctx_init(LaneCtx& L, const FeatTables* __re
 // (bins 4..127) in the warp's power region.  mel_pair() finishes the job; the caller issues the next pair's sample
 // loads between the two (the FFT registers are dead by then).
 __device__ __forceinline__ void fft_pair(float2 (&x)[16], const LaneCtx& L, int lane) {
+#if CD_ABLATE == 3
+    {   // keep the loads and the window multiplies alive, nothing else
+        float2 acc = x[0];
+#pragma unroll
+        for (int a = 1; a < 13; ++a) acc = cadd(acc, x[a]);
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(L.p0_s), "f"(acc.x), "f"(acc.y) : "memory");
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(L.pb_s + L.pstep), "f"(acc.y), "f"(acc.x) : "memory");
+        return;
+    }
+#endif
     // ---- stage 1: DFT16 over a, then twiddles W512^(m r) ---------------------------------------------
 #if CD_TW == 2
     fft16_twiddled(x, L.tw_s);
@@ -404,6 +419,7 @@ __device__ __forceinline__ void fft_pair(float2 (&x)[16], const LaneCtx& L, int 
     }
 #endif
     // ---- the one exchange: lane (r, c) gathers Y'[2 b + c][r], b = 0..15 -------------------------------
+#if CD_ABLATE != 4
 #pragma unroll
     for (int r = 0; r < 16; ++r)
         asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(L.xw_s + r * (kXchRow * 8)), "f"(x[F16(r)].x), "f"(x[F16(r)].y) : "memory");
@@ -412,6 +428,7 @@ __device__ __forceinline__ void fft_pair(float2 (&x)[16], const LaneCtx& L, int 
     for (int j = 0; j < 8; ++j)
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                      : "=f"(x[2 * j].x), "=f"(x[2 * j].y), "=f"(x[2 * j + 1].x), "=f"(x[2 * j + 1].y) : "r"(L.xr_s + j * 16) : "memory");
+#endif
     // ---- stage 2: DFT16 over b.  c = 0: V(t) = E[t];  c = 1: V(t) = (-1)^t O[(t + 8) & 15] (sign flip of the
     //      lanes m = 3 mod 4 folded into their window + the swapped halves of the c = 1 rows) ----------------
     fft16<false>(x);
@@ -469,6 +486,11 @@ __device__ __forceinline__ void fft_pair(float2 (&x)[16], const LaneCtx& L, int 
 // Second half: mel POWER of the two frames for bands `lane` (lo) and `lane + 32` (hi); .x = first frame, .y = second.
 __device__ __forceinline__ void mel_pair(const LaneCtx& L, int lane, float2& lo, float2& hi) {
     __syncwarp();
+#if CD_ABLATE == 2 || CD_ABLATE == 3
+    lo = lds64(L.p0_s);
+    hi = lds64(L.pb_s + L.pstep);
+    return;
+#endif
     // ---- banded mel contraction (cd_common.cuh): the lane reads the bins of its two segments once, for both
     //      frames, and hands the rising-side sums to the lane above ----------------------------------------
     lo = make_float2(0.f, 0.f);
@@ -1059,6 +1081,10 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
         if (tid == 0) prefetch_next(0, 1);
 #endif
         const bool dd = (mode & kModeDeltaDelta) != 0;
+#if CD_ABLATE == 1
+        if (tid == 0 && feat) feat[b * (int64_t)kFeatElem] = top + inv2;
+        if (false)
+#endif
         feat_tail<PCEN>(S, top, inv2, feat ? feat + b * (int64_t)(dd ? kFeatElemDD : kFeatElem) : nullptr,
                         map_out ? map_out + b * (int64_t)(dd ? NetShape<kFeatDD>::MAP_ELEMS : kMapElems) : nullptr, tid, dd);
         __syncthreads();                                               // xb / db free again

@@ -26,7 +26,11 @@ def main():
     copy_json("bench_ref.json", f"{R}_bench_reference_arm.json")
     if os.path.exists(os.path.join(SRC, "bench_fp32.json")):
         copy_json("bench_fp32.json", f"{R}_bench_fp32.json")
-    copy_json("stream.json", f"{R}_stream_bench_1gpu.json")
+    if os.path.exists(os.path.join(SRC, "stream.json")):
+        copy_json("stream.json", f"{R}_stream_bench_1gpu.json")
+    for src, dst in (("latency.json", f"{R}_latency.json"), ("h2d_matrix.json", f"{R}_h2d_matrix_1gpu.json")):
+        if os.path.exists(os.path.join(SRC, src)):
+            copy_json(src, dst)
     shutil.copy(os.path.join(SRC, "smoke.log"), os.path.join(DST, f"{R}_smoke.log"))
     # launch list: keep kernel name, grid, block, duration
     rows = [r for r in csv.reader(open(os.path.join(SRC, "launches.csv"))) if len(r) > 10]
