@@ -9,6 +9,8 @@ from .preprocessing import AudioPreprocessor, RealtimePreprocessor, create_prepr
 from .model import (CoughDetector, CoughDetectorResidual, CoughDetectorSmall, ConvBlock, ResidualBlock, create_model,  # noqa: F401
                     count_parameters)
 from .inference import CoughDetectorInference, smooth_and_debounce  # noqa: F401
+from .augmentation import SpecAugment  # noqa: F401
+from .dataset import CoughDataset  # noqa: F401
 
 __all__ = ["AudioPreprocessor", "RealtimePreprocessor", "create_preprocessor", "CoughDetectorResidual",
-           "ResidualBlock", "CoughDetector", "CoughDetectorSmall", "ConvBlock", "create_model", "count_parameters", "CoughDetectorInference", "smooth_and_debounce"]
+           "ResidualBlock", "CoughDetector", "CoughDetectorSmall", "ConvBlock", "create_model", "count_parameters", "CoughDetectorInference", "smooth_and_debounce", "SpecAugment", "CoughDataset"]
