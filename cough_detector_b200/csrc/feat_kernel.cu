@@ -1,4 +1,4 @@
-// Fused feature kernel: clip -> (90 | 103, 101) features, persistent, three 256-thread CTAs per SM.
+// Fused feature kernel: clip -> (90 | 103, 101) features, persistent, four 128-thread CTAs per SM.
 //
 // Replaces, per clip, AudioPreprocessor.normalize (src/preprocessing.py:199-212), pad_or_trim
 // (:358-385) and extract_features (:432-489): T.MelSpectrogram (reflect pad, 400-sample periodic
@@ -47,10 +47,8 @@ namespace cd {
 #ifndef CD_TW
 #define CD_TW 2
 #endif
-// CD_PF: where the next pair's 10 new samples are requested.  0: after the mel contraction;  1: before it;  2: before the FFT.
-#ifndef CD_PF
-#define CD_PF 2
-#endif
+// The next pair's 10 new samples are requested before the current pair's FFT (requesting them after the FFT or after the mel
+// contraction was measured slower: the loads then arrive too late to hide under anything).
 // CD_L2PF: when the clip after this one is pulled into L2.  0: never;  1: when this clip starts;  2: when this clip's tail
 //   starts (a shorter stay in L2: with 4 x 148 clips in flight a whole-clip lead is ~38 MB of prefetched lines on top of
 //   the ~59 MB that stream through meanwhile);  3: each warp pulls its quarter half-way through its run.
@@ -570,10 +568,9 @@ __device__ __forceinline__ void lane_window(const FeatTables* __restrict__ table
 }
 
 // raw[q] = sample s0 + 32 q + lane of the pair's 576-sample span; frame 0 uses q = 0..12, frame 1 q = 5..17
-template <bool MAYBE_SINGLE>
-__device__ __forceinline__ void form_inputs(const float (&raw)[18], const float (&w)[13], bool second, float2 (&x)[16]) {
+__device__ __forceinline__ void form_inputs(const float (&raw)[18], const float (&w)[13], float2 (&x)[16]) {
 #pragma unroll
-    for (int a = 0; a < 13; ++a) x[a] = make_float2(w[a] * raw[a], (!MAYBE_SINGLE || second) ? w[a] * raw[a + 5] : 0.f);
+    for (int a = 0; a < 13; ++a) x[a] = make_float2(w[a] * raw[a], w[a] * raw[a + 5]);
 }
 // the pair's mel power into the tile: frames 2 p, 2 p + 1 of bands lane and lane + 32 as two 8-byte stores
 __device__ __forceinline__ float store_pair(float* db, int lane, int p, bool second, float2 lo, float2 hi) {
@@ -979,21 +976,19 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
                 if (lane == 0 && pass == 0 && p == (wp0 + wp1) / 2) prefetch_next(warp, kFeatWarps);
 #endif
                 const bool edge = (p == 0) || (p >= 49);
+                const bool second = (2 * p + 1) < kFrames;             // pair 50 holds frame 100 only
                 const int s0 = 2 * kHop * p - kWin / 2 + lane;         // this lane's sample of window tap 0
                 float2 x[16], lo, hi;
+                // ---- raw[] <- the pair's 18 samples per lane (ONE copy of the FFT / mel code follows for all three cases) ----
                 if (edge || !fast) {
-                    // reflect-padded pairs and clips that are trimmed / padded: every sample through the index mapping
-                    const bool second = (2 * p + 1) < kFrames;
+                    // reflect-padded pairs and clips that are trimmed / padded: every sample through the index mapping.
+                    // (Pair 50's second frame does not exist: its samples are reflected ones like any other, the frame is
+                    // computed and store_pair drops it.)
                     if (fast) {
 #pragma unroll
                         for (int q = 0; q < 18; ++q) raw[q] = sample_reflect<PRE, true>(v, s0 + 32 * q, coef);
-                    } else {
 #pragma unroll
-                        for (int q = 0; q < 18; ++q) raw[q] = sample_reflect<PRE, false>(v, s0 + 32 * q, coef);
-                    }
-                    if (fast) {                                        // reflected samples are samples: they count for the peak
-#pragma unroll
-                        for (int q = 0; q < 18; ++q) {
+                        for (int q = 0; q < 18; ++q) {                 // reflected samples are samples: they count for the peak
                             if (PRE) {
                                 int i = s0 + 32 * q;
                                 i = i < 0 ? -i : i;
@@ -1003,62 +998,32 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
                                 amax = fmaxf(amax, fabsf(raw[q]));
                             }
                         }
-                    }
-                    form_inputs<true>(raw, w, second, x);
-                    have = false;
-                    if (p == 0 && fast && p + 1 < wp1) {               // pair 1 starts from pair 0's last eight sample registers
+                    } else {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) raw[q] = raw[q + 10];
-                        have = true;
+                        for (int q = 0; q < 18; ++q) raw[q] = sample_reflect<PRE, false>(v, s0 + 32 * q, coef);
                     }
-#if CD_PF == 2
-                    if (have) request_next_impl<PRE>(v.src + s0 + 2 * kHop, raw, amax, coef);
-#endif
-                    fft_pair(x, L, lane);
-#if CD_PF == 1
-                    if (have) request_next_impl<PRE>(v.src + s0 + 2 * kHop, raw, amax, coef);
-#endif
-                    mel_pair(L, lane, lo, hi);
-#if CD_PF == 0
-                    if (have) request_next_impl<PRE>(v.src + s0 + 2 * kHop, raw, amax, coef);
-#endif
-                    pmax = fmaxf(pmax, store_pair(S.db, lane, p, second, lo, hi));
-                } else {
-                    if (have) {                                        // requested during the previous pair: they arrive about now
-                        if (!PRE) {
+                } else if (!have) {                                    // first interior pair of the warp's run
+                    const T* ps = v.src + s0;
 #pragma unroll
-                            for (int q = 8; q < 18; ++q) amax = fmaxf(amax, fabsf(raw[q]));
-                        }
-                    } else {                                           // first pair of the warp's run
-                        const T* ps = v.src + s0;
-#pragma unroll
-                        for (int q = 0; q < 18; ++q) {
-                            const float xq = (float)ps[32 * q];
-                            amax = fmaxf(amax, fabsf(xq));
-                            raw[q] = PRE ? __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1])) : xq;
-                        }
+                    for (int q = 0; q < 18; ++q) {
+                        const float xq = (float)ps[32 * q];
+                        amax = fmaxf(amax, fabsf(xq));
+                        raw[q] = PRE ? __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1])) : xq;
                     }
-                    form_inputs<false>(raw, w, true, x);
-                    // the samples of the next pair: 8 carried in registers, 10 new ones issued once this pair's FFT
-                    // registers are dead, consumed after the mel contraction
-                    have = (p + 1 < wp1) && (p + 1) < 49;
-                    if (have) {
+                } else if (!PRE) {                                     // requested during the previous pair: they arrive about now
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) raw[q] = raw[q + 10];
-                    }
-#if CD_PF == 2
-                    if (have) request_next_impl<PRE>(v.src + s0 + 2 * kHop, raw, amax, coef);
-#endif
-                    fft_pair(x, L, lane);
-#if CD_PF == 1
-                    if (have) request_next_impl<PRE>(v.src + s0 + 2 * kHop, raw, amax, coef);
-#endif
-                    mel_pair(L, lane, lo, hi);
-#if CD_PF == 0
-                    if (have) request_next_impl<PRE>(v.src + s0 + 2 * kHop, raw, amax, coef);
-#endif
-                    pmax = fmaxf(pmax, store_pair(S.db, lane, p, true, lo, hi));
+                    for (int q = 8; q < 18; ++q) amax = fmaxf(amax, fabsf(raw[q]));
                 }
+                form_inputs(raw, w, x);
+                // ---- the next pair's samples: 8 carried in registers (pair 0 hands its last eight to pair 1 as well), 10 new
+                //      ones requested before the FFT and consumed after the mel contraction -----------------------------
+                have = fast && (p + 1 < wp1) && (p + 1) < 49;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) raw[q] = raw[q + 10];
+                if (have) request_next_impl<PRE>(v.src + s0 + 2 * kHop, raw, amax, coef);
+                fft_pair(x, L, lane);
+                mel_pair(L, lane, lo, hi);
+                pmax = fmaxf(pmax, store_pair(S.db, lane, p, second, lo, hi));
             }
             const float2 mx = block_reduce2<true>(make_float2(pmax, amax), S.red);   // barrier: the power tile is complete
             top = mx.x;
@@ -1144,7 +1109,7 @@ stream_mel_kernel(const float* __restrict__ audio, int64_t F, float* __restrict_
             raw[k] = PRE ? __fsub_rn(xq, __fmul_rn(coef, ps[32 * k - 1])) : xq;
         }
         float2 x[16], lo, hi;
-        form_inputs<false>(raw, w, true, x);
+        form_inputs(raw, w, x);
         fft_pair(x, L, lane);
         mel_pair(L, lane, lo, hi);
         float* o = melp + f0 * kMels + lane;
@@ -1189,7 +1154,7 @@ stream_window_kernel(const float* __restrict__ audio, int64_t hop, int64_t n_win
 #pragma unroll
             for (int q = 0; q < 18; ++q) raw[q] = sample_reflect<PRE, true>(v, s0 + 32 * q, coef);
             float2 x[16], lo, hi;
-            form_inputs<true>(raw, w, second, x);
+            form_inputs(raw, w, x);
             fft_pair(x, L, lane);
             mel_pair(L, lane, lo, hi);
             wmax = store_pair(S.db, lane, p, second, lo, hi);

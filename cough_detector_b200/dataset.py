@@ -37,7 +37,7 @@ def decode_audio(path: str) -> Tuple[torch.Tensor, int]:
                 if w.getsampwidth() == 2 and w.getcomptype() == "NONE":
                     n, c, sr = w.getnframes(), w.getnchannels(), w.getframerate()
                     pcm = np.frombuffer(w.readframes(n), dtype="<i2").reshape(-1, c).T
-                    return torch.from_numpy(np.ascontiguousarray(pcm)), sr
+                    return torch.from_numpy(np.array(pcm, order="C")), sr            # a writable copy (frombuffer views are read-only)
         except (wave.Error, EOFError):
             pass                                            # not plain PCM: let torchaudio try
     try:

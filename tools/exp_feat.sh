@@ -1,6 +1,7 @@
 #!/bin/bash
 # Times every experimental feature-kernel build (lib/exp/*.so) against the default one; with NCU=1 also records their DRAM
 # bytes, instruction count and issue rate (one ncu pass per build).
+shopt -s nullglob
 O=gpurun_out/exp
 mkdir -p $O
 N=${1:-65536}
