@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "cd_common.cuh"
+#include <stdlib.h>
 
 namespace cd {
 
@@ -383,11 +384,13 @@ struct S1Args {
     int64_t y_plane_elems;         // WRITE_XS: y_bf16 is written phase-split (Ps2Layout<H, W>, 4 planes this far apart)
     int64_t ps_plane_elems;
     int n;                         // clips
+    int rev;                       // walk the tiles from the last to the first (see tile_order)
 };
 
 template <int C, int H, int W, bool OUT_F32, bool WRITE_XS>
 __global__ void __launch_bounds__(kS1Threads, 1)
 conv3x3_s1_tc_kernel(const S1Args a) {
+    const bool REV_ORDER = a.rev != 0;
     using S = S1Shape<C, H, W>;
     using PS = PsLayout<H, W>;
     using PSN = PsLayout<(H + 1) / 2, (W + 1) / 2>;               // the next block's grid (stride 2, pad 1, k 3)
@@ -438,7 +441,8 @@ conv3x3_s1_tc_kernel(const S1Args a) {
             tc::bulk_g2s(s_w + 9 * S::NPL * 8192, a.wskip + (size_t)half * 64 * 64, 8192, &w_bar);
             tc::pdl_wait();                            // weights are in flight; the activations need the previous kernel
             int it = 0;
-            for (int tile = cta; tile < n_tiles; tile += n_cta, ++it) {
+            for (int t_ = cta; t_ < n_tiles; t_ += n_cta, ++it) {
+                const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
                 const int s = it % S::STAGES;
                 const uint32_t par = (uint32_t)(((it / S::STAGES) & 1) ^ 1);
 #pragma unroll
@@ -456,7 +460,8 @@ conv3x3_s1_tc_kernel(const S1Args a) {
         if (lane == 0) {
             tc::mbar_wait(&w_bar, 0);
             int it = 0;
-            for (int tile = cta; tile < n_tiles; tile += n_cta, ++it) {
+            for (int t_ = cta; t_ < n_tiles; t_ += n_cta, ++it) {
+                const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
                 const int s = it % S::STAGES, acc = it & 1;
                 const uint32_t par = (uint32_t)((it / S::STAGES) & 1);
                 tc::mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
@@ -494,7 +499,8 @@ conv3x3_s1_tc_kernel(const S1Args a) {
         // ======================= epilogue: + bias, ReLU, store the valid pixels ======================
         const int lane_grp = warp & 3;
         int it = 0;
-        for (int tile = cta; tile < n_tiles; tile += n_cta, ++it) {
+        for (int t_ = cta; t_ < n_tiles; t_ += n_cta, ++it) {
+                const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
             const int acc = it & 1;
             const int64_t mp = (int64_t)tile * 128 + lane_grp * 32 + lane;      // padded-row index m'
             const int clip = (int)(mp / PS::RPC), rem = (int)(mp - (int64_t)clip * PS::RPC);
@@ -578,6 +584,7 @@ struct S1PairShape {
 template <int H, int W>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kS1Threads, 1)
 conv3x3_s1_pair_tc_kernel(const S1Args a) {
+    const bool REV_ORDER = a.rev != 0;
     constexpr int C = 128;
     using S = S1PairShape<H, W>;
     using PS = PsLayout<H, W>;
@@ -631,7 +638,8 @@ conv3x3_s1_pair_tc_kernel(const S1Args a) {
             tc::bulk_g2s(s_w + 18 * 8192, a.wskip + (size_t)rank * 64 * 64, 8192, &w_bar);
             tc::pdl_wait();
             int it = 0;
-            for (int tp = pair; tp < n_tp; tp += n_pairs, ++it) {
+            for (int t_ = pair; t_ < n_tp; t_ += n_pairs, ++it) {
+                const int tp = REV_ORDER ? n_tp - 1 - t_ : t_;
                 const int64_t tile = 2 * (int64_t)tp + rank;
 #pragma unroll
                 for (int q = 0; q < NB; ++q) {
@@ -649,7 +657,8 @@ conv3x3_s1_pair_tc_kernel(const S1Args a) {
                 // ======================= MMA issuer (leader) ==============================================
                 const uint64_t dw = tc::desc_sw128(tc::s32(s_w));
                 int it = 0;
-                for (int tp = pair; tp < n_tp; tp += n_pairs, ++it) {
+                for (int t_ = pair; t_ < n_tp; t_ += n_pairs, ++it) {
+                const int tp = REV_ORDER ? n_tp - 1 - t_ : t_;
                     const int acc = it & 1;
                     tc::mbar_wait_cluster(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
                     const uint32_t d = tmem_base + acc * 128;
@@ -681,7 +690,8 @@ conv3x3_s1_pair_tc_kernel(const S1Args a) {
             } else {
                 // ======================= relay (peer): tell the leader when my slots are full ============
                 int it = 0;
-                for (int tp = pair; tp < n_tp; tp += n_pairs, ++it) {
+                for (int t_ = pair; t_ < n_tp; t_ += n_pairs, ++it) {
+                const int tp = REV_ORDER ? n_tp - 1 - t_ : t_;
 #pragma unroll
                     for (int q = 0; q < NB; ++q) {
                         tc::mbar_wait(&full_bar[q], (uint32_t)(it & 1));
@@ -694,7 +704,8 @@ conv3x3_s1_pair_tc_kernel(const S1Args a) {
         // ======================= epilogue (both CTAs): my 128 rows x all 128 channels ================
         const int lane_grp = warp & 3;
         int it = 0;
-        for (int tp = pair; tp < n_tp; tp += n_pairs, ++it) {
+        for (int t_ = pair; t_ < n_tp; t_ += n_pairs, ++it) {
+                const int tp = REV_ORDER ? n_tp - 1 - t_ : t_;
             const int acc = it & 1;
             const int64_t mp = (2 * (int64_t)tp + rank) * 128 + lane_grp * 32 + lane;
             const int clip = (int)(mp / PS::RPC), rem = (int)(mp - (int64_t)clip * PS::RPC);
@@ -769,11 +780,13 @@ struct S2Args {
     __nv_bfloat16* y;              // PS layout of the (HO, WO) output, COUT/64 planes out_plane_elems apart
     int64_t in_plane_elems, out_plane_elems;
     int n;
+    int rev;                       // walk the tiles from the last to the first (see tile_order)
 };
 
 template <int CIN, int COUT, int H, int W>
 __global__ void __launch_bounds__(kS1Threads, 1)
 conv3x3_s2_tc_kernel(const S2Args a) {
+    const bool REV_ORDER = a.rev != 0;
     using S = S2Shape<CIN, COUT, H, W>;
     using P2 = Ps2Layout<H, W>;
     constexpr int HO = (H - 1) / 2 + 1, WO = (W - 1) / 2 + 1;
@@ -821,7 +834,8 @@ conv3x3_s2_tc_kernel(const S2Args a) {
                 tc::bulk_g2s(s_w + (size_t)q * COUT * 128, a.w + (size_t)q * COUT * 64, COUT * 128, &w_bar);
             tc::pdl_wait();
             int it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            for (int t_ = blockIdx.x; t_ < n_tiles; t_ += gridDim.x, ++it) {
+                const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
                 const int s = it % S::STAGES;
                 const uint32_t par = (uint32_t)(((it / S::STAGES) & 1) ^ 1);
 #pragma unroll
@@ -839,7 +853,8 @@ conv3x3_s2_tc_kernel(const S2Args a) {
         if (lane == 0) {
             tc::mbar_wait(&w_bar, 0);
             int it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            for (int t_ = blockIdx.x; t_ < n_tiles; t_ += gridDim.x, ++it) {
+                const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
                 const int s = it % S::STAGES, acc = it & 1;
                 const uint32_t par = (uint32_t)((it / S::STAGES) & 1);
                 tc::mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
@@ -883,7 +898,8 @@ conv3x3_s2_tc_kernel(const S2Args a) {
         // ======================= epilogue: + bias, ReLU, bf16 rows in the PS layout of the output ======
         const int lane_grp = warp & 3;
         int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        for (int t_ = blockIdx.x; t_ < n_tiles; t_ += gridDim.x, ++it) {
+                const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
             const int acc = it & 1;
             const int64_t mp = (int64_t)tile * 128 + lane_grp * 32 + lane;
             const int clip = (int)(mp / P2::RPC), rem = (int)(mp - (int64_t)clip * P2::RPC);
@@ -946,7 +962,8 @@ template <int NF>
 __global__ void __launch_bounds__(kS1Threads, 1)
 stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __restrict__ wq,
                const float* __restrict__ bias, __nv_bfloat16* __restrict__ x0, int64_t x0_plane_elems,
-               __nv_bfloat16* __restrict__ xs0, int B) {
+               __nv_bfloat16* __restrict__ xs0, int B, int rev) {
+    const bool REV_ORDER = rev != 0;
     using NS = NetShape<NF>;
     constexpr int kRows = NS::BROWS;                            // GEMM rows per clip
     extern __shared__ unsigned char raw[];
@@ -989,7 +1006,8 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
             tc::bulk_g2s(sB, wq, kStemBBytes, &w_bar);
             tc::pdl_wait();
             int it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            for (int t_ = blockIdx.x; t_ < n_tiles; t_ += gridDim.x, ++it) {
+                const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
                 const int s = it % kStemStages;
                 tc::mbar_wait(&empty_bar[s], (uint32_t)(((it / kStemStages) & 1) ^ 1));
                 tc::mbar_arrive_expect_tx(&full_bar[s], kStemRowsIn * 32);
@@ -1002,7 +1020,8 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
             tc::mbar_wait(&w_bar, 0);
             const uint64_t db = tc::desc_sw128(tc::s32(sB));
             int it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            for (int t_ = blockIdx.x; t_ < n_tiles; t_ += gridDim.x, ++it) {
+                const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
                 const int s = it % kStemStages, acc = it & 1;
                 tc::mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
                 tc::mbar_wait(&full_bar[s], (uint32_t)((it / kStemStages) & 1));
@@ -1024,7 +1043,8 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
 #pragma unroll
         for (int i = 0; i < 32; ++i) bq[i] = __ldg(bias + i);
         int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        for (int t_ = blockIdx.x; t_ < n_tiles; t_ += gridDim.x, ++it) {
+                const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
             const int acc = it & 1;
             const int64_t mp = (int64_t)tile * 128 + lane_grp * 32 + lane;
             const int clip = (int)(mp / kRows), rem = (int)(mp - (int64_t)clip * kRows);
@@ -1322,6 +1342,12 @@ static int launch_cnn_tc_nf(cd_handle* h, const float* d_feat, int64_t B, float*
     __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(ws + P::kOffH2);   // planes 0, 1: conv1 output, plane 2: x1 at (2y, 2x)
     float* x2 = reinterpret_cast<float*>(ws + P::kOffX2);
     constexpr int64_t kPl0 = P::kPs0Rows * 64, kPl1 = P::kPs1Rows * 64;
+    // Tile order alternates down the chain: a kernel that walks its tiles backwards starts with the rows its producer
+    // wrote LAST, which are still dirty in L2 (the hand-offs of a 16 384-clip slab are 3 - 5 x the L2, so only that end
+    // can hit).  feature kernel / map conversion: forward;  stem: backward;  b0 conv1: forward;  b0 conv2: backward;
+    // b1 conv1: forward;  b1 conv2: backward.  CD_TC_ORDER=0 walks every kernel forward (the A/B switch of tools/slab_sweep.py).
+    const char* order_env = getenv("CD_TC_ORDER");
+    const int alt = (order_env && order_env[0] == '0') ? 0 : 1;
     for (int64_t c0 = 0; c0 < B; c0 += kTcChunk) {
         const int n = (int)((B - c0) < kTcChunk ? (B - c0) : kTcChunk);
         if (d_feat) {
@@ -1332,13 +1358,13 @@ static int launch_cnn_tc_nf(cd_handle* h, const float* d_feat, int64_t B, float*
             const int tiles = (int)(((int64_t)n * N::BROWS + 127) / 128);
             CD_CUDA(h, launch_pdl(stem_tc_kernel<NF>, dim3(tiles < h->sm_count ? tiles : h->sm_count), dim3(kS1Threads), kStemSmem, s,
                                   (const __nv_bfloat16*)maps, (const __nv_bfloat16*)W.stem_w, (const float*)W.stem_b, x0,
-                                  (int64_t)(P::kP20Rows * 64), h1 + kPl0, n));
+                                  (int64_t)(P::kP20Rows * 64), h1 + kPl0, n, alt));
         }
         h->launches += 1;
         {
             using S = S2Shape<32, 64, N::H0, N::W0>;
             S2Args q{};
-            q.x = x0; q.w = W.b0c1; q.bias = W.b0c1_b; q.y = h1; q.in_plane_elems = P::kP20Rows * 64; q.out_plane_elems = kPl0; q.n = n;
+            q.x = x0; q.w = W.b0c1; q.bias = W.b0c1_b; q.y = h1; q.in_plane_elems = P::kP20Rows * 64; q.out_plane_elems = kPl0; q.n = n; q.rev = 0;
             const int tiles = (int)(((int64_t)n * P::P20::RPC + 127) / 128);
             CD_CUDA(h, launch_pdl(conv3x3_s2_tc_kernel<32, 64, N::H0, N::W0>, dim3(tiles < h->sm_count ? tiles : h->sm_count),
                                   dim3(kS1Threads), S::SMEM, s, q));
@@ -1348,7 +1374,7 @@ static int launch_cnn_tc_nf(cd_handle* h, const float* d_feat, int64_t B, float*
             using S = S1Shape<64, N::H1, N::W1>;
             S1Args q{};
             q.x = h1; q.w = W.b0c2; q.wskip = W.b0sk; q.bias = W.b0c2_b; q.y_bf16 = x1; q.xs_out = h2 + 2 * kPl1;
-            q.y_plane_elems = P::kP21Rows * 64; q.ps_plane_elems = kPl0; q.n = n;
+            q.y_plane_elems = P::kP21Rows * 64; q.ps_plane_elems = kPl0; q.n = n; q.rev = alt;
             const int tiles = (int)(((int64_t)n * P::Ps0::RPC + 127) / 128);
             const int grid = (tiles < h->sm_count ? tiles : h->sm_count) * S::HALVES;
             CD_CUDA(h, launch_pdl(conv3x3_s1_tc_kernel<64, N::H1, N::W1, false, true>, dim3(grid), dim3(kS1Threads), S::SMEM, s, q));
@@ -1357,7 +1383,7 @@ static int launch_cnn_tc_nf(cd_handle* h, const float* d_feat, int64_t B, float*
         {
             using S = S2Shape<64, 128, N::H1, N::W1>;
             S2Args q{};
-            q.x = x1; q.w = W.b1c1; q.bias = W.b1c1_b; q.y = h2; q.in_plane_elems = P::kP21Rows * 64; q.out_plane_elems = kPl1; q.n = n;
+            q.x = x1; q.w = W.b1c1; q.bias = W.b1c1_b; q.y = h2; q.in_plane_elems = P::kP21Rows * 64; q.out_plane_elems = kPl1; q.n = n; q.rev = 0;
             const int tiles = (int)(((int64_t)n * P::P21::RPC + 127) / 128);
             CD_CUDA(h, launch_pdl(conv3x3_s2_tc_kernel<64, 128, N::H1, N::W1>, dim3(tiles < h->sm_count ? tiles : h->sm_count),
                                   dim3(kS1Threads), S::SMEM, s, q));
@@ -1366,7 +1392,7 @@ static int launch_cnn_tc_nf(cd_handle* h, const float* d_feat, int64_t B, float*
         {
             using S = S1PairShape<N::H2, N::W2>;
             S1Args q{};
-            q.x = h2; q.w = W.b1c2; q.wskip = W.b1sk; q.bias = W.b1c2_b; q.psum = x2; q.ps_plane_elems = kPl1; q.n = n;
+            q.x = h2; q.w = W.b1c2; q.wskip = W.b1sk; q.bias = W.b1c2_b; q.psum = x2; q.ps_plane_elems = kPl1; q.n = n; q.rev = alt;
             const int tiles = (int)(((int64_t)n * P::Ps1::RPC + 127) / 128);
             const int tp = (tiles + 1) / 2, max_pairs = h->sm_count / 2;
             CD_CUDA(h, launch_pdl(conv3x3_s1_pair_tc_kernel<N::H2, N::W2>, dim3(2 * (tp < max_pairs ? tp : max_pairs)),

@@ -181,6 +181,19 @@ __device__ __forceinline__ void st_out(uint4* p, uint4 v) {
 #endif
 }
 
+// the stem's map is read back by the very next kernel: plain stores, so that its last-written end can still be in L2
+// (CD_MAP_STCS=1 gives them the streaming hint too, for comparison)
+#ifndef CD_MAP_STCS
+#define CD_MAP_STCS 0
+#endif
+__device__ __forceinline__ void st_map(uint4* p, uint4 v) {
+#if CD_MAP_STCS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 // ----------------------------------------------------------------------------------------------
 // 16-point DFT in registers, radix 4 x 4
 // ----------------------------------------------------------------------------------------------
@@ -728,7 +741,7 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float inv2, float* _
     if (staged) {                                                      // stage A -> global, full sectors
         const uint4* s16 = reinterpret_cast<const uint4*>(stage);
         uint4* g16 = reinterpret_cast<uint4*>(mo);
-        for (int i = tid; i < kStageRowsA * kBmapB * 2; i += kFeatThreads) st_out(g16 + i, s16[i]);
+        for (int i = tid; i < kStageRowsA * kBmapB * 2; i += kFeatThreads) st_map(g16 + i, s16[i]);
     }
 
     // ---- MFCC = DCT-II(13 x 64) of the floored dB, then (x - mean) / (std + 1e-8) ---------------
@@ -816,7 +829,7 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float inv2, float* _
         const int n16 = (map_rows / 4 - kStageRowsA) * kBmapB * 2;    // 16-byte pieces of stage B
         const uint4* s16 = reinterpret_cast<const uint4*>(stage);
         uint4* g16 = reinterpret_cast<uint4*>(mo) + kStageRowsA * kBmapB * 2;
-        for (int i = tid; i < n16; i += kFeatThreads) st_out(g16 + i, s16[i]);
+        for (int i = tid; i < n16; i += kFeatThreads) st_map(g16 + i, s16[i]);
     }
 
     if (PCEN) {
