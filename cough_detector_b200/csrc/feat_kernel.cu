@@ -67,6 +67,10 @@ namespace cd {
 #ifndef CD_ABLATE
 #define CD_ABLATE 0
 #endif
+#ifndef CD_PIN_CTX
+#define CD_PIN_CTX 1
+#endif
+
 constexpr int kFeatWarps   = CD_FEAT_WARPS;
 constexpr int kFeatThreads = kFeatWarps * 32;
 constexpr int kFeatCtasPerSm = CD_FEAT_CTAS;  // one CTA's reductions / tail overlap the others' FFTs
@@ -348,7 +352,7 @@ struct LaneCtx {
 #endif
     uint32_t tw_s;           // shared address of this lane's row of the twiddle table
     float2 mw[kMelSlots];    // mel taps of the lane's two segments (cd_common.cuh)
-    int bin_lo, bin_hi;
+    uint32_t mel_s[kMelSlots]; // shared addresses of the power pairs the lane's mel slots read (unused slots: the zero slot)
     uint32_t xw_s;           // shared address this lane writes exchange row 0 to
     uint32_t xr_s;           // shared address this lane reads its 16 stage-2 inputs from (128 B, contiguous)
     uint32_t pw_s;           // shared address of the warp's power region
@@ -368,8 +372,6 @@ __device__ __forceinline__ void lane_ctx_init(LaneCtx& L, const FeatTables* __re
     L.tw_s = smem_u32(twl + lane * kTwPitch);
 #pragma unroll
     for (int s = 0; s < kMelSlots; ++s) L.mw[s] = tables->melt[s][lane];
-    L.bin_lo = tables->melb[0][lane];
-    L.bin_hi = tables->melb[1][lane];
     const int m = lane, c1 = m & 1;
     // stage-1 lane m = 2 b + c1 writes row r at r * 34 + c1 * 16 + (b ^ 8 c1): the reader of (r, c1) gets 16 contiguous
     // float2 (c1 = 1: its two halves swapped, which the final butterfly's constants absorb), writes are conflict-free
@@ -389,6 +391,24 @@ __device__ __forceinline__ void lane_ctx_init(LaneCtx& L, const FeatTables* __re
     L.pb_s = L.pw_s + 8u * (uint32_t)pb;
     L.pstep = 8 * st;
     L.partner = ((16 - r) & 15) + 16 * (1 - c);
+    {
+        // the lane's mel slots: bins b, b + 1, .. of its two segments at padded index k + 2 (k / 16); a slot beyond the segment
+        // reads the region's zero slot instead of being predicated off
+        const int lo = tables->melb[0][lane], hi = tables->melb[1][lane];
+#pragma unroll
+        for (int sl = 0; sl < kMelSlots; ++sl) {
+            const int packed = sl < kMelSlotsLo ? lo : hi, k = sl < kMelSlotsLo ? sl : sl - kMelSlotsLo;
+            const int bin = (packed & 0xff) + k;
+            L.mel_s[sl] = L.pw_s + 8u * (uint32_t)(k < (packed >> 8) ? bin + 2 * (bin >> 4) : kPowZero);
+        }
+    }
+#if CD_PIN_CTX
+    // opaque to the compiler from here on: it would otherwise re-derive these lane constants from %tid inside the pair loop
+    // (about 30 integer instructions per pair) instead of keeping six registers
+    asm volatile("" : "+r"(L.xw_s), "+r"(L.xr_s), "+r"(L.tw_s), "+r"(L.p0_s), "+r"(L.pb_s), "+r"(L.pw_s));
+    asm volatile("" : "+r"(L.pstep), "+r"(L.partner));
+    asm volatile("" : "+r"(L.mel_s[0]), "+r"(L.mel_s[1]), "+r"(L.mel_s[2]), "+r"(L.mel_s[3]), "+r"(L.mel_s[4]), "+r"(L.mel_s[5]));
+#endif
 }
 
 // One frame pair, first half: x[a] = z[32 a + lane], a = 0..12 (x[13..15] ignored) -> the pair's two power spectra
@@ -508,21 +528,15 @@ __device__ __forceinline__ void mel_pair(const LaneCtx& L, int lane, float2& lo,
     hi = lo;
     float2 ulo = lo, uhi = lo;
     {
-        // unused slots read the region's zero slot instead of being predicated off
-        const uint32_t zero_s = L.pw_s + 8u * kPowZero;
-        const int b0 = L.bin_lo & 0xff, n0 = L.bin_lo >> 8;
 #pragma unroll
         for (int s = 0; s < kMelSlotsLo; ++s) {
-            const int bin = b0 + s;
-            const float2 pw = lds64(s < n0 ? L.pw_s + 8u * (uint32_t)(bin + 2 * (bin >> 4)) : zero_s);
+            const float2 pw = lds64(L.mel_s[s]);
             lo = fma2s(L.mw[s].x, pw, lo);
             ulo = fma2s(L.mw[s].y, pw, ulo);
         }
-        const int b1 = L.bin_hi & 0xff, n1 = L.bin_hi >> 8;
 #pragma unroll
         for (int s = 0; s < kMelSlotsHi; ++s) {
-            const int bin = b1 + s;
-            const float2 pw = lds64(s < n1 ? L.pw_s + 8u * (uint32_t)(bin + 2 * (bin >> 4)) : zero_s);
+            const float2 pw = lds64(L.mel_s[kMelSlotsLo + s]);
             hi = fma2s(L.mw[kMelSlotsLo + s].x, pw, hi);
             uhi = fma2s(L.mw[kMelSlotsLo + s].y, pw, uhi);
         }
@@ -945,6 +959,9 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
     __syncthreads();
     int wp0, wp1;
     warp_pair_range(warp, wp0, wp1);
+#if CD_PIN_CTX
+    asm volatile("" : "+r"(wp0), "+r"(wp1));       // (kept in registers: otherwise re-derived from %tid in every pair)
+#endif
     float w[13];                                                       // the lane's window weights, loaded once
     lane_window(tables, 1.0f, lane, w);
     const bool var = (mode & kModeMask) == kModeVar;
