@@ -1000,57 +1000,69 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
             if (pass) lane_window(tables, pre, lane, w);               // (rare) pre-scaled second pass
             float pmax = 0.f, amax = peak_pre;
             float raw[18];
-            bool have = false;                                         // raw[] already holds this pair's samples
-            for (int p = wp0; p < wp1; ++p) {
-#if CD_L2PF == 3
-                if (lane == 0 && pass == 0 && p == (wp0 + wp1) / 2) prefetch_next(warp, kFeatWarps);
-#endif
-                const bool edge = (p == 0) || (p >= 49);
-                const bool second = (2 * p + 1) < kFrames;             // pair 50 holds frame 100 only
-                const int s0 = 2 * kHop * p - kWin / 2 + lane;         // this lane's sample of window tap 0
-                float2 x[16], lo, hi;
-                // ---- raw[] <- the pair's 18 samples per lane (ONE copy of the FFT / mel code follows for all three cases) ----
-                if (edge || !fast) {
-                    // reflect-padded pairs and clips that are trimmed / padded: every sample through the index mapping.
-                    // (Pair 50's second frame does not exist: its samples are reflected ones like any other, the frame is
-                    // computed and store_pair drops it.)
-                    if (fast) {
+            // Reflected sample s (torch.stft's reflect padding) of a whole clip and, with pre-emphasis, the peak of the RAW
+            // samples it touches (reflected samples are samples: they count for the peak).
+            auto reflect_fast = [&](int s) {
+                if (PRE) {
+                    int i = s < 0 ? -s : s;
+                    i = i >= kSeg ? 2 * (kSeg - 1) - i : i;
+                    amax = fmaxf(amax, fabsf((float)v.src[i]));
+                }
+                return sample_reflect<PRE, true>(v, s, coef);
+            };
+            // ---- prologue: the 18 samples per lane of the run's first pair.  Every later pair takes its first eight from
+            //      the pair before it (registers) and requests ten new ones a pair ahead, so the loop below has ONE shape
+            //      for edge and interior pairs alike. -----------------------------------------------------------------
+            {
+                const int s0 = 2 * kHop * wp0 - kWin / 2 + lane;
+                if (!fast) {                                           // trimmed / padded clip: everything through the index mapping
 #pragma unroll
-                        for (int q = 0; q < 18; ++q) raw[q] = sample_reflect<PRE, true>(v, s0 + 32 * q, coef);
+                    for (int q = 0; q < 18; ++q) raw[q] = sample_reflect<PRE, false>(v, s0 + 32 * q, coef);
+                } else if (wp0 == 0) {                                 // pair 0 starts in the left reflect padding
 #pragma unroll
-                        for (int q = 0; q < 18; ++q) {                 // reflected samples are samples: they count for the peak
-                            if (PRE) {
-                                int i = s0 + 32 * q;
-                                i = i < 0 ? -i : i;
-                                i = i >= kSeg ? 2 * (kSeg - 1) - i : i;
-                                amax = fmaxf(amax, fabsf((float)v.src[i]));
-                            } else {
-                                amax = fmaxf(amax, fabsf(raw[q]));
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 18; ++q) raw[q] = sample_reflect<PRE, false>(v, s0 + 32 * q, coef);
-                    }
-                } else if (!have) {                                    // first interior pair of the warp's run
+                    for (int q = 0; q < 18; ++q) raw[q] = reflect_fast(s0 + 32 * q);
+                } else {
                     const T* ps = v.src + s0;
 #pragma unroll
                     for (int q = 0; q < 18; ++q) {
                         const float xq = (float)ps[32 * q];
-                        amax = fmaxf(amax, fabsf(xq));
+                        if (PRE) amax = fmaxf(amax, fabsf(xq));
                         raw[q] = PRE ? __fsub_rn(xq, __fmul_rn(coef, (float)ps[32 * q - 1])) : xq;
                     }
-                } else if (!PRE) {                                     // requested during the previous pair: they arrive about now
+                }
+                if (fast && !PRE) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) amax = fmaxf(amax, fabsf(raw[q]));      // the loop counts raw[8..17]
+                }
+            }
+            for (int p = wp0; p < wp1; ++p) {
+#if CD_L2PF == 3
+                if (lane == 0 && pass == 0 && p == (wp0 + wp1) / 2) prefetch_next(warp, kFeatWarps);
+#endif
+                const bool second = (2 * p + 1) < kFrames;             // pair 50 holds frame 100 only: its second frame is computed
+                                                                       // from reflected samples like any other and dropped by store_pair
+                const int n0 = 2 * kHop * (p + 1) - kWin / 2 + lane;   // the NEXT pair's sample of window tap 0
+                float2 x[16], lo, hi;
+                if (fast && !PRE) {                                    // requested during the previous pair: they arrive about now
 #pragma unroll
                     for (int q = 8; q < 18; ++q) amax = fmaxf(amax, fabsf(raw[q]));
                 }
                 form_inputs(raw, w, x);
-                // ---- the next pair's samples: 8 carried in registers (pair 0 hands its last eight to pair 1 as well), 10 new
-                //      ones requested before the FFT and consumed after the mel contraction -----------------------------
-                have = fast && (p + 1 < wp1) && (p + 1) < 49;
+                // ---- the next pair's samples: 8 carried in registers, 10 new ones requested before the FFT and consumed
+                //      after the mel contraction ---------------------------------------------------------------------
 #pragma unroll
                 for (int q = 0; q < 8; ++q) raw[q] = raw[q + 10];
-                if (have) request_next_impl<PRE>(v.src + s0 + 2 * kHop, raw, amax, coef);
+                if (p + 1 < wp1) {
+                    if (!fast) {
+#pragma unroll
+                        for (int q = 8; q < 18; ++q) raw[q] = sample_reflect<PRE, false>(v, n0 + 32 * q, coef);
+                    } else if (p + 1 >= 49) {                          // pairs 49 and 50 reach into the right reflect padding
+#pragma unroll
+                        for (int q = 8; q < 18; ++q) raw[q] = reflect_fast(n0 + 32 * q);
+                    } else {
+                        request_next_impl<PRE>(v.src + n0, raw, amax, coef);
+                    }
+                }
                 fft_pair(x, L, lane);
                 mel_pair(L, lane, lo, hi);
                 pmax = fmaxf(pmax, store_pair(S.db, lane, p, second, lo, hi));
