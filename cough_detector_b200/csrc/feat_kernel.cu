@@ -67,6 +67,10 @@ namespace cd {
 #ifndef CD_ABLATE
 #define CD_ABLATE 0
 #endif
+#ifndef CD_PAIR_UNROLL
+#define CD_PAIR_UNROLL 1
+#endif
+constexpr int kPairUnroll = CD_PAIR_UNROLL;      // unroll of the frame-pair loop (2 was measured: see profiles/r2_feat_ablation.txt)
 #ifndef CD_PIN_CTX
 #define CD_PIN_CTX 1
 #endif
@@ -1035,6 +1039,7 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
                     for (int q = 0; q < 8; ++q) amax = fmaxf(amax, fabsf(raw[q]));      // the loop counts raw[8..17]
                 }
             }
+#pragma unroll kPairUnroll
             for (int p = wp0; p < wp1; ++p) {
 #if CD_L2PF == 3
                 if (lane == 0 && pass == 0 && p == (wp0 + wp1) / 2) prefetch_next(warp, kFeatWarps);
