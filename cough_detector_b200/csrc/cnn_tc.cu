@@ -442,7 +442,7 @@ conv3x3_s1_tc_kernel(const S1Args a) {
             tc::pdl_wait();                            // weights are in flight; the activations need the previous kernel
             int it = 0;
             for (int t_ = cta; t_ < n_tiles; t_ += n_cta, ++it) {
-                const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
+                [[maybe_unused]] const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
                 const int s = it % S::STAGES;
                 const uint32_t par = (uint32_t)(((it / S::STAGES) & 1) ^ 1);
 #pragma unroll
@@ -461,7 +461,7 @@ conv3x3_s1_tc_kernel(const S1Args a) {
             tc::mbar_wait(&w_bar, 0);
             int it = 0;
             for (int t_ = cta; t_ < n_tiles; t_ += n_cta, ++it) {
-                const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
+                [[maybe_unused]] const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
                 const int s = it % S::STAGES, acc = it & 1;
                 const uint32_t par = (uint32_t)((it / S::STAGES) & 1);
                 tc::mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
@@ -485,8 +485,11 @@ conv3x3_s1_tc_kernel(const S1Args a) {
                         }
                     } else {
                         const uint32_t shift = (uint32_t)(PS::WP + 1) * 128;                          // centre tap
+                        // the skip projection reads the block's INPUT channels (C / 2): with C = 64 only the first 32 of a
+                        // skip-plane row's 64 channel slots are populated (the rest, and their weights, are zero)
+                        constexpr int kSkipSteps = C == 64 ? 2 : 4;
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4)
+                        for (int k4 = 0; k4 < kSkipSteps; ++k4)
                             tc::umma_bf16(d, tc::desc_adv(da, shift + k4 * 32),
                                           tc::desc_adv(dw, 9 * S::NPL * 8192 + k4 * 32), IDESC, 1u);
                     }
@@ -500,7 +503,7 @@ conv3x3_s1_tc_kernel(const S1Args a) {
         const int lane_grp = warp & 3;
         int it = 0;
         for (int t_ = cta; t_ < n_tiles; t_ += n_cta, ++it) {
-                const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
+                [[maybe_unused]] const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
             const int acc = it & 1;
             const int64_t mp = (int64_t)tile * 128 + lane_grp * 32 + lane;      // padded-row index m'
             const int clip = (int)(mp / PS::RPC), rem = (int)(mp - (int64_t)clip * PS::RPC);
@@ -639,7 +642,7 @@ conv3x3_s1_pair_tc_kernel(const S1Args a) {
             tc::pdl_wait();
             int it = 0;
             for (int t_ = pair; t_ < n_tp; t_ += n_pairs, ++it) {
-                const int tp = REV_ORDER ? n_tp - 1 - t_ : t_;
+                [[maybe_unused]] const int tp = REV_ORDER ? n_tp - 1 - t_ : t_;
                 const int64_t tile = 2 * (int64_t)tp + rank;
 #pragma unroll
                 for (int q = 0; q < NB; ++q) {
@@ -658,7 +661,7 @@ conv3x3_s1_pair_tc_kernel(const S1Args a) {
                 const uint64_t dw = tc::desc_sw128(tc::s32(s_w));
                 int it = 0;
                 for (int t_ = pair; t_ < n_tp; t_ += n_pairs, ++it) {
-                const int tp = REV_ORDER ? n_tp - 1 - t_ : t_;
+                [[maybe_unused]] const int tp = REV_ORDER ? n_tp - 1 - t_ : t_;
                     const int acc = it & 1;
                     tc::mbar_wait_cluster(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
                     const uint32_t d = tmem_base + acc * 128;
@@ -691,7 +694,7 @@ conv3x3_s1_pair_tc_kernel(const S1Args a) {
                 // ======================= relay (peer): tell the leader when my slots are full ============
                 int it = 0;
                 for (int t_ = pair; t_ < n_tp; t_ += n_pairs, ++it) {
-                const int tp = REV_ORDER ? n_tp - 1 - t_ : t_;
+                [[maybe_unused]] const int tp = REV_ORDER ? n_tp - 1 - t_ : t_;
 #pragma unroll
                     for (int q = 0; q < NB; ++q) {
                         tc::mbar_wait(&full_bar[q], (uint32_t)(it & 1));
@@ -705,7 +708,7 @@ conv3x3_s1_pair_tc_kernel(const S1Args a) {
         const int lane_grp = warp & 3;
         int it = 0;
         for (int t_ = pair; t_ < n_tp; t_ += n_pairs, ++it) {
-                const int tp = REV_ORDER ? n_tp - 1 - t_ : t_;
+                [[maybe_unused]] const int tp = REV_ORDER ? n_tp - 1 - t_ : t_;
             const int acc = it & 1;
             const int64_t mp = (2 * (int64_t)tp + rank) * 128 + lane_grp * 32 + lane;
             const int clip = (int)(mp / PS::RPC), rem = (int)(mp - (int64_t)clip * PS::RPC);
@@ -835,7 +838,7 @@ conv3x3_s2_tc_kernel(const S2Args a) {
             tc::pdl_wait();
             int it = 0;
             for (int t_ = blockIdx.x; t_ < n_tiles; t_ += gridDim.x, ++it) {
-                const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
+                [[maybe_unused]] const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
                 const int s = it % S::STAGES;
                 const uint32_t par = (uint32_t)(((it / S::STAGES) & 1) ^ 1);
 #pragma unroll
@@ -854,7 +857,7 @@ conv3x3_s2_tc_kernel(const S2Args a) {
             tc::mbar_wait(&w_bar, 0);
             int it = 0;
             for (int t_ = blockIdx.x; t_ < n_tiles; t_ += gridDim.x, ++it) {
-                const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
+                [[maybe_unused]] const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
                 const int s = it % S::STAGES, acc = it & 1;
                 const uint32_t par = (uint32_t)((it / S::STAGES) & 1);
                 tc::mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
@@ -899,7 +902,7 @@ conv3x3_s2_tc_kernel(const S2Args a) {
         const int lane_grp = warp & 3;
         int it = 0;
         for (int t_ = blockIdx.x; t_ < n_tiles; t_ += gridDim.x, ++it) {
-                const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
+                [[maybe_unused]] const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
             const int acc = it & 1;
             const int64_t mp = (int64_t)tile * 128 + lane_grp * 32 + lane;
             const int clip = (int)(mp / P2::RPC), rem = (int)(mp - (int64_t)clip * P2::RPC);
@@ -1007,7 +1010,7 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
             tc::pdl_wait();
             int it = 0;
             for (int t_ = blockIdx.x; t_ < n_tiles; t_ += gridDim.x, ++it) {
-                const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
+                [[maybe_unused]] const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
                 const int s = it % kStemStages;
                 tc::mbar_wait(&empty_bar[s], (uint32_t)(((it / kStemStages) & 1) ^ 1));
                 tc::mbar_arrive_expect_tx(&full_bar[s], kStemRowsIn * 32);
@@ -1021,7 +1024,7 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
             const uint64_t db = tc::desc_sw128(tc::s32(sB));
             int it = 0;
             for (int t_ = blockIdx.x; t_ < n_tiles; t_ += gridDim.x, ++it) {
-                const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
+                [[maybe_unused]] const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
                 const int s = it % kStemStages, acc = it & 1;
                 tc::mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
                 tc::mbar_wait(&full_bar[s], (uint32_t)((it / kStemStages) & 1));
@@ -1044,7 +1047,7 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
         for (int i = 0; i < 32; ++i) bq[i] = __ldg(bias + i);
         int it = 0;
         for (int t_ = blockIdx.x; t_ < n_tiles; t_ += gridDim.x, ++it) {
-                const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
+                [[maybe_unused]] const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
             const int acc = it & 1;
             const int64_t mp = (int64_t)tile * 128 + lane_grp * 32 + lane;
             const int clip = (int)(mp / kRows), rem = (int)(mp - (int64_t)clip * kRows);
