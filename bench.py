@@ -31,10 +31,10 @@ AUDIO_BYTES = 64000           # 16000 fp32 samples
 FEAT_BYTES = 36360            # 90 x 101 fp32
 CNN_FLOPS = 42_865_600        # 2 x 21 432 800 MAC per clip
 # feat_kernel dram__bytes_read + dram__bytes_write per clip: a CONSTANT taken from one ncu --set full capture of this launch
-# (profiles/r2_ncu_feat_kernel_65536.csv: 4.284 GB + 2.352 GB per 65 536-clip launch), scaled by the launch size below
-NCU_TRAFFIC_PER_CLIP = 101_254
-NCU_TRAFFIC_SOURCE = ("ncu --set full of cd_feat_forward over 65 536 clips (profiles/r2_ncu_feat_kernel_65536.csv): dram read 4.284 GB + "
-                      "write 2.352 GB = 101 254 B per clip, 1.009 x the algorithmic bytes (a constant in bench.py, scaled by the launch size)")
+# (profiles/r2_ncu_feat_kernel_65536.csv: 4.252 GB + 2.351 GB per 65 536-clip launch), scaled by the launch size below
+NCU_TRAFFIC_PER_CLIP = 100_757
+NCU_TRAFFIC_SOURCE = ("ncu --set full of cd_feat_forward over 65 536 clips (profiles/r2_ncu_feat_kernel_65536.csv): dram read 4.252 GB + "
+                      "write 2.351 GB = 100 757 B per clip, 1.004 x the algorithmic bytes (a constant in bench.py, scaled by the launch size)")
 METRIC = "1-s clips/sec (mel+MFCC+CNN)"
 
 

@@ -1022,7 +1022,8 @@ feat_kernel(const T* __restrict__ audio, const int64_t* __restrict__ offs, const
                 if (!fast) {                                           // trimmed / padded clip: everything through the index mapping
 #pragma unroll
                     for (int q = 0; q < 18; ++q) raw[q] = sample_reflect<PRE, false>(v, s0 + 32 * q, coef);
-                } else if (wp0 == 0) {                                 // pair 0 starts in the left reflect padding
+                } else if (wp0 == 0 || wp0 >= 49) {                    // pair 0 starts in the left reflect padding (a run that
+                                                                       // started at pair 49 / 50 would reach into the right one)
 #pragma unroll
                     for (int q = 0; q < 18; ++q) raw[q] = reflect_fast(s0 + 32 * q);
                 } else {
