@@ -75,10 +75,10 @@ class SpecAugment:
         return x if spectrogram.is_cuda else x.to(spectrogram.device)
 
     def __call__(self, spectrogram: torch.Tensor) -> torch.Tensor:
-        """(channels, freq, time) or (batch, channels, freq, time); a batch shares ONE set of masks, as in the reference
-        (mask_along_axis: "All examples will have the same mask interval")."""
-        if spectrogram.dim() not in (3, 4):
-            raise ValueError(f"expected (C, F, T) or (B, C, F, T), got {tuple(spectrogram.shape)}")
+        """(..., freq, time) -- usually (channels, freq, time) or (batch, channels, freq, time); every leading index shares ONE
+        set of masks, as in the reference (mask_along_axis: "All examples will have the same mask interval")."""
+        if spectrogram.dim() < 2:
+            raise ValueError(f"Spectrogram must have at least two dimensions (time and frequency) ({spectrogram.dim()} given).")
         n_rows, n_cols = int(spectrogram.shape[-2]), int(spectrogram.shape[-1])
         m = self.sample(n_rows, n_cols)
         if m is None:

@@ -837,11 +837,17 @@ __device__ __forceinline__ void feat_tail(SM& S, float top, float inv2, float* _
         }
     }
     if (staged) {
-        // left / right zero columns of stage B: one thread per padding column
-        const int k = tid - (kFeatThreads - 7);                        // the last seven threads
-        if (k >= 0) {
-            const int C = k < 3 ? k : 101 + k;                         // 0, 1, 2, 104, 105, 106, 107
-            for (int R = 4 * kStageRowsA; R < map_rows; ++R) stage[bmap_offset(R, C) - kStageBase] = bz;
+        // left / right zero columns of stage B (C = 0, 1, 2 and 104..107: the last block column is all padding): one thread
+        // per (row, side), the four right-hand cells as one 8-byte store, the three left-hand ones as 4 + 2 bytes
+        for (int i = tid; i < 2 * (map_rows - 4 * kStageRowsA); i += kFeatThreads) {
+            const int R = 4 * kStageRowsA + (i >> 1);
+            if (i & 1) {
+                *reinterpret_cast<uint2*>(stage + (bmap_offset(R, 104) - kStageBase)) = make_uint2(0u, 0u);
+            } else {
+                __nv_bfloat16* l = stage + (bmap_offset(R, 0) - kStageBase);
+                *reinterpret_cast<uint32_t*>(l) = 0u;
+                l[2] = bz;
+            }
         }
         __syncthreads();
         const int n16 = (map_rows / 4 - kStageRowsA) * kBmapB * 2;    // 16-byte pieces of stage B

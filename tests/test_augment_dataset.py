@@ -56,6 +56,31 @@ def test_host_sampler_draws_like_the_reference():
             assert np.array_equal((y[0] == 0).numpy(), zero[call]), (ci, call)
 
 
+def test_host_sampler_edge_cases():
+    """p = 0 never touches the generators' torch side; a zero mask parameter draws nothing (the reference returns before
+    torch.rand); intervals stay inside the axis; more than 8 masks per axis is refused (the kernel's limit)."""
+    sa = SpecAugment(p=0.0)
+    torch.manual_seed(5)
+    before = torch.rand(1)
+    torch.manual_seed(5)
+    assert sa.sample(90, 101) is None and torch.equal(torch.rand(1), before)
+    x = torch.rand(1, 90, 101)
+    assert sa(x) is x                                              # untouched input comes back as is, like the reference
+    sa0 = SpecAugment(freq_mask_param=0, time_mask_param=0, n_freq_masks=2, n_time_masks=2, p=1.0)
+    torch.manual_seed(5)
+    assert sa0.sample(90, 101) == [0, 0] * 4 and torch.equal(torch.rand(1), before)
+    random.seed(1)
+    torch.manual_seed(1)
+    m = SpecAugment(freq_mask_param=10, time_mask_param=20, n_freq_masks=3, n_time_masks=1, p=1.0).sample_batch(200, 90, 101)
+    f, t = m[:, :6].reshape(-1, 2), m[:, 6:].reshape(-1, 2)
+    assert (f[:, 0] >= 0).all() and (f[:, 1] <= 90).all() and ((f[:, 1] - f[:, 0]) < 10).all() and ((f[:, 1] - f[:, 0]) >= 0).all()
+    assert (t[:, 0] >= 0).all() and (t[:, 1] <= 101).all() and ((t[:, 1] - t[:, 0]) < 20).all()
+    with pytest.raises(NotImplementedError):
+        SpecAugment(n_freq_masks=9)
+    with pytest.raises(ValueError):
+        SpecAugment(p=1.0)(torch.rand(101))                        # torchaudio: "at least two dimensions"
+
+
 @pytest.mark.gpu
 def test_spec_augment_kernel_matches_reference():
     cases, batch = gio.load_spec_augment()
