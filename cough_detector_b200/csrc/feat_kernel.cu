@@ -1188,14 +1188,27 @@ stream_window_kernel(const float* __restrict__ audio, int64_t hop, int64_t n_win
     if (lane == 0) S.xb[warp][kXchElems + kPowZero] = make_float2(0.f, 0.f);
     __syncthreads();
     const int64_t h = hop / kHop;
+    float w[13];                                                       // the lane's window weights, loaded once
+    lane_window(tables, 1.0f, lane, w);
     for (int64_t j = blockIdx.x; j < n_windows; j += gridDim.x) {
         if (lane == 0) S.xb[warp][kXchElems + kPowZero] = make_float2(0.f, 0.f);   // (the tail's map stage may have used it)
         const float peak = tid < kSeg / kHop ? bmax[j * h + tid] : 0.f;
         float wmax = 0.f;
+        {
+            // frames 2..97 come from the shared global frames j h + t.  Item = (mel band, frame pair): two coalesced loads
+            // (consecutive lanes = consecutive bands of one frame) and one conflict-free 8-byte store into the band's tile
+            // row -- by ALL warps, requested before the edge pairs below so the L2 latency hides under their FFTs.
+            const float* src = melp + (j * h + 2) * kMels;
+#pragma unroll 4
+            for (int i = tid; i < 48 * kMels; i += kFeatThreads) {
+                const int u = i >> 6, m = i & 63;
+                const float d0 = src[(2 * u) * kMels + m], d1 = src[(2 * u + 1) * kMels + m];
+                *reinterpret_cast<float2*>(S.db + m * kTilePitch + 2 * u + 2) = make_float2(d0, d1);
+                wmax = fmaxf(wmax, fmaxf(d0, d1));
+            }
+        }
         if (warp < 3) {
             // frames that touch this window's reflect padding: pairs (0,1), (98,99), (100,-)
-            float w[13];
-            lane_window(tables, 1.0f, lane, w);
             const int p = warp == 0 ? 0 : 48 + warp;
             const bool second = (2 * p + 1) < kFrames;
             ClipView<float> v;
@@ -1211,16 +1224,7 @@ stream_window_kernel(const float* __restrict__ audio, int64_t hop, int64_t n_win
             form_inputs(raw, w, x);
             fft_pair(x, L, lane);
             mel_pair(L, lane, lo, hi);
-            wmax = store_pair(S.db, lane, p, second, lo, hi);
-        } else {
-            // frames 2..97 come from the shared global frames j h + t
-            const float* src = melp + (j * h + 2) * kMels;
-            for (int i = tid - 96; i < 96 * kMels; i += kFeatThreads - 96) {
-                const int t = i >> 6, m = i & 63;
-                const float d = src[i];
-                S.db[m * kTilePitch + t + 2] = d;
-                wmax = fmaxf(wmax, d);
-            }
+            wmax = fmaxf(wmax, store_pair(S.db, lane, p, second, lo, hi));
         }
         const float2 mx = block_reduce2<true>(make_float2(wmax, peak), S.red);
         const float inv = mx.y > 0.f ? 1.0f / mx.y : 1.0f;           // normalize(): skipped for silence
