@@ -1124,16 +1124,27 @@ struct MelSmem {
 };
 using StreamSmem = FeatSmem;
 
-// bmax[i] = max |x[160 i .. 160 i + 159]|, one warp per block
+// bmax[i] = max |x[160 i .. 160 i + 159]|: one warp per FOUR consecutive blocks, all twenty loads of a lane issued before the
+// first is used (the kernel is pure latency: one block per warp kept 5 loads in flight and ran at a fifth of the HBM rate)
+constexpr int kBmaxPerWarp = 4;
 __global__ void __launch_bounds__(256)
 block_max_kernel(const float* __restrict__ audio, int64_t n_blocks, float* __restrict__ bmax) {
-    const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (i >= n_blocks) return;
-    const float* p = audio + i * kHop;
-    float m = 0.f;
-    for (int k = threadIdx.x & 31; k < kHop; k += 32) m = fmaxf(m, fabsf(p[k]));
-    m = warp_max(m);
-    if ((threadIdx.x & 31) == 0) bmax[i] = m;
+    const int lane = threadIdx.x & 31;
+    const int64_t i0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * kBmaxPerWarp;
+    if (i0 >= n_blocks) return;
+    const float* p = audio + i0 * kHop;
+    const int64_t n = min((int64_t)kBmaxPerWarp, n_blocks - i0) * kHop;            // samples this warp covers
+    float v[kBmaxPerWarp * kHop / 32];
+#pragma unroll
+    for (int k = 0; k < kBmaxPerWarp * kHop / 32; ++k) v[k] = 32 * k + lane < n ? fabsf(p[32 * k + lane]) : 0.f;
+#pragma unroll
+    for (int b = 0; b < kBmaxPerWarp; ++b) {
+        float m = 0.f;
+#pragma unroll
+        for (int k = 0; k < kHop / 32; ++k) m = fmaxf(m, v[b * (kHop / 32) + k]);
+        m = warp_max(m);
+        if (lane == 0 && i0 + b < n_blocks) bmax[i0 + b] = m;
+    }
 }
 
 // melp[f][64] = un-normalised mel power of global frame f, f in [2, F)
@@ -1344,7 +1355,7 @@ int launch_features(cd_handle* h, const float* d_audio, const int64_t* d_offsets
         }
         float* melp = h->d_ws_stream;
         float* bmax = melp + (size_t)F * kMels;
-        block_max_kernel<<<(unsigned)((n_blocks + 7) / 8), 256, 0, s>>>(d_audio, n_blocks, bmax);
+        block_max_kernel<<<(unsigned)((n_blocks + 8 * kBmaxPerWarp - 1) / (8 * kBmaxPerWarp)), 256, 0, s>>>(d_audio, n_blocks, bmax);
         const int64_t pair_ctas = ((F - 1) / 2 + kFeatWarps - 1) / kFeatWarps;
         const int mel_grid = (int)(pair_ctas < 4 * slots ? pair_ctas : 4 * slots);
         if (pre)
