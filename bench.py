@@ -8,7 +8,7 @@ One "step" = one pass of the hot path over one batch of 16 384 synthetic 1-s cli
 only the final (B, 2) logit gather.  Prints ONE JSON line on rank 0 (contract in the task brief):
 value = device-resident throughput, e2e = the same through cd_e2e_forward_host with pinned HOST
 buffers (H2D of the audio and D2H of the logits inside the timed region), roofline = the feature
-kernel against the measured HBM peak, cpu_baseline = the oracle port on the host cores, stream =
+kernel against the measured HBM peak, cpu_baseline = the reference's own bytecode (oracle/_ref, else the oracle port) on the host cores, stream =
 BASELINE configs[3] (1 h of audio, 100 ms hop, time-sharded), sweep = configs[4] (4 194 304 clips
 generated per chunk on the device, strong scaling).  Timed regions last >= 1 s.
 """
@@ -39,22 +39,39 @@ METRIC = "1-s clips/sec (mel+MFCC+CNN)"
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (same torchaudio/torch calls as the reference's per-clip loop)
+# CPU arm: the unmodified reference from oracle/_ref when built (oracle/ref_build.py), else the oracle port
 # ------------------------------------------------------------------------------------------------
 def _cpu_worker(args):
+    """One single-threaded worker of the CPU arm.  With oracle/_ref built (oracle/ref_build.py: the unmodified
+    reference's own bytecode) it runs the reference itself, per clip as BASELINE.md §5 says; otherwise the port."""
     seed, n = args
     import torch
     torch.set_num_threads(1)
     from cough_detector_b200 import synth
-    from oracle import reference_port as rp
+    from oracle import ref_build
+    ref = ref_build.load()
     torch.manual_seed(0)
+    clips = synth.synth_batch(n, seed=seed, device="cpu")
+    if ref is not None:
+        pp = ref["preprocessing"].AudioPreprocessor(use_pcen=False, use_pre_emphasis=False, use_delta_delta=False,
+                                                    use_spectral_contrast=False)
+        model = ref["model"].create_model("residual", n_mels=90, num_classes=2, in_channels=1).eval()
+        t0 = time.perf_counter()
+        out = []
+        with torch.no_grad():
+            for w in clips:
+                w = pp.pad_or_trim(pp.normalize(w.reshape(1, -1)))
+                out.append(model(pp.extract_features(w).unsqueeze(0))[0])
+        out = torch.stack(out)
+        dt = time.perf_counter() - t0
+        return n, dt, float(out.sum()), "reference"
+    from oracle import reference_port as rp
     model = rp.PortResidual().eval()
     pp = rp.PortPreprocessor()
-    clips = synth.synth_batch(n, seed=seed, device="cpu")
     t0 = time.perf_counter()
     out = rp.run_clips(pp, model, clips)
     dt = time.perf_counter() - t0
-    return n, dt, float(out.sum())
+    return n, dt, float(out.sum()), "port"
 
 
 def cpu_throughput(clips_per_worker: int, workers: int, seed0: int = 0):
@@ -67,7 +84,7 @@ def cpu_throughput(clips_per_worker: int, workers: int, seed0: int = 0):
         res = pool.map(_cpu_worker, [(seed0 + i, clips_per_worker) for i in range(workers)])
         wall = time.perf_counter() - t0
     n = sum(r[0] for r in res)
-    return n / wall, n, wall, max(r[1] for r in res)
+    return n / wall, n, wall, max(r[1] for r in res), res[0][3]
 
 
 def host_cores() -> int:
@@ -85,7 +102,7 @@ def run_reference_arm(args):
     per_worker = 512
     vals = []
     for s in range(args.warmup + args.steps):
-        v, n, wall, _ = cpu_throughput(per_worker, cores, seed0=s * 100)
+        v, n, wall, _, kind = cpu_throughput(per_worker, cores, seed0=s * 100)
         if s >= args.warmup:
             vals.append((v, n, wall))
     n_tot = sum(v[1] for v in vals)
@@ -97,7 +114,7 @@ def run_reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(1, len(vals)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "e2e features + CoughDetectorResidual, per-clip loop, CPU", "batch": BATCH},
-        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -172,8 +189,8 @@ def run_gpu_arm(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:       # before CUDA is touched; bounded to ~10-20 s
         cores = min(host_cores(), 64)
-        v, n, wall, _ = cpu_throughput(768, cores)
-        cpu = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
+        v, n, wall, _, kind = cpu_throughput(768, cores)
+        cpu = {"value": v, "unit": "clips/s", "cores": cores, "kind": kind,
                "sample": f"{n} clips of the same synthetic workload, {cores} single-thread processes, {wall:.1f} s"}
 
     import torch

@@ -3,6 +3,7 @@ import numpy as np
 import torch
 
 from oracle import cough_oracle as co
+from oracle import ref_build
 from oracle import reference_port as rp
 from tests import golden_io as gio
 
@@ -47,6 +48,36 @@ def test_port_is_bit_identical_to_reference():
     pp = rp.PortPreprocessor()
     for x, f in zip(clips, feats):
         assert torch.equal(pp.process(x.reshape(1, -1))[0], f)
+
+
+def test_built_reference_reproduces_goldens_and_port():
+    """oracle/_ref (the unmodified reference's bytecode, oracle/ref_build.py) must give the committed goldens bit for bit,
+    the port must equal it on fresh seeded clips, and both models must agree from one state dict.  Skipped only where
+    oracle/_ref has not been built (no /root/reference and no prebuilt files)."""
+    import pytest
+    from cough_detector_b200 import synth
+    ref = ref_build.load()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    pp = ref["preprocessing"].AudioPreprocessor(use_pcen=False, use_pre_emphasis=False, use_delta_delta=False,
+                                                use_spectral_contrast=False)
+    clips, feats, _ = gio.load_features()
+    for x, f in zip(clips[:8], feats[:8]):
+        assert torch.equal(pp.process(x.reshape(1, -1), 16000)[0], f)
+    port = rp.PortPreprocessor()
+    fresh = synth.synth_batch(6, seed=4242, device="cpu")
+    got = []
+    for w in fresh:
+        w = pp.pad_or_trim(pp.normalize(w.reshape(1, -1)))          # BASELINE.md §5's per-clip sequence
+        got.append(pp.extract_features(w))
+        assert torch.equal(got[-1], port.process(w))
+    torch.manual_seed(0)
+    m_ref = ref["model"].create_model("residual", n_mels=90, num_classes=2, in_channels=1).eval()
+    m_port = rp.PortResidual().eval()
+    m_port.load_state_dict(m_ref.state_dict())
+    with torch.no_grad():
+        x = torch.stack(got)
+        assert torch.equal(m_ref(x), m_port(x))
 
 
 def test_cnn_forward_matches_reference_logits():
