@@ -74,17 +74,30 @@ def _cpu_worker(args):
     return n, dt, float(out.sum()), "port"
 
 
-def cpu_throughput(clips_per_worker: int, workers: int, seed0: int = 0):
-    """clips/s of the port with `workers` single-threaded processes (intra-op threads hurt the per-clip path)."""
-    import multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(workers) as pool:
-        pool.map(_cpu_worker, [(seed0 + 1000 + i, 2) for i in range(workers)])       # import + warm-up, untimed
+def cpu_throughput(clips_per_worker: int, workers: int, seed0: int = 0, pool=None):
+    """clips/s of the CPU arm with `workers` single-threaded processes (intra-op threads hurt the per-clip path).
+    `pool`: an already warmed-up pool to reuse (the reference arm keeps one across its steps)."""
+    own = pool is None
+    if own:
+        pool = cpu_pool(workers)
+    try:
         t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, [(seed0 + i, clips_per_worker) for i in range(workers)])
+        res = pool.map(_cpu_worker, [(seed0 + i, clips_per_worker) for i in range(workers)], chunksize=1)
         wall = time.perf_counter() - t0
+    finally:
+        if own:
+            pool.terminate()
+            pool.join()
     n = sum(r[0] for r in res)
     return n / wall, n, wall, max(r[1] for r in res), res[0][3]
+
+
+def cpu_pool(workers: int):
+    """`workers` spawned processes, each past its imports and a two-clip warm-up (untimed)."""
+    import multiprocessing as mp
+    pool = mp.get_context("spawn").Pool(workers)
+    pool.map(_cpu_worker, [(1000 + i, 2) for i in range(workers)], chunksize=1)
+    return pool
 
 
 def host_cores() -> int:
@@ -101,10 +114,15 @@ def run_reference_arm(args):
     cores = min(host_cores(), 64)
     per_worker = 512
     vals = []
-    for s in range(args.warmup + args.steps):
-        v, n, wall, _, kind = cpu_throughput(per_worker, cores, seed0=s * 100)
-        if s >= args.warmup:
-            vals.append((v, n, wall))
+    pool = cpu_pool(cores)
+    try:
+        for s in range(args.warmup + args.steps):
+            v, n, wall, _, kind = cpu_throughput(per_worker, cores, seed0=s * 100, pool=pool)
+            if s >= args.warmup:
+                vals.append((v, n, wall))
+    finally:
+        pool.terminate()
+        pool.join()
     n_tot = sum(v[1] for v in vals)
     t_tot = sum(v[2] for v in vals)
     value = n_tot / t_tot
