@@ -66,6 +66,8 @@ def _cpu_worker(args):
         dt = time.perf_counter() - t0
         return n, dt, float(out.sum()), "reference"
     from oracle import reference_port as rp
+    if n == 2 and seed == 1000:
+        print(f"bench.py: CPU arm falls back to the port ({ref_build.last_error})", file=sys.stderr, flush=True)
     model = rp.PortResidual().eval()
     pp = rp.PortPreprocessor()
     t0 = time.perf_counter()

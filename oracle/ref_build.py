@@ -6,7 +6,7 @@ container, so the reference cannot be imported on the GPU box.  What can travel 
 artefact, exactly like a compiled C reference would: ``build()`` runs CPython's own compiler
 over ``/root/reference/src/preprocessing.py`` and ``src/model.py`` (the two files on the path,
 SURVEY.md §8a; neither imports anything else from the reference) and writes sourceless
-bytecode to ``oracle/_ref/*.pyc``.  No reference source text is copied; ``oracle/_ref/`` is
+bytecode to ``oracle/_ref/*.bytecode`` (``.pyc`` content).  No reference source text is copied; ``oracle/_ref/`` is
 git-ignored and not gpurun-ignored, so the bytecode travels with the snapshot to a box that
 runs this same interpreter.
 
@@ -29,7 +29,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = "/root/reference/src"
 OUT = os.path.join(HERE, "_ref")
 FILES = ("preprocessing", "model")          # src/preprocessing.py, src/model.py
+EXT = ".bytecode"                           # CPython .pyc content; not named *.pyc so no sync tool filters it out
 _cache: Optional[Dict[str, ModuleType]] = None
+last_error = ""                             # why load() returned None (bench.py prints it on stderr)
 
 
 def build(verbose: bool = True) -> bool:
@@ -39,7 +41,7 @@ def build(verbose: bool = True) -> bool:
         return False
     os.makedirs(OUT, exist_ok=True)
     for f in FILES:
-        py_compile.compile(os.path.join(REF_SRC, f + ".py"), cfile=os.path.join(OUT, f + ".pyc"),
+        py_compile.compile(os.path.join(REF_SRC, f + ".py"), cfile=os.path.join(OUT, f + EXT),
                            dfile=f"<reference>/src/{f}.py", doraise=True,
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
     with open(os.path.join(OUT, "BUILT_WITH"), "w") as fh:
@@ -50,7 +52,7 @@ def build(verbose: bool = True) -> bool:
 
 
 def _load_one(name: str) -> ModuleType:
-    path = os.path.join(OUT, name + ".pyc")
+    path = os.path.join(OUT, name + EXT)
     loader = importlib.machinery.SourcelessFileLoader("cough_reference_" + name, path)
     spec = importlib.util.spec_from_loader(loader.name, loader)
     mod = importlib.util.module_from_spec(spec)
@@ -60,16 +62,18 @@ def _load_one(name: str) -> ModuleType:
 
 def load() -> Optional[Dict[str, ModuleType]]:
     """{'preprocessing': module, 'model': module} of the unmodified reference, or None."""
-    global _cache
+    global _cache, last_error
     if _cache is not None:
         return _cache
     try:
         with open(os.path.join(OUT, "BUILT_WITH")) as fh:
             magic = fh.read().split()[1]
         if magic != importlib.util.MAGIC_NUMBER.hex():
+            last_error = f"oracle/_ref was built by another interpreter (magic {magic})"
             return None
         _cache = {f: _load_one(f) for f in FILES}
-    except (OSError, IndexError, ImportError):
+    except (OSError, IndexError, ImportError) as e:
+        last_error = f"{type(e).__name__}: {e}"
         return None
     return _cache
 
