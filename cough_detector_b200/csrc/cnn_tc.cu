@@ -142,9 +142,10 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(s32(bar) & 0xFEFFFFFFu) : "memory");
 }
 
-// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane = tile row)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane = tile row).  The _issue form does
+// not wait: several loads can be in flight under ONE tmem_ld_wait (an epilogue that waits after every load pays the full
+// TMEM latency once per 32 columns).
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -154,7 +155,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    tmem_ld32_issue(taddr, r);
+    tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
@@ -514,8 +520,14 @@ conv3x3_s1_tc_kernel(const S1Args a) {
             tc::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * 64;
             float v0[32], v1[32];
-            tc::tmem_ld32(taddr, v0);
-            tc::tmem_ld32(taddr + 32, v1);
+            {
+                uint32_t r0[32], r1[32];
+                tc::tmem_ld32_issue(taddr, r0);
+                tc::tmem_ld32_issue(taddr + 32, r1);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { v0[i] = __uint_as_float(r0[i]); v1[i] = __uint_as_float(r1[i]); }
+            }
             tc::tc_fence_before();
             tc::mbar_arrive(&tempty_bar[acc]);
             if (live) {
@@ -966,7 +978,8 @@ __global__ void __launch_bounds__(kS1Threads, 1)
 stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __restrict__ wq,
                const float* __restrict__ bias, __nv_bfloat16* __restrict__ x0, int64_t x0_plane_elems,
                __nv_bfloat16* __restrict__ xs0, int B, int rev) {
-    const bool REV_ORDER = rev != 0;
+    const bool REV_ORDER = (rev & 1) != 0;
+    const bool FULL_N = (rev & 2) != 0;                         // A/B switch: every tap at N = 128 (CD_STEM_PRUNE=0)
     using NS = NetShape<NF>;
     constexpr int kRows = NS::BROWS;                            // GEMM rows per clip
     extern __shared__ unsigned char raw[];
@@ -976,7 +989,7 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
     float* s_bias = reinterpret_cast<float*>(sB + kStemBBytes);
     __shared__ uint64_t full_bar[kStemStages], empty_bar[kStemStages], tfull_bar[2], tempty_bar[2], w_bar;
     __shared__ uint32_t tmem_base_s;
-    constexpr uint32_t IDESC = tc::idesc_bf16(128, 128);
+    constexpr uint32_t IDESC = tc::idesc_bf16(128, 128), IDESC64 = tc::idesc_bf16(128, 64), IDESC32 = tc::idesc_bf16(128, 32);
     constexpr int TMEM_COLS = 256;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1031,10 +1044,25 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
                 tc::tc_fence_after();
                 const uint32_t d = tmem_base + acc * 128;
                 const uint64_t da = tc::desc_sw32(tc::s32(sA + s * kStemABytes));
+                // Blocks i = 2 / j = 2 hold only patch row 8 / column 8, which only the pool members with dy = 1 / dx = 1
+                // read: their other weight rows are zero.  The members sit in the order (0,0) (0,1) (1,1) (1,0), so those
+                // taps run at N = 64 over accumulator columns [64, 128) / [32, 96) and the corner block at N = 32 over
+                // [64, 96): 1 952 instead of 2 304 operand rows fetched per tile, same sums (the skipped terms are + 0).
+                if (FULL_N) {
 #pragma unroll
-                for (int q = 0; q < 9; ++q)                      // block (i, j) = (q / 3, q % 3); K step q of the weights
-                    tc::umma_bf16(d, tc::desc_adv(da, ((q / 3) * kBmapB + (q % 3)) * 32),
-                                  tc::desc_adv(db, (q >> 2) * 16384 + (q & 3) * 32), IDESC, q != 0);
+                    for (int q = 0; q < 9; ++q)                  // block (i, j) = (q / 3, q % 3); K step q of the weights
+                        tc::umma_bf16(d, tc::desc_adv(da, ((q / 3) * kBmapB + (q % 3)) * 32),
+                                      tc::desc_adv(db, (q >> 2) * 16384 + (q & 3) * 32), IDESC, q != 0);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) {
+                        const int bi = q / 3, bj = q % 3;
+                        const int n0 = (bi == 2) ? 64 : (bj == 2 ? 32 : 0);        // first weight row / accumulator column
+                        const uint32_t idesc = (bi == 2 && bj == 2) ? IDESC32 : ((bi == 2 || bj == 2) ? IDESC64 : IDESC);
+                        tc::umma_bf16(d + n0, tc::desc_adv(da, (bi * kBmapB + bj) * 32),
+                                      tc::desc_adv(db, (q >> 2) * 16384 + (q & 3) * 32 + n0 * 128), idesc, q != 0);
+                    }
+                }
                 tc::tc_commit(&empty_bar[s]);
                 tc::tc_commit(&tfull_bar[acc]);
             }
@@ -1056,13 +1084,18 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
             tc::mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
             tc::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * 128;
-            float m[32], v[32];
-            tc::tmem_ld32(taddr, m);
+            float m[32];
+            {   // the four pool members' columns: four loads in flight under one wait, then one 4-way max per channel
+                uint32_t r0[32], r1[32], r2[32], r3[32];
+                tc::tmem_ld32_issue(taddr, r0);
+                tc::tmem_ld32_issue(taddr + 32, r1);
+                tc::tmem_ld32_issue(taddr + 64, r2);
+                tc::tmem_ld32_issue(taddr + 96, r3);
+                tc::tmem_ld_wait();
 #pragma unroll
-            for (int g = 1; g < 4; ++g) {
-                tc::tmem_ld32(taddr + g * 32, v);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) m[i] = fmaxf(m[i], v[i]);
+                for (int i = 0; i < 32; ++i)
+                    m[i] = fmaxf(fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])),
+                                 fmaxf(__uint_as_float(r2[i]), __uint_as_float(r3[i])));
             }
             tc::tc_fence_before();
             tc::mbar_arrive(&tempty_bar[acc]);
@@ -1197,7 +1230,8 @@ int upload_cnn_tc(cd_handle* h, const std::vector<std::vector<float>>& wf, const
         total_bf += (packs[i].size() + 63) & ~size_t(63);
     }
     {   // stem as a pooled GEMM over 3x3 blocks of 4x4 pixels: patch pixel (ry, rx) = (2dy + ky, 2dx + kx) lives in
-        // block (ry / 4, rx / 4) at k16 = 4 (ry % 4) + rx % 4:  W2[k][n = (dy*2+dx)*32 + co] = w[co][ky][kx]
+        // block (ry / 4, rx / 4) at k16 = 4 (ry % 4) + rx % 4:  W2[k][n = member(dy,dx)*32 + co] = w[co][ky][kx], members in the
+        // order (0,0) (0,1) (1,1) (1,0) so that "dy = 1" and "dx = 1" are each a contiguous range of weight rows (stem kernel)
         std::vector<float> w2((size_t)192 * 128, 0.f);
         for (int dy = 0; dy < 2; ++dy)
             for (int dx = 0; dx < 2; ++dx)
@@ -1206,7 +1240,8 @@ int upload_cnn_tc(cd_handle* h, const std::vector<std::vector<float>>& wf, const
                         for (int co = 0; co < 32; ++co) {
                             const int ry = 2 * dy + ky, rx = 2 * dx + kx;
                             const int k = ((ry >> 2) * 3 + (rx >> 2)) * 16 + (ry & 3) * 4 + (rx & 3);
-                            w2[(size_t)k * 128 + (dy * 2 + dx) * 32 + co] = wf[0][(size_t)(ky * 7 + kx) * 32 + co];
+                            const int member = dy ? 3 - dx : dx;
+                            w2[(size_t)k * 128 + member * 32 + co] = wf[0][(size_t)(ky * 7 + kx) * 32 + co];
                         }
         pack_weights(w2, 192, 1, 128, packs[6]);
         total_bf += (packs[6].size() + 63) & ~size_t(63);
@@ -1351,6 +1386,8 @@ static int launch_cnn_tc_nf(cd_handle* h, const float* d_feat, int64_t B, float*
     // b1 conv1: forward;  b1 conv2: backward.  CD_TC_ORDER=0 walks every kernel forward (the A/B switch of tools/slab_sweep.py).
     const char* order_env = getenv("CD_TC_ORDER");
     const int alt = (order_env && order_env[0] == '0') ? 0 : 1;
+    const char* prune_env = getenv("CD_STEM_PRUNE");            // CD_STEM_PRUNE=0: every stem tap at N = 128 (A/B switch)
+    const int stem_full = (prune_env && prune_env[0] == '0') ? 2 : 0;
     for (int64_t c0 = 0; c0 < B; c0 += kTcChunk) {
         const int n = (int)((B - c0) < kTcChunk ? (B - c0) : kTcChunk);
         if (d_feat) {
@@ -1361,7 +1398,7 @@ static int launch_cnn_tc_nf(cd_handle* h, const float* d_feat, int64_t B, float*
             const int tiles = (int)(((int64_t)n * N::BROWS + 127) / 128);
             CD_CUDA(h, launch_pdl(stem_tc_kernel<NF>, dim3(tiles < h->sm_count ? tiles : h->sm_count), dim3(kS1Threads), kStemSmem, s,
                                   (const __nv_bfloat16*)maps, (const __nv_bfloat16*)W.stem_w, (const float*)W.stem_b, x0,
-                                  (int64_t)(P::kP20Rows * 64), h1 + kPl0, n, alt));
+                                  (int64_t)(P::kP20Rows * 64), h1 + kPl0, n, alt | stem_full));
         }
         h->launches += 1;
         {
