@@ -51,7 +51,8 @@ def main():
                 w.writerow([r[i] for i in keep_b])
     tool = os.path.join(ROOT, "tools", "ncu_summary.py")
     subprocess.run([sys.executable, tool, os.path.join(SRC, "prof_full.ncu-rep"), os.path.join(DST, f"{R}_ncu_full_summary.csv")], check=True)
-    subprocess.run([sys.executable, tool, os.path.join(SRC, "prof_feat.ncu-rep"), os.path.join(DST, f"{R}_ncu_feat_kernel_65536.csv"), "feat_kernel"], check=True)
+    if os.path.exists(os.path.join(SRC, "prof_feat.ncu-rep")):       # absent after tools/run_profiles_short.sh
+        subprocess.run([sys.executable, tool, os.path.join(SRC, "prof_feat.ncu-rep"), os.path.join(DST, f"{R}_ncu_feat_kernel_65536.csv"), "feat_kernel"], check=True)
     # per-clip shares from the launch list (second pass = launches 7..13)
     dur = {}
     for r in rows[1:]:
