@@ -972,9 +972,13 @@ constexpr int kStemABytes = ((kStemRowsIn * 32 + 255) / 256) * 256;   // 5888 ->
 constexpr int kStemStages = 4;
 constexpr int kStemBBytes = 3 * 16384;            // 128 weight rows x 3 chunks of 64 K-elements (144 used)
 constexpr size_t kStemSmem = 1024 + kStemStages * kStemABytes + kStemBBytes + 128;
+// warp 0: producer, warp 1: MMA, warps 2-5: epilogue of the even tiles (accumulator 0), warps 6-9: of the odd tiles (accumulator 1).
+// One epilogue warp per scheduler spends ~ 760 of a tile's ~ 1 150 cycles in its own dependent instruction stream (ncu stall
+// samples, profiles/r2_stem_prune_ab.txt) -- as long as the nine MMAs take; two sets take it off the critical path.
+constexpr int kStemThreads = 320;
 
 template <int NF>
-__global__ void __launch_bounds__(kS1Threads, 1)
+__global__ void __launch_bounds__(kStemThreads, 1)
 stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __restrict__ wq,
                const float* __restrict__ bias, __nv_bfloat16* __restrict__ x0, int64_t x0_plane_elems,
                __nv_bfloat16* __restrict__ xs0, int B, int rev) {
@@ -1069,16 +1073,15 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
         }
     } else {
         // ======================= epilogue: pool max over the 4 column groups, bias, ReLU, bf16 ========
-        const int lane_grp = warp & 3;
-        float bq[32];                                           // folded bias, resident in registers
-#pragma unroll
-        for (int i = 0; i < 32; ++i) bq[i] = __ldg(bias + i);
+        const int lane_grp = warp & 3;                          // TMEM lane quadrant a warp may read = warp % 4
+        const int eset = (warp - 2) >> 2;                       // 0: even tiles / accumulator 0, 1: odd tiles / accumulator 1
         int it = 0;
         for (int t_ = blockIdx.x; t_ < n_tiles; t_ += gridDim.x, ++it) {
-                [[maybe_unused]] const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
-            const int acc = it & 1;
-            const int64_t mp = (int64_t)tile * 128 + lane_grp * 32 + lane;
-            const int clip = (int)(mp / kRows), rem = (int)(mp - (int64_t)clip * kRows);
+            if ((it & 1) != eset) continue;
+            [[maybe_unused]] const int tile = REV_ORDER ? n_tiles - 1 - t_ : t_;
+            const int acc = eset;
+            const int mp = tile * 128 + lane_grp * 32 + lane;   // a launch covers <= kTcChunk clips: rows < 2^31
+            const int clip = mp / kRows, rem = mp - clip * kRows;
             const int py = rem / kBmapB, px = rem - py * kBmapB;
             const bool live = clip < B && py < NS::H0 && px < NS::W0;
             tc::mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
@@ -1115,9 +1118,12 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
                 for (int q = 0; q < 4; ++q) {
                     uint32_t w[4];
 #pragma unroll
+                    const float4 b0 = *reinterpret_cast<const float4*>(s_bias + 8 * q), b1 = *reinterpret_cast<const float4*>(s_bias + 8 * q + 4);
+                    const float bq[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};     // folded bias (broadcast reads)
+#pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int c = 8 * q + 2 * e;
-                        __nv_bfloat162 pk = __floats2bfloat162_rn(fmaxf(m[c] + bq[c], 0.f), fmaxf(m[c + 1] + bq[c + 1], 0.f));
+                        __nv_bfloat162 pk = __floats2bfloat162_rn(fmaxf(m[c] + bq[2 * e], 0.f), fmaxf(m[c + 1] + bq[2 * e + 1], 0.f));
                         w[e] = *reinterpret_cast<uint32_t*>(&pk);
                     }
                     *reinterpret_cast<uint4*>(op + (((jb + q) ^ (int)(r2 & 7)) << 3)) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -1396,7 +1402,7 @@ static int launch_cnn_tc_nf(cd_handle* h, const float* d_feat, int64_t B, float*
         }
         {
             const int tiles = (int)(((int64_t)n * N::BROWS + 127) / 128);
-            CD_CUDA(h, launch_pdl(stem_tc_kernel<NF>, dim3(tiles < h->sm_count ? tiles : h->sm_count), dim3(kS1Threads), kStemSmem, s,
+            CD_CUDA(h, launch_pdl(stem_tc_kernel<NF>, dim3(tiles < h->sm_count ? tiles : h->sm_count), dim3(kStemThreads), kStemSmem, s,
                                   (const __nv_bfloat16*)maps, (const __nv_bfloat16*)W.stem_w, (const float*)W.stem_b, x0,
                                   (int64_t)(P::kP20Rows * 64), h1 + kPl0, n, alt | stem_full));
         }
