@@ -33,6 +33,14 @@ exp: $(OBJS)
 ablations:
 	$(MAKE) exp EXP="ab1:-DCD_ABLATE=1 ab2:-DCD_ABLATE=2 ab3:-DCD_ABLATE=3 ab4:-DCD_ABLATE=4"
 
+# EXPERIMENTAL, never run on a GPU (see CD_MMA_ELECT in cnn_tc.cu, profiles/r2_mma_issue_bound.txt): the single-CTA conv kernels with a
+# convergent MMA warp and elect.sync-predicated tcgen05 instructions -> lib/exp/libelect.so.  First thing to do with a GPU:
+#   make elect && CD_LIB=cough_detector_b200/lib/exp/libelect.so python -m pytest tests -m gpu -x -q   (tests/conftest.py honours CD_LIB)
+elect: $(OBJS)
+	@mkdir -p build/exp $(OUT_DIR)/exp
+	$(NVCC) $(NVCCFLAGS) -DCD_MMA_ELECT=1 -c $(SRC_DIR)/cnn_tc.cu -o build/exp/cnn_tc_elect.o 2> build/exp/cnn_tc_elect.ptxas.log || (cat build/exp/cnn_tc_elect.ptxas.log; false)
+	$(NVCC) -shared $(ARCH) -o $(OUT_DIR)/exp/libelect.so build/api.o build/feat_kernel.o build/cnn_fp32.o build/exp/cnn_tc_elect.o build/cnn_plain.o build/resample.o build/spec_augment.o
+
 # C++ callers of the C ABI (no Python, no torch)
 examples: $(LIB)
 	$(NVCC) -O2 -std=c++17 $(ARCH) -Iinclude examples/e2e_minimal.cu -o build/e2e_minimal -L$(OUT_DIR) -lcough_b200 -Xlinker -rpath,'$$ORIGIN/../$(OUT_DIR)'
@@ -40,4 +48,4 @@ examples: $(LIB)
 clean:
 	rm -rf build $(LIB)
 
-.PHONY: all clean exp examples ablations
+.PHONY: all clean exp examples ablations elect

@@ -92,6 +92,37 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// EXPERIMENTAL issue form, OFF by default and not in the shipped library (`make elect`; never run on a GPU -- round 2 found the
+// issue-bound profile after its GPU budget was spent, profiles/r2_mma_issue_bound.txt).  With CD_MMA_ELECT=1 the MMA warp of the
+// single-CTA kernels stays CONVERGENT: all 32 lanes run the tile loop and the barrier waits, and only the tcgen05 instruction
+// itself is predicated on the lane elect.sync picks (the CuTe pattern), so the compiler emits straight-line `@UP UTCHMMA` instead
+// of wrapping every MMA issued from `if (lane == 0)` in an R2UR / ELECT / BRA.U.ANY retry loop.
+#ifndef CD_MMA_ELECT
+#define CD_MMA_ELECT 0
+#endif
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(s32(bar)) : "memory");
+}
+#if CD_MMA_ELECT
+#define CD_MMA_ISSUER(lane) true
+#define CD_UMMA tc::umma_bf16_elect
+#define CD_COMMIT tc::tc_commit_elect
+#else
+#define CD_MMA_ISSUER(lane) ((lane) == 0)
+#define CD_UMMA tc::umma_bf16
+#define CD_COMMIT tc::tc_commit
+#endif
 // ---- CTA-pair (cta_group::2) variants: one MMA spans two SMs (M = 256: 128 rows from each CTA's shared memory,
 // each CTA supplies half of the N rows of B), issued by the even ("leader") CTA of a 2-CTA cluster.
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -463,7 +494,7 @@ conv3x3_s1_tc_kernel(const S1Args a) {
         }
     } else if (warp == 1) {
         // ======================= MMA issuer: per plane 9 taps x 4 K-steps, skip plane 1 tap ===========
-        if (lane == 0) {
+        if (CD_MMA_ISSUER(lane)) {
             tc::mbar_wait(&w_bar, 0);
             int it = 0;
             for (int t_ = cta; t_ < n_tiles; t_ += n_cta, ++it) {
@@ -485,7 +516,7 @@ conv3x3_s1_tc_kernel(const S1Args a) {
                             const uint32_t shift = (uint32_t)((tap / 3) * PS::WP + (tap % 3)) * 128;   // rows down the image
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4)
-                                tc::umma_bf16(d, tc::desc_adv(da, shift + k4 * 32),
+                                CD_UMMA(d, tc::desc_adv(da, shift + k4 * 32),
                                               tc::desc_adv(dw, (tap * S::NPL + q) * 8192 + k4 * 32), IDESC,
                                               (q | tap | k4) != 0);
                         }
@@ -496,12 +527,12 @@ conv3x3_s1_tc_kernel(const S1Args a) {
                         constexpr int kSkipSteps = C == 64 ? 2 : 4;
 #pragma unroll
                         for (int k4 = 0; k4 < kSkipSteps; ++k4)
-                            tc::umma_bf16(d, tc::desc_adv(da, shift + k4 * 32),
+                            CD_UMMA(d, tc::desc_adv(da, shift + k4 * 32),
                                           tc::desc_adv(dw, 9 * S::NPL * 8192 + k4 * 32), IDESC, 1u);
                     }
-                    tc::tc_commit(&empty_bar[bi]);        // this plane's slot can be refilled for the next tile
+                    CD_COMMIT(&empty_bar[bi]);        // this plane's slot can be refilled for the next tile
                 }
-                tc::tc_commit(&tfull_bar[acc]);
+                CD_COMMIT(&tfull_bar[acc]);
             }
         }
     } else {
@@ -865,7 +896,7 @@ conv3x3_s2_tc_kernel(const S2Args a) {
         }
     } else if (warp == 1) {
         // ======================= MMA issuer: taps grouped by the plane (phase) they read =============
-        if (lane == 0) {
+        if (CD_MMA_ISSUER(lane)) {
             tc::mbar_wait(&w_bar, 0);
             int it = 0;
             for (int t_ = blockIdx.x; t_ < n_tiles; t_ += gridDim.x, ++it) {
@@ -891,22 +922,22 @@ conv3x3_s2_tc_kernel(const S2Args a) {
                         if (CIN == 32) {      // 32 channels = 2 K-steps in the (kx & 1) half of the row
 #pragma unroll
                             for (int hk = 0; hk < 2; ++hk) {
-                                tc::umma_bf16(d, tc::desc_adv(da, shift + (kx & 1) * 64 + hk * 32),
+                                CD_UMMA(d, tc::desc_adv(da, shift + (kx & 1) * 64 + hk * 32),
                                               tc::desc_adv(dw, (tap >> 1) * COUT * 128 + ((tap & 1) * 2 + hk) * 32), IDESC, accum);
                                 accum = 1;
                             }
                         } else {
 #pragma unroll
                             for (int hk = 0; hk < 4; ++hk) {
-                                tc::umma_bf16(d, tc::desc_adv(da, shift + hk * 32), tc::desc_adv(dw, tap * COUT * 128 + hk * 32),
+                                CD_UMMA(d, tc::desc_adv(da, shift + hk * 32), tc::desc_adv(dw, tap * COUT * 128 + hk * 32),
                                               IDESC, accum);
                                 accum = 1;
                             }
                         }
                     }
-                    tc::tc_commit(&empty_bar[bi]);
+                    CD_COMMIT(&empty_bar[bi]);
                 }
-                tc::tc_commit(&tfull_bar[acc]);
+                CD_COMMIT(&tfull_bar[acc]);
             }
         }
     } else {
@@ -1036,7 +1067,7 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
         }
     } else if (warp == 1) {
         // ======================= MMA issuer: nine 4x4-block taps as shifted SWIZZLE_32B views =========
-        if (lane == 0) {
+        if (CD_MMA_ISSUER(lane)) {
             tc::mbar_wait(&w_bar, 0);
             const uint64_t db = tc::desc_sw128(tc::s32(sB));
             int it = 0;
@@ -1055,7 +1086,7 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
                 if (FULL_N) {
 #pragma unroll
                     for (int q = 0; q < 9; ++q)                  // block (i, j) = (q / 3, q % 3); K step q of the weights
-                        tc::umma_bf16(d, tc::desc_adv(da, ((q / 3) * kBmapB + (q % 3)) * 32),
+                        CD_UMMA(d, tc::desc_adv(da, ((q / 3) * kBmapB + (q % 3)) * 32),
                                       tc::desc_adv(db, (q >> 2) * 16384 + (q & 3) * 32), IDESC, q != 0);
                 } else {
 #pragma unroll
@@ -1063,12 +1094,12 @@ stem_tc_kernel(const __nv_bfloat16* __restrict__ maps, const __nv_bfloat16* __re
                         const int bi = q / 3, bj = q % 3;
                         const int n0 = (bi == 2) ? 64 : (bj == 2 ? 32 : 0);        // first weight row / accumulator column
                         const uint32_t idesc = (bi == 2 && bj == 2) ? IDESC32 : ((bi == 2 || bj == 2) ? IDESC64 : IDESC);
-                        tc::umma_bf16(d + n0, tc::desc_adv(da, (bi * kBmapB + bj) * 32),
+                        CD_UMMA(d + n0, tc::desc_adv(da, (bi * kBmapB + bj) * 32),
                                       tc::desc_adv(db, (q >> 2) * 16384 + (q & 3) * 32 + n0 * 128), idesc, q != 0);
                     }
                 }
-                tc::tc_commit(&empty_bar[s]);
-                tc::tc_commit(&tfull_bar[acc]);
+                CD_COMMIT(&empty_bar[s]);
+                CD_COMMIT(&tfull_bar[acc]);
             }
         }
     } else {

@@ -10,6 +10,9 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    if os.environ.get("CD_LIB"):          # run the suite against an experimental build (Makefile: exp / elect), like the tools do
+        from cough_detector_b200 import _lib
+        _lib.LIB_PATH = os.path.abspath(os.environ["CD_LIB"])
 
 
 def pytest_collection_modifyitems(config, items):
