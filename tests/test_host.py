@@ -150,3 +150,29 @@ def test_cpp_example_builds_against_the_c_abi():
     r = subprocess.run(["make", "-C", root, "examples"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert os.path.exists(os.path.join(root, "build", "e2e_minimal"))
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` needs no GPU: one JSON line with the metric keys of the b200 arm, `impl`, a `cpu_baseline`
+    describing this run and an `e2e` that repeats the value with zero copies (the driver computes the ratio from it)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "clips/s" and line["higher_is_better"] is True
+    assert line["metric"] == "1-s clips/sec (mel+MFCC+CNN)" and line["value"] > 0 and line["gpu_launches"] == 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # a rank other than 0 of a torchrun launch exits 0 without work or output
+    env["RANK"], env["WORLD_SIZE"] = "1", "2"
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=120, env=env, cwd=root)
+    assert out.returncode == 0 and out.stdout.strip() == "", (out.stdout, out.stderr[-500:])
